@@ -1,0 +1,369 @@
+"""Synthetic scene descriptions for the configs of BASELINE.json.
+
+This is the USD-free stand-in for what `hdGatling` hands to the `gi` API: meshes arrive already
+triangulated and de-indexed the way /root/reference/src/hdGatling/mesh.cpp:837-1138 does it
+(fan triangulation, faceVarying normals force de-indexing, Duff-basis fallback tangents when no
+texcoords are authored, mesh.cpp:236-268), cameras like renderPass.cpp:191-228, render settings
+with the defaults of renderDelegate.cpp:93-110.
+
+Everything is plain numpy; both the product binding (gatling_b200.gi) and the test oracle consume
+the same `SceneDesc`.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import List, Optional
+
+import numpy as np
+
+# ---- closure ids / parameter slots (include/gtlc.h) -------------------------------------------
+CLOSURE_DIFFUSE = 0
+CLOSURE_USD_PREVIEW_SURFACE = 1
+CLOSURE_OPENPBR = 2
+MATERIAL_PARAM_COUNT = 48
+
+UPS = dict(diffuse=0, emissive=3, useSpecularWorkflow=6, specular=7, metallic=10, roughness=11,
+           clearcoat=12, clearcoatRoughness=13, opacity=14, ior=15)
+OPBR = dict(base_weight=0, base_color=1, base_diffuse_roughness=4, base_metalness=5, specular_weight=6,
+            specular_color=7, specular_roughness=10, specular_ior=11, specular_roughness_anisotropy=12,
+            transmission_weight=13, transmission_color=14, transmission_depth=17, coat_weight=18,
+            coat_color=19, coat_roughness=22, coat_ior=23, coat_darkening=24, fuzz_weight=25,
+            fuzz_color=26, fuzz_roughness=29, emission_luminance=30, emission_color=31,
+            thin_film_weight=34, thin_film_thickness=35, thin_film_ior=36, geometry_opacity=37,
+            geometry_thin_walled=38, subsurface_weight=39, subsurface_color=40)
+
+VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("u", "<f4"), ("norm", "<f4", 3), ("v", "<f4"),
+                         ("tangent", "<f4", 3), ("bitangentSign", "<f4")])  # GiVertex, Gi.h:109-117
+assert VERTEX_DTYPE.itemsize == 48
+
+
+@dataclasses.dataclass
+class Material:
+    closure: int
+    params: np.ndarray  # float32[48]
+    name: str = ""
+
+
+def material_diffuse(tint, name="") -> Material:
+    p = np.zeros(MATERIAL_PARAM_COUNT, np.float32)
+    p[0:3] = tint
+    return Material(CLOSURE_DIFFUSE, p, name)
+
+
+def material_usd_preview_surface(name="", **kw) -> Material:
+    """UsdPreviewSurface with spec defaults (diffuse .18, roughness .5, ior 1.5, ...)."""
+    p = np.zeros(MATERIAL_PARAM_COUNT, np.float32)
+    p[UPS["diffuse"]:UPS["diffuse"] + 3] = 0.18
+    p[UPS["roughness"]] = 0.5
+    p[UPS["clearcoatRoughness"]] = 0.01
+    p[UPS["opacity"]] = 1.0
+    p[UPS["ior"]] = 1.5
+    for k, v in kw.items():
+        i = UPS[k]
+        if np.ndim(v) == 0:
+            p[i] = v
+        else:
+            p[i:i + 3] = v
+    return Material(CLOSURE_USD_PREVIEW_SURFACE, p, name)
+
+
+def material_openpbr(name="", **kw) -> Material:
+    """open_pbr_surface with the defaults of src/gi/mtlx/open_pbr_surface.mtlx:11-84."""
+    p = np.zeros(MATERIAL_PARAM_COUNT, np.float32)
+    d = dict(base_weight=1.0, base_color=(0.8, 0.8, 0.8), specular_weight=1.0, specular_color=(1, 1, 1),
+             specular_roughness=0.3, specular_ior=1.5, transmission_color=(1, 1, 1), coat_color=(1, 1, 1),
+             coat_ior=1.6, coat_darkening=1.0, fuzz_color=(1, 1, 1), fuzz_roughness=0.5,
+             emission_color=(1, 1, 1), thin_film_thickness=0.5, thin_film_ior=1.4, geometry_opacity=1.0,
+             subsurface_color=(0.8, 0.8, 0.8))
+    d.update(kw)
+    for k, v in d.items():
+        i = OPBR[k]
+        if np.ndim(v) == 0:
+            p[i] = v
+        else:
+            p[i:i + 3] = v
+    return Material(CLOSURE_OPENPBR, p, name)
+
+
+@dataclasses.dataclass
+class Mesh:
+    vertices: np.ndarray            # VERTEX_DTYPE[n]
+    faces: np.ndarray               # uint32[m, 3]
+    material: int                   # index into SceneDesc.materials
+    transform: np.ndarray = dataclasses.field(default_factory=lambda: np.eye(4, dtype=np.float32))  # USD row-major, row-vector convention
+    instance_transforms: Optional[np.ndarray] = None   # float32[k, 4, 4]; None = one identity instance
+    double_sided: bool = True
+    left_handed: bool = False
+    object_id: int = 0
+    name: str = ""
+
+
+@dataclasses.dataclass
+class Camera:  # GiCameraDesc, Gi.h:95-107
+    position: tuple
+    forward: tuple
+    up: tuple
+    vfov: float
+    fStop: float = 0.0
+    focusDistance: float = 0.0
+    focalLength: float = 0.05
+    clipStart: float = 0.1
+    clipEnd: float = 100.0
+    exposure: float = 0.0
+
+
+@dataclasses.dataclass
+class RenderSettings:  # GiRenderSettings, Gi.h:139-159; defaults renderDelegate.cpp:93-110
+    clippingPlanes: bool = False
+    depthOfField: bool = False
+    domeLightCameraVisible: bool = True
+    filterImportanceSampling: bool = True
+    frame: float = 0.0
+    jitteredSampling: bool = True
+    lightIntensityMultiplier: float = 1.0
+    maxBounces: int = 13
+    maxSampleValue: float = 10.0
+    maxVolumeWalkLength: int = 7
+    mediumStackSize: int = 0
+    metersPerSceneUnit: float = 1.0
+    nextEventEstimation: bool = False
+    progressiveAccumulation: bool = True
+    rrBounceOffset: int = 3
+    rrInvMinTermProb: float = 0.95
+    spp: int = 1
+    time: float = 0.0
+
+
+@dataclasses.dataclass
+class SphereLight:
+    position: tuple
+    base_emission: tuple
+    radius: tuple = (0.5, 0.5, 0.5)
+    diffuse: float = 1.0
+    specular: float = 1.0
+
+
+@dataclasses.dataclass
+class DistantLight:
+    direction: tuple
+    base_emission: tuple
+    angle: float = 0.0
+    diffuse: float = 1.0
+    specular: float = 1.0
+
+
+@dataclasses.dataclass
+class RectLight:
+    origin: tuple
+    t0: tuple
+    t1: tuple
+    base_emission: tuple
+    width: float = 1.0
+    height: float = 1.0
+    diffuse: float = 1.0
+    specular: float = 1.0
+
+
+@dataclasses.dataclass
+class DiskLight:
+    origin: tuple
+    t0: tuple
+    t1: tuple
+    base_emission: tuple
+    radius: tuple = (0.5, 0.5)
+    diffuse: float = 1.0
+    specular: float = 1.0
+
+
+@dataclasses.dataclass
+class DomeLight:
+    texels: np.ndarray  # float32[h, w, 4] lat-long
+    rotation: tuple = (0.0, 0.0, 0.0, 1.0)
+    base_emission: tuple = (1.0, 1.0, 1.0)
+
+
+@dataclasses.dataclass
+class SceneDesc:
+    name: str
+    meshes: List[Mesh]
+    materials: List[Material]
+    camera: Camera
+    settings: RenderSettings
+    width: int
+    height: int
+    clear_color: tuple = (1.0, 1.0, 1.0, 1.0)   # renderDelegate.cpp:227-230 (test harness background)
+    sphere_lights: List[SphereLight] = dataclasses.field(default_factory=list)
+    distant_lights: List[DistantLight] = dataclasses.field(default_factory=list)
+    rect_lights: List[RectLight] = dataclasses.field(default_factory=list)
+    disk_lights: List[DiskLight] = dataclasses.field(default_factory=list)
+    dome_light: Optional[DomeLight] = None
+
+    @property
+    def triangle_count(self) -> int:
+        n = 0
+        for m in self.meshes:
+            k = 1 if m.instance_transforms is None else len(m.instance_transforms)
+            n += len(m.faces) * k
+        return n
+
+
+# ---- reproducible random stream: the reference's own hash_pcg32 (common.glsl:93-98) -------------
+def pcg32_stream(seed: int, count: int) -> np.ndarray:
+    """count outputs of hash_pcg32 applied to an LCG state starting at `seed` (vectorised)."""
+    a = np.uint32(747796405)
+    c = np.uint32(2891336453)
+    with np.errstate(over="ignore"):
+        pw = np.empty(count + 1, np.uint32)
+        pw[0] = 1
+        pw[1:] = a
+        pw = np.cumprod(pw, dtype=np.uint32)            # a^i mod 2^32
+        geo = np.cumsum(pw[:-1], dtype=np.uint32)       # sum_{k<i+1} a^k
+        state = pw[1:] * np.uint32(seed) + c * geo      # state after i+1 steps
+        word = ((state >> ((state >> np.uint32(28)) + np.uint32(4))) ^ state) * np.uint32(277803737)
+        return (word >> np.uint32(22)) ^ word
+
+
+def pcg32_uniform(seed: int, count: int) -> np.ndarray:
+    """floats in [0,1) via uintAsFloat (common.glsl:44-47)."""
+    w = pcg32_stream(seed, count)
+    return ((w >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1.0)
+
+
+# ---- vertex baking helpers (hdGatling/mesh.cpp conventions) ------------------------------------
+def duff_basis(n: np.ndarray):
+    """_DuffOrthonormalBasis, mesh.cpp:225-233 (float32 arithmetic)."""
+    n = n.astype(np.float32)
+    sign = np.where(n[:, 2] >= 0, np.float32(1), np.float32(-1))
+    a = np.float32(-1.0) / (sign + n[:, 2])
+    b = n[:, 0] * n[:, 1] * a
+    t = np.stack([np.float32(1) + sign * n[:, 0] * n[:, 0] * a, sign * b, -sign * n[:, 0]], 1)
+    bt = np.stack([b, sign + n[:, 1] * n[:, 1] * a, -n[:, 1]], 1)
+    return t.astype(np.float32), bt.astype(np.float32)
+
+
+def bake_vertices(points: np.ndarray, normals: np.ndarray, uvs: Optional[np.ndarray] = None) -> np.ndarray:
+    """_BakeMeshGeometry (mesh.cpp:271-330) for the no-authored-tangent, no-texcoord case:
+    fallback tangents from the Duff basis, bitangentSign = sign(dot(cross(t, b), n)) (mesh.cpp:83-86)."""
+    n = len(points)
+    t, b = duff_basis(normals)
+    sign = np.where(np.einsum("ij,ij->i", np.cross(t, b), normals) > 0, 1.0, -1.0).astype(np.float32)
+    v = np.zeros(n, VERTEX_DTYPE)
+    v["pos"] = points
+    v["norm"] = normals
+    v["tangent"] = t
+    v["bitangentSign"] = sign
+    if uvs is not None:
+        v["u"] = uvs[:, 0]
+        v["v"] = uvs[:, 1]
+    return v
+
+
+def polygon_mesh(points, face_vertex_counts, face_vertex_indices, facevarying_normals):
+    """Fan-triangulate (HdMeshUtil::ComputeTriangleIndices) and de-index a polygon mesh with
+    faceVarying normals (mesh.cpp:916-920,1011-1017)."""
+    points = np.asarray(points, np.float32)
+    normals = np.asarray(facevarying_normals, np.float32)
+    tri_pts, tri_nrm = [], []
+    off = 0
+    for cnt in face_vertex_counts:
+        for i in range(1, cnt - 1):
+            for corner in (0, i, i + 1):
+                tri_pts.append(points[face_vertex_indices[off + corner]])
+                tri_nrm.append(normals[off + corner])
+        off += cnt
+    tri_pts = np.asarray(tri_pts, np.float32)
+    tri_nrm = np.asarray(tri_nrm, np.float32)
+    faces = np.arange(len(tri_pts), dtype=np.uint32).reshape(-1, 3)
+    return bake_vertices(tri_pts, tri_nrm), faces
+
+
+# ---- C1: cornell box --------------------------------------------------------------------------
+# Geometry tables restate /root/reference/cornell.usda:1-247 (8 meshes, 46 triangles, Z-up).
+_BOX_POINTS = [(-1, -1, -1), (-1, -1, 1), (-1, 1, -1), (-1, 1, 1), (1, -1, -1), (1, -1, 1), (1, 1, -1), (1, 1, 1)]
+_BOX_COUNTS = [4] * 6
+_BOX_INDICES = [0, 1, 3, 2, 2, 3, 7, 6, 6, 7, 5, 4, 4, 5, 1, 0, 2, 6, 4, 0, 7, 3, 1, 5]
+_BOX_NORMALS = [(-1, -0.0, 0)] * 4 + [(0, 1, 0)] * 4 + [(1, -0.0, 0)] * 4 + [(0, -1, 0)] * 4 + [(0, 0, -1)] * 4 + [(0, -0.0, 1)] * 4
+_F = np.float32
+
+
+def _cornell_tables():
+    light_pts = [(-0.5, -0.5, 0.98), (-0.5, -0.5, 1), (-0.5, 0.5, 0.98), (-0.5, 0.5, 1),
+                 (0.5, -0.5, 0.98), (0.5, -0.5, 1), (0.5, 0.5, 0.98), (0.5, 0.5, 1)]
+    quad = ([4], [0, 1, 3, 2])
+    eye = np.eye(4, dtype=np.float64)
+    box1 = np.array([(0.28844988346099854, 0.19823384284973145, 0, 0), (-0.19823384284973145, 0.28844988346099854, 0, 0),
+                     (0, 0, 0.699999988079071, 0), (-0.3499999940395355, 0.3499999940395355, -0.30000001192092896, 1)])
+    box2 = np.array([(0.2831651270389557, -0.09908341616392136, 0, 0), (0.09908341616392136, 0.2831651270389557, 0, 0),
+                     (0, 0, 0.3501630127429962, 0), (0.45550230145454407, -0.41113391518592834, -0.6499999761581421, 1)])
+    # name, material, xform, points, counts, indices, normals
+    return [
+        ("Light", "Light", eye, light_pts, _BOX_COUNTS, _BOX_INDICES, _BOX_NORMALS),
+        ("BottomPlane", "White", eye, [(-1, -1, -1), (1, -1, -1), (-1, 1, -1), (1, 1, -1)], *quad, [(0, 0, 1)] * 4),
+        ("TopPlane", "White", eye, [(1, -1, 0.99999994), (-1, -1, 1.0000001), (1, 1, 0.99999994), (-1, 1, 1.0000001)], *quad,
+         [(-8.940697e-8, 0, -1)] * 4),
+        ("BackPlane", "White", eye, [(-1, 1, -1), (1, 1, -1), (-1, 0.99999994, 1), (1, 0.99999994, 1)], *quad,
+         [(0, -1, -2.9802322e-8)] * 4),
+        ("LeftPlane", "Red", eye, [(-0.99999994, -1, 1), (-1, -1, -1), (-0.99999994, 1, 1), (-1, 1, -1)], *quad,
+         [(1, 0, -2.9802322e-8)] * 4),
+        ("RightPlane", "Green", eye, [(1, -1, -1), (1, -1, 1), (1, 1, -1), (1, 1, 1)], *quad, [(-1, -0.0, 0)] * 4),
+        ("Box1", "White", box1, _BOX_POINTS, _BOX_COUNTS, _BOX_INDICES, _BOX_NORMALS),
+        ("Box2", "White", box2, _BOX_POINTS, _BOX_COUNTS, _BOX_INDICES, _BOX_NORMALS),
+    ]
+
+
+def cornell_camera() -> Camera:
+    # cornell.usda:13 camera xform; renderPass.cpp:191-228: forward = dir(0,0,-1), up = dir(0,1,0)
+    m = np.array([(1, 0, 0, 0), (0, -4.371138828673793e-8, 1, 0), (0, -1, -4.371138828673793e-8, 0), (0, -7, 0, 1)], np.float64)
+    pos = (np.array([0, 0, 0, 1.0]) @ m)[:3]
+    fwd = (np.array([0, 0, -1.0, 0]) @ m)[:3]
+    up = (np.array([0, 1.0, 0, 0]) @ m)[:3]
+    fwd /= np.linalg.norm(fwd)
+    up /= np.linalg.norm(up)
+    aperture = np.float32(20.25) * np.float32(0.1)    # GfCamera::APERTURE_UNIT
+    focal = np.float32(50.0) * np.float32(0.1)        # GfCamera::FOCAL_LENGTH_UNIT
+    vfov = np.float32(2.0) * np.float32(math.atan(float(aperture / (np.float32(2.0) * focal))))
+    return Camera(position=tuple(float(_F(x)) for x in pos), forward=tuple(float(_F(x)) for x in fwd),
+                  up=tuple(float(_F(x)) for x in up), vfov=float(vfov), focalLength=float(focal),
+                  clipStart=0.1, clipEnd=100.0)
+
+
+def cornell(width=512, height=512, spp=64, max_bounces=4) -> SceneDesc:
+    """Config C1: cornell.usda 512x512 spp 64 max-bounces 4, UsdPreviewSurface, NEE off, background (1,1,1)."""
+    mats = {
+        "Light": material_usd_preview_surface("Light", diffuse=(0.8, 0.8, 0.8), emissive=(8.5, 6, 4)),
+        "White": material_usd_preview_surface("White", diffuse=(0.8, 0.8, 0.8)),
+        "Red": material_usd_preview_surface("Red", diffuse=(1, 0, 0)),
+        "Green": material_usd_preview_surface("Green", diffuse=(0, 1, 0)),
+    }
+    names = list(mats)
+    meshes = []
+    for i, (name, mat, xf, pts, counts, idx, nrm) in enumerate(_cornell_tables()):
+        v, f = polygon_mesh(pts, counts, idx, nrm)
+        meshes.append(Mesh(v, f, names.index(mat), np.asarray(xf, np.float32), None, True, False, i + 1, name))
+    st = RenderSettings(spp=spp, maxBounces=max_bounces)
+    return SceneDesc("cornell", meshes, [mats[n] for n in names], cornell_camera(), st, width, height)
+
+
+# ---- C2: 1M random triangles ------------------------------------------------------------------
+def random_triangles(n_tris=1_000_000, width=1920, height=1080, spp=256, max_bounces=8, seed=0x2545F491) -> SceneDesc:
+    """Config C2: centre ~ U[-1,1]^3, edges ~ U[-0.02,0.02]^3, flat normals, non-indexed,
+    one mesh / one identity instance, Lambert 0.8, camera (0,-4,0) -> +Y, up +Z, vfov 40 deg."""
+    r = pcg32_uniform(seed, n_tris * 9).reshape(n_tris, 9)
+    c = r[:, 0:3] * np.float32(2) - np.float32(1)
+    e1 = (r[:, 3:6] * np.float32(2) - np.float32(1)) * np.float32(0.02)
+    e2 = (r[:, 6:9] * np.float32(2) - np.float32(1)) * np.float32(0.02)
+    pts = np.empty((n_tris, 3, 3), np.float32)
+    pts[:, 0] = c
+    pts[:, 1] = c + e1
+    pts[:, 2] = c + e2
+    nrm = np.cross(e1, e2).astype(np.float32)
+    ln = np.linalg.norm(nrm, axis=1, keepdims=True).astype(np.float32)
+    nrm = np.where(ln > 0, nrm / np.maximum(ln, np.float32(1e-30)), np.float32([0, 0, 1])).astype(np.float32)
+    normals = np.repeat(nrm, 3, axis=0)
+    v = bake_vertices(pts.reshape(-1, 3), normals)
+    f = np.arange(n_tris * 3, dtype=np.uint32).reshape(-1, 3)
+    mesh = Mesh(v, f, 0, name="soup", object_id=1)
+    cam = Camera(position=(0.0, -4.0, 0.0), forward=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0), vfov=float(np.float32(0.6981317)))
+    st = RenderSettings(spp=spp, maxBounces=max_bounces)
+    return SceneDesc("random_tris_%d" % n_tris, [mesh], [material_diffuse((0.8, 0.8, 0.8), "lambert")], cam, st, width, height)

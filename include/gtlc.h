@@ -1,0 +1,335 @@
+/*
+ * gtlc.h -- C-ABI of the B200-native wavefront path-tracing core.
+ *
+ * This is the drop-in boundary: every entry point below is what a
+ * binding of the reference's `gi` renderer API would call instead of the Vulkan-RT
+ * implementation in src/gi/impl/Gi.cpp.  Plain pointers, sizes and opaque 64-bit handles
+ * (modelled on the POD `struct{uint64_t handle}` handles of src/cgpu/gtl/cgpu/Cgpu.h:118-128);
+ * no C++ types, no torch types, no exceptions.  The reference interface each function
+ * replaces is cited as (Gi.h:LINE) = /root/reference/src/gi/gtl/gi/Gi.h.
+ *
+ * The C++ facade with the reference's exact signatures lives in include/gtl/gi/Gi.h and is
+ * implemented purely on top of this header (gatling_b200/gi_cpp/Gi.cpp).
+ */
+#ifndef GTLC_H
+#define GTLC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GTLC_API __declspec(dllexport)
+#else
+#define GTLC_API __attribute__((visibility("default")))
+#endif
+
+typedef uint64_t GtlcHandle; /* 0 == invalid (reference: nullptr from giCreate*) */
+
+enum { GTLC_OK = 0, GTLC_ERROR = 1 }; /* GiStatus, Gi.h:32 */
+
+/* GiAovId, Gi.h:34-54.  Round 1 renders Color; the others are accepted and cleared. */
+enum {
+  GTLC_AOV_COLOR = 0, GTLC_AOV_NORMAL, GTLC_AOV_NEE, GTLC_AOV_BARYCENTRICS, GTLC_AOV_TEXCOORDS,
+  GTLC_AOV_BOUNCES, GTLC_AOV_CLOCK_CYCLES, GTLC_AOV_OPACITY, GTLC_AOV_TANGENTS, GTLC_AOV_BITANGENTS,
+  GTLC_AOV_THIN_WALLED, GTLC_AOV_OBJECT_ID, GTLC_AOV_DEPTH, GTLC_AOV_FACE_ID, GTLC_AOV_INSTANCE_ID,
+  GTLC_AOV_DOUBLE_SIDED, GTLC_AOV_ALBEDO, GTLC_AOV_COUNT
+};
+
+/* GiRenderBufferFormat, Gi.h:68-73 */
+enum { GTLC_FORMAT_INT32 = 0, GTLC_FORMAT_FLOAT32 = 1, GTLC_FORMAT_FLOAT32_VEC4 = 2 };
+
+/* GiVertex, Gi.h:109-117 (48 bytes) */
+typedef struct GtlcVertex {
+  float pos[3];
+  float u;
+  float norm[3];
+  float v;
+  float tangent[3];
+  float bitangentSign;
+} GtlcVertex;
+
+/* GiFace, Gi.h:119-122 */
+typedef struct GtlcFace {
+  uint32_t v_i[3];
+} GtlcFace;
+
+/* GiMeshDesc, Gi.h:124-137 with the std::vector references flattened to pointer + count.
+ * Primvars (scene data) are a "next" row and not part of this struct yet. */
+typedef struct GtlcMeshDesc {
+  uint32_t          faceCount;
+  const GtlcFace*   faces;
+  const int32_t*    faceIds;      /* may be NULL */
+  int32_t           id;
+  int32_t           isDoubleSided;
+  int32_t           isLeftHanded;
+  const char*       name;         /* may be NULL */
+  uint32_t          maxFaceId;
+  uint32_t          vertexCount;
+  const GtlcVertex* vertices;
+} GtlcMeshDesc;
+
+/* GiCameraDesc, Gi.h:95-107 */
+typedef struct GtlcCameraDesc {
+  float position[3];
+  float forward[3];
+  float up[3];
+  float vfov;
+  float fStop;
+  float focusDistance;
+  float focalLength;
+  float clipStart;
+  float clipEnd;
+  float exposure;
+} GtlcCameraDesc;
+
+/* GiRenderSettings, Gi.h:139-159 (bool -> int32_t) */
+typedef struct GtlcRenderSettings {
+  int32_t  clippingPlanes;
+  int32_t  depthOfField;
+  int32_t  domeLightCameraVisible;
+  int32_t  filterImportanceSampling;
+  float    frame;
+  int32_t  jitteredSampling;
+  float    lightIntensityMultiplier;
+  uint32_t maxBounces;
+  float    maxSampleValue;
+  uint32_t maxVolumeWalkLength;
+  uint32_t mediumStackSize;
+  float    metersPerSceneUnit;
+  int32_t  nextEventEstimation;
+  int32_t  progressiveAccumulation;
+  uint32_t rrBounceOffset;
+  float    rrInvMinTermProb;
+  uint32_t spp;
+  float    time;
+} GtlcRenderSettings;
+
+/* GiAovBinding, Gi.h:161-166 */
+typedef struct GtlcAovBinding {
+  int32_t    aovId;
+  uint8_t    clearValue[16];
+  GtlcHandle renderBuffer;
+} GtlcAovBinding;
+
+/* GiRenderParams, Gi.h:168-175 */
+typedef struct GtlcRenderParams {
+  uint32_t              aovBindingCount;
+  const GtlcAovBinding* aovBindings;
+  GtlcCameraDesc        camera;
+  GtlcHandle            domeLight;   /* 0 = none */
+  GtlcRenderSettings    renderSettings;
+  GtlcHandle            scene;
+} GtlcRenderParams;
+
+/*
+ * Materials.  The reference lowers MaterialX/MDL to per-material GLSL through the closed MDL SDK
+ * (src/mc, SURVEY.md 8b "inner boundary"); here a material is a closure kind plus a parameter
+ * block (class-compiled instead of instance-compiled).  The C++ facade lowers MaterialX XML
+ * (constant inputs) to these blocks.
+ */
+enum {
+  GTLC_CLOSURE_DIFFUSE = 0,             /* df::diffuse_reflection_bsdf(tint)           16 B  */
+  GTLC_CLOSURE_USD_PREVIEW_SURFACE = 1, /* ND_UsdPreviewSurface_surfaceshader          64 B  */
+  GTLC_CLOSURE_OPENPBR = 2              /* src/gi/mtlx/open_pbr_surface.mtlx:99-635   192 B  */
+};
+
+#define GTLC_MATERIAL_PARAM_COUNT 48
+
+/* Indices into GtlcMaterialDesc.params for GTLC_CLOSURE_DIFFUSE */
+enum { GTLC_DIFFUSE_TINT_R = 0, GTLC_DIFFUSE_TINT_G, GTLC_DIFFUSE_TINT_B, GTLC_DIFFUSE_PAD };
+
+/* ... for GTLC_CLOSURE_USD_PREVIEW_SURFACE (UsdPreviewSurface spec input names) */
+enum {
+  GTLC_UPS_DIFFUSE_R = 0, GTLC_UPS_DIFFUSE_G, GTLC_UPS_DIFFUSE_B,
+  GTLC_UPS_EMISSIVE_R, GTLC_UPS_EMISSIVE_G, GTLC_UPS_EMISSIVE_B,
+  GTLC_UPS_USE_SPECULAR_WORKFLOW,
+  GTLC_UPS_SPECULAR_R, GTLC_UPS_SPECULAR_G, GTLC_UPS_SPECULAR_B,
+  GTLC_UPS_METALLIC, GTLC_UPS_ROUGHNESS, GTLC_UPS_CLEARCOAT, GTLC_UPS_CLEARCOAT_ROUGHNESS,
+  GTLC_UPS_OPACITY, GTLC_UPS_IOR,
+  GTLC_UPS_PARAM_COUNT /* 16 */
+};
+
+/* ... for GTLC_CLOSURE_OPENPBR (input names of open_pbr_surface.mtlx:4-97) */
+enum {
+  GTLC_OPBR_BASE_WEIGHT = 0,
+  GTLC_OPBR_BASE_COLOR_R, GTLC_OPBR_BASE_COLOR_G, GTLC_OPBR_BASE_COLOR_B,
+  GTLC_OPBR_BASE_DIFFUSE_ROUGHNESS, GTLC_OPBR_BASE_METALNESS,
+  GTLC_OPBR_SPECULAR_WEIGHT,
+  GTLC_OPBR_SPECULAR_COLOR_R, GTLC_OPBR_SPECULAR_COLOR_G, GTLC_OPBR_SPECULAR_COLOR_B,
+  GTLC_OPBR_SPECULAR_ROUGHNESS, GTLC_OPBR_SPECULAR_IOR, GTLC_OPBR_SPECULAR_ROUGHNESS_ANISOTROPY,
+  GTLC_OPBR_TRANSMISSION_WEIGHT,
+  GTLC_OPBR_TRANSMISSION_COLOR_R, GTLC_OPBR_TRANSMISSION_COLOR_G, GTLC_OPBR_TRANSMISSION_COLOR_B,
+  GTLC_OPBR_TRANSMISSION_DEPTH,
+  GTLC_OPBR_COAT_WEIGHT,
+  GTLC_OPBR_COAT_COLOR_R, GTLC_OPBR_COAT_COLOR_G, GTLC_OPBR_COAT_COLOR_B,
+  GTLC_OPBR_COAT_ROUGHNESS, GTLC_OPBR_COAT_IOR, GTLC_OPBR_COAT_DARKENING,
+  GTLC_OPBR_FUZZ_WEIGHT,
+  GTLC_OPBR_FUZZ_COLOR_R, GTLC_OPBR_FUZZ_COLOR_G, GTLC_OPBR_FUZZ_COLOR_B,
+  GTLC_OPBR_FUZZ_ROUGHNESS,
+  GTLC_OPBR_EMISSION_LUMINANCE,
+  GTLC_OPBR_EMISSION_COLOR_R, GTLC_OPBR_EMISSION_COLOR_G, GTLC_OPBR_EMISSION_COLOR_B,
+  GTLC_OPBR_THIN_FILM_WEIGHT, GTLC_OPBR_THIN_FILM_THICKNESS, GTLC_OPBR_THIN_FILM_IOR,
+  GTLC_OPBR_GEOMETRY_OPACITY, GTLC_OPBR_GEOMETRY_THIN_WALLED,
+  GTLC_OPBR_SUBSURFACE_WEIGHT,
+  GTLC_OPBR_SUBSURFACE_COLOR_R, GTLC_OPBR_SUBSURFACE_COLOR_G, GTLC_OPBR_SUBSURFACE_COLOR_B,
+  GTLC_OPBR_PARAM_COUNT /* 43 <= 48 */
+};
+
+typedef struct GtlcMaterialDesc {
+  int32_t     closure;                           /* GTLC_CLOSURE_* */
+  const char* name;                              /* may be NULL */
+  float       params[GTLC_MATERIAL_PARAM_COUNT]; /* see enums above */
+} GtlcMaterialDesc;
+
+/* Fill `desc` with the closure's spec defaults (UsdPreviewSurface spec / open_pbr_surface.mtlx:4-97). */
+GTLC_API void gtlc_material_desc_defaults(int32_t closure, GtlcMaterialDesc* desc);
+
+/* ---- lifecycle: giInitialize / giTerminate (Gi.h:199-200) -------------------------------- */
+typedef struct GtlcInitParams {
+  int32_t deviceIndex;  /* CUDA ordinal; -1 = LOCAL_RANK env or 0 (reference: GTL_DEVICE_INDEX_OVERRIDE, CgpuVk.cpp:975) */
+  int32_t reserved;
+} GtlcInitParams;
+
+GTLC_API int  gtlc_initialize(const GtlcInitParams* params);
+GTLC_API void gtlc_terminate(void);
+/* Last error text (reference logs through GB_ERROR; the C-ABI keeps the line for the binding to log). */
+GTLC_API const char* gtlc_last_error(void);
+
+/* ---- scene: giCreateScene / giDestroyScene (Gi.h:220-221) -------------------------------- */
+GTLC_API GtlcHandle gtlc_scene_create(void);
+GTLC_API void       gtlc_scene_destroy(GtlcHandle scene);
+
+/* ---- materials: giCreateMaterialFrom* / giDestroyMaterial (Gi.h:204-207) ----------------- */
+GTLC_API GtlcHandle gtlc_material_create(GtlcHandle scene, const GtlcMaterialDesc* desc);
+GTLC_API void       gtlc_material_destroy(GtlcHandle material);
+
+/* ---- meshes: Gi.h:209-216 ---------------------------------------------------------------- */
+GTLC_API GtlcHandle gtlc_mesh_create(GtlcHandle scene, const GtlcMeshDesc* desc);          /* giCreateMesh */
+GTLC_API void gtlc_mesh_set_transform(GtlcHandle mesh, const float* mat4x4);                /* giSetMeshTransform: USD row-major float[16] */
+GTLC_API void gtlc_mesh_set_instance_transforms(GtlcHandle mesh, uint32_t count, const float* transforms4x4); /* giSetMeshInstanceTransforms */
+GTLC_API void gtlc_mesh_set_instance_ids(GtlcHandle mesh, uint32_t count, const int32_t* ids);               /* giSetMeshInstanceIds */
+GTLC_API void gtlc_mesh_set_material(GtlcHandle mesh, GtlcHandle material);                 /* giSetMeshMaterial */
+GTLC_API void gtlc_mesh_set_visibility(GtlcHandle mesh, int32_t visible);                   /* giSetMeshVisibility */
+GTLC_API void gtlc_mesh_destroy(GtlcHandle mesh);                                           /* giDestroyMesh */
+
+/* ---- analytic lights: Gi.h:223-251 ------------------------------------------------------- */
+GTLC_API GtlcHandle gtlc_sphere_light_create(GtlcHandle scene);
+GTLC_API void gtlc_sphere_light_destroy(GtlcHandle scene, GtlcHandle light);
+GTLC_API void gtlc_sphere_light_set_position(GtlcHandle light, const float* position);
+GTLC_API void gtlc_sphere_light_set_base_emission(GtlcHandle light, const float* rgb);
+GTLC_API void gtlc_sphere_light_set_radius(GtlcHandle light, float radiusX, float radiusY, float radiusZ);
+GTLC_API void gtlc_sphere_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
+
+GTLC_API GtlcHandle gtlc_distant_light_create(GtlcHandle scene);
+GTLC_API void gtlc_distant_light_destroy(GtlcHandle scene, GtlcHandle light);
+GTLC_API void gtlc_distant_light_set_direction(GtlcHandle light, const float* direction);
+GTLC_API void gtlc_distant_light_set_base_emission(GtlcHandle light, const float* rgb);
+GTLC_API void gtlc_distant_light_set_angle(GtlcHandle light, float angle);
+GTLC_API void gtlc_distant_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
+
+GTLC_API GtlcHandle gtlc_rect_light_create(GtlcHandle scene);
+GTLC_API void gtlc_rect_light_destroy(GtlcHandle scene, GtlcHandle light);
+GTLC_API void gtlc_rect_light_set_origin(GtlcHandle light, const float* origin);
+GTLC_API void gtlc_rect_light_set_tangents(GtlcHandle light, const float* t0, const float* t1);
+GTLC_API void gtlc_rect_light_set_base_emission(GtlcHandle light, const float* rgb);
+GTLC_API void gtlc_rect_light_set_dimensions(GtlcHandle light, float width, float height);
+GTLC_API void gtlc_rect_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
+
+GTLC_API GtlcHandle gtlc_disk_light_create(GtlcHandle scene);
+GTLC_API void gtlc_disk_light_destroy(GtlcHandle scene, GtlcHandle light);
+GTLC_API void gtlc_disk_light_set_origin(GtlcHandle light, const float* origin);
+GTLC_API void gtlc_disk_light_set_tangents(GtlcHandle light, const float* t0, const float* t1);
+GTLC_API void gtlc_disk_light_set_base_emission(GtlcHandle light, const float* rgb);
+GTLC_API void gtlc_disk_light_set_radius(GtlcHandle light, float radiusX, float radiusY);
+GTLC_API void gtlc_disk_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
+
+/* ---- dome light: Gi.h:253-257.  The reference loads a lat-long image through imgio (out of
+ * scope); the C-ABI takes decoded RGBA float32 texels instead of a file path. ---------------- */
+GTLC_API GtlcHandle gtlc_dome_light_create(GtlcHandle scene, uint32_t width, uint32_t height, const float* rgbaTexels);
+GTLC_API void gtlc_dome_light_destroy(GtlcHandle light);
+GTLC_API void gtlc_dome_light_set_rotation(GtlcHandle light, const float* quatXYZW);
+GTLC_API void gtlc_dome_light_set_base_emission(GtlcHandle light, const float* rgb);
+GTLC_API void gtlc_dome_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
+
+/* ---- render buffers: Gi.h:259-261 -------------------------------------------------------- */
+GTLC_API GtlcHandle gtlc_render_buffer_create(uint32_t width, uint32_t height, int32_t format);  /* giCreateRenderBuffer */
+GTLC_API void       gtlc_render_buffer_destroy(GtlcHandle renderBuffer);                         /* giDestroyRenderBuffer */
+GTLC_API void*      gtlc_render_buffer_mem(GtlcHandle renderBuffer);                             /* giGetRenderBufferMem: pinned host memory, row 0 = bottom */
+/* Device-side copy of the same buffer (what gtlc_render wrote before the D2H copy); the multi-GPU
+ * harness hands this pointer to ncclReduce. */
+GTLC_API void*      gtlc_render_buffer_device_mem(GtlcHandle renderBuffer);
+
+/* ---- render: giRender (Gi.h:218).  Synchronous: on return every bound AOV is in host memory. */
+GTLC_API int gtlc_render(const GtlcRenderParams* params);
+
+/*
+ * ---- extensions that have no counterpart in Gi.h (documented in INTEGRATION.md) -------------
+ */
+
+/* Multi-GPU framebuffer sharding: this process renders only the tiles with
+ * (tileIndex % worldSize == rank); all other pixels of the colour AOV are written as 0 so that a
+ * single sum-reduce over ranks yields the full image.  tileSize in pixels (square tiles). */
+GTLC_API void gtlc_scene_set_shard(GtlcHandle scene, uint32_t rank, uint32_t worldSize, uint32_t tileSize);
+
+/* Render-loop tuning knobs (all have defaults; the bench records the values it used). */
+typedef struct GtlcTuning {
+  uint32_t maxPathsPerWave;   /* path-state pool size; default 1<<24 */
+  int32_t  sortByMaterial;    /* -1 auto (on iff >1 material), 0 off, 1 on */
+  int32_t  skipReadback;      /* 1: leave AOVs on the device (kernel-only timing) */
+  int32_t  countVisits;       /* 1: traversal kernels also count node/triangle visits (slower; roofline bookkeeping) */
+  int32_t  traceVariant;      /* 0 default; other values select experimental traversal kernels */
+  int32_t  reserved[3];
+} GtlcTuning;
+GTLC_API void gtlc_set_tuning(const GtlcTuning* tuning);
+GTLC_API void gtlc_get_tuning(GtlcTuning* tuning);
+
+/* Counters of the last gtlc_render / gtlc_trace_rays call. */
+typedef struct GtlcStats {
+  uint64_t closestRays;       /* rays traced by trace_closest */
+  uint64_t shadowRays;        /* rays traced by trace_any (tMax > 0 only) */
+  uint64_t nodeVisits;        /* BVH8 nodes fetched (valid iff countVisits) */
+  uint64_t triVisits;         /* triangles tested   (valid iff countVisits) */
+  uint64_t kernelLaunches;    /* number of __global__ launches issued */
+  uint64_t paths;             /* camera paths started */
+  float    msTotal;           /* CUDA-event time of the whole call on the render stream */
+  float    msTraceClosest;    /* summed CUDA-event time of trace_closest launches */
+  float    msTraceAny;
+  float    msShade;
+  float    msRaygen;
+  float    msSort;
+  float    msResolve;
+  float    msBvhBuild;        /* host BVH8 build + upload of the last (re)build, wall clock */
+  uint32_t bvhNodeCount;
+  uint32_t bvhTriCount;
+  uint32_t bvhMaxDepth;
+  uint32_t reserved;
+} GtlcStats;
+GTLC_API void gtlc_get_stats(GtlcStats* stats);
+
+/* Ray-query entry point used by the traversal parity tests and the roofline bench: traces `count`
+ * rays (host arrays) against the scene's BVH8 with the production kernels.
+ *   rays : count x 8 floats  (ox, oy, oz, tMin, dx, dy, dz, tMax)          [32 B, SURVEY 8d]
+ *   hits : count x 5 x 4 B   (t, u, v, primitiveId(u32), instanceIndex(u32)) [20 B]; miss: t = -1,
+ *          prim = inst = 0xFFFFFFFF.  For anyHit != 0 only `t` is meaningful (>=0 occluded, -1 free).
+ *   visits : optional count x 2 uint32 (nodes, triangles) per-ray visit counts, or NULL. */
+GTLC_API int gtlc_trace_rays(GtlcHandle scene, const float* rays, uint32_t count, int32_t anyHit,
+                             void* hits, uint32_t* visits);
+
+/* Access to the host copy of the flattened BVH8 (test/oracle cross-check of the identical structure). */
+typedef struct GtlcBvhView {
+  const void*  nodes;       /* nodeCount x 80 B compressed BVH8 nodes (layout: DESIGN.md) */
+  uint32_t     nodeCount;
+  const float* triangles;   /* triCount x 12 floats: 3 x (x, y, z, w); w0 = primId bits, w1 = instance bits */
+  uint32_t     triCount;
+} GtlcBvhView;
+GTLC_API int gtlc_scene_get_bvh(GtlcHandle scene, GtlcBvhView* view);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GTLC_H */

@@ -1,0 +1,647 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of the reference's path-tracing hot path, scalar C++ with
+// OpenMP over image rows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load this library; the product (gatling_b200/) never does.
+//
+// PARITY STATUS: UNPINNED.  Nothing of the reference can be built or run in this environment and all
+// of its golden images are Git-LFS stubs, so this file could not be checked against
+// reference outputs.  It follows the reference *source text* line by line where the source is in
+// tree (integrator: rp_main.rgen / rp_main.chit / rp_main.miss / rp_main_shadow.miss, common.glsl,
+// mdl_shading_state.glsl, Gi.cpp host encoders) and restates published definitions where the
+// arithmetic lives in third-party binaries (BSDF bodies: orc_bsdf.h; traversal: orc_scene.h).
+// Deviations and free choices: ORACLE_DEVIATIONS.md.
+//
+// Each function cites the reference lines it follows as file:line relative to
+// /root/reference/src/gi/shaders/ unless a longer path is given.
+#include "orc_scene.h"
+#include "orc_openpbr.h"
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+// rp_main_payload.glsl:3-9
+static const uint32_t PAYLOAD_VOLUME_WALK_MISS_FLAG = 0x40000000u;
+static const uint32_t PAYLOAD_MEDIUM_IDX_MASK = 0x0f000000u;
+static const uint32_t PAYLOAD_MEDIUM_IDX_OFFSET = 24;
+static const uint32_t PAYLOAD_WALK_MASK = 0x00fff000u;
+static const uint32_t PAYLOAD_BOUNCES_MASK = 0x00000fffu;
+static const uint32_t PAYLOAD_TERMINATE_FLAG = 0x80000000u;
+
+// rp_main_payload.glsl:20-47 (MEDIUM_STACK_SIZE == 0)
+struct ShadeRayPayload {
+  V3 throughput; uint32_t bitfield; V3 radiance; uint32_t rng_state;
+  V3 ray_origin, ray_dir, neeToLight, neeContrib; uint32_t pixelIndex;
+};
+
+// rp_main_payload.glsl:76-89 with MEDIUM_STACK_SIZE 0 -> maxMediumIdx = 1
+static inline uint32_t payloadGetMediumIdx(const ShadeRayPayload& p)
+{
+  uint32_t b = (p.bitfield & PAYLOAD_MEDIUM_IDX_MASK) >> PAYLOAD_MEDIUM_IDX_OFFSET;
+  return b < 1u ? b : 1u;
+}
+// rp_main_payload.glsl:91-95
+static inline void payloadSetMediumIdx(ShadeRayPayload& p, uint32_t idx)
+{
+  p.bitfield &= ~PAYLOAD_MEDIUM_IDX_MASK;
+  uint32_t v = idx << PAYLOAD_MEDIUM_IDX_OFFSET;
+  p.bitfield |= (v < PAYLOAD_MEDIUM_IDX_MASK ? v : PAYLOAD_MEDIUM_IDX_MASK);
+}
+
+// interface/rp_main.h:25-56 (fields the CPU path reads), filled like Gi.cpp:2391-2423
+struct Ubo {
+  float domeLightRotation[4]; V3 domeLightEmissionMultiplier;
+  uint32_t sphereLightCount, distantLightCount, rectLightCount, diskLightCount, totalLightCount;
+  float metersPerSceneUnit;
+  V3 cameraPosition; uint32_t imageDims; V3 cameraForward; float focusDistance; V3 cameraUp; float cameraVFoV;
+  uint32_t sampleOffset; float lensRadius; uint32_t spp; float invTotalSampleCount; float maxSampleValue;
+  uint32_t maxBouncesAndRrBounceOffset; float rrInvMinTermProb; float lightIntensityMultiplier;
+  uint32_t clipRangePacked; float sensorExposure;
+};
+
+struct Flags { // compile-time #defines of the reference, GlslShaderGen.cpp:57-72,95-133
+  bool jittered, fis, dof, nee, clipping, progressive, domeCameraVisible;
+};
+
+struct RenderCtx { const Scene* s; Ubo ubo; Flags fl; V4 background; };
+
+// rp_main.rgen:118-130
+static inline V2 fisGauss(V2 xi)
+{
+  float u1 = fmaxf(1e-38f, xi.x);
+  float u2 = xi.y;
+  float sigma = 0.375f;
+  float r = sigma * sqrtf(-2.0f * logf(u1));
+  float phi = 2.0f * PI * u2;
+  V2 o; o.x = cosf(phi) * r; o.y = sinf(phi) * r;
+  return o;
+}
+
+// rp_main.rgen:99-112
+static inline bool russian_roulette(float random_float, V3& throughput, float rrInvMinTermProb)
+{
+  float max_throughput = fmaxf(throughput.x, fmaxf(throughput.y, throughput.z));
+  float p = fminf(max_throughput, rrInvMinTermProb);
+  if (random_float > p) return true;
+  throughput = throughput / p;
+  return false;
+}
+
+// rp_main.rgen:191-271: primary ray for pixel (x, y), sample s.  Draws 2 (+2 with DoF) numbers.
+static inline void camera_ray(const Ubo& ubo, const Flags& fl, uint32_t px, uint32_t py, uint32_t& rng_state, V3& ray_origin, V3& ray_dir)
+{
+  uint32_t imageWidth = ubo.imageDims & 0xFFFFu;
+  uint32_t imageHeight = ubo.imageDims >> 16;
+  V3 camera_right = cross(ubo.cameraForward, ubo.cameraUp);              // :199
+  float aspect_ratio = (float) imageWidth / (float) imageHeight;         // :200
+  float H = 1.0f;
+  float W = H * aspect_ratio;
+  float d = H / (2.0f * tanf(ubo.cameraVFoV * 0.5f));                    // :204
+  float WX = W / (float) imageWidth;
+  float HY = H / (float) imageHeight;
+  V3 C = ubo.cameraPosition + ubo.cameraForward * d;                     // :209
+  V3 L = (C - (camera_right * W) * 0.5f) - (ubo.cameraUp * H) * 0.5f;    // :210
+
+  V2 rand2_xy = rng1d_next2f(rng_state);                                 // :224
+  V2 sampleOffset; sampleOffset.x = 0.5f; sampleOffset.y = 0.5f;         // :227
+  if (fl.jittered) {
+    if (fl.fis) { V2 g = fisGauss(rand2_xy); sampleOffset.x = 0.5f + g.x; sampleOffset.y = 0.5f + g.y; } // :232
+    else sampleOffset = rand2_xy;                                        // :235
+  }
+  V3 P = (L + (camera_right * ((float) px + sampleOffset.x)) * WX) + (ubo.cameraUp * ((float) py + sampleOffset.y)) * HY; // :239-242
+  ray_origin = ubo.cameraPosition;
+  ray_dir = normalize(P - ray_origin);                                   // :245
+  if (fl.dof && ubo.lensRadius > 0.0f) {                                 // :250-267
+    V2 rand2_zw = rng1d_next2f(rng_state);
+    V3 focalPoint = ray_origin + ray_dir * ubo.focusDistance;
+    V3 h = sample_hemisphere(rand2_zw);
+    float ax = h.x * ubo.lensRadius, ay = h.y * ubo.lensRadius;
+    ray_origin += camera_right * ax;
+    ray_origin += ubo.cameraUp * ay;
+    ray_dir = normalize(focalPoint - ray_origin);
+  }
+  ray_dir.x += (ray_dir.x == 0.0f) ? FLOAT_MIN : 0.0f;                   // :271
+  ray_dir.y += (ray_dir.y == 0.0f) ? FLOAT_MIN : 0.0f;
+  ray_dir.z += (ray_dir.z == 0.0f) ? FLOAT_MIN : 0.0f;
+}
+
+// rp_main.miss:39-44
+static inline V3 quatRotateDir(const float* q, V3 dir)
+{
+  V3 qv = v3(q[0], q[1], q[2]);
+  V3 a = cross(qv, dir);
+  V3 b = cross(qv, a);
+  return dir + ((a * q[3]) + b) * 2.0f;
+}
+
+// Bilinear lat-long lookup with sampler state linear/linear, REPEAT (Gi.cpp:388-392), unnormalised
+// texel centres at +0.5 (Vulkan spec 16.x "Texel Filtering").
+static inline V3 texture_latlong(const Scene& s, float u, float v)
+{
+  int W = (int) s.domeW, H = (int) s.domeH;
+  float x = u * (float) W - 0.5f, y = v * (float) H - 0.5f;
+  float fx = floorf(x), fy = floorf(y);
+  float ax = x - fx, ay = y - fy;
+  int x0 = (int) fx, y0 = (int) fy;
+  auto wrap = [](int i, int n) { int m = i % n; return m < 0 ? m + n : m; };
+  int xa = wrap(x0, W), xb = wrap(x0 + 1, W), ya = wrap(y0, H), yb = wrap(y0 + 1, H);
+  auto tex = [&](int xx, int yy) { const float* p = &s.domeTexels[((size_t) yy * W + xx) * 4]; return v3(p[0], p[1], p[2]); };
+  V3 top = tex(xa, ya) * (1.0f - ax) + tex(xb, ya) * ax;
+  V3 bot = tex(xa, yb) * (1.0f - ax) + tex(xb, yb) * ax;
+  return top * (1.0f - ay) + bot * ay;
+}
+
+// rp_main.miss:46-53 + texture binding logic Gi.cpp:2183-2199,2334-2337
+static inline V3 sampleDomeLight(const RenderCtx& c, uint32_t domeLightIndex, V3 rayDir)
+{
+  bool haveDome = !c.s->domeTexels.empty();
+  if (domeLightIndex == 0 || !haveDome) {
+    // 1x1 RGBA8 fallback holding the colour-AOV clear value: glm::u8vec4(backgroundColor * 255.0f)
+    V3 bg;
+    bg.x = (float)(uint8_t)(c.background.x * 255.0f) / 255.0f;
+    bg.y = (float)(uint8_t)(c.background.y * 255.0f) / 255.0f;
+    bg.z = (float)(uint8_t)(c.background.z * 255.0f) / 255.0f;
+    return bg;
+  }
+  float u = (atan2f(rayDir.z, rayDir.x) + 0.5f * PI) / (2.0f * PI);
+  float v = 1.0f - acosf(rayDir.y) / PI;
+  return texture_latlong(*c.s, u, v);
+}
+
+// rp_main.miss:55-87 (MEDIUM_STACK_SIZE == 0, colour AOV bound)
+static inline void miss_shader(const RenderCtx& c, ShadeRayPayload& p, V3 worldRayDir)
+{
+  p.bitfield |= PAYLOAD_TERMINATE_FLAG;                                  // :68
+  bool useFallbackDomeLight = false;
+  if (!c.fl.domeCameraVisible) {                                         // :76-80
+    bool isPrimaryRay = (p.bitfield & PAYLOAD_BOUNCES_MASK) == 0;
+    useFallbackDomeLight = isPrimaryRay;
+  }
+  uint32_t domeLightIndex = useFallbackDomeLight ? 0u : 1u;              // :82
+  V3 sampleDir = normalize(quatRotateDir(c.ubo.domeLightRotation, worldRayDir)); // :83
+  V3 radiance = sampleDomeLight(c, domeLightIndex, sampleDir) * c.ubo.domeLightEmissionMultiplier; // :84
+  p.radiance += p.throughput * radiance;                                 // :86
+}
+
+// rp_main.chit:30-129
+static inline void sampleLight(const RenderCtx& c, V4 k4, V3 surfacePos, V3& dirToLight, float& dist, V3& power, float& invPdf, uint32_t& diffuseSpecularPacked)
+{
+  const Ubo& ubo = c.ubo; const Scene& s = *c.s;
+  static const SphereLight zeroSphere = {};
+  float total = (float) ubo.totalLightCount;
+  if ((k4.x * total) <= (float) ubo.sphereLightCount) {                                        // :32
+    uint32_t n = ubo.sphereLightCount;
+    uint32_t lightIndex = (uint32_t)(k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u; // :34 (n==0 wraps to UINT_MAX)
+    const SphereLight& light = (n == 0 || lightIndex >= s.sphereLights.size()) ? zeroSphere : s.sphereLights[lightIndex];
+    V3 lpos = v3(light.pos[0], light.pos[1], light.pos[2]);
+    V2 zw; zw.x = k4.z; zw.y = k4.w;
+    V3 samplePos = lpos + sample_sphere(zw, v3(light.radiusXYZ[0], light.radiusXYZ[1], light.radiusXYZ[2])); // :40
+    V3 dir = samplePos - surfacePos;
+    dist = length(dir);
+    dirToLight = safe_div(dir, dist);
+    V3 lightNormal = normalize(samplePos - lpos);                                              // :46
+    float cosTheta = fmaxf(0.0f, dot(-dirToLight, lightNormal));
+    invPdf = safe_div((light.area > 0.0f) ? (light.area * cosTheta) : 1.0f, dist * dist);    // :48
+    power = v3(light.baseEmission[0], light.baseEmission[1], light.baseEmission[2]) * ubo.lightIntensityMultiplier;
+    diffuseSpecularPacked = light.diffuseSpecularPacked;
+  } else if ((k4.x * total) <= (float)(ubo.sphereLightCount + ubo.distantLightCount)) {        // :53
+    uint32_t n = ubo.distantLightCount;
+    uint32_t lightIndex = (uint32_t)(k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u;
+    const DistantLight& light = s.distantLights[lightIndex];
+    dist = 100000.0f;
+    dirToLight = -v3(light.direction[0], light.direction[1], light.direction[2]);
+    power = v3(light.baseEmission[0], light.baseEmission[1], light.baseEmission[2]) * ubo.lightIntensityMultiplier;
+    invPdf = light.invPdf;
+    diffuseSpecularPacked = light.diffuseSpecularPacked;
+    if (light.angle > 0.0f) {                                                                  // :65-74
+      V3 t1, t2;
+      orthonormal_basis(dirToLight, t1, t2);
+      float phi = ((k4.z * 2.0f) * PI) - PI;
+      float theta = k4.w * light.angle;
+      dirToLight = normalize(((t1 * cosf(phi) + t2 * sinf(phi)) * sinf(theta)) + dirToLight * cosf(theta));
+    }
+  } else if ((k4.x * total) <= (float)(ubo.sphereLightCount + ubo.distantLightCount + ubo.rectLightCount)) { // :76
+    uint32_t n = ubo.rectLightCount;
+    uint32_t lightIndex = (uint32_t)(k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u;
+    const RectLight& light = s.rectLights[lightIndex];
+    float sx = (k4.z - 0.5f) * light.width, sy = (k4.w - 0.5f) * light.height;                 // :83
+    V3 t0 = decode_direction(light.tangentFramePacked[0]);
+    V3 t1 = decode_direction(light.tangentFramePacked[1]);
+    V3 samplePos = (v3(light.origin[0], light.origin[1], light.origin[2]) + t0 * sx) + t1 * sy; // :87
+    V3 dir = samplePos - surfacePos;
+    dist = length(dir);
+    dirToLight = safe_div(dir, dist);
+    V3 lightNormal = cross(t1, t0);                                                            // :93
+    float cosTheta = fmaxf(0.0f, dot(-dirToLight, lightNormal));
+    float area = light.width * light.height;
+    invPdf = safe_div((area > 0.0f) ? (area * cosTheta) : 1.0f, dist * dist);
+    power = v3(light.baseEmission[0], light.baseEmission[1], light.baseEmission[2]) * ubo.lightIntensityMultiplier;
+    diffuseSpecularPacked = light.diffuseSpecularPacked;
+  } else {                                                                                     // :101
+    uint32_t n = ubo.diskLightCount;
+    uint32_t lightIndex = (uint32_t)(k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u;
+    const DiskLight& light = s.diskLights[lightIndex];
+    V2 radiusXY; radiusXY.x = light.radiusX; radiusXY.y = light.radiusY;
+    V2 zw; zw.x = k4.z; zw.y = k4.w;
+    V2 sampleOnDisk = sample_disk(zw, radiusXY);
+    V3 t0 = decode_direction(light.tangentFramePacked[0]);
+    V3 t1 = decode_direction(light.tangentFramePacked[1]);
+    V3 samplePos = (v3(light.origin[0], light.origin[1], light.origin[2]) + t0 * sampleOnDisk.x) + t1 * sampleOnDisk.y;
+    V3 dir = samplePos - surfacePos;
+    dist = length(dir);
+    dirToLight = safe_div(dir, dist);
+    V3 lightNormal = cross(t1, t0);
+    float cosTheta = fmaxf(0.0f, dot(-dirToLight, lightNormal));
+    float area = (radiusXY.x * radiusXY.y) * PI;
+    invPdf = safe_div((area > 0.0f) ? (area * cosTheta) : 1.0f, dist * dist);
+    power = v3(light.baseEmission[0], light.baseEmission[1], light.baseEmission[2]) * ubo.lightIntensityMultiplier;
+    diffuseSpecularPacked = light.diffuseSpecularPacked;
+  }
+  power *= exp2f(ubo.sensorExposure);                                                          // :127
+  invPdf *= (float) ubo.totalLightCount;                                                       // :128
+}
+
+// rp_main.chit:132-493 (MEDIUM_STACK_SIZE == 0; AOV section :191-290 handled by the caller for Color only)
+static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, const Hit& hit, V3 worldRayDir)
+{
+  const Scene& s = *c.s;
+  const InstanceDesc& in = s.instances[hit.inst];
+  bool isLeftHanded = (in.flags & 1u) != 0;                               // :137
+  bool isDoubleSided = (in.flags & 2u) != 0;                              // :138
+  const Material& mat = s.materials[in.material];
+
+  State st; bool isFrontFace;
+  setup_shading_state(s, hit, worldRayDir, st, isFrontFace);              // :143
+  const V3 normal = st.normal;                                            // :147
+
+  V3 throughput = p.throughput;
+  V3 radiance = p.radiance;
+  uint32_t mediumIdx = payloadGetMediumIdx(p);                            // :153
+  bool thinWalled = mat_is_thin_walled(mat);                              // :155-158
+
+  if (mediumIdx > 0) {                                                    // :164-186
+    float distance = hit.t * c.ubo.metersPerSceneUnit;
+    V3 sigma_a = mat_volume_absorption(mat);
+    V3 transmittance = v3(expf(-sigma_a.x * distance), expf(-sigma_a.y * distance), expf(-sigma_a.z * distance));
+    throughput *= transmittance;
+  }
+  // :188-189 with prev/nextMediumIor = 1 (MEDIUM_STACK_SIZE == 0)
+  const float USE_MATERIAL_IOR = -1.0f;
+  V3 iorCurrent = (isFrontFace || thinWalled) ? v3(1.0f) : v3(USE_MATERIAL_IOR);
+  V3 iorOther = (isFrontFace || thinWalled) ? v3(USE_MATERIAL_IOR) : v3(1.0f);
+
+  if (mat_is_emissive(mat)) {                                             // :293-343
+    if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
+    EdfEvaluateData e; e.k1 = -worldRayDir; e.pdf = 0.0f; e.edf = v3(0.0f); e.cos = 0.0f;
+    if (isFrontFace || !isDoubleSided) edf_evaluate(e, st);
+    if (e.pdf > 0.0f) {
+      V3 emission_intensity = v3(0.0f);
+      if (isFrontFace || !isDoubleSided) emission_intensity = mat_emission_intensity(mat);
+      emission_intensity *= exp2f(c.ubo.sensorExposure);
+      radiance += (throughput * e.edf) * emission_intensity;
+    }
+    if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
+  }
+  st.normal = normal;                                                     // :346
+
+  uint32_t eventType;
+  {                                                                       // :361-389
+    BsdfSampleData d;
+    d.ior1 = iorCurrent; d.ior2 = iorOther; d.k1 = -worldRayDir;
+    d.xi = rng1d_next4f(p.rng_state);                                     // :370
+    bsdf_sample(mat, d, st);
+    eventType = (uint32_t) d.event_type;
+    throughput *= d.bsdf_over_pdf;                                        // :386
+    p.ray_dir = d.k2;                                                     // :388
+  }
+  bool isTransmissionEvent = (eventType & BSDF_EVENT_TRANSMISSION) != 0;  // :391
+
+  if (c.fl.nee && (eventType & (BSDF_EVENT_DIFFUSE | BSDF_EVENT_GLOSSY)) != 0) { // :394-444
+    st.normal = normal;
+    V4 k4 = rng1d_next4f(p.rng_state);                                    // :404
+    V3 dirToLight, lightPower; float lightDist, invLightSamplePdf; uint32_t diffuseSpecularPacked;
+    sampleLight(c, k4, st.position, dirToLight, lightDist, lightPower, invLightSamplePdf, diffuseSpecularPacked);
+    V3 neeContrib = v3(0.0f);
+    bool neeValid = (lightDist > 0.0f) && dot(dirToLight, st.geom_normal) > 0.0f; // :415
+    if (neeValid) {
+      BsdfEvaluateData e;
+      e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = dirToLight;
+      bsdf_evaluate(mat, e, st);                                          // :425 (always the front-face BSDF)
+      neeValid = (e.pdf > 0.0f);
+      if (neeValid) {
+        V2 diffuseSpecular = unpackHalf2x16(diffuseSpecularPacked);
+        V3 neeRadiance = lightPower * invLightSamplePdf;
+        V3 weight = throughput * neeRadiance;
+        neeContrib += (weight * e.bsdf_diffuse) * diffuseSpecular.x;      // :436
+        neeContrib += (weight * e.bsdf_glossy) * diffuseSpecular.y;       // :437
+      }
+    }
+    p.neeToLight = dirToLight * lightDist;                                // :441
+    p.neeContrib = neeContrib;
+  }
+
+  if (!thinWalled && isTransmissionEvent) {                               // :447-480
+    mediumIdx = (1u - mediumIdx);                                         // :473
+    p.bitfield &= ~PAYLOAD_WALK_MASK;
+    payloadSetMediumIdx(p, mediumIdx);
+  }
+  if (eventType == BSDF_EVENT_ABSORB) p.bitfield |= PAYLOAD_TERMINATE_FLAG; // :483-486
+
+  V3 geomNormal = st.geom_normal * (isTransmissionEvent ? -1.0f : 1.0f);  // :488
+  p.ray_origin = offset_ray_origin(st.position, geomNormal);              // :489
+  p.throughput = throughput;
+  p.radiance = radiance;
+}
+
+struct RayCounters { uint64_t closest, shadow; };
+
+// rp_main.rgen:215-499: one sample of one pixel; returns the clamped sample colour.
+static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint32_t pixelIndex, uint32_t s, RayCounters& rc)
+{
+  const Ubo& ubo = c.ubo;
+  uint32_t sampleIndex = ubo.sampleOffset + s;                            // :217
+  uint32_t rng_state = rng1d_init(pixelIndex, sampleIndex);               // :223
+  V3 ray_origin, ray_dir;
+  camera_ray(ubo, c.fl, px, py, rng_state, ray_origin, ray_dir);
+
+  ShadeRayPayload p;                                                      // :274-283
+  p.throughput = v3(1.0f); p.bitfield = 0; p.radiance = v3(0.0f); p.rng_state = rng_state;
+  p.ray_origin = ray_origin; p.ray_dir = ray_dir; p.pixelIndex = pixelIndex;
+  p.neeToLight = v3(0.0f); p.neeContrib = v3(0.0f);
+
+  float cosConeAngle = fmaxf(1e-5f, dot(ray_dir, ubo.cameraForward));     // :287
+  V2 clipRange = unpackHalf2x16(ubo.clipRangePacked);
+  clipRange.x = clipRange.x / cosConeAngle; clipRange.y = clipRange.y / cosConeAngle; // :288
+
+  uint32_t rrBounceOffset = ubo.maxBouncesAndRrBounceOffset & 0xFFFFu;    // :291
+  uint32_t maxBounces = ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > PAYLOAD_BOUNCES_MASK) maxBounces = PAYLOAD_BOUNCES_MASK;
+
+  while (true) {                                                          // :294
+    uint32_t bounce = (p.bitfield & PAYLOAD_BOUNCES_MASK);
+    bool terminate = (p.bitfield & PAYLOAD_TERMINATE_FLAG) != 0;
+    if (bounce >= maxBounces || terminate) break;                         // :301
+    float tMin = 0.0f, tMax = FLOAT_MAX;
+    if (c.fl.clipping && bounce == 0) { tMin = clipRange.x; tMax = clipRange.y; } // :308-314
+    p.neeContrib = v3(0.0f);                                              // :349
+
+    Hit hit;
+    V3 d = p.ray_dir, o = p.ray_origin;
+    rc.closest++;
+    if (scene_trace(*c.s, o, d, tMin, tMax, false, hit)) closest_hit_shader(c, p, hit, d); // :381-393
+    else miss_shader(c, p, d);
+
+    if (c.fl.nee) {                                                       // :397-438
+      V3 shadowray_origin = p.ray_origin;
+      float lightDist = length(p.neeToLight);
+      V3 shadowray_dir = safe_div(p.neeToLight, lightDist);
+      bool traceRay = luminance(p.neeContrib) > 1e-6f && lightDist > 1e-9f; // :407
+      float stMin = traceRay ? 0.01f : 0.0f;
+      float stMax = traceRay ? lightDist : 0.0f;
+      bool shadowed = true;
+      if (traceRay) {
+        rc.shadow++;
+        Hit sh;
+        shadowed = scene_trace(*c.s, shadowray_origin, shadowray_dir, stMin, stMax, true, sh);
+      }
+      bool addContrib = traceRay && !shadowed;                            // :426
+      if (addContrib) p.radiance += p.neeContrib;                         // :429
+    }
+    if (length(p.throughput) < 1e-9f) p.bitfield |= PAYLOAD_TERMINATE_FLAG; // :441-444
+    if (bounce > rrBounceOffset) {                                        // :447-459
+      float k1 = rng1d_next1f(p.rng_state);
+      if (russian_roulette(k1, p.throughput, ubo.rrInvMinTermProb)) p.bitfield |= PAYLOAD_TERMINATE_FLAG;
+    }
+    p.bitfield++;                                                         // :480
+  }
+  V3 radiance = p.radiance;                                               // :489-496
+  float maxValue = fmaxf(radiance.x, fmaxf(radiance.y, radiance.z));
+  if (maxValue > ubo.maxSampleValue) radiance *= (ubo.maxSampleValue / maxValue);
+  return vmax(radiance, 0.0f);
+}
+
+// --------------------------------------------------------------------------------------------
+// C API (ctypes)
+// --------------------------------------------------------------------------------------------
+extern "C" {
+
+struct OrcSceneDesc {
+  const GtlcVertex* vertices; uint32_t vertexCount;
+  const uint32_t* faces; uint32_t faceCount;
+  const InstanceDesc* instances; uint32_t instanceCount;
+  const GtlcMaterialDesc* materials; uint32_t materialCount;
+  const SphereLight* sphereLights; uint32_t sphereLightCount;
+  const DistantLight* distantLights; uint32_t distantLightCount;
+  const RectLight* rectLights; uint32_t rectLightCount;
+  const DiskLight* diskLights; uint32_t diskLightCount;
+  const float* domeTexels; uint32_t domeW, domeH;
+  float domeRotation[4]; float domeEmission[3]; uint32_t pad;
+};
+
+struct OrcRenderDesc {
+  GtlcCameraDesc camera;
+  GtlcRenderSettings settings;
+  float clearColor[4];
+  uint32_t width, height;
+  uint32_t sampleOffset;
+  uint32_t rowBegin, rowEnd;      // bounded samples for the CPU baseline: render rows [rowBegin, rowEnd)
+  uint32_t shardRank, shardCount, shardTile; // shardCount <= 1: everything
+};
+
+void* orc_scene_create(const OrcSceneDesc* d)
+{
+  Scene* s = new Scene();
+  s->vertices.assign(d->vertices, d->vertices + d->vertexCount);
+  s->faces.assign(d->faces, d->faces + (size_t) d->faceCount * 3);
+  s->instances.assign(d->instances, d->instances + d->instanceCount);
+  for (uint32_t i = 0; i < d->materialCount; i++) {
+    Material m; m.closure = d->materials[i].closure; memcpy(m.p, d->materials[i].params, sizeof(m.p));
+    s->materials.push_back(m);
+  }
+  if (d->sphereLightCount) s->sphereLights.assign(d->sphereLights, d->sphereLights + d->sphereLightCount);
+  if (d->distantLightCount) s->distantLights.assign(d->distantLights, d->distantLights + d->distantLightCount);
+  if (d->rectLightCount) s->rectLights.assign(d->rectLights, d->rectLights + d->rectLightCount);
+  if (d->diskLightCount) s->diskLights.assign(d->diskLights, d->diskLights + d->diskLightCount);
+  if (d->domeTexels && d->domeW && d->domeH) {
+    s->domeTexels.assign(d->domeTexels, d->domeTexels + (size_t) d->domeW * d->domeH * 4);
+    s->domeW = d->domeW; s->domeH = d->domeH;
+    memcpy(s->domeRotation, d->domeRotation, 16); memcpy(s->domeEmission, d->domeEmission, 12);
+  }
+  scene_build(*s);
+  return s;
+}
+void orc_scene_destroy(void* h) { delete (Scene*) h; }
+
+static void fill_ctx(RenderCtx& c, const Scene* s, const OrcRenderDesc* r)
+{
+  const GtlcRenderSettings& rs = r->settings;
+  c.s = s;
+  Ubo& u = c.ubo;
+  bool dome = !s->domeTexels.empty();
+  // Gi.cpp:2384-2386: no dome -> rotation "doesn't matter", emission multiplier 1
+  if (dome) { memcpy(u.domeLightRotation, s->domeRotation, 16); u.domeLightEmissionMultiplier = v3(s->domeEmission[0], s->domeEmission[1], s->domeEmission[2]); }
+  else { u.domeLightRotation[0] = u.domeLightRotation[1] = u.domeLightRotation[2] = 0.0f; u.domeLightRotation[3] = 1.0f; u.domeLightEmissionMultiplier = v3(1.0f); }
+  u.sphereLightCount = (uint32_t) s->sphereLights.size(); u.distantLightCount = (uint32_t) s->distantLights.size();
+  u.rectLightCount = (uint32_t) s->rectLights.size(); u.diskLightCount = (uint32_t) s->diskLights.size();
+  u.totalLightCount = u.sphereLightCount + u.distantLightCount + u.rectLightCount + u.diskLightCount;
+  u.metersPerSceneUnit = rs.metersPerSceneUnit;
+  u.cameraPosition = v3(r->camera.position[0], r->camera.position[1], r->camera.position[2]);
+  u.imageDims = (r->height << 16) | r->width;
+  u.cameraForward = normalize(v3(r->camera.forward[0], r->camera.forward[1], r->camera.forward[2])); // Gi.cpp:2375
+  u.cameraUp = normalize(v3(r->camera.up[0], r->camera.up[1], r->camera.up[2]));
+  u.focusDistance = r->camera.focusDistance;
+  u.cameraVFoV = r->camera.vfov;
+  u.sampleOffset = r->sampleOffset;
+  u.lensRadius = (r->camera.fStop > 0.0f) ? (r->camera.focalLength / (2.0f * r->camera.fStop)) : 0.0f; // Gi.cpp:2378-2382
+  u.spp = rs.spp;
+  u.invTotalSampleCount = 1.0f / (float)(r->sampleOffset + rs.spp);
+  u.maxSampleValue = rs.maxSampleValue;
+  u.maxBouncesAndRrBounceOffset = (rs.maxBounces << 16) | rs.rrBounceOffset;
+  u.rrInvMinTermProb = rs.rrInvMinTermProb;
+  u.lightIntensityMultiplier = rs.lightIntensityMultiplier;
+  u.clipRangePacked = packHalf2x16(r->camera.clipStart, r->camera.clipEnd);
+  u.sensorExposure = r->camera.exposure;
+  c.fl.jittered = rs.jitteredSampling != 0; c.fl.fis = rs.filterImportanceSampling != 0; c.fl.dof = rs.depthOfField != 0;
+  c.fl.nee = rs.nextEventEstimation != 0; c.fl.clipping = rs.clippingPlanes != 0; c.fl.progressive = rs.progressiveAccumulation != 0;
+  c.fl.domeCameraVisible = rs.domeLightCameraVisible != 0;
+  c.background.x = r->clearColor[0]; c.background.y = r->clearColor[1]; c.background.z = r->clearColor[2]; c.background.w = r->clearColor[3];
+}
+
+// rgba: width*height*4 floats, row 0 = bottom (rp_main.rgen:210,239-242).  On entry (sampleOffset > 0
+// and progressive) it must hold the previous ColorAov; on exit the new one (rp_main.rgen:506-515).
+// rayCounts (optional): [closest, shadow].  Returns seconds spent in the sample loop.
+double orc_render(void* h, const OrcRenderDesc* r, float* rgba, uint64_t* rayCounts)
+{
+  const Scene* s = (const Scene*) h;
+  RenderCtx c; fill_ctx(c, s, r);
+  uint32_t W = r->width, H = r->height, spp = r->settings.spp;
+  uint32_t rowEnd = r->rowEnd ? r->rowEnd : H;
+  float invSpp = 1.0f / (float) spp;                                      // :212
+  uint64_t nClosest = 0, nShadow = 0;
+  auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nClosest, nShadow)
+  for (int y = (int) r->rowBegin; y < (int) rowEnd; y++) {
+    RayCounters rc = { 0, 0 };
+    for (uint32_t x = 0; x < W; x++) {
+      uint32_t pixelIndex = x + (uint32_t) y * W;                         // :195
+      float* out = &rgba[(size_t) pixelIndex * 4];
+      if (r->shardCount > 1) {
+        uint32_t tilesX = (W + r->shardTile - 1) / r->shardTile;
+        uint32_t tile = ((uint32_t) y / r->shardTile) * tilesX + (x / r->shardTile);
+        if (tile % r->shardCount != r->shardRank) { out[0] = out[1] = out[2] = out[3] = 0.0f; continue; }
+      }
+      V3 pixel_color = v3(0.0f);
+      for (uint32_t sIdx = 0; sIdx < spp; sIdx++) {
+        V3 sample_color = trace_sample(c, x, (uint32_t) y, pixelIndex, sIdx, rc);
+        pixel_color += sample_color * invSpp;                             // :498
+      }
+      V3 prevColor = pixel_color;                                         // :507-514
+      if (c.fl.progressive && c.ubo.sampleOffset > 0) prevColor = v3(out[0], out[1], out[2]);
+      V3 o = (prevColor * (float) c.ubo.sampleOffset + pixel_color * (float) c.ubo.spp) * c.ubo.invTotalSampleCount;
+      out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = 1.0f;
+    }
+    nClosest += rc.closest; nShadow += rc.shadow;
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  if (rayCounts) { rayCounts[0] = nClosest; rayCounts[1] = nShadow; }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// rays: n x (ox, oy, oz, tMin, dx, dy, dz, tMax); hits: n x (t, u, v, prim, inst) 20 B records
+void orc_trace(void* h, const float* rays, uint32_t n, int anyHit, void* hitsOut)
+{
+  const Scene* s = (const Scene*) h;
+  Hit* hits = (Hit*) hitsOut;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < (int) n; i++) {
+    const float* r = &rays[(size_t) i * 8];
+    Hit hit;
+    scene_trace(*s, v3(r[0], r[1], r[2]), v3(r[4], r[5], r[6]), r[3], r[7], anyHit != 0, hit);
+    hits[i] = hit;
+  }
+}
+
+// First bounce path state for raygen parity: out n x 8 floats (ox, oy, oz, rng bits, dx, dy, dz, 0)
+void orc_camera_rays(const OrcRenderDesc* r, uint32_t sampleIndex, float* out)
+{
+  Scene dummy; RenderCtx c; fill_ctx(c, &dummy, r);
+  for (uint32_t y = 0; y < r->height; y++)
+    for (uint32_t x = 0; x < r->width; x++) {
+      uint32_t pixelIndex = x + y * r->width;
+      uint32_t rng = rng1d_init(pixelIndex, sampleIndex);
+      V3 o, d; camera_ray(c.ubo, c.fl, x, y, rng, o, d);
+      float* p = &out[(size_t) pixelIndex * 8];
+      p[0] = o.x; p[1] = o.y; p[2] = o.z; p[3] = uintBitsToFloat(rng); p[4] = d.x; p[5] = d.y; p[6] = d.z; p[7] = 0.0f;
+    }
+}
+
+// Closure-level access for white-furnace / reciprocity tests.
+// state: normal(3) geom_normal(3) tangent_u(3); k1(3); xi(4) -> k2(3) bsdf_over_pdf(3) event
+void orc_bsdf_sample(const GtlcMaterialDesc* md, const float* state9, const float* k1, const float* xi, float* k2, float* bsdfOverPdf, int32_t* eventType)
+{
+  Material m; m.closure = md->closure; memcpy(m.p, md->params, sizeof(m.p));
+  State st; st.normal = v3(state9[0], state9[1], state9[2]); st.geom_normal = v3(state9[3], state9[4], state9[5]);
+  st.tangent_u = v3(state9[6], state9[7], state9[8]); st.tangent_v = cross(st.normal, st.tangent_u); st.position = v3(0.0f); st.text_coords = v3(0.0f);
+  BsdfSampleData d; d.ior1 = v3(1.0f); d.ior2 = v3(-1.0f); d.k1 = v3(k1[0], k1[1], k1[2]);
+  d.xi.x = xi[0]; d.xi.y = xi[1]; d.xi.z = xi[2]; d.xi.w = xi[3];
+  bsdf_sample(m, d, st);
+  k2[0] = d.k2.x; k2[1] = d.k2.y; k2[2] = d.k2.z;
+  bsdfOverPdf[0] = d.bsdf_over_pdf.x; bsdfOverPdf[1] = d.bsdf_over_pdf.y; bsdfOverPdf[2] = d.bsdf_over_pdf.z;
+  *eventType = d.event_type;
+}
+void orc_bsdf_evaluate(const GtlcMaterialDesc* md, const float* state9, const float* k1, const float* k2, float* diffuse, float* glossy, float* pdf)
+{
+  Material m; m.closure = md->closure; memcpy(m.p, md->params, sizeof(m.p));
+  State st; st.normal = v3(state9[0], state9[1], state9[2]); st.geom_normal = v3(state9[3], state9[4], state9[5]);
+  st.tangent_u = v3(state9[6], state9[7], state9[8]); st.tangent_v = cross(st.normal, st.tangent_u); st.position = v3(0.0f); st.text_coords = v3(0.0f);
+  BsdfEvaluateData d; d.ior1 = v3(1.0f); d.ior2 = v3(-1.0f); d.k1 = v3(k1[0], k1[1], k1[2]); d.k2 = v3(k2[0], k2[1], k2[2]);
+  bsdf_evaluate(m, d, st);
+  diffuse[0] = d.bsdf_diffuse.x; diffuse[1] = d.bsdf_diffuse.y; diffuse[2] = d.bsdf_diffuse.z;
+  glossy[0] = d.bsdf_glossy.x; glossy[1] = d.bsdf_glossy.y; glossy[2] = d.bsdf_glossy.z;
+  *pdf = d.pdf;
+}
+
+// ---- known-answer access to the pure functions (common.glsl) ---------------------------------
+uint32_t orc_hash_theironborn(uint32_t x) { return hash_theironborn(x); }
+uint32_t orc_hash_pcg32(uint32_t* state) { return hash_pcg32(*state); }
+float orc_uint_as_float(uint32_t v) { return uintAsFloat(v); }
+uint32_t orc_rng_init(uint32_t pixelIndex, uint32_t sampleIndex) { return rng1d_init(pixelIndex, sampleIndex); }
+float orc_rng_next1f(uint32_t* state) { return rng1d_next1f(*state); }
+void orc_orthonormal_basis(const float* n, float* b1, float* b2) { V3 a, b; orthonormal_basis(v3(n[0], n[1], n[2]), a, b); b1[0] = a.x; b1[1] = a.y; b1[2] = a.z; b2[0] = b.x; b2[1] = b.y; b2[2] = b.z; }
+void orc_offset_ray_origin(const float* p, const float* n, float* o) { V3 r = offset_ray_origin(v3(p[0], p[1], p[2]), v3(n[0], n[1], n[2])); o[0] = r.x; o[1] = r.y; o[2] = r.z; }
+uint32_t orc_encode_direction(const float* d) { return encode_direction(v3(d[0], d[1], d[2])); }
+uint32_t orc_host_encode_direction(const float* d) { return host_encode_direction(v3(d[0], d[1], d[2])); }
+void orc_decode_direction(uint32_t e, float* o) { V3 r = decode_direction(e); o[0] = r.x; o[1] = r.y; o[2] = r.z; }
+void orc_sample_hemisphere(const float* xi, float* o) { V2 x; x.x = xi[0]; x.y = xi[1]; V3 r = sample_hemisphere(x); o[0] = r.x; o[1] = r.y; o[2] = r.z; }
+void orc_sample_sphere(const float* xi, const float* radius, float* o) { V2 x; x.x = xi[0]; x.y = xi[1]; V3 r = sample_sphere(x, v3(radius[0], radius[1], radius[2])); o[0] = r.x; o[1] = r.y; o[2] = r.z; }
+void orc_sample_disk(const float* xi, const float* radius, float* o) { V2 x, rr; x.x = xi[0]; x.y = xi[1]; rr.x = radius[0]; rr.y = radius[1]; V2 r = sample_disk(x, rr); o[0] = r.x; o[1] = r.y; }
+float orc_luminance(const float* c) { return luminance(v3(c[0], c[1], c[2])); }
+void orc_fis_gauss(const float* xi, float* o) { V2 x; x.x = xi[0]; x.y = xi[1]; V2 r = fisGauss(x); o[0] = r.x; o[1] = r.y; }
+uint32_t orc_pack_half2x16(float a, float b) { return packHalf2x16(a, b); }
+void orc_unpack_half2x16(uint32_t p, float* o) { V2 r = unpackHalf2x16(p); o[0] = r.x; o[1] = r.y; }
+void orc_invert_affine(const float* m, float* o) { invert_affine(m, o); }
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+// Watertight triangle test (KAT + parity of the GPU intersector)
+int orc_tri_intersect(const float* o, const float* d, const float* p0, const float* p1, const float* p2, float* tuv)
+{
+  RayPre rp = ray_precompute(v3(d[0], d[1], d[2]));
+  float t, u, v;
+  bool ok = tri_intersect(rp, v3(o[0], o[1], o[2]), v3(p0[0], p0[1], p0[2]), v3(p1[0], p1[1], p1[2]), v3(p2[0], p2[1], p2[2]), t, u, v);
+  if (ok) { tuv[0] = t; tuv[1] = u; tuv[2] = v; }
+  return ok ? 1 : 0;
+}
+
+} // extern "C"
+
+#include "orc_bvh8.h"

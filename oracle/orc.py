@@ -1,0 +1,313 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by
+gatling_b200/."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+
+
+class MaterialDesc(C.Structure):  # GtlcMaterialDesc
+    _fields_ = [("closure", C.c_int32), ("name", C.c_char_p), ("params", C.c_float * 48)]
+
+
+class CameraDesc(C.Structure):  # GtlcCameraDesc
+    _fields_ = [("position", C.c_float * 3), ("forward", C.c_float * 3), ("up", C.c_float * 3), ("vfov", C.c_float),
+                ("fStop", C.c_float), ("focusDistance", C.c_float), ("focalLength", C.c_float), ("clipStart", C.c_float),
+                ("clipEnd", C.c_float), ("exposure", C.c_float)]
+
+
+class RenderSettings(C.Structure):  # GtlcRenderSettings
+    _fields_ = [("clippingPlanes", C.c_int32), ("depthOfField", C.c_int32), ("domeLightCameraVisible", C.c_int32),
+                ("filterImportanceSampling", C.c_int32), ("frame", C.c_float), ("jitteredSampling", C.c_int32),
+                ("lightIntensityMultiplier", C.c_float), ("maxBounces", C.c_uint32), ("maxSampleValue", C.c_float),
+                ("maxVolumeWalkLength", C.c_uint32), ("mediumStackSize", C.c_uint32), ("metersPerSceneUnit", C.c_float),
+                ("nextEventEstimation", C.c_int32), ("progressiveAccumulation", C.c_int32), ("rrBounceOffset", C.c_uint32),
+                ("rrInvMinTermProb", C.c_float), ("spp", C.c_uint32), ("time", C.c_float)]
+
+
+INSTANCE_DTYPE = np.dtype([("vertexBase", "<u4"), ("faceBase", "<u4"), ("faceCount", "<u4"), ("flags", "<u4"),
+                           ("material", "<u4"), ("instanceId", "<i4"), ("objectId", "<i4"), ("pad", "<u4"),
+                           ("objectToWorld", "<f4", 12)])
+assert INSTANCE_DTYPE.itemsize == 80
+
+SPHERE_LIGHT_DTYPE = np.dtype([("pos", "<f4", 3), ("diffuseSpecularPacked", "<u4"), ("baseEmission", "<f4", 3), ("area", "<f4"),
+                               ("radiusXYZ", "<f4", 3), ("padding", "<f4")])
+DISTANT_LIGHT_DTYPE = np.dtype([("direction", "<f4", 3), ("angle", "<f4"), ("baseEmission", "<f4", 3),
+                                ("diffuseSpecularPacked", "<u4"), ("padding", "<f4", 3), ("invPdf", "<f4")])
+RECT_LIGHT_DTYPE = np.dtype([("origin", "<f4", 3), ("width", "<f4"), ("baseEmission", "<f4", 3), ("height", "<f4"),
+                             ("tangentFramePacked", "<u4", 2), ("diffuseSpecularPacked", "<u4"), ("padding", "<f4")])
+DISK_LIGHT_DTYPE = np.dtype([("origin", "<f4", 3), ("radiusX", "<f4"), ("baseEmission", "<f4", 3), ("radiusY", "<f4"),
+                             ("tangentFramePacked", "<u4", 2), ("diffuseSpecularPacked", "<u4"), ("padding", "<f4")])
+for _d in (SPHERE_LIGHT_DTYPE, DISTANT_LIGHT_DTYPE, RECT_LIGHT_DTYPE, DISK_LIGHT_DTYPE):
+    assert _d.itemsize == 48
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("inst", "<u4")])
+
+
+class SceneDescC(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("vertexCount", C.c_uint32),
+                ("faces", C.c_void_p), ("faceCount", C.c_uint32),
+                ("instances", C.c_void_p), ("instanceCount", C.c_uint32),
+                ("materials", C.POINTER(MaterialDesc)), ("materialCount", C.c_uint32),
+                ("sphereLights", C.c_void_p), ("sphereLightCount", C.c_uint32),
+                ("distantLights", C.c_void_p), ("distantLightCount", C.c_uint32),
+                ("rectLights", C.c_void_p), ("rectLightCount", C.c_uint32),
+                ("diskLights", C.c_void_p), ("diskLightCount", C.c_uint32),
+                ("domeTexels", C.c_void_p), ("domeW", C.c_uint32), ("domeH", C.c_uint32),
+                ("domeRotation", C.c_float * 4), ("domeEmission", C.c_float * 3), ("pad", C.c_uint32)]
+
+
+class RenderDescC(C.Structure):
+    _fields_ = [("camera", CameraDesc), ("settings", RenderSettings), ("clearColor", C.c_float * 4),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("sampleOffset", C.c_uint32),
+                ("rowBegin", C.c_uint32), ("rowEnd", C.c_uint32),
+                ("shardRank", C.c_uint32), ("shardCount", C.c_uint32), ("shardTile", C.c_uint32)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        L = _lib
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.POINTER(SceneDescC)]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_render.restype = C.c_double
+        L.orc_render.argtypes = [C.c_void_p, C.POINTER(RenderDescC), C.c_void_p, C.c_void_p]
+        L.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+        L.orc_camera_rays.argtypes = [C.POINTER(RenderDescC), C.c_uint32, C.c_void_p]
+        L.orc_hash_theironborn.restype = C.c_uint32
+        L.orc_hash_theironborn.argtypes = [C.c_uint32]
+        L.orc_hash_pcg32.restype = C.c_uint32
+        L.orc_hash_pcg32.argtypes = [C.POINTER(C.c_uint32)]
+        L.orc_uint_as_float.restype = C.c_float
+        L.orc_uint_as_float.argtypes = [C.c_uint32]
+        L.orc_rng_init.restype = C.c_uint32
+        L.orc_rng_init.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_rng_next1f.restype = C.c_float
+        L.orc_rng_next1f.argtypes = [C.POINTER(C.c_uint32)]
+        L.orc_luminance.restype = C.c_float
+        L.orc_pack_half2x16.restype = C.c_uint32
+        L.orc_pack_half2x16.argtypes = [C.c_float, C.c_float]
+        L.orc_encode_direction.restype = C.c_uint32
+        L.orc_host_encode_direction.restype = C.c_uint32
+        L.orc_num_threads.restype = C.c_int
+        L.orc_tri_intersect.restype = C.c_int
+        if hasattr(L, "orc_bvh8_trace"):
+            L.orc_bvh8_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
+                                         C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def _f3(x):
+    return (C.c_float * 3)(*[float(v) for v in x])
+
+
+def _fa(x, n):
+    a = np.ascontiguousarray(np.asarray(x, np.float32).reshape(n))
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def compose_transform(mesh_xf, inst_xf):
+    """Row-major 3x4 object->world of (mesh.transform, instanceTransform) as Gi.cpp:1191 composes it:
+    world = inst o mesh, i.e. USD row-vector product M_mesh . M_inst.  Evaluated in float64 in a fixed
+    order and rounded once (the product host code does the same)."""
+    a = np.asarray(mesh_xf, np.float32).astype(np.float64)
+    b = np.asarray(inst_xf, np.float32).astype(np.float64)
+    r = a[:, [0]] * b[[0], :]
+    for k in (1, 2, 3):
+        r = r + a[:, [k]] * b[[k], :]
+    g = r.T  # column-vector convention
+    return g[:3, :].astype(np.float32).reshape(12)
+
+
+def pack_half(a):
+    return int(np.float16(a).view(np.uint16))
+
+
+def camera_c(cam) -> CameraDesc:
+    c = CameraDesc()
+    c.position = _f3(cam.position)
+    c.forward = _f3(cam.forward)
+    c.up = _f3(cam.up)
+    for k in ("vfov", "fStop", "focusDistance", "focalLength", "clipStart", "clipEnd", "exposure"):
+        setattr(c, k, float(getattr(cam, k)))
+    return c
+
+
+def settings_c(st) -> RenderSettings:
+    s = RenderSettings()
+    for name, ctype in RenderSettings._fields_:
+        v = getattr(st, name)
+        setattr(s, name, float(v) if ctype is C.c_float else int(v))
+    return s
+
+
+def light_arrays(desc):
+    """Host-side light encoding exactly as Gi.cpp:2573-2941 does it (restated through the oracle's own
+    encoders)."""
+    L = lib()
+    sp = np.zeros(len(desc.sphere_lights), SPHERE_LIGHT_DTYPE)
+    for i, l in enumerate(desc.sphere_lights):
+        rx, ry, rz = [np.float32(v) for v in l.radius]
+        ab = np.float32(np.power(rx * ry, np.float32(1.6)))
+        ac = np.float32(np.power(rx * rz, np.float32(1.6)))
+        bc = np.float32(np.power(ry * rz, np.float32(1.6)))
+        area = np.float32(np.float32(np.power((ab + ac + bc) / np.float32(3.0), np.float32(1.0 / 1.6))) * np.float32(4.0) * np.float32(np.pi))
+        sp[i] = (l.position, L.orc_pack_half2x16(l.diffuse, l.specular), l.base_emission, area, l.radius, 0.0)
+    di = np.zeros(len(desc.distant_lights), DISTANT_LIGHT_DTYPE)
+    for i, l in enumerate(desc.distant_lights):
+        half = np.float32(0.5) * np.float32(l.angle)
+        inv_pdf = np.float32(2.0 * np.pi * (1.0 - np.cos(half, dtype=np.float32))) if half > 0 else np.float32(1.0)
+        di[i] = (l.direction, l.angle, l.base_emission, L.orc_pack_half2x16(l.diffuse, l.specular), (0, 0, 0), inv_pdf)
+    re = np.zeros(len(desc.rect_lights), RECT_LIGHT_DTYPE)
+    for i, l in enumerate(desc.rect_lights):
+        t0 = L.orc_host_encode_direction(_f3(l.t0))
+        t1 = L.orc_host_encode_direction(_f3(l.t1))
+        re[i] = (l.origin, l.width, l.base_emission, l.height, (t0, t1), L.orc_pack_half2x16(l.diffuse, l.specular), 0.0)
+    dk = np.zeros(len(desc.disk_lights), DISK_LIGHT_DTYPE)
+    for i, l in enumerate(desc.disk_lights):
+        t0 = L.orc_host_encode_direction(_f3(l.t0))
+        t1 = L.orc_host_encode_direction(_f3(l.t1))
+        dk[i] = (l.origin, l.radius[0], l.base_emission, l.radius[1], (t0, t1), L.orc_pack_half2x16(l.diffuse, l.specular), 0.0)
+    return sp, di, re, dk
+
+
+class OracleScene:
+    """Flattens a gatling_b200.scenes.SceneDesc and builds the oracle's scene."""
+
+    def __init__(self, desc):
+        self.desc = desc
+        L = lib()
+        verts, faces, inst = [], [], []
+        vbase = fbase = 0
+        for mi, m in enumerate(desc.meshes):
+            verts.append(m.vertices)
+            faces.append(np.ascontiguousarray(m.faces, np.uint32))
+            xfs = m.instance_transforms if m.instance_transforms is not None else np.eye(4, dtype=np.float32)[None]
+            flags = (1 if m.left_handed else 0) | (2 if m.double_sided else 0)
+            for k, ixf in enumerate(xfs):
+                rec = np.zeros(1, INSTANCE_DTYPE)
+                rec["vertexBase"] = vbase
+                rec["faceBase"] = fbase
+                rec["faceCount"] = len(m.faces)
+                rec["flags"] = flags
+                rec["material"] = m.material
+                rec["instanceId"] = k
+                rec["objectId"] = m.object_id
+                rec["objectToWorld"] = compose_transform(m.transform, ixf)
+                inst.append(rec)
+            vbase += len(m.vertices)
+            fbase += len(m.faces)
+        self.vertices = np.ascontiguousarray(np.concatenate(verts))
+        self.faces = np.ascontiguousarray(np.concatenate(faces).reshape(-1, 3))
+        self.instances = np.ascontiguousarray(np.concatenate(inst))
+        self.mats = (MaterialDesc * len(desc.materials))()
+        for i, m in enumerate(desc.materials):
+            self.mats[i].closure = m.closure
+            self.mats[i].name = None
+            self.mats[i].params = (C.c_float * 48)(*[float(x) for x in m.params])
+        self.sp, self.di, self.re, self.dk = light_arrays(desc)
+        d = SceneDescC()
+        d.vertices = self.vertices.ctypes.data
+        d.vertexCount = len(self.vertices)
+        d.faces = self.faces.ctypes.data
+        d.faceCount = len(self.faces)
+        d.instances = self.instances.ctypes.data
+        d.instanceCount = len(self.instances)
+        d.materials = self.mats
+        d.materialCount = len(desc.materials)
+        d.sphereLights = self.sp.ctypes.data if len(self.sp) else None
+        d.sphereLightCount = len(self.sp)
+        d.distantLights = self.di.ctypes.data if len(self.di) else None
+        d.distantLightCount = len(self.di)
+        d.rectLights = self.re.ctypes.data if len(self.re) else None
+        d.rectLightCount = len(self.re)
+        d.diskLights = self.dk.ctypes.data if len(self.dk) else None
+        d.diskLightCount = len(self.dk)
+        if desc.dome_light is not None:
+            self.dome = np.ascontiguousarray(desc.dome_light.texels, np.float32)
+            d.domeTexels = self.dome.ctypes.data
+            d.domeH, d.domeW = self.dome.shape[0], self.dome.shape[1]
+            d.domeRotation = (C.c_float * 4)(*desc.dome_light.rotation)
+            d.domeEmission = (C.c_float * 3)(*desc.dome_light.base_emission)
+        self.handle = L.orc_scene_create(C.byref(d))
+
+    def close(self):
+        if self.handle:
+            lib().orc_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render_desc(self, sample_offset=0, rows=None, shard=None, spp=None) -> RenderDescC:
+        d = self.desc
+        r = RenderDescC()
+        r.camera = camera_c(d.camera)
+        r.settings = settings_c(d.settings)
+        if spp is not None:
+            r.settings.spp = spp
+        r.clearColor = (C.c_float * 4)(*d.clear_color)
+        r.width, r.height = d.width, d.height
+        r.sampleOffset = sample_offset
+        r.rowBegin, r.rowEnd = rows if rows else (0, d.height)
+        r.shardRank, r.shardCount, r.shardTile = shard if shard else (0, 1, 64)
+        return r
+
+    def render(self, sample_offset=0, prev=None, rows=None, shard=None, spp=None):
+        """Returns (rgba float32[h, w, 4] with row 0 = bottom, seconds, (closestRays, shadowRays))."""
+        d = self.desc
+        img = np.zeros((d.height, d.width, 4), np.float32) if prev is None else np.ascontiguousarray(prev, np.float32).copy()
+        counts = np.zeros(2, np.uint64)
+        r = self.render_desc(sample_offset, rows, shard, spp)
+        secs = lib().orc_render(self.handle, C.byref(r), img.ctypes.data, counts.ctypes.data)
+        return img, secs, (int(counts[0]), int(counts[1]))
+
+    def trace(self, rays, any_hit=False):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        lib().orc_trace(self.handle, rays.ctypes.data, len(rays), 1 if any_hit else 0, hits.ctypes.data)
+        return hits
+
+
+def camera_rays(desc, sample_index=0):
+    """(n, 8) float32: ox oy oz rngbits dx dy dz 0 for every pixel (rp_main.rgen:191-271)."""
+    tmp = type("T", (), {})()
+    r = RenderDescC()
+    r.camera = camera_c(desc.camera)
+    r.settings = settings_c(desc.settings)
+    r.clearColor = (C.c_float * 4)(*desc.clear_color)
+    r.width, r.height = desc.width, desc.height
+    out = np.zeros((desc.width * desc.height, 8), np.float32)
+    lib().orc_camera_rays(C.byref(r), sample_index, out.ctypes.data)
+    return out
+
+
+def bvh8_trace(nodes, tris, rays, any_hit=False):
+    """Walks the product's BVH8 bytes with the oracle's restatement of the traversal order; returns
+    (hits, visits[n, 2])."""
+    L = lib()
+    rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    hits = np.zeros(len(rays), HIT_DTYPE)
+    visits = np.zeros((len(rays), 2), np.uint32)
+    L.orc_bvh8_trace(nodes.ctypes.data, len(nodes) // 80, tris.ctypes.data, len(tris) // 12, rays.ctypes.data, len(rays),
+                     1 if any_hit else 0, hits.ctypes.data, visits.ctypes.data)
+    return hits, visits
