@@ -1,0 +1,277 @@
+// Host builder of the compressed BVH8 (see bvh8.h).  Binned-SAH binary BVH (OpenMP tasks) ->
+// greedy surface-area collapse to 8-wide nodes -> octant-aware slot assignment -> quantisation.
+// Stands in for the Vulkan driver's PREFER_FAST_TRACE build the reference requests
+// (/root/reference/src/cgpu/impl/CgpuVk.cpp:2575); a GPU LBVH/PLOC builder is the "next" row 1 of
+// SURVEY.md 8f.
+#include "bvh8.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <deque>
+
+namespace gtlc {
+namespace {
+
+struct Box {
+  float lo[3], hi[3];
+  void reset() { for (int k = 0; k < 3; k++) { lo[k] = 3.402823466e38f; hi[k] = -3.402823466e38f; } }
+  void grow(const float* p) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+  void grow(const Box& b) { for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+  float area() const
+  {
+    float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    if (dx < 0.0f) return 0.0f;
+    return 2.0f * (dx * dy + dy * dz + dz * dx);
+  }
+};
+
+struct BinNode { Box box; uint32_t left, right, first, count; };
+
+constexpr int kBins = 16;
+constexpr uint32_t kMaxLeaf = 3;
+constexpr float kNodeCost = 0.6f;  // relative to one triangle test
+constexpr float kTriCost = 1.0f;
+
+struct Builder {
+  const std::vector<BuildTri>& tris;
+  std::vector<Box> triBox;
+  std::vector<float> cen;  // 3 per tri
+  std::vector<uint32_t> idx;
+  std::vector<BinNode> nodes;
+  std::atomic<uint32_t> nodeCount{ 0 };
+
+  explicit Builder(const std::vector<BuildTri>& t) : tris(t) {}
+
+  void build(uint32_t node, uint32_t begin, uint32_t end)
+  {
+    Box box, cbox;
+    box.reset(); cbox.reset();
+    for (uint32_t i = begin; i < end; i++) {
+      box.grow(triBox[idx[i]]);
+      cbox.grow(&cen[(size_t) idx[i] * 3]);
+    }
+    BinNode& n = nodes[node];
+    n.box = box;
+    uint32_t count = end - begin;
+    auto makeLeaf = [&]() { n.first = begin; n.count = count; n.left = n.right = 0; };
+    if (count == 1) { makeLeaf(); return; }
+
+    // binned SAH over the three axes
+    float bestCost = 3.402823466e38f; int bestAxis = -1; int bestBin = -1;
+    for (int axis = 0; axis < 3; axis++) {
+      float lo = cbox.lo[axis], ext = cbox.hi[axis] - cbox.lo[axis];
+      if (!(ext > 0.0f)) continue;
+      float scale = (float) kBins / ext;
+      Box bb[kBins]; uint32_t bc[kBins];
+      for (int b = 0; b < kBins; b++) { bb[b].reset(); bc[b] = 0; }
+      for (uint32_t i = begin; i < end; i++) {
+        int b = (int) ((cen[(size_t) idx[i] * 3 + axis] - lo) * scale);
+        b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+        bb[b].grow(triBox[idx[i]]); bc[b]++;
+      }
+      float rightArea[kBins]; uint32_t rightCount[kBins];
+      Box acc; acc.reset(); uint32_t c = 0;
+      for (int b = kBins - 1; b > 0; b--) { acc.grow(bb[b]); c += bc[b]; rightArea[b] = acc.area(); rightCount[b] = c; }
+      acc.reset(); c = 0;
+      for (int b = 0; b < kBins - 1; b++) {
+        acc.grow(bb[b]); c += bc[b];
+        if (c == 0 || rightCount[b + 1] == 0) continue;
+        float cost = acc.area() * (float) c + rightArea[b + 1] * (float) rightCount[b + 1];
+        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+      }
+    }
+    uint32_t mid;
+    if (bestAxis < 0) {
+      if (count <= kMaxLeaf) { makeLeaf(); return; }
+      mid = begin + count / 2;  // identical centroids: split by index
+    } else {
+      float area = box.area();
+      float splitCost = kNodeCost * area + kTriCost * bestCost;
+      float leafCost = kTriCost * (float) count * area;
+      if (count <= kMaxLeaf && leafCost <= splitCost) { makeLeaf(); return; }
+      float lo = cbox.lo[bestAxis], scale = (float) kBins / (cbox.hi[bestAxis] - cbox.lo[bestAxis]);
+      auto it = std::partition(idx.begin() + begin, idx.begin() + end, [&](uint32_t t) {
+        int b = (int) ((cen[(size_t) t * 3 + bestAxis] - lo) * scale);
+        b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+        return b <= bestBin;
+      });
+      mid = (uint32_t) (it - idx.begin());
+      if (mid == begin || mid == end) mid = begin + count / 2;
+    }
+    uint32_t l = nodeCount.fetch_add(2);
+    n.left = l; n.right = l + 1; n.count = 0; n.first = 0;
+    if (count > 16384) {
+#pragma omp task default(shared)
+      build(l, begin, mid);
+#pragma omp task default(shared)
+      build(l + 1, mid, end);
+#pragma omp taskwait
+    } else {
+      build(l, begin, mid);
+      build(l + 1, mid, end);
+    }
+  }
+};
+
+struct WideChild { uint32_t bin; bool leaf; };
+
+inline uint32_t floatExponentBits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return (u >> 23) & 0xFFu; }
+
+} // namespace
+
+void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
+{
+  auto t0 = std::chrono::steady_clock::now();
+  out.nodes.clear(); out.tris.clear(); out.maxDepth = 0;
+  const uint32_t N = (uint32_t) tris.size();
+  if (N == 0) {
+    Bvh8Node empty; std::memset(&empty, 0, sizeof(empty));
+    out.nodes.push_back(empty);
+    out.buildSeconds = 0.0;
+    return;
+  }
+  Builder b(tris);
+  b.triBox.resize(N); b.cen.resize((size_t) N * 3); b.idx.resize(N);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t) N; i++) {
+    Box bx; bx.reset();
+    for (int k = 0; k < 3; k++) bx.grow(tris[i].v[k]);
+    b.triBox[i] = bx;
+    for (int k = 0; k < 3; k++) b.cen[(size_t) i * 3 + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
+    b.idx[i] = (uint32_t) i;
+  }
+  b.nodes.resize((size_t) 2 * N);
+  b.nodeCount = 1;
+#pragma omp parallel
+#pragma omp single
+  b.build(0, 0, N);
+
+  // ---- collapse into 8-wide nodes, breadth first -------------------------------------------
+  struct Pending { uint32_t bin, wide, depth; };
+  std::deque<Pending> queue;
+  out.nodes.reserve(N / 4 + 16);
+  out.tris.reserve((size_t) N * 12);
+  out.nodes.emplace_back();
+  queue.push_back({ 0u, 0u, 1u });
+  const std::vector<BinNode>& bn = b.nodes;
+
+  while (!queue.empty()) {
+    Pending cur = queue.front(); queue.pop_front();
+    out.maxDepth = std::max(out.maxDepth, cur.depth);
+    const BinNode& root = bn[cur.bin];
+    WideChild ch[8]; int n = 0;
+    if (root.count > 0) { ch[n++] = { cur.bin, true }; }
+    else {
+      ch[n++] = { root.left, bn[root.left].count > 0 };
+      ch[n++] = { root.right, bn[root.right].count > 0 };
+      while (n < 8) {
+        int best = -1; float bestArea = -1.0f;
+        for (int i = 0; i < n; i++) {
+          if (ch[i].leaf) continue;
+          float a = bn[ch[i].bin].box.area();
+          if (a > bestArea) { bestArea = a; best = i; }
+        }
+        if (best < 0) break;
+        uint32_t l = bn[ch[best].bin].left, r = bn[ch[best].bin].right;
+        ch[best] = { l, bn[l].count > 0 };
+        ch[n++] = { r, bn[r].count > 0 };
+      }
+    }
+    // ---- octant-aware slot assignment (greedy): slot s sits towards the corner whose sign bits are s
+    const Box& pb = root.box;
+    float pc[3] = { 0.5f * (pb.lo[0] + pb.hi[0]), 0.5f * (pb.lo[1] + pb.hi[1]), 0.5f * (pb.lo[2] + pb.hi[2]) };
+    int slotOf[8]; bool slotUsed[8] = { false, false, false, false, false, false, false, false };
+    bool childDone[8] = { false, false, false, false, false, false, false, false };
+    float cost[8][8];
+    for (int i = 0; i < n; i++) {
+      const Box& cb = bn[ch[i].bin].box;
+      float d[3] = { 0.5f * (cb.lo[0] + cb.hi[0]) - pc[0], 0.5f * (cb.lo[1] + cb.hi[1]) - pc[1], 0.5f * (cb.lo[2] + cb.hi[2]) - pc[2] };
+      for (int s = 0; s < 8; s++)
+        cost[i][s] = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
+    }
+    for (int k = 0; k < n; k++) {
+      int bi = -1, bs = -1; float bc = -3.402823466e38f;
+      for (int i = 0; i < n; i++) {
+        if (childDone[i]) continue;
+        for (int s = 0; s < 8; s++) {
+          if (slotUsed[s]) continue;
+          if (cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+        }
+      }
+      slotOf[bi] = bs; childDone[bi] = true; slotUsed[bs] = true;
+    }
+    int childAtSlot[8]; for (int s = 0; s < 8; s++) childAtSlot[s] = -1;
+    for (int i = 0; i < n; i++) childAtSlot[slotOf[i]] = i;
+
+    // ---- quantisation grid ------------------------------------------------------------------
+    uint32_t ebits[3]; double scale[3];
+    for (int k = 0; k < 3; k++) {
+      double ext = (double) pb.hi[k] - (double) pb.lo[k];
+      int e = (ext > 0.0) ? (int) std::ceil(std::log2(ext / 253.0)) : -126;
+      if (e < -126) e = -126;
+      if (e > 127) e = 127;
+      while (ext / std::ldexp(1.0, e) > 253.0 && e < 127) e++;
+      ebits[k] = (uint32_t) (e + 127);
+      scale[k] = std::ldexp(1.0, e);
+    }
+    Bvh8Node node; std::memset(&node, 0, sizeof(node));
+    std::memcpy(&node.w[0], &pb.lo[0], 4); std::memcpy(&node.w[1], &pb.lo[1], 4); std::memcpy(&node.w[2], &pb.lo[2], 4);
+    uint8_t meta[8] = { 0 }; uint8_t q[6][8]; std::memset(q, 0, sizeof(q));
+    uint32_t imask = 0;
+    uint32_t childBase = (uint32_t) out.nodes.size();
+    uint32_t triBase = (uint32_t) (out.tris.size() / 12);
+    uint32_t nInternal = 0, triOffset = 0;
+    for (int s = 0; s < 8; s++) {
+      int i = childAtSlot[s];
+      if (i < 0) continue;
+      const BinNode& c = bn[ch[i].bin];
+      for (int k = 0; k < 3; k++) {
+        double lo = ((double) c.box.lo[k] - (double) pb.lo[k]) / scale[k];
+        double hi = ((double) c.box.hi[k] - (double) pb.lo[k]) / scale[k];
+        double ql = std::floor(lo), qh = std::ceil(hi);
+        if (lo - ql < 1.0 / 64.0 && ql > 0.0) ql -= 1.0;   // safety quantum when the bound sits on a grid line
+        if (qh - hi < 1.0 / 64.0 && qh < 255.0) qh += 1.0;
+        if (ql < 0.0) ql = 0.0;
+        if (qh > 255.0) qh = 255.0;
+        q[k][s] = (uint8_t) ql; q[3 + k][s] = (uint8_t) qh;
+      }
+      if (ch[i].leaf) {
+        uint32_t cnt = c.count;  // 1..3
+        meta[s] = (uint8_t) ((((1u << cnt) - 1u) << 5) | triOffset);
+        for (uint32_t t = 0; t < cnt; t++) {
+          const BuildTri& tr = tris[b.idx[c.first + t]];
+          float rec[12];
+          for (int v = 0; v < 3; v++) { rec[v * 4 + 0] = tr.v[v][0]; rec[v * 4 + 1] = tr.v[v][1]; rec[v * 4 + 2] = tr.v[v][2]; }
+          std::memcpy(&rec[3], &tr.prim, 4); std::memcpy(&rec[7], &tr.inst, 4); rec[11] = 0.0f;
+          out.tris.insert(out.tris.end(), rec, rec + 12);
+        }
+        triOffset += cnt;
+      } else {
+        meta[s] = (uint8_t) (0x20u | (24u + (uint32_t) s));
+        imask |= 1u << s;
+        nInternal++;
+      }
+    }
+    node.w[3] = ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24);
+    node.w[4] = childBase; node.w[5] = triBase;
+    std::memcpy(&node.w[6], meta, 8);
+    std::memcpy(&node.w[8], q[0], 8);  std::memcpy(&node.w[10], q[1], 8);   // qlo_x, qlo_y
+    std::memcpy(&node.w[12], q[2], 8); std::memcpy(&node.w[14], q[3], 8);   // qlo_z, qhi_x
+    std::memcpy(&node.w[16], q[4], 8); std::memcpy(&node.w[18], q[5], 8);   // qhi_y, qhi_z
+    out.nodes[cur.wide] = node;
+    // internal children get consecutive indices in slot order
+    uint32_t next = childBase;
+    out.nodes.resize(out.nodes.size() + nInternal);
+    for (int s = 0; s < 8; s++) {
+      int i = childAtSlot[s];
+      if (i < 0 || ch[i].leaf) continue;
+      queue.push_back({ ch[i].bin, next++, cur.depth + 1 });
+    }
+  }
+  out.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+} // namespace gtlc

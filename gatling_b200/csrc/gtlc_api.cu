@@ -1,0 +1,956 @@
+// C-ABI implementation (include/gtlc.h): object store, scene flattening + BVH8 build/upload, and the
+// host side of the wavefront render loop.  Replaces the bodies of the reference's gi* functions
+// (/root/reference/src/gi/impl/Gi.cpp) and the cgpu/ggpu Vulkan layers underneath them with CUDA
+// runtime calls: cudaMalloc'd SoA queues, one stream, CUDA events for per-kernel timing.
+#include "../../include/gtlc.h"
+#include "bvh8.h"
+#include "wavefront.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+using namespace gtlc;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// error handling (reference: GB_ERROR + GiStatus::Error, no exceptions across the boundary)
+// ---------------------------------------------------------------------------------------------
+std::mutex g_errMutex;
+std::string g_lastError;
+
+void setError(const char* fmt, ...)
+{
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  std::lock_guard<std::mutex> g(g_errMutex);
+  g_lastError = buf;
+  fprintf(stderr, "[gtlc] error: %s\n", buf);
+}
+
+#define CUDA_OK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { setError("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); return false; } } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { TAG_SCENE = 0x53434e45, TAG_MATERIAL = 0x4d41544c, TAG_MESH = 0x4d455348, TAG_SPHERE = 0x5350484c,
+                  TAG_DISTANT = 0x44495354, TAG_RECT = 0x52454354, TAG_DISK = 0x4449534b, TAG_DOME = 0x444f4d45, TAG_RB = 0x52424620 };
+
+struct Object { uint32_t tag; };
+
+struct Scene;
+
+struct Material : Object { Scene* scene; int32_t closure; float params[GTLC_MATERIAL_PARAM_COUNT]; std::string name; };
+
+struct Mesh : Object {
+  Scene* scene;
+  std::vector<GtlcVertex> vertices;
+  std::vector<GtlcFace> faces;
+  std::vector<int32_t> faceIds;
+  int32_t id; bool doubleSided, flipFacing, visible;
+  std::string name;
+  float transform[12];                       // row-major 3x4 (Gi.cpp:641-650)
+  std::vector<float> instanceTransforms;     // 12 per instance
+  std::vector<int32_t> instanceIds;
+  Material* material;
+};
+
+// rp_main.h:73-113, 48 bytes each
+struct SphereLightData { float pos[3]; uint32_t diffuseSpecularPacked; float baseEmission[3]; float area; float radiusXYZ[3]; float padding; };
+struct DistantLightData { float direction[3]; float angle; float baseEmission[3]; uint32_t diffuseSpecularPacked; float padding[3]; float invPdf; };
+struct RectLightData { float origin[3]; float width; float baseEmission[3]; float height; uint32_t tangentFramePacked[2]; uint32_t diffuseSpecularPacked; float padding; };
+struct DiskLightData { float origin[3]; float radiusX; float baseEmission[3]; float radiusY; uint32_t tangentFramePacked[2]; uint32_t diffuseSpecularPacked; float padding; };
+static_assert(sizeof(SphereLightData) == 48 && sizeof(DistantLightData) == 48 && sizeof(RectLightData) == 48 && sizeof(DiskLightData) == 48, "light structs are 48 bytes");
+
+template <typename T> struct Light : Object { Scene* scene; T data; };
+using SphereLight = Light<SphereLightData>;
+using DistantLight = Light<DistantLightData>;
+using RectLight = Light<RectLightData>;
+using DiskLight = Light<DiskLightData>;
+
+struct DomeLight : Object { Scene* scene; uint32_t width, height; std::vector<float> texels; float rotation[4]; float baseEmission[3]; float diffuse, specular; float4* dTexels; };
+
+struct RenderBuffer : Object { uint32_t width, height; int32_t format; size_t size; void* hostMem; void* devMem; };
+
+template <typename T> struct DeviceArray {
+  T* ptr = nullptr; size_t capacity = 0;
+  bool reserve(size_t n) { if (n <= capacity) return true; release(); CUDA_OK(cudaMalloc(&ptr, std::max<size_t>(n, 1) * sizeof(T))); capacity = std::max<size_t>(n, 1); return true; }
+  bool upload(const T* src, size_t n, cudaStream_t st) { if (!reserve(n)) return false; if (n) CUDA_OK(cudaMemcpyAsync(ptr, src, n * sizeof(T), cudaMemcpyHostToDevice, st)); return true; }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; capacity = 0; }
+};
+
+struct Scene : Object {
+  std::mutex mutex;                            // Gi.cpp:224
+  std::unordered_set<Mesh*> meshSet;           // ownership only
+  std::vector<Mesh*> meshes;                   // creation order (deterministic flattening)
+  std::vector<Material*> materials;
+  std::vector<SphereLight*> sphereLights;
+  std::vector<DistantLight*> distantLights;
+  std::vector<RectLight*> rectLights;
+  std::vector<DiskLight*> diskLights;
+  bool geometryDirty = true, lightsDirty = true, materialsDirty = true, framebufferDirty = true;
+  uint32_t sampleOffset = 0;                   // Gi.cpp:230
+  // multi-GPU shard
+  uint32_t shardRank = 0, shardCount = 1, shardTile = 64;
+  // flattened host copies
+  Bvh8 bvh; bool bvhValid = false;
+  std::vector<float> hFverts; std::vector<uint32_t> hFaces;
+  std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo;
+  std::vector<Material*> flatMaterials;
+  // device
+  DeviceArray<uint4> dNodes; DeviceArray<float4> dTris; DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;
+  DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo;
+  DeviceArray<float> dMatParams; DeviceArray<int32_t> dMatClosure; DeviceArray<uint32_t> dMatFlags;
+  DeviceArray<float4> dSphere, dDistant, dRect, dDisk;
+  DeviceArray<uint32_t> dPixelMap; uint32_t pixelMapW = 0, pixelMapH = 0, pixelMapRank = 0, pixelMapCount = 1, pixelMapTile = 0, localPixels = 0;
+  double lastBuildMs = 0.0;
+  GtlcRenderParams oldParams; bool haveOldParams = false; std::vector<GtlcAovBinding> oldBindings;
+};
+
+struct Global {
+  bool initialized = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int smCount = 148;
+  GtlcTuning tuning;
+  GtlcStats stats;
+  // path-state pool
+  size_t poolCapacity = 0;
+  PathQueue q[2];
+  float4* hitTUVP = nullptr; uint32_t* hitInst = nullptr;
+  float4 *shO = nullptr, *shD = nullptr, *shC = nullptr;
+  float4* sampleRad = nullptr;
+  float4* accum = nullptr; size_t accumCapacity = 0;
+  Counters* counters = nullptr;
+  uint32_t* visits = nullptr; size_t visitsCapacity = 0;
+  std::vector<cudaEvent_t> events; size_t eventsUsed = 0;
+  Global() { memset(&tuning, 0, sizeof(tuning)); tuning.maxPathsPerWave = 1u << 24; tuning.sortByMaterial = -1; memset(&stats, 0, sizeof(stats)); memset(q, 0, sizeof(q)); }
+};
+Global g;
+std::mutex g_destroyMutex;   // Gi.cpp:249
+
+template <typename T> T* as(GtlcHandle h, uint32_t tag)
+{
+  Object* o = reinterpret_cast<Object*>(static_cast<uintptr_t>(h));
+  if (!o || o->tag != tag) { if (h) setError("invalid handle (expected tag %08x)", tag); return nullptr; }
+  return static_cast<T*>(o);
+}
+template <typename T> GtlcHandle handleOf(T* p) { return static_cast<GtlcHandle>(reinterpret_cast<uintptr_t>(static_cast<Object*>(p))); }
+
+// ---------------------------------------------------------------------------------------------
+// host encoders: Gi.cpp:287-300, glm::packHalf2x16
+// ---------------------------------------------------------------------------------------------
+uint32_t packUnorm2x16(float x, float y)
+{
+  auto q = [](float v) { v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); return (uint32_t) roundf(v * 65535.0f); };
+  return q(x) | (q(y) << 16);
+}
+uint32_t encodeDirection(const float* d)   // _EncodeDirection, Gi.cpp:294-300
+{
+  float len = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+  float inv = 1.0f / len;
+  float v[3] = { d[0] * inv, d[1] * inv, d[2] * inv };
+  float s = (fabsf(v[0]) + fabsf(v[1])) + fabsf(v[2]);
+  v[0] /= s; v[1] /= s; v[2] /= s;
+  float ex, ey;
+  if (v[2] < 0.0f) { ex = (1.0f - fabsf(v[1])) * (v[0] >= 0.0f ? 1.0f : -1.0f); ey = (1.0f - fabsf(v[0])) * (v[1] >= 0.0f ? 1.0f : -1.0f); }
+  else { ex = v[0]; ey = v[1]; }
+  return packUnorm2x16(ex * 0.5f + 0.5f, ey * 0.5f + 0.5f);
+}
+uint16_t floatToHalf(float f)
+{
+  uint32_t x; memcpy(&x, &f, 4);
+  uint32_t sign = (x >> 16) & 0x8000u, mant = x & 0x007FFFFFu; int32_t exp = (int32_t) ((x >> 23) & 0xFF);
+  if (exp == 255) return (uint16_t) (sign | 0x7C00u | (mant ? 0x200u : 0u));
+  int32_t e = exp - 127 + 15;
+  if (e >= 31) return (uint16_t) (sign | 0x7C00u);
+  if (e <= 0) {
+    if (e < -10) return (uint16_t) sign;
+    mant |= 0x00800000u;
+    uint32_t shift = (uint32_t) (14 - e), h = mant >> shift, rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1u))) h++;
+    return (uint16_t) (sign | h);
+  }
+  uint32_t h = ((uint32_t) e << 10) | (mant >> 13), rem = mant & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+  return (uint16_t) (sign | h);
+}
+uint32_t packHalf2x16(float a, float b) { return (uint32_t) floatToHalf(a) | ((uint32_t) floatToHalf(b) << 16); }
+
+// USD row-major float[16] (row-vector convention) -> row-major 3x4 for column vectors (Gi.cpp:641-650)
+void usdToRow3x4(const float* m, float* out)
+{
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) out[r * 4 + c] = m[c * 4 + r];
+}
+// world = instance o mesh (Gi.cpp:1191), evaluated in float64 in a fixed order, rounded once
+void composeTransforms(const float* meshT, const float* instT, float* out)
+{
+  double a[16], b[16], r[16];
+  auto expand = [](const float* t, double* m) { for (int i = 0; i < 12; i++) m[i] = t[i]; m[12] = m[13] = m[14] = 0.0; m[15] = 1.0; };
+  expand(instT, a); expand(meshT, b);   // column-vector convention: world = I * M
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+    double s = a[i * 4 + 0] * b[0 * 4 + j];
+    s = s + a[i * 4 + 1] * b[1 * 4 + j];
+    s = s + a[i * 4 + 2] * b[2 * 4 + j];
+    s = s + a[i * 4 + 3] * b[3 * 4 + j];
+    r[i * 4 + j] = s;
+  }
+  for (int i = 0; i < 12; i++) out[i] = (float) r[i];
+}
+void invertAffine(const float* m, float* out)
+{
+  double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], gg = m[8], h = m[9], i = m[10];
+  double A = e * i - f * h, B = -(d * i - f * gg), C = d * h - e * gg;
+  double det = a * A + b * B + c * C;
+  double id = 1.0 / det;
+  double r[9] = { A * id, -(b * i - c * h) * id, (b * f - c * e) * id,
+                  B * id, (a * i - c * gg) * id, -(a * f - c * d) * id,
+                  C * id, -(a * h - b * gg) * id, (a * e - b * d) * id };
+  double tx = m[3], ty = m[7], tz = m[11];
+  for (int k = 0; k < 3; k++) {
+    out[k * 4 + 0] = (float) r[k * 3 + 0]; out[k * 4 + 1] = (float) r[k * 3 + 1]; out[k * 4 + 2] = (float) r[k * 3 + 2];
+    out[k * 4 + 3] = (float) (-(r[k * 3 + 0] * tx + r[k * 3 + 1] * ty + r[k * 3 + 2] * tz));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene flattening + BVH8 (replaces _giBuildGeometryStructures/_giCreateBvh, Gi.cpp:784-1315)
+// ---------------------------------------------------------------------------------------------
+bool buildHostGeometry(Scene* s)
+{
+  auto t0 = std::chrono::steady_clock::now();
+  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->flatMaterials.clear();
+  std::vector<BuildTri> tris;
+  size_t totalTris = 0;
+  for (Mesh* m : s->meshes) if (m->visible && m->material) totalTris += m->faces.size() * (m->instanceTransforms.size() / 12);
+  tris.reserve(totalTris);
+  for (Mesh* m : s->meshes) {
+    if (!m->visible) continue;                                          // Gi.cpp:801-804
+    if (!m->material) { setError("invalid BLAS material (mesh '%s' has no material)", m->name.c_str()); continue; }   // Gi.cpp:819-823
+    if (m->faces.empty()) continue;                                     // Gi.cpp:833-836
+    uint32_t matIndex = 0;
+    for (; matIndex < s->flatMaterials.size(); matIndex++) if (s->flatMaterials[matIndex] == m->material) break;
+    if (matIndex == s->flatMaterials.size()) s->flatMaterials.push_back(m->material);
+    const uint32_t vertexBase = (uint32_t) (s->hFverts.size() / 8);
+    const uint32_t faceBase = (uint32_t) (s->hFaces.size() / 3);
+    for (const GtlcVertex& v : m->vertices) {                           // FVertex packing, Gi.cpp:845-859
+      uint32_t en = encodeDirection(v.norm), et = encodeDirection(v.tangent);
+      float f[8] = { v.pos[0], v.pos[1], v.pos[2], v.bitangentSign, 0.0f, 0.0f, v.u, v.v };
+      memcpy(&f[4], &en, 4); memcpy(&f[5], &et, 4);
+      s->hFverts.insert(s->hFverts.end(), f, f + 8);
+    }
+    for (const GtlcFace& f : m->faces) { s->hFaces.push_back(f.v_i[0]); s->hFaces.push_back(f.v_i[1]); s->hFaces.push_back(f.v_i[2]); }
+    const uint32_t flags = (m->flipFacing ? 1u : 0u) | (m->doubleSided ? 2u : 0u);   // Gi.cpp:1135-1143
+    const size_t instCount = m->instanceTransforms.size() / 12;
+    for (size_t k = 0; k < instCount; k++) {                            // Gi.cpp:1188-1202
+      float o2w[12], w2o[12];
+      composeTransforms(m->transform, &m->instanceTransforms[k * 12], o2w);
+      invertAffine(o2w, w2o);
+      const uint32_t inst = (uint32_t) s->hInstInfo.size();
+      s->hO2W.insert(s->hO2W.end(), o2w, o2w + 12);
+      s->hW2O.insert(s->hW2O.end(), w2o, w2o + 12);
+      s->hInstInfo.push_back({ vertexBase, faceBase, flags, matIndex });
+      for (uint32_t f = 0; f < m->faces.size(); f++) {
+        BuildTri t; t.prim = f; t.inst = inst;
+        for (int c = 0; c < 3; c++) {
+          const float* p = m->vertices[m->faces[f].v_i[c]].pos;
+          t.v[c][0] = ((o2w[0] * p[0] + o2w[1] * p[1]) + o2w[2] * p[2]) + o2w[3];
+          t.v[c][1] = ((o2w[4] * p[0] + o2w[5] * p[1]) + o2w[6] * p[2]) + o2w[7];
+          t.v[c][2] = ((o2w[8] * p[0] + o2w[9] * p[1]) + o2w[10] * p[2]) + o2w[11];
+        }
+        tris.push_back(t);
+      }
+    }
+  }
+  bvh8_build(tris, s->bvh);
+  if (s->bvh.maxDepth > (uint32_t) kStackSize) { setError("BVH8 depth %u exceeds traversal stack %d", s->bvh.maxDepth, kStackSize); return false; }
+  s->bvhValid = true;
+  s->lastBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return true;
+}
+
+bool uploadGeometry(Scene* s)
+{
+  cudaStream_t st = g.stream;
+  auto t0 = std::chrono::steady_clock::now();
+  if (!s->dNodes.upload((const uint4*) s->bvh.nodes.data(), s->bvh.nodes.size() * 5, st)) return false;
+  if (!s->dTris.upload((const float4*) s->bvh.tris.data(), s->bvh.tris.size() / 4, st)) return false;
+  if (!s->dFverts.upload((const float4*) s->hFverts.data(), s->hFverts.size() / 4, st)) return false;
+  if (!s->dFaces.upload(s->hFaces.data(), s->hFaces.size(), st)) return false;
+  if (!s->dO2W.upload((const float4*) s->hO2W.data(), s->hO2W.size() / 4, st)) return false;
+  if (!s->dW2O.upload((const float4*) s->hW2O.data(), s->hW2O.size() / 4, st)) return false;
+  if (!s->dInstInfo.upload(s->hInstInfo.data(), s->hInstInfo.size(), st)) return false;
+  CUDA_OK(cudaStreamSynchronize(st));
+  s->lastBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return true;
+}
+
+bool uploadMaterials(Scene* s)
+{
+  std::vector<float> params; std::vector<int32_t> closure; std::vector<uint32_t> flags;
+  for (Material* m : s->flatMaterials) {
+    params.insert(params.end(), m->params, m->params + GTLC_MATERIAL_PARAM_COUNT);
+    closure.push_back(m->closure);
+    flags.push_back((mat_is_emissive(m->closure, m->params) ? kMatFlagEmissive : 0u) | (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u));
+  }
+  if (!s->dMatParams.upload(params.data(), params.size(), g.stream)) return false;
+  if (!s->dMatClosure.upload(closure.data(), closure.size(), g.stream)) return false;
+  if (!s->dMatFlags.upload(flags.data(), flags.size(), g.stream)) return false;
+  CUDA_OK(cudaStreamSynchronize(g.stream));
+  return true;
+}
+
+template <typename L, typename D> bool uploadLightArray(const std::vector<L*>& lights, DeviceArray<float4>& dst)
+{
+  std::vector<D> host; host.reserve(lights.size());
+  for (L* l : lights) host.push_back(l->data);
+  return dst.upload((const float4*) host.data(), host.size() * 3, g.stream);
+}
+bool uploadLights(Scene* s)
+{
+  if (!uploadLightArray<SphereLight, SphereLightData>(s->sphereLights, s->dSphere)) return false;
+  if (!uploadLightArray<DistantLight, DistantLightData>(s->distantLights, s->dDistant)) return false;
+  if (!uploadLightArray<RectLight, RectLightData>(s->rectLights, s->dRect)) return false;
+  if (!uploadLightArray<DiskLight, DiskLightData>(s->diskLights, s->dDisk)) return false;
+  CUDA_OK(cudaStreamSynchronize(g.stream));
+  return true;
+}
+
+bool ensurePool(size_t capacity)
+{
+  if (capacity <= g.poolCapacity) return true;
+  auto freeQ = [](PathQueue& q) { cudaFree(q.rayO); cudaFree(q.rayD); cudaFree(q.thr); cudaFree(q.rad); cudaFree(q.slot); memset(&q, 0, sizeof(q)); };
+  freeQ(g.q[0]); freeQ(g.q[1]);
+  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.sampleRad);
+  g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.sampleRad = nullptr; g.poolCapacity = 0;
+  for (int k = 0; k < 2; k++) {
+    CUDA_OK(cudaMalloc(&g.q[k].rayO, capacity * 16)); CUDA_OK(cudaMalloc(&g.q[k].rayD, capacity * 16));
+    CUDA_OK(cudaMalloc(&g.q[k].thr, capacity * 16)); CUDA_OK(cudaMalloc(&g.q[k].rad, capacity * 16));
+    CUDA_OK(cudaMalloc(&g.q[k].slot, capacity * 4));
+  }
+  CUDA_OK(cudaMalloc(&g.hitTUVP, capacity * 16)); CUDA_OK(cudaMalloc(&g.hitInst, capacity * 4));
+  CUDA_OK(cudaMalloc(&g.shO, capacity * 16)); CUDA_OK(cudaMalloc(&g.shD, capacity * 16)); CUDA_OK(cudaMalloc(&g.shC, capacity * 16));
+  CUDA_OK(cudaMalloc(&g.sampleRad, capacity * 16));
+  g.poolCapacity = capacity;
+  return true;
+}
+
+cudaEvent_t nextEvent()
+{
+  if (g.eventsUsed == g.events.size()) { cudaEvent_t e; cudaEventCreate(&e); g.events.push_back(e); }
+  return g.events[g.eventsUsed++];
+}
+
+struct TimedSpan { cudaEvent_t a, b; int kind; };
+enum { K_RAYGEN, K_TRACE, K_SHADE, K_SHADOW, K_RESOLVE, K_SORT, K_COUNT };
+
+bool requireInit()
+{
+  if (!g.initialized) { setError("gtlc_initialize() has not been called (or failed: no CUDA device) -- there is no CPU fallback"); return false; }
+  return true;
+}
+
+bool buildPixelMap(Scene* s, uint32_t W, uint32_t H)
+{
+  if (s->shardCount <= 1) { s->localPixels = W * H; s->pixelMapCount = 1; s->pixelMapW = W; s->pixelMapH = H; return true; }
+  if (s->pixelMapW == W && s->pixelMapH == H && s->pixelMapRank == s->shardRank && s->pixelMapCount == s->shardCount && s->pixelMapTile == s->shardTile) return true;
+  std::vector<uint32_t> map;
+  const uint32_t T = s->shardTile, tilesX = (W + T - 1) / T;
+  for (uint32_t y = 0; y < H; y++) for (uint32_t x = 0; x < W; x++) {
+    uint32_t tile = (y / T) * tilesX + (x / T);
+    if (tile % s->shardCount == s->shardRank) map.push_back(x + y * W);
+  }
+  if (!s->dPixelMap.upload(map.data(), map.size(), g.stream)) return false;
+  CUDA_OK(cudaStreamSynchronize(g.stream));
+  s->localPixels = (uint32_t) map.size();
+  s->pixelMapW = W; s->pixelMapH = H; s->pixelMapRank = s->shardRank; s->pixelMapCount = s->shardCount; s->pixelMapTile = s->shardTile;
+  return true;
+}
+
+TraceParams makeTraceParams(Scene* s)
+{
+  TraceParams P; memset(&P, 0, sizeof(P));
+  P.nodes = s->dNodes.ptr; P.tris = s->dTris.ptr;
+  P.stats = g.counters->stats;
+  return P;
+}
+
+template <int MODE> void launchTrace(const TraceParams& P, bool count, int blocks)
+{
+  if (count) trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+  else trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+}
+
+// _CalcDirtyFlagsForRenderParams (Gi.cpp:1859-1987), reduced to "does the accumulated image survive?"
+bool paramsResetAccumulation(Scene* s, const GtlcRenderParams* p)
+{
+  if (!s->haveOldParams) return true;
+  const GtlcRenderParams& o = s->oldParams;
+  if (memcmp(&o.camera, &p->camera, sizeof(GtlcCameraDesc)) != 0) return true;
+  GtlcRenderSettings a = o.renderSettings, b = p->renderSettings;
+  a.spp = b.spp = 0;   // the sample count per call does not invalidate the image
+  if (memcmp(&a, &b, sizeof(a)) != 0) return true;
+  if (o.domeLight != p->domeLight) return true;
+  if (s->oldBindings.size() != p->aovBindingCount) return true;
+  for (uint32_t i = 0; i < p->aovBindingCount; i++) {
+    const GtlcAovBinding &x = s->oldBindings[i], &y = p->aovBindings[i];
+    if (x.aovId != y.aovId || x.renderBuffer != y.renderBuffer || memcmp(x.clearValue, y.clearValue, 16) != 0) return true;
+  }
+  return false;
+}
+
+} // namespace
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" {
+
+const char* gtlc_last_error(void) { std::lock_guard<std::mutex> l(g_errMutex); static thread_local std::string copy; copy = g_lastError; return copy.c_str(); }
+
+void gtlc_material_desc_defaults(int32_t closure, GtlcMaterialDesc* d)
+{
+  memset(d, 0, sizeof(*d)); d->closure = closure;
+  float* p = d->params;
+  if (closure == GTLC_CLOSURE_DIFFUSE) { p[0] = p[1] = p[2] = 0.8f; }
+  else if (closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) {   // UsdPreviewSurface specification defaults
+    p[GTLC_UPS_DIFFUSE_R] = p[GTLC_UPS_DIFFUSE_G] = p[GTLC_UPS_DIFFUSE_B] = 0.18f;
+    p[GTLC_UPS_ROUGHNESS] = 0.5f; p[GTLC_UPS_CLEARCOAT_ROUGHNESS] = 0.01f; p[GTLC_UPS_OPACITY] = 1.0f; p[GTLC_UPS_IOR] = 1.5f;
+  } else if (closure == GTLC_CLOSURE_OPENPBR) {             // open_pbr_surface.mtlx:11-84
+    p[GTLC_OPBR_BASE_WEIGHT] = 1.0f; p[GTLC_OPBR_BASE_COLOR_R] = p[GTLC_OPBR_BASE_COLOR_G] = p[GTLC_OPBR_BASE_COLOR_B] = 0.8f;
+    p[GTLC_OPBR_SPECULAR_WEIGHT] = 1.0f; p[GTLC_OPBR_SPECULAR_COLOR_R] = p[GTLC_OPBR_SPECULAR_COLOR_G] = p[GTLC_OPBR_SPECULAR_COLOR_B] = 1.0f;
+    p[GTLC_OPBR_SPECULAR_ROUGHNESS] = 0.3f; p[GTLC_OPBR_SPECULAR_IOR] = 1.5f;
+    p[GTLC_OPBR_TRANSMISSION_COLOR_R] = p[GTLC_OPBR_TRANSMISSION_COLOR_G] = p[GTLC_OPBR_TRANSMISSION_COLOR_B] = 1.0f;
+    p[GTLC_OPBR_COAT_COLOR_R] = p[GTLC_OPBR_COAT_COLOR_G] = p[GTLC_OPBR_COAT_COLOR_B] = 1.0f; p[GTLC_OPBR_COAT_IOR] = 1.6f; p[GTLC_OPBR_COAT_DARKENING] = 1.0f;
+    p[GTLC_OPBR_FUZZ_COLOR_R] = p[GTLC_OPBR_FUZZ_COLOR_G] = p[GTLC_OPBR_FUZZ_COLOR_B] = 1.0f; p[GTLC_OPBR_FUZZ_ROUGHNESS] = 0.5f;
+    p[GTLC_OPBR_EMISSION_COLOR_R] = p[GTLC_OPBR_EMISSION_COLOR_G] = p[GTLC_OPBR_EMISSION_COLOR_B] = 1.0f;
+    p[GTLC_OPBR_THIN_FILM_THICKNESS] = 0.5f; p[GTLC_OPBR_THIN_FILM_IOR] = 1.4f; p[GTLC_OPBR_GEOMETRY_OPACITY] = 1.0f;
+    p[GTLC_OPBR_SUBSURFACE_COLOR_R] = p[GTLC_OPBR_SUBSURFACE_COLOR_G] = p[GTLC_OPBR_SUBSURFACE_COLOR_B] = 0.8f;
+  }
+}
+
+int gtlc_initialize(const GtlcInitParams* params)
+{
+  if (g.initialized) return GTLC_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) { setError("no CUDA device available (%s); the B200 path has no CPU fallback", cudaGetErrorString(e)); return GTLC_ERROR; }
+  int dev = params ? params->deviceIndex : -1;
+  if (dev < 0) { const char* lr = getenv("LOCAL_RANK"); dev = lr ? atoi(lr) % count : 0; }
+  if (dev >= count) { setError("device index %d out of range (%d devices)", dev, count); return GTLC_ERROR; }
+  if (cudaSetDevice(dev) != cudaSuccess) { setError("cudaSetDevice(%d) failed", dev); return GTLC_ERROR; }
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev);
+  g.device = dev; g.smCount = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking) != cudaSuccess) { setError("cudaStreamCreate failed"); return GTLC_ERROR; }
+  if (cudaMalloc(&g.counters, sizeof(Counters)) != cudaSuccess) { setError("cudaMalloc(counters) failed"); return GTLC_ERROR; }
+  cudaMemset(g.counters, 0, sizeof(Counters));
+  g.initialized = true;
+  return GTLC_OK;
+}
+
+void gtlc_terminate(void)
+{
+  if (!g.initialized) return;
+  cudaSetDevice(g.device);
+  cudaDeviceSynchronize();
+  for (int k = 0; k < 2; k++) { cudaFree(g.q[k].rayO); cudaFree(g.q[k].rayD); cudaFree(g.q[k].thr); cudaFree(g.q[k].rad); cudaFree(g.q[k].slot); }
+  memset(g.q, 0, sizeof(g.q));
+  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits);
+  g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.sampleRad = nullptr; g.accum = nullptr; g.counters = nullptr; g.visits = nullptr;
+  g.poolCapacity = 0; g.accumCapacity = 0; g.visitsCapacity = 0;
+  for (cudaEvent_t e : g.events) cudaEventDestroy(e);
+  g.events.clear(); g.eventsUsed = 0;
+  cudaStreamDestroy(g.stream); g.stream = nullptr;
+  g.initialized = false;
+}
+
+void gtlc_set_tuning(const GtlcTuning* t) { if (t) { g.tuning = *t; if (g.tuning.maxPathsPerWave == 0) g.tuning.maxPathsPerWave = 1u << 24; } }
+void gtlc_get_tuning(GtlcTuning* t) { if (t) *t = g.tuning; }
+void gtlc_get_stats(GtlcStats* s) { if (s) *s = g.stats; }
+
+// ---- scene ---------------------------------------------------------------------------------
+GtlcHandle gtlc_scene_create(void) { Scene* s = new Scene(); s->tag = TAG_SCENE; return handleOf(s); }
+
+void gtlc_scene_destroy(GtlcHandle h)
+{
+  Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
+  if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
+  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release();
+  s->dMatParams.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
+  s->tag = 0;
+  delete s;
+}
+
+void gtlc_scene_set_shard(GtlcHandle h, uint32_t rank, uint32_t worldSize, uint32_t tileSize)
+{
+  Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
+  std::lock_guard<std::mutex> l(s->mutex);
+  s->shardRank = rank; s->shardCount = worldSize ? worldSize : 1; s->shardTile = tileSize ? tileSize : 64;
+  s->framebufferDirty = true;
+}
+
+// ---- materials -----------------------------------------------------------------------------
+GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
+{
+  Scene* s = as<Scene>(sh, TAG_SCENE); if (!s || !d) return 0;
+  if (d->closure < GTLC_CLOSURE_DIFFUSE || d->closure > GTLC_CLOSURE_OPENPBR) { setError("unknown closure %d", d->closure); return 0; }
+  Material* m = new Material(); m->tag = TAG_MATERIAL; m->scene = s; m->closure = d->closure; memcpy(m->params, d->params, sizeof(m->params));
+  if (d->name) m->name = d->name;
+  std::lock_guard<std::mutex> l(s->mutex);
+  s->materials.push_back(m);
+  return handleOf(m);
+}
+void gtlc_material_destroy(GtlcHandle h)
+{
+  Material* m = as<Material>(h, TAG_MATERIAL); if (!m) return;
+  std::lock_guard<std::mutex> dl(g_destroyMutex);
+  Scene* s = m->scene;
+  {
+    std::lock_guard<std::mutex> l(s->mutex);
+    s->materials.erase(std::remove(s->materials.begin(), s->materials.end(), m), s->materials.end());
+    for (Mesh* mesh : s->meshes) if (mesh->material == m) mesh->material = nullptr;
+    s->geometryDirty = true; s->framebufferDirty = true;
+  }
+  m->tag = 0; delete m;
+}
+
+// ---- meshes --------------------------------------------------------------------------------
+GtlcHandle gtlc_mesh_create(GtlcHandle sh, const GtlcMeshDesc* d)
+{
+  Scene* s = as<Scene>(sh, TAG_SCENE); if (!s || !d) return 0;
+  if (d->faceCount && (!d->faces || !d->vertices)) { setError("gtlc_mesh_create: null geometry"); return 0; }
+  for (uint32_t f = 0; f < d->faceCount; f++) for (int c = 0; c < 3; c++)
+    if (d->faces[f].v_i[c] >= d->vertexCount) { setError("gtlc_mesh_create: face %u references vertex %u >= %u", f, d->faces[f].v_i[c], d->vertexCount); return 0; }
+  Mesh* m = new Mesh(); m->tag = TAG_MESH; m->scene = s;
+  m->vertices.assign(d->vertices, d->vertices + d->vertexCount);      // giCreateMesh copies (Gi.cpp:620-631)
+  m->faces.assign(d->faces, d->faces + d->faceCount);
+  if (d->faceIds) m->faceIds.assign(d->faceIds, d->faceIds + d->faceCount);
+  m->id = d->id; m->doubleSided = d->isDoubleSided != 0; m->flipFacing = d->isLeftHanded != 0; m->visible = true;
+  if (d->name) m->name = d->name;
+  const float ident[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+  memcpy(m->transform, ident, sizeof(ident));
+  m->instanceTransforms.assign(ident, ident + 12);
+  m->instanceIds.assign(1, 0);
+  m->material = nullptr;
+  std::lock_guard<std::mutex> l(s->mutex);
+  s->meshSet.insert(m); s->meshes.push_back(m);
+  s->geometryDirty = true; s->framebufferDirty = true;
+  return handleOf(m);
+}
+void gtlc_mesh_set_transform(GtlcHandle h, const float* m16)
+{
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m || !m16) return;
+  std::lock_guard<std::mutex> l(m->scene->mutex);
+  usdToRow3x4(m16, m->transform);
+  m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
+}
+void gtlc_mesh_set_instance_transforms(GtlcHandle h, uint32_t count, const float* t16)
+{
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  std::lock_guard<std::mutex> l(m->scene->mutex);
+  m->instanceTransforms.resize((size_t) count * 12);
+  for (uint32_t i = 0; i < count; i++) usdToRow3x4(t16 + (size_t) i * 16, &m->instanceTransforms[(size_t) i * 12]);
+  if (m->instanceIds.size() != count) { m->instanceIds.resize(count); for (uint32_t i = 0; i < count; i++) m->instanceIds[i] = (int32_t) i; }
+  m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
+}
+void gtlc_mesh_set_instance_ids(GtlcHandle h, uint32_t count, const int32_t* ids)
+{
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  std::lock_guard<std::mutex> l(m->scene->mutex);
+  m->instanceIds.assign(ids, ids + count);
+  m->scene->framebufferDirty = true;
+}
+void gtlc_mesh_set_material(GtlcHandle h, GtlcHandle mat)
+{
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  Material* mm = mat ? as<Material>(mat, TAG_MATERIAL) : nullptr;
+  std::lock_guard<std::mutex> l(m->scene->mutex);
+  m->material = mm;
+  m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
+}
+void gtlc_mesh_set_visibility(GtlcHandle h, int32_t visible)
+{
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  std::lock_guard<std::mutex> l(m->scene->mutex);
+  m->visible = visible != 0;
+  m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
+}
+void gtlc_mesh_destroy(GtlcHandle h)
+{
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  std::lock_guard<std::mutex> dl(g_destroyMutex);
+  Scene* s = m->scene;
+  {
+    std::lock_guard<std::mutex> l(s->mutex);
+    s->meshSet.erase(m);
+    s->meshes.erase(std::remove(s->meshes.begin(), s->meshes.end(), m), s->meshes.end());
+    s->geometryDirty = true; s->framebufferDirty = true;
+  }
+  m->tag = 0; delete m;
+}
+
+// ---- lights (Gi.cpp:2573-2941) ---------------------------------------------------------------
+#define LIGHT_COMMON(TYPE, TAGV, VEC)                                                                        \
+  static TYPE* new_##TYPE(Scene* s) { TYPE* l = new TYPE(); l->tag = TAGV; l->scene = s; memset(&l->data, 0, sizeof(l->data)); return l; } \
+  static void destroy_##TYPE(Scene* s, TYPE* l) { std::lock_guard<std::mutex> g2(s->mutex); s->VEC.erase(std::remove(s->VEC.begin(), s->VEC.end(), l), s->VEC.end()); s->lightsDirty = true; s->framebufferDirty = true; l->tag = 0; delete l; }
+LIGHT_COMMON(SphereLight, TAG_SPHERE, sphereLights)
+LIGHT_COMMON(DistantLight, TAG_DISTANT, distantLights)
+LIGHT_COMMON(RectLight, TAG_RECT, rectLights)
+LIGHT_COMMON(DiskLight, TAG_DISK, diskLights)
+#define TOUCH(l) do { std::lock_guard<std::mutex> g2((l)->scene->mutex); (l)->scene->lightsDirty = true; (l)->scene->framebufferDirty = true; } while (0)
+
+GtlcHandle gtlc_sphere_light_create(GtlcHandle sh)
+{
+  Scene* s = as<Scene>(sh, TAG_SCENE); if (!s) return 0;
+  SphereLight* l = new_SphereLight(s);                                  // defaults Gi.cpp:2584-2594
+  l->data.diffuseSpecularPacked = packHalf2x16(1.0f, 1.0f); l->data.area = 1.0f;
+  l->data.radiusXYZ[0] = l->data.radiusXYZ[1] = l->data.radiusXYZ[2] = 0.5f;
+  std::lock_guard<std::mutex> g2(s->mutex); s->sphereLights.push_back(l); s->lightsDirty = true; s->framebufferDirty = true;
+  return handleOf(l);
+}
+void gtlc_sphere_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (s && l) destroy_SphereLight(s, l); }
+void gtlc_sphere_light_set_position(GtlcHandle h, const float* p) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return; memcpy(l->data.pos, p, 12); TOUCH(l); }
+void gtlc_sphere_light_set_base_emission(GtlcHandle h, const float* c) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_sphere_light_set_radius(GtlcHandle h, float rx, float ry, float rz)
+{
+  SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return;
+  float ab = powf(rx * ry, 1.6f), ac = powf(rx * rz, 1.6f), bc = powf(ry * rz, 1.6f);    // Knud Thomsen, Gi.cpp:2637-2640
+  float area = float(powf((ab + ac + bc) / 3.0f, 1.0f / 1.6f) * 4.0f * M_PI);
+  l->data.radiusXYZ[0] = rx; l->data.radiusXYZ[1] = ry; l->data.radiusXYZ[2] = rz; l->data.area = area; TOUCH(l);
+}
+void gtlc_sphere_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+
+GtlcHandle gtlc_distant_light_create(GtlcHandle sh)
+{
+  Scene* s = as<Scene>(sh, TAG_SCENE); if (!s) return 0;
+  DistantLight* l = new_DistantLight(s);                                // Gi.cpp:2680-2688
+  l->data.diffuseSpecularPacked = packHalf2x16(1.0f, 1.0f); l->data.invPdf = 1.0f;
+  std::lock_guard<std::mutex> g2(s->mutex); s->distantLights.push_back(l); s->lightsDirty = true; s->framebufferDirty = true;
+  return handleOf(l);
+}
+void gtlc_distant_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (s && l) destroy_DistantLight(s, l); }
+void gtlc_distant_light_set_direction(GtlcHandle h, const float* d) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return; memcpy(l->data.direction, d, 12); TOUCH(l); }
+void gtlc_distant_light_set_base_emission(GtlcHandle h, const float* c) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_distant_light_set_angle(GtlcHandle h, float angle)
+{
+  DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return;
+  float halfAngle = 0.5f * angle;                                       // Gi.cpp:2723-2726
+  float invPdf = (halfAngle > 0.0f) ? float(2.0f * M_PI * (1.0f - cosf(halfAngle))) : 1.0f;
+  l->data.angle = angle; l->data.invPdf = invPdf; TOUCH(l);
+}
+void gtlc_distant_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+
+GtlcHandle gtlc_rect_light_create(GtlcHandle sh)
+{
+  Scene* s = as<Scene>(sh, TAG_SCENE); if (!s) return 0;
+  RectLight* l = new_RectLight(s);                                      // Gi.cpp:2757-2771
+  const float t0[3] = { 1, 0, 0 }, t1[3] = { 0, 1, 0 };
+  l->data.width = 1.0f; l->data.height = 1.0f; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1);
+  l->data.diffuseSpecularPacked = packHalf2x16(1.0f, 1.0f);
+  std::lock_guard<std::mutex> g2(s->mutex); s->rectLights.push_back(l); s->lightsDirty = true; s->framebufferDirty = true;
+  return handleOf(l);
+}
+void gtlc_rect_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); RectLight* l = as<RectLight>(h, TAG_RECT); if (s && l) destroy_RectLight(s, l); }
+void gtlc_rect_light_set_origin(GtlcHandle h, const float* o) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
+void gtlc_rect_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
+void gtlc_rect_light_set_base_emission(GtlcHandle h, const float* c) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_rect_light_set_dimensions(GtlcHandle h, float w, float hh) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.width = w; l->data.height = hh; TOUCH(l); }
+void gtlc_rect_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+
+GtlcHandle gtlc_disk_light_create(GtlcHandle sh)
+{
+  Scene* s = as<Scene>(sh, TAG_SCENE); if (!s) return 0;
+  DiskLight* l = new_DiskLight(s);                                      // Gi.cpp:2852-2866
+  const float t0[3] = { 1, 0, 0 }, t1[3] = { 0, 1, 0 };
+  l->data.radiusX = 0.5f; l->data.radiusY = 0.5f; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1);
+  l->data.diffuseSpecularPacked = packHalf2x16(1.0f, 1.0f);
+  std::lock_guard<std::mutex> g2(s->mutex); s->diskLights.push_back(l); s->lightsDirty = true; s->framebufferDirty = true;
+  return handleOf(l);
+}
+void gtlc_disk_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); DiskLight* l = as<DiskLight>(h, TAG_DISK); if (s && l) destroy_DiskLight(s, l); }
+void gtlc_disk_light_set_origin(GtlcHandle h, const float* o) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
+void gtlc_disk_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
+void gtlc_disk_light_set_base_emission(GtlcHandle h, const float* c) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_disk_light_set_radius(GtlcHandle h, float rx, float ry) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.radiusX = rx; l->data.radiusY = ry; TOUCH(l); }
+void gtlc_disk_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+
+// ---- dome light (Gi.cpp:2943-3000) -----------------------------------------------------------
+GtlcHandle gtlc_dome_light_create(GtlcHandle sh, uint32_t w, uint32_t hgt, const float* rgba)
+{
+  Scene* s = as<Scene>(sh, TAG_SCENE); if (!s || !rgba || !w || !hgt) { setError("gtlc_dome_light_create: invalid arguments"); return 0; }
+  if (!requireInit()) return 0;
+  DomeLight* d = new DomeLight(); d->tag = TAG_DOME; d->scene = s; d->width = w; d->height = hgt;
+  d->texels.assign(rgba, rgba + (size_t) w * hgt * 4);
+  d->rotation[0] = d->rotation[1] = d->rotation[2] = 0.0f; d->rotation[3] = 1.0f;
+  d->baseEmission[0] = d->baseEmission[1] = d->baseEmission[2] = 1.0f; d->diffuse = d->specular = 1.0f; d->dTexels = nullptr;
+  cudaSetDevice(g.device);
+  if (cudaMalloc(&d->dTexels, (size_t) w * hgt * 16) != cudaSuccess || cudaMemcpy(d->dTexels, rgba, (size_t) w * hgt * 16, cudaMemcpyHostToDevice) != cudaSuccess) {
+    setError("dome light upload failed"); delete d; return 0;
+  }
+  return handleOf(d);
+}
+void gtlc_dome_light_destroy(GtlcHandle h) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; if (d->dTexels) cudaFree(d->dTexels); { std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; } d->tag = 0; delete d; }
+void gtlc_dome_light_set_rotation(GtlcHandle h, const float* q) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; memcpy(d->rotation, q, 16); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
+void gtlc_dome_light_set_base_emission(GtlcHandle h, const float* c) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; memcpy(d->baseEmission, c, 12); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
+void gtlc_dome_light_set_diffuse_specular(GtlcHandle h, float df, float sp) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; d->diffuse = df; d->specular = sp; std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
+
+// ---- render buffers (Gi.cpp:2995-3006) -------------------------------------------------------
+GtlcHandle gtlc_render_buffer_create(uint32_t w, uint32_t h, int32_t format)
+{
+  if (!requireInit()) return 0;
+  if (format < GTLC_FORMAT_INT32 || format > GTLC_FORMAT_FLOAT32_VEC4) { setError("bad render buffer format %d", format); return 0; }
+  cudaSetDevice(g.device);
+  RenderBuffer* rb = new RenderBuffer(); rb->tag = TAG_RB; rb->width = w; rb->height = h; rb->format = format;
+  rb->size = (size_t) w * h * (format == GTLC_FORMAT_FLOAT32_VEC4 ? 16 : 4);
+  rb->hostMem = nullptr; rb->devMem = nullptr;
+  if (cudaHostAlloc(&rb->hostMem, std::max<size_t>(rb->size, 16), cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&rb->devMem, std::max<size_t>(rb->size, 16)) != cudaSuccess) {
+    setError("render buffer allocation failed (%zu bytes)", rb->size); if (rb->hostMem) cudaFreeHost(rb->hostMem); delete rb; return 0;
+  }
+  memset(rb->hostMem, 0, rb->size); cudaMemset(rb->devMem, 0, rb->size);
+  return handleOf(rb);
+}
+void gtlc_render_buffer_destroy(GtlcHandle h) { RenderBuffer* rb = as<RenderBuffer>(h, TAG_RB); if (!rb) return; cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); cudaFreeHost(rb->hostMem); cudaFree(rb->devMem); rb->tag = 0; delete rb; }
+void* gtlc_render_buffer_mem(GtlcHandle h) { RenderBuffer* rb = as<RenderBuffer>(h, TAG_RB); return rb ? rb->hostMem : nullptr; }
+void* gtlc_render_buffer_device_mem(GtlcHandle h) { RenderBuffer* rb = as<RenderBuffer>(h, TAG_RB); return rb ? rb->devMem : nullptr; }
+
+// ---- BVH access ------------------------------------------------------------------------------
+int gtlc_scene_get_bvh(GtlcHandle h, GtlcBvhView* view)
+{
+  Scene* s = as<Scene>(h, TAG_SCENE); if (!s || !view) return GTLC_ERROR;
+  std::lock_guard<std::mutex> l(s->mutex);
+  if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s)) return GTLC_ERROR; /* device upload happens lazily in render/trace */ }
+  view->nodes = s->bvh.nodes.data(); view->nodeCount = (uint32_t) s->bvh.nodes.size();
+  view->triangles = s->bvh.tris.data(); view->triCount = (uint32_t) (s->bvh.tris.size() / 12);
+  return GTLC_OK;
+}
+
+static bool syncSceneToDevice(Scene* s)
+{
+  if (s->geometryDirty || !s->bvhValid || !s->dNodes.ptr) {
+    if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s)) return false; }
+    if (!uploadGeometry(s)) return false;
+    s->geometryDirty = false; s->materialsDirty = true;
+    g.stats.msBvhBuild = (float) s->lastBuildMs;
+  }
+  if (s->materialsDirty) { if (!uploadMaterials(s)) return false; s->materialsDirty = false; }
+  if (s->lightsDirty) { if (!uploadLights(s)) return false; s->lightsDirty = false; }
+  g.stats.bvhNodeCount = (uint32_t) s->bvh.nodes.size(); g.stats.bvhTriCount = (uint32_t) (s->bvh.tris.size() / 12); g.stats.bvhMaxDepth = s->bvh.maxDepth;
+  return true;
+}
+
+// ---- ray queries (parity tests / roofline bench) ---------------------------------------------
+int gtlc_trace_rays(GtlcHandle h, const float* rays, uint32_t count, int32_t anyHit, void* hitsOut, uint32_t* visitsOut)
+{
+  if (!requireInit()) return GTLC_ERROR;
+  Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return GTLC_ERROR;
+  std::lock_guard<std::mutex> l(s->mutex);
+  cudaSetDevice(g.device);
+  if (!syncSceneToDevice(s)) return GTLC_ERROR;
+  auto body = [&]() -> bool {
+    if (!ensurePool(std::max<size_t>(count, 1))) return false;
+    std::vector<float4> o(count), d(count);
+    for (uint32_t i = 0; i < count; i++) { const float* r = rays + (size_t) i * 8; o[i] = make_float4(r[0], r[1], r[2], r[3]); d[i] = make_float4(r[4], r[5], r[6], r[7]); }
+    CUDA_OK(cudaMemcpyAsync(g.q[0].rayO, o.data(), (size_t) count * 16, cudaMemcpyHostToDevice, g.stream));
+    CUDA_OK(cudaMemcpyAsync(g.q[0].rayD, d.data(), (size_t) count * 16, cudaMemcpyHostToDevice, g.stream));
+    Counters c; memset(&c, 0, sizeof(c)); c.numPaths[0] = count;
+    CUDA_OK(cudaMemcpyAsync(g.counters, &c, sizeof(c), cudaMemcpyHostToDevice, g.stream));
+    const bool countVisits = visitsOut != nullptr || g.tuning.countVisits;
+    if (visitsOut) {
+      if (g.visitsCapacity < count) { cudaFree(g.visits); g.visits = nullptr; CUDA_OK(cudaMalloc(&g.visits, (size_t) count * 8)); g.visitsCapacity = count; }
+    }
+    TraceParams P = makeTraceParams(s);
+    P.rayO = g.q[0].rayO; P.rayD = g.q[0].rayD; P.hitTUVP = g.hitTUVP; P.hitInst = g.hitInst;
+    P.numRays = &g.counters->numPaths[0]; P.workCounter = &g.counters->workCounter; P.visitsPerRay = visitsOut ? g.visits : nullptr;
+    cudaEvent_t e0 = nextEvent(), e1 = nextEvent();
+    cudaEventRecord(e0, g.stream);
+    const int blocks = g.smCount * 8;
+    if (anyHit) launchTrace<TRACE_ANY>(P, countVisits, blocks); else launchTrace<TRACE_CLOSEST>(P, countVisits, blocks);
+    cudaEventRecord(e1, g.stream);
+    CUDA_OK(cudaGetLastError());
+    std::vector<float4> tuvp(count); std::vector<uint32_t> inst(count);
+    CUDA_OK(cudaMemcpyAsync(tuvp.data(), g.hitTUVP, (size_t) count * 16, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_OK(cudaMemcpyAsync(inst.data(), g.hitInst, (size_t) count * 4, cudaMemcpyDeviceToHost, g.stream));
+    if (visitsOut) CUDA_OK(cudaMemcpyAsync(visitsOut, g.visits, (size_t) count * 8, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_OK(cudaMemcpyAsync(&c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_OK(cudaStreamSynchronize(g.stream));
+    float ms = 0.0f; cudaEventElapsedTime(&ms, e0, e1);
+    struct HitRec { float t, u, v; uint32_t prim, inst; };
+    HitRec* out = (HitRec*) hitsOut;
+    for (uint32_t i = 0; i < count; i++) { out[i].t = tuvp[i].x; out[i].u = tuvp[i].y; out[i].v = tuvp[i].z; memcpy(&out[i].prim, &tuvp[i].w, 4); out[i].inst = inst[i]; }
+    memset(&g.stats, 0, offsetof(GtlcStats, msBvhBuild));
+    if (anyHit) { g.stats.shadowRays = count; g.stats.msTraceAny = ms; } else { g.stats.closestRays = count; g.stats.msTraceClosest = ms; }
+    g.stats.nodeVisits = c.stats[1]; g.stats.triVisits = c.stats[2]; g.stats.kernelLaunches = 1; g.stats.msTotal = ms;
+    return true;
+  };
+  g.eventsUsed = 0;
+  return body() ? GTLC_OK : GTLC_ERROR;
+}
+
+// ---- giRender (Gi.cpp:1989-2524) -------------------------------------------------------------
+int gtlc_render(const GtlcRenderParams* params)
+{
+  if (!requireInit()) return GTLC_ERROR;
+  if (!params) { setError("gtlc_render: null params"); return GTLC_ERROR; }
+  Scene* s = as<Scene>(params->scene, TAG_SCENE); if (!s) return GTLC_ERROR;
+  std::lock_guard<std::mutex> l(s->mutex);
+  cudaSetDevice(g.device);
+  const GtlcRenderSettings& rs = params->renderSettings;
+  if (rs.mediumStackSize != 0) { setError("mediumStackSize > 0 (volume random walk) is not implemented in this build (SURVEY.md 8f rank 4)"); return GTLC_ERROR; }
+  if (rs.spp == 0) { setError("spp must be > 0"); return GTLC_ERROR; }
+
+  // colour AOV + dimensions (Gi.cpp:2265-2267: the first bound render buffer defines the image size)
+  RenderBuffer* colorRb = nullptr; uint32_t W = 0, H = 0; float clear[4] = { 0, 0, 0, 0 };
+  for (uint32_t i = 0; i < params->aovBindingCount; i++) {
+    const GtlcAovBinding& b = params->aovBindings[i];
+    RenderBuffer* rb = as<RenderBuffer>(b.renderBuffer, TAG_RB); if (!rb) return GTLC_ERROR;
+    if (!W) { W = rb->width; H = rb->height; }
+    if (rb->width != W || rb->height != H) { setError("AOV render buffers differ in size"); return GTLC_ERROR; }
+    if (b.aovId == GTLC_AOV_COLOR) {
+      if (rb->format != GTLC_FORMAT_FLOAT32_VEC4) { setError("colour AOV needs a Float32Vec4 render buffer"); return GTLC_ERROR; }
+      colorRb = rb; memcpy(clear, b.clearValue, 16);
+    }
+  }
+  if (!W || !H) { setError("gtlc_render: no AOV bound"); return GTLC_ERROR; }
+  if (W > 65535 || H > 65535) { setError("image dimensions exceed 65535 (imageDims packing, rp_main.h:39)"); return GTLC_ERROR; }
+
+  // dirty-flag evaluation (Gi.cpp:2048-2052, 2125-2129)
+  if (paramsResetAccumulation(s, params)) s->framebufferDirty = true;
+  if (s->geometryDirty || s->materialsDirty || s->lightsDirty) s->framebufferDirty = true;
+  if (!syncSceneToDevice(s)) return GTLC_ERROR;
+  if (s->framebufferDirty) { s->sampleOffset = 0; s->framebufferDirty = false; }
+  s->oldParams = *params; s->oldBindings.assign(params->aovBindings, params->aovBindings + params->aovBindingCount); s->oldParams.aovBindings = nullptr; s->haveOldParams = true;
+
+  DomeLight* dome = params->domeLight ? as<DomeLight>(params->domeLight, TAG_DOME) : nullptr;
+
+  // UniformData fill (Gi.cpp:2373-2426)
+  UniformData ubo; memset(&ubo, 0, sizeof(ubo));
+  auto norm3 = [](const float* v, float* o) { float len = sqrtf((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); float inv = 1.0f / len; o[0] = v[0] * inv; o[1] = v[1] * inv; o[2] = v[2] * inv; };
+  if (dome) { memcpy(ubo.domeLightRotation, dome->rotation, 16); memcpy(ubo.domeLightEmissionMultiplier, dome->baseEmission, 12); }
+  else { ubo.domeLightRotation[3] = 1.0f; ubo.domeLightEmissionMultiplier[0] = ubo.domeLightEmissionMultiplier[1] = ubo.domeLightEmissionMultiplier[2] = 1.0f; }
+  ubo.sphereLightCount = (uint32_t) s->sphereLights.size(); ubo.distantLightCount = (uint32_t) s->distantLights.size();
+  ubo.rectLightCount = (uint32_t) s->rectLights.size(); ubo.diskLightCount = (uint32_t) s->diskLights.size();
+  ubo.totalLightCount = ubo.sphereLightCount + ubo.distantLightCount + ubo.rectLightCount + ubo.diskLightCount;
+  ubo.metersPerSceneUnit = rs.metersPerSceneUnit;
+  memcpy(ubo.cameraPosition, params->camera.position, 12);
+  ubo.imageDims = (H << 16) | W;
+  norm3(params->camera.forward, ubo.cameraForward); norm3(params->camera.up, ubo.cameraUp);
+  ubo.focusDistance = params->camera.focusDistance; ubo.cameraVFoV = params->camera.vfov;
+  ubo.sampleOffset = s->sampleOffset;
+  ubo.lensRadius = (params->camera.fStop > 0.0f) ? (params->camera.focalLength / (2.0f * params->camera.fStop)) : 0.0f;
+  ubo.spp = rs.spp; ubo.invTotalSampleCount = 1.0f / float(s->sampleOffset + rs.spp);
+  ubo.maxSampleValue = rs.maxSampleValue; ubo.maxBouncesAndRrBounceOffset = (rs.maxBounces << 16) | rs.rrBounceOffset;
+  ubo.rrInvMinTermProb = rs.rrInvMinTermProb; ubo.lightIntensityMultiplier = rs.lightIntensityMultiplier;
+  ubo.clipRangePacked = packHalf2x16(params->camera.clipStart, params->camera.clipEnd); ubo.sensorExposure = params->camera.exposure;
+  ubo.flags = (rs.jitteredSampling ? FLAG_JITTERED : 0u) | (rs.filterImportanceSampling ? FLAG_FIS : 0u) | (rs.depthOfField ? FLAG_DOF : 0u) |
+              (rs.nextEventEstimation ? FLAG_NEE : 0u) | (rs.clippingPlanes ? FLAG_CLIPPING : 0u) | (rs.progressiveAccumulation ? FLAG_PROGRESSIVE : 0u) |
+              (rs.domeLightCameraVisible ? FLAG_DOME_CAMERA_VISIBLE : 0u) | (dome ? FLAG_HAS_DOME : 0u);
+  for (int k = 0; k < 3; k++) ubo.background[k] = (float) (uint8_t) (clear[k] * 255.0f) / 255.0f;   // Gi.cpp:2196
+
+  auto body = [&]() -> bool {
+    if (!buildPixelMap(s, W, H)) return false;
+    const uint32_t localPixels = s->localPixels;
+    const uint32_t maxPaths = std::max<uint32_t>(g.tuning.maxPathsPerWave, 1024u);
+    uint32_t pixelsPerWave = std::min(localPixels, maxPaths);
+    uint32_t samplesPerWave = std::max<uint32_t>(1u, std::min<uint32_t>(rs.spp, pixelsPerWave ? maxPaths / pixelsPerWave : 1u));
+    if (pixelsPerWave < localPixels) samplesPerWave = 1;
+    if (!ensurePool((size_t) pixelsPerWave * samplesPerWave)) return false;
+    if (g.accumCapacity < localPixels) { cudaFree(g.accum); g.accum = nullptr; CUDA_OK(cudaMalloc(&g.accum, std::max<size_t>(localPixels, 1) * 16)); g.accumCapacity = localPixels; }
+
+    DeviceScene ds; memset(&ds, 0, sizeof(ds));
+    ds.fverts = s->dFverts.ptr; ds.faces = s->dFaces.ptr; ds.instO2W = s->dO2W.ptr; ds.instW2O = s->dW2O.ptr; ds.instInfo = s->dInstInfo.ptr;
+    ds.matParams = s->dMatParams.ptr; ds.matClosure = s->dMatClosure.ptr; ds.matFlags = s->dMatFlags.ptr;
+    ds.sphereLights = s->dSphere.ptr; ds.distantLights = s->dDistant.ptr; ds.rectLights = s->dRect.ptr; ds.diskLights = s->dDisk.ptr;
+    if (dome) { ds.domeTexels = dome->dTexels; ds.domeW = dome->width; ds.domeH = dome->height; }
+
+    float4* colorDev = colorRb ? (float4*) colorRb->devMem : nullptr;
+    std::vector<TimedSpan> spans;
+    g.eventsUsed = 0;
+    uint64_t launches = 0;
+    auto timed = [&](int kind, auto&& fn) { TimedSpan t; t.kind = kind; t.a = nextEvent(); t.b = nextEvent(); cudaEventRecord(t.a, g.stream); fn(); cudaEventRecord(t.b, g.stream); spans.push_back(t); launches++; };
+
+    CUDA_OK(cudaMemsetAsync(g.counters, 0, sizeof(Counters), g.stream));
+    cudaEvent_t evStart = nextEvent(), evEnd = nextEvent();
+    cudaEventRecord(evStart, g.stream);
+    // sharded render: pixels of other ranks are 0 so that one sum-reduce assembles the image
+    if (colorDev && s->shardCount > 1 && s->sampleOffset == 0) CUDA_OK(cudaMemsetAsync(colorDev, 0, (size_t) W * H * 16, g.stream));
+    // other bound AOVs: cleared to their clear value (not rendered in this build)
+    for (uint32_t i = 0; i < params->aovBindingCount; i++) {
+      const GtlcAovBinding& b = params->aovBindings[i];
+      if (b.aovId == GTLC_AOV_COLOR) continue;
+      RenderBuffer* rb = as<RenderBuffer>(b.renderBuffer, TAG_RB);
+      const size_t comp = rb->format == GTLC_FORMAT_FLOAT32_VEC4 ? 16 : 4;
+      uint8_t* hm = (uint8_t*) rb->hostMem;
+      for (size_t p = 0; p < (size_t) W * H; p++) memcpy(hm + p * comp, b.clearValue, comp);
+      CUDA_OK(cudaMemcpyAsync(rb->devMem, rb->hostMem, rb->size, cudaMemcpyHostToDevice, g.stream));
+    }
+
+    const int gridElem = g.smCount * 8;
+    const int traceBlocks = g.smCount * 8;
+    const bool countVisits = g.tuning.countVisits != 0;
+    uint64_t paths = 0;
+    for (uint32_t pixBase = 0; pixBase < localPixels; pixBase += pixelsPerWave) {
+      const uint32_t wavePixels = std::min(pixelsPerWave, localPixels - pixBase);
+      for (uint32_t sBase = 0; sBase < rs.spp; sBase += samplesPerWave) {
+        WaveParams wp; wp.wavePixelBase = pixBase; wp.wavePixels = wavePixels; wp.waveSamples = std::min(samplesPerWave, rs.spp - sBase);
+        wp.waveSampleBase = sBase; wp.pixelMap = (s->shardCount > 1) ? s->dPixelMap.ptr : nullptr;
+        paths += (uint64_t) wp.wavePixels * wp.waveSamples;
+        timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.q[0], g.counters); });
+        int inIdx = 0;
+        for (uint32_t bounce = 0; bounce < rs.maxBounces; bounce++) {
+          prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 0); launches++;
+          TraceParams P = makeTraceParams(s);
+          P.rayO = g.q[inIdx].rayO; P.rayD = g.q[inIdx].rayD; P.hitTUVP = g.hitTUVP; P.hitInst = g.hitInst;
+          P.numRays = &g.counters->numPaths[inIdx]; P.workCounter = &g.counters->workCounter;
+          timed(K_TRACE, [&] { launchTrace<TRACE_CLOSEST>(P, countVisits, traceBlocks); });
+          timed(K_SHADE, [&] { shade_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, nullptr,
+                                                                          g.shO, g.shD, g.shC, g.sampleRad, g.counters, inIdx); });
+          if (rs.nextEventEstimation) {
+            prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;
+            TraceParams S = makeTraceParams(s);
+            S.rayO = g.shO; S.rayD = g.shD; S.shContrib = g.shC; S.radPath = g.q[inIdx ^ 1].rad; S.radSample = g.sampleRad;
+            S.numRays = &g.counters->numShadow; S.workCounter = &g.counters->workCounter;
+            timed(K_SHADOW, [&] { launchTrace<TRACE_SHADOW>(S, countVisits, traceBlocks); });
+          }
+          inIdx ^= 1;
+        }
+        const int lastWave = (sBase + samplesPerWave >= rs.spp) ? 1 : 0;
+        timed(K_RESOLVE, [&] { resolve_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, g.accum, colorDev, lastWave); });
+      }
+    }
+    cudaEventRecord(evEnd, g.stream);
+    CUDA_OK(cudaGetLastError());
+    // readback of every bound AOV (Gi.cpp:2439-2489) + blocking wait (Gi.cpp:2492-2502)
+    Counters c;
+    CUDA_OK(cudaMemcpyAsync(&c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, g.stream));
+    if (!g.tuning.skipReadback && colorRb) CUDA_OK(cudaMemcpyAsync(colorRb->hostMem, colorRb->devMem, colorRb->size, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_OK(cudaStreamSynchronize(g.stream));
+    float keepBuild = g.stats.msBvhBuild; uint32_t kn = g.stats.bvhNodeCount, kt = g.stats.bvhTriCount, kd = g.stats.bvhMaxDepth;
+    memset(&g.stats, 0, sizeof(g.stats));
+    g.stats.msBvhBuild = keepBuild; g.stats.bvhNodeCount = kn; g.stats.bvhTriCount = kt; g.stats.bvhMaxDepth = kd;
+    cudaEventElapsedTime(&g.stats.msTotal, evStart, evEnd);
+    for (const TimedSpan& t : spans) {
+      float ms = 0.0f; cudaEventElapsedTime(&ms, t.a, t.b);
+      switch (t.kind) {
+        case K_RAYGEN: g.stats.msRaygen += ms; break; case K_TRACE: g.stats.msTraceClosest += ms; break; case K_SHADE: g.stats.msShade += ms; break;
+        case K_SHADOW: g.stats.msTraceAny += ms; break; case K_RESOLVE: g.stats.msResolve += ms; break; case K_SORT: g.stats.msSort += ms; break;
+      }
+    }
+    g.stats.closestRays = c.stats[0]; g.stats.shadowRays = c.stats[3]; g.stats.nodeVisits = c.stats[1]; g.stats.triVisits = c.stats[2];
+    g.stats.kernelLaunches = launches; g.stats.paths = paths;
+    return true;
+  };
+  if (!body()) return GTLC_ERROR;
+  s->sampleOffset += rs.spp;                                            // Gi.cpp:2515
+  return GTLC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,281 @@
+// BVH8 traversal kernels: trace_closest (R3) and trace_any / shadow (R8) of SURVEY.md 8a.
+//
+// Replaces traceRayEXT(sceneAS, ...) of /root/reference/src/gi/shaders/rp_main.rgen:381-393 (closest,
+// flags 0, no culling -- CgpuVk.cpp:2810) and :412-424 (shadow, TerminateOnFirstHit|SkipClosestHit);
+// the rp_main_shadow.miss "shadowed = false" + "radiance += neeContrib" (rgen:426-429) pair is fused
+// into the shadow kernel's epilogue.
+//
+// Execution model: persistent warps (grid = k x 148 CTAs) pull rays from a global queue with one
+// warp-aggregated atomic per refill ("work stealing"); a lane whose ray finished is refilled as soon
+// as >= kRefillThreshold lanes of its warp are idle, so divergence in path length does not idle
+// the warp (Aila & Laine 2009 "persistent while-while", dynamic fetch).  One ray per lane, per-lane
+// traversal stack of 8-byte node-group entries (Ylitie et al. 2017), watertight Woop/Benthin/Wald
+// 2013 triangle test in world space.  All node / triangle / ray traffic is 128-bit loads.
+//
+// Determinism: closest hit = smallest t, ties broken by (instanceIndex, primitiveId); the result does
+// not depend on traversal order.
+#pragma once
+#include "device_math.cuh"
+
+namespace gtlc {
+
+constexpr int kTraceBlock = 128;         // threads per CTA
+constexpr int kStackSize = 40;           // >= wide-tree depth (checked on the host at build time)
+constexpr int kRefillThreshold = 8;      // idle lanes that trigger a refill
+constexpr float kBoxPad = 1.0000004f;    // Ize 2013 robust slab padding
+
+enum { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_SHADOW = 2 };
+
+struct TraceParams {
+  const uint4* __restrict__ nodes;      // 5 x uint4 per BVH8 node
+  const float4* __restrict__ tris;      // 3 x float4 per triangle
+  const float4* __restrict__ rayO;      // (origin.xyz, tMin)
+  const float4* __restrict__ rayD;      // (direction.xyz, tMax)
+  float4* __restrict__ hitTUVP;         // (t, u, v, bits primitiveId); miss: t = -1
+  uint32_t* __restrict__ hitInst;       // instance index; miss: 0xFFFFFFFF
+  const uint32_t* __restrict__ numRays; // device-resident queue length
+  uint32_t* workCounter;                // zeroed before the launch
+  // TRACE_SHADOW epilogue: unoccluded -> target.xyz += contrib
+  const float4* __restrict__ shContrib; // (contrib.xyz, bits target): target bit31 = sample slot, else path queue position
+  float4* __restrict__ radPath;         // (radiance.xyz, rng) of the continuing paths
+  float4* __restrict__ radSample;       // (radiance.xyz, -) of finished samples
+  // bookkeeping
+  unsigned long long* stats;            // [0] rays traced, [1] node visits, [2] triangle tests
+  uint32_t* visitsPerRay;               // optional 2 x uint32 per ray
+};
+
+GTLC_D float byte_to_float(uint32_t w, uint32_t sel)
+{
+  // 0x4B0000qq = 2^23 + q exactly; one PRMT + one FADD, no integer->float conversion pipe
+  return u2f(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+}
+
+struct RaySetup {
+  V3 o, d;
+  float tmin;
+  V3 idir;
+  uint32_t octinv;
+  int kx, ky, kz;
+  float Sx, Sy, Sz;
+};
+
+GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
+{
+  r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z); r.tmin = ro.w;
+  r.idir = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+  uint32_t oct = (r.d.x < 0.0f ? 1u : 0u) | (r.d.y < 0.0f ? 2u : 0u) | (r.d.z < 0.0f ? 4u : 0u);
+  r.octinv = 7u - oct;
+  float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
+  r.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
+  r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
+  if (comp(r.d, r.kz) < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
+  float dz = comp(r.d, r.kz);
+  r.Sx = comp(r.d, r.kx) / dz;
+  r.Sy = comp(r.d, r.ky) / dz;
+  r.Sz = 1.0f / dz;
+}
+
+// Woop, Benthin, Wald 2013.  Returns true with (t, u, v) when the ray line pierces the triangle.
+GTLC_D bool tri_intersect(const RaySetup& r, V3 p0, V3 p1, V3 p2, float& t, float& u, float& v)
+{
+  V3 A = p0 - r.o, B = p1 - r.o, C = p2 - r.o;
+  float Ax = comp(A, r.kx) - r.Sx * comp(A, r.kz);
+  float Ay = comp(A, r.ky) - r.Sy * comp(A, r.kz);
+  float Bx = comp(B, r.kx) - r.Sx * comp(B, r.kz);
+  float By = comp(B, r.ky) - r.Sy * comp(B, r.kz);
+  float Cx = comp(C, r.kx) - r.Sx * comp(C, r.kz);
+  float Cy = comp(C, r.ky) - r.Sy * comp(C, r.kz);
+  float U = Cx * By - Cy * Bx;
+  float V = Ax * Cy - Ay * Cx;
+  float W = Bx * Ay - By * Ax;
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    double CxBy = (double) Cx * (double) By, CyBx = (double) Cy * (double) Bx;
+    U = (float) (CxBy - CyBx);
+    double AxCy = (double) Ax * (double) Cy, AyCx = (double) Ay * (double) Cx;
+    V = (float) (AxCy - AyCx);
+    double BxAy = (double) Bx * (double) Ay, ByAx = (double) By * (double) Ax;
+    W = (float) (BxAy - ByAx);
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  float det = (U + V) + W;
+  if (det == 0.0f) return false;
+  float Az = r.Sz * comp(A, r.kz);
+  float Bz = r.Sz * comp(B, r.kz);
+  float Cz = r.Sz * comp(C, r.kz);
+  float T = (U * Az + V * Bz) + W * Cz;
+  float rcp = 1.0f / det;
+  t = T * rcp;
+  u = V * rcp;
+  v = W * rcp;
+  return true;
+}
+
+// Slab-tests the 8 quantised child boxes of one node; returns the 32-bit hit mask
+// (bits 31..24: internal children in traversal priority order, bits 23..0: triangles).
+GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
+                             const RaySetup& r, float tbest)
+{
+  const uint32_t e = n0.w;
+  const float sx = u2f((e & 0xFFu) << 23) * r.idir.x;
+  const float sy = u2f(((e >> 8) & 0xFFu) << 23) * r.idir.y;
+  const float sz = u2f(((e >> 16) & 0xFFu) << 23) * r.idir.z;
+  const float ox = (u2f(n0.x) - r.o.x) * r.idir.x;
+  const float oy = (u2f(n0.y) - r.o.y) * r.idir.y;
+  const float oz = (u2f(n0.z) - r.o.z) * r.idir.z;
+  const bool nx = r.d.x < 0.0f, ny = r.d.y < 0.0f, nz = r.d.z < 0.0f;
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const uint32_t meta4 = half ? n1.w : n1.z;
+    const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+    const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+    const uint32_t nearx = nx ? qhix : qlox, farx = nx ? qlox : qhix;
+    const uint32_t neary = ny ? qhiy : qloy, fary = ny ? qloy : qhiy;
+    const uint32_t nearz = nz ? qhiz : qloz, farz = nz ? qloz : qhiz;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t sel = 0x7650u | (uint32_t) j;
+      const float tnx = fmaf(byte_to_float(nearx, sel), sx, ox);
+      const float tny = fmaf(byte_to_float(neary, sel), sy, oy);
+      const float tnz = fmaf(byte_to_float(nearz, sel), sz, oz);
+      const float tfx = fmaf(byte_to_float(farx, sel), sx, ox);
+      const float tfy = fmaf(byte_to_float(fary, sel), sy, oy);
+      const float tfz = fmaf(byte_to_float(farz, sel), sz, oz);
+      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest)) * kBoxPad;
+      const uint32_t m = (meta4 >> (8 * j)) & 0xFFu;
+      if (tn <= tf && m != 0u) {
+        const uint32_t bits = m >> 5;
+        const uint32_t lo5 = m & 31u;
+        const uint32_t idx = (lo5 >= 24u) ? (24u + ((lo5 & 7u) ^ r.octinv)) : lo5;
+        hitmask |= bits << idx;
+      }
+    }
+  }
+  return hitmask;
+}
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock) trace_kernel(TraceParams P)
+{
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = *P.numRays;
+
+  uint2 stack[kStackSize];
+  int sp = 0;
+  bool active = false;
+  bool exhausted = false;   // warp-uniform: the global queue has no more rays
+  uint32_t rayIdx = 0;
+  RaySetup r;
+  float bt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t bprim = 0xFFFFFFFFu, binst = 0xFFFFFFFFu;
+  float tmax = 0.0f;
+  uint2 G = make_uint2(0u, 0u);
+  uint32_t cNodes = 0, cTris = 0;
+
+  while (true) {
+    // ---- refill idle lanes from the global queue (one atomic per warp) -----------------------
+    if (!exhausted) {
+      const unsigned need = __ballot_sync(FULL, !active);
+      if (need) {
+        const int leader = __ffs(need) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t) __popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active) {
+          rayIdx = base + (uint32_t) __popc(need & ((1u << lane) - 1u));
+          if (rayIdx < n) {
+            const float4 ro = __ldg(&P.rayO[rayIdx]);
+            const float4 rd = __ldg(&P.rayD[rayIdx]);
+            ray_setup(r, ro, rd);
+            tmax = rd.w;
+            bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
+            sp = 0; cNodes = 0; cTris = 0;
+            active = tmax > r.tmin;   // empty interval (e.g. disabled shadow ray): immediate miss
+            G = make_uint2(0u, 0x80000000u);
+            if (!active) {
+              if (MODE == TRACE_CLOSEST || MODE == TRACE_ANY) { P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu; }
+              // TRACE_SHADOW: an empty interval means "no shadow ray" (rgen:407-410): nothing is added
+              if (COUNT && P.visitsPerRay) { P.visitsPerRay[2 * (size_t) rayIdx] = 0; P.visitsPerRay[2 * (size_t) rayIdx + 1] = 0; }
+            }
+          }
+        }
+        if (base + (uint32_t) __popc(need) >= n) exhausted = true;
+      }
+    }
+    if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
+
+    // ---- traversal steps until enough lanes went idle ------------------------------------------
+    while (true) {
+      if (active) {
+        uint2 T;
+        if (G.y & 0xFF000000u) {
+          const uint32_t hits_imask = G.y;
+          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
+          G.y &= ~(1u << bit);
+          if (G.y & 0xFF000000u) stack[sp++] = G;
+          const uint32_t slot = (bit - 24u) ^ r.octinv;
+          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
+          const uint32_t node = G.x + rel;
+          const uint4* np = P.nodes + (size_t) node * 5;
+          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          if (COUNT) cNodes++;
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
+          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+          T = make_uint2(n1.y, hm & 0x00FFFFFFu);
+        } else {
+          T = make_uint2(0u, 0u);
+        }
+        bool done = false;
+        while (T.y) {
+          const uint32_t j = (uint32_t) __ffs(T.y) - 1u;
+          T.y &= T.y - 1u;
+          const float4* tp = P.tris + (size_t) (T.x + j) * 3;
+          const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+          if (COUNT) cTris++;
+          float t, u, v;
+          if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+            if (t > r.tmin && t < tmax) {
+              const uint32_t prim = f2u(a.w), inst = f2u(b.w);
+              if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
+              const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
+              if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
+            }
+          }
+        }
+        if (!done && !(G.y & 0xFF000000u)) {
+          if (sp == 0) done = true;
+          else G = stack[--sp];
+        }
+        if (done) {
+          const bool hit = bprim != 0xFFFFFFFFu;
+          if (MODE == TRACE_SHADOW) {
+            if (!hit) {
+              const float4 c = __ldg(&P.shContrib[rayIdx]);
+              const uint32_t target = f2u(c.w);
+              float4* dst = (target & 0x80000000u) ? (P.radSample + (target & 0x7FFFFFFFu)) : (P.radPath + target);
+              float4 cur = *dst;
+              cur.x += c.x; cur.y += c.y; cur.z += c.z;
+              *dst = cur;
+            }
+          } else {
+            P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
+            if (P.hitInst) P.hitInst[rayIdx] = binst;
+          }
+          if (COUNT) {
+            atomicAdd(&P.stats[1], (unsigned long long) cNodes);
+            atomicAdd(&P.stats[2], (unsigned long long) cTris);
+            if (P.visitsPerRay) { P.visitsPerRay[2 * (size_t) rayIdx] = cNodes; P.visitsPerRay[2 * (size_t) rayIdx + 1] = cTris; }
+          }
+          active = false;
+        }
+      }
+      const unsigned idle = __ballot_sync(FULL, !active);
+      if (idle == FULL) break;
+      if (!exhausted && __popc(idle) >= kRefillThreshold) break;
+    }
+  }
+}
+
+} // namespace gtlc

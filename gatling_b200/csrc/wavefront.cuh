@@ -1,0 +1,532 @@
+// Wavefront path-tracing kernels: ray generation, shading (closest-hit + miss + NEE + path control),
+// and sample resolve.  Together with traverse.cuh they replace the reference's single Vulkan-RT
+// megakernel (/root/reference/src/gi/shaders/rp_main.{rgen,chit,miss}, rp_main_shadow.miss); every
+// function cites the shader lines it restates (paths relative to /root/reference/src/gi/shaders/).
+//
+// Data layout (all queues are SoA arrays of 16-byte words, read and written with 128-bit accesses):
+//   path queue entry i : rayO[i] = (origin.xyz, tMin)      rayD[i] = (dir.xyz, tMax)
+//                        thr[i]  = (throughput.xyz, bitfield)   rad[i] = (radiance.xyz, rng_state)
+//                        slot[i] = sample slot (sampleInWave * wavePixels + pixelInWave)
+//   hit record i       : hitTUVP[i] = (t, u, v, primitiveId)  hitInst[i] = instance index
+//   shadow queue entry : shO = (origin.xyz, 0.01)  shD = (dir.xyz, lightDist)  shC = (neeContrib.xyz, target)
+//   sampleRad[slot]    : final (unclamped) radiance of a finished sample
+// The path queue is double buffered: the shade kernel compacts surviving paths into the "out"
+// queue with warp-ballot + one atomic per warp, so the next bounce reads densely packed state
+// (this is ShadeRayPayload, rp_main_payload.glsl:20-47, turned inside out).
+#pragma once
+#include "closures.cuh"
+#include "traverse.cuh"
+
+namespace gtlc {
+
+// rp_main_payload.glsl:3-9
+constexpr uint32_t kPayloadMediumIdxMask = 0x0f000000u;
+constexpr uint32_t kPayloadMediumIdxOffset = 24;
+constexpr uint32_t kPayloadWalkMask = 0x00fff000u;
+constexpr uint32_t kPayloadBouncesMask = 0x00000fffu;
+constexpr uint32_t kPayloadTerminateFlag = 0x80000000u;
+
+// interface/rp_main.h:25-56 UniformData (T1), as kernel launch parameters instead of a UBO.
+struct UniformData {
+  float domeLightRotation[4];
+  float domeLightEmissionMultiplier[3];
+  uint32_t sphereLightCount, distantLightCount, rectLightCount, diskLightCount, totalLightCount;
+  float metersPerSceneUnit;
+  float cameraPosition[3]; uint32_t imageDims;
+  float cameraForward[3]; float focusDistance;
+  float cameraUp[3]; float cameraVFoV;
+  uint32_t sampleOffset; float lensRadius; uint32_t spp; float invTotalSampleCount;
+  float maxSampleValue; uint32_t maxBouncesAndRrBounceOffset; float rrInvMinTermProb;
+  float lightIntensityMultiplier; uint32_t clipRangePacked; float sensorExposure;
+  // compile-time #defines of the reference (GlslShaderGen.cpp:57-72,95-133) as run-time flags
+  uint32_t flags;
+  float background[3];   // 1x1 fallback dome texel = u8(clearValue * 255) / 255 (Gi.cpp:2183-2199)
+};
+enum : uint32_t {
+  FLAG_JITTERED = 1u, FLAG_FIS = 2u, FLAG_DOF = 4u, FLAG_NEE = 8u, FLAG_CLIPPING = 16u,
+  FLAG_PROGRESSIVE = 32u, FLAG_DOME_CAMERA_VISIBLE = 64u, FLAG_HAS_DOME = 128u
+};
+
+// Per-instance record (BlasPayload, rp_main.h:118-123, + CgpuBlasInstance hit-group index)
+struct InstanceInfo { uint32_t vertexBase, faceBase, flags, material; };
+constexpr uint32_t kMatFlagEmissive = 1u, kMatFlagThinWalled = 2u;
+
+struct DeviceScene {
+  const float4* __restrict__ fverts;     // 2 x float4 per FVertex (rp_main.h:58-64)
+  const uint32_t* __restrict__ faces;    // 3 per Face (rp_main.h:66-71)
+  const float4* __restrict__ instO2W;    // 3 x float4 per instance (gl_ObjectToWorldEXT rows)
+  const float4* __restrict__ instW2O;    // 3 x float4 per instance (gl_WorldToObjectEXT rows)
+  const InstanceInfo* __restrict__ instInfo;
+  const float* __restrict__ matParams;   // GTLC_MATERIAL_PARAM_COUNT floats per material
+  const int32_t* __restrict__ matClosure;
+  const uint32_t* __restrict__ matFlags;
+  const float4* __restrict__ sphereLights;   // 3 x float4 per light (rp_main.h:73-113)
+  const float4* __restrict__ distantLights;
+  const float4* __restrict__ rectLights;
+  const float4* __restrict__ diskLights;
+  const float4* __restrict__ domeTexels; uint32_t domeW, domeH;
+};
+
+struct PathQueue { float4* rayO; float4* rayD; float4* thr; float4* rad; uint32_t* slot; };
+
+struct WaveParams {
+  uint32_t wavePixelBase;   // first local pixel of this wave
+  uint32_t wavePixels;      // pixels in this wave
+  uint32_t waveSamples;     // samples per pixel in this wave
+  uint32_t waveSampleBase;  // index of the wave's first sample within this giRender call (s in rgen:215)
+  const uint32_t* __restrict__ pixelMap;  // local pixel -> global pixel index (NULL = identity)
+};
+
+struct Counters {          // device-resident
+  uint32_t numPaths[2];    // path-queue lengths (double buffered)
+  uint32_t numShadow;
+  uint32_t workCounter;
+  unsigned long long stats[4];  // [0] closest rays, [1] node visits, [2] tri tests, [3] shadow rays
+};
+
+// ---- rp_main.rgen:118-130 ---------------------------------------------------------------------
+GTLC_D V2 fisGauss(V2 xi)
+{
+  float u1 = fmaxf(1e-38f, xi.x);
+  float u2 = xi.y;
+  float sigma = 0.375f;
+  float r = sigma * sqrtf(-2.0f * logf(u1));
+  float phi = 2.0f * kPi * u2;
+  V2 o; o.x = cosf(phi) * r; o.y = sinf(phi) * r;
+  return o;
+}
+
+GTLC_D V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+
+// ---- raygen: rp_main.rgen:191-288 -------------------------------------------------------------
+__global__ void __launch_bounds__(256) raygen_kernel(UniformData ubo, WaveParams wp, PathQueue q, Counters* ctr)
+{
+  const uint32_t total = wp.wavePixels * wp.waveSamples;
+  const uint32_t imageWidth = ubo.imageDims & 0xFFFFu;
+  const uint32_t imageHeight = ubo.imageDims >> 16;
+  const V3 camPos = ld3(ubo.cameraPosition), camFwd = ld3(ubo.cameraForward), camUp = ld3(ubo.cameraUp);
+  const V3 camera_right = cross(camFwd, camUp);                          // :199
+  const float aspect_ratio = (float) imageWidth / (float) imageHeight;   // :200
+  const float H = 1.0f;
+  const float W = H * aspect_ratio;
+  const float d = H / (2.0f * tanf(ubo.cameraVFoV * 0.5f));              // :204
+  const float WX = W / (float) imageWidth;
+  const float HY = H / (float) imageHeight;
+  const V3 C = camPos + camFwd * d;                                      // :209
+  const V3 L = (C - (camera_right * W) * 0.5f) - (camUp * H) * 0.5f;     // :210
+
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+    const uint32_t j = slot / wp.wavePixels;
+    const uint32_t lp = wp.wavePixelBase + (slot - j * wp.wavePixels);
+    const uint32_t pixelIndex = wp.pixelMap ? wp.pixelMap[lp] : lp;      // :195
+    const uint32_t px = pixelIndex % imageWidth, py = pixelIndex / imageWidth;
+    const uint32_t sampleIndex = ubo.sampleOffset + wp.waveSampleBase + j;  // :217
+    uint32_t rng_state = rng1d_init(pixelIndex, sampleIndex);            // :223
+    V2 rand2_xy = rng1d_next2f(rng_state);                               // :224
+    V2 so; so.x = 0.5f; so.y = 0.5f;                                     // :227
+    if (ubo.flags & FLAG_JITTERED) {
+      if (ubo.flags & FLAG_FIS) { V2 g = fisGauss(rand2_xy); so.x = 0.5f + g.x; so.y = 0.5f + g.y; }  // :232
+      else so = rand2_xy;                                                // :235
+    }
+    V3 P = (L + (camera_right * ((float) px + so.x)) * WX) + (camUp * ((float) py + so.y)) * HY;  // :239-242
+    V3 ray_origin = camPos;
+    V3 ray_dir = normalize(P - ray_origin);                              // :245
+    if ((ubo.flags & FLAG_DOF) && ubo.lensRadius > 0.0f) {               // :250-267
+      V2 rand2_zw = rng1d_next2f(rng_state);
+      V3 focalPoint = ray_origin + ray_dir * ubo.focusDistance;
+      V3 h = sample_hemisphere(rand2_zw);
+      float ax = h.x * ubo.lensRadius, ay = h.y * ubo.lensRadius;
+      ray_origin += camera_right * ax;
+      ray_origin += camUp * ay;
+      ray_dir = normalize(focalPoint - ray_origin);
+    }
+    ray_dir.x += (ray_dir.x == 0.0f) ? kFloatMin : 0.0f;                 // :271
+    ray_dir.y += (ray_dir.y == 0.0f) ? kFloatMin : 0.0f;
+    ray_dir.z += (ray_dir.z == 0.0f) ? kFloatMin : 0.0f;
+    float tMin = 0.0f, tMax = kFloatMax;                                 // :306-314 (bounce 0)
+    if (ubo.flags & FLAG_CLIPPING) {
+      float cosConeAngle = fmaxf(1e-5f, dot(ray_dir, camFwd));           // :287
+      V2 clipRange = unpackHalf2x16(ubo.clipRangePacked);
+      tMin = clipRange.x / cosConeAngle; tMax = clipRange.y / cosConeAngle;   // :288
+    }
+    q.rayO[slot] = make_float4(ray_origin.x, ray_origin.y, ray_origin.z, tMin);
+    q.rayD[slot] = make_float4(ray_dir.x, ray_dir.y, ray_dir.z, tMax);
+    q.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));               // :274-275
+    q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(rng_state));        // :276-277
+    q.slot[slot] = slot;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->numPaths[0] = total; ctr->numPaths[1] = 0; ctr->numShadow = 0; ctr->workCounter = 0; }
+}
+
+// Resets the per-bounce counters and accumulates ray statistics (one thread).
+__global__ void prep_kernel(Counters* ctr, int inIdx, int phase)
+{
+  if (phase == 0) {   // before trace_closest of a bounce
+    ctr->workCounter = 0; ctr->numPaths[inIdx ^ 1] = 0; ctr->numShadow = 0;
+    ctr->stats[0] += ctr->numPaths[inIdx];
+  } else {            // before trace_shadow
+    ctr->workCounter = 0;
+    ctr->stats[3] += ctr->numShadow;
+  }
+}
+
+// ---- rp_main.miss:39-53 -------------------------------------------------------------------------
+GTLC_D V3 quatRotateDir(const float* q, V3 dir)
+{
+  V3 qv = v3(q[0], q[1], q[2]);
+  V3 a = cross(qv, dir);
+  V3 b = cross(qv, a);
+  return dir + ((a * q[3]) + b) * 2.0f;
+}
+
+GTLC_D V3 texture_latlong(const DeviceScene& s, float u, float v)
+{
+  // sampler: linear / linear, REPEAT (Gi.cpp:388-392); one mip
+  const int W = (int) s.domeW, H = (int) s.domeH;
+  float x = u * (float) W - 0.5f, y = v * (float) H - 0.5f;
+  float fx = floorf(x), fy = floorf(y);
+  float ax = x - fx, ay = y - fy;
+  int x0 = (int) fx, y0 = (int) fy;
+  int xa = x0 % W; if (xa < 0) xa += W;
+  int xb = (x0 + 1) % W; if (xb < 0) xb += W;
+  int ya = y0 % H; if (ya < 0) ya += H;
+  int yb = (y0 + 1) % H; if (yb < 0) yb += H;
+  float4 t00 = __ldg(&s.domeTexels[(size_t) ya * W + xa]), t10 = __ldg(&s.domeTexels[(size_t) ya * W + xb]);
+  float4 t01 = __ldg(&s.domeTexels[(size_t) yb * W + xa]), t11 = __ldg(&s.domeTexels[(size_t) yb * W + xb]);
+  V3 top = v3(t00.x, t00.y, t00.z) * (1.0f - ax) + v3(t10.x, t10.y, t10.z) * ax;
+  V3 bot = v3(t01.x, t01.y, t01.z) * (1.0f - ax) + v3(t11.x, t11.y, t11.z) * ax;
+  return top * (1.0f - ay) + bot * ay;
+}
+
+GTLC_D V3 sampleDomeLight(const UniformData& ubo, const DeviceScene& s, uint32_t domeLightIndex, V3 rayDir)
+{
+  if (domeLightIndex == 0 || !(ubo.flags & FLAG_HAS_DOME)) return ld3(ubo.background);
+  float u = (atan2f(rayDir.z, rayDir.x) + 0.5f * kPi) / (2.0f * kPi);    // miss:48
+  float v = 1.0f - acosf(rayDir.y) / kPi;                                // miss:49
+  return texture_latlong(s, u, v);
+}
+
+struct LightSample { V3 dirToLight; float dist; V3 power; float invPdf; uint32_t diffuseSpecularPacked; };
+
+// ---- rp_main.chit:30-129 ------------------------------------------------------------------------
+GTLC_D void sampleLight(const UniformData& ubo, const DeviceScene& s, V4 k4, V3 surfacePos, LightSample& ls)
+{
+  const float total = (float) ubo.totalLightCount;
+  if ((k4.x * total) <= (float) ubo.sphereLightCount) {                                      // :32
+    const uint32_t n = ubo.sphereLightCount;
+    uint32_t lightIndex = (uint32_t) (k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u;   // :34
+    float4 l0 = make_float4(0, 0, 0, 0), l1 = l0, l2 = l0;   // no lights: zero-filled buffer
+    if (n != 0u) { l0 = __ldg(&s.sphereLights[lightIndex * 3 + 0]); l1 = __ldg(&s.sphereLights[lightIndex * 3 + 1]); l2 = __ldg(&s.sphereLights[lightIndex * 3 + 2]); }
+    const V3 lpos = v3(l0.x, l0.y, l0.z);
+    V2 zw; zw.x = k4.z; zw.y = k4.w;
+    V3 samplePos = lpos + sample_sphere(zw, v3(l2.x, l2.y, l2.z));                           // :40
+    V3 dir = samplePos - surfacePos;
+    ls.dist = length(dir);
+    ls.dirToLight = safe_div(dir, ls.dist);
+    V3 lightNormal = normalize(samplePos - lpos);                                            // :46
+    float cosTheta = fmaxf(0.0f, dot(-ls.dirToLight, lightNormal));
+    const float area = l1.w;
+    ls.invPdf = safe_div((area > 0.0f) ? (area * cosTheta) : 1.0f, ls.dist * ls.dist);      // :48
+    ls.power = v3(l1.x, l1.y, l1.z) * ubo.lightIntensityMultiplier;
+    ls.diffuseSpecularPacked = f2u(l0.w);
+  } else if ((k4.x * total) <= (float) (ubo.sphereLightCount + ubo.distantLightCount)) {     // :53
+    const uint32_t n = ubo.distantLightCount;
+    uint32_t lightIndex = (uint32_t) (k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u;
+    const float4 l0 = __ldg(&s.distantLights[lightIndex * 3 + 0]), l1 = __ldg(&s.distantLights[lightIndex * 3 + 1]), l2 = __ldg(&s.distantLights[lightIndex * 3 + 2]);
+    ls.dist = 100000.0f;
+    ls.dirToLight = -v3(l0.x, l0.y, l0.z);
+    ls.power = v3(l1.x, l1.y, l1.z) * ubo.lightIntensityMultiplier;
+    ls.invPdf = l2.w;
+    ls.diffuseSpecularPacked = f2u(l1.w);
+    const float angle = l0.w;
+    if (angle > 0.0f) {                                                                      // :65-74
+      V3 t1, t2;
+      orthonormal_basis(ls.dirToLight, t1, t2);
+      float phi = ((k4.z * 2.0f) * kPi) - kPi;
+      float theta = k4.w * angle;
+      ls.dirToLight = normalize(((t1 * cosf(phi) + t2 * sinf(phi)) * sinf(theta)) + ls.dirToLight * cosf(theta));
+    }
+  } else if ((k4.x * total) <= (float) (ubo.sphereLightCount + ubo.distantLightCount + ubo.rectLightCount)) {   // :76
+    const uint32_t n = ubo.rectLightCount;
+    uint32_t lightIndex = (uint32_t) (k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u;
+    const float4 l0 = __ldg(&s.rectLights[lightIndex * 3 + 0]), l1 = __ldg(&s.rectLights[lightIndex * 3 + 1]), l2 = __ldg(&s.rectLights[lightIndex * 3 + 2]);
+    const float width = l0.w, height = l1.w;
+    float sx = (k4.z - 0.5f) * width, sy = (k4.w - 0.5f) * height;                           // :83
+    V3 t0 = decode_direction(f2u(l2.x));
+    V3 t1 = decode_direction(f2u(l2.y));
+    V3 samplePos = (v3(l0.x, l0.y, l0.z) + t0 * sx) + t1 * sy;                               // :87
+    V3 dir = samplePos - surfacePos;
+    ls.dist = length(dir);
+    ls.dirToLight = safe_div(dir, ls.dist);
+    V3 lightNormal = cross(t1, t0);                                                          // :93
+    float cosTheta = fmaxf(0.0f, dot(-ls.dirToLight, lightNormal));
+    float area = width * height;
+    ls.invPdf = safe_div((area > 0.0f) ? (area * cosTheta) : 1.0f, ls.dist * ls.dist);
+    ls.power = v3(l1.x, l1.y, l1.z) * ubo.lightIntensityMultiplier;
+    ls.diffuseSpecularPacked = f2u(l2.z);
+  } else {                                                                                   // :101
+    const uint32_t n = ubo.diskLightCount;
+    uint32_t lightIndex = (uint32_t) (k4.y * (float) n); if (lightIndex > n - 1u) lightIndex = n - 1u;
+    const float4 l0 = __ldg(&s.diskLights[lightIndex * 3 + 0]), l1 = __ldg(&s.diskLights[lightIndex * 3 + 1]), l2 = __ldg(&s.diskLights[lightIndex * 3 + 2]);
+    V2 radiusXY; radiusXY.x = l0.w; radiusXY.y = l1.w;
+    V2 zw; zw.x = k4.z; zw.y = k4.w;
+    V2 sampleOnDisk = sample_disk(zw, radiusXY);
+    V3 t0 = decode_direction(f2u(l2.x));
+    V3 t1 = decode_direction(f2u(l2.y));
+    V3 samplePos = (v3(l0.x, l0.y, l0.z) + t0 * sampleOnDisk.x) + t1 * sampleOnDisk.y;
+    V3 dir = samplePos - surfacePos;
+    ls.dist = length(dir);
+    ls.dirToLight = safe_div(dir, ls.dist);
+    V3 lightNormal = cross(t1, t0);
+    float cosTheta = fmaxf(0.0f, dot(-ls.dirToLight, lightNormal));
+    float area = (radiusXY.x * radiusXY.y) * kPi;
+    ls.invPdf = safe_div((area > 0.0f) ? (area * cosTheta) : 1.0f, ls.dist * ls.dist);
+    ls.power = v3(l1.x, l1.y, l1.z) * ubo.lightIntensityMultiplier;
+    ls.diffuseSpecularPacked = f2u(l2.z);
+  }
+  ls.power *= exp2f(ubo.sensorExposure);                                                     // :127
+  ls.invPdf *= (float) ubo.totalLightCount;                                                  // :128
+}
+
+// ---- mdl_shading_state.glsl:4-98 (R4) -----------------------------------------------------------
+GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uint32_t inst, uint32_t prim, float hu, float hv,
+                                V3 rayDir, ShadingState& st, bool& isFrontFace)
+{
+  const float4 o0 = __ldg(&s.instO2W[inst * 3 + 0]), o1 = __ldg(&s.instO2W[inst * 3 + 1]), o2 = __ldg(&s.instO2W[inst * 3 + 2]);
+  const float4 w0 = __ldg(&s.instW2O[inst * 3 + 0]), w1 = __ldg(&s.instW2O[inst * 3 + 1]), w2 = __ldg(&s.instW2O[inst * 3 + 2]);
+  const uint32_t* f = s.faces + (size_t) (in.faceBase + prim) * 3;                     // :10
+  const uint32_t i0 = __ldg(f + 0), i1 = __ldg(f + 1), i2 = __ldg(f + 2);
+  const float4* vb = s.fverts + (size_t) in.vertexBase * 2;
+  const float4 a1 = __ldg(vb + (size_t) i0 * 2), a2 = __ldg(vb + (size_t) i0 * 2 + 1);   // :12-14
+  const float4 b1 = __ldg(vb + (size_t) i1 * 2), b2 = __ldg(vb + (size_t) i1 * 2 + 1);
+  const float4 c1 = __ldg(vb + (size_t) i2 * 2), c2 = __ldg(vb + (size_t) i2 * 2 + 1);
+  const V3 bc = v3((1.0f - hu) - hv, hu, hv);                                          // :16
+  const V3 p0 = v3(a1.x, a1.y, a1.z), p1 = v3(b1.x, b1.y, b1.z), p2 = v3(c1.x, c1.y, c1.z);
+  const V3 localPos = (p0 * bc.x + p1 * bc.y) + p2 * bc.z;                             // :23
+  const V3 pos = xform_point(o0, o1, o2, localPos);                                    // :24
+  V3 geomNormal = normalize(cross(p1 - p0, p2 - p0));                                  // :26
+  geomNormal = normalize(xform_dir_transposed(w0, w1, w2, geomNormal));                // :27
+  const V3 n0 = decode_direction(f2u(a2.x)), n1 = decode_direction(f2u(b2.x)), n2 = decode_direction(f2u(c2.x));  // :30-32
+  const V3 localNormal = normalize((n0 * bc.x + n1 * bc.y) + n2 * bc.z);               // :34
+  V3 normal = normalize(xform_dir_transposed(w0, w1, w2, localNormal));                // :35
+  isFrontFace = dot(geomNormal, -rayDir) >= 0.0f;                                      // :38
+  if (!isFrontFace) { geomNormal = -geomNormal; normal = -normal; }                    // :40-44
+  const V3 t0 = decode_direction(f2u(a2.y)), t1 = decode_direction(f2u(b2.y)), t2 = decode_direction(f2u(c2.y));  // :47-49
+  const V3 localTangent = normalize((t0 * bc.x + t1 * bc.y) + t2 * bc.z);              // :51
+  V3 tangent = normalize(xform_dir(o0, o1, o2, localTangent));                         // :52
+  tangent = normalize(tangent - normal * dot(tangent, normal));                        // :55
+  const float bitangentSign = (bc.x * a1.w + bc.y * b1.w) + bc.z * c1.w;               // :57
+  const V3 bitangent = cross(normal, tangent) * bitangentSign;                         // :58
+  st.u = (bc.x * a2.z + bc.y * b2.z) + bc.z * c2.z;                                    // :61-64
+  st.v = (bc.x * a2.w + bc.y * b2.w) + bc.z * c2.w;
+  st.normal = normal; st.geom_normal = geomNormal; st.position = pos;                  // :82-90
+  st.tangent_u = tangent; st.tangent_v = bitangent;
+}
+
+// ---- shade: rp_main.chit:132-493 + rp_main.miss:55-87 + rp_main.rgen:397-480 ----------------------
+// One thread per live path.  Survivors are compacted into `qout`, shadow rays appended to the shadow
+// queue, finished samples written to sampleRad[slot].
+__global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
+                                                    const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
+                                                    const uint32_t* __restrict__ perm,
+                                                    float4* shO, float4* shD, float4* shC, float4* sampleRad,
+                                                    Counters* ctr, int inIdx)
+{
+  const unsigned FULL = 0xFFFFFFFFu;
+  const uint32_t n = ctr->numPaths[inIdx];
+  const uint32_t nRounded = (n + 31u) & ~31u;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rrBounceOffset = ubo.maxBouncesAndRrBounceOffset & 0xFFFFu;           // rgen:291
+  uint32_t maxBounces = ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > kPayloadBouncesMask) maxBounces = kPayloadBouncesMask;
+  const bool nee = (ubo.flags & FLAG_NEE) != 0;
+
+  for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nRounded; it += gridDim.x * blockDim.x) {
+    bool valid = it < n;
+    bool survives = false, wantShadow = false;
+    V3 ray_origin = v3(0.0f), ray_dir = v3(0.0f), throughput = v3(0.0f), radiance = v3(0.0f);
+    V3 neeToLight = v3(0.0f), neeContrib = v3(0.0f);
+    uint32_t bitfield = 0, rng_state = 0, slot = 0;
+    if (valid) {
+      const uint32_t i = perm ? perm[it] : it;
+      const float4 ro = qin.rayO[i], rd = qin.rayD[i], th = qin.thr[i], ra = qin.rad[i];
+      const float4 h = hitTUVP[i];
+      const uint32_t inst = hitInst[i];
+      slot = qin.slot[i];
+      ray_origin = v3(ro.x, ro.y, ro.z); ray_dir = v3(rd.x, rd.y, rd.z);
+      const V3 worldRayDir = ray_dir;
+      throughput = v3(th.x, th.y, th.z); bitfield = f2u(th.w);
+      radiance = v3(ra.x, ra.y, ra.z); rng_state = f2u(ra.w);
+      const uint32_t bounce = bitfield & kPayloadBouncesMask;                          // rgen:298
+
+      if (inst == 0xFFFFFFFFu) {
+        // ---- rp_main.miss:55-87 ----
+        bitfield |= kPayloadTerminateFlag;                                             // miss:68
+        bool useFallbackDomeLight = false;
+        if (!(ubo.flags & FLAG_DOME_CAMERA_VISIBLE)) useFallbackDomeLight = (bounce == 0);   // miss:76-80
+        const uint32_t domeLightIndex = useFallbackDomeLight ? 0u : 1u;                // miss:82
+        const V3 sampleDir = normalize(quatRotateDir(ubo.domeLightRotation, worldRayDir));   // miss:83
+        const V3 rdn = sampleDomeLight(ubo, s, domeLightIndex, sampleDir) * ld3(ubo.domeLightEmissionMultiplier);  // miss:84
+        radiance += throughput * rdn;                                                  // miss:86
+      } else {
+        // ---- rp_main.chit:132-493 ----
+        const uint32_t prim = f2u(h.w);
+        const InstanceInfo in = s.instInfo[inst];
+        const bool isLeftHanded = (in.flags & 1u) != 0;                                // chit:137
+        const bool isDoubleSided = (in.flags & 2u) != 0;                               // chit:138
+        const float* mp = s.matParams + (size_t) in.material * GTLC_MATERIAL_PARAM_COUNT;
+        const int closure = s.matClosure[in.material];
+        const uint32_t mflags = s.matFlags[in.material];
+        ShadingState st; bool isFrontFace;
+        setup_shading_state(s, in, inst, prim, h.y, h.z, worldRayDir, st, isFrontFace);   // chit:143
+        const V3 normal = st.normal;                                                   // chit:147
+        uint32_t mediumIdx = (bitfield & kPayloadMediumIdxMask) >> kPayloadMediumIdxOffset; if (mediumIdx > 1u) mediumIdx = 1u;  // chit:153
+        const bool thinWalled = (mflags & kMatFlagThinWalled) != 0;                    // chit:155-158
+        if (mediumIdx > 0) {                                                           // chit:164-186
+          const float distance = h.x * ubo.metersPerSceneUnit;
+          const V3 sigma_a = mat_volume_absorption(closure, mp);
+          throughput *= v3(expf(-sigma_a.x * distance), expf(-sigma_a.y * distance), expf(-sigma_a.z * distance));
+        }
+        const float kUseMaterialIor = -1.0f;                                           // mdl_types.glsl:155
+        const V3 iorCurrent = (isFrontFace || thinWalled) ? v3(1.0f) : v3(kUseMaterialIor);   // chit:188
+        const V3 iorOther = (isFrontFace || thinWalled) ? v3(kUseMaterialIor) : v3(1.0f);     // chit:189
+        if (mflags & kMatFlagEmissive) {                                               // chit:293-343
+          if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
+          float edfPdf = 0.0f;
+          if (isFrontFace || !isDoubleSided) edfPdf = fmaxf(dot(-worldRayDir, st.normal), 0.0f) * kInvPi;   // df::diffuse_edf
+          if (edfPdf > 0.0f) {
+            V3 emission_intensity = mat_emission_intensity(closure, mp);
+            emission_intensity *= exp2f(ubo.sensorExposure);
+            radiance += (throughput * v3(kInvPi)) * emission_intensity;                // chit:335
+          }
+          if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
+        }
+        st.normal = normal;                                                            // chit:346
+        uint32_t eventType;
+        {                                                                              // chit:361-389
+          BsdfSample d;
+          d.ior1 = iorCurrent; d.ior2 = iorOther; d.k1 = -worldRayDir;
+          d.xi = rng1d_next4f(rng_state);                                              // chit:370
+          bsdf_sample(closure, mp, d, st);
+          eventType = (uint32_t) d.event_type;
+          throughput *= d.bsdf_over_pdf;                                               // chit:386
+          ray_dir = d.k2;                                                              // chit:388
+        }
+        const bool isTransmissionEvent = (eventType & BSDF_EVENT_TRANSMISSION) != 0;   // chit:391
+        if (nee && (eventType & (BSDF_EVENT_DIFFUSE | BSDF_EVENT_GLOSSY)) != 0) {      // chit:394-444
+          st.normal = normal;
+          const V4 k4 = rng1d_next4f(rng_state);                                       // chit:404
+          LightSample ls;
+          sampleLight(ubo, s, k4, st.position, ls);
+          bool neeValid = (ls.dist > 0.0f) && dot(ls.dirToLight, st.geom_normal) > 0.0f;   // chit:415
+          if (neeValid) {
+            BsdfEval e;
+            e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = ls.dirToLight;
+            bsdf_evaluate(closure, mp, e, st);                                         // chit:425
+            neeValid = (e.pdf > 0.0f);
+            if (neeValid) {
+              const V2 diffuseSpecular = unpackHalf2x16(ls.diffuseSpecularPacked);
+              const V3 neeRadiance = ls.power * ls.invPdf;
+              const V3 weight = throughput * neeRadiance;
+              neeContrib += (weight * e.bsdf_diffuse) * diffuseSpecular.x;             // chit:436
+              neeContrib += (weight * e.bsdf_glossy) * diffuseSpecular.y;              // chit:437
+            }
+          }
+          neeToLight = ls.dirToLight * ls.dist;                                        // chit:441
+        }
+        if (!thinWalled && isTransmissionEvent) {                                      // chit:447-480 (MEDIUM_STACK_SIZE 0)
+          mediumIdx = 1u - mediumIdx;                                                  // chit:473
+          bitfield &= ~kPayloadWalkMask;
+          bitfield &= ~kPayloadMediumIdxMask;
+          bitfield |= (mediumIdx << kPayloadMediumIdxOffset);
+        }
+        if (eventType == BSDF_EVENT_ABSORB) bitfield |= kPayloadTerminateFlag;         // chit:483-486
+        const V3 geomNormal = st.geom_normal * (isTransmissionEvent ? -1.0f : 1.0f);   // chit:488
+        ray_origin = offset_ray_origin(st.position, geomNormal);                       // chit:489
+      }
+
+      // ---- rp_main.rgen:397-480 ----
+      if (nee) {
+        const float lightDist = length(neeToLight);                                    // rgen:403
+        wantShadow = luminance(neeContrib) > 1e-6f && lightDist > 1e-9f;               // rgen:407
+      }
+      if (length(throughput) < 1e-9f) bitfield |= kPayloadTerminateFlag;               // rgen:441-444
+      if (bounce > rrBounceOffset) {                                                   // rgen:447-459
+        const float k1 = rng1d_next1f(rng_state);
+        const float max_throughput = fmaxf(throughput.x, fmaxf(throughput.y, throughput.z));   // rgen:101
+        const float p = fminf(max_throughput, ubo.rrInvMinTermProb);
+        if (k1 > p) bitfield |= kPayloadTerminateFlag;
+        else throughput = throughput / p;
+      }
+      bitfield++;                                                                      // rgen:480
+      const uint32_t nextBounce = bitfield & kPayloadBouncesMask;
+      survives = !(bitfield & kPayloadTerminateFlag) && nextBounce < maxBounces;       // rgen:301
+    }
+
+    // ---- compaction: warp ballot + one atomic per warp -------------------------------------------
+    const unsigned liveMask = __ballot_sync(FULL, survives);
+    uint32_t outPos = 0;
+    if (liveMask) {
+      const int leader = __ffs(liveMask) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&ctr->numPaths[inIdx ^ 1], (uint32_t) __popc(liveMask));
+      base = __shfl_sync(FULL, base, leader);
+      outPos = base + (uint32_t) __popc(liveMask & ((1u << lane) - 1u));
+    }
+    const unsigned shMask = __ballot_sync(FULL, wantShadow);
+    uint32_t shPos = 0;
+    if (shMask) {
+      const int leader = __ffs(shMask) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&ctr->numShadow, (uint32_t) __popc(shMask));
+      base = __shfl_sync(FULL, base, leader);
+      shPos = base + (uint32_t) __popc(shMask & ((1u << lane) - 1u));
+    }
+    if (valid) {
+      if (survives) {
+        qout.rayO[outPos] = make_float4(ray_origin.x, ray_origin.y, ray_origin.z, 0.0f);   // rgen:306
+        qout.rayD[outPos] = make_float4(ray_dir.x, ray_dir.y, ray_dir.z, kFloatMax);       // rgen:307
+        qout.thr[outPos] = make_float4(throughput.x, throughput.y, throughput.z, u2f(bitfield));
+        qout.rad[outPos] = make_float4(radiance.x, radiance.y, radiance.z, u2f(rng_state));
+        qout.slot[outPos] = slot;
+      } else {
+        sampleRad[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+      }
+      if (wantShadow) {
+        const float lightDist = length(neeToLight);
+        const V3 sdir = safe_div(neeToLight, lightDist);                               // rgen:404
+        shO[shPos] = make_float4(ray_origin.x, ray_origin.y, ray_origin.z, 0.01f);     // rgen:402,409
+        shD[shPos] = make_float4(sdir.x, sdir.y, sdir.z, lightDist);                   // rgen:410
+        const uint32_t target = survives ? outPos : (0x80000000u | slot);
+        shC[shPos] = make_float4(neeContrib.x, neeContrib.y, neeContrib.z, u2f(target));
+      }
+    }
+  }
+}
+
+// ---- resolve: rp_main.rgen:488-498 (+ :506-515 on the last wave) ----------------------------------
+__global__ void __launch_bounds__(256) resolve_kernel(UniformData ubo, WaveParams wp, const float4* __restrict__ sampleRad,
+                                                      float4* accum, float4* colorAov, int lastWave)
+{
+  const float invSpp = 1.0f / (float) ubo.spp;                                         // :212
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < wp.wavePixels; q += gridDim.x * blockDim.x) {
+    const uint32_t lp = wp.wavePixelBase + q;
+    float4 a4 = (wp.waveSampleBase == 0) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : accum[lp];
+    V3 pixel_color = v3(a4.x, a4.y, a4.z);
+    for (uint32_t j = 0; j < wp.waveSamples; j++) {
+      const float4 r4 = sampleRad[(size_t) j * wp.wavePixels + q];
+      V3 radiance = v3(r4.x, r4.y, r4.z);                                              // :489
+      const float maxValue = fmaxf(radiance.x, fmaxf(radiance.y, radiance.z));
+      if (maxValue > ubo.maxSampleValue) radiance *= (ubo.maxSampleValue / maxValue);  // :491-494
+      const V3 sample_color = vmax(radiance, 0.0f);                                    // :496
+      pixel_color += sample_color * invSpp;                                            // :498
+    }
+    if (!lastWave) { accum[lp] = make_float4(pixel_color.x, pixel_color.y, pixel_color.z, 0.0f); continue; }
+    const uint32_t pixelIndex = wp.pixelMap ? wp.pixelMap[lp] : lp;
+    V3 prevColor = pixel_color;                                                        // :507
+    if ((ubo.flags & FLAG_PROGRESSIVE) && ubo.sampleOffset > 0) { const float4 p4 = colorAov[pixelIndex]; prevColor = v3(p4.x, p4.y, p4.z); }  // :508-513
+    const V3 o = (prevColor * (float) ubo.sampleOffset + pixel_color * (float) ubo.spp) * ubo.invTotalSampleCount;   // :514
+    colorAov[pixelIndex] = make_float4(o.x, o.y, o.z, 1.0f);
+  }
+}
+
+} // namespace gtlc

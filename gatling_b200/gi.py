@@ -1,0 +1,376 @@
+"""Python mirror of the reference's `gi` renderer API (/root/reference/src/gi/gtl/gi/Gi.h:199-261).
+
+Same function names, argument meaning and error behaviour (GiStatus / None on failure, no exceptions
+for renderer errors), implemented over the C-ABI in include/gtlc.h.  The C++ facade with the exact
+reference signatures is include/gtl/gi/Gi.h + gatling_b200/gi_cpp/Gi.cpp; this module is what the tests
+and bench.py drive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from . import scenes as S
+
+
+class GiStatus(enum.IntEnum):  # Gi.h:32
+    Ok = 0
+    Error = 1
+
+
+class GiAovId(enum.IntEnum):  # Gi.h:34-54
+    Color = 0
+    Normal = 1
+    NEE = 2
+    Barycentrics = 3
+    Texcoords = 4
+    Bounces = 5
+    ClockCycles = 6
+    Opacity = 7
+    Tangents = 8
+    Bitangents = 9
+    ThinWalled = 10
+    ObjectId = 11
+    Depth = 12
+    FaceId = 13
+    InstanceId = 14
+    DoubleSided = 15
+    Albedo = 16
+
+
+class GiRenderBufferFormat(enum.IntEnum):  # Gi.h:68-73
+    Int32 = 0
+    Float32 = 1
+    Float32Vec4 = 2
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def _lib():
+    return L.load()
+
+
+def giLastError() -> str:
+    return (_lib().gtlc_last_error() or b"").decode()
+
+
+# ---- lifecycle (Gi.h:199-200) ---------------------------------------------------------------------
+def giInitialize(device_index: int = -1) -> GiStatus:
+    p = L.InitParams(device_index, 0)
+    return GiStatus(_lib().gtlc_initialize(C.byref(p)))
+
+
+def giTerminate():
+    _lib().gtlc_terminate()
+
+
+# ---- scene (Gi.h:220-221) ---------------------------------------------------------------------------
+def giCreateScene():
+    return _lib().gtlc_scene_create() or None
+
+
+def giDestroyScene(scene):
+    _lib().gtlc_scene_destroy(scene)
+
+
+# ---- materials (Gi.h:204-207).  The reference takes MaterialX / MDL; the binding takes the lowered
+# closure + parameter block (see gtlc.h) -- gi_cpp/Gi.cpp does the MaterialX-XML lowering. ------------
+def giCreateMaterial(scene, closure: int, params: Sequence[float], name: str = ""):
+    d = L.MaterialDesc()
+    d.closure = closure
+    d.name = name.encode() if name else None
+    arr = np.zeros(48, np.float32)
+    arr[:len(params)] = params
+    d.params = (C.c_float * 48)(*[float(x) for x in arr])
+    return _lib().gtlc_material_create(scene, C.byref(d)) or None
+
+
+def giDestroyMaterial(mat):
+    _lib().gtlc_material_destroy(mat)
+
+
+# ---- meshes (Gi.h:209-216) ----------------------------------------------------------------------------
+def giCreateMesh(scene, vertices: np.ndarray, faces: np.ndarray, *, id: int = 0, isDoubleSided=True, isLeftHanded=False,
+                 name: str = "", faceIds: Optional[np.ndarray] = None):
+    v = np.ascontiguousarray(vertices)
+    assert v.dtype.itemsize == 48, "vertices must be GiVertex records (48 bytes)"
+    f = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
+    d = L.MeshDesc()
+    d.faceCount = len(f)
+    d.faces = f.ctypes.data
+    fid = None
+    if faceIds is not None:
+        fid = np.ascontiguousarray(faceIds, np.int32)
+        d.faceIds = fid.ctypes.data
+    d.id = id
+    d.isDoubleSided = int(isDoubleSided)
+    d.isLeftHanded = int(isLeftHanded)
+    d.name = name.encode() if name else None
+    d.maxFaceId = int(fid.max()) if fid is not None and len(fid) else max(len(f) - 1, 0)
+    d.vertexCount = len(v)
+    d.vertices = v.ctypes.data
+    return _lib().gtlc_mesh_create(scene, C.byref(d)) or None
+
+
+def giSetMeshTransform(mesh, mat4x4):
+    m = np.ascontiguousarray(mat4x4, np.float32).reshape(16)
+    _lib().gtlc_mesh_set_transform(mesh, m.ctypes.data)
+
+
+def giSetMeshInstanceTransforms(mesh, transforms):
+    t = np.ascontiguousarray(transforms, np.float32).reshape(-1, 16)
+    _lib().gtlc_mesh_set_instance_transforms(mesh, len(t), t.ctypes.data)
+
+
+def giSetMeshInstanceIds(mesh, ids):
+    a = np.ascontiguousarray(ids, np.int32)
+    _lib().gtlc_mesh_set_instance_ids(mesh, len(a), a.ctypes.data)
+
+
+def giSetMeshMaterial(mesh, mat):
+    _lib().gtlc_mesh_set_material(mesh, mat or 0)
+
+
+def giSetMeshVisibility(mesh, visible: bool):
+    _lib().gtlc_mesh_set_visibility(mesh, int(visible))
+
+
+def giDestroyMesh(mesh):
+    _lib().gtlc_mesh_destroy(mesh)
+
+
+# ---- lights (Gi.h:223-257) -----------------------------------------------------------------------------
+def giCreateSphereLight(scene): return _lib().gtlc_sphere_light_create(scene) or None
+def giDestroySphereLight(scene, l): _lib().gtlc_sphere_light_destroy(scene, l)
+def giSetSphereLightPosition(l, p): _lib().gtlc_sphere_light_set_position(l, _f3(p))
+def giSetSphereLightBaseEmission(l, rgb): _lib().gtlc_sphere_light_set_base_emission(l, _f3(rgb))
+def giSetSphereLightRadius(l, rx, ry, rz): _lib().gtlc_sphere_light_set_radius(l, rx, ry, rz)
+def giSetSphereLightDiffuseSpecular(l, d, s): _lib().gtlc_sphere_light_set_diffuse_specular(l, d, s)
+def giCreateDistantLight(scene): return _lib().gtlc_distant_light_create(scene) or None
+def giDestroyDistantLight(scene, l): _lib().gtlc_distant_light_destroy(scene, l)
+def giSetDistantLightDirection(l, d): _lib().gtlc_distant_light_set_direction(l, _f3(d))
+def giSetDistantLightBaseEmission(l, rgb): _lib().gtlc_distant_light_set_base_emission(l, _f3(rgb))
+def giSetDistantLightAngle(l, a): _lib().gtlc_distant_light_set_angle(l, a)
+def giSetDistantLightDiffuseSpecular(l, d, s): _lib().gtlc_distant_light_set_diffuse_specular(l, d, s)
+def giCreateRectLight(scene): return _lib().gtlc_rect_light_create(scene) or None
+def giDestroyRectLight(scene, l): _lib().gtlc_rect_light_destroy(scene, l)
+def giSetRectLightOrigin(l, o): _lib().gtlc_rect_light_set_origin(l, _f3(o))
+def giSetRectLightTangents(l, t0, t1): _lib().gtlc_rect_light_set_tangents(l, _f3(t0), _f3(t1))
+def giSetRectLightBaseEmission(l, rgb): _lib().gtlc_rect_light_set_base_emission(l, _f3(rgb))
+def giSetRectLightDimensions(l, w, h): _lib().gtlc_rect_light_set_dimensions(l, w, h)
+def giSetRectLightDiffuseSpecular(l, d, s): _lib().gtlc_rect_light_set_diffuse_specular(l, d, s)
+def giCreateDiskLight(scene): return _lib().gtlc_disk_light_create(scene) or None
+def giDestroyDiskLight(scene, l): _lib().gtlc_disk_light_destroy(scene, l)
+def giSetDiskLightOrigin(l, o): _lib().gtlc_disk_light_set_origin(l, _f3(o))
+def giSetDiskLightTangents(l, t0, t1): _lib().gtlc_disk_light_set_tangents(l, _f3(t0), _f3(t1))
+def giSetDiskLightBaseEmission(l, rgb): _lib().gtlc_disk_light_set_base_emission(l, _f3(rgb))
+def giSetDiskLightRadius(l, rx, ry): _lib().gtlc_disk_light_set_radius(l, rx, ry)
+def giSetDiskLightDiffuseSpecular(l, d, s): _lib().gtlc_disk_light_set_diffuse_specular(l, d, s)
+
+
+def giCreateDomeLight(scene, texels: np.ndarray):
+    """The reference takes a file path and decodes through imgio (out of scope); here: lat-long float32[h, w, 4]."""
+    t = np.ascontiguousarray(texels, np.float32)
+    return _lib().gtlc_dome_light_create(scene, t.shape[1], t.shape[0], t.ctypes.data) or None
+
+
+def giDestroyDomeLight(l): _lib().gtlc_dome_light_destroy(l)
+def giSetDomeLightRotation(l, quat): _lib().gtlc_dome_light_set_rotation(l, (C.c_float * 4)(*quat))
+def giSetDomeLightBaseEmission(l, rgb): _lib().gtlc_dome_light_set_base_emission(l, _f3(rgb))
+def giSetDomeLightDiffuseSpecular(l, d, s): _lib().gtlc_dome_light_set_diffuse_specular(l, d, s)
+
+
+# ---- render buffers (Gi.h:259-261) ---------------------------------------------------------------------
+class RenderBuffer:
+    def __init__(self, handle, width, height, fmt):
+        self.handle, self.width, self.height, self.format = handle, width, height, fmt
+
+    def mem(self) -> np.ndarray:
+        """giGetRenderBufferMem: the persistently mapped (pinned) host memory, row 0 = bottom."""
+        ptr = _lib().gtlc_render_buffer_mem(self.handle)
+        comps = 4 if self.format == GiRenderBufferFormat.Float32Vec4 else 1
+        ctype = C.c_int32 if self.format == GiRenderBufferFormat.Int32 else C.c_float
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(self.height, self.width, comps))
+        return arr
+
+    def device_ptr(self) -> int:
+        return _lib().gtlc_render_buffer_device_mem(self.handle)
+
+
+def giCreateRenderBuffer(width, height, fmt=GiRenderBufferFormat.Float32Vec4) -> Optional[RenderBuffer]:
+    h = _lib().gtlc_render_buffer_create(width, height, int(fmt))
+    return RenderBuffer(h, width, height, fmt) if h else None
+
+
+def giDestroyRenderBuffer(rb: RenderBuffer):
+    _lib().gtlc_render_buffer_destroy(rb.handle)
+
+
+def giGetRenderBufferMem(rb: RenderBuffer) -> np.ndarray:
+    return rb.mem()
+
+
+# ---- render (Gi.h:218) ----------------------------------------------------------------------------------
+def _camera_c(cam: S.Camera) -> L.CameraDesc:
+    c = L.CameraDesc()
+    c.position = _f3(cam.position)
+    c.forward = _f3(cam.forward)
+    c.up = _f3(cam.up)
+    for k in ("vfov", "fStop", "focusDistance", "focalLength", "clipStart", "clipEnd", "exposure"):
+        setattr(c, k, float(getattr(cam, k)))
+    return c
+
+
+def _settings_c(st: S.RenderSettings) -> L.RenderSettings:
+    s = L.RenderSettings()
+    for name, ctype in L.RenderSettings._fields_:
+        v = getattr(st, name)
+        setattr(s, name, float(v) if ctype is C.c_float else int(v))
+    return s
+
+
+def giRender(scene, camera: S.Camera, settings: S.RenderSettings, aov_bindings, dome_light=None) -> GiStatus:
+    """aov_bindings: list of (GiAovId, clearValue bytes-or-floats, RenderBuffer)."""
+    arr = (L.AovBinding * len(aov_bindings))()
+    for i, (aov, clear, rb) in enumerate(aov_bindings):
+        arr[i].aovId = int(aov)
+        raw = bytes(clear) if isinstance(clear, (bytes, bytearray)) else np.asarray(clear, np.float32).tobytes()
+        raw = (raw + b"\0" * 16)[:16]
+        arr[i].clearValue = (C.c_uint8 * 16)(*raw)
+        arr[i].renderBuffer = rb.handle
+    p = L.RenderParams()
+    p.aovBindingCount = len(aov_bindings)
+    p.aovBindings = arr
+    p.camera = _camera_c(camera)
+    p.domeLight = dome_light or 0
+    p.renderSettings = _settings_c(settings)
+    p.scene = scene
+    return GiStatus(_lib().gtlc_render(C.byref(p)))
+
+
+# ---- extensions (no Gi.h counterpart) ---------------------------------------------------
+def set_shard(scene, rank, world_size, tile=64):
+    _lib().gtlc_scene_set_shard(scene, rank, world_size, tile)
+
+
+def set_tuning(**kw):
+    t = L.Tuning()
+    _lib().gtlc_get_tuning(C.byref(t))
+    for k, v in kw.items():
+        setattr(t, k, v)
+    _lib().gtlc_set_tuning(C.byref(t))
+
+
+def get_stats() -> dict:
+    s = L.Stats()
+    _lib().gtlc_get_stats(C.byref(s))
+    return s.as_dict()
+
+
+HIT_DTYPE = np.dtype([("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<u4"), ("inst", "<u4")])
+
+
+def trace_rays(scene, rays: np.ndarray, any_hit=False, want_visits=False):
+    r = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    hits = np.zeros(len(r), HIT_DTYPE)
+    visits = np.zeros((len(r), 2), np.uint32) if want_visits else None
+    st = _lib().gtlc_trace_rays(scene, r.ctypes.data, len(r), int(any_hit), hits.ctypes.data,
+                                visits.ctypes.data if want_visits else None)
+    if st != 0:
+        raise RuntimeError("gtlc_trace_rays failed: " + giLastError())
+    return (hits, visits) if want_visits else hits
+
+
+def get_bvh(scene):
+    """(nodes uint8[n*80], tris float32[m*12]) copies of the host BVH8."""
+    v = L.BvhView()
+    if _lib().gtlc_scene_get_bvh(scene, C.byref(v)) != 0:
+        raise RuntimeError("gtlc_scene_get_bvh failed: " + giLastError())
+    nodes = np.ctypeslib.as_array(C.cast(v.nodes, C.POINTER(C.c_uint8)), shape=(v.nodeCount * 80,)).copy()
+    tris = np.ctypeslib.as_array(C.cast(v.triangles, C.POINTER(C.c_float)), shape=(v.triCount * 12,)).copy() if v.triCount else np.zeros(0, np.float32)
+    return nodes, tris
+
+
+# ---- SceneDesc -> gi calls (what hdGatling's prim sync does, src/hdGatling/mesh.cpp:470-610) --------------
+class BuiltScene:
+    def __init__(self, desc: S.SceneDesc):
+        self.desc = desc
+        self.scene = giCreateScene()
+        self.materials = [giCreateMaterial(self.scene, m.closure, m.params, m.name) for m in desc.materials]
+        self.meshes = []
+        for m in desc.meshes:
+            h = giCreateMesh(self.scene, m.vertices, m.faces, id=m.object_id, isDoubleSided=m.double_sided,
+                             isLeftHanded=m.left_handed, name=m.name)
+            if h is None:
+                raise RuntimeError("giCreateMesh failed: " + giLastError())
+            giSetMeshTransform(h, m.transform)
+            if m.instance_transforms is not None:
+                giSetMeshInstanceTransforms(h, m.instance_transforms)
+            giSetMeshMaterial(h, self.materials[m.material])
+            self.meshes.append(h)
+        self.lights = []
+        for l in desc.sphere_lights:
+            h = giCreateSphereLight(self.scene)
+            giSetSphereLightPosition(h, l.position); giSetSphereLightBaseEmission(h, l.base_emission)
+            giSetSphereLightRadius(h, *l.radius); giSetSphereLightDiffuseSpecular(h, l.diffuse, l.specular)
+            self.lights.append(("sphere", h))
+        for l in desc.distant_lights:
+            h = giCreateDistantLight(self.scene)
+            giSetDistantLightDirection(h, l.direction); giSetDistantLightBaseEmission(h, l.base_emission)
+            giSetDistantLightAngle(h, l.angle); giSetDistantLightDiffuseSpecular(h, l.diffuse, l.specular)
+            self.lights.append(("distant", h))
+        for l in desc.rect_lights:
+            h = giCreateRectLight(self.scene)
+            giSetRectLightOrigin(h, l.origin); giSetRectLightTangents(h, l.t0, l.t1); giSetRectLightBaseEmission(h, l.base_emission)
+            giSetRectLightDimensions(h, l.width, l.height); giSetRectLightDiffuseSpecular(h, l.diffuse, l.specular)
+            self.lights.append(("rect", h))
+        for l in desc.disk_lights:
+            h = giCreateDiskLight(self.scene)
+            giSetDiskLightOrigin(h, l.origin); giSetDiskLightTangents(h, l.t0, l.t1); giSetDiskLightBaseEmission(h, l.base_emission)
+            giSetDiskLightRadius(h, *l.radius); giSetDiskLightDiffuseSpecular(h, l.diffuse, l.specular)
+            self.lights.append(("disk", h))
+        self.dome = None
+        if desc.dome_light is not None:
+            self.dome = giCreateDomeLight(self.scene, desc.dome_light.texels)
+            giSetDomeLightRotation(self.dome, desc.dome_light.rotation)
+            giSetDomeLightBaseEmission(self.dome, desc.dome_light.base_emission)
+        self.color = None
+
+    def render(self, spp=None, settings=None) -> np.ndarray:
+        """One giRender call; returns the colour AOV (float32[h, w, 4], row 0 = bottom).  Successive calls
+        accumulate (sampleOffset) exactly like the reference."""
+        d = self.desc
+        if self.color is None:
+            self.color = giCreateRenderBuffer(d.width, d.height, GiRenderBufferFormat.Float32Vec4)
+            if self.color is None:
+                raise RuntimeError("giCreateRenderBuffer failed: " + giLastError())
+        st = settings or d.settings
+        if spp is not None:
+            import dataclasses
+            st = dataclasses.replace(st, spp=spp)
+        status = giRender(self.scene, d.camera, st, [(GiAovId.Color, d.clear_color, self.color)], self.dome)
+        if status != GiStatus.Ok:
+            raise RuntimeError("giRender failed: " + giLastError())
+        return self.color.mem()
+
+    def close(self):
+        if self.scene is None:
+            return
+        if self.color is not None:
+            giDestroyRenderBuffer(self.color)
+        for h in self.meshes:
+            giDestroyMesh(h)
+        for kind, h in self.lights:
+            {"sphere": giDestroySphereLight, "distant": giDestroyDistantLight, "rect": giDestroyRectLight, "disk": giDestroyDiskLight}[kind](self.scene, h)
+        if self.dome:
+            giDestroyDomeLight(self.dome)
+        for h in self.materials:
+            giDestroyMaterial(h)
+        giDestroyScene(self.scene)
+        self.scene = None

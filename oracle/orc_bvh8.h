@@ -1,2 +1,116 @@
-// ORACLE -- TEST INFRASTRUCTURE ONLY.  BVH8 walker (filled in once the node layout is fixed).
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see orc_math.h header).
+//
+// Scalar CPU walker over the PRODUCT's compressed BVH8 bytes (layout: gatling_b200/csrc/bvh8.h).
+// Purpose: (1) check on the CPU that the host-built BVH8 returns the same closest hits as the oracle's
+// own binary BVH; (2) produce the exact per-ray node / triangle visit counts that define the
+// algorithmic bytes of the traversal roofline (32 + 20 + 80*n_nodes + 48*n_tris), by
+// restating the kernel's traversal order: children in octant order (slot ^ octinv, highest first),
+// siblings deferred as one stack entry, a node's triangles tested right after its slab tests in
+// ascending slot order, no re-test of a deferred child's own box.
 #pragma once
+
+namespace orc {
+
+static inline uint32_t ld32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline float ldf(const uint8_t* p) { float v; memcpy(&v, p, 4); return v; }
+
+static inline uint32_t bvh8_node_hitmask(const uint8_t* nd, V3 o, V3 d, V3 idir, float tmin, float tbest, uint32_t octinv)
+{
+  const uint32_t e = ld32(nd + 12);
+  const float sx = uintBitsToFloat((e & 0xFFu) << 23) * idir.x;
+  const float sy = uintBitsToFloat(((e >> 8) & 0xFFu) << 23) * idir.y;
+  const float sz = uintBitsToFloat(((e >> 16) & 0xFFu) << 23) * idir.z;
+  const float ox = (ldf(nd + 0) - o.x) * idir.x;
+  const float oy = (ldf(nd + 4) - o.y) * idir.y;
+  const float oz = (ldf(nd + 8) - o.z) * idir.z;
+  const uint8_t* meta = nd + 24;
+  const uint8_t* qlox = nd + 32; const uint8_t* qloy = nd + 40; const uint8_t* qloz = nd + 48;
+  const uint8_t* qhix = nd + 56; const uint8_t* qhiy = nd + 64; const uint8_t* qhiz = nd + 72;
+  uint32_t hitmask = 0;
+  for (int i = 0; i < 8; i++) {
+    const float nx = (float) (d.x < 0.0f ? qhix[i] : qlox[i]), fx = (float) (d.x < 0.0f ? qlox[i] : qhix[i]);
+    const float ny = (float) (d.y < 0.0f ? qhiy[i] : qloy[i]), fy = (float) (d.y < 0.0f ? qloy[i] : qhiy[i]);
+    const float nz = (float) (d.z < 0.0f ? qhiz[i] : qloz[i]), fz = (float) (d.z < 0.0f ? qloz[i] : qhiz[i]);
+    const float tnx = fmaf(nx, sx, ox), tny = fmaf(ny, sy, oy), tnz = fmaf(nz, sz, oz);
+    const float tfx = fmaf(fx, sx, ox), tfy = fmaf(fy, sy, oy), tfz = fmaf(fz, sz, oz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest)) * 1.0000004f;
+    const uint32_t m = meta[i];
+    if (tn <= tf && m != 0u) {
+      const uint32_t bits = m >> 5, lo5 = m & 31u;
+      const uint32_t idx = (lo5 >= 24u) ? (24u + ((lo5 & 7u) ^ octinv)) : lo5;
+      hitmask |= bits << idx;
+    }
+  }
+  return hitmask;
+}
+
+static inline void bvh8_trace_one(const uint8_t* nodes, const float* tris, V3 o, V3 d, float tmin, float tmax, bool anyHit,
+                                  Hit& best, uint32_t& nNodes, uint32_t& nTris)
+{
+  best.t = -1.0f; best.u = best.v = 0.0f; best.prim = best.inst = 0xFFFFFFFFu;
+  nNodes = nTris = 0;
+  if (!(tmax > tmin)) return;
+  RayPre rp = ray_precompute(d);
+  V3 idir = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+  const uint32_t octinv = 7u - oct;
+  float bt = tmax;
+  uint32_t stackX[64], stackY[64]; int sp = 0;
+  uint32_t Gx = 0, Gy = 0x80000000u;
+  while (true) {
+    uint32_t Tx = 0, Ty = 0;
+    if (Gy & 0xFF000000u) {
+      const uint32_t hits_imask = Gy;
+      uint32_t bit = 31; while (!(hits_imask & (1u << bit))) bit--;
+      Gy &= ~(1u << bit);
+      if (Gy & 0xFF000000u) { stackX[sp] = Gx; stackY[sp] = Gy; sp++; }
+      const uint32_t slot = (bit - 24u) ^ octinv;
+      const uint32_t below = (slot == 0) ? 0u : (hits_imask & ((1u << slot) - 1u));
+      const uint32_t rel = (uint32_t) __builtin_popcount(below);
+      const uint8_t* nd = nodes + (size_t) (Gx + rel) * 80;
+      nNodes++;
+      const uint32_t hm = bvh8_node_hitmask(nd, o, d, idir, tmin, bt, octinv);
+      Gx = ld32(nd + 16); Gy = (hm & 0xFF000000u) | (ld32(nd + 12) >> 24);
+      Tx = ld32(nd + 20); Ty = hm & 0x00FFFFFFu;
+    }
+    bool done = false;
+    while (Ty) {
+      const uint32_t j = (uint32_t) __builtin_ctz(Ty);
+      Ty &= Ty - 1u;
+      const float* tp = tris + (size_t) (Tx + j) * 12;
+      nTris++;
+      float t, u, v;
+      if (tri_intersect(rp, o, v3(tp[0], tp[1], tp[2]), v3(tp[4], tp[5], tp[6]), v3(tp[8], tp[9], tp[10]), t, u, v)) {
+        if (t > tmin && t < tmax) {
+          const uint32_t prim = floatBitsToUint(tp[3]), inst = floatBitsToUint(tp[7]);
+          if (anyHit) { best.t = t; best.u = u; best.v = v; best.prim = prim; best.inst = inst; done = true; break; }
+          if (hit_better(t, inst, prim, best)) { best.t = t; best.u = u; best.v = v; best.prim = prim; best.inst = inst; bt = t; }
+        }
+      }
+    }
+    if (done) return;
+    if (!(Gy & 0xFF000000u)) {
+      if (sp == 0) return;
+      sp--; Gx = stackX[sp]; Gy = stackY[sp];
+    }
+  }
+}
+
+} // namespace orc
+
+extern "C" void orc_bvh8_trace(const void* nodes, uint32_t nodeCount, const void* tris, uint32_t triCount, const float* rays, uint32_t n,
+                               int anyHit, void* hitsOut, void* visitsOut)
+{
+  (void) nodeCount; (void) triCount;
+  orc::Hit* hits = (orc::Hit*) hitsOut;
+  uint32_t* visits = (uint32_t*) visitsOut;
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < (int) n; i++) {
+    const float* r = &rays[(size_t) i * 8];
+    orc::Hit h; uint32_t nn, nt;
+    orc::bvh8_trace_one((const uint8_t*) nodes, (const float*) tris, orc::v3(r[0], r[1], r[2]), orc::v3(r[4], r[5], r[6]), r[3], r[7], anyHit != 0, h, nn, nt);
+    hits[i] = h;
+    if (visits) { visits[2 * (size_t) i] = nn; visits[2 * (size_t) i + 1] = nt; }
+  }
+}

@@ -1,0 +1,196 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs.  Bars: traversal hit records bit-exact (t, u, v, primitive,
+instance) and visit counts identical; images |a-b| <= 1e-3 + 1e-3|b| on >= 99.9 % of channels and
+RMSE < 1e-3 at identical spp/settings."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from gatling_b200 import scenes
+from oracle import orc
+from helpers import image_metrics, random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _trace_parity(gi, desc, rays):
+    b = gi.BuiltScene(desc)
+    try:
+        o = orc.OracleScene(desc)
+        nodes, tris = gi.get_bvh(b.scene)
+        h_gpu, v_gpu = gi.trace_rays(b.scene, rays, want_visits=True)
+        h_ref = o.trace(rays)
+        h_walk, v_walk = orc.bvh8_trace(nodes, tris, rays)
+        for k in ("prim", "inst", "t", "u", "v"):
+            assert np.array_equal(h_gpu[k], h_ref[k]), "closest hit field %s differs from the oracle" % k
+        assert np.array_equal(v_gpu, v_walk), "node/triangle visit counts differ from the oracle's BVH8 walk"
+        a_gpu = gi.trace_rays(b.scene, rays, any_hit=True)
+        a_ref = o.trace(rays, any_hit=True)
+        assert np.array_equal(a_gpu["t"] >= 0, a_ref["t"] >= 0), "any-hit occlusion differs"
+        return h_gpu
+    finally:
+        b.close()
+
+
+def test_trace_parity_cornell(gpu):
+    d = scenes.cornell(96, 96, spp=1)
+    cam = orc.camera_rays(d, 0)
+    cam[:, 3] = 0.0
+    cam[:, 7] = 3.0e38
+    rays = np.concatenate([cam, random_rays(50000, 7)])
+    h = _trace_parity(gpu, d, rays)
+    assert (h["inst"] != 0xFFFFFFFF).mean() > 0.5
+
+
+def test_trace_parity_random_triangles(gpu):
+    d = scenes.random_triangles(100000, 64, 64, spp=1)
+    cam = orc.camera_rays(d, 0)
+    cam[:, 3] = 0.0
+    cam[:, 7] = 3.0e38
+    short = random_rays(20000, 11, tmax=0.05)       # shadow-like short segments
+    rays = np.concatenate([cam, random_rays(200000, 3), short])
+    _trace_parity(gpu, d, rays)
+
+
+def test_trace_edge_cases(gpu):
+    d = scenes.cornell(8, 8, spp=1)
+    rays = random_rays(64, 5)
+    rays[:16, 7] = 0.0            # empty interval (disabled shadow ray, rgen:409-410)
+    rays[16:32, 3] = 5.0          # tMin beyond the scene
+    rays[32:40, 4:7] = [0.0, 1.0, 0.0]   # axis-aligned directions (zero components)
+    rays[40:48, 4:7] = [0.0, 0.0, -1.0]
+    _trace_parity(gpu, d, rays)
+    b = gpu.BuiltScene(d)
+    try:
+        h = gpu.trace_rays(b.scene, np.zeros((0, 8), np.float32))   # empty queue
+        assert len(h) == 0
+    finally:
+        b.close()
+
+
+def _render_parity(gi, desc, rmse_bar=1e-3, within_bar=0.999):
+    b = gi.BuiltScene(desc)
+    try:
+        o = orc.OracleScene(desc)
+        img = b.render().copy()
+        ref, _, rays = o.render()
+        st = gi.get_stats()
+        rmse, within = image_metrics(img, ref)
+        assert rmse < rmse_bar, "RMSE %.3e" % rmse
+        assert within >= within_bar, "only %.5f of channels within tolerance" % within
+        assert st["closestRays"] == rays[0] and st["shadowRays"] == rays[1], (st, rays)
+        assert np.all(img[..., 3] == 1.0)
+        return img, ref
+    finally:
+        b.close()
+
+
+def test_render_parity_cornell(gpu):
+    _render_parity(gpu, scenes.cornell(128, 128, spp=16, max_bounces=4))
+
+
+def test_render_parity_random_triangles(gpu):
+    _render_parity(gpu, scenes.random_triangles(50000, 160, 90, spp=4, max_bounces=8))
+
+
+def _lit_cornell(w=96, h=96, spp=8):
+    d = scenes.cornell(w, h, spp=spp, max_bounces=5)
+    d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
+    d.rect_lights.append(scenes.RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(12, 12, 12), width=0.6, height=0.6))
+    d.sphere_lights.append(scenes.SphereLight(position=(0.5, -0.5, 0.2), base_emission=(4, 3, 2), radius=(0.1, 0.1, 0.1)))
+    d.distant_lights.append(scenes.DistantLight(direction=(0.2, 0.9, -0.4), base_emission=(1.0, 1.0, 1.2), angle=0.05))
+    d.disk_lights.append(scenes.DiskLight(origin=(-0.6, 0.0, 0.5), t0=(0, 1, 0), t1=(0, 0, 1), base_emission=(3, 5, 3), radius=(0.2, 0.15)))
+    return d
+
+
+def test_render_parity_nee_all_light_types(gpu):
+    _render_parity(gpu, _lit_cornell())
+
+
+def test_render_parity_settings_variants(gpu):
+    d = scenes.cornell(64, 64, spp=4, max_bounces=6)
+    d.settings = dataclasses.replace(d.settings, filterImportanceSampling=False, rrBounceOffset=1, maxSampleValue=2.0)
+    _render_parity(gpu, d)
+    d.settings = dataclasses.replace(d.settings, jitteredSampling=False, clippingPlanes=True)
+    d.camera = dataclasses.replace(d.camera, clipStart=6.5, clipEnd=7.6)
+    _render_parity(gpu, d)
+    d.settings = dataclasses.replace(d.settings, depthOfField=True, jitteredSampling=True, clippingPlanes=False)
+    d.camera = dataclasses.replace(d.camera, fStop=8.0, focusDistance=7.0, focalLength=0.5)
+    _render_parity(gpu, d)
+
+
+def test_progressive_accumulation(gpu):
+    d = scenes.cornell(64, 64, spp=4, max_bounces=4)
+    b = gpu.BuiltScene(d)
+    try:
+        o = orc.OracleScene(d)
+        img1 = b.render().copy()
+        img2 = b.render().copy()          # second giRender call refines: sampleOffset = 4
+        ref1, _, _ = o.render(sample_offset=0)
+        ref2, _, _ = o.render(sample_offset=4, prev=ref1)
+        for a, r in ((img1, ref1), (img2, ref2)):
+            rmse, within = image_metrics(a, r)
+            assert rmse < 1e-3 and within >= 0.999
+        # changing the camera resets the accumulation (Gi.cpp:1859-1987)
+        d2 = dataclasses.replace(d, camera=dataclasses.replace(d.camera, vfov=0.5))
+        b.desc = d2
+        img3 = b.render().copy()
+        ref3, _, _ = orc.OracleScene(d2).render()
+        rmse, within = image_metrics(img3, ref3)
+        assert rmse < 1e-3 and within >= 0.999
+    finally:
+        b.close()
+
+
+def test_wave_splitting_is_invisible(gpu):
+    """Small path pools force many waves / pixel chunks; pixels must not change."""
+    d = scenes.cornell(64, 48, spp=6, max_bounces=4)
+    b = gpu.BuiltScene(d)
+    try:
+        full = b.render().copy()
+    finally:
+        b.close()
+    for pool in (64 * 48 * 2, 1500):
+        gpu.set_tuning(maxPathsPerWave=pool)
+        b = gpu.BuiltScene(d)
+        try:
+            img = b.render().copy()
+        finally:
+            b.close()
+            gpu.set_tuning(maxPathsPerWave=1 << 24)
+        assert np.array_equal(img, full), "pool %d changed the image" % pool
+
+
+def test_shard_sum_equals_full(gpu):
+    d = _lit_cornell(80, 64, spp=4)
+    b = gpu.BuiltScene(d)
+    try:
+        full = b.render().copy()
+    finally:
+        b.close()
+    acc = np.zeros_like(full)
+    for rank in range(3):
+        b = gpu.BuiltScene(d)
+        try:
+            gpu.set_shard(b.scene, rank, 3, 16)
+            part = b.render().copy()
+            o, _, _ = orc.OracleScene(d).render(shard=(rank, 3, 16))
+            rmse, within = image_metrics(part, o)
+            assert rmse < 1e-3 and within >= 0.999
+            acc += part
+        finally:
+            b.close()
+    assert np.array_equal(acc, full)
+
+
+def test_errors_are_loud(gpu):
+    d = scenes.cornell(16, 16, spp=1)
+    b = gpu.BuiltScene(d)
+    try:
+        st = dataclasses.replace(d.settings, mediumStackSize=2)
+        with pytest.raises(RuntimeError):
+            b.render(settings=st)
+        assert "mediumStackSize" in gpu.giLastError()
+    finally:
+        b.close()
