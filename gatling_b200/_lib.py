@@ -61,7 +61,7 @@ class Stats(C.Structure):
                 ("kernelLaunches", C.c_uint64), ("paths", C.c_uint64), ("msTotal", C.c_float), ("msTraceClosest", C.c_float),
                 ("msTraceAny", C.c_float), ("msShade", C.c_float), ("msRaygen", C.c_float), ("msSort", C.c_float),
                 ("msResolve", C.c_float), ("msBvhBuild", C.c_float), ("bvhNodeCount", C.c_uint32), ("bvhTriCount", C.c_uint32),
-                ("bvhMaxDepth", C.c_uint32), ("reserved", C.c_uint32)]
+                ("bvhMaxDepth", C.c_uint32), ("maxNodeVisitsPerRay", C.c_uint32), ("nonFiniteRays", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

@@ -206,19 +206,24 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     int childAtSlot[8]; for (int s = 0; s < 8; s++) childAtSlot[s] = -1;
     for (int i = 0; i < n; i++) childAtSlot[slotOf[i]] = i;
 
-    // ---- quantisation grid ------------------------------------------------------------------
-    uint32_t ebits[3]; double scale[3];
+    // ---- quantisation grid: origin one quantum below the node's lower corner and 251 quanta of extent,
+    // so that every child bound can be padded by a safety quantum on BOTH sides (the slab test's
+    // 2^15-bias arithmetic is accurate to ~1/512 quantum; see traverse.cuh) ----------------------
+    uint32_t ebits[3]; double scale[3]; float porigin[3];
     for (int k = 0; k < 3; k++) {
       double ext = (double) pb.hi[k] - (double) pb.lo[k];
-      int e = (ext > 0.0) ? (int) std::ceil(std::log2(ext / 253.0)) : -126;
-      if (e < -126) e = -126;
-      if (e > 127) e = 127;
-      while (ext / std::ldexp(1.0, e) > 253.0 && e < 127) e++;
+      int e = (ext > 0.0) ? (int) std::ceil(std::log2(ext / 250.0)) : -100;
+      if (e < -100) e = -100;
+      if (e > 100) e = 100;
+      while (ext / std::ldexp(1.0, e) > 250.0 && e < 100) e++;
       ebits[k] = (uint32_t) (e + 127);
       scale[k] = std::ldexp(1.0, e);
+      float po = (float) ((double) pb.lo[k] - scale[k]);
+      while ((double) po > (double) pb.lo[k] - 0.75 * scale[k]) po = std::nextafterf(po, -3.402823466e38f);
+      porigin[k] = po;
     }
     Bvh8Node node; std::memset(&node, 0, sizeof(node));
-    std::memcpy(&node.w[0], &pb.lo[0], 4); std::memcpy(&node.w[1], &pb.lo[1], 4); std::memcpy(&node.w[2], &pb.lo[2], 4);
+    std::memcpy(&node.w[0], &porigin[0], 4); std::memcpy(&node.w[1], &porigin[1], 4); std::memcpy(&node.w[2], &porigin[2], 4);
     uint8_t meta[8] = { 0 }; uint8_t q[6][8]; std::memset(q, 0, sizeof(q));
     uint32_t imask = 0;
     uint32_t childBase = (uint32_t) out.nodes.size();
@@ -229,8 +234,8 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
       if (i < 0) continue;
       const BinNode& c = bn[ch[i].bin];
       for (int k = 0; k < 3; k++) {
-        double lo = ((double) c.box.lo[k] - (double) pb.lo[k]) / scale[k];
-        double hi = ((double) c.box.hi[k] - (double) pb.lo[k]) / scale[k];
+        double lo = ((double) c.box.lo[k] - (double) porigin[k]) / scale[k];
+        double hi = ((double) c.box.hi[k] - (double) porigin[k]) / scale[k];
         double ql = std::floor(lo), qh = std::ceil(hi);
         if (lo - ql < 1.0 / 64.0 && ql > 0.0) ql -= 1.0;   // safety quantum when the bound sits on a grid line
         if (qh - hi < 1.0 / 64.0 && qh < 255.0) qh += 1.0;

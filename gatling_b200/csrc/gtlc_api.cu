@@ -272,7 +272,7 @@ bool buildHostGeometry(Scene* s)
     }
   }
   bvh8_build(tris, s->bvh);
-  if (s->bvh.maxDepth > (uint32_t) kStackSize) { setError("BVH8 depth %u exceeds traversal stack %d", s->bvh.maxDepth, kStackSize); return false; }
+  if (s->bvh.maxDepth * 2 > (uint32_t) kStackSize) { setError("BVH8 depth %u needs a traversal stack of %u entries (have %d)", s->bvh.maxDepth, s->bvh.maxDepth * 2, kStackSize); return false; }
   s->bvhValid = true;
   s->lastBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return true;
@@ -386,8 +386,14 @@ TraceParams makeTraceParams(Scene* s)
 
 template <int MODE> void launchTrace(const TraceParams& P, bool count, int blocks)
 {
-  if (count) trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, g.stream>>>(P);
-  else trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+  if (count) { trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // visit counting: variant 0 order = the oracle's walk
+  switch (g.tuning.traceVariant) {
+    case 1: trace_kernel_v1<MODE, 1><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    case 2: trace_kernel_v1<MODE, 2><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    case 3: trace_kernel_v1<MODE, 3><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    case 4: trace_kernel_v1<MODE, 4><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    default: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+  }
 }
 
 // _CalcDirtyFlagsForRenderParams (Gi.cpp:1859-1987), reduced to "does the accumulated image survive?"
@@ -789,6 +795,7 @@ int gtlc_trace_rays(GtlcHandle h, const float* rays, uint32_t count, int32_t any
     memset(&g.stats, 0, offsetof(GtlcStats, msBvhBuild));
     if (anyHit) { g.stats.shadowRays = count; g.stats.msTraceAny = ms; } else { g.stats.closestRays = count; g.stats.msTraceClosest = ms; }
     g.stats.nodeVisits = c.stats[1]; g.stats.triVisits = c.stats[2]; g.stats.kernelLaunches = 1; g.stats.msTotal = ms;
+    g.stats.maxNodeVisitsPerRay = (uint32_t) c.stats[4]; g.stats.nonFiniteRays = c.stats[5];
     return true;
   };
   g.eventsUsed = 0;
@@ -946,6 +953,7 @@ int gtlc_render(const GtlcRenderParams* params)
     }
     g.stats.closestRays = c.stats[0]; g.stats.shadowRays = c.stats[3]; g.stats.nodeVisits = c.stats[1]; g.stats.triVisits = c.stats[2];
     g.stats.kernelLaunches = launches; g.stats.paths = paths;
+    g.stats.maxNodeVisitsPerRay = (uint32_t) c.stats[4]; g.stats.nonFiniteRays = c.stats[5];
     return true;
   };
   if (!body()) return GTLC_ERROR;

@@ -20,7 +20,7 @@
 namespace gtlc {
 
 constexpr int kTraceBlock = 128;         // threads per CTA
-constexpr int kStackSize = 40;           // >= wide-tree depth (checked on the host at build time)
+constexpr int kStackSize = 48;           // >= 2 x wide-tree depth (node groups + postponed triangle groups; checked on the host)
 constexpr int kRefillThreshold = 8;      // idle lanes that trigger a refill
 constexpr float kBoxPad = 1.0000004f;    // Ize 2013 robust slab padding
 
@@ -40,14 +40,22 @@ struct TraceParams {
   float4* __restrict__ radPath;         // (radiance.xyz, rng) of the continuing paths
   float4* __restrict__ radSample;       // (radiance.xyz, -) of finished samples
   // bookkeeping
-  unsigned long long* stats;            // [0] rays traced, [1] node visits, [2] triangle tests
+  unsigned long long* stats;            // [1] node visits, [2] triangle tests, [4] max node visits of one ray, [5] non-finite rays
   uint32_t* visitsPerRay;               // optional 2 x uint32 per ray
 };
 
-GTLC_D float byte_to_float(uint32_t w, uint32_t sel)
+// Quantised byte q (0..255) taken from byte `j` of `w`, as the float 32768 + q: one PRMT builds
+// 0x4700qq00 (exponent 2^15, q in mantissa bits 8..15), no integer->float conversion pipe involved.
+// The bias is folded into the slab origin (o - 32768 s), so a bound costs PRMT + FFMA.
+GTLC_D float biased_byte(uint32_t w, uint32_t sel) { return u2f(__byte_perm(w, 0x47000000u, sel)); }
+
+// A ray with a NaN/Inf origin or direction can never hit a triangle (every comparison of the watertight
+// test fails) but would pass every NaN-dropping slab test and walk the whole tree: answer it as a miss.
+GTLC_D bool ray_is_finite(float4 ro, float4 rd)
 {
-  // 0x4B0000qq = 2^23 + q exactly; one PRMT + one FADD, no integer->float conversion pipe
-  return u2f(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+  const float m = fmaxf(fmaxf(fabsf(ro.x), fabsf(ro.y)), fmaxf(fabsf(ro.z), fmaxf(fmaxf(fabsf(rd.x), fabsf(rd.y)), fabsf(rd.z))));
+  const float sum = ((ro.x + ro.y) + ro.z) + ((rd.x + rd.y) + rd.z);   // NaN propagates through +, fmaxf drops it
+  return (m <= kFloatMax) && (sum == sum);
 }
 
 struct RaySetup {
@@ -62,7 +70,13 @@ struct RaySetup {
 GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
 {
   r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z); r.tmin = ro.w;
-  r.idir = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+  // |d| is clamped to 2^-80 for the slab tests only (Ylitie et al. 2017): with an exactly-zero or denormal
+  // component 1/d = inf turns the quantised slab arithmetic q*s + o into inf - inf = NaN, the NaN-dropping
+  // min/max then never cull along that axis and the ray walks a whole slice of the tree.
+  const float kMinDir = 8.271806125530277e-25f;   // 2^-80
+  r.idir = v3(1.0f / (fabsf(r.d.x) > kMinDir ? r.d.x : copysignf(kMinDir, r.d.x)),
+              1.0f / (fabsf(r.d.y) > kMinDir ? r.d.y : copysignf(kMinDir, r.d.y)),
+              1.0f / (fabsf(r.d.z) > kMinDir ? r.d.z : copysignf(kMinDir, r.d.z)));
   uint32_t oct = (r.d.x < 0.0f ? 1u : 0u) | (r.d.y < 0.0f ? 2u : 0u) | (r.d.z < 0.0f ? 4u : 0u);
   r.octinv = 7u - oct;
   float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
@@ -113,6 +127,7 @@ GTLC_D bool tri_intersect(const RaySetup& r, V3 p0, V3 p1, V3 p2, float& t, floa
 
 // Slab-tests the 8 quantised child boxes of one node; returns the 32-bit hit mask
 // (bits 31..24: internal children in traversal priority order, bits 23..0: triangles).
+// t = (32768 + q) * s + (o - 32768 s) with s = 2^e / d, o = (p - origin) / d; branch-free.
 GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
                              const RaySetup& r, float tbest)
 {
@@ -120,14 +135,20 @@ GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, con
   const float sx = u2f((e & 0xFFu) << 23) * r.idir.x;
   const float sy = u2f(((e >> 8) & 0xFFu) << 23) * r.idir.y;
   const float sz = u2f(((e >> 16) & 0xFFu) << 23) * r.idir.z;
-  const float ox = (u2f(n0.x) - r.o.x) * r.idir.x;
-  const float oy = (u2f(n0.y) - r.o.y) * r.idir.y;
-  const float oz = (u2f(n0.z) - r.o.z) * r.idir.z;
+  const float ox = (u2f(n0.x) - r.o.x) * r.idir.x - 32768.0f * sx;
+  const float oy = (u2f(n0.y) - r.o.y) * r.idir.y - 32768.0f * sy;
+  const float oz = (u2f(n0.z) - r.o.z) * r.idir.z - 32768.0f * sz;
   const bool nx = r.d.x < 0.0f, ny = r.d.y < 0.0f, nz = r.d.z < 0.0f;
+  const uint32_t octinv4 = r.octinv * 0x01010101u;
   uint32_t hitmask = 0;
 #pragma unroll
   for (int half = 0; half < 2; half++) {
     const uint32_t meta4 = half ? n1.w : n1.z;
+    // word-level decode of the 4 meta bytes (Ylitie et al. 2017, listing 2)
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;          // bit 4 set iff low5 >= 24
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;                     // 0xFF in every internal-child byte
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
     const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
     const uint32_t nearx = nx ? qhix : qlox, farx = nx ? qlox : qhix;
@@ -135,22 +156,18 @@ GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, con
     const uint32_t nearz = nz ? qhiz : qloz, farz = nz ? qloz : qhiz;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const uint32_t sel = 0x7650u | (uint32_t) j;
-      const float tnx = fmaf(byte_to_float(nearx, sel), sx, ox);
-      const float tny = fmaf(byte_to_float(neary, sel), sy, oy);
-      const float tnz = fmaf(byte_to_float(nearz, sel), sz, oz);
-      const float tfx = fmaf(byte_to_float(farx, sel), sx, ox);
-      const float tfy = fmaf(byte_to_float(fary, sel), sy, oy);
-      const float tfz = fmaf(byte_to_float(farz, sel), sz, oz);
+      const uint32_t sel = 0x7604u | ((uint32_t) j << 4);
+      const float tnx = fmaf(biased_byte(nearx, sel), sx, ox);
+      const float tny = fmaf(biased_byte(neary, sel), sy, oy);
+      const float tnz = fmaf(biased_byte(nearz, sel), sz, oz);
+      const float tfx = fmaf(biased_byte(farx, sel), sx, ox);
+      const float tfy = fmaf(biased_byte(fary, sel), sy, oy);
+      const float tfz = fmaf(biased_byte(farz, sel), sz, oz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest)) * kBoxPad;
-      const uint32_t m = (meta4 >> (8 * j)) & 0xFFu;
-      if (tn <= tf && m != 0u) {
-        const uint32_t bits = m >> 5;
-        const uint32_t lo5 = m & 31u;
-        const uint32_t idx = (lo5 >= 24u) ? (24u + ((lo5 & 7u) ^ r.octinv)) : lo5;
-        hitmask |= bits << idx;
-      }
+      const uint32_t bits = (child_bits4 >> (8 * j)) & 0xFFu;
+      const uint32_t idx = (bit_index4 >> (8 * j)) & 0xFFu;
+      hitmask |= (tn <= tf) ? (bits << idx) : 0u;
     }
   }
   return hitmask;
@@ -193,6 +210,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(TraceParams P)
             bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
             sp = 0; cNodes = 0; cTris = 0;
             active = tmax > r.tmin;   // empty interval (e.g. disabled shadow ray): immediate miss
+            if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
             G = make_uint2(0u, 0x80000000u);
             if (!active) {
               if (MODE == TRACE_CLOSEST || MODE == TRACE_ANY) { P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu; }
@@ -266,10 +284,137 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(TraceParams P)
           if (COUNT) {
             atomicAdd(&P.stats[1], (unsigned long long) cNodes);
             atomicAdd(&P.stats[2], (unsigned long long) cTris);
+            atomicMax(&P.stats[4], (unsigned long long) cNodes);
             if (P.visitsPerRay) { P.visitsPerRay[2 * (size_t) rayIdx] = cNodes; P.visitsPerRay[2 * (size_t) rayIdx + 1] = cTris; }
           }
           active = false;
         }
+      }
+      const unsigned idle = __ballot_sync(FULL, !active);
+      if (idle == FULL) break;
+      if (!exhausted && __popc(idle) >= kRefillThreshold) break;
+    }
+  }
+}
+
+// ---- variant 1: triangle postponing (Ylitie et al. 2017, section 4.3) -----------------------------
+// Same traversal, but a lane's triangle group is only tested when at least kTriEighths/8 of the
+// warp's active lanes have triangles pending; otherwise the group is pushed on the lane's stack and
+// the lane goes on with node work, so node steps and triangle tests each run with better SIMD
+// utilisation.  Results are identical to variant 0 (closest hit is order independent); the
+// node/triangle visit COUNTS are not (culling happens later), which is why the roofline's algorithmic
+// bytes are counted with variant 0 (= the oracle's walk) and variant 1 is only timed.
+template <int MODE, int kTriEighths>
+__global__ void __launch_bounds__(kTraceBlock) trace_kernel_v1(TraceParams P)
+{
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = *P.numRays;
+
+  uint2 stack[kStackSize];
+  int sp = 0;
+  bool active = false;
+  bool exhausted = false;
+  uint32_t rayIdx = 0;
+  RaySetup r;
+  float bt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t bprim = 0xFFFFFFFFu, binst = 0xFFFFFFFFu;
+  float tmax = 0.0f;
+  uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
+
+  while (true) {
+    if (!exhausted) {
+      const unsigned need = __ballot_sync(FULL, !active);
+      if (need) {
+        const int leader = __ffs(need) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t) __popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active) {
+          rayIdx = base + (uint32_t) __popc(need & ((1u << lane) - 1u));
+          if (rayIdx < n) {
+            const float4 ro = __ldg(&P.rayO[rayIdx]);
+            const float4 rd = __ldg(&P.rayD[rayIdx]);
+            ray_setup(r, ro, rd);
+            tmax = rd.w;
+            bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
+            sp = 0;
+            active = tmax > r.tmin;
+            if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
+            G = make_uint2(0u, 0x80000000u); T = make_uint2(0u, 0u);
+            if (!active && MODE != TRACE_SHADOW) { P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu; }
+          }
+        }
+        if (base + (uint32_t) __popc(need) >= n) exhausted = true;
+      }
+    }
+    if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
+
+    while (true) {
+      bool done = false;
+      // ---- A: node step / pop (only lanes without pending triangles) ----
+      if (active && T.y == 0u) {
+        if (G.y & 0xFF000000u) {
+          const uint32_t hits_imask = G.y;
+          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
+          G.y &= ~(1u << bit);
+          if (G.y & 0xFF000000u) stack[sp++] = G;
+          const uint32_t slot = (bit - 24u) ^ r.octinv;
+          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
+          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
+          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
+          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+          T = make_uint2(n1.y, hm & 0x00FFFFFFu);
+        } else if (sp > 0) {
+          const uint2 e = stack[--sp];
+          if (e.y & 0xFF000000u) G = e; else T = e;
+        } else {
+          done = true;
+        }
+      }
+      // ---- B: triangle phase, entered only when enough lanes have triangles ----
+      const unsigned actMask = __ballot_sync(FULL, active && !done);
+      unsigned triMask = __ballot_sync(FULL, active && !done && T.y != 0u);
+      const int thr = max(1, (__popc(actMask) * kTriEighths) >> 3);
+      while (__popc(triMask) >= thr) {
+        if (active && !done && T.y != 0u) {
+          const uint32_t j = (uint32_t) __ffs(T.y) - 1u;
+          T.y &= T.y - 1u;
+          const float4* tp = P.tris + (size_t) (T.x + j) * 3;
+          const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+          float t, u, v;
+          if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+            if (t > r.tmin && t < tmax) {
+              const uint32_t prim = f2u(a.w), inst = f2u(b.w);
+              if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; }
+              else {
+                const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
+                if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
+              }
+            }
+          }
+        }
+        triMask = __ballot_sync(FULL, active && !done && T.y != 0u);
+        if (!triMask) break;
+      }
+      // postpone what is left
+      if (active && !done && T.y != 0u) { stack[sp++] = T; T.y = 0u; }
+      if (done) {
+        const bool hit = bprim != 0xFFFFFFFFu;
+        if (MODE == TRACE_SHADOW) {
+          if (!hit) {
+            const float4 c = __ldg(&P.shContrib[rayIdx]);
+            const uint32_t target = f2u(c.w);
+            float4* dst = (target & 0x80000000u) ? (P.radSample + (target & 0x7FFFFFFFu)) : (P.radPath + target);
+            float4 cur = *dst;
+            cur.x += c.x; cur.y += c.y; cur.z += c.z;
+            *dst = cur;
+          }
+        } else {
+          P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
+          if (P.hitInst) P.hitInst[rayIdx] = binst;
+        }
+        active = false;
       }
       const unsigned idle = __ballot_sync(FULL, !active);
       if (idle == FULL) break;

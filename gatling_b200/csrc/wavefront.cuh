@@ -81,7 +81,7 @@ struct Counters {          // device-resident
   uint32_t numPaths[2];    // path-queue lengths (double buffered)
   uint32_t numShadow;
   uint32_t workCounter;
-  unsigned long long stats[4];  // [0] closest rays, [1] node visits, [2] tri tests, [3] shadow rays
+  unsigned long long stats[6];  // [0] closest rays, [1] node visits, [2] tri tests, [3] shadow rays, [4] max node visits of one ray, [5] non-finite rays
 };
 
 // ---- rp_main.rgen:118-130 ---------------------------------------------------------------------

@@ -306,7 +306,8 @@ typedef struct GtlcStats {
   uint32_t bvhNodeCount;
   uint32_t bvhTriCount;
   uint32_t bvhMaxDepth;
-  uint32_t reserved;
+  uint32_t maxNodeVisitsPerRay; /* valid iff countVisits */
+  uint64_t nonFiniteRays;       /* rays with a NaN/Inf origin or direction (answered as misses without traversal) */
 } GtlcStats;
 GTLC_API void gtlc_get_stats(GtlcStats* stats);
 

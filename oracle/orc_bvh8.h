@@ -20,17 +20,18 @@ static inline uint32_t bvh8_node_hitmask(const uint8_t* nd, V3 o, V3 d, V3 idir,
   const float sx = uintBitsToFloat((e & 0xFFu) << 23) * idir.x;
   const float sy = uintBitsToFloat(((e >> 8) & 0xFFu) << 23) * idir.y;
   const float sz = uintBitsToFloat(((e >> 16) & 0xFFu) << 23) * idir.z;
-  const float ox = (ldf(nd + 0) - o.x) * idir.x;
-  const float oy = (ldf(nd + 4) - o.y) * idir.y;
-  const float oz = (ldf(nd + 8) - o.z) * idir.z;
+  // slab origin with the kernel's 2^15 byte bias folded in: t = (32768 + q) * s + (o - 32768 s)
+  const float ox = (ldf(nd + 0) - o.x) * idir.x - 32768.0f * sx;
+  const float oy = (ldf(nd + 4) - o.y) * idir.y - 32768.0f * sy;
+  const float oz = (ldf(nd + 8) - o.z) * idir.z - 32768.0f * sz;
   const uint8_t* meta = nd + 24;
   const uint8_t* qlox = nd + 32; const uint8_t* qloy = nd + 40; const uint8_t* qloz = nd + 48;
   const uint8_t* qhix = nd + 56; const uint8_t* qhiy = nd + 64; const uint8_t* qhiz = nd + 72;
   uint32_t hitmask = 0;
   for (int i = 0; i < 8; i++) {
-    const float nx = (float) (d.x < 0.0f ? qhix[i] : qlox[i]), fx = (float) (d.x < 0.0f ? qlox[i] : qhix[i]);
-    const float ny = (float) (d.y < 0.0f ? qhiy[i] : qloy[i]), fy = (float) (d.y < 0.0f ? qloy[i] : qhiy[i]);
-    const float nz = (float) (d.z < 0.0f ? qhiz[i] : qloz[i]), fz = (float) (d.z < 0.0f ? qloz[i] : qhiz[i]);
+    const float nx = 32768.0f + (float) (d.x < 0.0f ? qhix[i] : qlox[i]), fx = 32768.0f + (float) (d.x < 0.0f ? qlox[i] : qhix[i]);
+    const float ny = 32768.0f + (float) (d.y < 0.0f ? qhiy[i] : qloy[i]), fy = 32768.0f + (float) (d.y < 0.0f ? qloy[i] : qhiy[i]);
+    const float nz = 32768.0f + (float) (d.z < 0.0f ? qhiz[i] : qloz[i]), fz = 32768.0f + (float) (d.z < 0.0f ? qloz[i] : qhiz[i]);
     const float tnx = fmaf(nx, sx, ox), tny = fmaf(ny, sy, oy), tnz = fmaf(nz, sz, oz);
     const float tfx = fmaf(fx, sx, ox), tfy = fmaf(fy, sy, oy), tfz = fmaf(fz, sz, oz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
@@ -51,8 +52,15 @@ static inline void bvh8_trace_one(const uint8_t* nodes, const float* tris, V3 o,
   best.t = -1.0f; best.u = best.v = 0.0f; best.prim = best.inst = 0xFFFFFFFFu;
   nNodes = nTris = 0;
   if (!(tmax > tmin)) return;
+  {  // the kernel answers non-finite rays as misses without traversal (they cannot hit a triangle)
+    const float c[6] = { o.x, o.y, o.z, d.x, d.y, d.z };
+    for (int k = 0; k < 6; k++) if (!(fabsf(c[k]) <= FLOAT_MAX)) return;
+  }
   RayPre rp = ray_precompute(d);
-  V3 idir = v3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  const float kMinDir = 8.271806125530277e-25f;   // 2^-80, slab tests only (mirrors the kernel)
+  V3 idir = v3(1.0f / (fabsf(d.x) > kMinDir ? d.x : copysignf(kMinDir, d.x)),
+               1.0f / (fabsf(d.y) > kMinDir ? d.y : copysignf(kMinDir, d.y)),
+               1.0f / (fabsf(d.z) > kMinDir ? d.z : copysignf(kMinDir, d.z)));
   const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
   const uint32_t octinv = 7u - oct;
   float bt = tmax;

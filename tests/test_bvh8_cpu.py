@@ -1,0 +1,77 @@
+"""CPU: the product's host-built BVH8 (through the C-ABI, no GPU needed) walked by the oracle's
+restatement of the traversal gives bit-identical closest hits to the oracle's own binary BVH."""
+import numpy as np
+import pytest
+
+from gatling_b200 import gi, scenes
+from oracle import orc
+from helpers import random_rays
+
+
+def _check(desc, rays):
+    b = gi.BuiltScene(desc)
+    try:
+        nodes, tris = gi.get_bvh(b.scene)
+        assert len(nodes) % 80 == 0 and len(tris) % 12 == 0
+        assert len(tris) // 12 == desc.triangle_count
+        o = orc.OracleScene(desc)
+        ref = o.trace(rays)
+        walk, visits = orc.bvh8_trace(nodes, tris, rays)
+        for k in ("prim", "inst", "t", "u", "v"):
+            assert np.array_equal(ref[k], walk[k]), k
+        a_ref = o.trace(rays, any_hit=True)
+        a_walk, _ = orc.bvh8_trace(nodes, tris, rays, any_hit=True)
+        assert np.array_equal(a_ref["t"] >= 0, a_walk["t"] >= 0)
+        return nodes, tris, visits
+    finally:
+        b.close()
+
+
+def test_cornell_bvh8():
+    d = scenes.cornell(32, 32, spp=1)
+    cam = orc.camera_rays(d, 0); cam[:, 3] = 0; cam[:, 7] = 3e38
+    nodes, tris, visits = _check(d, np.concatenate([cam, random_rays(5000, 1)]))
+    assert len(tris) // 12 == 46
+
+
+def test_random_triangles_bvh8():
+    d = scenes.random_triangles(30000, 32, 32, spp=1)
+    nodes, tris, visits = _check(d, np.concatenate([random_rays(20000, 2), random_rays(5000, 4, tmax=0.1)]))
+    assert visits[:, 0].mean() > 5       # the walk really descends
+    # every triangle is referenced exactly once
+    prim = tris.reshape(-1, 12)[:, 3].view(np.uint32)
+    assert np.array_equal(np.sort(prim), np.arange(30000, dtype=np.uint32))
+
+
+def test_instanced_and_transformed_meshes():
+    d = scenes.cornell(16, 16, spp=1)
+    box = d.meshes[6]
+    xf = np.eye(4, dtype=np.float32)
+    inst = []
+    for k in range(5):
+        m = xf.copy(); m[3, :3] = (0.3 * k - 0.6, -0.5, 0.1 * k)
+        inst.append(m)
+    box.instance_transforms = np.stack(inst)
+    _check(d, random_rays(20000, 9))
+
+
+def test_degenerate_inputs():
+    d = scenes.random_triangles(64, 8, 8, spp=1)
+    m = d.meshes[0]
+    v = m.vertices.copy()
+    v["pos"][0:3] = v["pos"][0]          # zero-area triangle
+    v["pos"][3:6] = [[0, 0, 0], [1, 1, 1], [2, 2, 2]]   # collinear
+    v["pos"][6:12] = v["pos"][12:18]     # duplicated (coincident) triangles -> tie break on primitive id
+    m.vertices = v
+    _check(d, random_rays(20000, 13))
+    # a scene without geometry
+    e = scenes.cornell(8, 8, spp=1)
+    e.meshes = []
+    b = gi.BuiltScene(e)
+    try:
+        nodes, tris = gi.get_bvh(b.scene)
+        assert len(nodes) == 80 and len(tris) == 0
+        h, _ = orc.bvh8_trace(nodes, tris, random_rays(100, 1))
+        assert np.all(h["t"] == -1)
+    finally:
+        b.close()

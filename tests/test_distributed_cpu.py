@@ -1,0 +1,49 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of the benchmark -- tile sharding ("tile % world == rank"),
+zero-filled foreign pixels and ONE sum-reduce of the HDR accumulator to rank 0 -- exercised
+with the CPU oracle as the renderer (the CUDA renderer is covered by test_shard_sum_equals_full on the GPU)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gatling_b200 import scenes
+from oracle import orc
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = scenes.cornell(48, 32, spp=2, max_bounces=3)
+    part, _, rays = orc.OracleScene(d).render(shard=(rank, world, 8))
+    t = torch.from_numpy(part.copy())
+    dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+    counts = torch.tensor([float(rays[0] + rays[1])], dtype=torch.float64)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        np.save(out_path, t.numpy())
+        np.save(out_path + ".rays.npy", counts.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_tile_shard_and_reduce(tmp_path):
+    out = str(tmp_path / "reduced.npy")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    d = scenes.cornell(48, 32, spp=2, max_bounces=3)
+    full, _, rays = orc.OracleScene(d).render()
+    got = np.load(out)
+    assert np.array_equal(got, full)                      # disjoint tiles: x + 0 is exact
+    assert int(np.load(out + ".rays.npy")[0]) == rays[0] + rays[1]

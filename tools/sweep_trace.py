@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""GPU tuning sweep: traversal kernel variants / knobs on config C2 at reduced spp.  Prints one line per
+setting; all settings must produce the bit-identical image."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gatling_b200 import gi, scenes  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--tris", type=int, default=1_000_000)
+ap.add_argument("--spp", type=int, default=16)
+ap.add_argument("--variants", default="0,1,2,3,4")
+ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+
+assert gi.giInitialize(0) == gi.GiStatus.Ok, gi.giLastError()
+d = scenes.random_triangles(a.tris, 1920, 1080, a.spp, 8)
+b = gi.BuiltScene(d)
+ref = None
+gi.set_tuning(countVisits=1)
+b.render()
+s = gi.get_stats()
+print("counting pass: rays %d  nodes/ray %.2f  tris/ray %.2f  max nodes of one ray %d  non-finite rays %d"
+      % (s["closestRays"], s["nodeVisits"] / s["closestRays"], s["triVisits"] / s["closestRays"], s["maxNodeVisitsPerRay"], s["nonFiniteRays"]), flush=True)
+gi.set_tuning(countVisits=0)
+for v in [int(x) for x in a.variants.split(",")]:
+    gi.set_tuning(traceVariant=v, skipReadback=0)
+    best = None
+    for _ in range(a.reps):
+        gi.set_shard(b.scene, 0, 1, 64)
+        img = b.render().copy()
+        s = gi.get_stats()
+        if best is None or s["msTotal"] < best["msTotal"]:
+            best = s
+    if ref is None:
+        ref = img
+    same = bool(np.array_equal(ref, img))
+    rays = best["closestRays"] + best["shadowRays"]
+    print("variant %d: %.1f Mray/s total  trace %.2f ms  shade %.2f ms  total %.2f ms  identical=%s depth=%d"
+          % (v, rays / best["msTotal"] / 1e3, best["msTraceClosest"], best["msShade"], best["msTotal"], same, best["bvhMaxDepth"]), flush=True)
+b.close()
+gi.giTerminate()
