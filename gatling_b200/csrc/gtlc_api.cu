@@ -381,6 +381,7 @@ TraceParams makeTraceParams(Scene* s)
   TraceParams P; memset(&P, 0, sizeof(P));
   P.nodes = s->dNodes.ptr; P.tris = s->dTris.ptr;
   P.stats = g.counters->stats;
+  P.refillThreshold = g.tuning.reserved[0] > 0 ? g.tuning.reserved[0] : kRefillThreshold;
   return P;
 }
 
@@ -901,7 +902,7 @@ int gtlc_render(const GtlcRenderParams* params)
     }
 
     const int gridElem = g.smCount * 8;
-    const int traceBlocks = g.smCount * 8;
+    const int traceBlocks = g.smCount * (g.tuning.reserved[1] > 0 ? g.tuning.reserved[1] : 8);
     const bool countVisits = g.tuning.countVisits != 0;
     uint64_t paths = 0;
     for (uint32_t pixBase = 0; pixBase < localPixels; pixBase += pixelsPerWave) {

@@ -42,6 +42,7 @@ struct TraceParams {
   // bookkeeping
   unsigned long long* stats;            // [1] node visits, [2] triangle tests, [4] max node visits of one ray, [5] non-finite rays
   uint32_t* visitsPerRay;               // optional 2 x uint32 per ray
+  int refillThreshold;                  // idle lanes that trigger a refill (kRefillThreshold by default)
 };
 
 // Quantised byte q (0..255) taken from byte `j` of `w`, as the float 32768 + q: one PRMT builds
@@ -63,8 +64,11 @@ struct RaySetup {
   float tmin;
   V3 idir;
   uint32_t octinv;
-  int kx, ky, kz;
-  float Sx, Sy, Sz;
+  // Woop shear as three sparse basis vectors: mx = e_kx - Sx e_kz, my = e_ky - Sy e_kz, mz = Sz e_kz.
+  // dot(A, mx) evaluates to exactly fl(A[kx] - fl(Sx * A[kz])) -- the products with 1 and 0 are exact and
+  // adding the zero term is exact -- i.e. bit-identical to the indexed form of the paper (and of the CPU
+  // oracle) without any data-dependent component selection in the per-triangle code.
+  V3 mx, my, mz;
 };
 
 GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
@@ -80,45 +84,47 @@ GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
   uint32_t oct = (r.d.x < 0.0f ? 1u : 0u) | (r.d.y < 0.0f ? 2u : 0u) | (r.d.z < 0.0f ? 4u : 0u);
   r.octinv = 7u - oct;
   float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
-  r.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
-  r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
-  r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
-  if (comp(r.d, r.kz) < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
-  float dz = comp(r.d, r.kz);
-  r.Sx = comp(r.d, r.kx) / dz;
-  r.Sy = comp(r.d, r.ky) / dz;
-  r.Sz = 1.0f / dz;
+  int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  if (comp(r.d, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
+  const float dz = comp(r.d, kz);
+  const float Sx = comp(r.d, kx) / dz;
+  const float Sy = comp(r.d, ky) / dz;
+  const float Sz = 1.0f / dz;
+  r.mx = v3(kx == 0 ? 1.0f : (kz == 0 ? -Sx : 0.0f), kx == 1 ? 1.0f : (kz == 1 ? -Sx : 0.0f), kx == 2 ? 1.0f : (kz == 2 ? -Sx : 0.0f));
+  r.my = v3(ky == 0 ? 1.0f : (kz == 0 ? -Sy : 0.0f), ky == 1 ? 1.0f : (kz == 1 ? -Sy : 0.0f), ky == 2 ? 1.0f : (kz == 2 ? -Sy : 0.0f));
+  r.mz = v3(kz == 0 ? Sz : 0.0f, kz == 1 ? Sz : 0.0f, kz == 2 ? Sz : 0.0f);
+}
+
+// Rare path of the watertight test: an edge function is exactly zero -> recompute all three in double.
+__device__ __noinline__ void tri_edges_double(float Ax, float Ay, float Bx, float By, float Cx, float Cy, float& U, float& V, float& W)
+{
+  double CxBy = (double) Cx * (double) By, CyBx = (double) Cy * (double) Bx;
+  U = (float) (CxBy - CyBx);
+  double AxCy = (double) Ax * (double) Cy, AyCx = (double) Ay * (double) Cx;
+  V = (float) (AxCy - AyCx);
+  double BxAy = (double) Bx * (double) Ay, ByAx = (double) By * (double) Ax;
+  W = (float) (BxAy - ByAx);
 }
 
 // Woop, Benthin, Wald 2013.  Returns true with (t, u, v) when the ray line pierces the triangle.
 GTLC_D bool tri_intersect(const RaySetup& r, V3 p0, V3 p1, V3 p2, float& t, float& u, float& v)
 {
-  V3 A = p0 - r.o, B = p1 - r.o, C = p2 - r.o;
-  float Ax = comp(A, r.kx) - r.Sx * comp(A, r.kz);
-  float Ay = comp(A, r.ky) - r.Sy * comp(A, r.kz);
-  float Bx = comp(B, r.kx) - r.Sx * comp(B, r.kz);
-  float By = comp(B, r.ky) - r.Sy * comp(B, r.kz);
-  float Cx = comp(C, r.kx) - r.Sx * comp(C, r.kz);
-  float Cy = comp(C, r.ky) - r.Sy * comp(C, r.kz);
+  const V3 A = p0 - r.o, B = p1 - r.o, C = p2 - r.o;
+  const float Ax = dot(A, r.mx), Ay = dot(A, r.my);
+  const float Bx = dot(B, r.mx), By = dot(B, r.my);
+  const float Cx = dot(C, r.mx), Cy = dot(C, r.my);
   float U = Cx * By - Cy * Bx;
   float V = Ax * Cy - Ay * Cx;
   float W = Bx * Ay - By * Ax;
-  if (U == 0.0f || V == 0.0f || W == 0.0f) {
-    double CxBy = (double) Cx * (double) By, CyBx = (double) Cy * (double) Bx;
-    U = (float) (CxBy - CyBx);
-    double AxCy = (double) Ax * (double) Cy, AyCx = (double) Ay * (double) Cx;
-    V = (float) (AxCy - AyCx);
-    double BxAy = (double) Bx * (double) Ay, ByAx = (double) By * (double) Ax;
-    W = (float) (BxAy - ByAx);
-  }
+  if (U == 0.0f || V == 0.0f || W == 0.0f) tri_edges_double(Ax, Ay, Bx, By, Cx, Cy, U, V, W);
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-  float det = (U + V) + W;
+  const float det = (U + V) + W;
   if (det == 0.0f) return false;
-  float Az = r.Sz * comp(A, r.kz);
-  float Bz = r.Sz * comp(B, r.kz);
-  float Cz = r.Sz * comp(C, r.kz);
-  float T = (U * Az + V * Bz) + W * Cz;
-  float rcp = 1.0f / det;
+  const float Az = dot(A, r.mz), Bz = dot(B, r.mz), Cz = dot(C, r.mz);
+  const float T = (U * Az + V * Bz) + W * Cz;
+  const float rcp = 1.0f / det;
   t = T * rcp;
   u = V * rcp;
   v = W * rcp;
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(TraceParams P)
       }
       const unsigned idle = __ballot_sync(FULL, !active);
       if (idle == FULL) break;
-      if (!exhausted && __popc(idle) >= kRefillThreshold) break;
+      if (!exhausted && __popc(idle) >= P.refillThreshold) break;
     }
   }
 }
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v1(TraceParams P)
       }
       const unsigned idle = __ballot_sync(FULL, !active);
       if (idle == FULL) break;
-      if (!exhausted && __popc(idle) >= kRefillThreshold) break;
+      if (!exhausted && __popc(idle) >= P.refillThreshold) break;
     }
   }
 }
