@@ -134,13 +134,15 @@ def cpu_baseline_sample(a, desc, target_seconds):
     o = orc.OracleScene(desc)
     H = desc.height
     mid = H // 2
-    # calibration: 2 rows, 1 spp
-    _, secs, rays = o.render(rows=(mid, mid + 2), spp=1)
+    # calibration: a band of rows at 1 spp (long enough to amortise the OpenMP start-up), then the real sample
+    cal_rows = min(H, 32)
+    o.render(rows=(mid, mid + 2), spp=1)
+    _, secs, rays = o.render(rows=(mid - cal_rows // 2, mid - cal_rows // 2 + cal_rows), spp=1)
     rate = (rays[0] + rays[1]) / max(secs, 1e-6)
-    rays_per_row_spp = (rays[0] + rays[1]) / 2.0
-    budget_rays = rate * target_seconds
-    rows = int(min(H, max(2, budget_rays / max(rays_per_row_spp * 4, 1))))
+    rays_per_row_spp = (rays[0] + rays[1]) / float(cal_rows)
     spp = 4
+    budget_rays = rate * target_seconds
+    rows = int(min(H, max(2, budget_rays / max(rays_per_row_spp * spp, 1))))
     r0 = max(0, mid - rows // 2)
     _, secs, rays = o.render(rows=(r0, r0 + rows), spp=spp)
     total = rays[0] + rays[1]

@@ -59,6 +59,26 @@ def build(force=False, verbose=False):
     return LIB
 
 
+FACADE_LIB = os.path.join(HERE, "libgi.so")
+FACADE_TEST = os.path.join(HERE, "..", "tests", "cpp", "gi_facade_main")
+
+
+def build_facade(force=False):
+    """C++ facade (gtl::gi* over the C-ABI) as libgi.so + the C++ test driver.  Plain g++: no CUDA in here."""
+    inc = os.path.join(HERE, "..", "include")
+    src = os.path.join(HERE, "gi_cpp", "Gi.cpp")
+    main = os.path.join(HERE, "..", "tests", "cpp", "gi_facade_main.cpp")
+    newest = max(os.path.getmtime(x) for x in (src, main, os.path.join(inc, "gtl", "gi", "Gi.h"), os.path.join(inc, "gtlc.h"), LIB))
+    if force or not os.path.exists(FACADE_LIB) or os.path.getmtime(FACADE_LIB) < newest:
+        subprocess.check_call([_host_cxx(), "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + inc, src, "-o", FACADE_LIB,
+                               "-L" + HERE, "-lgtlc", "-Wl,-rpath,$ORIGIN"])
+    if force or not os.path.exists(FACADE_TEST) or os.path.getmtime(FACADE_TEST) < max(newest, os.path.getmtime(FACADE_LIB)):
+        subprocess.check_call([_host_cxx(), "-std=c++17", "-O2", "-I" + inc, main, "-o", FACADE_TEST,
+                               "-L" + HERE, "-lgi", "-lgtlc", "-Wl,-rpath," + HERE])
+    return FACADE_LIB
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print("built", LIB)
+    print("built", build_facade(force="--force" in sys.argv))

@@ -1,0 +1,297 @@
+// C++ facade: the reference's gi* API (include/gtl/gi/Gi.h == src/gi/gtl/gi/Gi.h:199-261) implemented
+// as a thin adapter over the C-ABI (include/gtlc.h).  This file plus libgtlc.so is what replaces
+// src/gi/impl/Gi.cpp in a gatling build; it contains no rendering code.
+//
+// Material lowering: the reference hands a MaterialX document to `mc`, which patches it, generates MDL
+// and compiles that with the MDL SDK into per-material GLSL (src/mc, out of scope -- closed SDK).
+// Here MaterialX XML is lowered directly to a closure id + parameter block for the two surface shaders
+// the configs name (UsdPreviewSurface, open_pbr_surface); only constant inputs are honoured, connected
+// inputs (textures, primvar readers) fall back to the node's default with a warning.
+#include <gtl/gi/Gi.h>
+
+#include "../../include/gtlc.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <string>
+
+namespace gtl
+{
+  // Opaque reference types wrap a C-ABI handle.
+  struct GiScene { GtlcHandle h; };
+  struct GiMaterial { GtlcHandle h; };
+  struct GiMesh { GtlcHandle h; };
+  struct GiSphereLight { GtlcHandle h; };
+  struct GiDistantLight { GtlcHandle h; };
+  struct GiRectLight { GtlcHandle h; };
+  struct GiDiskLight { GtlcHandle h; };
+  struct GiDomeLight { GtlcHandle h; };
+  struct GiRenderBuffer { GtlcHandle h; };
+
+  namespace
+  {
+    GiMtlxDocToXmlFn s_docSerializer = nullptr;
+    GiAssetReader* s_assetReader = nullptr;
+    std::string s_lastError;
+    std::mutex s_errMutex;
+
+    void logError(const std::string& msg)
+    {
+      std::lock_guard<std::mutex> g(s_errMutex);
+      s_lastError = msg;
+      fprintf(stderr, "[gi] error: %s\n", msg.c_str());
+    }
+
+    template <typename T> T* wrap(GtlcHandle h) { if (!h) { logError(gtlc_last_error()); return nullptr; } T* o = new T; o->h = h; return o; }
+
+    // ---- minimal MaterialX XML scanning -------------------------------------------------------
+    struct XmlInput { std::string name, value; bool connected; };
+
+    bool attr(const std::string& tag, const char* key, std::string& out)
+    {
+      std::string k = std::string(key) + "=\"";
+      size_t p = tag.find(" " + k);
+      if (p == std::string::npos) return false;
+      p += k.size() + 1;
+      size_t e = tag.find('"', p);
+      if (e == std::string::npos) return false;
+      out = tag.substr(p, e - p);
+      return true;
+    }
+
+    // Finds the first <nodeName ...> element (surface shader instance, not the nodedef) and collects its <input> children.
+    bool findShaderNode(const std::string& xml, const char* nodeName, std::vector<XmlInput>& inputs)
+    {
+      std::string open = std::string("<") + nodeName;
+      size_t p = 0;
+      while ((p = xml.find(open, p)) != std::string::npos) {
+        char c = xml[p + open.size()];
+        if (c != ' ' && c != '\t' && c != '\n' && c != '\r' && c != '>') { p += open.size(); continue; }
+        size_t tagEnd = xml.find('>', p);
+        if (tagEnd == std::string::npos) return false;
+        bool selfClosing = xml[tagEnd - 1] == '/';
+        inputs.clear();
+        if (selfClosing) return true;
+        std::string close = std::string("</") + nodeName + ">";
+        size_t end = xml.find(close, tagEnd);
+        if (end == std::string::npos) return false;
+        size_t q = tagEnd;
+        while ((q = xml.find("<input", q)) != std::string::npos && q < end) {
+          size_t e = xml.find('>', q);
+          std::string tag = xml.substr(q, e - q);
+          XmlInput in; in.connected = false;
+          std::string dummy;
+          if (attr(tag, "name", in.name)) {
+            if (!attr(tag, "value", in.value)) in.connected = attr(tag, "nodename", dummy) || attr(tag, "nodegraph", dummy) || attr(tag, "output", dummy) || attr(tag, "interfacename", dummy);
+            inputs.push_back(in);
+          }
+          q = e;
+        }
+        return true;
+      }
+      return false;
+    }
+
+    int parseFloats(const std::string& v, float* out, int maxCount)
+    {
+      int n = 0; const char* s = v.c_str();
+      while (*s && n < maxCount) {
+        char* end = nullptr;
+        float f = strtof(s, &end);
+        if (end == s) { if (!strncmp(s, "true", 4)) { f = 1.0f; end = (char*) s + 4; } else if (!strncmp(s, "false", 5)) { f = 0.0f; end = (char*) s + 5; } else { s++; continue; } }
+        out[n++] = f; s = end;
+      }
+      return n;
+    }
+
+    struct Slot { const char* name; int index; int count; };
+    const Slot kUpsSlots[] = {
+      { "diffuseColor", GTLC_UPS_DIFFUSE_R, 3 }, { "emissiveColor", GTLC_UPS_EMISSIVE_R, 3 }, { "useSpecularWorkflow", GTLC_UPS_USE_SPECULAR_WORKFLOW, 1 },
+      { "specularColor", GTLC_UPS_SPECULAR_R, 3 }, { "metallic", GTLC_UPS_METALLIC, 1 }, { "roughness", GTLC_UPS_ROUGHNESS, 1 },
+      { "clearcoat", GTLC_UPS_CLEARCOAT, 1 }, { "clearcoatRoughness", GTLC_UPS_CLEARCOAT_ROUGHNESS, 1 }, { "opacity", GTLC_UPS_OPACITY, 1 }, { "ior", GTLC_UPS_IOR, 1 } };
+    const Slot kOpbrSlots[] = {
+      { "base_weight", GTLC_OPBR_BASE_WEIGHT, 1 }, { "base_color", GTLC_OPBR_BASE_COLOR_R, 3 }, { "base_diffuse_roughness", GTLC_OPBR_BASE_DIFFUSE_ROUGHNESS, 1 },
+      { "base_metalness", GTLC_OPBR_BASE_METALNESS, 1 }, { "specular_weight", GTLC_OPBR_SPECULAR_WEIGHT, 1 }, { "specular_color", GTLC_OPBR_SPECULAR_COLOR_R, 3 },
+      { "specular_roughness", GTLC_OPBR_SPECULAR_ROUGHNESS, 1 }, { "specular_ior", GTLC_OPBR_SPECULAR_IOR, 1 },
+      { "specular_roughness_anisotropy", GTLC_OPBR_SPECULAR_ROUGHNESS_ANISOTROPY, 1 }, { "transmission_weight", GTLC_OPBR_TRANSMISSION_WEIGHT, 1 },
+      { "transmission_color", GTLC_OPBR_TRANSMISSION_COLOR_R, 3 }, { "transmission_depth", GTLC_OPBR_TRANSMISSION_DEPTH, 1 },
+      { "coat_weight", GTLC_OPBR_COAT_WEIGHT, 1 }, { "coat_color", GTLC_OPBR_COAT_COLOR_R, 3 }, { "coat_roughness", GTLC_OPBR_COAT_ROUGHNESS, 1 },
+      { "coat_ior", GTLC_OPBR_COAT_IOR, 1 }, { "coat_darkening", GTLC_OPBR_COAT_DARKENING, 1 }, { "fuzz_weight", GTLC_OPBR_FUZZ_WEIGHT, 1 },
+      { "fuzz_color", GTLC_OPBR_FUZZ_COLOR_R, 3 }, { "fuzz_roughness", GTLC_OPBR_FUZZ_ROUGHNESS, 1 }, { "emission_luminance", GTLC_OPBR_EMISSION_LUMINANCE, 1 },
+      { "emission_color", GTLC_OPBR_EMISSION_COLOR_R, 3 }, { "thin_film_weight", GTLC_OPBR_THIN_FILM_WEIGHT, 1 }, { "thin_film_thickness", GTLC_OPBR_THIN_FILM_THICKNESS, 1 },
+      { "thin_film_ior", GTLC_OPBR_THIN_FILM_IOR, 1 }, { "geometry_opacity", GTLC_OPBR_GEOMETRY_OPACITY, 1 }, { "geometry_thin_walled", GTLC_OPBR_GEOMETRY_THIN_WALLED, 1 },
+      { "subsurface_weight", GTLC_OPBR_SUBSURFACE_WEIGHT, 1 }, { "subsurface_color", GTLC_OPBR_SUBSURFACE_COLOR_R, 3 } };
+
+    template <size_t N> void applyInputs(const std::vector<XmlInput>& inputs, const Slot (&slots)[N], GtlcMaterialDesc& d, const char* matName)
+    {
+      for (const XmlInput& in : inputs) {
+        const Slot* slot = nullptr;
+        for (const Slot& s : slots) if (in.name == s.name) { slot = &s; break; }
+        if (!slot) continue;   // inputs the closures do not model (normal, displacement, occlusion, ...)
+        if (in.connected) { fprintf(stderr, "[gi] warning: material '%s': input '%s' is connected (texture/primvar); using the default value\n", matName ? matName : "", in.name.c_str()); continue; }
+        float v[4];
+        if (parseFloats(in.value, v, slot->count) == slot->count) memcpy(&d.params[slot->index], v, sizeof(float) * slot->count);
+      }
+    }
+  }
+
+  // Exposed for tests: lowers MaterialX XML to a closure + parameter block.  Returns false if no supported shader node is present.
+  bool giLowerMtlxToClosure(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out)
+  {
+    std::string xml(mtlxSrc ? mtlxSrc : "");
+    std::vector<XmlInput> inputs;
+    if (findShaderNode(xml, "UsdPreviewSurface", inputs)) {
+      gtlc_material_desc_defaults(GTLC_CLOSURE_USD_PREVIEW_SURFACE, out);
+      applyInputs(inputs, kUpsSlots, *out, name);
+    } else if (findShaderNode(xml, "open_pbr_surface", inputs)) {
+      gtlc_material_desc_defaults(GTLC_CLOSURE_OPENPBR, out);
+      applyInputs(inputs, kOpbrSlots, *out, name);
+    } else {
+      return false;
+    }
+    out->name = name;
+    return true;
+  }
+
+  const char* giGetLastError() { std::lock_guard<std::mutex> g(s_errMutex); static thread_local std::string c; c = s_lastError; return c.c_str(); }
+  void giRegisterMtlxDocSerializer(GiMtlxDocToXmlFn fn) { s_docSerializer = fn; }
+
+  GiStatus giInitialize(const GiInitParams& /* shader / MDL paths are meaningless here: closures are compiled ahead of time */)
+  {
+    GtlcInitParams p; p.deviceIndex = -1; p.reserved = 0;
+    if (const char* ov = getenv("GTL_DEVICE_INDEX_OVERRIDE")) p.deviceIndex = atoi(ov);   // CgpuVk.cpp:975
+    if (gtlc_initialize(&p) != GTLC_OK) { logError(gtlc_last_error()); return GiStatus::Error; }
+    return GiStatus::Ok;
+  }
+  void giTerminate() { gtlc_terminate(); }
+  void giRegisterAssetReader(GiAssetReader* reader) { s_assetReader = reader; }
+
+  GiScene* giCreateScene() { return wrap<GiScene>(gtlc_scene_create()); }
+  void giDestroyScene(GiScene* s) { if (!s) return; gtlc_scene_destroy(s->h); delete s; }
+
+  GiMaterial* giCreateMaterialFromMtlxStr(GiScene* scene, const char* name, const char* mtlxSrc)
+  {
+    if (!scene) return nullptr;
+    GtlcMaterialDesc d;
+    if (!giLowerMtlxToClosure(mtlxSrc, name, &d)) { logError(std::string("material '") + (name ? name : "") + "': no UsdPreviewSurface / open_pbr_surface node found (other MaterialX shading models need the mc/MDL path, out of scope)"); return nullptr; }
+    return wrap<GiMaterial>(gtlc_material_create(scene->h, &d));
+  }
+  GiMaterial* giCreateMaterialFromMtlxDoc(GiScene* scene, const char* name, const std::shared_ptr<void> doc)
+  {
+    if (!s_docSerializer) { logError("giCreateMaterialFromMtlxDoc: no MaterialX serializer registered (giRegisterMtlxDocSerializer); see INTEGRATION.md"); return nullptr; }
+    std::string xml = s_docSerializer(doc);
+    return giCreateMaterialFromMtlxStr(scene, name, xml.c_str());
+  }
+  GiMaterial* giCreateMaterialFromMdlFile(GiScene*, const char* name, const char* filePath, const char*, const GiMaterialParameters&)
+  {
+    logError(std::string("giCreateMaterialFromMdlFile('") + (name ? name : "") + "', '" + (filePath ? filePath : "") + "'): arbitrary MDL needs the MDL SDK (not available; SURVEY.md section 2 #8)");
+    return nullptr;
+  }
+  void giDestroyMaterial(GiMaterial* m) { if (!m) return; gtlc_material_destroy(m->h); delete m; }
+
+  GiMesh* giCreateMesh(GiScene* scene, const GiMeshDesc& desc)
+  {
+    if (!scene) return nullptr;
+    static_assert(sizeof(GiVertex) == sizeof(GtlcVertex) && sizeof(GiFace) == sizeof(GtlcFace), "layouts must match");
+    GtlcMeshDesc d;
+    d.faceCount = desc.faceCount; d.faces = reinterpret_cast<const GtlcFace*>(desc.faces.data());
+    d.faceIds = desc.faceIds.size() == desc.faceCount ? reinterpret_cast<const int32_t*>(desc.faceIds.data()) : nullptr;
+    d.id = desc.id; d.isDoubleSided = desc.isDoubleSided; d.isLeftHanded = desc.isLeftHanded; d.name = desc.name; d.maxFaceId = desc.maxFaceId;
+    d.vertexCount = desc.vertexCount; d.vertices = reinterpret_cast<const GtlcVertex*>(desc.vertices.data());
+    return wrap<GiMesh>(gtlc_mesh_create(scene->h, &d));
+  }
+  void giSetMeshTransform(GiMesh* m, const float* mat4x4) { if (m) gtlc_mesh_set_transform(m->h, mat4x4); }
+  void giSetMeshInstanceTransforms(GiMesh* m, uint32_t count, const float (*t)[4][4]) { if (m) gtlc_mesh_set_instance_transforms(m->h, count, reinterpret_cast<const float*>(t)); }
+  void giSetMeshInstancerPrimvars(GiMesh*, const std::vector<GiPrimvarData>&) { /* primvar readers: SURVEY.md 8f rank 2 */ }
+  void giSetMeshInstanceIds(GiMesh* m, uint32_t count, int* ids) { if (m) gtlc_mesh_set_instance_ids(m->h, count, ids); }
+  void giSetMeshMaterial(GiMesh* m, GiMaterial* mat) { if (m) gtlc_mesh_set_material(m->h, mat ? mat->h : 0); }
+  void giSetMeshVisibility(GiMesh* m, bool visible) { if (m) gtlc_mesh_set_visibility(m->h, visible); }
+  void giDestroyMesh(GiMesh* m) { if (!m) return; gtlc_mesh_destroy(m->h); delete m; }
+
+  GiStatus giRender(const GiRenderParams& params)
+  {
+    std::vector<GtlcAovBinding> bindings(params.aovBindings.size());
+    for (size_t i = 0; i < bindings.size(); i++) {
+      bindings[i].aovId = (int32_t) params.aovBindings[i].aovId;
+      memcpy(bindings[i].clearValue, params.aovBindings[i].clearValue, GI_MAX_AOV_COMP_SIZE);
+      bindings[i].renderBuffer = params.aovBindings[i].renderBuffer ? params.aovBindings[i].renderBuffer->h : 0;
+    }
+    GtlcRenderParams p;
+    p.aovBindingCount = (uint32_t) bindings.size(); p.aovBindings = bindings.data();
+    static_assert(sizeof(GiCameraDesc) == sizeof(GtlcCameraDesc), "camera layouts must match");
+    memcpy(&p.camera, &params.camera, sizeof(GtlcCameraDesc));
+    p.domeLight = params.domeLight ? params.domeLight->h : 0;
+    const GiRenderSettings& s = params.renderSettings;
+    GtlcRenderSettings& r = p.renderSettings;
+    r.clippingPlanes = s.clippingPlanes; r.depthOfField = s.depthOfField; r.domeLightCameraVisible = s.domeLightCameraVisible;
+    r.filterImportanceSampling = s.filterImportanceSampling; r.frame = s.frame; r.jitteredSampling = s.jitteredSampling;
+    r.lightIntensityMultiplier = s.lightIntensityMultiplier; r.maxBounces = s.maxBounces; r.maxSampleValue = s.maxSampleValue;
+    r.maxVolumeWalkLength = s.maxVolumeWalkLength; r.mediumStackSize = s.mediumStackSize; r.metersPerSceneUnit = s.metersPerSceneUnit;
+    r.nextEventEstimation = s.nextEventEstimation; r.progressiveAccumulation = s.progressiveAccumulation; r.rrBounceOffset = s.rrBounceOffset;
+    r.rrInvMinTermProb = s.rrInvMinTermProb; r.spp = s.spp; r.time = s.time;
+    p.scene = params.scene ? params.scene->h : 0;
+    if (gtlc_render(&p) != GTLC_OK) { logError(gtlc_last_error()); return GiStatus::Error; }
+    return GiStatus::Ok;
+  }
+
+#define GI_LIGHT_BOILERPLATE(Type, prefix)                                                                           \
+  Gi##Type##Light* giCreate##Type##Light(GiScene* scene) { return scene ? wrap<Gi##Type##Light>(gtlc_##prefix##_light_create(scene->h)) : nullptr; } \
+  void giDestroy##Type##Light(GiScene* scene, Gi##Type##Light* l) { if (!scene || !l) return; gtlc_##prefix##_light_destroy(scene->h, l->h); delete l; } \
+  void giSet##Type##LightBaseEmission(Gi##Type##Light* l, float* rgb) { if (l) gtlc_##prefix##_light_set_base_emission(l->h, rgb); } \
+  void giSet##Type##LightDiffuseSpecular(Gi##Type##Light* l, float d, float s) { if (l) gtlc_##prefix##_light_set_diffuse_specular(l->h, d, s); }
+  GI_LIGHT_BOILERPLATE(Sphere, sphere)
+  GI_LIGHT_BOILERPLATE(Distant, distant)
+  GI_LIGHT_BOILERPLATE(Rect, rect)
+  GI_LIGHT_BOILERPLATE(Disk, disk)
+  void giSetSphereLightPosition(GiSphereLight* l, float* p) { if (l) gtlc_sphere_light_set_position(l->h, p); }
+  void giSetSphereLightRadius(GiSphereLight* l, float x, float y, float z) { if (l) gtlc_sphere_light_set_radius(l->h, x, y, z); }
+  void giSetDistantLightDirection(GiDistantLight* l, float* d) { if (l) gtlc_distant_light_set_direction(l->h, d); }
+  void giSetDistantLightAngle(GiDistantLight* l, float a) { if (l) gtlc_distant_light_set_angle(l->h, a); }
+  void giSetRectLightOrigin(GiRectLight* l, float* o) { if (l) gtlc_rect_light_set_origin(l->h, o); }
+  void giSetRectLightTangents(GiRectLight* l, float* t0, float* t1) { if (l) gtlc_rect_light_set_tangents(l->h, t0, t1); }
+  void giSetRectLightDimensions(GiRectLight* l, float w, float h) { if (l) gtlc_rect_light_set_dimensions(l->h, w, h); }
+  void giSetDiskLightOrigin(GiDiskLight* l, float* o) { if (l) gtlc_disk_light_set_origin(l->h, o); }
+  void giSetDiskLightTangents(GiDiskLight* l, float* t0, float* t1) { if (l) gtlc_disk_light_set_tangents(l->h, t0, t1); }
+  void giSetDiskLightRadius(GiDiskLight* l, float x, float y) { if (l) gtlc_disk_light_set_radius(l->h, x, y); }
+
+  // Dome light: the reference decodes any image format through imgio (out of scope).  The facade reads
+  // Portable Float Maps (.pfm, "PF" header, bottom-to-top rows) itself -- through the registered
+  // GiAssetReader when there is one -- and reports other formats as an error.
+  GiDomeLight* giCreateDomeLight(GiScene* scene, const char* filePath)
+  {
+    if (!scene || !filePath) return nullptr;
+    std::string bytes;
+    if (s_assetReader) {
+      GiAsset* a = s_assetReader->open(filePath);
+      if (a) { bytes.assign((const char*) s_assetReader->data(a), s_assetReader->size(a)); s_assetReader->close(a); }
+    }
+    if (bytes.empty()) { std::ifstream f(filePath, std::ios::binary); bytes.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>()); }
+    int w = 0, h = 0, consumed = 0; float scale = 0.0f; char magic[3] = { 0, 0, 0 };
+    if (bytes.size() < 8 || sscanf(bytes.c_str(), "%2s %d %d %f%n", magic, &w, &h, &scale, &consumed) != 4 || strcmp(magic, "PF") != 0 || w <= 0 || h <= 0) {
+      logError(std::string("unable to load dome light texture at ") + filePath + " (this build decodes .pfm only; imgio is out of scope)");
+      return nullptr;
+    }
+    size_t off = (size_t) consumed + 1;
+    if (bytes.size() < off + (size_t) w * h * 12) { logError("truncated .pfm dome light texture"); return nullptr; }
+    std::vector<float> rgba((size_t) w * h * 4);
+    const float* src = reinterpret_cast<const float*>(bytes.data() + off);
+    for (int y = 0; y < h; y++)          // PFM rows run bottom to top; the sampler's v = 0 row is the top of the image
+      for (int x = 0; x < w; x++) {
+        const float* s = src + ((size_t) (h - 1 - y) * w + x) * 3;
+        float* d = &rgba[((size_t) y * w + x) * 4];
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = 1.0f;
+      }
+    return wrap<GiDomeLight>(gtlc_dome_light_create(scene->h, (uint32_t) w, (uint32_t) h, rgba.data()));
+  }
+  void giDestroyDomeLight(GiDomeLight* l) { if (!l) return; gtlc_dome_light_destroy(l->h); delete l; }
+  void giSetDomeLightRotation(GiDomeLight* l, float* q) { if (l) gtlc_dome_light_set_rotation(l->h, q); }
+  void giSetDomeLightBaseEmission(GiDomeLight* l, float* rgb) { if (l) gtlc_dome_light_set_base_emission(l->h, rgb); }
+  void giSetDomeLightDiffuseSpecular(GiDomeLight* l, float d, float s) { if (l) gtlc_dome_light_set_diffuse_specular(l->h, d, s); }
+
+  GiRenderBuffer* giCreateRenderBuffer(uint32_t w, uint32_t h, GiRenderBufferFormat f) { return wrap<GiRenderBuffer>(gtlc_render_buffer_create(w, h, (int32_t) f)); }
+  void giDestroyRenderBuffer(GiRenderBuffer* rb) { if (!rb) return; gtlc_render_buffer_destroy(rb->h); delete rb; }
+  void* giGetRenderBufferMem(GiRenderBuffer* rb) { return rb ? gtlc_render_buffer_mem(rb->h) : nullptr; }
+}

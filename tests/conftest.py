@@ -22,6 +22,7 @@ def _built_libraries():
     from gatling_b200 import build as B
     if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
         B.build()
+        B.build_facade()
     yield
 
 
