@@ -126,7 +126,8 @@ GTLC_HD bool mat_is_thin_walled(int closure, const float* p) { return closure ==
 GTLC_D V3 mat_emission_intensity(int closure, const float* p)
 {
   if (closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) return p3(p, GTLC_UPS_EMISSIVE_R) * kPi;
-  if (closure == GTLC_CLOSURE_OPENPBR) return (p3(p, GTLC_OPBR_EMISSION_COLOR_R) * p[GTLC_OPBR_EMISSION_LUMINANCE]) * kPi;
+  if (closure == GTLC_CLOSURE_OPENPBR)   // open_pbr_surface.mtlx:582-623: uniform_edf tinted by the coat colour
+    return ((p3(p, GTLC_OPBR_EMISSION_COLOR_R) * p[GTLC_OPBR_EMISSION_LUMINANCE]) * kPi) * mix(v3(1.0f), p3(p, GTLC_OPBR_COAT_COLOR_R), clampf(p[GTLC_OPBR_COAT_WEIGHT], 0.0f, 1.0f));
   return v3(0.0f);
 }
 // mdl_volume_absorption_coefficient

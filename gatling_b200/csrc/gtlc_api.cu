@@ -5,6 +5,7 @@
 #include "../../include/gtlc.h"
 #include "bvh8.h"
 #include "wavefront.cuh"
+#include "sort.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -132,6 +133,7 @@ struct Global {
   float4* accum = nullptr; size_t accumCapacity = 0;
   Counters* counters = nullptr;
   uint32_t* visits = nullptr; size_t visitsCapacity = 0;
+  uint32_t* perm = nullptr; uint32_t* sortHist = nullptr; int sortBlocks = 0;
   std::vector<cudaEvent_t> events; size_t eventsUsed = 0;
   Global() { memset(&tuning, 0, sizeof(tuning)); tuning.maxPathsPerWave = 1u << 24; tuning.sortByMaterial = -1; memset(&stats, 0, sizeof(stats)); memset(q, 0, sizeof(q)); }
 };
@@ -340,6 +342,9 @@ bool ensurePool(size_t capacity)
   CUDA_OK(cudaMalloc(&g.hitTUVP, capacity * 16)); CUDA_OK(cudaMalloc(&g.hitInst, capacity * 4));
   CUDA_OK(cudaMalloc(&g.shO, capacity * 16)); CUDA_OK(cudaMalloc(&g.shD, capacity * 16)); CUDA_OK(cudaMalloc(&g.shC, capacity * 16));
   CUDA_OK(cudaMalloc(&g.sampleRad, capacity * 16));
+  cudaFree(g.perm); g.perm = nullptr;
+  CUDA_OK(cudaMalloc(&g.perm, capacity * 4));
+  if (!g.sortHist) { g.sortBlocks = g.smCount * 4; CUDA_OK(cudaMalloc(&g.sortHist, (size_t) kSortBins * g.sortBlocks * 4)); }
   g.poolCapacity = capacity;
   return true;
 }
@@ -471,7 +476,7 @@ void gtlc_terminate(void)
   cudaDeviceSynchronize();
   for (int k = 0; k < 2; k++) { cudaFree(g.q[k].rayO); cudaFree(g.q[k].rayD); cudaFree(g.q[k].thr); cudaFree(g.q[k].rad); cudaFree(g.q[k].slot); }
   memset(g.q, 0, sizeof(g.q));
-  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits);
+  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits); cudaFree(g.perm); cudaFree(g.sortHist); g.perm = nullptr; g.sortHist = nullptr;
   g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.sampleRad = nullptr; g.accum = nullptr; g.counters = nullptr; g.visits = nullptr;
   g.poolCapacity = 0; g.accumCapacity = 0; g.visitsCapacity = 0;
   for (cudaEvent_t e : g.events) cudaEventDestroy(e);
@@ -904,6 +909,7 @@ int gtlc_render(const GtlcRenderParams* params)
     const int gridElem = g.smCount * 8;
     const int traceBlocks = g.smCount * (g.tuning.reserved[1] > 0 ? g.tuning.reserved[1] : 8);
     const bool countVisits = g.tuning.countVisits != 0;
+    const bool sortByMaterial = g.tuning.sortByMaterial > 0 || (g.tuning.sortByMaterial < 0 && s->flatMaterials.size() > 1);
     uint64_t paths = 0;
     for (uint32_t pixBase = 0; pixBase < localPixels; pixBase += pixelsPerWave) {
       const uint32_t wavePixels = std::min(pixelsPerWave, localPixels - pixBase);
@@ -919,7 +925,15 @@ int gtlc_render(const GtlcRenderParams* params)
           P.rayO = g.q[inIdx].rayO; P.rayD = g.q[inIdx].rayD; P.hitTUVP = g.hitTUVP; P.hitInst = g.hitInst;
           P.numRays = &g.counters->numPaths[inIdx]; P.workCounter = &g.counters->workCounter;
           timed(K_TRACE, [&] { launchTrace<TRACE_CLOSEST>(P, countVisits, traceBlocks); });
-          timed(K_SHADE, [&] { shade_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, nullptr,
+          if (sortByMaterial) {
+            timed(K_SORT, [&] {
+              sort_count_kernel<<<g.sortBlocks, kSortBlock, 0, g.stream>>>(g.counters, inIdx, g.hitInst, ds.instInfo, g.sortHist);
+              sort_scan_kernel<<<1, 1024, 0, g.stream>>>(g.sortHist, (uint32_t) (kSortBins * g.sortBlocks));
+              sort_scatter_kernel<<<g.sortBlocks, kSortBlock, 0, g.stream>>>(g.counters, inIdx, g.hitInst, ds.instInfo, g.sortHist, g.perm);
+            });
+            launches += 2;
+          }
+          timed(K_SHADE, [&] { shade_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, sortByMaterial ? g.perm : nullptr,
                                                                           g.shO, g.shD, g.shC, g.sampleRad, g.counters, inIdx); });
           if (rs.nextEventEstimation) {
             prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;

@@ -367,3 +367,158 @@ def random_triangles(n_tris=1_000_000, width=1920, height=1080, spp=256, max_bou
     cam = Camera(position=(0.0, -4.0, 0.0), forward=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0), vfov=float(np.float32(0.6981317)))
     st = RenderSettings(spp=spp, maxBounces=max_bounces)
     return SceneDesc("random_tris_%d" % n_tris, [mesh], [material_diffuse((0.8, 0.8, 0.8), "lambert")], cam, st, width, height)
+
+
+# ---- parametric meshes (indexed, smooth normals, fallback tangents) --------------------------------
+def _grid_faces(nu, nv, wrap_u=True, wrap_v=False):
+    """Two triangles per (u, v) cell of an (nu x nv) vertex grid (wrapping adds the seam cell)."""
+    cu = nu if wrap_u else nu - 1
+    cv = nv if wrap_v else nv - 1
+    i, j = np.meshgrid(np.arange(cu), np.arange(cv), indexing="ij")
+    i2, j2 = (i + 1) % nu, (j + 1) % nv
+    a, b, c, d = i * nv + j, i2 * nv + j, i2 * nv + j2, i * nv + j2
+    f = np.stack([np.stack([a, b, c], -1), np.stack([a, c, d], -1)], -2).reshape(-1, 3)
+    return f.astype(np.uint32)
+
+
+def sphere_mesh(nu, nv, radius=1.0, displacement=0.0, seed=1):
+    """UV sphere with 2*nu*(nv-1) triangles (incl. degenerate pole slivers), optional radial displacement."""
+    u = (np.arange(nu, dtype=np.float32) / np.float32(nu)) * np.float32(2 * np.pi)
+    v = (np.arange(nv, dtype=np.float32) / np.float32(nv - 1)) * np.float32(np.pi)
+    uu, vv = np.meshgrid(u, v, indexing="ij")
+    n = np.stack([np.sin(vv) * np.cos(uu), np.sin(vv) * np.sin(uu), np.cos(vv)], -1).reshape(-1, 3).astype(np.float32)
+    r = np.full(len(n), radius, np.float32)
+    if displacement:
+        r = r * (np.float32(1) + np.float32(displacement) * (np.sin(np.float32(7 + seed % 5) * uu) * np.sin(np.float32(5 + seed % 3) * vv)).reshape(-1).astype(np.float32))
+    # v runs from the +z pole downwards, so (du x dv) points inwards: reverse the winding to face outwards
+    return bake_vertices(n * r[:, None], n), np.ascontiguousarray(_grid_faces(nu, nv, True, False)[:, ::-1])
+
+
+def torus_mesh(nu, nv, R=1.0, r=0.35):
+    u = (np.arange(nu, dtype=np.float32) / np.float32(nu)) * np.float32(2 * np.pi)
+    v = (np.arange(nv, dtype=np.float32) / np.float32(nv)) * np.float32(2 * np.pi)
+    uu, vv = np.meshgrid(u, v, indexing="ij")
+    n = np.stack([np.cos(vv) * np.cos(uu), np.cos(vv) * np.sin(uu), np.sin(vv)], -1).reshape(-1, 3).astype(np.float32)
+    c = np.stack([np.cos(uu), np.sin(uu), np.zeros_like(uu)], -1).reshape(-1, 3).astype(np.float32) * np.float32(R)
+    return bake_vertices(c + n * np.float32(r), n), _grid_faces(nu, nv, True, True)
+
+
+def cylinder_mesh(nu, nv, radius=0.5, height=1.0):
+    """Open-ended tube (side only), 2*nu*(nv-1) triangles, z in [0, height]."""
+    u = (np.arange(nu, dtype=np.float32) / np.float32(nu)) * np.float32(2 * np.pi)
+    z = (np.arange(nv, dtype=np.float32) / np.float32(nv - 1)) * np.float32(height)
+    uu, zz = np.meshgrid(u, z, indexing="ij")
+    n = np.stack([np.cos(uu), np.sin(uu), np.zeros_like(uu)], -1).reshape(-1, 3).astype(np.float32)
+    p = n * np.float32(radius)
+    p[:, 2] = zz.reshape(-1)
+    return bake_vertices(p, n), _grid_faces(nu, nv, True, False)
+
+
+def box_mesh(n, size=(1.0, 1.0, 1.0), inward=False):
+    """Axis-aligned box centred at the origin, every face an n x n grid (12 n^2 triangles), flat normals."""
+    verts, faces, base = [], [], 0
+    s = np.asarray(size, np.float32) * np.float32(0.5)
+    lin = (np.arange(n + 1, dtype=np.float32) / np.float32(n)) * np.float32(2) - np.float32(1)
+    a, b = np.meshgrid(lin, lin, indexing="ij")
+    for axis in range(3):
+        for sign in (-1.0, 1.0):
+            p = np.zeros(((n + 1) * (n + 1), 3), np.float32)
+            p[:, axis] = sign
+            p[:, (axis + 1) % 3] = a.reshape(-1)
+            p[:, (axis + 2) % 3] = b.reshape(-1)
+            nrm = np.zeros_like(p)
+            nrm[:, axis] = -sign if inward else sign
+            f = _grid_faces(n + 1, n + 1, False, False)
+            if (sign < 0) != inward:
+                f = f[:, ::-1]                       # keep the winding consistent with the outward/inward normal
+            verts.append(bake_vertices(p * s, nrm))
+            faces.append(f + np.uint32(base))
+            base += len(p)
+    return np.concatenate(verts), np.ascontiguousarray(np.concatenate(faces))
+
+
+def _trs(scale, angle, pos):
+    """USD row-vector 4x4: scale, rotate about Z, translate."""
+    c, s = math.cos(angle), math.sin(angle)
+    m = np.eye(4, dtype=np.float64)
+    m[0, :3] = (c * scale, s * scale, 0)
+    m[1, :3] = (-s * scale, c * scale, 0)
+    m[2, 2] = scale
+    m[3, :3] = pos
+    return m.astype(np.float32)
+
+
+_PALETTE = [(0.8, 0.8, 0.8), (0.75, 0.2, 0.15), (0.2, 0.55, 0.25), (0.15, 0.3, 0.7), (0.85, 0.65, 0.2), (0.5, 0.25, 0.6), (0.9, 0.5, 0.3), (0.3, 0.3, 0.3)]
+
+
+def openpbr_material_table(count, seed=0x9E3779B9):
+    """Fixed tables from SURVEY.md 8d: base colours x {rough dielectric, coated glossy dielectric, metal}, every 12th set glass."""
+    r = pcg32_uniform(seed, count * 4).reshape(count, 4)
+    mats = []
+    for i in range(count):
+        col = _PALETTE[i % len(_PALETTE)]
+        rough = float(np.float32(0.05) + r[i, 0] * np.float32(0.55))
+        kind = i % 3
+        if i % 12 == 11:
+            mats.append(material_openpbr("glass%d" % i, base_color=col, specular_roughness=min(rough, 0.15), transmission_weight=1.0,
+                                         transmission_color=(0.9, 0.95, 1.0), transmission_depth=0.5 if i % 24 == 23 else 0.0))
+        elif kind == 0:
+            mats.append(material_openpbr("diel%d" % i, base_color=col, specular_roughness=rough))
+        elif kind == 1:
+            mats.append(material_openpbr("coat%d" % i, base_color=col, specular_roughness=rough, coat_weight=1.0, coat_roughness=0.05 + 0.2 * float(r[i, 1]),
+                                         coat_color=(1.0, 0.95, 0.9)))
+        else:
+            mats.append(material_openpbr("metal%d" % i, base_color=col, base_metalness=1.0, specular_roughness=rough))
+    return mats
+
+
+def kitchen_standin(tris_per_instance=12500, instances=400, meshes=120, materials=24, width=1920, height=1080, spp=1024, max_bounces=8,
+                    seed=0x9E3779B9) -> SceneDesc:
+    """Configs C3/C4 stand-in (the Evermotion kitchen is not redistributable): 8x6x3 m room + instanced boxes / tubes / tori,
+    OpenPBR parameter sets, 2 rect lights at the ceiling + 1 distant light, NEE on."""
+    n_box = max(1, int(round(math.sqrt(tris_per_instance / 12.0))))
+    n_ring = max(3, int(round(math.sqrt(tris_per_instance / 2.0))))
+    protos = [box_mesh(n_box, (1.0, 1.0, 1.0)), cylinder_mesh(n_ring, n_ring + 1, 0.5, 1.0), torus_mesh(n_ring, n_ring, 0.6, 0.25)]
+    mats = openpbr_material_table(materials, seed)
+    room_v, room_f = box_mesh(1, (8.0, 6.0, 3.0), inward=True)
+    out = [Mesh(room_v, room_f, 0, _trs(1.0, 0.0, (0.0, 0.0, 1.5)), None, True, False, 1, "room")]
+    r = pcg32_uniform(seed ^ 0x5bd1e995, instances * 5).reshape(instances, 5)
+    per_mesh = [[] for _ in range(meshes)]
+    for k in range(instances):
+        scale = 0.2 + 0.3 * float(r[k, 0])
+        pos = (-3.6 + 7.2 * float(r[k, 1]), -2.6 + 5.2 * float(r[k, 2]), 0.02 + 1.6 * float(r[k, 3]) * float(r[k, 3]))
+        per_mesh[k % meshes].append(_trs(scale, 6.2831853 * float(r[k, 4]), pos))
+    for mi in range(meshes):
+        if not per_mesh[mi]:
+            continue
+        v, f = protos[mi % 3]
+        out.append(Mesh(v, f, 1 + (mi % (materials - 1)) if materials > 1 else 0, np.eye(4, dtype=np.float32), np.stack(per_mesh[mi]), True, False, 2 + mi, "prop%d" % mi))
+    cam = Camera(position=(0.0, -2.8, 1.6), forward=(0.0, 1.0, -0.12), up=(0.0, 0.12, 1.0), vfov=float(np.float32(1.0)))
+    st = RenderSettings(spp=spp, maxBounces=max_bounces, nextEventEstimation=True)
+    d = SceneDesc("kitchen_standin", out, mats, cam, st, width, height)
+    d.rect_lights.append(RectLight(origin=(-2.0, 0.0, 2.95), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(30, 30, 30), width=1.0, height=1.0))
+    d.rect_lights.append(RectLight(origin=(2.0, 0.5, 2.95), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(30, 28, 25), width=1.0, height=1.0))
+    d.distant_lights.append(DistantLight(direction=(0.3, 0.5, -0.8), base_emission=(2.0, 2.0, 2.2), angle=0.02))
+    return d
+
+
+def material_stress(tris_per_mesh=31250, meshes=64, width=1920, height=1080, spp=512, max_bounces=8, seed=0x9E3779B9) -> SceneDesc:
+    """Config C5 stand-in (GPUOpen matlib is not reachable): an 8x8 wall of displaced spheres, one distinct OpenPBR parameter
+    set per mesh (diffuse / coated / metal / glass), constant white dome light + one distant light, NEE on."""
+    side = int(math.ceil(math.sqrt(meshes)))
+    nu = max(4, int(round(math.sqrt(tris_per_mesh / 2.0))))
+    mats = openpbr_material_table(meshes, seed)
+    perm = np.argsort(pcg32_stream(seed, meshes), kind="stable")     # neighbouring spheres get unrelated parameter sets
+    out = []
+    for k in range(meshes):
+        v, f = sphere_mesh(nu, nu + 1, 1.0, 0.04, seed=k)
+        gx, gz = k % side, k // side
+        pos = ((gx - (side - 1) / 2.0) * 2.1, 0.0, (gz - (side - 1) / 2.0) * 2.1)
+        out.append(Mesh(v, f, int(perm[k]), _trs(1.0, 0.37 * k, pos), None, True, False, 1 + k, "ball%d" % k))
+    dist = side * 2.1 * 0.5 / math.tan(0.35) + 2.0
+    cam = Camera(position=(0.0, -dist, 0.0), forward=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0), vfov=float(np.float32(0.7)))
+    st = RenderSettings(spp=spp, maxBounces=max_bounces, nextEventEstimation=True)
+    d = SceneDesc("material_stress", out, mats, cam, st, width, height)
+    d.dome_light = DomeLight(np.ones((2, 4, 4), np.float32))
+    d.distant_lights.append(DistantLight(direction=(0.4, 0.7, -0.6), base_emission=(3.0, 3.0, 3.0), angle=0.05))
+    return d

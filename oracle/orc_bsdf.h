@@ -162,7 +162,8 @@ static inline bool mat_is_thin_walled(const Material& m)
 static inline V3 mat_emission_intensity(const Material& m)
 {
   if (m.closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) return p3(m, GTLC_UPS_EMISSIVE_R) * PI;
-  if (m.closure == GTLC_CLOSURE_OPENPBR) return (p3(m, GTLC_OPBR_EMISSION_COLOR_R) * m.p[GTLC_OPBR_EMISSION_LUMINANCE]) * PI;
+  if (m.closure == GTLC_CLOSURE_OPENPBR)   // open_pbr_surface.mtlx:582-623: uniform_edf tinted by the coat colour
+    return ((p3(m, GTLC_OPBR_EMISSION_COLOR_R) * m.p[GTLC_OPBR_EMISSION_LUMINANCE]) * PI) * mix(v3(1.0f), p3(m, GTLC_OPBR_COAT_COLOR_R), clampf(m.p[GTLC_OPBR_COAT_WEIGHT], 0.0f, 1.0f));
   return v3(0.0f);
 }
 // mdl_edf_emission_evaluate for df::diffuse_edf()

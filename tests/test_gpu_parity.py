@@ -194,3 +194,29 @@ def test_errors_are_loud(gpu):
         assert "mediumStackSize" in gpu.giLastError()
     finally:
         b.close()
+
+
+def test_render_parity_openpbr_material_stress(gpu):
+    """C5 stand-in at test size: 16 OpenPBR parameter sets (diffuse / coat / metal / glass), dome + distant light, NEE on."""
+    _render_parity(gpu, scenes.material_stress(tris_per_mesh=400, meshes=16, width=96, height=72, spp=4))
+
+
+def test_render_parity_kitchen_standin(gpu):
+    """C3 stand-in at test size: instanced boxes / tubes / tori in a room, rect + distant lights, NEE on."""
+    _render_parity(gpu, scenes.kitchen_standin(tris_per_instance=300, instances=60, meshes=12, materials=8, width=96, height=72, spp=4))
+
+
+def test_material_sort_is_invisible(gpu):
+    d = scenes.material_stress(tris_per_mesh=300, meshes=25, width=80, height=60, spp=3)
+    imgs = []
+    for mode in (0, 1):
+        gpu.set_tuning(sortByMaterial=mode)
+        b = gpu.BuiltScene(d)
+        try:
+            imgs.append(b.render().copy())
+            st = gpu.get_stats()
+            assert (st["msSort"] > 0) == (mode == 1)
+        finally:
+            b.close()
+            gpu.set_tuning(sortByMaterial=-1)
+    assert np.array_equal(imgs[0], imgs[1])

@@ -57,7 +57,8 @@ MATERIALS = [
     ("ups_default", scenes.material_usd_preview_surface(diffuse=(0.8, 0.8, 0.8))),
     ("ups_metal_coat", scenes.material_usd_preview_surface(diffuse=(0.9, 0.6, 0.2), metallic=1.0, roughness=0.3, clearcoat=1.0, clearcoatRoughness=0.1)),
     ("openpbr_default", scenes.material_openpbr()),
-    ("openpbr_metal_coat", scenes.material_openpbr(base_color=(0.9, 0.6, 0.3), base_metalness=1.0, specular_roughness=0.25, coat_weight=1.0, coat_roughness=0.1)),
+    ("openpbr_half_metal_tinted_coat", scenes.material_openpbr(base_color=(0.7, 0.3, 0.2), base_metalness=0.5, specular_roughness=0.5, specular_color=(0.9, 0.8, 0.7), coat_weight=0.6, coat_roughness=0.35, coat_color=(0.8, 0.9, 1.0), subsurface_weight=0.3)),
+    ("openpbr_metal_coat", scenes.material_openpbr(base_color=(0.9, 0.6, 0.3), base_metalness=1.0, specular_roughness=0.4, coat_weight=1.0, coat_roughness=0.3)),
 ]
 
 
