@@ -162,12 +162,14 @@ def run_reference(a):
     o = orc.OracleScene(desc)
     H = desc.height
     mid = H // 2
-    _, secs, rays = o.render(rows=(mid, mid + 2), spp=1)
+    cal_rows = min(H, 32)
+    o.render(rows=(mid, mid + 2), spp=1)                       # thread start-up
+    _, secs, rays = o.render(rows=(mid - cal_rows // 2, mid - cal_rows // 2 + cal_rows), spp=1)
     rate = (rays[0] + rays[1]) / max(secs, 1e-6)
     per_step_target = max(2.0, min(20.0, 120.0 / max(a.steps + a.warmup, 1)))
-    rows = int(min(H, max(2, rate * per_step_target / max((rays[0] + rays[1]) / 2.0 * 2, 1))))
-    r0 = max(0, mid - rows // 2)
     spp = 2
+    rows = int(min(H, max(2, rate * per_step_target / max((rays[0] + rays[1]) / float(cal_rows) * spp, 1))))
+    r0 = max(0, mid - rows // 2)
     for _ in range(a.warmup):
         o.render(rows=(r0, r0 + rows), spp=spp)
     t_total, ray_total = 0.0, 0

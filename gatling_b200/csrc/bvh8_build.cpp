@@ -9,6 +9,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 
@@ -31,8 +32,9 @@ struct Box {
 struct BinNode { Box box; uint32_t left, right, first, count; };
 
 constexpr int kBins = 16;
-constexpr uint32_t kMaxLeaf = 3;
-constexpr float kNodeCost = 0.6f;  // relative to one triangle test
+// SAH parameters (overridable through GTLC_BVH_MAX_LEAF / GTLC_BVH_NODE_COST for tuning experiments)
+uint32_t kMaxLeaf = 3;
+float kNodeCost = 0.6f;  // relative to one triangle test
 constexpr float kTriCost = 1.0f;
 
 struct Builder {
@@ -133,6 +135,8 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     out.buildSeconds = 0.0;
     return;
   }
+  if (const char* e = getenv("GTLC_BVH_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 3) kMaxLeaf = (uint32_t) v; }
+  if (const char* e = getenv("GTLC_BVH_NODE_COST")) { float v = (float) atof(e); if (v > 0.0f) kNodeCost = v; }
   Builder b(tris);
   b.triBox.resize(N); b.cen.resize((size_t) N * 3); b.idx.resize(N);
 #pragma omp parallel for schedule(static)

@@ -387,6 +387,7 @@ TraceParams makeTraceParams(Scene* s)
   P.nodes = s->dNodes.ptr; P.tris = s->dTris.ptr;
   P.stats = g.counters->stats;
   P.refillThreshold = g.tuning.reserved[0] > 0 ? g.tuning.reserved[0] : kRefillThreshold;
+  P.triThreshold = g.tuning.reserved[2] > 0 ? g.tuning.reserved[2] : 8;
   return P;
 }
 
@@ -398,6 +399,7 @@ template <int MODE> void launchTrace(const TraceParams& P, bool count, int block
     case 2: trace_kernel_v1<MODE, 2><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 3: trace_kernel_v1<MODE, 3><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 4: trace_kernel_v1<MODE, 4><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    case 5: trace_kernel_v2<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     default: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
   }
 }

@@ -19,6 +19,9 @@
 
 namespace gtlc {
 
+#ifndef GTLC_TRACE_MIN_BLOCKS
+#define GTLC_TRACE_MIN_BLOCKS 7   // 72 registers: 7 CTAs = 28 warps per SM (measured best of 6/7/8 on C2)
+#endif
 constexpr int kTraceBlock = 128;         // threads per CTA
 constexpr int kStackSize = 48;           // >= 2 x wide-tree depth (node groups + postponed triangle groups; checked on the host)
 constexpr int kRefillThreshold = 8;      // idle lanes that trigger a refill
@@ -43,6 +46,7 @@ struct TraceParams {
   unsigned long long* stats;            // [1] node visits, [2] triangle tests, [4] max node visits of one ray, [5] non-finite rays
   uint32_t* visitsPerRay;               // optional 2 x uint32 per ray
   int refillThreshold;                  // idle lanes that trigger a refill (kRefillThreshold by default)
+  int triThreshold;                     // variant 5: lanes with pending triangles that trigger a triangle phase
 };
 
 // Quantised byte q (0..255) taken from byte `j` of `w`, as the float 32768 + q: one PRMT builds
@@ -180,7 +184,7 @@ GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, con
 }
 
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock) trace_kernel(TraceParams P)
+__global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kernel(TraceParams P)
 {
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
@@ -405,6 +409,129 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v1(TraceParams P)
       }
       // postpone what is left
       if (active && !done && T.y != 0u) { stack[sp++] = T; T.y = 0u; }
+      if (done) {
+        const bool hit = bprim != 0xFFFFFFFFu;
+        if (MODE == TRACE_SHADOW) {
+          if (!hit) {
+            const float4 c = __ldg(&P.shContrib[rayIdx]);
+            const uint32_t target = f2u(c.w);
+            float4* dst = (target & 0x80000000u) ? (P.radSample + (target & 0x7FFFFFFFu)) : (P.radPath + target);
+            float4 cur = *dst;
+            cur.x += c.x; cur.y += c.y; cur.z += c.z;
+            *dst = cur;
+          }
+        } else {
+          P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
+          if (P.hitInst) P.hitInst[rayIdx] = binst;
+        }
+        active = false;
+      }
+      const unsigned idle = __ballot_sync(FULL, !active);
+      if (idle == FULL) break;
+      if (!exhausted && __popc(idle) >= P.refillThreshold) break;
+    }
+  }
+}
+
+// ---- variant 5: two-deep pending-triangle FIFO ------------------------------------------------------
+// A lane keeps up to two triangle groups (T0, T1) in registers and goes on with node steps while it has
+// room; the warp enters a triangle phase only when >= triThreshold lanes have triangles pending or nobody
+// can make progress on nodes.  Culling is delayed by at most one node step per lane (unlike variant 1,
+// which parks triangle groups on the stack indefinitely).  Hits are identical to variant 0.
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock) trace_kernel_v2(TraceParams P)
+{
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = *P.numRays;
+  const int triThr = P.triThreshold;
+
+  uint2 stack[kStackSize];
+  int sp = 0;
+  bool active = false;
+  bool exhausted = false;
+  uint32_t rayIdx = 0;
+  RaySetup r;
+  float bt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t bprim = 0xFFFFFFFFu, binst = 0xFFFFFFFFu;
+  float tmax = 0.0f;
+  uint2 G = make_uint2(0u, 0u), T0 = make_uint2(0u, 0u), T1 = make_uint2(0u, 0u);
+
+  while (true) {
+    if (!exhausted) {
+      const unsigned need = __ballot_sync(FULL, !active);
+      if (need) {
+        const int leader = __ffs(need) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t) __popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active) {
+          rayIdx = base + (uint32_t) __popc(need & ((1u << lane) - 1u));
+          if (rayIdx < n) {
+            const float4 ro = __ldg(&P.rayO[rayIdx]);
+            const float4 rd = __ldg(&P.rayD[rayIdx]);
+            ray_setup(r, ro, rd);
+            tmax = rd.w;
+            bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
+            sp = 0;
+            active = tmax > r.tmin;
+            if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
+            G = make_uint2(0u, 0x80000000u); T0 = make_uint2(0u, 0u); T1 = make_uint2(0u, 0u);
+            if (!active && MODE != TRACE_SHADOW) { P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu; }
+          }
+        }
+        if (base + (uint32_t) __popc(need) >= n) exhausted = true;
+      }
+    }
+    if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
+
+    while (true) {
+      bool done = false;
+      // ---- A: one node step for every lane that has node work and room for its triangles ----
+      if (active && T1.y == 0u) {
+        if (!(G.y & 0xFF000000u) && sp > 0) G = stack[--sp];
+        if (G.y & 0xFF000000u) {
+          const uint32_t hits_imask = G.y;
+          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
+          G.y &= ~(1u << bit);
+          if (G.y & 0xFF000000u) stack[sp++] = G;
+          const uint32_t slot = (bit - 24u) ^ r.octinv;
+          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
+          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
+          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
+          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+          const uint2 Tn = make_uint2(n1.y, hm & 0x00FFFFFFu);
+          if (Tn.y) { if (T0.y == 0u) T0 = Tn; else T1 = Tn; }
+        }
+      }
+      // ---- B: triangle phase when enough lanes wait for it, or when nothing else can progress ----
+      const bool canNode = active && T1.y == 0u && ((G.y & 0xFF000000u) != 0u || sp > 0);
+      unsigned pendMask = __ballot_sync(FULL, active && T0.y != 0u);
+      const unsigned nodeMask = __ballot_sync(FULL, canNode);
+      if (pendMask && (__popc(pendMask) >= triThr || nodeMask == 0u)) {
+        do {
+          if (active && !done && T0.y != 0u) {
+            const uint32_t j = (uint32_t) __ffs(T0.y) - 1u;
+            T0.y &= T0.y - 1u;
+            const float4* tp = P.tris + (size_t) (T0.x + j) * 3;
+            const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            float t, u, v;
+            if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+              if (t > r.tmin && t < tmax) {
+                const uint32_t prim = f2u(a.w), inst = f2u(b.w);
+                if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; }
+                else {
+                  const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
+                  if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
+                }
+              }
+            }
+            if (T0.y == 0u) { T0 = T1; T1 = make_uint2(0u, 0u); }
+          }
+          pendMask = __ballot_sync(FULL, active && !done && T0.y != 0u);
+        } while (pendMask);
+      }
+      if (active && !done && T0.y == 0u && !(G.y & 0xFF000000u) && sp == 0) done = true;
       if (done) {
         const bool hit = bprim != 0xFFFFFFFFu;
         if (MODE == TRACE_SHADOW) {

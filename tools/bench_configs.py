@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Runs the non-headline configs of BASELINE.json (C1 cornell, C3 kitchen stand-in, C5 material stress) on one GPU at a
+reduced sample count and prints one JSON line each: Mray/s, kernel times, BVH build time, sort on/off."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gatling_b200 import gi, scenes  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--configs", default="c1,c3,c5")
+ap.add_argument("--spp", type=int, default=16)
+ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale of c3/c5")
+a = ap.parse_args()
+assert gi.giInitialize(0) == gi.GiStatus.Ok, gi.giLastError()
+
+
+def make(name):
+    if name == "c1":
+        return scenes.cornell(512, 512, spp=64, max_bounces=4)
+    if name == "c3":
+        return scenes.kitchen_standin(tris_per_instance=int(12500 * a.scale), spp=a.spp)
+    if name == "c5":
+        return scenes.material_stress(tris_per_mesh=int(31250 * a.scale), spp=a.spp)
+    raise SystemExit("unknown config " + name)
+
+
+for name in a.configs.split(","):
+    t0 = time.perf_counter()
+    d = make(name)
+    t_gen = time.perf_counter() - t0
+    b = gi.BuiltScene(d)
+    for sort in ((-1,) if len(d.materials) == 1 else (0, 1)):
+        gi.set_tuning(sortByMaterial=sort)
+        best = None
+        for rep in range(3):
+            gi.set_shard(b.scene, 0, 1, 64)
+            b.render()
+            s = gi.get_stats()
+            if best is None or s["msTotal"] < best["msTotal"]:
+                best = s
+        rays = best["closestRays"] + best["shadowRays"]
+        print(json.dumps({"config": name, "scene": d.name, "triangles": d.triangle_count, "materials": len(d.materials), "spp": d.settings.spp,
+                          "sort": sort, "Mray_s": rays / best["msTotal"] / 1e3, "ms_total": best["msTotal"], "closest": best["closestRays"],
+                          "shadow": best["shadowRays"], "ms_trace": best["msTraceClosest"], "ms_shadow": best["msTraceAny"], "ms_shade": best["msShade"],
+                          "ms_sort": best["msSort"], "bvh_build_ms": best["msBvhBuild"], "bvh_nodes": best["bvhNodeCount"], "depth": best["bvhMaxDepth"],
+                          "scene_gen_s": round(t_gen, 2)}), flush=True)
+    b.close()
+gi.giTerminate()

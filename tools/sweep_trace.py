@@ -17,6 +17,7 @@ ap.add_argument("--variants", default="0,1,2,3,4")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--refill", default="0")
 ap.add_argument("--ctas", default="0")
+ap.add_argument("--trithr", default="0")
 a = ap.parse_args()
 
 assert gi.giInitialize(0) == gi.GiStatus.Ok, gi.giLastError()
@@ -31,8 +32,9 @@ print("counting pass: rays %d  nodes/ray %.2f  tris/ray %.2f  max nodes of one r
 gi.set_tuning(countVisits=0)
 import ctypes as C
 combos = [(v, rf, ct) for v in [int(x) for x in a.variants.split(",")] for rf in [int(x) for x in a.refill.split(",")] for ct in [int(x) for x in a.ctas.split(",")]]
-for v, rf, ct in combos:
-    gi.set_tuning(traceVariant=v, skipReadback=0, reserved=(C.c_int32 * 3)(rf, ct, 0))
+combos = [(v, rf, ct, tt) for (v, rf, ct) in combos for tt in ([int(x) for x in a.trithr.split(",")] if v == 5 else [0])]
+for v, rf, ct, tt in combos:
+    gi.set_tuning(traceVariant=v, skipReadback=0, reserved=(C.c_int32 * 3)(rf, ct, tt))
     best = None
     for _ in range(a.reps):
         gi.set_shard(b.scene, 0, 1, 64)
@@ -44,7 +46,7 @@ for v, rf, ct in combos:
         ref = img
     same = bool(np.array_equal(ref, img))
     rays = best["closestRays"] + best["shadowRays"]
-    print("variant %d refill %d ctas/SM %d: %.1f Mray/s total  trace %.2f ms  shade %.2f ms  total %.2f ms  identical=%s depth=%d"
-          % (v, rf, ct, rays / best["msTotal"] / 1e3, best["msTraceClosest"], best["msShade"], best["msTotal"], same, best["bvhMaxDepth"]), flush=True)
+    print("variant %d refill %d ctas/SM %d triThr %d: %.1f Mray/s total  trace %.2f ms  shade %.2f ms  total %.2f ms  identical=%s depth=%d"
+          % (v, rf, ct, tt, rays / best["msTotal"] / 1e3, best["msTraceClosest"], best["msShade"], best["msTotal"], same, best["bvhMaxDepth"]), flush=True)
 b.close()
 gi.giTerminate()
