@@ -272,22 +272,23 @@ GTLC_D void ups_evaluate(const float* p, BsdfEval& d, const ShadingState& s)
 
 namespace gtlc {
 
-// The generated mdl_bsdf_scattering_sample / _evaluate entry points, selected by closure id.
+// The generated mdl_bsdf_scattering_sample / _evaluate entry points, selected by closure id.  MAXC = highest
+// closure id present in the scene: kernels are instantiated per closure set so that a diffuse-only scene does
+// not pay the registers of the layered closures (the counterpart of the reference's per-material shader
+// permutations, GlslShaderGen.cpp:211-262).
+template <int MAXC>
 GTLC_D void bsdf_sample(int closure, const float* p, BsdfSample& d, const ShadingState& s)
 {
-  switch (closure) {
-    case GTLC_CLOSURE_DIFFUSE: diffuse_sample(p, d, s); break;
-    case GTLC_CLOSURE_USD_PREVIEW_SURFACE: ups_sample(p, d, s); break;
-    default: openpbr_sample(p, d, s); break;
-  }
+  if (MAXC == GTLC_CLOSURE_DIFFUSE || closure == GTLC_CLOSURE_DIFFUSE) { diffuse_sample(p, d, s); return; }
+  if (MAXC == GTLC_CLOSURE_USD_PREVIEW_SURFACE || closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { ups_sample(p, d, s); return; }
+  openpbr_sample(p, d, s);
 }
+template <int MAXC>
 GTLC_D void bsdf_evaluate(int closure, const float* p, BsdfEval& d, const ShadingState& s)
 {
-  switch (closure) {
-    case GTLC_CLOSURE_DIFFUSE: diffuse_evaluate(p, d, s); break;
-    case GTLC_CLOSURE_USD_PREVIEW_SURFACE: ups_evaluate(p, d, s); break;
-    default: openpbr_evaluate(p, d, s); break;
-  }
+  if (MAXC == GTLC_CLOSURE_DIFFUSE || closure == GTLC_CLOSURE_DIFFUSE) { diffuse_evaluate(p, d, s); return; }
+  if (MAXC == GTLC_CLOSURE_USD_PREVIEW_SURFACE || closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { ups_evaluate(p, d, s); return; }
+  openpbr_evaluate(p, d, s);
 }
 
 } // namespace gtlc

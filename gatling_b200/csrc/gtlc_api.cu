@@ -912,6 +912,8 @@ int gtlc_render(const GtlcRenderParams* params)
     const int traceBlocks = g.smCount * (g.tuning.reserved[1] > 0 ? g.tuning.reserved[1] : 8);
     const bool countVisits = g.tuning.countVisits != 0;
     const bool sortByMaterial = g.tuning.sortByMaterial > 0 || (g.tuning.sortByMaterial < 0 && s->flatMaterials.size() > 1);
+    int maxClosure = GTLC_CLOSURE_DIFFUSE;
+    for (Material* m : s->flatMaterials) maxClosure = std::max(maxClosure, (int) m->closure);
     uint64_t paths = 0;
     for (uint32_t pixBase = 0; pixBase < localPixels; pixBase += pixelsPerWave) {
       const uint32_t wavePixels = std::min(pixelsPerWave, localPixels - pixBase);
@@ -935,8 +937,15 @@ int gtlc_render(const GtlcRenderParams* params)
             });
             launches += 2;
           }
-          timed(K_SHADE, [&] { shade_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, sortByMaterial ? g.perm : nullptr,
-                                                                          g.shO, g.shD, g.shC, g.sampleRad, g.counters, inIdx); });
+          timed(K_SHADE, [&] {
+            const uint32_t* permArg = sortByMaterial ? g.perm : nullptr;
+#define GTLC_LAUNCH_SHADE(MAXC, NEE) shade_kernel<MAXC, NEE><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.sampleRad, g.counters, inIdx)
+            const bool nee = rs.nextEventEstimation != 0;
+            if (maxClosure == GTLC_CLOSURE_DIFFUSE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, false); }
+            else if (maxClosure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_USD_PREVIEW_SURFACE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_USD_PREVIEW_SURFACE, false); }
+            else { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_OPENPBR, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_OPENPBR, false); }
+#undef GTLC_LAUNCH_SHADE
+          });
           if (rs.nextEventEstimation) {
             prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;
             TraceParams S = makeTraceParams(s);

@@ -326,6 +326,7 @@ GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uin
 // ---- shade: rp_main.chit:132-493 + rp_main.miss:55-87 + rp_main.rgen:397-480 ----------------------
 // One thread per live path.  Survivors are compacted into `qout`, shadow rays appended to the shadow
 // queue, finished samples written to sampleRad[slot].
+template <int MAXC, bool NEE>
 __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
   const int lane = threadIdx.x & 31;
   const uint32_t rrBounceOffset = ubo.maxBouncesAndRrBounceOffset & 0xFFFFu;           // rgen:291
   uint32_t maxBounces = ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > kPayloadBouncesMask) maxBounces = kPayloadBouncesMask;
-  const bool nee = (ubo.flags & FLAG_NEE) != 0;
+  const bool nee = NEE;   // NEXT_EVENT_ESTIMATION is a compile-time permutation in the reference too (GlslShaderGen.cpp:107,247)
 
   for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nRounded; it += gridDim.x * blockDim.x) {
     bool valid = it < n;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           BsdfSample d;
           d.ior1 = iorCurrent; d.ior2 = iorOther; d.k1 = -worldRayDir;
           d.xi = rng1d_next4f(rng_state);                                              // chit:370
-          bsdf_sample(closure, mp, d, st);
+          bsdf_sample<MAXC>(closure, mp, d, st);
           eventType = (uint32_t) d.event_type;
           throughput *= d.bsdf_over_pdf;                                               // chit:386
           ray_dir = d.k2;                                                              // chit:388
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           if (neeValid) {
             BsdfEval e;
             e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = ls.dirToLight;
-            bsdf_evaluate(closure, mp, e, st);                                         // chit:425
+            bsdf_evaluate<MAXC>(closure, mp, e, st);                                         // chit:425
             neeValid = (e.pdf > 0.0f);
             if (neeValid) {
               const V2 diffuseSpecular = unpackHalf2x16(ls.diffuseSpecularPacked);
