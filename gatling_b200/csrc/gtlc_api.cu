@@ -400,6 +400,7 @@ template <int MODE> void launchTrace(const TraceParams& P, bool count, int block
     case 3: trace_kernel_v1<MODE, 3><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 4: trace_kernel_v1<MODE, 4><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 5: trace_kernel_v2<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    case 6: trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     default: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
   }
 }

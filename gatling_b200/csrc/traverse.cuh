@@ -556,4 +556,183 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v2(TraceParams P)
   }
 }
 
+// ---- variant 6: ray tiles staged through TMA into shared memory ------------------------------------
+// Every warp owns two 32-ray stages of shared memory (2 x 512 B of rayO + 2 x 512 B of rayD).  Lane 0 claims
+// the next 32 rays of the SoA queue with one atomic and issues two `cp.async.bulk` (TMA, 1-D) copies that
+// complete on an mbarrier; while the warp traverses, the following tile is already in flight, so a refill
+// reads its rays from shared memory instead of waiting for an HBM round trip with the whole warp stalled.
+// Traversal itself is variant 0.
+GTLC_D uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+GTLC_D void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "LAB_WAIT:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE;\n"
+    "bra LAB_WAIT;\n"
+    "DONE:\n"
+    "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P)
+{
+  __shared__ __align__(128) float4 sO[kTraceBlock / 32][2][32];
+  __shared__ __align__(128) float4 sD[kTraceBlock / 32][2][32];
+  __shared__ __align__(8) unsigned long long sBar[kTraceBlock / 32][2];
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n = *P.numRays;
+
+  // claims the next tile and starts its copy into `stage`; returns (base, count) to the whole warp
+  auto issue = [&](int stage, uint32_t& base, uint32_t& cnt) {
+    base = 0; cnt = 0;
+    if (lane == 0) {
+      base = atomicAdd(P.workCounter, 32u);
+      cnt = base < n ? min(32u, n - base) : 0u;
+      if (cnt) {
+        const uint32_t bar = smem_u32(&sBar[warp][stage]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(cnt * 32u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(&sO[warp][stage][0])), "l"(P.rayO + base), "r"(cnt * 16u), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(&sD[warp][stage][0])), "l"(P.rayD + base), "r"(cnt * 16u), "r"(bar) : "memory");
+      }
+    }
+    base = __shfl_sync(FULL, base, 0); cnt = __shfl_sync(FULL, cnt, 0);
+  };
+
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sBar[warp][0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sBar[warp][1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  // stage bookkeeping in scalar registers (selected with `cur`), all warp-uniform
+  uint32_t base0, cnt0, base1, cnt1, phase0 = 0u, phase1 = 0u;
+  issue(0, base0, cnt0);
+  issue(1, base1, cnt1);
+  int cur = 0; uint32_t cursor = 0;
+  if (cnt0) { mbar_wait(smem_u32(&sBar[warp][0]), phase0); phase0 ^= 1u; }
+  bool exhausted = cnt0 == 0u;
+
+  uint2 stack[kStackSize];
+  int sp = 0;
+  bool active = false;
+  uint32_t rayIdx = 0;
+  RaySetup r;
+  float bt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t bprim = 0xFFFFFFFFu, binst = 0xFFFFFFFFu;
+  float tmax = 0.0f;
+  uint2 G = make_uint2(0u, 0u);
+
+  while (true) {
+    if (!exhausted) {
+      const unsigned need = __ballot_sync(FULL, !active);
+      if (need) {
+        const uint32_t rank = (uint32_t) __popc(need & ((1u << lane) - 1u));
+        const uint32_t needCount = (uint32_t) __popc(need);
+        const uint32_t curBase = cur ? base1 : base0, curCnt = cur ? cnt1 : cnt0;
+        const uint32_t remaining = curCnt - cursor;
+        bool got = false; float4 ro, rd;
+        if (!active && rank < remaining) { ro = sO[warp][cur][cursor + rank]; rd = sD[warp][cur][cursor + rank]; rayIdx = curBase + cursor + rank; got = true; }
+        if (needCount >= remaining) {
+          // current stage used up: swap to the prefetched one and start prefetching into the freed stage
+          __syncwarp();
+          const int old = cur; cur ^= 1;
+          const uint32_t nxtBase = cur ? base1 : base0, nxtCnt = cur ? cnt1 : cnt0;
+          if (nxtCnt) {
+            if (cur) { mbar_wait(smem_u32(&sBar[warp][1]), phase1); phase1 ^= 1u; }
+            else { mbar_wait(smem_u32(&sBar[warp][0]), phase0); phase0 ^= 1u; }
+          }
+          const uint32_t over = rank - remaining;
+          if (!active && rank >= remaining && over < nxtCnt) { ro = sO[warp][cur][over]; rd = sD[warp][cur][over]; rayIdx = nxtBase + over; got = true; }
+          cursor = min(needCount - remaining, nxtCnt);
+          if (nxtCnt == 0u) exhausted = true;
+          __syncwarp();
+          if (old) issue(1, base1, cnt1); else issue(0, base0, cnt0);
+        } else {
+          cursor += needCount;
+        }
+        if (got) {
+          ray_setup(r, ro, rd);
+          tmax = rd.w;
+          bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
+          sp = 0;
+          active = tmax > r.tmin;
+          if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
+          G = make_uint2(0u, 0x80000000u);
+          if (!active && MODE != TRACE_SHADOW) { P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu; }
+        }
+      }
+    }
+    if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
+
+    while (true) {
+      if (active) {
+        uint2 T;
+        if (G.y & 0xFF000000u) {
+          const uint32_t hits_imask = G.y;
+          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
+          G.y &= ~(1u << bit);
+          if (G.y & 0xFF000000u) stack[sp++] = G;
+          const uint32_t slot = (bit - 24u) ^ r.octinv;
+          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
+          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
+          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
+          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+          T = make_uint2(n1.y, hm & 0x00FFFFFFu);
+        } else {
+          T = make_uint2(0u, 0u);
+        }
+        bool done = false;
+        while (T.y) {
+          const uint32_t j = (uint32_t) __ffs(T.y) - 1u;
+          T.y &= T.y - 1u;
+          const float4* tp = P.tris + (size_t) (T.x + j) * 3;
+          const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+          float t, u, v;
+          if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+            if (t > r.tmin && t < tmax) {
+              const uint32_t prim = f2u(a.w), inst = f2u(b.w);
+              if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
+              const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
+              if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
+            }
+          }
+        }
+        if (!done && !(G.y & 0xFF000000u)) {
+          if (sp == 0) done = true;
+          else G = stack[--sp];
+        }
+        if (done) {
+          const bool hit = bprim != 0xFFFFFFFFu;
+          if (MODE == TRACE_SHADOW) {
+            if (!hit) {
+              const float4 c = __ldg(&P.shContrib[rayIdx]);
+              const uint32_t target = f2u(c.w);
+              float4* dst = (target & 0x80000000u) ? (P.radSample + (target & 0x7FFFFFFFu)) : (P.radPath + target);
+              float4 cur4 = *dst;
+              cur4.x += c.x; cur4.y += c.y; cur4.z += c.z;
+              *dst = cur4;
+            }
+          } else {
+            P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
+            if (P.hitInst) P.hitInst[rayIdx] = binst;
+          }
+          active = false;
+        }
+      }
+      const unsigned idle = __ballot_sync(FULL, !active);
+      if (idle == FULL) break;
+      if (!exhausted && __popc(idle) >= P.refillThreshold) break;
+    }
+  }
+}
+
 } // namespace gtlc
