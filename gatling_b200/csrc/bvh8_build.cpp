@@ -29,7 +29,7 @@ struct Box {
   }
 };
 
-struct BinNode { Box box; uint32_t left, right, first, count; };
+struct BinNode { Box box; uint32_t left, right, first, count, total; };   // count > 0: binary leaf; total = triangles in the subtree
 
 constexpr int kBins = 16;
 // SAH parameters (overridable through GTLC_BVH_MAX_LEAF / GTLC_BVH_NODE_COST for tuning experiments)
@@ -58,7 +58,7 @@ struct Builder {
     BinNode& n = nodes[node];
     n.box = box;
     uint32_t count = end - begin;
-    auto makeLeaf = [&]() { n.first = begin; n.count = count; n.left = n.right = 0; };
+    auto makeLeaf = [&]() { n.first = begin; n.count = count; n.total = count; n.left = n.right = 0; };
     if (count == 1) { makeLeaf(); return; }
 
     // binned SAH over the three axes
@@ -87,13 +87,8 @@ struct Builder {
     }
     uint32_t mid;
     if (bestAxis < 0) {
-      if (count <= kMaxLeaf) { makeLeaf(); return; }
       mid = begin + count / 2;  // identical centroids: split by index
     } else {
-      float area = box.area();
-      float splitCost = kNodeCost * area + kTriCost * bestCost;
-      float leafCost = kTriCost * (float) count * area;
-      if (count <= kMaxLeaf && leafCost <= splitCost) { makeLeaf(); return; }
       float lo = cbox.lo[bestAxis], scale = (float) kBins / (cbox.hi[bestAxis] - cbox.lo[bestAxis]);
       auto it = std::partition(idx.begin() + begin, idx.begin() + end, [&](uint32_t t) {
         int b = (int) ((cen[(size_t) t * 3 + bestAxis] - lo) * scale);
@@ -104,7 +99,7 @@ struct Builder {
       if (mid == begin || mid == end) mid = begin + count / 2;
     }
     uint32_t l = nodeCount.fetch_add(2);
-    n.left = l; n.right = l + 1; n.count = 0; n.first = 0;
+    n.left = l; n.right = l + 1; n.count = 0; n.first = begin; n.total = count;
     if (count > 16384) {
 #pragma omp task default(shared)
       build(l, begin, mid);
@@ -153,37 +148,68 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
 #pragma omp single
   b.build(0, 0, N);
 
-  // ---- collapse into 8-wide nodes, breadth first -------------------------------------------
+  // ---- SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1), dynamic programme bottom-up over the
+  // binary tree: cost[n][i-1] = cheapest way to present subtree n to its parent as at most i children
+  // (i = 1..7), each child either a leaf of <= kMaxLeaf triangles or a wide node.  Children of a binary node
+  // always have larger indices than the node itself (allocation order), so a descending index sweep is bottom-up.
+  const std::vector<BinNode>& bn = b.nodes;
+  const uint32_t binCount = b.nodeCount.load();
+  struct Dp { float cost[7]; uint8_t split[7]; uint8_t rootSplit; uint8_t rootIsLeaf; };
+  std::vector<Dp> dp(binCount);
+  const float INF = 3.402823466e38f;
+  for (int64_t ni = (int64_t) binCount - 1; ni >= 0; ni--) {
+    const BinNode& n = bn[ni];
+    Dp& d = dp[ni];
+    const float area = n.box.area();
+    const float leafCost = (n.total <= kMaxLeaf) ? area * (float) n.total * kTriCost : INF;
+    if (n.count > 0) {                       // binary leaf (single triangle or coincident centroids)
+      for (int i = 0; i < 7; i++) { d.cost[i] = leafCost; d.split[i] = 0; }
+      d.rootSplit = 0; d.rootIsLeaf = 1;
+      continue;
+    }
+    const Dp& L = dp[n.left]; const Dp& R = dp[n.right];
+    // as one wide node: distribute 8 child slots between the two binary children
+    float best = INF; uint8_t bk = 1;
+    for (int k = 1; k <= 7; k++) { const float c = L.cost[k - 1] + R.cost[8 - k - 1]; if (c < best) { best = c; bk = (uint8_t) k; } }
+    const float internalCost = best + area * kNodeCost;
+    d.rootSplit = bk; d.rootIsLeaf = leafCost <= internalCost;
+    d.cost[0] = d.rootIsLeaf ? leafCost : internalCost; d.split[0] = 0;
+    for (int i = 2; i <= 7; i++) {            // as at most i children of the parent
+      float bd = INF; uint8_t bs = 0;
+      for (int k = 1; k < i; k++) { const float c = L.cost[k - 1] + R.cost[i - k - 1]; if (c < bd) { bd = c; bs = (uint8_t) k; } }
+      if (bd < d.cost[i - 2]) { d.cost[i - 1] = bd; d.split[i - 1] = bs; }
+      else { d.cost[i - 1] = d.cost[i - 2]; d.split[i - 1] = 0; }   // 0 = same as with one child fewer
+    }
+  }
+  // expands "subtree `node` as at most `i` children" into the child list
+  struct WideChildList { WideChild ch[8]; int n; };
+  auto gather = [&](auto&& self, uint32_t node, int i, WideChildList& out) -> void {
+    const Dp& d = dp[node];
+    while (i > 1 && d.split[i - 1] == 0) i--;
+    if (i == 1) { out.ch[out.n++] = { node, d.rootIsLeaf != 0 }; return; }
+    const int k = d.split[i - 1];
+    self(self, bn[node].left, k, out);
+    self(self, bn[node].right, i - k, out);
+  };
+
   struct Pending { uint32_t bin, wide, depth; };
   std::deque<Pending> queue;
   out.nodes.reserve(N / 4 + 16);
   out.tris.reserve((size_t) N * 12);
   out.nodes.emplace_back();
   queue.push_back({ 0u, 0u, 1u });
-  const std::vector<BinNode>& bn = b.nodes;
 
   while (!queue.empty()) {
     Pending cur = queue.front(); queue.pop_front();
     out.maxDepth = std::max(out.maxDepth, cur.depth);
     const BinNode& root = bn[cur.bin];
-    WideChild ch[8]; int n = 0;
-    if (root.count > 0) { ch[n++] = { cur.bin, true }; }
+    WideChildList list; list.n = 0;
+    if (dp[cur.bin].rootIsLeaf) { list.ch[list.n++] = { cur.bin, true }; }       // only possible for the global root
     else {
-      ch[n++] = { root.left, bn[root.left].count > 0 };
-      ch[n++] = { root.right, bn[root.right].count > 0 };
-      while (n < 8) {
-        int best = -1; float bestArea = -1.0f;
-        for (int i = 0; i < n; i++) {
-          if (ch[i].leaf) continue;
-          float a = bn[ch[i].bin].box.area();
-          if (a > bestArea) { bestArea = a; best = i; }
-        }
-        if (best < 0) break;
-        uint32_t l = bn[ch[best].bin].left, r = bn[ch[best].bin].right;
-        ch[best] = { l, bn[l].count > 0 };
-        ch[n++] = { r, bn[r].count > 0 };
-      }
+      gather(gather, root.left, dp[cur.bin].rootSplit, list);
+      gather(gather, root.right, 8 - dp[cur.bin].rootSplit, list);
     }
+    WideChild* ch = list.ch; const int n = list.n;
     // ---- octant-aware slot assignment (greedy): slot s sits towards the corner whose sign bits are s
     const Box& pb = root.box;
     float pc[3] = { 0.5f * (pb.lo[0] + pb.hi[0]), 0.5f * (pb.lo[1] + pb.hi[1]), 0.5f * (pb.lo[2] + pb.hi[2]) };
@@ -248,7 +274,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
         q[k][s] = (uint8_t) ql; q[3 + k][s] = (uint8_t) qh;
       }
       if (ch[i].leaf) {
-        uint32_t cnt = c.count;  // 1..3
+        uint32_t cnt = c.total;  // 1..kMaxLeaf triangles: the whole binary subtree becomes one leaf
         meta[s] = (uint8_t) ((((1u << cnt) - 1u) << 5) | triOffset);
         for (uint32_t t = 0; t < cnt; t++) {
           const BuildTri& tr = tris[b.idx[c.first + t]];

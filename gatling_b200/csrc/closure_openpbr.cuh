@@ -195,4 +195,18 @@ GTLC_D void openpbr_evaluate(const float* p, BsdfEval& d, const ShadingState& s)
 }
 
 
+// mdl_bsdf_scattering_auxiliary: albedo_diffuse + albedo_glossy at the viewing angle
+GTLC_D V3 openpbr_albedo(const float* p, V3 k1, const ShadingState& s)
+{
+  const OpbrLobes o = opbr_lobes(p);
+  const float nk1 = clampf(dot(k1, s.normal), 0.0f, 1.0f);
+  const float fs = fresnel_dielectric(nk1, o.eta);
+  const V3 substrate = o.Kd * (1.0f - o.trans_w) + o.trans_tint * o.trans_w;
+  const V3 dielectric = o.spec_color * fs + substrate * (1.0f - fs);
+  const V3 base = opbr_metal_fresnel(o, nk1) * o.metal + dielectric * (1.0f - o.metal);
+  if (!(o.coat_w > 0.0f)) return base;
+  const float fc = o.coat_w * fresnel_dielectric(nk1, o.coat_ior);
+  return v3(fc) + (base * o.coat_att) * (1.0f - fc);
+}
+
 } // namespace gtlc

@@ -283,6 +283,24 @@ GTLC_D void bsdf_sample(int closure, const float* p, BsdfSample& d, const Shadin
   if (MAXC == GTLC_CLOSURE_USD_PREVIEW_SURFACE || closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { ups_sample(p, d, s); return; }
   openpbr_sample(p, d, s);
 }
+GTLC_D V3 ups_albedo(const float* p, V3 k1, const ShadingState& s)
+{
+  UpsLobes u = ups_lobes(p);
+  const float nk1 = clampf(dot(k1, s.normal), 0.0f, 1.0f);
+  const V3 F = schlick(u.F0, u.F90, nk1);
+  const V3 inner = F + (v3(1.0f) - F) * u.Kd;
+  if (!(u.coat > 0.0f)) return inner;
+  const float fc = u.coat * fresnel_dielectric(nk1, 1.5f);
+  return v3(fc) + inner * (1.0f - fc);
+}
+// mdl_bsdf_scattering_auxiliary (rp_main.chit:264-280): albedo_diffuse + albedo_glossy
+template <int MAXC>
+GTLC_D V3 bsdf_albedo(int closure, const float* p, V3 k1, const ShadingState& s)
+{
+  if (MAXC == GTLC_CLOSURE_DIFFUSE || closure == GTLC_CLOSURE_DIFFUSE) return p3(p, GTLC_DIFFUSE_TINT_R);
+  if (MAXC == GTLC_CLOSURE_USD_PREVIEW_SURFACE || closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) return ups_albedo(p, k1, s);
+  return openpbr_albedo(p, k1, s);
+}
 template <int MAXC>
 GTLC_D void bsdf_evaluate(int closure, const float* p, BsdfEval& d, const ShadingState& s)
 {

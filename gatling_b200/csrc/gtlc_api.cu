@@ -105,11 +105,11 @@ struct Scene : Object {
   // flattened host copies
   Bvh8 bvh; bool bvhValid = false;
   std::vector<float> hFverts; std::vector<uint32_t> hFaces;
-  std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo;
+  std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo; std::vector<int2> hInstIds; std::vector<int32_t> hFaceIds;
   std::vector<Material*> flatMaterials;
   // device
   DeviceArray<uint4> dNodes; DeviceArray<float4> dTris; DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;
-  DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo;
+  DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo; DeviceArray<int2> dInstIds; DeviceArray<int32_t> dFaceIds;
   DeviceArray<float> dMatParams; DeviceArray<int32_t> dMatClosure; DeviceArray<uint32_t> dMatFlags;
   DeviceArray<float4> dSphere, dDistant, dRect, dDisk;
   DeviceArray<uint32_t> dPixelMap; uint32_t pixelMapW = 0, pixelMapH = 0, pixelMapRank = 0, pixelMapCount = 1, pixelMapTile = 0, localPixels = 0;
@@ -134,8 +134,9 @@ struct Global {
   Counters* counters = nullptr;
   uint32_t* visits = nullptr; size_t visitsCapacity = 0;
   uint32_t* perm = nullptr; uint32_t* sortHist = nullptr; int sortBlocks = 0;
+  AovSampleBuffers aovSamples; size_t aovCapacity = 0;
   std::vector<cudaEvent_t> events; size_t eventsUsed = 0;
-  Global() { memset(&tuning, 0, sizeof(tuning)); tuning.maxPathsPerWave = 1u << 24; tuning.sortByMaterial = -1; memset(&stats, 0, sizeof(stats)); memset(q, 0, sizeof(q)); }
+  Global() { memset(&aovSamples, 0, sizeof(aovSamples)); memset(&tuning, 0, sizeof(tuning)); tuning.maxPathsPerWave = 1u << 24; tuning.sortByMaterial = -1; memset(&stats, 0, sizeof(stats)); memset(q, 0, sizeof(q)); }
 };
 Global g;
 std::mutex g_destroyMutex;   // Gi.cpp:249
@@ -230,7 +231,7 @@ void invertAffine(const float* m, float* out)
 bool buildHostGeometry(Scene* s)
 {
   auto t0 = std::chrono::steady_clock::now();
-  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->flatMaterials.clear();
+  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->flatMaterials.clear();
   std::vector<BuildTri> tris;
   size_t totalTris = 0;
   for (Mesh* m : s->meshes) if (m->visible && m->material) totalTris += m->faces.size() * (m->instanceTransforms.size() / 12);
@@ -251,6 +252,7 @@ bool buildHostGeometry(Scene* s)
       s->hFverts.insert(s->hFverts.end(), f, f + 8);
     }
     for (const GtlcFace& f : m->faces) { s->hFaces.push_back(f.v_i[0]); s->hFaces.push_back(f.v_i[1]); s->hFaces.push_back(f.v_i[2]); }
+    for (uint32_t f = 0; f < m->faces.size(); f++) s->hFaceIds.push_back(m->faceIds.size() == m->faces.size() ? m->faceIds[f] : (int32_t) f);   // rp_main.chit:232-240
     const uint32_t flags = (m->flipFacing ? 1u : 0u) | (m->doubleSided ? 2u : 0u);   // Gi.cpp:1135-1143
     const size_t instCount = m->instanceTransforms.size() / 12;
     for (size_t k = 0; k < instCount; k++) {                            // Gi.cpp:1188-1202
@@ -261,6 +263,7 @@ bool buildHostGeometry(Scene* s)
       s->hO2W.insert(s->hO2W.end(), o2w, o2w + 12);
       s->hW2O.insert(s->hW2O.end(), w2o, w2o + 12);
       s->hInstInfo.push_back({ vertexBase, faceBase, flags, matIndex });
+      s->hInstIds.push_back(make_int2(m->id, k < m->instanceIds.size() ? m->instanceIds[k] : (int32_t) k));
       for (uint32_t f = 0; f < m->faces.size(); f++) {
         BuildTri t; t.prim = f; t.inst = inst;
         for (int c = 0; c < 3; c++) {
@@ -291,6 +294,8 @@ bool uploadGeometry(Scene* s)
   if (!s->dO2W.upload((const float4*) s->hO2W.data(), s->hO2W.size() / 4, st)) return false;
   if (!s->dW2O.upload((const float4*) s->hW2O.data(), s->hW2O.size() / 4, st)) return false;
   if (!s->dInstInfo.upload(s->hInstInfo.data(), s->hInstInfo.size(), st)) return false;
+  if (!s->dInstIds.upload(s->hInstIds.data(), s->hInstIds.size(), st)) return false;
+  if (!s->dFaceIds.upload(s->hFaceIds.data(), s->hFaceIds.size(), st)) return false;
   CUDA_OK(cudaStreamSynchronize(st));
   s->lastBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return true;
@@ -346,6 +351,16 @@ bool ensurePool(size_t capacity)
   CUDA_OK(cudaMalloc(&g.perm, capacity * 4));
   if (!g.sortHist) { g.sortBlocks = g.smCount * 4; CUDA_OK(cudaMalloc(&g.sortHist, (size_t) kSortBins * g.sortBlocks * 4)); }
   g.poolCapacity = capacity;
+  return true;
+}
+
+bool ensureAovSamples(size_t capacity)
+{
+  if (capacity <= g.aovCapacity) return true;
+  for (int k = 0; k < 6; k++) { cudaFree(g.aovSamples.a[k]); g.aovSamples.a[k] = nullptr; }
+  g.aovCapacity = 0;
+  for (int k = 0; k < 6; k++) CUDA_OK(cudaMalloc(&g.aovSamples.a[k], capacity * 16));
+  g.aovCapacity = capacity;
   return true;
 }
 
@@ -480,6 +495,8 @@ void gtlc_terminate(void)
   for (int k = 0; k < 2; k++) { cudaFree(g.q[k].rayO); cudaFree(g.q[k].rayD); cudaFree(g.q[k].thr); cudaFree(g.q[k].rad); cudaFree(g.q[k].slot); }
   memset(g.q, 0, sizeof(g.q));
   cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits); cudaFree(g.perm); cudaFree(g.sortHist); g.perm = nullptr; g.sortHist = nullptr;
+  for (int k = 0; k < 6; k++) { cudaFree(g.aovSamples.a[k]); g.aovSamples.a[k] = nullptr; }
+  g.aovCapacity = 0;
   g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.sampleRad = nullptr; g.accum = nullptr; g.counters = nullptr; g.visits = nullptr;
   g.poolCapacity = 0; g.accumCapacity = 0; g.visitsCapacity = 0;
   for (cudaEvent_t e : g.events) cudaEventDestroy(e);
@@ -499,7 +516,7 @@ void gtlc_scene_destroy(GtlcHandle h)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
-  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release();
+  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release();
   s->dMatParams.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
@@ -582,7 +599,7 @@ void gtlc_mesh_set_instance_ids(GtlcHandle h, uint32_t count, const int32_t* ids
   Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
   std::lock_guard<std::mutex> l(m->scene->mutex);
   m->instanceIds.assign(ids, ids + count);
-  m->scene->framebufferDirty = true;
+  m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
 }
 void gtlc_mesh_set_material(GtlcHandle h, GtlcHandle mat)
 {
@@ -882,7 +899,7 @@ int gtlc_render(const GtlcRenderParams* params)
     if (g.accumCapacity < localPixels) { cudaFree(g.accum); g.accum = nullptr; CUDA_OK(cudaMalloc(&g.accum, std::max<size_t>(localPixels, 1) * 16)); g.accumCapacity = localPixels; }
 
     DeviceScene ds; memset(&ds, 0, sizeof(ds));
-    ds.fverts = s->dFverts.ptr; ds.faces = s->dFaces.ptr; ds.instO2W = s->dO2W.ptr; ds.instW2O = s->dW2O.ptr; ds.instInfo = s->dInstInfo.ptr;
+    ds.fverts = s->dFverts.ptr; ds.faces = s->dFaces.ptr; ds.instO2W = s->dO2W.ptr; ds.instW2O = s->dW2O.ptr; ds.instInfo = s->dInstInfo.ptr; ds.instIds = s->dInstIds.ptr; ds.faceIds = s->dFaceIds.ptr;
     ds.matParams = s->dMatParams.ptr; ds.matClosure = s->dMatClosure.ptr; ds.matFlags = s->dMatFlags.ptr;
     ds.sphereLights = s->dSphere.ptr; ds.distantLights = s->dDistant.ptr; ds.rectLights = s->dRect.ptr; ds.diskLights = s->dDisk.ptr;
     if (dome) { ds.domeTexels = dome->dTexels; ds.domeW = dome->width; ds.domeH = dome->height; }
@@ -898,16 +915,22 @@ int gtlc_render(const GtlcRenderParams* params)
     cudaEventRecord(evStart, g.stream);
     // sharded render: pixels of other ranks are 0 so that one sum-reduce assembles the image
     if (colorDev && s->shardCount > 1 && s->sampleOffset == 0) CUDA_OK(cudaMemsetAsync(colorDev, 0, (size_t) W * H * 16, g.stream));
-    // other bound AOVs: cleared to their clear value (not rendered in this build)
+    // auxiliary AOVs (everything but Color): device targets + clear values for resolve_aov_kernel
+    AovTargets targets; memset(&targets, 0, sizeof(targets));
+    bool aovMode = false;
     for (uint32_t i = 0; i < params->aovBindingCount; i++) {
       const GtlcAovBinding& b = params->aovBindings[i];
-      if (b.aovId == GTLC_AOV_COLOR) continue;
+      if (b.aovId == GTLC_AOV_COLOR || b.aovId < 0 || b.aovId >= GTLC_AOV_COUNT) continue;
       RenderBuffer* rb = as<RenderBuffer>(b.renderBuffer, TAG_RB);
-      const size_t comp = rb->format == GTLC_FORMAT_FLOAT32_VEC4 ? 16 : 4;
-      uint8_t* hm = (uint8_t*) rb->hostMem;
-      for (size_t p = 0; p < (size_t) W * H; p++) memcpy(hm + p * comp, b.clearValue, comp);
-      CUDA_OK(cudaMemcpyAsync(rb->devMem, rb->hostMem, rb->size, cudaMemcpyHostToDevice, g.stream));
+      const bool isInt = b.aovId == GTLC_AOV_OBJECT_ID || b.aovId == GTLC_AOV_FACE_ID || b.aovId == GTLC_AOV_INSTANCE_ID;
+      const bool isScalar = b.aovId == GTLC_AOV_DEPTH;
+      const int32_t want = isInt ? GTLC_FORMAT_INT32 : (isScalar ? GTLC_FORMAT_FLOAT32 : GTLC_FORMAT_FLOAT32_VEC4);
+      if (rb->format != want) { setError("AOV %d needs render buffer format %d (got %d)", b.aovId, want, rb->format); return false; }
+      targets.buf[b.aovId] = rb->devMem;
+      memcpy(&targets.clear[b.aovId], b.clearValue, 16);
+      aovMode = true;
     }
+    if (aovMode && !ensureAovSamples(g.poolCapacity)) return false;
 
     const int gridElem = g.smCount * 8;
     const int traceBlocks = g.smCount * (g.tuning.reserved[1] > 0 ? g.tuning.reserved[1] : 8);
@@ -940,12 +963,14 @@ int gtlc_render(const GtlcRenderParams* params)
           }
           timed(K_SHADE, [&] {
             const uint32_t* permArg = sortByMaterial ? g.perm : nullptr;
-#define GTLC_LAUNCH_SHADE(MAXC, NEE) shade_kernel<MAXC, NEE><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.sampleRad, g.counters, inIdx)
+#define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) shade_kernel<MAXC, NEE, AOV><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.sampleRad, g.counters, inIdx, g.aovSamples)
+#define GTLC_LAUNCH_SHADE(MAXC, NEE) do { if (aovMode && bounce == 0) GTLC_LAUNCH_SHADE2(MAXC, NEE, true); else GTLC_LAUNCH_SHADE2(MAXC, NEE, false); } while (0)
             const bool nee = rs.nextEventEstimation != 0;
             if (maxClosure == GTLC_CLOSURE_DIFFUSE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, false); }
             else if (maxClosure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_USD_PREVIEW_SURFACE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_USD_PREVIEW_SURFACE, false); }
             else { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_OPENPBR, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_OPENPBR, false); }
 #undef GTLC_LAUNCH_SHADE
+#undef GTLC_LAUNCH_SHADE2
           });
           if (rs.nextEventEstimation) {
             prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;
@@ -958,6 +983,7 @@ int gtlc_render(const GtlcRenderParams* params)
         }
         const int lastWave = (sBase + samplesPerWave >= rs.spp) ? 1 : 0;
         timed(K_RESOLVE, [&] { resolve_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, g.accum, colorDev, lastWave); });
+        if (aovMode) timed(K_RESOLVE, [&] { resolve_aov_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, g.aovSamples, targets, sBase == 0 ? 1 : 0, lastWave); });
       }
     }
     cudaEventRecord(evEnd, g.stream);
@@ -965,7 +991,12 @@ int gtlc_render(const GtlcRenderParams* params)
     // readback of every bound AOV (Gi.cpp:2439-2489) + blocking wait (Gi.cpp:2492-2502)
     Counters c;
     CUDA_OK(cudaMemcpyAsync(&c, g.counters, sizeof(c), cudaMemcpyDeviceToHost, g.stream));
-    if (!g.tuning.skipReadback && colorRb) CUDA_OK(cudaMemcpyAsync(colorRb->hostMem, colorRb->devMem, colorRb->size, cudaMemcpyDeviceToHost, g.stream));
+    if (!g.tuning.skipReadback) {
+      for (uint32_t i = 0; i < params->aovBindingCount; i++) {
+        RenderBuffer* rb = as<RenderBuffer>(params->aovBindings[i].renderBuffer, TAG_RB);
+        CUDA_OK(cudaMemcpyAsync(rb->hostMem, rb->devMem, rb->size, cudaMemcpyDeviceToHost, g.stream));
+      }
+    }
     CUDA_OK(cudaStreamSynchronize(g.stream));
     float keepBuild = g.stats.msBvhBuild; uint32_t kn = g.stats.bvhNodeCount, kt = g.stats.bvhTriCount, kd = g.stats.bvhMaxDepth;
     memset(&g.stats, 0, sizeof(g.stats));

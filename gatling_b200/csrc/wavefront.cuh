@@ -57,6 +57,8 @@ struct DeviceScene {
   const float4* __restrict__ instO2W;    // 3 x float4 per instance (gl_ObjectToWorldEXT rows)
   const float4* __restrict__ instW2O;    // 3 x float4 per instance (gl_WorldToObjectEXT rows)
   const InstanceInfo* __restrict__ instInfo;
+  const int2* __restrict__ instIds;       // (objectId, instanceId) per instance (preamble.objectId, InstanceIds[], rp_main.chit:223,243)
+  const int32_t* __restrict__ faceIds;    // one per face of the global face array (rp_main.chit:232-240)
   const float* __restrict__ matParams;   // GTLC_MATERIAL_PARAM_COUNT floats per material
   const int32_t* __restrict__ matClosure;
   const uint32_t* __restrict__ matFlags;
@@ -76,6 +78,12 @@ struct WaveParams {
   uint32_t waveSampleBase;  // index of the wave's first sample within this giRender call (s in rgen:215)
   const uint32_t* __restrict__ pixelMap;  // local pixel -> global pixel index (NULL = identity)
 };
+
+// Per-sample capture of what the closest-hit shader writes into the auxiliary AOVs on the first bounce
+// (rp_main.chit:191-290); resolve_aov_kernel replays the megakernel's per-pixel write order from it.
+//   a[0] = (barycentrics.xyz, flags: bit0 hit, bit1 thinWalled, bit2 doubleSided)   a[1] = (texcoords.xyz, depth)
+//   a[2] = (tangent.xyz, objectId)   a[3] = (bitangent.xyz, faceId)   a[4] = (posNormal.xyz, instanceId)   a[5] = (albedo.xyz, -)
+struct AovSampleBuffers { float4* a[6]; };
 
 struct Counters {          // device-resident
   uint32_t numPaths[2];    // path-queue lengths (double buffered)
@@ -326,12 +334,12 @@ GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uin
 // ---- shade: rp_main.chit:132-493 + rp_main.miss:55-87 + rp_main.rgen:397-480 ----------------------
 // One thread per live path.  Survivors are compacted into `qout`, shadow rays appended to the shadow
 // queue, finished samples written to sampleRad[slot].
-template <int MAXC, bool NEE>
+template <int MAXC, bool NEE, bool AOV>
 __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
                                                     float4* shO, float4* shD, float4* shC, float4* sampleRad,
-                                                    Counters* ctr, int inIdx)
+                                                    Counters* ctr, int inIdx, AovSampleBuffers aov)
 {
   const unsigned FULL = 0xFFFFFFFFu;
   const uint32_t n = ctr->numPaths[inIdx];
@@ -368,6 +376,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         const V3 sampleDir = normalize(quatRotateDir(ubo.domeLightRotation, worldRayDir));   // miss:83
         const V3 rdn = sampleDomeLight(ubo, s, domeLightIndex, sampleDir) * ld3(ubo.domeLightEmissionMultiplier);  // miss:84
         radiance += throughput * rdn;                                                  // miss:86
+        if (AOV && bounce == 0) aov.a[0][slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));
       } else {
         // ---- rp_main.chit:132-493 ----
         const uint32_t prim = f2u(h.w);
@@ -390,6 +399,22 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         const float kUseMaterialIor = -1.0f;                                           // mdl_types.glsl:155
         const V3 iorCurrent = (isFrontFace || thinWalled) ? v3(1.0f) : v3(kUseMaterialIor);   // chit:188
         const V3 iorOther = (isFrontFace || thinWalled) ? v3(kUseMaterialIor) : v3(1.0f);     // chit:189
+        if (AOV && bounce == 0) {                                                      // chit:192-290
+          const V2 clipRange = unpackHalf2x16(ubo.clipRangePacked);                    // chit:227
+          const float logDepth = 2.0f * logf(h.x / clipRange.x) / logf(clipRange.y / clipRange.x) - 1.0f;   // chit:228
+          const int2 ids = s.instIds[inst];
+          const int32_t faceId = s.faceIds[in.faceBase + prim];
+          const V3 tanAov = (st.tangent_u + v3(1.0f)) * 0.5f, bitAov = (st.tangent_v + v3(1.0f)) * 0.5f;   // chit:208,211
+          const V3 posNormal = (normal + v3(1.0f)) * 0.5f;                             // chit:252
+          const V3 albedo = bsdf_albedo<MAXC>(closure, mp, -worldRayDir, st);         // chit:264-280
+          const uint32_t fl = 1u | (thinWalled ? 2u : 0u) | (isDoubleSided ? 4u : 0u);
+          aov.a[0][slot] = make_float4((1.0f - h.y) - h.z, h.y, h.z, u2f(fl));         // chit:214
+          aov.a[1][slot] = make_float4(st.u, st.v, 0.0f, logDepth);                    // chit:217
+          aov.a[2][slot] = make_float4(tanAov.x, tanAov.y, tanAov.z, u2f((uint32_t) ids.x));
+          aov.a[3][slot] = make_float4(bitAov.x, bitAov.y, bitAov.z, u2f((uint32_t) faceId));
+          aov.a[4][slot] = make_float4(posNormal.x, posNormal.y, posNormal.z, u2f((uint32_t) ids.y));
+          aov.a[5][slot] = make_float4(albedo.x, albedo.y, albedo.z, 0.0f);
+        }
         if (mflags & kMatFlagEmissive) {                                               // chit:293-343
           if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
           float edfPdf = 0.0f;
@@ -490,7 +515,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         qout.rad[outPos] = make_float4(radiance.x, radiance.y, radiance.z, u2f(rng_state));
         qout.slot[outPos] = slot;
       } else {
-        sampleRad[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+        sampleRad[slot] = make_float4(radiance.x, radiance.y, radiance.z, u2f(bitfield & kPayloadBouncesMask));   // .w: bounces (rgen:483-486)
       }
       if (wantShadow) {
         const float lightDist = length(neeToLight);
@@ -522,11 +547,96 @@ __global__ void __launch_bounds__(256) resolve_kernel(UniformData ubo, WaveParam
       pixel_color += sample_color * invSpp;                                            // :498
     }
     if (!lastWave) { accum[lp] = make_float4(pixel_color.x, pixel_color.y, pixel_color.z, 0.0f); continue; }
+    if (!colorAov) continue;                                                           // colour AOV not bound (AOV_MASK & AOV_BIT_COLOR == 0)
     const uint32_t pixelIndex = wp.pixelMap ? wp.pixelMap[lp] : lp;
     V3 prevColor = pixel_color;                                                        // :507
     if ((ubo.flags & FLAG_PROGRESSIVE) && ubo.sampleOffset > 0) { const float4 p4 = colorAov[pixelIndex]; prevColor = v3(p4.x, p4.y, p4.z); }  // :508-513
     const V3 o = (prevColor * (float) ubo.sampleOffset + pixel_color * (float) ubo.spp) * ubo.invTotalSampleCount;   // :514
     colorAov[pixelIndex] = make_float4(o.x, o.y, o.z, 1.0f);
+  }
+}
+
+// colormap.glsl:42-53
+GTLC_D V3 colormap_inferno(float t)
+{
+  const V3 c0 = v3(0.0002189403691192265f, 0.001651004631001012f, -0.01948089843709184f);
+  const V3 c1 = v3(0.1065134194856116f, 0.5639564367884091f, 3.932712388889277f);
+  const V3 c2 = v3(11.60249308247187f, -3.972853965665698f, -15.9423941062914f);
+  const V3 c3 = v3(-41.70399613139459f, 17.43639888205313f, 44.35414519872813f);
+  const V3 c4 = v3(77.162935699427f, -33.40235894210092f, -81.80730925738993f);
+  const V3 c5 = v3(-71.31942824499214f, 32.62606426397723f, 73.20951985803202f);
+  const V3 c6 = v3(25.13112622477341f, -12.24266895238567f, -23.07032500287172f);
+  return c0 + (c1 + (c2 + (c3 + (c4 + (c5 + c6 * t) * t) * t) * t) * t) * t;
+}
+
+// Destination render buffers of the auxiliary AOVs (device pointers, NULL = not bound) and their clear values.
+struct AovTargets { void* buf[GTLC_AOV_COUNT]; float4 clear[GTLC_AOV_COUNT]; };
+
+// ---- auxiliary AOV resolve: replays, per pixel and in sample order, the writes the megakernel performs:
+// clearAovs (rgen:132-183, only in the first wave of a giRender call), first-bounce writes of every sample
+// (chit:191-290; the last sample that hit wins, Normal/Albedo follow the progressive recurrence), Bounces after
+// every sample (rgen:483-486), and the final re-normalisation of the normal (rgen:517-520, last wave only).
+__global__ void __launch_bounds__(256) resolve_aov_kernel(UniformData ubo, WaveParams wp, const float4* __restrict__ sampleRad,
+                                                          AovSampleBuffers smp, AovTargets tg, int firstWave, int lastWave)
+{
+  uint32_t maxBounces = ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > kPayloadBouncesMask) maxBounces = kPayloadBouncesMask;
+  const bool progressive = (ubo.flags & FLAG_PROGRESSIVE) && ubo.sampleOffset > 0;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < wp.wavePixels; q += gridDim.x * blockDim.x) {
+    const uint32_t lp = wp.wavePixelBase + q;
+    const uint32_t pix = wp.pixelMap ? wp.pixelMap[lp] : lp;
+    float4* const* vb = (float4* const*) tg.buf;
+    if (firstWave) {
+      const int lastWins[10] = { GTLC_AOV_BARYCENTRICS, GTLC_AOV_TEXCOORDS, GTLC_AOV_OPACITY, GTLC_AOV_TANGENTS, GTLC_AOV_BITANGENTS, GTLC_AOV_THIN_WALLED,
+                                 GTLC_AOV_DOUBLE_SIDED, GTLC_AOV_BOUNCES, GTLC_AOV_NEE, GTLC_AOV_CLOCK_CYCLES };
+#pragma unroll
+      for (int k = 0; k < 10; k++) if (tg.buf[lastWins[k]]) vb[lastWins[k]][pix] = tg.clear[lastWins[k]];
+      if (tg.buf[GTLC_AOV_OBJECT_ID]) ((int32_t*) tg.buf[GTLC_AOV_OBJECT_ID])[pix] = (int32_t) f2u(tg.clear[GTLC_AOV_OBJECT_ID].x);
+      if (tg.buf[GTLC_AOV_FACE_ID]) ((int32_t*) tg.buf[GTLC_AOV_FACE_ID])[pix] = (int32_t) f2u(tg.clear[GTLC_AOV_FACE_ID].x);
+      if (tg.buf[GTLC_AOV_INSTANCE_ID]) ((int32_t*) tg.buf[GTLC_AOV_INSTANCE_ID])[pix] = (int32_t) f2u(tg.clear[GTLC_AOV_INSTANCE_ID].x);
+      if (tg.buf[GTLC_AOV_DEPTH]) ((float*) tg.buf[GTLC_AOV_DEPTH])[pix] = tg.clear[GTLC_AOV_DEPTH].x;
+      if (ubo.sampleOffset == 0) {
+        if (tg.buf[GTLC_AOV_NORMAL]) vb[GTLC_AOV_NORMAL][pix] = tg.clear[GTLC_AOV_NORMAL];
+        if (tg.buf[GTLC_AOV_ALBEDO]) vb[GTLC_AOV_ALBEDO][pix] = tg.clear[GTLC_AOV_ALBEDO];
+      }
+    }
+    for (uint32_t j = 0; j < wp.waveSamples; j++) {
+      const size_t slot = (size_t) j * wp.wavePixels + q;
+      const float4 a0 = smp.a[0][slot];
+      const uint32_t fl = f2u(a0.w);
+      if (fl & 1u) {
+        const float4 a1 = smp.a[1][slot], a2 = smp.a[2][slot], a3 = smp.a[3][slot], a4 = smp.a[4][slot], a5 = smp.a[5][slot];
+        auto put3 = [&](int id, float x, float y, float z) { if (tg.buf[id]) { float4 c = vb[id][pix]; c.x = x; c.y = y; c.z = z; vb[id][pix] = c; } };
+        put3(GTLC_AOV_OPACITY, 1.0f, 0.0f, 0.0f);                                     // chit:202
+        put3(GTLC_AOV_TANGENTS, a2.x, a2.y, a2.z); put3(GTLC_AOV_BITANGENTS, a3.x, a3.y, a3.z);
+        put3(GTLC_AOV_BARYCENTRICS, a0.x, a0.y, a0.z); put3(GTLC_AOV_TEXCOORDS, a1.x, a1.y, a1.z);
+        if (fl & 2u) put3(GTLC_AOV_THIN_WALLED, 1.0f, 0.0f, 0.0f); else put3(GTLC_AOV_THIN_WALLED, 0.0f, 1.0f, 0.0f);     // chit:220
+        if (fl & 4u) put3(GTLC_AOV_DOUBLE_SIDED, 0.0f, 1.0f, 0.0f); else put3(GTLC_AOV_DOUBLE_SIDED, 1.0f, 0.0f, 0.0f);   // chit:247
+        if (tg.buf[GTLC_AOV_OBJECT_ID]) ((int32_t*) tg.buf[GTLC_AOV_OBJECT_ID])[pix] = (int32_t) f2u(a2.w);
+        if (tg.buf[GTLC_AOV_FACE_ID]) ((int32_t*) tg.buf[GTLC_AOV_FACE_ID])[pix] = (int32_t) f2u(a3.w);
+        if (tg.buf[GTLC_AOV_INSTANCE_ID]) ((int32_t*) tg.buf[GTLC_AOV_INSTANCE_ID])[pix] = (int32_t) f2u(a4.w);
+        if (tg.buf[GTLC_AOV_DEPTH]) ((float*) tg.buf[GTLC_AOV_DEPTH])[pix] = a1.w;
+        auto accumulate = [&](int id, V3 cur) {                                        // chit:251-261, 263-289
+          if (!tg.buf[id]) return;
+          float4 c = vb[id][pix];
+          V3 prev = cur;
+          if (progressive) prev = v3(c.x, c.y, c.z);
+          const V3 o = (prev * (float) ubo.sampleOffset + cur * (float) ubo.spp) * ubo.invTotalSampleCount;
+          c.x = o.x; c.y = o.y; c.z = o.z; vb[id][pix] = c;
+        };
+        accumulate(GTLC_AOV_NORMAL, v3(a4.x, a4.y, a4.z));
+        accumulate(GTLC_AOV_ALBEDO, v3(a5.x, a5.y, a5.z));
+      }
+      if (tg.buf[GTLC_AOV_BOUNCES]) {                                                  // rgen:483-486
+        const V3 cm = colormap_inferno((float) f2u(sampleRad[slot].w) / (float) maxBounces);
+        float4 c = vb[GTLC_AOV_BOUNCES][pix]; c.x = cm.x; c.y = cm.y; c.z = cm.z; vb[GTLC_AOV_BOUNCES][pix] = c;
+      }
+    }
+    if (lastWave && tg.buf[GTLC_AOV_NORMAL]) {                                         // rgen:517-520
+      float4 c = vb[GTLC_AOV_NORMAL][pix];
+      const V3 n = v3(c.x, c.y, c.z) * 2.0f - v3(1.0f);
+      const V3 r = (normalize(n) + v3(1.0f)) * 0.5f;
+      c.x = r.x; c.y = r.y; c.z = r.z; vb[GTLC_AOV_NORMAL][pix] = c;
+    }
   }
 }
 

@@ -359,11 +359,42 @@ class BuiltScene:
             raise RuntimeError("giRender failed: " + giLastError())
         return self.color.mem()
 
+    def render_aovs(self, aov_ids, clear_values=None, spp=None, settings=None):
+        """giRender with several AOV bindings.  Returns {GiAovId: ndarray} (Color: float32[h,w,4]; vec3 AOVs: float32[h,w,4];
+        Depth: float32[h,w,1]; ObjectId/FaceId/InstanceId: int32[h,w,1]).  Buffers persist across calls (progressive refinement)."""
+        d = self.desc
+        if not hasattr(self, "aov_buffers"):
+            self.aov_buffers = {}
+        bindings = []
+        for aov in aov_ids:
+            aov = GiAovId(aov)
+            fmt = (GiRenderBufferFormat.Int32 if aov in (GiAovId.ObjectId, GiAovId.FaceId, GiAovId.InstanceId)
+                   else GiRenderBufferFormat.Float32 if aov == GiAovId.Depth else GiRenderBufferFormat.Float32Vec4)
+            if aov not in self.aov_buffers:
+                rb = giCreateRenderBuffer(d.width, d.height, fmt)
+                if rb is None:
+                    raise RuntimeError("giCreateRenderBuffer failed: " + giLastError())
+                self.aov_buffers[aov] = rb
+            clear = (clear_values or {}).get(aov, d.clear_color if aov == GiAovId.Color else (0.0, 0.0, 0.0, 0.0))
+            if fmt == GiRenderBufferFormat.Int32 and not isinstance(clear, (bytes, bytearray)):
+                clear = np.asarray(clear, np.int32).tobytes()
+            bindings.append((aov, clear, self.aov_buffers[aov]))
+        st = settings or d.settings
+        if spp is not None:
+            import dataclasses
+            st = dataclasses.replace(st, spp=spp)
+        status = giRender(self.scene, d.camera, st, bindings, self.dome)
+        if status != GiStatus.Ok:
+            raise RuntimeError("giRender failed: " + giLastError())
+        return {aov: self.aov_buffers[aov].mem().copy() for aov, _, _ in bindings}
+
     def close(self):
         if self.scene is None:
             return
         if self.color is not None:
             giDestroyRenderBuffer(self.color)
+        for rb in getattr(self, "aov_buffers", {}).values():
+            giDestroyRenderBuffer(rb)
         for h in self.meshes:
             giDestroyMesh(h)
         for kind, h in self.lights:

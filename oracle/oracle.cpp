@@ -68,7 +68,29 @@ struct Flags { // compile-time #defines of the reference, GlslShaderGen.cpp:57-7
   bool jittered, fis, dof, nee, clipping, progressive, domeCameraVisible;
 };
 
-struct RenderCtx { const Scene* s; Ubo ubo; Flags fl; V4 background; };
+struct RenderCtx { const Scene* s; Ubo ubo; Flags fl; V4 background; uint32_t aovMask; };
+
+// What the closest-hit shader writes into the auxiliary AOVs on the first bounce (rp_main.chit:191-290),
+// captured per sample so that the per-pixel write order of the megakernel can be replayed.
+struct AovSample {
+  bool hit; uint32_t bounces;
+  V3 bary, texcoords, tangent, bitangent, posNormal, albedo;
+  bool thinWalled, doubleSided;
+  int32_t objectId, faceId, instanceId; float depth;
+};
+
+// colormap.glsl:42-53
+static inline V3 colormap_inferno(float t)
+{
+  const V3 c0 = v3(0.0002189403691192265f, 0.001651004631001012f, -0.01948089843709184f);
+  const V3 c1 = v3(0.1065134194856116f, 0.5639564367884091f, 3.932712388889277f);
+  const V3 c2 = v3(11.60249308247187f, -3.972853965665698f, -15.9423941062914f);
+  const V3 c3 = v3(-41.70399613139459f, 17.43639888205313f, 44.35414519872813f);
+  const V3 c4 = v3(77.162935699427f, -33.40235894210092f, -81.80730925738993f);
+  const V3 c5 = v3(-71.31942824499214f, 32.62606426397723f, 73.20951985803202f);
+  const V3 c6 = v3(25.13112622477341f, -12.24266895238567f, -23.07032500287172f);
+  return c0 + (c1 + (c2 + (c3 + (c4 + (c5 + c6 * t) * t) * t) * t) * t) * t;
+}
 
 // rp_main.rgen:118-130
 static inline V2 fisGauss(V2 xi)
@@ -267,7 +289,7 @@ static inline void sampleLight(const RenderCtx& c, V4 k4, V3 surfacePos, V3& dir
 }
 
 // rp_main.chit:132-493 (MEDIUM_STACK_SIZE == 0; AOV section :191-290 handled by the caller for Color only)
-static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, const Hit& hit, V3 worldRayDir)
+static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, const Hit& hit, V3 worldRayDir, AovSample* aov)
 {
   const Scene& s = *c.s;
   const InstanceDesc& in = s.instances[hit.inst];
@@ -294,6 +316,23 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
   const float USE_MATERIAL_IOR = -1.0f;
   V3 iorCurrent = (isFrontFace || thinWalled) ? v3(1.0f) : v3(USE_MATERIAL_IOR);
   V3 iorOther = (isFrontFace || thinWalled) ? v3(USE_MATERIAL_IOR) : v3(1.0f);
+
+  if (aov && (p.bitfield & PAYLOAD_BOUNCES_MASK) == 0) {                  // :192-290 auxiliary AOVs on the first bounce
+    aov->hit = true;
+    aov->tangent = (st.tangent_u + v3(1.0f)) * 0.5f;                      // :208
+    aov->bitangent = (st.tangent_v + v3(1.0f)) * 0.5f;                    // :211
+    aov->bary = v3((1.0f - hit.u) - hit.v, hit.u, hit.v);                 // :214
+    aov->texcoords = st.text_coords;                                      // :217
+    aov->thinWalled = thinWalled;                                         // :220
+    aov->objectId = in.objectId;                                          // :223-224
+    V2 clipRange = unpackHalf2x16(c.ubo.clipRangePacked);                 // :227
+    aov->depth = 2.0f * logf(hit.t / clipRange.x) / logf(clipRange.y / clipRange.x) - 1.0f;   // :228
+    aov->faceId = s.faceIds.empty() ? (int32_t) hit.prim : s.faceIds[in.faceBase + hit.prim];   // :232-240
+    aov->instanceId = in.instanceId;                                      // :243
+    aov->doubleSided = isDoubleSided;                                     // :247
+    aov->posNormal = (normal + v3(1.0f)) * 0.5f;                          // :252
+    aov->albedo = bsdf_albedo(mat, -worldRayDir, st);                     // :264-280 (front-face BSDF; no backface BSDFs exist here)
+  }
 
   if (mat_is_emissive(mat)) {                                             // :293-343
     if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
@@ -361,8 +400,9 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
 struct RayCounters { uint64_t closest, shadow; };
 
 // rp_main.rgen:215-499: one sample of one pixel; returns the clamped sample colour.
-static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint32_t pixelIndex, uint32_t s, RayCounters& rc)
+static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint32_t pixelIndex, uint32_t s, RayCounters& rc, AovSample* aov = nullptr)
 {
+  if (aov) { aov->hit = false; aov->bounces = 0; }
   const Ubo& ubo = c.ubo;
   uint32_t sampleIndex = ubo.sampleOffset + s;                            // :217
   uint32_t rng_state = rng1d_init(pixelIndex, sampleIndex);               // :223
@@ -392,7 +432,7 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
     Hit hit;
     V3 d = p.ray_dir, o = p.ray_origin;
     rc.closest++;
-    if (scene_trace(*c.s, o, d, tMin, tMax, false, hit)) closest_hit_shader(c, p, hit, d); // :381-393
+    if (scene_trace(*c.s, o, d, tMin, tMax, false, hit)) closest_hit_shader(c, p, hit, d, aov); // :381-393
     else miss_shader(c, p, d);
 
     if (c.fl.nee) {                                                       // :397-438
@@ -418,6 +458,7 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
     }
     p.bitfield++;                                                         // :480
   }
+  if (aov) aov->bounces = (p.bitfield & PAYLOAD_BOUNCES_MASK);            // :483-486
   V3 radiance = p.radiance;                                               // :489-496
   float maxValue = fmaxf(radiance.x, fmaxf(radiance.y, radiance.z));
   if (maxValue > ubo.maxSampleValue) radiance *= (ubo.maxSampleValue / maxValue);
@@ -440,6 +481,7 @@ struct OrcSceneDesc {
   const DiskLight* diskLights; uint32_t diskLightCount;
   const float* domeTexels; uint32_t domeW, domeH;
   float domeRotation[4]; float domeEmission[3]; uint32_t pad;
+  const int32_t* faceIds;   // optional: one per face of the global face array (GiMeshDesc.faceIds)
 };
 
 struct OrcRenderDesc {
@@ -471,6 +513,7 @@ void* orc_scene_create(const OrcSceneDesc* d)
     s->domeW = d->domeW; s->domeH = d->domeH;
     memcpy(s->domeRotation, d->domeRotation, 16); memcpy(s->domeEmission, d->domeEmission, 12);
   }
+  if (d->faceIds) s->faceIds.assign(d->faceIds, d->faceIds + d->faceCount);
   scene_build(*s);
   return s;
 }
@@ -543,6 +586,92 @@ double orc_render(void* h, const OrcRenderDesc* r, float* rgba, uint64_t* rayCou
       if (c.fl.progressive && c.ubo.sampleOffset > 0) prevColor = v3(out[0], out[1], out[2]);
       V3 o = (prevColor * (float) c.ubo.sampleOffset + pixel_color * (float) c.ubo.spp) * c.ubo.invTotalSampleCount;
       out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = 1.0f;
+    }
+    nClosest += rc.closest; nShadow += rc.shadow;
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  if (rayCounts) { rayCounts[0] = nClosest; rayCounts[1] = nShadow; }
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Same as orc_render, additionally producing the auxiliary AOVs with the write order of the megakernel:
+// clearAovs (rp_main.rgen:132-183), per-sample first-bounce writes of the closest-hit shader in sample order
+// (rp_main.chit:191-290: the last sample that hit geometry wins for the non-accumulating AOVs, Normal/Albedo
+// follow the progressive recurrence), Bounces after every sample (rgen:483-486), final normal re-normalisation
+// (rgen:517-520).  NEE and ClockCycles debug AOVs are not produced (left at their clear value).
+// buffers[id]: Float32Vec4 (vec3 AOVs, w = clear value's w), Float32 (Depth), Int32 (ObjectId/FaceId/InstanceId).
+struct OrcAovDesc { uint32_t mask; uint32_t pad; void* buffers[GTLC_AOV_COUNT]; uint8_t clear[GTLC_AOV_COUNT][16]; };
+
+double orc_render_aovs(void* h, const OrcRenderDesc* r, float* rgba, uint64_t* rayCounts, const OrcAovDesc* a)
+{
+  const Scene* s = (const Scene*) h;
+  RenderCtx c; fill_ctx(c, s, r);
+  c.aovMask = a->mask;
+  const uint32_t W = r->width, H = r->height, spp = r->settings.spp;
+  const float invSpp = 1.0f / (float) spp;
+  uint32_t maxBounces = c.ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > PAYLOAD_BOUNCES_MASK) maxBounces = PAYLOAD_BOUNCES_MASK;
+  uint64_t nClosest = 0, nShadow = 0;
+  auto has = [&](int id) { return (a->mask & (1u << id)) != 0 && a->buffers[id] != nullptr; };
+  auto clearF = [&](int id, int k) { float v; memcpy(&v, &a->clear[id][4 * k], 4); return v; };
+  auto clearI = [&](int id) { int32_t v; memcpy(&v, &a->clear[id][0], 4); return v; };
+  auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nClosest, nShadow)
+  for (int y = 0; y < (int) H; y++) {
+    RayCounters rc = { 0, 0 };
+    for (uint32_t x = 0; x < W; x++) {
+      const uint32_t pixelIndex = x + (uint32_t) y * W;
+      float* out = &rgba[(size_t) pixelIndex * 4];
+      auto v3buf = [&](int id) { return &((float*) a->buffers[id])[(size_t) pixelIndex * 4]; };
+      // clearAovs
+      const int lastWins[] = { GTLC_AOV_BARYCENTRICS, GTLC_AOV_TEXCOORDS, GTLC_AOV_OPACITY, GTLC_AOV_TANGENTS, GTLC_AOV_BITANGENTS, GTLC_AOV_THIN_WALLED, GTLC_AOV_DOUBLE_SIDED, GTLC_AOV_BOUNCES, GTLC_AOV_NEE, GTLC_AOV_CLOCK_CYCLES };
+      for (int id : lastWins) if (has(id)) { float* b = v3buf(id); for (int k = 0; k < 4; k++) b[k] = clearF(id, k); }
+      if (has(GTLC_AOV_OBJECT_ID)) ((int32_t*) a->buffers[GTLC_AOV_OBJECT_ID])[pixelIndex] = clearI(GTLC_AOV_OBJECT_ID);
+      if (has(GTLC_AOV_FACE_ID)) ((int32_t*) a->buffers[GTLC_AOV_FACE_ID])[pixelIndex] = clearI(GTLC_AOV_FACE_ID);
+      if (has(GTLC_AOV_INSTANCE_ID)) ((int32_t*) a->buffers[GTLC_AOV_INSTANCE_ID])[pixelIndex] = clearI(GTLC_AOV_INSTANCE_ID);
+      if (has(GTLC_AOV_DEPTH)) ((float*) a->buffers[GTLC_AOV_DEPTH])[pixelIndex] = clearF(GTLC_AOV_DEPTH, 0);
+      if (c.ubo.sampleOffset == 0) {
+        if (has(GTLC_AOV_NORMAL)) { float* b = v3buf(GTLC_AOV_NORMAL); for (int k = 0; k < 4; k++) b[k] = clearF(GTLC_AOV_NORMAL, k); }
+        if (has(GTLC_AOV_ALBEDO)) { float* b = v3buf(GTLC_AOV_ALBEDO); for (int k = 0; k < 4; k++) b[k] = clearF(GTLC_AOV_ALBEDO, k); }
+      }
+      V3 pixel_color = v3(0.0f);
+      for (uint32_t sIdx = 0; sIdx < spp; sIdx++) {
+        AovSample as;
+        V3 sample_color = trace_sample(c, x, (uint32_t) y, pixelIndex, sIdx, rc, &as);
+        pixel_color += sample_color * invSpp;
+        if (as.hit) {
+          auto put3 = [&](int id, V3 v) { if (has(id)) { float* b = v3buf(id); b[0] = v.x; b[1] = v.y; b[2] = v.z; } };
+          put3(GTLC_AOV_OPACITY, v3(1.0f, 0.0f, 0.0f));                                 // chit:202
+          put3(GTLC_AOV_TANGENTS, as.tangent); put3(GTLC_AOV_BITANGENTS, as.bitangent);
+          put3(GTLC_AOV_BARYCENTRICS, as.bary); put3(GTLC_AOV_TEXCOORDS, as.texcoords);
+          put3(GTLC_AOV_THIN_WALLED, as.thinWalled ? v3(1.0f, 0.0f, 0.0f) : v3(0.0f, 1.0f, 0.0f));   // chit:220
+          put3(GTLC_AOV_DOUBLE_SIDED, as.doubleSided ? v3(0.0f, 1.0f, 0.0f) : v3(1.0f, 0.0f, 0.0f)); // chit:247
+          if (has(GTLC_AOV_OBJECT_ID)) ((int32_t*) a->buffers[GTLC_AOV_OBJECT_ID])[pixelIndex] = as.objectId;
+          if (has(GTLC_AOV_FACE_ID)) ((int32_t*) a->buffers[GTLC_AOV_FACE_ID])[pixelIndex] = as.faceId;
+          if (has(GTLC_AOV_INSTANCE_ID)) ((int32_t*) a->buffers[GTLC_AOV_INSTANCE_ID])[pixelIndex] = as.instanceId;
+          if (has(GTLC_AOV_DEPTH)) ((float*) a->buffers[GTLC_AOV_DEPTH])[pixelIndex] = as.depth;
+          auto accumulate = [&](int id, V3 cur) {                                        // chit:251-261, 263-289
+            if (!has(id)) return;
+            float* b = v3buf(id);
+            V3 prev = cur;
+            if (c.fl.progressive && c.ubo.sampleOffset > 0) prev = v3(b[0], b[1], b[2]);
+            V3 o = (prev * (float) c.ubo.sampleOffset + cur * (float) c.ubo.spp) * c.ubo.invTotalSampleCount;
+            b[0] = o.x; b[1] = o.y; b[2] = o.z;
+          };
+          accumulate(GTLC_AOV_NORMAL, as.posNormal);
+          accumulate(GTLC_AOV_ALBEDO, as.albedo);
+        }
+        if (has(GTLC_AOV_BOUNCES)) { V3 cm = colormap_inferno((float) as.bounces / (float) maxBounces); float* b = v3buf(GTLC_AOV_BOUNCES); b[0] = cm.x; b[1] = cm.y; b[2] = cm.z; }   // rgen:483-486
+      }
+      V3 prevColor = pixel_color;
+      if (c.fl.progressive && c.ubo.sampleOffset > 0) prevColor = v3(out[0], out[1], out[2]);
+      V3 o = (prevColor * (float) c.ubo.sampleOffset + pixel_color * (float) c.ubo.spp) * c.ubo.invTotalSampleCount;
+      out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = 1.0f;
+      if (has(GTLC_AOV_NORMAL)) {                                                        // rgen:517-520
+        float* b = v3buf(GTLC_AOV_NORMAL);
+        V3 n = v3(b[0], b[1], b[2]) * 2.0f - v3(1.0f);
+        V3 q = (normalize(n) + v3(1.0f)) * 0.5f;
+        b[0] = q.x; b[1] = q.y; b[2] = q.z;
+      }
     }
     nClosest += rc.closest; nShadow += rc.shadow;
   }

@@ -67,7 +67,11 @@ class SceneDescC(C.Structure):
                 ("rectLights", C.c_void_p), ("rectLightCount", C.c_uint32),
                 ("diskLights", C.c_void_p), ("diskLightCount", C.c_uint32),
                 ("domeTexels", C.c_void_p), ("domeW", C.c_uint32), ("domeH", C.c_uint32),
-                ("domeRotation", C.c_float * 4), ("domeEmission", C.c_float * 3), ("pad", C.c_uint32)]
+                ("domeRotation", C.c_float * 4), ("domeEmission", C.c_float * 3), ("pad", C.c_uint32), ("faceIds", C.c_void_p)]
+
+
+class AovDescC(C.Structure):
+    _fields_ = [("mask", C.c_uint32), ("pad", C.c_uint32), ("buffers", C.c_void_p * 17), ("clear", (C.c_uint8 * 16) * 17)]
 
 
 class RenderDescC(C.Structure):
@@ -88,6 +92,8 @@ def lib():
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_render.restype = C.c_double
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(RenderDescC), C.c_void_p, C.c_void_p]
+        L.orc_render_aovs.restype = C.c_double
+        L.orc_render_aovs.argtypes = [C.c_void_p, C.POINTER(RenderDescC), C.c_void_p, C.c_void_p, C.POINTER(AovDescC)]
         L.orc_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.orc_camera_rays.argtypes = [C.POINTER(RenderDescC), C.c_uint32, C.c_void_p]
         L.orc_hash_theironborn.restype = C.c_uint32
@@ -280,6 +286,38 @@ class OracleScene:
         r = self.render_desc(sample_offset, rows, shard, spp)
         secs = lib().orc_render(self.handle, C.byref(r), img.ctypes.data, counts.ctypes.data)
         return img, secs, (int(counts[0]), int(counts[1]))
+
+    def render_aovs(self, aov_ids, clear_values=None, sample_offset=0, prev=None, spp=None):
+        """Colour + auxiliary AOVs; `prev` = dict of the previous call's outputs for progressive refinement."""
+        d = self.desc
+        INT = (11, 13, 14)
+        out = {}
+        a = AovDescC()
+        for aov in aov_ids:
+            aov = int(aov)
+            if aov == 0:
+                continue
+            if aov in INT:
+                buf = np.zeros((d.height, d.width, 1), np.int32)
+            elif aov == 12:
+                buf = np.zeros((d.height, d.width, 1), np.float32)
+            else:
+                buf = np.zeros((d.height, d.width, 4), np.float32)
+            if prev is not None and aov in prev:
+                buf[...] = prev[aov]
+            out[aov] = buf
+            a.mask |= (1 << aov)
+            a.buffers[aov] = buf.ctypes.data
+            clear = (clear_values or {}).get(aov, (0.0, 0.0, 0.0, 0.0))
+            raw = bytes(clear) if isinstance(clear, (bytes, bytearray)) else (np.asarray(clear, np.int32).tobytes() if aov in INT else np.asarray(clear, np.float32).tobytes())
+            raw = (raw + b"\0" * 16)[:16]
+            a.clear[aov] = (C.c_uint8 * 16)(*raw)
+        img = np.zeros((d.height, d.width, 4), np.float32) if prev is None or 0 not in prev else np.ascontiguousarray(prev[0], np.float32).copy()
+        counts = np.zeros(2, np.uint64)
+        r = self.render_desc(sample_offset, None, None, spp)
+        lib().orc_render_aovs(self.handle, C.byref(r), img.ctypes.data, counts.ctypes.data, C.byref(a))
+        out[0] = img
+        return out
 
     def trace(self, rays, any_hit=False):
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)

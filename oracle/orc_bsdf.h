@@ -312,9 +312,21 @@ static inline void ups_evaluate(const Material& m, BsdfEvaluateData& d, const St
   d.pdf = pdf;
 }
 
+static inline V3 ups_albedo(const Material& m, V3 k1, const State& s)
+{
+  UpsLobes u = ups_lobes(m);
+  const float nk1 = clampf(dot(k1, s.normal), 0.0f, 1.0f);
+  const V3 F = schlick(u.F0, u.F90, nk1);
+  const V3 inner = F + (v3(1.0f) - F) * u.Kd;
+  if (!(u.coat > 0.0f)) return inner;
+  const float fc = u.coat * fresnel_dielectric(nk1, 1.5f);
+  return v3(fc) + inner * (1.0f - fc);
+}
+
 // ---- closure 2: OpenPBR (subset, see orc_openpbr.h) -----------------------------------------
 void openpbr_sample(const Material& m, BsdfSampleData& d, const State& s);
 void openpbr_evaluate(const Material& m, BsdfEvaluateData& d, const State& s);
+V3 openpbr_albedo(const Material& m, V3 k1, const State& s);
 
 // ---- dispatch = the generated mdl_bsdf_scattering_* entry points ---------------------------
 static inline void bsdf_sample(const Material& m, BsdfSampleData& d, const State& s)
@@ -331,6 +343,16 @@ static inline void bsdf_evaluate(const Material& m, BsdfEvaluateData& d, const S
     case GTLC_CLOSURE_DIFFUSE: diffuse_evaluate(m, d, s); break;
     case GTLC_CLOSURE_USD_PREVIEW_SURFACE: ups_evaluate(m, d, s); break;
     default: openpbr_evaluate(m, d, s); break;
+  }
+}
+
+// mdl_bsdf_scattering_auxiliary (rp_main.chit:264-280): albedo_diffuse + albedo_glossy
+static inline V3 bsdf_albedo(const Material& m, V3 k1, const State& s)
+{
+  switch (m.closure) {
+    case GTLC_CLOSURE_DIFFUSE: return p3(m, GTLC_DIFFUSE_TINT_R);
+    case GTLC_CLOSURE_USD_PREVIEW_SURFACE: return ups_albedo(m, k1, s);
+    default: return openpbr_albedo(m, k1, s);
   }
 }
 

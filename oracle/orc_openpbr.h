@@ -209,4 +209,19 @@ inline void openpbr_evaluate(const Material& m, BsdfEvaluateData& d, const State
   d.pdf = pdf;
 }
 
+// mdl_bsdf_scattering_auxiliary: albedo_diffuse + albedo_glossy of the layer stack at the viewing angle
+// (directional albedo of every specular lobe taken as its Fresnel weight at n.k1).
+inline V3 openpbr_albedo(const Material& m, V3 k1, const State& s)
+{
+  const OpbrLobes o = opbr_lobes(m);
+  const float nk1 = clampf(dot(k1, s.normal), 0.0f, 1.0f);
+  const float fs = fresnel_dielectric(nk1, o.eta);
+  const V3 substrate = o.Kd * (1.0f - o.trans_w) + o.trans_tint * o.trans_w;
+  const V3 dielectric = o.spec_color * fs + substrate * (1.0f - fs);
+  const V3 base = opbr_metal_fresnel(o, nk1) * o.metal + dielectric * (1.0f - o.metal);
+  if (!(o.coat_w > 0.0f)) return base;
+  const float fc = o.coat_w * fresnel_dielectric(nk1, o.coat_ior);
+  return v3(fc) + (base * o.coat_att) * (1.0f - fc);
+}
+
 } // namespace orc

@@ -102,6 +102,7 @@ struct Scene {
   std::vector<GtlcVertex> vertices;   // host vertices as passed to giCreateMesh (Gi.h:109-117)
   std::vector<FVertex> fverts;        // packed like Gi.cpp:845-859
   std::vector<uint32_t> faces;        // 3 per face, mesh-local
+  std::vector<int32_t> faceIds;       // optional, one per face (rp_main.chit:232-240)
   std::vector<InstanceDesc> instances;
   std::vector<float> worldToObject;   // 12 per instance
   std::vector<Material> materials;

@@ -220,3 +220,57 @@ def test_material_sort_is_invisible(gpu):
             b.close()
             gpu.set_tuning(sortByMaterial=-1)
     assert np.array_equal(imgs[0], imgs[1])
+
+
+AOVS = [0, 1, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]   # everything but the NEE / ClockCycles debug AOVs
+INT_AOVS = (11, 13, 14)
+
+
+def _aov_parity(gi, desc, second_call=False):
+    clear = {11: (-1,), 13: (-1,), 14: (-1,), 1: (0.5, 0.5, 1.0, 0.0), 12: (1.0,)}
+    b = gi.BuiltScene(desc)
+    try:
+        o = orc.OracleScene(desc)
+        got = b.render_aovs(AOVS, clear)
+        ref = o.render_aovs(AOVS, clear)
+        if second_call:            # progressive refinement of the accumulating AOVs (Color, Normal, Albedo)
+            got = b.render_aovs(AOVS, clear)
+            ref = o.render_aovs(AOVS, clear, sample_offset=desc.settings.spp, prev=ref)
+        for aov in AOVS:
+            g, r = got[gi.GiAovId(aov)], ref[aov]
+            if aov in INT_AOVS:
+                assert (g != r).mean() < 1e-3, "integer AOV %d differs on %.4f of the pixels" % (aov, (g != r).mean())
+            else:
+                diff = np.abs(g[..., :3 if g.shape[-1] == 4 else 1].astype(np.float64) - r[..., :3 if r.shape[-1] == 4 else 1])
+                assert np.sqrt(np.mean(diff ** 2)) < 2e-3, "AOV %d RMSE %.3e" % (aov, np.sqrt(np.mean(diff ** 2)))
+                assert (diff <= 1e-3 + 1e-3 * np.abs(r[..., :diff.shape[-1]])).mean() >= 0.998, "AOV %d" % aov
+        return got
+    finally:
+        b.close()
+
+
+def test_aov_parity_cornell(gpu):
+    got = _aov_parity(gpu, scenes.cornell(64, 64, spp=3, max_bounces=4))
+    ids = got[gpu.GiAovId.ObjectId]
+    assert set(np.unique(ids)) <= set(range(-1, 9)) and (ids > 0).mean() > 0.5     # 8 meshes, object ids 1..8, clear value -1
+
+
+def test_aov_parity_instances_and_progressive(gpu):
+    d = scenes.kitchen_standin(tris_per_instance=200, instances=30, meshes=6, materials=6, width=64, height=48, spp=2)
+    got = _aov_parity(gpu, d, second_call=True)
+    assert got[gpu.GiAovId.InstanceId].max() >= 3      # instanced props carry their instance index
+
+
+def test_color_only_render_is_unchanged_by_aov_support(gpu):
+    d = scenes.cornell(48, 48, spp=2, max_bounces=3)
+    b = gpu.BuiltScene(d)
+    try:
+        plain = b.render().copy()
+    finally:
+        b.close()
+    b = gpu.BuiltScene(d)
+    try:
+        with_aovs = b.render_aovs([0, 1, 16, 12])[gpu.GiAovId.Color]
+    finally:
+        b.close()
+    assert np.array_equal(plain, with_aovs)
