@@ -31,7 +31,8 @@ typedef uint64_t GtlcHandle; /* 0 == invalid (reference: nullptr from giCreate*)
 
 enum { GTLC_OK = 0, GTLC_ERROR = 1 }; /* GiStatus, Gi.h:32 */
 
-/* GiAovId, Gi.h:34-54.  Round 1 renders Color; the others are accepted and cleared. */
+/* GiAovId, Gi.h:34-54.  All AOVs are rendered except the NEE and ClockCycles debug AOVs, which are accepted and
+ * left at their clear value.  Formats: Color and every vec3 AOV Float32Vec4, Depth Float32, ObjectId/FaceId/InstanceId Int32. */
 enum {
   GTLC_AOV_COLOR = 0, GTLC_AOV_NORMAL, GTLC_AOV_NEE, GTLC_AOV_BARYCENTRICS, GTLC_AOV_TEXCOORDS,
   GTLC_AOV_BOUNCES, GTLC_AOV_CLOCK_CYCLES, GTLC_AOV_OPACITY, GTLC_AOV_TANGENTS, GTLC_AOV_BITANGENTS,
