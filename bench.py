@@ -192,6 +192,9 @@ def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # torchrun pins OMP_NUM_THREADS=1; the host-side BVH8 build (outside the timed region) is OpenMP-parallel
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
     import torch
     dist = None
     if world > 1:

@@ -68,10 +68,8 @@ struct RaySetup {
   float tmin;
   V3 idir;
   uint32_t octinv;
-  // Woop shear as three sparse basis vectors: mx = e_kx - Sx e_kz, my = e_ky - Sy e_kz, mz = Sz e_kz.
-  // dot(A, mx) evaluates to exactly fl(A[kx] - fl(Sx * A[kz])) -- the products with 1 and 0 are exact and
-  // adding the zero term is exact -- i.e. bit-identical to the indexed form of the paper (and of the CPU
-  // oracle) without any data-dependent component selection in the per-triangle code.
+  // Woop shear as three sparse basis vectors: mx = e_kx - Sx e_kz, my = e_ky - Sy e_kz, mz = Sz e_kz, so that
+  // the per-triangle code needs no data-dependent component selection (same definition in the CPU oracle).
   V3 mx, my, mz;
 };
 
@@ -92,14 +90,18 @@ GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
   int kx = kz + 1; if (kx == 3) kx = 0;
   int ky = kx + 1; if (ky == 3) ky = 0;
   if (comp(r.d, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
-  const float dz = comp(r.d, kz);
-  const float Sx = comp(r.d, kx) / dz;
-  const float Sy = comp(r.d, ky) / dz;
-  const float Sz = 1.0f / dz;
+  const float Sz = comp(r.idir, kz);          // = 1 / d[kz] exactly (the dominant component is never clamped): no extra division
+  const float Sx = comp(r.d, kx) * Sz;
+  const float Sy = comp(r.d, ky) * Sz;
   r.mx = v3(kx == 0 ? 1.0f : (kz == 0 ? -Sx : 0.0f), kx == 1 ? 1.0f : (kz == 1 ? -Sx : 0.0f), kx == 2 ? 1.0f : (kz == 2 ? -Sx : 0.0f));
   r.my = v3(ky == 0 ? 1.0f : (kz == 0 ? -Sy : 0.0f), ky == 1 ? 1.0f : (kz == 1 ? -Sy : 0.0f), ky == 2 ? 1.0f : (kz == 2 ? -Sy : 0.0f));
   r.mz = v3(kz == 0 ? Sz : 0.0f, kz == 1 ? Sz : 0.0f, kz == 2 ? Sz : 0.0f);
 }
+
+// Sheared coordinate of a translated vertex: FMA chain over the sparse basis vector (3 instructions).  Per-vertex
+// quantities may be fused -- they depend only on (vertex, ray), so shared vertices agree across triangles; the edge
+// functions U, V, W below must NOT be fused (their exact antisymmetry across a shared edge is the watertightness).
+GTLC_D float shear(V3 a, V3 m) { return fmaf(a.z, m.z, fmaf(a.y, m.y, a.x * m.x)); }
 
 // Rare path of the watertight test: an edge function is exactly zero -> recompute all three in double.
 __device__ __noinline__ void tri_edges_double(float Ax, float Ay, float Bx, float By, float Cx, float Cy, float& U, float& V, float& W)
@@ -116,9 +118,9 @@ __device__ __noinline__ void tri_edges_double(float Ax, float Ay, float Bx, floa
 GTLC_D bool tri_intersect(const RaySetup& r, V3 p0, V3 p1, V3 p2, float& t, float& u, float& v)
 {
   const V3 A = p0 - r.o, B = p1 - r.o, C = p2 - r.o;
-  const float Ax = dot(A, r.mx), Ay = dot(A, r.my);
-  const float Bx = dot(B, r.mx), By = dot(B, r.my);
-  const float Cx = dot(C, r.mx), Cy = dot(C, r.my);
+  const float Ax = shear(A, r.mx), Ay = shear(A, r.my);
+  const float Bx = shear(B, r.mx), By = shear(B, r.my);
+  const float Cx = shear(C, r.mx), Cy = shear(C, r.my);
   float U = Cx * By - Cy * Bx;
   float V = Ax * Cy - Ay * Cx;
   float W = Bx * Ay - By * Ax;
@@ -126,8 +128,8 @@ GTLC_D bool tri_intersect(const RaySetup& r, V3 p0, V3 p1, V3 p2, float& t, floa
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
   const float det = (U + V) + W;
   if (det == 0.0f) return false;
-  const float Az = dot(A, r.mz), Bz = dot(B, r.mz), Cz = dot(C, r.mz);
-  const float T = (U * Az + V * Bz) + W * Cz;
+  const float Az = shear(A, r.mz), Bz = shear(B, r.mz), Cz = shear(C, r.mz);
+  const float T = fmaf(W, Cz, fmaf(V, Bz, U * Az));
   const float rcp = 1.0f / det;
   t = T * rcp;
   u = V * rcp;

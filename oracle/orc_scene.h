@@ -43,36 +43,44 @@ struct Tri { V3 v0, v1, v2; uint32_t prim, inst; };
 
 struct BNode { V3 lo, hi; uint32_t left, right; uint32_t first, count; }; // count > 0: leaf
 
-struct RayPre { int kx, ky, kz; float Sx, Sy, Sz; };
+// Per-ray shear of the watertight test as three sparse basis vectors (mx = e_kx - Sx e_kz, my = e_ky - Sy e_kz,
+// mz = Sz e_kz), Sx = d[kx] * Sz, Sy = d[ky] * Sz, Sz = 1 / d[kz].
+struct RayPre { V3 mx, my, mz; };
 
 static inline float comp(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 
-// Woop, Benthin, Wald: "Watertight Ray/Triangle Intersection", JCGT 2(1) 2013, section 3.
+// Woop, Benthin, Wald: "Watertight Ray/Triangle Intersection", JCGT 2(1) 2013, section 3 (dimension choice and
+// winding-preserving swap as in the paper; the shear constants use the reciprocal of the dominant component).
 static inline RayPre ray_precompute(V3 d)
 {
-  RayPre r;
   float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-  r.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
-  r.kx = r.kz + 1; if (r.kx == 3) r.kx = 0;
-  r.ky = r.kx + 1; if (r.ky == 3) r.ky = 0;
-  if (comp(d, r.kz) < 0.0f) { int t = r.kx; r.kx = r.ky; r.ky = t; }
-  r.Sx = comp(d, r.kx) / comp(d, r.kz);
-  r.Sy = comp(d, r.ky) / comp(d, r.kz);
-  r.Sz = 1.0f / comp(d, r.kz);
+  int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  if (comp(d, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
+  const float Sz = 1.0f / comp(d, kz);
+  const float Sx = comp(d, kx) * Sz;
+  const float Sy = comp(d, ky) * Sz;
+  RayPre r;
+  r.mx = v3(kx == 0 ? 1.0f : (kz == 0 ? -Sx : 0.0f), kx == 1 ? 1.0f : (kz == 1 ? -Sx : 0.0f), kx == 2 ? 1.0f : (kz == 2 ? -Sx : 0.0f));
+  r.my = v3(ky == 0 ? 1.0f : (kz == 0 ? -Sy : 0.0f), ky == 1 ? 1.0f : (kz == 1 ? -Sy : 0.0f), ky == 2 ? 1.0f : (kz == 2 ? -Sy : 0.0f));
+  r.mz = v3(kz == 0 ? Sz : 0.0f, kz == 1 ? Sz : 0.0f, kz == 2 ? Sz : 0.0f);
   return r;
 }
 
+// Sheared coordinate of a translated vertex: an FMA chain over the sparse basis vector.  It depends only on the
+// vertex and the ray, so shared vertices get identical values in every triangle (what watertightness needs).
+static inline float shear(V3 a, V3 m) { return fmaf(a.z, m.z, fmaf(a.y, m.y, a.x * m.x)); }
+
 // Returns true and (t, u, v) when the ray hits the triangle's plane inside its edges; the caller
-// applies the (tMin, tMax) interval.
+// applies the (tMin, tMax) interval.  The edge functions U, V, W are NOT fused: antisymmetry
+// fl(fl(ab) - fl(cd)) = -fl(fl(cd) - fl(ab)) across the two triangles of a shared edge is what makes the test watertight.
 static inline bool tri_intersect(const RayPre& rp, V3 o, V3 p0, V3 p1, V3 p2, float& t, float& u, float& v)
 {
   V3 A = p0 - o, B = p1 - o, C = p2 - o;
-  float Ax = comp(A, rp.kx) - rp.Sx * comp(A, rp.kz);
-  float Ay = comp(A, rp.ky) - rp.Sy * comp(A, rp.kz);
-  float Bx = comp(B, rp.kx) - rp.Sx * comp(B, rp.kz);
-  float By = comp(B, rp.ky) - rp.Sy * comp(B, rp.kz);
-  float Cx = comp(C, rp.kx) - rp.Sx * comp(C, rp.kz);
-  float Cy = comp(C, rp.ky) - rp.Sy * comp(C, rp.kz);
+  float Ax = shear(A, rp.mx), Ay = shear(A, rp.my);
+  float Bx = shear(B, rp.mx), By = shear(B, rp.my);
+  float Cx = shear(C, rp.mx), Cy = shear(C, rp.my);
   float U = Cx * By - Cy * Bx;
   float V = Ax * Cy - Ay * Cx;
   float W = Bx * Ay - By * Ax;
@@ -87,10 +95,8 @@ static inline bool tri_intersect(const RayPre& rp, V3 o, V3 p0, V3 p1, V3 p2, fl
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
   float det = (U + V) + W;
   if (det == 0.0f) return false;
-  float Az = rp.Sz * comp(A, rp.kz);
-  float Bz = rp.Sz * comp(B, rp.kz);
-  float Cz = rp.Sz * comp(C, rp.kz);
-  float T = (U * Az + V * Bz) + W * Cz;
+  float Az = shear(A, rp.mz), Bz = shear(B, rp.mz), Cz = shear(C, rp.mz);
+  float T = fmaf(W, Cz, fmaf(V, Bz, U * Az));
   float rcp = 1.0f / det;
   t = T * rcp;
   u = V * rcp;
