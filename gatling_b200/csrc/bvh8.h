@@ -22,7 +22,7 @@
 // child box = p + q * 2^e, quantised conservatively (floor/ceil, plus a safety quantum when a bound
 // falls on a grid line).
 //
-// Triangle = 48 bytes = 3 x float4: (v0.xyz, bits primitiveId) (v1.xyz, bits instanceIndex) (v2.xyz, 0).
+// Triangle = 48 bytes = 3 x float4: (v0.xyz, bits primitiveId) (v1.xyz, bits instanceIndex) (v2.xyz, cutout opacity; 1 = opaque).
 #pragma once
 #include <stdint.h>
 #include <vector>
@@ -39,7 +39,7 @@ struct Bvh8 {
   double buildSeconds = 0.0;
 };
 
-struct BuildTri { float v[3][3]; uint32_t prim, inst; };
+struct BuildTri { float v[3][3]; uint32_t prim, inst; float opacity; };   // opacity < 1: stochastic cutout (rp_main.ahit)
 
 // Builds the BVH8 over `tris` (world space).  Deterministic for a given input.
 void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out);

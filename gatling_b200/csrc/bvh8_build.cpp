@@ -280,7 +280,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
           const BuildTri& tr = tris[b.idx[c.first + t]];
           float rec[12];
           for (int v = 0; v < 3; v++) { rec[v * 4 + 0] = tr.v[v][0]; rec[v * 4 + 1] = tr.v[v][1]; rec[v * 4 + 2] = tr.v[v][2]; }
-          std::memcpy(&rec[3], &tr.prim, 4); std::memcpy(&rec[7], &tr.inst, 4); rec[11] = 0.0f;
+          std::memcpy(&rec[3], &tr.prim, 4); std::memcpy(&rec[7], &tr.inst, 4); rec[11] = tr.opacity;
           out.tris.insert(out.tris.end(), rec, rec + 12);
         }
         triOffset += cnt;

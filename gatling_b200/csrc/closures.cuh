@@ -120,6 +120,14 @@ GTLC_HD bool mat_is_emissive(int closure, const float* p)
     return p[GTLC_OPBR_EMISSION_LUMINANCE] > 0.0f && (p[GTLC_OPBR_EMISSION_COLOR_R] > 0.0f || p[GTLC_OPBR_EMISSION_COLOR_G] > 0.0f || p[GTLC_OPBR_EMISSION_COLOR_B] > 0.0f);
   return false;
 }
+// mdl_cutout_opacity (rp_main.ahit:42): UsdPreviewSurface `opacity`, OpenPBR `geometry_opacity`
+GTLC_HD float mat_cutout_opacity(int closure, const float* p)
+{
+  float o = 1.0f;
+  if (closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) o = p[GTLC_UPS_OPACITY];
+  else if (closure == GTLC_CLOSURE_OPENPBR) o = p[GTLC_OPBR_GEOMETRY_OPACITY];
+  return o < 0.0f ? 0.0f : (o > 1.0f ? 1.0f : o);
+}
 GTLC_HD bool mat_is_thin_walled(int closure, const float* p) { return closure == GTLC_CLOSURE_OPENPBR && p[GTLC_OPBR_GEOMETRY_THIN_WALLED] != 0.0f; }
 
 // mdl_edf_emission_intensity (MaterialX uniform_edf -> df::diffuse_edf, intensity = color * PI)

@@ -128,7 +128,7 @@ struct Global {
   size_t poolCapacity = 0;
   PathQueue q[2];
   float4* hitTUVP = nullptr; uint32_t* hitInst = nullptr;
-  float4 *shO = nullptr, *shD = nullptr, *shC = nullptr;
+  float4 *shO = nullptr, *shD = nullptr, *shC = nullptr; uint32_t* shSeed = nullptr;
   float4* sampleRad = nullptr;
   float4* accum = nullptr; size_t accumCapacity = 0;
   Counters* counters = nullptr;
@@ -265,7 +265,7 @@ bool buildHostGeometry(Scene* s)
       s->hInstInfo.push_back({ vertexBase, faceBase, flags, matIndex });
       s->hInstIds.push_back(make_int2(m->id, k < m->instanceIds.size() ? m->instanceIds[k] : (int32_t) k));
       for (uint32_t f = 0; f < m->faces.size(); f++) {
-        BuildTri t; t.prim = f; t.inst = inst;
+        BuildTri t; t.prim = f; t.inst = inst; t.opacity = mat_cutout_opacity(m->material->closure, m->material->params);
         for (int c = 0; c < 3; c++) {
           const float* p = m->vertices[m->faces[f].v_i[c]].pos;
           t.v[c][0] = ((o2w[0] * p[0] + o2w[1] * p[1]) + o2w[2] * p[2]) + o2w[3];
@@ -307,7 +307,8 @@ bool uploadMaterials(Scene* s)
   for (Material* m : s->flatMaterials) {
     params.insert(params.end(), m->params, m->params + GTLC_MATERIAL_PARAM_COUNT);
     closure.push_back(m->closure);
-    flags.push_back((mat_is_emissive(m->closure, m->params) ? kMatFlagEmissive : 0u) | (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u));
+    flags.push_back((mat_is_emissive(m->closure, m->params) ? kMatFlagEmissive : 0u) | (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u) |
+                    (mat_cutout_opacity(m->closure, m->params) < 1.0f ? kMatFlagCutout : 0u));
   }
   if (!s->dMatParams.upload(params.data(), params.size(), g.stream)) return false;
   if (!s->dMatClosure.upload(closure.data(), closure.size(), g.stream)) return false;
@@ -337,8 +338,8 @@ bool ensurePool(size_t capacity)
   if (capacity <= g.poolCapacity) return true;
   auto freeQ = [](PathQueue& q) { cudaFree(q.rayO); cudaFree(q.rayD); cudaFree(q.thr); cudaFree(q.rad); cudaFree(q.slot); memset(&q, 0, sizeof(q)); };
   freeQ(g.q[0]); freeQ(g.q[1]);
-  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.sampleRad);
-  g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.sampleRad = nullptr; g.poolCapacity = 0;
+  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.shSeed); cudaFree(g.sampleRad);
+  g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.shSeed = nullptr; g.sampleRad = nullptr; g.poolCapacity = 0;
   for (int k = 0; k < 2; k++) {
     CUDA_OK(cudaMalloc(&g.q[k].rayO, capacity * 16)); CUDA_OK(cudaMalloc(&g.q[k].rayD, capacity * 16));
     CUDA_OK(cudaMalloc(&g.q[k].thr, capacity * 16)); CUDA_OK(cudaMalloc(&g.q[k].rad, capacity * 16));
@@ -346,6 +347,7 @@ bool ensurePool(size_t capacity)
   }
   CUDA_OK(cudaMalloc(&g.hitTUVP, capacity * 16)); CUDA_OK(cudaMalloc(&g.hitInst, capacity * 4));
   CUDA_OK(cudaMalloc(&g.shO, capacity * 16)); CUDA_OK(cudaMalloc(&g.shD, capacity * 16)); CUDA_OK(cudaMalloc(&g.shC, capacity * 16));
+  CUDA_OK(cudaMalloc(&g.shSeed, capacity * 4));
   CUDA_OK(cudaMalloc(&g.sampleRad, capacity * 16));
   cudaFree(g.perm); g.perm = nullptr;
   CUDA_OK(cudaMalloc(&g.perm, capacity * 4));
@@ -494,10 +496,10 @@ void gtlc_terminate(void)
   cudaDeviceSynchronize();
   for (int k = 0; k < 2; k++) { cudaFree(g.q[k].rayO); cudaFree(g.q[k].rayD); cudaFree(g.q[k].thr); cudaFree(g.q[k].rad); cudaFree(g.q[k].slot); }
   memset(g.q, 0, sizeof(g.q));
-  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits); cudaFree(g.perm); cudaFree(g.sortHist); g.perm = nullptr; g.sortHist = nullptr;
+  cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.shSeed); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits); cudaFree(g.perm); cudaFree(g.sortHist); g.perm = nullptr; g.sortHist = nullptr;
   for (int k = 0; k < 6; k++) { cudaFree(g.aovSamples.a[k]); g.aovSamples.a[k] = nullptr; }
   g.aovCapacity = 0;
-  g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.sampleRad = nullptr; g.accum = nullptr; g.counters = nullptr; g.visits = nullptr;
+  g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.shSeed = nullptr; g.sampleRad = nullptr; g.accum = nullptr; g.counters = nullptr; g.visits = nullptr;
   g.poolCapacity = 0; g.accumCapacity = 0; g.visitsCapacity = 0;
   for (cudaEvent_t e : g.events) cudaEventDestroy(e);
   g.events.clear(); g.eventsUsed = 0;
@@ -951,7 +953,7 @@ int gtlc_render(const GtlcRenderParams* params)
           prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 0); launches++;
           TraceParams P = makeTraceParams(s);
           P.rayO = g.q[inIdx].rayO; P.rayD = g.q[inIdx].rayD; P.hitTUVP = g.hitTUVP; P.hitInst = g.hitInst;
-          P.numRays = &g.counters->numPaths[inIdx]; P.workCounter = &g.counters->workCounter;
+          P.numRays = &g.counters->numPaths[inIdx]; P.workCounter = &g.counters->workCounter; P.seedRad = g.q[inIdx].rad;
           timed(K_TRACE, [&] { launchTrace<TRACE_CLOSEST>(P, countVisits, traceBlocks); });
           if (sortByMaterial) {
             timed(K_SORT, [&] {
@@ -963,7 +965,7 @@ int gtlc_render(const GtlcRenderParams* params)
           }
           timed(K_SHADE, [&] {
             const uint32_t* permArg = sortByMaterial ? g.perm : nullptr;
-#define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) shade_kernel<MAXC, NEE, AOV><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.sampleRad, g.counters, inIdx, g.aovSamples)
+#define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) shade_kernel<MAXC, NEE, AOV><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
 #define GTLC_LAUNCH_SHADE(MAXC, NEE) do { if (aovMode && bounce == 0) GTLC_LAUNCH_SHADE2(MAXC, NEE, true); else GTLC_LAUNCH_SHADE2(MAXC, NEE, false); } while (0)
             const bool nee = rs.nextEventEstimation != 0;
             if (maxClosure == GTLC_CLOSURE_DIFFUSE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, false); }
@@ -976,7 +978,7 @@ int gtlc_render(const GtlcRenderParams* params)
             prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;
             TraceParams S = makeTraceParams(s);
             S.rayO = g.shO; S.rayD = g.shD; S.shContrib = g.shC; S.radPath = g.q[inIdx ^ 1].rad; S.radSample = g.sampleRad;
-            S.numRays = &g.counters->numShadow; S.workCounter = &g.counters->workCounter;
+            S.numRays = &g.counters->numShadow; S.workCounter = &g.counters->workCounter; S.seedU32 = g.shSeed;
             timed(K_SHADOW, [&] { launchTrace<TRACE_SHADOW>(S, countVisits, traceBlocks); });
           }
           inIdx ^= 1;

@@ -47,6 +47,8 @@ struct TraceParams {
   uint32_t* visitsPerRay;               // optional 2 x uint32 per ray
   int refillThreshold;                  // idle lanes that trigger a refill (kRefillThreshold by default)
   int triThreshold;                     // variant 5: lanes with pending triangles that trigger a triangle phase
+  const float4* __restrict__ seedRad;   // cutout any-hit: per-ray RNG seed = bits of seedRad[i].w (path queue `rad`), or
+  const uint32_t* __restrict__ seedU32; //   seedU32[i] (shadow queue); both NULL = seed 0
 };
 
 // Quantised byte q (0..255) taken from byte `j` of `w`, as the float 32768 + q: one PRMT builds
@@ -96,6 +98,22 @@ GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
   r.mx = v3(kx == 0 ? 1.0f : (kz == 0 ? -Sx : 0.0f), kx == 1 ? 1.0f : (kz == 1 ? -Sx : 0.0f), kx == 2 ? 1.0f : (kz == 2 ? -Sx : 0.0f));
   r.my = v3(ky == 0 ? 1.0f : (kz == 0 ? -Sy : 0.0f), ky == 1 ? 1.0f : (kz == 1 ? -Sy : 0.0f), ky == 2 ? 1.0f : (kz == 2 ? -Sy : 0.0f));
   r.mz = v3(kz == 0 ? Sz : 0.0f, kz == 1 ? Sz : 0.0f, kz == 2 ? Sz : 0.0f);
+}
+
+// Stochastic cutout (rp_main.ahit:35-61: `if (rand > mdl_cutout_opacity) ignoreIntersectionEXT`).  The reference
+// draws from the path's RNG once per any-hit invocation, in an order the Vulkan spec leaves undefined; here the
+// decision is a pure function of (ray seed, primitive, instance), so it does not depend on traversal order:
+// xi = uintAsFloat(hash_pcg32(seed ^ hash_theironborn(prim ^ inst * 0x9E3779B1))).  `opacity` rides in the spare
+// .w of the triangle record (1.0 = opaque, the common case costs one compare).
+GTLC_D bool cutout_ignored(const TraceParams& P, uint32_t rayIdx, float opacity, uint32_t prim, uint32_t inst)
+{
+  if (opacity >= 1.0f) return false;
+  uint32_t seed = 0u;
+  if (P.seedRad) seed = f2u(__ldg(&P.seedRad[rayIdx]).w);
+  else if (P.seedU32) seed = __ldg(&P.seedU32[rayIdx]);
+  uint32_t st = seed ^ hash_theironborn(prim ^ (inst * 0x9E3779B1u));
+  const float xi = uintAsFloat(hash_pcg32(st));
+  return xi > opacity;
 }
 
 // Sheared coordinate of a translated vertex: FMA chain over the sparse basis vector (3 instructions).  Per-vertex
@@ -266,7 +284,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
           if (COUNT) cTris++;
           float t, u, v;
           if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-            if (t > r.tmin && t < tmax) {
+            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
               const uint32_t prim = f2u(a.w), inst = f2u(b.w);
               if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
               const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v1(TraceParams P)
           const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
           float t, u, v;
           if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-            if (t > r.tmin && t < tmax) {
+            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
               const uint32_t prim = f2u(a.w), inst = f2u(b.w);
               if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; }
               else {
@@ -519,7 +537,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v2(TraceParams P)
             const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
             float t, u, v;
             if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-              if (t > r.tmin && t < tmax) {
+              if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
                 const uint32_t prim = f2u(a.w), inst = f2u(b.w);
                 if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; }
                 else {
@@ -700,7 +718,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
           const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
           float t, u, v;
           if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-            if (t > r.tmin && t < tmax) {
+            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
               const uint32_t prim = f2u(a.w), inst = f2u(b.w);
               if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
               const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));

@@ -49,7 +49,7 @@ enum : uint32_t {
 
 // Per-instance record (BlasPayload, rp_main.h:118-123, + CgpuBlasInstance hit-group index)
 struct InstanceInfo { uint32_t vertexBase, faceBase, flags, material; };
-constexpr uint32_t kMatFlagEmissive = 1u, kMatFlagThinWalled = 2u;
+constexpr uint32_t kMatFlagEmissive = 1u, kMatFlagThinWalled = 2u, kMatFlagCutout = 4u;
 
 struct DeviceScene {
   const float4* __restrict__ fverts;     // 2 x float4 per FVertex (rp_main.h:58-64)
@@ -82,7 +82,7 @@ struct WaveParams {
 // Per-sample capture of what the closest-hit shader writes into the auxiliary AOVs on the first bounce
 // (rp_main.chit:191-290); resolve_aov_kernel replays the megakernel's per-pixel write order from it.
 //   a[0] = (barycentrics.xyz, flags: bit0 hit, bit1 thinWalled, bit2 doubleSided)   a[1] = (texcoords.xyz, depth)
-//   a[2] = (tangent.xyz, objectId)   a[3] = (bitangent.xyz, faceId)   a[4] = (posNormal.xyz, instanceId)   a[5] = (albedo.xyz, -)
+//   a[2] = (tangent.xyz, objectId)   a[3] = (bitangent.xyz, faceId)   a[4] = (posNormal.xyz, instanceId)   a[5] = (albedo.xyz, cutout opacity or -1)
 struct AovSampleBuffers { float4* a[6]; };
 
 struct Counters {          // device-resident
@@ -338,7 +338,7 @@ template <int MAXC, bool NEE, bool AOV>
 __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
-                                                    float4* shO, float4* shD, float4* shC, float4* sampleRad,
+                                                    float4* shO, float4* shD, float4* shC, uint32_t* shSeed, float4* sampleRad,
                                                     Counters* ctr, int inIdx, AovSampleBuffers aov)
 {
   const unsigned FULL = 0xFFFFFFFFu;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
     bool survives = false, wantShadow = false;
     V3 ray_origin = v3(0.0f), ray_dir = v3(0.0f), throughput = v3(0.0f), radiance = v3(0.0f);
     V3 neeToLight = v3(0.0f), neeContrib = v3(0.0f);
-    uint32_t bitfield = 0, rng_state = 0, slot = 0;
+    uint32_t bitfield = 0, rng_state = 0, slot = 0, shadowSeed = 0;
     if (valid) {
       const uint32_t i = perm ? perm[it] : it;
       const float4 ro = qin.rayO[i], rd = qin.rayD[i], th = qin.thr[i], ra = qin.rad[i];
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           aov.a[2][slot] = make_float4(tanAov.x, tanAov.y, tanAov.z, u2f((uint32_t) ids.x));
           aov.a[3][slot] = make_float4(bitAov.x, bitAov.y, bitAov.z, u2f((uint32_t) faceId));
           aov.a[4][slot] = make_float4(posNormal.x, posNormal.y, posNormal.z, u2f((uint32_t) ids.y));
-          aov.a[5][slot] = make_float4(albedo.x, albedo.y, albedo.z, 0.0f);
+          aov.a[5][slot] = make_float4(albedo.x, albedo.y, albedo.z, (mflags & kMatFlagCutout) ? mat_cutout_opacity(closure, mp) : -1.0f);
         }
         if (mflags & kMatFlagEmissive) {                                               // chit:293-343
           if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
       }
 
       // ---- rp_main.rgen:397-480 ----
+      shadowSeed = rng_state;                                                          // rgen:399 (before the roulette draw)
       if (nee) {
         const float lightDist = length(neeToLight);                                    // rgen:403
         wantShadow = luminance(neeContrib) > 1e-6f && lightDist > 1e-9f;               // rgen:407
@@ -524,6 +525,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         shD[shPos] = make_float4(sdir.x, sdir.y, sdir.z, lightDist);                   // rgen:410
         const uint32_t target = survives ? outPos : (0x80000000u | slot);
         shC[shPos] = make_float4(neeContrib.x, neeContrib.y, neeContrib.z, u2f(target));
+        shSeed[shPos] = shadowSeed;                                                    // rgen:399 shadowRayPayload.rng_state
       }
     }
   }
@@ -569,6 +571,19 @@ GTLC_D V3 colormap_inferno(float t)
   return c0 + (c1 + (c2 + (c3 + (c4 + (c5 + c6 * t) * t) * t) * t) * t) * t;
 }
 
+// colormap.glsl:3-14
+GTLC_D V3 colormap_viridis(float t)
+{
+  const V3 c0 = v3(0.2777273272234177f, 0.005407344544966578f, 0.3340998053353061f);
+  const V3 c1 = v3(0.1050930431085774f, 1.404613529898575f, 1.384590162594685f);
+  const V3 c2 = v3(-0.3308618287255563f, 0.214847559468213f, 0.09509516302823659f);
+  const V3 c3 = v3(-4.634230498983486f, -5.799100973351585f, -19.33244095627987f);
+  const V3 c4 = v3(6.228269936347081f, 14.17993336680509f, 56.69055260068105f);
+  const V3 c5 = v3(4.776384997670288f, -13.74514537774601f, -65.35303263337234f);
+  const V3 c6 = v3(-5.435455855934631f, 4.645852612178535f, 26.3124352495832f);
+  return c0 + (c1 + (c2 + (c3 + (c4 + (c5 + c6 * t) * t) * t) * t) * t) * t;
+}
+
 // Destination render buffers of the auxiliary AOVs (device pointers, NULL = not bound) and their clear values.
 struct AovTargets { void* buf[GTLC_AOV_COUNT]; float4 clear[GTLC_AOV_COUNT]; };
 
@@ -606,7 +621,8 @@ __global__ void __launch_bounds__(256) resolve_aov_kernel(UniformData ubo, WaveP
       if (fl & 1u) {
         const float4 a1 = smp.a[1][slot], a2 = smp.a[2][slot], a3 = smp.a[3][slot], a4 = smp.a[4][slot], a5 = smp.a[5][slot];
         auto put3 = [&](int id, float x, float y, float z) { if (tg.buf[id]) { float4 c = vb[id][pix]; c.x = x; c.y = y; c.z = z; vb[id][pix] = c; } };
-        put3(GTLC_AOV_OPACITY, 1.0f, 0.0f, 0.0f);                                     // chit:202
+        if (a5.w < 0.0f) put3(GTLC_AOV_OPACITY, 1.0f, 0.0f, 0.0f);                    // chit:202 (no cutout)
+        else { const V3 vc = (a5.w == 0.0f) ? v3(1.0f) : colormap_viridis(a5.w); put3(GTLC_AOV_OPACITY, vc.x, vc.y, vc.z); }   // ahit:48 for the accepted hit
         put3(GTLC_AOV_TANGENTS, a2.x, a2.y, a2.z); put3(GTLC_AOV_BITANGENTS, a3.x, a3.y, a3.z);
         put3(GTLC_AOV_BARYCENTRICS, a0.x, a0.y, a0.z); put3(GTLC_AOV_TEXCOORDS, a1.x, a1.y, a1.z);
         if (fl & 2u) put3(GTLC_AOV_THIN_WALLED, 1.0f, 0.0f, 0.0f); else put3(GTLC_AOV_THIN_WALLED, 0.0f, 1.0f, 0.0f);     // chit:220

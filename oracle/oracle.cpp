@@ -77,6 +77,7 @@ struct AovSample {
   V3 bary, texcoords, tangent, bitangent, posNormal, albedo;
   bool thinWalled, doubleSided;
   int32_t objectId, faceId, instanceId; float depth;
+  float cutoutOpacity;   // < 0: the material has no cutout (chit:202), else ahit:48
 };
 
 // colormap.glsl:42-53
@@ -89,6 +90,19 @@ static inline V3 colormap_inferno(float t)
   const V3 c4 = v3(77.162935699427f, -33.40235894210092f, -81.80730925738993f);
   const V3 c5 = v3(-71.31942824499214f, 32.62606426397723f, 73.20951985803202f);
   const V3 c6 = v3(25.13112622477341f, -12.24266895238567f, -23.07032500287172f);
+  return c0 + (c1 + (c2 + (c3 + (c4 + (c5 + c6 * t) * t) * t) * t) * t) * t;
+}
+
+// colormap.glsl:3-14
+static inline V3 colormap_viridis(float t)
+{
+  const V3 c0 = v3(0.2777273272234177f, 0.005407344544966578f, 0.3340998053353061f);
+  const V3 c1 = v3(0.1050930431085774f, 1.404613529898575f, 1.384590162594685f);
+  const V3 c2 = v3(-0.3308618287255563f, 0.214847559468213f, 0.09509516302823659f);
+  const V3 c3 = v3(-4.634230498983486f, -5.799100973351585f, -19.33244095627987f);
+  const V3 c4 = v3(6.228269936347081f, 14.17993336680509f, 56.69055260068105f);
+  const V3 c5 = v3(4.776384997670288f, -13.74514537774601f, -65.35303263337234f);
+  const V3 c6 = v3(-5.435455855934631f, 4.645852612178535f, 26.3124352495832f);
   return c0 + (c1 + (c2 + (c3 + (c4 + (c5 + c6 * t) * t) * t) * t) * t) * t;
 }
 
@@ -331,6 +345,7 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
     aov->instanceId = in.instanceId;                                      // :243
     aov->doubleSided = isDoubleSided;                                     // :247
     aov->posNormal = (normal + v3(1.0f)) * 0.5f;                          // :252
+    aov->cutoutOpacity = (mat_cutout_opacity(mat) < 1.0f) ? mat_cutout_opacity(mat) : -1.0f;
     aov->albedo = bsdf_albedo(mat, -worldRayDir, st);                     // :264-280 (front-face BSDF; no backface BSDFs exist here)
   }
 
@@ -432,7 +447,7 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
     Hit hit;
     V3 d = p.ray_dir, o = p.ray_origin;
     rc.closest++;
-    if (scene_trace(*c.s, o, d, tMin, tMax, false, hit)) closest_hit_shader(c, p, hit, d, aov); // :381-393
+    if (scene_trace(*c.s, o, d, tMin, tMax, false, hit, p.rng_state)) closest_hit_shader(c, p, hit, d, aov); // :381-393 (any-hit seed: ahit:159)
     else miss_shader(c, p, d);
 
     if (c.fl.nee) {                                                       // :397-438
@@ -446,7 +461,7 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
       if (traceRay) {
         rc.shadow++;
         Hit sh;
-        shadowed = scene_trace(*c.s, shadowray_origin, shadowray_dir, stMin, stMax, true, sh);
+        shadowed = scene_trace(*c.s, shadowray_origin, shadowray_dir, stMin, stMax, true, sh, p.rng_state);   // :399 shadow payload rng
       }
       bool addContrib = traceRay && !shadowed;                            // :426
       if (addContrib) p.radiance += p.neeContrib;                         // :429
@@ -640,7 +655,7 @@ double orc_render_aovs(void* h, const OrcRenderDesc* r, float* rgba, uint64_t* r
         pixel_color += sample_color * invSpp;
         if (as.hit) {
           auto put3 = [&](int id, V3 v) { if (has(id)) { float* b = v3buf(id); b[0] = v.x; b[1] = v.y; b[2] = v.z; } };
-          put3(GTLC_AOV_OPACITY, v3(1.0f, 0.0f, 0.0f));                                 // chit:202
+          put3(GTLC_AOV_OPACITY, as.cutoutOpacity < 0.0f ? v3(1.0f, 0.0f, 0.0f) : (as.cutoutOpacity == 0.0f ? v3(1.0f) : colormap_viridis(as.cutoutOpacity)));   // chit:202 / ahit:48
           put3(GTLC_AOV_TANGENTS, as.tangent); put3(GTLC_AOV_BITANGENTS, as.bitangent);
           put3(GTLC_AOV_BARYCENTRICS, as.bary); put3(GTLC_AOV_TEXCOORDS, as.texcoords);
           put3(GTLC_AOV_THIN_WALLED, as.thinWalled ? v3(1.0f, 0.0f, 0.0f) : v3(0.0f, 1.0f, 0.0f));   // chit:220

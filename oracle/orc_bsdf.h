@@ -154,6 +154,14 @@ static inline bool mat_is_emissive(const Material& m)
   }
   return false;
 }
+// mdl_cutout_opacity (rp_main.ahit:42): UsdPreviewSurface `opacity`, OpenPBR `geometry_opacity`
+static inline float mat_cutout_opacity(const Material& m)
+{
+  float o = 1.0f;
+  if (m.closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) o = m.p[GTLC_UPS_OPACITY];
+  else if (m.closure == GTLC_CLOSURE_OPENPBR) o = m.p[GTLC_OPBR_GEOMETRY_OPACITY];
+  return o < 0.0f ? 0.0f : (o > 1.0f ? 1.0f : o);
+}
 static inline bool mat_is_thin_walled(const Material& m)
 {
   return m.closure == GTLC_CLOSURE_OPENPBR && m.p[GTLC_OPBR_GEOMETRY_THIN_WALLED] != 0.0f;

@@ -47,7 +47,7 @@ static inline uint32_t bvh8_node_hitmask(const uint8_t* nd, V3 o, V3 d, V3 idir,
 }
 
 static inline void bvh8_trace_one(const uint8_t* nodes, const float* tris, V3 o, V3 d, float tmin, float tmax, bool anyHit,
-                                  Hit& best, uint32_t& nNodes, uint32_t& nTris)
+                                  Hit& best, uint32_t& nNodes, uint32_t& nTris, uint32_t seed = 0)
 {
   best.t = -1.0f; best.u = best.v = 0.0f; best.prim = best.inst = 0xFFFFFFFFu;
   nNodes = nTris = 0;
@@ -90,7 +90,7 @@ static inline void bvh8_trace_one(const uint8_t* nodes, const float* tris, V3 o,
       nTris++;
       float t, u, v;
       if (tri_intersect(rp, o, v3(tp[0], tp[1], tp[2]), v3(tp[4], tp[5], tp[6]), v3(tp[8], tp[9], tp[10]), t, u, v)) {
-        if (t > tmin && t < tmax) {
+        if (t > tmin && t < tmax && !cutout_ignored(seed, tp[11], floatBitsToUint(tp[3]), floatBitsToUint(tp[7]))) {
           const uint32_t prim = floatBitsToUint(tp[3]), inst = floatBitsToUint(tp[7]);
           if (anyHit) { best.t = t; best.u = u; best.v = v; best.prim = prim; best.inst = inst; done = true; break; }
           if (hit_better(t, inst, prim, best)) { best.t = t; best.u = u; best.v = v; best.prim = prim; best.inst = inst; bt = t; }

@@ -39,7 +39,7 @@ struct DiskLight { float origin[3]; float radiusX; float baseEmission[3]; float 
 
 struct Hit { float t, u, v; uint32_t prim, inst; };
 
-struct Tri { V3 v0, v1, v2; uint32_t prim, inst; };
+struct Tri { V3 v0, v1, v2; uint32_t prim, inst; float opacity; };
 
 struct BNode { V3 lo, hi; uint32_t left, right; uint32_t first, count; }; // count > 0: leaf
 
@@ -221,7 +221,7 @@ static void scene_build(Scene& s)
       t.v0 = xform_point(in.objectToWorld, v3(a.pos[0], a.pos[1], a.pos[2]));
       t.v1 = xform_point(in.objectToWorld, v3(b.pos[0], b.pos[1], b.pos[2]));
       t.v2 = xform_point(in.objectToWorld, v3(c.pos[0], c.pos[1], c.pos[2]));
-      t.prim = f; t.inst = (uint32_t) ii;
+      t.prim = f; t.inst = (uint32_t) ii; t.opacity = mat_cutout_opacity(s.materials[in.material]);
       s.tris.push_back(t);
     }
   }
@@ -250,6 +250,17 @@ static inline bool box_hit(const BNode& n, V3 o, V3 inv, float tmin, float tmax,
   return tn <= tf;
 }
 
+// Stochastic cutout, rp_main.ahit:35-61 (`if (k > opacity) ignoreIntersectionEXT`).  The reference draws k from
+// the path RNG once per any-hit invocation in an order Vulkan leaves undefined; the oracle (and the kernel) decide
+// with a pure function of (ray seed, primitive, instance) instead -- ORACLE_DEVIATIONS.md #10.
+static inline bool cutout_ignored(uint32_t seed, float opacity, uint32_t prim, uint32_t inst)
+{
+  if (opacity >= 1.0f) return false;
+  uint32_t st = seed ^ hash_theironborn(prim ^ (inst * 0x9E3779B1u));
+  const float xi = uintAsFloat(hash_pcg32(st));
+  return xi > opacity;
+}
+
 static inline bool hit_better(float t, uint32_t inst, uint32_t prim, const Hit& best)
 {
   if (best.prim == 0xFFFFFFFFu) return true;
@@ -259,7 +270,7 @@ static inline bool hit_better(float t, uint32_t inst, uint32_t prim, const Hit& 
 }
 
 // R3: closest hit in (tMin, tMax).  anyHit: R8 (terminate on first hit).
-static inline bool scene_trace(const Scene& s, V3 o, V3 d, float tMin, float tMax, bool anyHit, Hit& best)
+static inline bool scene_trace(const Scene& s, V3 o, V3 d, float tMin, float tMax, bool anyHit, Hit& best, uint32_t seed = 0)
 {
   best.t = -1.0f; best.u = best.v = 0.0f; best.prim = best.inst = 0xFFFFFFFFu;
   if (s.nodes.empty() || !(tMax > tMin)) return false;
@@ -278,6 +289,7 @@ static inline bool scene_trace(const Scene& s, V3 o, V3 d, float tMin, float tMa
         float t, u, v;
         if (!tri_intersect(rp, o, tr.v0, tr.v1, tr.v2, t, u, v)) continue;
         if (!(t > tMin && t < tMax)) continue;
+        if (cutout_ignored(seed, tr.opacity, tr.prim, tr.inst)) continue;
         if (anyHit) { best.t = t; best.u = u; best.v = v; best.prim = tr.prim; best.inst = tr.inst; return true; }
         if (hit_better(t, tr.inst, tr.prim, best)) { best.t = t; best.u = u; best.v = v; best.prim = tr.prim; best.inst = tr.inst; tlimit = t; }
       }

@@ -274,3 +274,32 @@ def test_color_only_render_is_unchanged_by_aov_support(gpu):
     finally:
         b.close()
     assert np.array_equal(plain, with_aovs)
+
+
+def _cutout_cornell(w=96, h=96, spp=6):
+    """Cornell box whose tall box is a 40 % cutout and whose short box is 85 % opaque; NEE on so shadow rays cross cutouts."""
+    d = _lit_cornell(w, h, spp)
+    d.materials = list(d.materials) + [scenes.material_usd_preview_surface("Cutout40", diffuse=(0.2, 0.4, 0.9), opacity=0.4),
+                                       scenes.material_usd_preview_surface("Cutout85", diffuse=(0.9, 0.8, 0.2), opacity=0.85)]
+    d.meshes[6] = dataclasses.replace(d.meshes[6], material=len(d.materials) - 2)
+    d.meshes[7] = dataclasses.replace(d.meshes[7], material=len(d.materials) - 1)
+    return d
+
+
+def test_cutout_trace_and_render_parity(gpu):
+    d = _cutout_cornell()
+    cam = orc.camera_rays(d, 0)
+    cam[:, 3] = 0.0
+    cam[:, 7] = 3.0e38
+    _trace_parity(gpu, d, np.concatenate([cam, random_rays(30000, 21)]))     # seed 0 on both sides
+    img, ref = _render_parity(gpu, d)
+    opaque = _lit_cornell(96, 96, 6)
+    b = gpu.BuiltScene(opaque)
+    try:
+        img_opaque = b.render().copy()
+    finally:
+        b.close()
+    assert np.abs(img - img_opaque).mean() > 1e-3, "the cutout materials changed nothing"
+    got = _aov_parity(gpu, dataclasses.replace(d, width=48, height=48))
+    op = got[gpu.GiAovId.Opacity][..., :3]
+    assert len(np.unique(op.reshape(-1, 3), axis=0)) >= 3      # clear, opaque red (chit:202), viridis(0.4) / viridis(0.85)
