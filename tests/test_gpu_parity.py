@@ -281,8 +281,12 @@ def _cutout_cornell(w=96, h=96, spp=6):
     d = _lit_cornell(w, h, spp)
     d.materials = list(d.materials) + [scenes.material_usd_preview_surface("Cutout40", diffuse=(0.2, 0.4, 0.9), opacity=0.4),
                                        scenes.material_usd_preview_surface("Cutout85", diffuse=(0.9, 0.8, 0.2), opacity=0.85)]
-    d.meshes[6] = dataclasses.replace(d.meshes[6], material=len(d.materials) - 2)
-    d.meshes[7] = dataclasses.replace(d.meshes[7], material=len(d.materials) - 1)
+    # the boxes of cornell.usda sit exactly ON the floor: once they are see-through, their bottom faces z-fight with the
+    # floor and the winner flips with the last ulp of the ray (libm vs CUDA sin/cos) -- lift them to keep the test sharp
+    for k, mat in ((6, len(d.materials) - 2), (7, len(d.materials) - 1)):
+        xf = d.meshes[k].transform.copy()
+        xf[3, 2] += 0.03
+        d.meshes[k] = dataclasses.replace(d.meshes[k], material=mat, transform=xf)
     return d
 
 
