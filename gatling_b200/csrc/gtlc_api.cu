@@ -105,11 +105,11 @@ struct Scene : Object {
   // flattened host copies
   Bvh8 bvh; bool bvhValid = false;
   std::vector<float> hFverts; std::vector<uint32_t> hFaces;
-  std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo; std::vector<int2> hInstIds; std::vector<int32_t> hFaceIds;
+  std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo; std::vector<int2> hInstIds; std::vector<int32_t> hFaceIds; std::vector<uint32_t> hRankBase;
   std::vector<Material*> flatMaterials;
   // device
   DeviceArray<uint4> dNodes; DeviceArray<float4> dTris; DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;
-  DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo; DeviceArray<int2> dInstIds; DeviceArray<int32_t> dFaceIds;
+  DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo; DeviceArray<int2> dInstIds; DeviceArray<int32_t> dFaceIds; DeviceArray<uint32_t> dRankBase;
   DeviceArray<float> dMatParams; DeviceArray<int32_t> dMatClosure; DeviceArray<uint32_t> dMatFlags;
   DeviceArray<float4> dSphere, dDistant, dRect, dDisk;
   DeviceArray<uint32_t> dPixelMap; uint32_t pixelMapW = 0, pixelMapH = 0, pixelMapRank = 0, pixelMapCount = 1, pixelMapTile = 0, localPixels = 0;
@@ -231,7 +231,7 @@ void invertAffine(const float* m, float* out)
 bool buildHostGeometry(Scene* s)
 {
   auto t0 = std::chrono::steady_clock::now();
-  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->flatMaterials.clear();
+  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->flatMaterials.clear();
   std::vector<BuildTri> tris;
   size_t totalTris = 0;
   for (Mesh* m : s->meshes) if (m->visible && m->material) totalTris += m->faces.size() * (m->instanceTransforms.size() / 12);
@@ -263,6 +263,7 @@ bool buildHostGeometry(Scene* s)
       s->hO2W.insert(s->hO2W.end(), o2w, o2w + 12);
       s->hW2O.insert(s->hW2O.end(), w2o, w2o + 12);
       s->hInstInfo.push_back({ vertexBase, faceBase, flags, matIndex });
+      s->hRankBase.push_back((uint32_t) tris.size());   // rank of (inst, prim) = rankBase[inst] + prim, ascending in (inst, prim)
       s->hInstIds.push_back(make_int2(m->id, k < m->instanceIds.size() ? m->instanceIds[k] : (int32_t) k));
       for (uint32_t f = 0; f < m->faces.size(); f++) {
         BuildTri t; t.prim = f; t.inst = inst; t.opacity = mat_cutout_opacity(m->material->closure, m->material->params);
@@ -296,6 +297,7 @@ bool uploadGeometry(Scene* s)
   if (!s->dInstInfo.upload(s->hInstInfo.data(), s->hInstInfo.size(), st)) return false;
   if (!s->dInstIds.upload(s->hInstIds.data(), s->hInstIds.size(), st)) return false;
   if (!s->dFaceIds.upload(s->hFaceIds.data(), s->hFaceIds.size(), st)) return false;
+  if (!s->dRankBase.upload(s->hRankBase.data(), s->hRankBase.size(), st)) return false;
   CUDA_OK(cudaStreamSynchronize(st));
   s->lastBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return true;
@@ -401,7 +403,7 @@ bool buildPixelMap(Scene* s, uint32_t W, uint32_t H)
 TraceParams makeTraceParams(Scene* s)
 {
   TraceParams P; memset(&P, 0, sizeof(P));
-  P.nodes = s->dNodes.ptr; P.tris = s->dTris.ptr;
+  P.nodes = s->dNodes.ptr; P.tris = s->dTris.ptr; P.instRankBase = s->dRankBase.ptr; P.biasWord = 0x47000000u;
   P.stats = g.counters->stats;
   P.refillThreshold = g.tuning.reserved[0] > 0 ? g.tuning.reserved[0] : kRefillThreshold;
   P.triThreshold = g.tuning.reserved[2] > 0 ? g.tuning.reserved[2] : 8;
@@ -412,12 +414,9 @@ template <int MODE> void launchTrace(const TraceParams& P, bool count, int block
 {
   if (count) { trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // visit counting: variant 0 order = the oracle's walk
   switch (g.tuning.traceVariant) {
-    case 1: trace_kernel_v1<MODE, 1><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
-    case 2: trace_kernel_v1<MODE, 2><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
-    case 3: trace_kernel_v1<MODE, 3><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
-    case 4: trace_kernel_v1<MODE, 4><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 5: trace_kernel_v2<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 6: trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    case 7: trace_kernel_batched<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     default: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
   }
 }
@@ -518,7 +517,7 @@ void gtlc_scene_destroy(GtlcHandle h)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
-  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release();
+  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release();
   s->dMatParams.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;

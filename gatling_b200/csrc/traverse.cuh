@@ -49,12 +49,17 @@ struct TraceParams {
   int triThreshold;                     // variant 5: lanes with pending triangles that trigger a triangle phase
   const float4* __restrict__ seedRad;   // cutout any-hit: per-ray RNG seed = bits of seedRad[i].w (path queue `rad`), or
   const uint32_t* __restrict__ seedU32; //   seedU32[i] (shadow queue); both NULL = seed 0
+  uint32_t biasWord;                           // 0x47000000 (see biased_byte)
+  const uint32_t* __restrict__ instRankBase;   // variant 7: first global (instance, primitive)-ordered triangle rank of every instance
 };
 
 // Quantised byte q (0..255) taken from byte `j` of `w`, as the float 32768 + q: one PRMT builds
 // 0x4700qq00 (exponent 2^15, q in mantissa bits 8..15), no integer->float conversion pipe involved.
 // The bias is folded into the slab origin (o - 32768 s), so a bound costs PRMT + FFMA.
-GTLC_D float biased_byte(uint32_t w, uint32_t sel) { return u2f(__byte_perm(w, 0x47000000u, sel)); }
+// `k47` = 0x47000000 read from the kernel parameters, NOT a literal: PRMT encodes one immediate only, and with a
+// literal ptxas keeps the constant as that immediate and spends a MOV per PRMT on the selector (44 of the ~300
+// instructions of a node step); with the constant in a register the selector becomes the immediate.
+GTLC_D float biased_byte(uint32_t w, uint32_t k47, uint32_t sel) { return u2f(__byte_perm(w, k47, sel)); }
 
 // A ray with a NaN/Inf origin or direction can never hit a triangle (every comparison of the watertight
 // test fails) but would pass every NaN-dropping slab test and walk the whole tree: answer it as a miss.
@@ -159,7 +164,7 @@ GTLC_D bool tri_intersect(const RaySetup& r, V3 p0, V3 p1, V3 p2, float& t, floa
 // (bits 31..24: internal children in traversal priority order, bits 23..0: triangles).
 // t = (32768 + q) * s + (o - 32768 s) with s = 2^e / d, o = (p - origin) / d; branch-free.
 GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
-                             const RaySetup& r, float tbest)
+                             const RaySetup& r, float tbest, uint32_t k47)
 {
   const uint32_t e = n0.w;
   const float sx = u2f((e & 0xFFu) << 23) * r.idir.x;
@@ -187,15 +192,15 @@ GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, con
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const uint32_t sel = 0x7604u | ((uint32_t) j << 4);
-      const float tnx = fmaf(biased_byte(nearx, sel), sx, ox);
-      const float tny = fmaf(biased_byte(neary, sel), sy, oy);
-      const float tnz = fmaf(biased_byte(nearz, sel), sz, oz);
-      const float tfx = fmaf(biased_byte(farx, sel), sx, ox);
-      const float tfy = fmaf(biased_byte(fary, sel), sy, oy);
-      const float tfz = fmaf(biased_byte(farz, sel), sz, oz);
+      const float tnx = fmaf(biased_byte(nearx, k47, sel), sx, ox);
+      const float tny = fmaf(biased_byte(neary, k47, sel), sy, oy);
+      const float tnz = fmaf(biased_byte(nearz, k47, sel), sz, oz);
+      const float tfx = fmaf(biased_byte(farx, k47, sel), sx, ox);
+      const float tfy = fmaf(biased_byte(fary, k47, sel), sy, oy);
+      const float tfz = fmaf(biased_byte(farz, k47, sel), sz, oz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest)) * kBoxPad;
-      const uint32_t bits = (child_bits4 >> (8 * j)) & 0xFFu;
+      const uint32_t bits = __byte_perm(child_bits4, 0u, 0x4440u | (uint32_t) j);
       const uint32_t idx = (bit_index4 >> (8 * j)) & 0xFFu;
       hitmask |= (tn <= tf) ? (bits << idx) : 0u;
     }
@@ -209,6 +214,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t n = *P.numRays;
+  const uint32_t k47 = P.biasWord;
 
   uint2 stack[kStackSize];
   int sp = 0;
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
           const uint4* np = P.nodes + (size_t) node * 5;
           const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
           if (COUNT) cNodes++;
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
           G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
           T = make_uint2(n1.y, hm & 0x00FFFFFFu);
         } else {
@@ -327,132 +333,6 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
   }
 }
 
-// ---- variant 1: triangle postponing (Ylitie et al. 2017, section 4.3) -----------------------------
-// Same traversal, but a lane's triangle group is only tested when at least kTriEighths/8 of the
-// warp's active lanes have triangles pending; otherwise the group is pushed on the lane's stack and
-// the lane goes on with node work, so node steps and triangle tests each run with better SIMD
-// utilisation.  Results are identical to variant 0 (closest hit is order independent); the
-// node/triangle visit COUNTS are not (culling happens later), which is why the roofline's algorithmic
-// bytes are counted with variant 0 (= the oracle's walk) and variant 1 is only timed.
-template <int MODE, int kTriEighths>
-__global__ void __launch_bounds__(kTraceBlock) trace_kernel_v1(TraceParams P)
-{
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const uint32_t n = *P.numRays;
-
-  uint2 stack[kStackSize];
-  int sp = 0;
-  bool active = false;
-  bool exhausted = false;
-  uint32_t rayIdx = 0;
-  RaySetup r;
-  float bt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t bprim = 0xFFFFFFFFu, binst = 0xFFFFFFFFu;
-  float tmax = 0.0f;
-  uint2 G = make_uint2(0u, 0u), T = make_uint2(0u, 0u);
-
-  while (true) {
-    if (!exhausted) {
-      const unsigned need = __ballot_sync(FULL, !active);
-      if (need) {
-        const int leader = __ffs(need) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t) __popc(need));
-        base = __shfl_sync(FULL, base, leader);
-        if (!active) {
-          rayIdx = base + (uint32_t) __popc(need & ((1u << lane) - 1u));
-          if (rayIdx < n) {
-            const float4 ro = __ldg(&P.rayO[rayIdx]);
-            const float4 rd = __ldg(&P.rayD[rayIdx]);
-            ray_setup(r, ro, rd);
-            tmax = rd.w;
-            bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
-            sp = 0;
-            active = tmax > r.tmin;
-            if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
-            G = make_uint2(0u, 0x80000000u); T = make_uint2(0u, 0u);
-            if (!active && MODE != TRACE_SHADOW) { P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu; }
-          }
-        }
-        if (base + (uint32_t) __popc(need) >= n) exhausted = true;
-      }
-    }
-    if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
-
-    while (true) {
-      bool done = false;
-      // ---- A: node step / pop (only lanes without pending triangles) ----
-      if (active && T.y == 0u) {
-        if (G.y & 0xFF000000u) {
-          const uint32_t hits_imask = G.y;
-          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
-          G.y &= ~(1u << bit);
-          if (G.y & 0xFF000000u) stack[sp++] = G;
-          const uint32_t slot = (bit - 24u) ^ r.octinv;
-          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
-          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
-          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
-          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-          T = make_uint2(n1.y, hm & 0x00FFFFFFu);
-        } else if (sp > 0) {
-          const uint2 e = stack[--sp];
-          if (e.y & 0xFF000000u) G = e; else T = e;
-        } else {
-          done = true;
-        }
-      }
-      // ---- B: triangle phase, entered only when enough lanes have triangles ----
-      const unsigned actMask = __ballot_sync(FULL, active && !done);
-      unsigned triMask = __ballot_sync(FULL, active && !done && T.y != 0u);
-      const int thr = max(1, (__popc(actMask) * kTriEighths) >> 3);
-      while (__popc(triMask) >= thr) {
-        if (active && !done && T.y != 0u) {
-          const uint32_t j = (uint32_t) __ffs(T.y) - 1u;
-          T.y &= T.y - 1u;
-          const float4* tp = P.tris + (size_t) (T.x + j) * 3;
-          const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
-          float t, u, v;
-          if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
-              const uint32_t prim = f2u(a.w), inst = f2u(b.w);
-              if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; }
-              else {
-                const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
-                if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
-              }
-            }
-          }
-        }
-        triMask = __ballot_sync(FULL, active && !done && T.y != 0u);
-        if (!triMask) break;
-      }
-      // postpone what is left
-      if (active && !done && T.y != 0u) { stack[sp++] = T; T.y = 0u; }
-      if (done) {
-        const bool hit = bprim != 0xFFFFFFFFu;
-        if (MODE == TRACE_SHADOW) {
-          if (!hit) {
-            const float4 c = __ldg(&P.shContrib[rayIdx]);
-            const uint32_t target = f2u(c.w);
-            float4* dst = (target & 0x80000000u) ? (P.radSample + (target & 0x7FFFFFFFu)) : (P.radPath + target);
-            float4 cur = *dst;
-            cur.x += c.x; cur.y += c.y; cur.z += c.z;
-            *dst = cur;
-          }
-        } else {
-          P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
-          if (P.hitInst) P.hitInst[rayIdx] = binst;
-        }
-        active = false;
-      }
-      const unsigned idle = __ballot_sync(FULL, !active);
-      if (idle == FULL) break;
-      if (!exhausted && __popc(idle) >= P.refillThreshold) break;
-    }
-  }
-}
-
 // ---- variant 5: two-deep pending-triangle FIFO ------------------------------------------------------
 // A lane keeps up to two triangle groups (T0, T1) in registers and goes on with node steps while it has
 // room; the warp enters a triangle phase only when >= triThreshold lanes have triangles pending or nobody
@@ -464,6 +344,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v2(TraceParams P)
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const uint32_t n = *P.numRays;
+  const uint32_t k47 = P.biasWord;
   const int triThr = P.triThreshold;
 
   uint2 stack[kStackSize];
@@ -518,7 +399,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v2(TraceParams P)
           const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
           const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
           const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
           G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
           const uint2 Tn = make_uint2(n1.y, hm & 0x00FFFFFFu);
           if (Tn.y) { if (T0.y == 0u) T0 = Tn; else T1 = Tn; }
@@ -606,6 +487,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n = *P.numRays;
+  const uint32_t k47 = P.biasWord;
 
   // claims the next tile and starts its copy into `stage`; returns (base, count) to the whole warp
   auto issue = [&](int stage, uint32_t& base, uint32_t& cnt) {
@@ -704,7 +586,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
           const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
           const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
           const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt);
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
           G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
           T = make_uint2(n1.y, hm & 0x00FFFFFFu);
         } else {
@@ -744,6 +626,172 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
           } else {
             P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
             if (P.hitInst) P.hitInst[rayIdx] = binst;
+          }
+          active = false;
+        }
+      }
+      const unsigned idle = __ballot_sync(FULL, !active);
+      if (idle == FULL) break;
+      if (!exhausted && __popc(idle) >= P.refillThreshold) break;
+    }
+  }
+}
+
+// ---- variant 7: warp-cooperative batched triangle tests ----------------------------------------------
+// The per-lane triangle loop of variant 0 runs with ~3 of 32 lanes active and was 37 % of all issued
+// instructions.  Here a lane only APPENDS the triangles its node step found to a per-warp queue in shared
+// memory ((owner lane << 27) | triangle index) and goes on traversing; once the queue holds >= 32 entries (or
+// nobody has node work left) the whole warp drains it 32 tests at a time: lane L tests entry L against the
+// OWNER's ray, whose origin / shear basis / interval live in shared memory, and publishes a hit with one 64-bit
+// shared-memory atomicMin on (t bits << 32 | (instance, primitive) rank) -- the same closest-hit order as
+// variant 0, so results are bit-identical.  Culling sees a new t a few node steps late (measured on the CPU
+// walker: +2.5 % node visits per step of delay), which the 32-wide triangle tests more than pay for.
+constexpr int kBatchQueueCap = 832;   // 31 left-overs + 32 lanes x 24 triangles of one node step, rounded up
+
+template <int MODE>
+__global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kernel_batched(TraceParams P)
+{
+  constexpr int kWarps = kTraceBlock / 32;
+  __shared__ float4 sRay[kWarps][32][4];             // (o.xyz, tMin) (mx.xyz, tMax) (my.xyz, ray index) (mz.xyz, -)
+  __shared__ unsigned long long sKey[kWarps][32];    // best (t bits << 32 | rank) per owner lane
+  __shared__ float4 sHit[kWarps][32];                // (u, v, primitive, instance) of the best hit
+  __shared__ uint32_t sQueue[kWarps][kBatchQueueCap];
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t n = *P.numRays;
+  const uint32_t k47 = P.biasWord;
+
+  uint2 stack[kStackSize];
+  int sp = 0;
+  bool active = false, exhausted = false, pending = false;
+  uint32_t rayIdx = 0;
+  RaySetup r;
+  float bt = 0.0f, tmax = 0.0f;
+  unsigned long long keyInit = 0ull;
+  uint2 G = make_uint2(0u, 0u);
+  uint32_t qCount = 0;    // warp-uniform
+
+  while (true) {
+    // ---- refill ----
+    if (!exhausted) {
+      const unsigned need = __ballot_sync(FULL, !active);
+      if (need) {
+        const int leader = __ffs(need) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t) __popc(need));
+        base = __shfl_sync(FULL, base, leader);
+        if (!active) {
+          rayIdx = base + (uint32_t) __popc(need & ((1u << lane) - 1u));
+          if (rayIdx < n) {
+            const float4 ro = __ldg(&P.rayO[rayIdx]);
+            const float4 rd = __ldg(&P.rayD[rayIdx]);
+            ray_setup(r, ro, rd);
+            tmax = rd.w; bt = tmax; sp = 0; pending = false;
+            active = tmax > r.tmin;
+            if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
+            G = make_uint2(0u, 0x80000000u);
+            if (active) {
+              sRay[w][lane][0] = make_float4(r.o.x, r.o.y, r.o.z, r.tmin);
+              sRay[w][lane][1] = make_float4(r.mx.x, r.mx.y, r.mx.z, tmax);
+              sRay[w][lane][2] = make_float4(r.my.x, r.my.y, r.my.z, u2f(rayIdx));
+              sRay[w][lane][3] = make_float4(r.mz.x, r.mz.y, r.mz.z, 0.0f);
+              keyInit = ((unsigned long long) f2u(tmax) << 32) | 0xFFFFFFFFull;
+              sKey[w][lane] = keyInit;
+            } else if (MODE != TRACE_SHADOW) {
+              P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu;
+            }
+          }
+        }
+        if (base + (uint32_t) __popc(need) >= n) exhausted = true;
+        __syncwarp();
+      }
+    }
+    if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
+
+    while (true) {
+      // ---- A: one node step per lane with node work; its triangles go to the warp queue ----
+      uint32_t triBase = 0, triMask = 0;
+      if (active) {
+        if (!(G.y & 0xFF000000u) && sp > 0) G = stack[--sp];
+        if (G.y & 0xFF000000u) {
+          const uint32_t hits_imask = G.y;
+          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
+          G.y &= ~(1u << bit);
+          if (G.y & 0xFF000000u) stack[sp++] = G;
+          const uint32_t slot = (bit - 24u) ^ r.octinv;
+          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
+          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
+          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
+          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+          triBase = n1.y; triMask = hm & 0x00FFFFFFu;
+        }
+      }
+      // enqueue, one triangle per lane per round (owners interleave in the queue)
+      unsigned have = __ballot_sync(FULL, triMask != 0u);
+      while (have) {
+        if (triMask) {
+          const uint32_t j = (uint32_t) __ffs(triMask) - 1u;
+          triMask &= triMask - 1u;
+          sQueue[w][qCount + (uint32_t) __popc(have & ((1u << lane) - 1u))] = ((uint32_t) lane << 27) | (triBase + j);
+          pending = true;
+        }
+        qCount += (uint32_t) __popc(have);
+        have = __ballot_sync(FULL, triMask != 0u);
+      }
+      // ---- B: drain the queue 32-wide when it is full enough or nothing else can progress ----
+      const unsigned nodeWork = __ballot_sync(FULL, active && ((G.y & 0xFF000000u) != 0u || sp > 0));
+      if (qCount >= 32u || (qCount > 0u && nodeWork == 0u)) {
+        __syncwarp();
+        for (uint32_t qb = 0; qb < qCount; qb += 32u) {
+          const uint32_t qi = qb + (uint32_t) lane;
+          bool won = false; unsigned long long key = 0ull; uint32_t owner = 0; float hu = 0.0f, hv = 0.0f; uint32_t hprim = 0, hinst = 0;
+          if (qi < qCount) {
+            const uint32_t e = sQueue[w][qi];
+            owner = e >> 27;
+            const float4* tp = P.tris + (size_t) (e & 0x07FFFFFFu) * 3;
+            const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            const float4 r0 = sRay[w][owner][0], r1 = sRay[w][owner][1], r2 = sRay[w][owner][2], r3 = sRay[w][owner][3];
+            RaySetup q;
+            q.o = v3(r0.x, r0.y, r0.z); q.mx = v3(r1.x, r1.y, r1.z); q.my = v3(r2.x, r2.y, r2.z); q.mz = v3(r3.x, r3.y, r3.z);
+            float t, u, v;
+            if (tri_intersect(q, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
+              hprim = f2u(a.w); hinst = f2u(b.w);
+              if (t > r0.w && t < r1.w && !cutout_ignored(P, f2u(r2.w), c.w, hprim, hinst)) {
+                key = ((unsigned long long) f2u(t) << 32) | (unsigned long long) (__ldg(&P.instRankBase[hinst]) + hprim);
+                won = key < atomicMin(&sKey[w][owner], key);
+                hu = u; hv = v;
+              }
+            }
+          }
+          __syncwarp();
+          if (won && sKey[w][owner] == key) sHit[w][owner] = make_float4(hu, hv, u2f(hprim), u2f(hinst));
+          __syncwarp();
+        }
+        qCount = 0;
+        pending = false;
+        if (active) bt = u2f((uint32_t) (sKey[w][lane] >> 32));
+      }
+      // ---- C: finished rays ----
+      if (active && !pending) {
+        const unsigned long long key = sKey[w][lane];
+        const bool hit = key != keyInit;
+        bool done = !(G.y & 0xFF000000u) && sp == 0;
+        if (MODE != TRACE_CLOSEST && hit) done = true;
+        if (done) {
+          if (MODE == TRACE_SHADOW) {
+            if (!hit) {
+              const float4 c = __ldg(&P.shContrib[rayIdx]);
+              const uint32_t target = f2u(c.w);
+              float4* dst = (target & 0x80000000u) ? (P.radSample + (target & 0x7FFFFFFFu)) : (P.radPath + target);
+              float4 cur = *dst;
+              cur.x += c.x; cur.y += c.y; cur.z += c.z;
+              *dst = cur;
+            }
+          } else {
+            const float4 h4 = sHit[w][lane];
+            P.hitTUVP[rayIdx] = hit ? make_float4(u2f((uint32_t) (key >> 32)), h4.x, h4.y, h4.z) : make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu));
+            if (P.hitInst) P.hitInst[rayIdx] = hit ? f2u(h4.w) : 0xFFFFFFFFu;
           }
           active = false;
         }

@@ -282,7 +282,7 @@ typedef struct GtlcTuning {
   int32_t  sortByMaterial;    /* -1 auto (on iff >1 material), 0 off, 1 on */
   int32_t  skipReadback;      /* 1: leave AOVs on the device (kernel-only timing) */
   int32_t  countVisits;       /* 1: traversal kernels also count node/triangle visits (slower; roofline bookkeeping) */
-  int32_t  traceVariant;      /* 0 default; other values select experimental traversal kernels */
+  int32_t  traceVariant;      /* 0 default; experimental: 5 pending-triangle FIFO, 6 TMA-staged ray tiles, 7 warp-batched triangle tests */
   int32_t  reserved[3];       /* [0] refill threshold (idle lanes), [1] trace CTAs per SM, [2] unused; 0 = default */
 } GtlcTuning;
 GTLC_API void gtlc_set_tuning(const GtlcTuning* tuning);

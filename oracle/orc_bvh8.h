@@ -122,3 +122,57 @@ extern "C" void orc_bvh8_trace(const void* nodes, uint32_t nodeCount, const void
     if (visits) { visits[2 * (size_t) i] = nn; visits[2 * (size_t) i + 1] = nt; }
   }
 }
+
+// Analysis helper (not used by any test): the same walk, but a node's triangle group is only tested after `delay`
+// further node steps of that ray -- how many extra node visits does late culling cost?  Guides kernel design.
+extern "C" void orc_bvh8_trace_delayed(const void* nodesV, const void* trisV, const float* rays, uint32_t n, int delay, uint64_t* outCounts)
+{
+  using namespace orc;
+  const uint8_t* nodes = (const uint8_t*) nodesV; const float* tris = (const float*) trisV;
+  uint64_t totN = 0, totT = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : totN, totT)
+  for (int i = 0; i < (int) n; i++) {
+    const float* rr = &rays[(size_t) i * 8];
+    V3 o = v3(rr[0], rr[1], rr[2]), d = v3(rr[4], rr[5], rr[6]); float tmin = rr[3], tmax = rr[7];
+    RayPre rp = ray_precompute(d);
+    const float kMinDir = 8.271806125530277e-25f;
+    V3 idir = v3(1.0f / (fabsf(d.x) > kMinDir ? d.x : copysignf(kMinDir, d.x)), 1.0f / (fabsf(d.y) > kMinDir ? d.y : copysignf(kMinDir, d.y)), 1.0f / (fabsf(d.z) > kMinDir ? d.z : copysignf(kMinDir, d.z)));
+    const uint32_t octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+    float bt = tmax; Hit best; best.prim = best.inst = 0xFFFFFFFFu; best.t = -1;
+    uint32_t stackX[64], stackY[64]; int sp = 0;
+    uint32_t Gx = 0, Gy = 0x80000000u;
+    struct Pend { uint32_t x, y; uint64_t due; } fifo[256]; int fh = 0, ft = 0; uint64_t step = 0;
+    auto testGroup = [&](uint32_t Tx, uint32_t Ty) {
+      while (Ty) {
+        const uint32_t j = (uint32_t) __builtin_ctz(Ty); Ty &= Ty - 1u;
+        const float* tp = tris + (size_t) (Tx + j) * 12; totT++;
+        float t, u, v;
+        if (tri_intersect(rp, o, v3(tp[0], tp[1], tp[2]), v3(tp[4], tp[5], tp[6]), v3(tp[8], tp[9], tp[10]), t, u, v) && t > tmin && t < tmax) {
+          const uint32_t prim = floatBitsToUint(tp[3]), inst = floatBitsToUint(tp[7]);
+          if (hit_better(t, inst, prim, best)) { best.t = t; best.prim = prim; best.inst = inst; bt = t; }
+        }
+      }
+    };
+    while (true) {
+      while (fh != ft && fifo[fh & 255].due <= step) { testGroup(fifo[fh & 255].x, fifo[fh & 255].y); fh++; }
+      if (Gy & 0xFF000000u) {
+        const uint32_t hits_imask = Gy;
+        uint32_t bit = 31; while (!(hits_imask & (1u << bit))) bit--;
+        Gy &= ~(1u << bit);
+        if (Gy & 0xFF000000u) { stackX[sp] = Gx; stackY[sp] = Gy; sp++; }
+        const uint32_t slot = (bit - 24u) ^ octinv;
+        const uint32_t below = (slot == 0) ? 0u : (hits_imask & ((1u << slot) - 1u));
+        const uint8_t* nd = nodes + (size_t) (Gx + (uint32_t) __builtin_popcount(below)) * 80;
+        totN++; step++;
+        const uint32_t hm = bvh8_node_hitmask(nd, o, d, idir, tmin, bt, octinv);
+        Gx = ld32(nd + 16); Gy = (hm & 0xFF000000u) | (ld32(nd + 12) >> 24);
+        if (hm & 0x00FFFFFFu) { fifo[ft & 255] = { ld32(nd + 20), hm & 0x00FFFFFFu, step + (uint64_t) delay }; ft++; }
+      }
+      if (!(Gy & 0xFF000000u)) {
+        if (sp == 0) { while (fh != ft) { testGroup(fifo[fh & 255].x, fifo[fh & 255].y); fh++; } break; }
+        sp--; Gx = stackX[sp]; Gy = stackY[sp];
+      }
+    }
+  }
+  outCounts[0] = totN; outCounts[1] = totT;
+}
