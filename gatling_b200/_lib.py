@@ -53,7 +53,7 @@ class InitParams(C.Structure):
 
 class Tuning(C.Structure):
     _fields_ = [("maxPathsPerWave", C.c_uint32), ("sortByMaterial", C.c_int32), ("skipReadback", C.c_int32),
-                ("countVisits", C.c_int32), ("traceVariant", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("countVisits", C.c_int32), ("traceVariant", C.c_int32), ("reserved", C.c_int32 * 3), ("bvhBuilder", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -61,7 +61,8 @@ class Stats(C.Structure):
                 ("kernelLaunches", C.c_uint64), ("paths", C.c_uint64), ("msTotal", C.c_float), ("msTraceClosest", C.c_float),
                 ("msTraceAny", C.c_float), ("msShade", C.c_float), ("msRaygen", C.c_float), ("msSort", C.c_float),
                 ("msResolve", C.c_float), ("msBvhBuild", C.c_float), ("bvhNodeCount", C.c_uint32), ("bvhTriCount", C.c_uint32),
-                ("bvhMaxDepth", C.c_uint32), ("maxNodeVisitsPerRay", C.c_uint32), ("nonFiniteRays", C.c_uint64)]
+                ("bvhMaxDepth", C.c_uint32), ("maxNodeVisitsPerRay", C.c_uint32), ("nonFiniteRays", C.c_uint64),
+                ("msBvhDeviceBuild", C.c_float), ("reservedStats", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

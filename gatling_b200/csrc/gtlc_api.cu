@@ -6,6 +6,7 @@
 #include "bvh8.h"
 #include "wavefront.cuh"
 #include "sort.cuh"
+#include "bvh8_gpu.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -103,7 +104,9 @@ struct Scene : Object {
   // multi-GPU shard
   uint32_t shardRank = 0, shardCount = 1, shardTile = 64;
   // flattened host copies
-  Bvh8 bvh; bool bvhValid = false;
+  Bvh8 bvh; bool bvhValid = false;        // host copy of the BVH8 (stale while bvhHostStale: built on the device, not yet read back)
+  bool bvhHostStale = false; uint32_t nodeCount = 0, triCount = 0, maxDepth = 0, totalTris = 0;
+  std::vector<float> hInstOpacity; DeviceArray<float> dInstOpacity;
   std::vector<float> hFverts; std::vector<uint32_t> hFaces;
   std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo; std::vector<int2> hInstIds; std::vector<int32_t> hFaceIds; std::vector<uint32_t> hRankBase;
   std::vector<Material*> flatMaterials;
@@ -228,14 +231,15 @@ void invertAffine(const float* m, float* out)
 // ---------------------------------------------------------------------------------------------
 // scene flattening + BVH8 (replaces _giBuildGeometryStructures/_giCreateBvh, Gi.cpp:784-1315)
 // ---------------------------------------------------------------------------------------------
-bool buildHostGeometry(Scene* s)
+bool buildHostGeometry(Scene* s, bool hostBvh = true)
 {
   auto t0 = std::chrono::steady_clock::now();
-  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->flatMaterials.clear();
+  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->hInstOpacity.clear(); s->flatMaterials.clear();
   std::vector<BuildTri> tris;
   size_t totalTris = 0;
   for (Mesh* m : s->meshes) if (m->visible && m->material) totalTris += m->faces.size() * (m->instanceTransforms.size() / 12);
-  tris.reserve(totalTris);
+  if (hostBvh) tris.reserve(totalTris);
+  uint32_t rank = 0;
   for (Mesh* m : s->meshes) {
     if (!m->visible) continue;                                          // Gi.cpp:801-804
     if (!m->material) { setError("invalid BLAS material (mesh '%s' has no material)", m->name.c_str()); continue; }   // Gi.cpp:819-823
@@ -263,7 +267,10 @@ bool buildHostGeometry(Scene* s)
       s->hO2W.insert(s->hO2W.end(), o2w, o2w + 12);
       s->hW2O.insert(s->hW2O.end(), w2o, w2o + 12);
       s->hInstInfo.push_back({ vertexBase, faceBase, flags, matIndex });
-      s->hRankBase.push_back((uint32_t) tris.size());   // rank of (inst, prim) = rankBase[inst] + prim, ascending in (inst, prim)
+      s->hRankBase.push_back(rank);   // rank of (inst, prim) = rankBase[inst] + prim, ascending in (inst, prim)
+      s->hInstOpacity.push_back(mat_cutout_opacity(m->material->closure, m->material->params));
+      rank += (uint32_t) m->faces.size();
+      if (!hostBvh) continue;   // the device builder flattens on the GPU (lbvh_flatten_kernel, same arithmetic)
       s->hInstIds.push_back(make_int2(m->id, k < m->instanceIds.size() ? m->instanceIds[k] : (int32_t) k));
       for (uint32_t f = 0; f < m->faces.size(); f++) {
         BuildTri t; t.prim = f; t.inst = inst; t.opacity = mat_cutout_opacity(m->material->closure, m->material->params);
@@ -277,19 +284,29 @@ bool buildHostGeometry(Scene* s)
       }
     }
   }
-  bvh8_build(tris, s->bvh);
-  if (s->bvh.maxDepth * 2 > (uint32_t) kStackSize) { setError("BVH8 depth %u needs a traversal stack of %u entries (have %d)", s->bvh.maxDepth, s->bvh.maxDepth * 2, kStackSize); return false; }
+  s->totalTris = rank;
+  if (hostBvh) {
+    bvh8_build(tris, s->bvh);
+    if (s->bvh.maxDepth > (uint32_t) kStackSize) { setError("BVH8 depth %u exceeds the traversal stack (%d entries)", s->bvh.maxDepth, kStackSize); return false; }
+    s->nodeCount = (uint32_t) s->bvh.nodes.size(); s->triCount = (uint32_t) (s->bvh.tris.size() / 12); s->maxDepth = s->bvh.maxDepth;
+    s->bvhHostStale = false;
+  }
   s->bvhValid = true;
   s->lastBuildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return true;
 }
 
-bool uploadGeometry(Scene* s)
+bool buildBvhOnDevice(Scene* s);
+
+bool uploadGeometry(Scene* s, bool hostBvh = true)
 {
   cudaStream_t st = g.stream;
   auto t0 = std::chrono::steady_clock::now();
-  if (!s->dNodes.upload((const uint4*) s->bvh.nodes.data(), s->bvh.nodes.size() * 5, st)) return false;
-  if (!s->dTris.upload((const float4*) s->bvh.tris.data(), s->bvh.tris.size() / 4, st)) return false;
+  if (hostBvh) {
+    if (!s->dNodes.upload((const uint4*) s->bvh.nodes.data(), s->bvh.nodes.size() * 5, st)) return false;
+    if (!s->dTris.upload((const float4*) s->bvh.tris.data(), s->bvh.tris.size() / 4, st)) return false;
+  }
+  if (!s->dInstOpacity.upload(s->hInstOpacity.data(), s->hInstOpacity.size(), st)) return false;
   if (!s->dFverts.upload((const float4*) s->hFverts.data(), s->hFverts.size() / 4, st)) return false;
   if (!s->dFaces.upload(s->hFaces.data(), s->hFaces.size(), st)) return false;
   if (!s->dO2W.upload((const float4*) s->hO2W.data(), s->hO2W.size() / 4, st)) return false;
@@ -299,7 +316,91 @@ bool uploadGeometry(Scene* s)
   if (!s->dFaceIds.upload(s->hFaceIds.data(), s->hFaceIds.size(), st)) return false;
   if (!s->dRankBase.upload(s->hRankBase.data(), s->hRankBase.size(), st)) return false;
   CUDA_OK(cudaStreamSynchronize(st));
+  if (!hostBvh && !buildBvhOnDevice(s)) return false;
   s->lastBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return true;
+}
+
+// Device BVH8 build (bvh8_gpu.cuh).  Inputs are the geometry arrays uploadGeometry() just placed in HBM.
+template <typename T> struct ScratchArray {
+  T* ptr = nullptr;
+  ~ScratchArray() { if (ptr) cudaFree(ptr); }
+  bool alloc(size_t n) { return cudaMalloc(&ptr, std::max<size_t>(n, 1) * sizeof(T)) == cudaSuccess; }
+};
+
+bool buildBvhOnDevice(Scene* s)
+{
+  const uint32_t n = s->totalTris;
+  cudaStream_t st = g.stream;
+  auto t0 = std::chrono::steady_clock::now();
+  g.stats.msBvhDeviceBuild = 0.0f;
+  if (n == 0) {                     // empty scene: one node without children (as the host builder)
+    Bvh8Node empty; memset(&empty, 0, sizeof(empty));
+    if (!s->dNodes.upload((const uint4*) &empty, 5, st)) return false;
+    if (!s->dTris.reserve(3)) return false;
+    CUDA_OK(cudaStreamSynchronize(st));
+    s->nodeCount = 1; s->triCount = 0; s->maxDepth = 0; s->bvhHostStale = true;
+    return true;
+  }
+  const uint32_t grid = (n + kLbvhBlock - 1) / kLbvhBlock;
+  const uint32_t sortGrid = std::min<uint32_t>(grid, (uint32_t) g.smCount * 4u);
+  ScratchArray<float4> inTris, boxLo, boxHi; ScratchArray<unsigned long long> keys0, keys1; ScratchArray<uint32_t> vals0, vals1, hist, parent, visit, bounds;
+  ScratchArray<uint2> children, range, queue0, queue1; ScratchArray<LbvhDp> dp; ScratchArray<uint32_t> childList, childCount, cntNodes, cntTris, totals; ScratchArray<uint4> nodesTmp;
+  const size_t refs = (size_t) 2 * n;
+  if (!inTris.alloc((size_t) n * 3) || !boxLo.alloc(refs) || !boxHi.alloc(refs) || !keys0.alloc(n) || !keys1.alloc(n) || !vals0.alloc(n) || !vals1.alloc(n) ||
+      !hist.alloc((size_t) 256 * sortGrid) || !parent.alloc(refs) || !visit.alloc(n) || !bounds.alloc(8) || !children.alloc(n) || !range.alloc(n) ||
+      !queue0.alloc(n) || !queue1.alloc(n) || !dp.alloc(n) || !childList.alloc((size_t) n * 8) || !childCount.alloc(n) || !cntNodes.alloc(n) || !cntTris.alloc(n) ||
+      !totals.alloc(2) || !nodesTmp.alloc((size_t) n * 5)) { setError("device BVH build: out of memory for %u triangles", n); return false; }
+  if (!s->dTris.reserve((size_t) n * 3)) return false;
+
+  lbvh_flatten_kernel<<<grid, kLbvhBlock, 0, st>>>(n, (uint32_t) s->hInstInfo.size(), s->dRankBase.ptr, s->dInstInfo.ptr, s->dO2W.ptr, s->dFverts.ptr, s->dFaces.ptr, s->dInstOpacity.ptr, inTris.ptr);
+  const uint32_t initBounds[8] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u };
+  CUDA_OK(cudaMemcpyAsync(bounds.ptr, initBounds, sizeof(initBounds), cudaMemcpyHostToDevice, st));
+  lbvh_bounds_kernel<<<std::min<uint32_t>(grid, (uint32_t) g.smCount * 8u), kLbvhBlock, 0, st>>>(n, inTris.ptr, bounds.ptr);
+  lbvh_morton_kernel<<<grid, kLbvhBlock, 0, st>>>(n, inTris.ptr, bounds.ptr, keys0.ptr, vals0.ptr);
+  unsigned long long* k[2] = { keys0.ptr, keys1.ptr }; uint32_t* v[2] = { vals0.ptr, vals1.ptr };
+  for (int pass = 0; pass < 8; pass++) {
+    lbvh_radix_count_kernel<<<sortGrid, kLbvhBlock, 0, st>>>(n, k[0], pass * 8, hist.ptr);
+    lbvh_scan_kernel<<<1, 1024, 0, st>>>(hist.ptr, 256u * sortGrid, nullptr);
+    lbvh_radix_scatter_kernel<<<sortGrid, kLbvhBlock, 0, st>>>(n, k[0], v[0], pass * 8, hist.ptr, k[1], v[1]);
+    std::swap(k[0], k[1]); std::swap(v[0], v[1]);
+  }
+  g.stats.kernelLaunches += 3 + 8 * 3;
+  LbvhTree T; memset(&T, 0, sizeof(T));
+  T.n = n; T.inTris = inTris.ptr; T.keys = k[0]; T.vals = v[0]; T.children = children.ptr; T.parent = parent.ptr; T.range = range.ptr;
+  T.boxLo = boxLo.ptr; T.boxHi = boxHi.ptr; T.visit = visit.ptr; T.dp = dp.ptr;
+  if (n > 1) lbvh_karras_kernel<<<grid, kLbvhBlock, 0, st>>>(T);
+  lbvh_refit_kernel<<<grid, kLbvhBlock, 0, st>>>(T);
+  g.stats.kernelLaunches += 2;
+
+  const uint2 rootEntry = make_uint2(0u, 0u);
+  CUDA_OK(cudaMemcpyAsync(queue0.ptr, &rootEntry, sizeof(rootEntry), cudaMemcpyHostToDevice, st));
+  LbvhLevel Lv; memset(&Lv, 0, sizeof(Lv));
+  Lv.childList = childList.ptr; Lv.childCount = childCount.ptr; Lv.cntNodes = cntNodes.ptr; Lv.cntTris = cntTris.ptr;
+  uint2* q[2] = { queue0.ptr, queue1.ptr };
+  uint32_t count = 1, nodeBase = 1, triBase = 0, depth = 0;
+  while (count > 0) {
+    depth++;
+    if (depth > (uint32_t) kStackSize) { setError("device BVH build: wide tree deeper than the traversal stack (%d)", kStackSize); return false; }
+    Lv.count = count; Lv.queue = q[0]; Lv.nextQueue = q[1]; Lv.nodeBase = nodeBase; Lv.triBase = triBase;
+    const uint32_t lg = (count + kLbvhBlock - 1) / kLbvhBlock;
+    lbvh_collapse_count_kernel<<<lg, kLbvhBlock, 0, st>>>(T, Lv);
+    lbvh_scan_kernel<<<1, 1024, 0, st>>>(cntNodes.ptr, count, totals.ptr + 0);
+    lbvh_scan_kernel<<<1, 1024, 0, st>>>(cntTris.ptr, count, totals.ptr + 1);
+    lbvh_collapse_emit_kernel<<<lg, kLbvhBlock, 0, st>>>(T, Lv, nodesTmp.ptr, s->dTris.ptr);
+    g.stats.kernelLaunches += 4;
+    uint32_t tot[2];
+    CUDA_OK(cudaMemcpyAsync(tot, totals.ptr, sizeof(tot), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    nodeBase += tot[0]; triBase += tot[1]; count = tot[0];
+    std::swap(q[0], q[1]);
+  }
+  if (triBase != n) { setError("device BVH build: emitted %u of %u triangles", triBase, n); return false; }
+  if (!s->dNodes.reserve((size_t) nodeBase * 5)) return false;
+  CUDA_OK(cudaMemcpyAsync(s->dNodes.ptr, nodesTmp.ptr, (size_t) nodeBase * 80, cudaMemcpyDeviceToDevice, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  s->nodeCount = nodeBase; s->triCount = n; s->maxDepth = depth; s->bvhHostStale = true;
+  g.stats.msBvhDeviceBuild = (float) std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return true;
 }
 
@@ -517,7 +618,7 @@ void gtlc_scene_destroy(GtlcHandle h)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
-  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release();
+  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
   s->dMatParams.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
@@ -756,11 +857,22 @@ void* gtlc_render_buffer_mem(GtlcHandle h) { RenderBuffer* rb = as<RenderBuffer>
 void* gtlc_render_buffer_device_mem(GtlcHandle h) { RenderBuffer* rb = as<RenderBuffer>(h, TAG_RB); return rb ? rb->devMem : nullptr; }
 
 // ---- BVH access ------------------------------------------------------------------------------
+static bool syncSceneToDevice(Scene* s);
 int gtlc_scene_get_bvh(GtlcHandle h, GtlcBvhView* view)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s || !view) return GTLC_ERROR;
   std::lock_guard<std::mutex> l(s->mutex);
-  if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s)) return GTLC_ERROR; /* device upload happens lazily in render/trace */ }
+  if (g.tuning.bvhBuilder == 1) {           // device builder: build if needed, then read the result back once
+    if (!requireInit()) return GTLC_ERROR;
+    cudaSetDevice(g.device);
+    if (!syncSceneToDevice(s)) return GTLC_ERROR;
+    if (s->bvhHostStale) {
+      s->bvh.nodes.resize(s->nodeCount); s->bvh.tris.resize((size_t) s->triCount * 12); s->bvh.maxDepth = s->maxDepth;
+      if (cudaMemcpy(s->bvh.nodes.data(), s->dNodes.ptr, (size_t) s->nodeCount * 80, cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(s->bvh.tris.data(), s->dTris.ptr, (size_t) s->triCount * 48, cudaMemcpyDeviceToHost) != cudaSuccess) { setError("BVH read-back failed"); return GTLC_ERROR; }
+      s->bvhHostStale = false;
+    }
+  } else if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s)) return GTLC_ERROR; /* device upload happens lazily in render/trace */ }
   view->nodes = s->bvh.nodes.data(); view->nodeCount = (uint32_t) s->bvh.nodes.size();
   view->triangles = s->bvh.tris.data(); view->triCount = (uint32_t) (s->bvh.tris.size() / 12);
   return GTLC_OK;
@@ -769,14 +881,15 @@ int gtlc_scene_get_bvh(GtlcHandle h, GtlcBvhView* view)
 static bool syncSceneToDevice(Scene* s)
 {
   if (s->geometryDirty || !s->bvhValid || !s->dNodes.ptr) {
-    if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s)) return false; }
-    if (!uploadGeometry(s)) return false;
+    const bool hostBvh = g.tuning.bvhBuilder != 1;
+    if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s, hostBvh)) return false; }
+    if (!uploadGeometry(s, hostBvh)) return false;
     s->geometryDirty = false; s->materialsDirty = true;
     g.stats.msBvhBuild = (float) s->lastBuildMs;
   }
   if (s->materialsDirty) { if (!uploadMaterials(s)) return false; s->materialsDirty = false; }
   if (s->lightsDirty) { if (!uploadLights(s)) return false; s->lightsDirty = false; }
-  g.stats.bvhNodeCount = (uint32_t) s->bvh.nodes.size(); g.stats.bvhTriCount = (uint32_t) (s->bvh.tris.size() / 12); g.stats.bvhMaxDepth = s->bvh.maxDepth;
+  g.stats.bvhNodeCount = s->nodeCount; g.stats.bvhTriCount = s->triCount; g.stats.bvhMaxDepth = s->maxDepth;
   return true;
 }
 
@@ -999,9 +1112,9 @@ int gtlc_render(const GtlcRenderParams* params)
       }
     }
     CUDA_OK(cudaStreamSynchronize(g.stream));
-    float keepBuild = g.stats.msBvhBuild; uint32_t kn = g.stats.bvhNodeCount, kt = g.stats.bvhTriCount, kd = g.stats.bvhMaxDepth;
+    float keepBuild = g.stats.msBvhBuild, keepDev = g.stats.msBvhDeviceBuild; uint32_t kn = g.stats.bvhNodeCount, kt = g.stats.bvhTriCount, kd = g.stats.bvhMaxDepth;
     memset(&g.stats, 0, sizeof(g.stats));
-    g.stats.msBvhBuild = keepBuild; g.stats.bvhNodeCount = kn; g.stats.bvhTriCount = kt; g.stats.bvhMaxDepth = kd;
+    g.stats.msBvhBuild = keepBuild; g.stats.msBvhDeviceBuild = keepDev; g.stats.bvhNodeCount = kn; g.stats.bvhTriCount = kt; g.stats.bvhMaxDepth = kd;
     cudaEventElapsedTime(&g.stats.msTotal, evStart, evEnd);
     for (const TimedSpan& t : spans) {
       float ms = 0.0f; cudaEventElapsedTime(&ms, t.a, t.b);

@@ -283,7 +283,8 @@ typedef struct GtlcTuning {
   int32_t  skipReadback;      /* 1: leave AOVs on the device (kernel-only timing) */
   int32_t  countVisits;       /* 1: traversal kernels also count node/triangle visits (slower; roofline bookkeeping) */
   int32_t  traceVariant;      /* 0 default; experimental: 5 pending-triangle FIFO, 6 TMA-staged ray tiles, 7 warp-batched triangle tests */
-  int32_t  reserved[3];       /* [0] refill threshold (idle lanes), [1] trace CTAs per SM, [2] unused; 0 = default */
+  int32_t  reserved[3];       /* [0] refill threshold (idle lanes), [1] trace CTAs per SM, [2] variant 5 triangle threshold; 0 = default */
+  int32_t  bvhBuilder;        /* 0 host binned-SAH build (default, best trace speed); 1 device LBVH build (fast rebuilds; takes effect at the next geometry change) */
 } GtlcTuning;
 GTLC_API void gtlc_set_tuning(const GtlcTuning* tuning);
 GTLC_API void gtlc_get_tuning(GtlcTuning* tuning);
@@ -309,6 +310,8 @@ typedef struct GtlcStats {
   uint32_t bvhMaxDepth;
   uint32_t maxNodeVisitsPerRay; /* valid iff countVisits */
   uint64_t nonFiniteRays;       /* rays with a NaN/Inf origin or direction (answered as misses without traversal) */
+  float    msBvhDeviceBuild;    /* bvhBuilder = 1: wall clock of the device build alone (scratch allocation .. final node copy), part of msBvhBuild */
+  float    reservedStats;
 } GtlcStats;
 GTLC_API void gtlc_get_stats(GtlcStats* stats);
 

@@ -789,3 +789,10 @@ int orc_tri_intersect(const float* o, const float* d, const float* p0, const flo
 } // extern "C"
 
 #include "orc_bvh8.h"
+#include "orc_lbvh8.h"
+
+// CPU restatement of the device BVH8 builder; see orc_lbvh8.h.  Returns the node count.
+extern "C" uint32_t orc_lbvh8_build(const float* tris, uint32_t n, uint32_t* nodes, float* outTris, uint32_t* depth)
+{
+  return orc_lbvh8::build(tris, n, nodes, outTris, depth);
+}

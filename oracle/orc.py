@@ -116,6 +116,9 @@ def lib():
         if hasattr(L, "orc_bvh8_trace"):
             L.orc_bvh8_trace.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
                                          C.c_void_p, C.c_void_p]
+        if hasattr(L, "orc_lbvh8_build"):
+            L.orc_lbvh8_build.restype = C.c_uint32
+            L.orc_lbvh8_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -349,3 +352,16 @@ def bvh8_trace(nodes, tris, rays, any_hit=False):
     L.orc_bvh8_trace(nodes.ctypes.data, len(nodes) // 80, tris.ctypes.data, len(tris) // 12, rays.ctypes.data, len(rays),
                      1 if any_hit else 0, hits.ctypes.data, visits.ctypes.data)
     return hits, visits
+
+
+def lbvh8_build(tris_rank_order):
+    """CPU restatement of the device BVH8 builder (orc_lbvh8.h): triangle records (n x 12 float32, in
+    (instance, primitive) order) -> (nodes bytes [nodeCount*80], tris float32 [n*12], depth)."""
+    L = lib()
+    t = np.ascontiguousarray(tris_rank_order, np.float32).reshape(-1, 12)
+    n = len(t)
+    nodes = np.zeros(max(n, 1) * 20, np.uint32)
+    out = np.zeros(max(n, 1) * 12, np.float32)
+    depth = C.c_uint32(0)
+    count = L.orc_lbvh8_build(t.ctypes.data, n, nodes.ctypes.data, out.ctypes.data, C.byref(depth))
+    return nodes[:count * 20].view(np.uint8).copy(), out[:n * 12].copy(), int(depth.value)

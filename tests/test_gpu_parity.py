@@ -307,3 +307,88 @@ def test_cutout_trace_and_render_parity(gpu):
     got = _aov_parity(gpu, dataclasses.replace(d, width=48, height=48))
     op = got[gpu.GiAovId.Opacity][..., :3]
     assert len(np.unique(op.reshape(-1, 3), axis=0)) >= 3      # clear, opaque red (chit:202), viridis(0.4) / viridis(0.85)
+
+
+def test_traversal_variants_are_invisible(gpu):
+    """The experimental traversal kernels (GtlcTuning.traceVariant 5/6/7) walk the BVH in a different order; the
+    closest hit is order-independent (smallest t, ties by (instance, primitive)), so hit records and images must be
+    bit-identical to variant 0 -- closest, any-hit and shadow mode, with cutouts."""
+    d = scenes.random_triangles(60000, 64, 64, spp=1)
+    rays = np.concatenate([random_rays(150000, 21), random_rays(20000, 22, tmax=0.05)])
+    lit = dataclasses.replace(_cutout_cornell(), width=64, height=64)
+    ref = None
+    try:
+        for variant in (0, 5, 6, 7):
+            gpu.set_tuning(traceVariant=variant)
+            b = gpu.BuiltScene(d)
+            try:
+                h = gpu.trace_rays(b.scene, rays)
+                a = gpu.trace_rays(b.scene, rays, any_hit=True)
+            finally:
+                b.close()
+            b = gpu.BuiltScene(lit)
+            try:
+                img = b.render().copy()
+            finally:
+                b.close()
+            got = ([h[k].copy() for k in ("prim", "inst", "t", "u", "v")], a["t"] >= 0, img)
+            if ref is None:
+                ref = got
+                continue
+            for x, y in zip(ref[0], got[0]):
+                assert np.array_equal(x, y), "variant %d: closest hits differ" % variant
+            assert np.array_equal(ref[1], got[1]), "variant %d: any-hit occlusion differs" % variant
+            assert np.array_equal(ref[2], got[2]), "variant %d: image differs" % variant
+    finally:
+        gpu.set_tuning(traceVariant=0)
+
+
+def test_device_bvh_build_parity(gpu):
+    """GtlcTuning.bvhBuilder = 1: flatten + Morton sort + Karras tree + SAH table + collapse on the GPU.  The node and
+    triangle arrays must equal the oracle's restatement (oracle/orc_lbvh8.h) byte for byte; the flattened records must
+    equal the host flatten; traversal and images must not change (closest hits do not depend on the tree)."""
+    from test_lbvh8_cpu import rank_order
+    inst_scene = scenes.kitchen_standin(tris_per_instance=300, instances=60, meshes=12, materials=8, width=64, height=48, spp=2)
+    cases = [scenes.cornell(48, 48, spp=2), scenes.random_triangles(200000, 64, 64, spp=1), inst_scene,
+             scenes.random_triangles(1, 8, 8, spp=1), scenes.random_triangles(3, 8, 8, spp=1), scenes.random_triangles(7, 8, 8, spp=1)]
+    try:
+        for d in cases:
+            gpu.set_tuning(bvhBuilder=0)
+            b = gpu.BuiltScene(d)
+            try:
+                _, host_tris = gpu.get_bvh(b.scene)
+                img_host = b.render().copy()
+            finally:
+                b.close()
+            gpu.set_tuning(bvhBuilder=1)
+            b = gpu.BuiltScene(d)
+            try:
+                nodes, tris = gpu.get_bvh(b.scene)
+                st = gpu.get_stats()
+                recs = rank_order(tris)
+                assert np.array_equal(recs, rank_order(host_tris)), "device flatten differs from the host flatten"
+                o_nodes, o_tris, o_depth = orc.lbvh8_build(recs)
+                assert len(nodes) == len(o_nodes) and np.array_equal(nodes, o_nodes), "BVH8 nodes differ from the oracle's build"
+                assert np.array_equal(tris, o_tris), "leaf-order triangles differ from the oracle's build"
+                assert st["bvhMaxDepth"] == o_depth and st["bvhNodeCount"] == len(o_nodes) // 80
+                rays = random_rays(40000, 31)
+                h_gpu, v_gpu = gpu.trace_rays(b.scene, rays, want_visits=True)
+                h_walk, v_walk = orc.bvh8_trace(nodes, tris, rays)
+                for k in ("prim", "inst", "t", "u", "v"):
+                    assert np.array_equal(h_gpu[k], h_walk[k]), k
+                assert np.array_equal(v_gpu, v_walk)
+                assert np.array_equal(b.render(), img_host), "image changed with the device-built BVH"
+            finally:
+                b.close()
+        # an empty scene
+        e = scenes.cornell(8, 8, spp=1)
+        e.meshes = []
+        b = gpu.BuiltScene(e)
+        try:
+            nodes, tris = gpu.get_bvh(b.scene)
+            assert len(nodes) == 80 and len(tris) == 0 and not nodes.any()
+            assert np.all(gpu.trace_rays(b.scene, random_rays(64, 2))["t"] == -1)
+        finally:
+            b.close()
+    finally:
+        gpu.set_tuning(bvhBuilder=0)
