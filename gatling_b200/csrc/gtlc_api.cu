@@ -249,14 +249,25 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
     if (matIndex == s->flatMaterials.size()) s->flatMaterials.push_back(m->material);
     const uint32_t vertexBase = (uint32_t) (s->hFverts.size() / 8);
     const uint32_t faceBase = (uint32_t) (s->hFaces.size() / 3);
-    for (const GtlcVertex& v : m->vertices) {                           // FVertex packing, Gi.cpp:845-859
-      uint32_t en = encodeDirection(v.norm), et = encodeDirection(v.tangent);
-      float f[8] = { v.pos[0], v.pos[1], v.pos[2], v.bitangentSign, 0.0f, 0.0f, v.u, v.v };
-      memcpy(&f[4], &en, 4); memcpy(&f[5], &et, 4);
-      s->hFverts.insert(s->hFverts.end(), f, f + 8);
+    {                                                                   // FVertex packing, Gi.cpp:845-859
+      const size_t nv = m->vertices.size(), nf = m->faces.size(), fv0 = s->hFverts.size(), ff0 = s->hFaces.size(), fi0 = s->hFaceIds.size();
+      s->hFverts.resize(fv0 + nv * 8); s->hFaces.resize(ff0 + nf * 3); s->hFaceIds.resize(fi0 + nf);
+      float* fv = s->hFverts.data() + fv0; uint32_t* ff = s->hFaces.data() + ff0; int32_t* fi = s->hFaceIds.data() + fi0;
+      const bool ownIds = m->faceIds.size() == nf;
+#pragma omp parallel for schedule(static) if (nv > 50000)
+      for (int64_t i = 0; i < (int64_t) nv; i++) {
+        const GtlcVertex& v = m->vertices[i];
+        const uint32_t en = encodeDirection(v.norm), et = encodeDirection(v.tangent);
+        float* f = fv + i * 8;
+        f[0] = v.pos[0]; f[1] = v.pos[1]; f[2] = v.pos[2]; f[3] = v.bitangentSign; f[6] = v.u; f[7] = v.v;
+        memcpy(&f[4], &en, 4); memcpy(&f[5], &et, 4);
+      }
+#pragma omp parallel for schedule(static) if (nf > 50000)
+      for (int64_t i = 0; i < (int64_t) nf; i++) {
+        ff[i * 3 + 0] = m->faces[i].v_i[0]; ff[i * 3 + 1] = m->faces[i].v_i[1]; ff[i * 3 + 2] = m->faces[i].v_i[2];
+        fi[i] = ownIds ? m->faceIds[i] : (int32_t) i;                    // rp_main.chit:232-240
+      }
     }
-    for (const GtlcFace& f : m->faces) { s->hFaces.push_back(f.v_i[0]); s->hFaces.push_back(f.v_i[1]); s->hFaces.push_back(f.v_i[2]); }
-    for (uint32_t f = 0; f < m->faces.size(); f++) s->hFaceIds.push_back(m->faceIds.size() == m->faces.size() ? m->faceIds[f] : (int32_t) f);   // rp_main.chit:232-240
     const uint32_t flags = (m->flipFacing ? 1u : 0u) | (m->doubleSided ? 2u : 0u);   // Gi.cpp:1135-1143
     const size_t instCount = m->instanceTransforms.size() / 12;
     for (size_t k = 0; k < instCount; k++) {                            // Gi.cpp:1188-1202
