@@ -13,8 +13,20 @@ HEADER = os.path.join(HERE, "..", "include", "gtlc.h")
 H = C.c_uint64
 
 
+class TextureDesc(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("reserved", C.c_int32), ("texels", C.c_void_p)]
+
+
+class TextureBinding(C.Structure):
+    _fields_ = [("paramIndex", C.c_int32), ("componentCount", C.c_int32), ("channels", C.c_int32 * 3), ("wrapU", C.c_int32),
+                ("wrapV", C.c_int32), ("srgb", C.c_int32), ("texture", C.c_uint64), ("fallback", C.c_float * 4),
+                ("scale", C.c_float * 4), ("bias", C.c_float * 4), ("uvRotation", C.c_float), ("uvScale", C.c_float * 2),
+                ("uvTranslation", C.c_float * 2), ("reserved", C.c_float)]
+
+
 class MaterialDesc(C.Structure):
-    _fields_ = [("closure", C.c_int32), ("name", C.c_char_p), ("params", C.c_float * 48)]
+    _fields_ = [("closure", C.c_int32), ("name", C.c_char_p), ("params", C.c_float * 48),
+                ("textures", C.POINTER(TextureBinding)), ("textureCount", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class MeshDesc(C.Structure):
@@ -108,6 +120,7 @@ _SIGNATURES = {
     "gtlc_dome_light_create": (H, [H, C.c_uint32, C.c_uint32, C.c_void_p]), "gtlc_dome_light_destroy": (None, [H]),
     "gtlc_dome_light_set_rotation": (None, [H, _F3]), "gtlc_dome_light_set_base_emission": (None, [H, _F3]),
     "gtlc_dome_light_set_diffuse_specular": (None, [H, C.c_float, C.c_float]),
+    "gtlc_texture_create": (H, [C.POINTER(TextureDesc)]), "gtlc_texture_destroy": (None, [H]),
     "gtlc_render_buffer_create": (H, [C.c_uint32, C.c_uint32, C.c_int32]), "gtlc_render_buffer_destroy": (None, [H]),
     "gtlc_render_buffer_mem": (C.c_void_p, [H]), "gtlc_render_buffer_device_mem": (C.c_void_p, [H]),
     "gtlc_render": (C.c_int, [C.POINTER(RenderParams)]),

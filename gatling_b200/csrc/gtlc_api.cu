@@ -45,13 +45,16 @@ void setError(const char* fmt, ...)
 // objects
 // ---------------------------------------------------------------------------------------------
 enum : uint32_t { TAG_SCENE = 0x53434e45, TAG_MATERIAL = 0x4d41544c, TAG_MESH = 0x4d455348, TAG_SPHERE = 0x5350484c,
-                  TAG_DISTANT = 0x44495354, TAG_RECT = 0x52454354, TAG_DISK = 0x4449534b, TAG_DOME = 0x444f4d45, TAG_RB = 0x52424620 };
+                  TAG_DISTANT = 0x44495354, TAG_RECT = 0x52454354, TAG_DISK = 0x4449534b, TAG_DOME = 0x444f4d45, TAG_RB = 0x52424620, TAG_TEXTURE = 0x54455854 };
 
 struct Object { uint32_t tag; };
 
 struct Scene;
 
-struct Material : Object { Scene* scene; int32_t closure; float params[GTLC_MATERIAL_PARAM_COUNT]; std::string name; };
+// Textures are shared between materials (and scenes): reference counted, the creator holds one reference.
+struct Texture : Object { uint32_t width, height; int32_t format; void* dTexels; int refs; };
+struct Material : Object { Scene* scene; int32_t closure; float params[GTLC_MATERIAL_PARAM_COUNT]; std::string name;
+                           std::vector<GtlcTextureBinding> bindings; std::vector<Texture*> boundTextures; };
 
 struct Mesh : Object {
   Scene* scene;
@@ -114,6 +117,7 @@ struct Scene : Object {
   DeviceArray<uint4> dNodes; DeviceArray<float4> dTris; DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;
   DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo; DeviceArray<int2> dInstIds; DeviceArray<int32_t> dFaceIds; DeviceArray<uint32_t> dRankBase;
   DeviceArray<float> dMatParams; DeviceArray<int32_t> dMatClosure; DeviceArray<uint32_t> dMatFlags;
+  DeviceArray<DeviceTexture> dTextures; DeviceArray<DeviceTexBinding> dTexBindings; DeviceArray<uint2> dMatTexRange; bool hasTextures = false;
   DeviceArray<float4> dSphere, dDistant, dRect, dDisk;
   DeviceArray<uint32_t> dPixelMap; uint32_t pixelMapW = 0, pixelMapH = 0, pixelMapRank = 0, pixelMapCount = 1, pixelMapTile = 0, localPixels = 0;
   double lastBuildMs = 0.0;
@@ -418,15 +422,38 @@ bool buildBvhOnDevice(Scene* s)
 bool uploadMaterials(Scene* s)
 {
   std::vector<float> params; std::vector<int32_t> closure; std::vector<uint32_t> flags;
+  std::vector<DeviceTexture> textures; std::vector<Texture*> textureIndex; std::vector<DeviceTexBinding> bindings; std::vector<uint2> ranges;
+  const double kPi = 3.14159265358979323846;
   for (Material* m : s->flatMaterials) {
     params.insert(params.end(), m->params, m->params + GTLC_MATERIAL_PARAM_COUNT);
     closure.push_back(m->closure);
-    flags.push_back((mat_is_emissive(m->closure, m->params) ? kMatFlagEmissive : 0u) | (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u) |
+    flags.push_back((mat_is_emissive(m->closure, m->params) || !m->bindings.empty() ? kMatFlagEmissive : 0u) |   // a textured input may be the emission
+                    (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u) |
                     (mat_cutout_opacity(m->closure, m->params) < 1.0f ? kMatFlagCutout : 0u));
+    ranges.push_back(make_uint2((uint32_t) bindings.size(), (uint32_t) m->bindings.size()));
+    for (size_t b = 0; b < m->bindings.size(); b++) {
+      const GtlcTextureBinding& src = m->bindings[b];
+      Texture* t = m->boundTextures[b];
+      uint32_t ti = 0;
+      for (; ti < textureIndex.size(); ti++) if (textureIndex[ti] == t) break;
+      if (ti == textureIndex.size()) { textureIndex.push_back(t); textures.push_back({ t->dTexels, t->width, t->height, (uint32_t) t->format, 0u }); }
+      DeviceTexBinding d; memset(&d, 0, sizeof(d));
+      d.paramIndex = src.paramIndex; d.texture = ti;
+      d.packed = (uint32_t) src.componentCount | ((uint32_t) src.channels[0] << 4) | ((uint32_t) src.channels[1] << 6) | ((uint32_t) src.channels[2] << 8) |
+                 ((uint32_t) src.wrapU << 10) | ((uint32_t) src.wrapV << 12) | ((src.srgb ? 1u : 0u) << 14);
+      memcpy(d.fallback, src.fallback, 16); memcpy(d.scale, src.scale, 16); memcpy(d.bias, src.bias, 16);
+      d.uvCos = (float) cos((double) src.uvRotation * kPi / 180.0); d.uvSin = (float) sin((double) src.uvRotation * kPi / 180.0);
+      d.uvScale[0] = src.uvScale[0]; d.uvScale[1] = src.uvScale[1]; d.uvTranslation[0] = src.uvTranslation[0]; d.uvTranslation[1] = src.uvTranslation[1];
+      bindings.push_back(d);
+    }
   }
+  s->hasTextures = !bindings.empty();
   if (!s->dMatParams.upload(params.data(), params.size(), g.stream)) return false;
   if (!s->dMatClosure.upload(closure.data(), closure.size(), g.stream)) return false;
   if (!s->dMatFlags.upload(flags.data(), flags.size(), g.stream)) return false;
+  if (!s->dTextures.upload(textures.data(), textures.size(), g.stream)) return false;
+  if (!s->dTexBindings.upload(bindings.data(), bindings.size(), g.stream)) return false;
+  if (!s->dMatTexRange.upload(ranges.data(), ranges.size(), g.stream)) return false;
   CUDA_OK(cudaStreamSynchronize(g.stream));
   return true;
 }
@@ -630,7 +657,7 @@ void gtlc_scene_destroy(GtlcHandle h)
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
   s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
-  s->dMatParams.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
+  s->dMatParams.release(); s->dTextures.release(); s->dTexBindings.release(); s->dMatTexRange.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
 }
@@ -644,12 +671,58 @@ void gtlc_scene_set_shard(GtlcHandle h, uint32_t rank, uint32_t worldSize, uint3
 }
 
 // ---- materials -----------------------------------------------------------------------------
+// ---- textures (R15) ------------------------------------------------------------------------
+static size_t texelBytes(int32_t format) { return format == GTLC_TEX_RGBA8_UNORM ? 4 : format == GTLC_TEX_RGBA16_FLOAT ? 8 : format == GTLC_TEX_R32_FLOAT ? 4 : 16; }
+static void releaseTexture(Texture* t)
+{
+  if (--t->refs > 0) return;
+  cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); cudaFree(t->dTexels);
+  t->tag = 0; delete t;
+}
+GtlcHandle gtlc_texture_create(const GtlcTextureDesc* d)
+{
+  if (!requireInit()) return 0;
+  if (!d || !d->texels || d->width == 0 || d->height == 0) { setError("gtlc_texture_create: empty texture"); return 0; }
+  if (d->format < GTLC_TEX_RGBA8_UNORM || d->format > GTLC_TEX_RGBA32_FLOAT) { setError("gtlc_texture_create: unknown format %d", d->format); return 0; }
+  cudaSetDevice(g.device);
+  Texture* t = new Texture(); t->tag = TAG_TEXTURE; t->width = d->width; t->height = d->height; t->format = d->format; t->refs = 1; t->dTexels = nullptr;
+  const size_t bytes = (size_t) d->width * d->height * texelBytes(d->format);
+  if (cudaMalloc(&t->dTexels, bytes) != cudaSuccess || cudaMemcpy(t->dTexels, d->texels, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    setError("gtlc_texture_create: device allocation of %zu bytes failed", bytes); cudaFree(t->dTexels); delete t; return 0;
+  }
+  return handleOf(t);
+}
+void gtlc_texture_destroy(GtlcHandle h)
+{
+  Texture* t = as<Texture>(h, TAG_TEXTURE); if (!t) return;
+  std::lock_guard<std::mutex> dl(g_destroyMutex);
+  releaseTexture(t);
+}
+
 GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
 {
   Scene* s = as<Scene>(sh, TAG_SCENE); if (!s || !d) return 0;
   if (d->closure < GTLC_CLOSURE_DIFFUSE || d->closure > GTLC_CLOSURE_OPENPBR) { setError("unknown closure %d", d->closure); return 0; }
+  if (d->textureCount && !d->textures) { setError("gtlc_material_create: null texture bindings"); return 0; }
+  std::vector<Texture*> bound;
+  for (uint32_t b = 0; b < d->textureCount; b++) {
+    const GtlcTextureBinding& tb = d->textures[b];
+    Texture* t = as<Texture>(tb.texture, TAG_TEXTURE);
+    if (!t) { setError("gtlc_material_create: binding %u has no valid texture", b); return 0; }
+    const bool okIndex = tb.paramIndex == GTLC_BIND_NORMAL || (tb.paramIndex >= 0 && tb.paramIndex + tb.componentCount <= GTLC_MATERIAL_PARAM_COUNT);
+    if (!okIndex || tb.componentCount < 1 || tb.componentCount > 3 || (tb.paramIndex == GTLC_BIND_NORMAL && tb.componentCount != 3)) { setError("gtlc_material_create: binding %u writes outside the parameter block", b); return 0; }
+    for (int k = 0; k < 3; k++) if (tb.channels[k] < 0 || tb.channels[k] > 3) { setError("gtlc_material_create: binding %u has an invalid channel", b); return 0; }
+    if (tb.wrapU < GTLC_WRAP_CLAMP || tb.wrapU > GTLC_WRAP_CLIP || tb.wrapV < GTLC_WRAP_CLAMP || tb.wrapV > GTLC_WRAP_CLIP) { setError("gtlc_material_create: binding %u has an invalid wrap mode", b); return 0; }
+    bound.push_back(t);
+  }
   Material* m = new Material(); m->tag = TAG_MATERIAL; m->scene = s; m->closure = d->closure; memcpy(m->params, d->params, sizeof(m->params));
   if (d->name) m->name = d->name;
+  if (d->textureCount) m->bindings.assign(d->textures, d->textures + d->textureCount);
+  {
+    std::lock_guard<std::mutex> dl(g_destroyMutex);
+    for (Texture* t : bound) t->refs++;
+  }
+  m->boundTextures = bound;
   std::lock_guard<std::mutex> l(s->mutex);
   s->materials.push_back(m);
   return handleOf(m);
@@ -665,6 +738,7 @@ void gtlc_material_destroy(GtlcHandle h)
     for (Mesh* mesh : s->meshes) if (mesh->material == m) mesh->material = nullptr;
     s->geometryDirty = true; s->framebufferDirty = true;
   }
+  for (Texture* t : m->boundTextures) releaseTexture(t);
   m->tag = 0; delete m;
 }
 
@@ -1026,6 +1100,7 @@ int gtlc_render(const GtlcRenderParams* params)
     DeviceScene ds; memset(&ds, 0, sizeof(ds));
     ds.fverts = s->dFverts.ptr; ds.faces = s->dFaces.ptr; ds.instO2W = s->dO2W.ptr; ds.instW2O = s->dW2O.ptr; ds.instInfo = s->dInstInfo.ptr; ds.instIds = s->dInstIds.ptr; ds.faceIds = s->dFaceIds.ptr;
     ds.matParams = s->dMatParams.ptr; ds.matClosure = s->dMatClosure.ptr; ds.matFlags = s->dMatFlags.ptr;
+    ds.textures = s->dTextures.ptr; ds.texBindings = s->dTexBindings.ptr; ds.matTexRange = s->dMatTexRange.ptr;
     ds.sphereLights = s->dSphere.ptr; ds.distantLights = s->dDistant.ptr; ds.rectLights = s->dRect.ptr; ds.diskLights = s->dDisk.ptr;
     if (dome) { ds.domeTexels = dome->dTexels; ds.domeW = dome->width; ds.domeH = dome->height; }
 
@@ -1088,7 +1163,8 @@ int gtlc_render(const GtlcRenderParams* params)
           }
           timed(K_SHADE, [&] {
             const uint32_t* permArg = sortByMaterial ? g.perm : nullptr;
-#define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) shade_kernel<MAXC, NEE, AOV><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
+#define GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, TEX) shade_kernel<MAXC, NEE, AOV, TEX><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
+#define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) do { if (s->hasTextures) GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, true); else GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, false); } while (0)
 #define GTLC_LAUNCH_SHADE(MAXC, NEE) do { if (aovMode && bounce == 0) GTLC_LAUNCH_SHADE2(MAXC, NEE, true); else GTLC_LAUNCH_SHADE2(MAXC, NEE, false); } while (0)
             const bool nee = rs.nextEventEstimation != 0;
             if (maxClosure == GTLC_CLOSURE_DIFFUSE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, false); }
@@ -1096,6 +1172,7 @@ int gtlc_render(const GtlcRenderParams* params)
             else { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_OPENPBR, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_OPENPBR, false); }
 #undef GTLC_LAUNCH_SHADE
 #undef GTLC_LAUNCH_SHADE2
+#undef GTLC_LAUNCH_SHADE3
           });
           if (rs.nextEventEstimation) {
             prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;

@@ -15,6 +15,7 @@
 // (this is ShadeRayPayload, rp_main_payload.glsl:20-47, turned inside out).
 #pragma once
 #include "closures.cuh"
+#include "textures.cuh"
 #include "traverse.cuh"
 
 namespace gtlc {
@@ -67,6 +68,9 @@ struct DeviceScene {
   const float4* __restrict__ rectLights;
   const float4* __restrict__ diskLights;
   const float4* __restrict__ domeTexels; uint32_t domeW, domeH;
+  const DeviceTexture* __restrict__ textures;        // R15: texture table
+  const DeviceTexBinding* __restrict__ texBindings;  // all materials' bindings, material-major
+  const uint2* __restrict__ matTexRange;             // (first binding, binding count) per material
 };
 
 struct PathQueue { float4* rayO; float4* rayD; float4* thr; float4* rad; uint32_t* slot; };
@@ -331,10 +335,45 @@ GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uin
   st.tangent_u = tangent; st.tangent_v = bitangent;
 }
 
+// ---- textured material inputs (R15) ------------------------------------------------------------------
+// Evaluates the material's texture bindings at the hit's uv and writes the results into `lp`, the path's private
+// copy of the parameter block.  A GTLC_BIND_NORMAL binding yields the mapped shading normal (returned through
+// `mappedNormal`; the caller installs it where the reference's *_init() would, rp_main.chit:346-357).
+GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 worldRayDir, const ShadingState& st, float* lp, V3& mappedNormal)
+{
+  const uint2 range = s.matTexRange[material];
+  bool hasNormal = false;
+  for (uint32_t b = 0; b < range.y; b++) {
+    const DeviceTexBinding& tb = s.texBindings[range.x + b];
+    const float su = st.u * tb.uvScale[0], sv = st.v * tb.uvScale[1];                   // UsdTransform2d: scale, rotate, translate
+    const float u = (su * tb.uvCos - sv * tb.uvSin) + tb.uvTranslation[0];
+    const float v = (su * tb.uvSin + sv * tb.uvCos) + tb.uvTranslation[1];
+    const int wrapU = (int) ((tb.packed >> 10) & 3u), wrapV = (int) ((tb.packed >> 12) & 3u);
+    bool clipped;
+    const V4 c = tex_lookup_float4_2d(s.textures[tb.texture], u, v, wrapU, wrapV, clipped);
+    float ch[4] = { c.x, c.y, c.z, c.w };
+    if (clipped) { ch[0] = tb.fallback[0]; ch[1] = tb.fallback[1]; ch[2] = tb.fallback[2]; ch[3] = tb.fallback[3]; }
+    if ((tb.packed >> 14) & 1u) { ch[0] = srgb_texture_to_linear(ch[0]); ch[1] = srgb_texture_to_linear(ch[1]); ch[2] = srgb_texture_to_linear(ch[2]); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) ch[k] = ch[k] * tb.scale[k] + tb.bias[k];               // UsdUVTexture scale / bias
+    const int count = (int) (tb.packed & 15u);
+    float val[3] = { 0.0f, 0.0f, 0.0f };
+    for (int k = 0; k < count && k < 3; k++) val[k] = ch[(tb.packed >> (4 + 2 * k)) & 3u];
+    if (tb.paramIndex == GTLC_BIND_NORMAL) {
+      const V3 n = normalize((st.tangent_u * val[0] + st.tangent_v * val[1]) + st.normal * val[2]);
+      mappedNormal = mdl_adapt_normal(worldRayDir, st.geom_normal, n);
+      hasNormal = true;
+    } else {
+      for (int k = 0; k < count && k < 3; k++) lp[tb.paramIndex + k] = val[k];
+    }
+  }
+  return hasNormal;
+}
+
 // ---- shade: rp_main.chit:132-493 + rp_main.miss:55-87 + rp_main.rgen:397-480 ----------------------
 // One thread per live path.  Survivors are compacted into `qout`, shadow rays appended to the shadow
 // queue, finished samples written to sampleRad[slot].
-template <int MAXC, bool NEE, bool AOV>
+template <int MAXC, bool NEE, bool AOV, bool TEX>
 __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
@@ -389,6 +428,13 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         ShadingState st; bool isFrontFace;
         setup_shading_state(s, in, inst, prim, h.y, h.z, worldRayDir, st, isFrontFace);   // chit:143
         const V3 normal = st.normal;                                                   // chit:147
+        float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT : 1];                                 // textured inputs: private parameter block
+        V3 mappedNormal = normal; bool hasMappedNormal = false;
+        if (TEX && s.matTexRange[in.material].y != 0u) {
+          for (int k = 0; k < GTLC_MATERIAL_PARAM_COUNT; k++) lp[k] = mp[k];
+          hasMappedNormal = apply_texture_bindings(s, in.material, worldRayDir, st, lp, mappedNormal);
+          mp = lp;
+        }
         uint32_t mediumIdx = (bitfield & kPayloadMediumIdxMask) >> kPayloadMediumIdxOffset; if (mediumIdx > 1u) mediumIdx = 1u;  // chit:153
         const bool thinWalled = (mflags & kMatFlagThinWalled) != 0;                    // chit:155-158
         if (mediumIdx > 0) {                                                           // chit:164-186
@@ -427,6 +473,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
         }
         st.normal = normal;                                                            // chit:346
+        if (TEX && hasMappedNormal) st.normal = mappedNormal;                          // what *_init() leaves in the state (chit:349-357)
         uint32_t eventType;
         {                                                                              // chit:361-389
           BsdfSample d;

@@ -81,13 +81,49 @@ def giDestroyScene(scene):
 
 # ---- materials (Gi.h:204-207).  The reference takes MaterialX / MDL; the binding takes the lowered
 # closure + parameter block (see gtlc.h) -- gi_cpp/Gi.cpp does the MaterialX-XML lowering. ------------
-def giCreateMaterial(scene, closure: int, params: Sequence[float], name: str = ""):
+def giCreateTexture(texels: np.ndarray):
+    """Decoded image -> texture handle.  texels[row, col, channels], row 0 = bottom; dtype uint8 (RGBA8), float16 (RGBA16F),
+    float32 with 1 channel (R32F) or 4 channels (RGBA32F).  (The reference decodes files through imgio, out of scope.)"""
+    t = S.Texture(np.ascontiguousarray(texels))
+    d = L.TextureDesc()
+    d.height, d.width = t.texels.shape[0], t.texels.shape[1]
+    d.format = t.format
+    d.texels = t.texels.ctypes.data
+    return _lib().gtlc_texture_create(C.byref(d)) or None
+
+
+def giDestroyTexture(tex):
+    _lib().gtlc_texture_destroy(tex)
+
+
+def texture_binding_c(b: "S.TextureBinding", handle) -> "L.TextureBinding":
+    c = L.TextureBinding()
+    c.paramIndex = b.param
+    c.componentCount = len(b.channels)
+    c.channels = (C.c_int32 * 3)(*(list(b.channels) + [0, 0, 0])[:3])
+    c.wrapU, c.wrapV, c.srgb = b.wrap_u, b.wrap_v, int(b.srgb)
+    c.texture = handle
+    c.fallback = (C.c_float * 4)(*b.fallback)
+    c.scale = (C.c_float * 4)(*b.scale)
+    c.bias = (C.c_float * 4)(*b.bias)
+    c.uvRotation = b.uv_rotation
+    c.uvScale = (C.c_float * 2)(*b.uv_scale)
+    c.uvTranslation = (C.c_float * 2)(*b.uv_translation)
+    return c
+
+
+def giCreateMaterial(scene, closure: int, params: Sequence[float], name: str = "", textures=(), texture_handles=()):
+    """`textures`: scenes.TextureBinding list whose .texture indexes `texture_handles`."""
     d = L.MaterialDesc()
     d.closure = closure
     d.name = name.encode() if name else None
     arr = np.zeros(48, np.float32)
     arr[:len(params)] = params
     d.params = (C.c_float * 48)(*[float(x) for x in arr])
+    if textures:
+        arr_b = (L.TextureBinding * len(textures))(*[texture_binding_c(b, texture_handles[b.texture]) for b in textures])
+        d.textures = arr_b
+        d.textureCount = len(textures)
     return _lib().gtlc_material_create(scene, C.byref(d)) or None
 
 
@@ -302,7 +338,10 @@ class BuiltScene:
     def __init__(self, desc: S.SceneDesc):
         self.desc = desc
         self.scene = giCreateScene()
-        self.materials = [giCreateMaterial(self.scene, m.closure, m.params, m.name) for m in desc.materials]
+        self.textures = [giCreateTexture(t.texels) for t in desc.textures]
+        if any(t is None for t in self.textures):
+            raise RuntimeError("giCreateTexture failed: " + giLastError())
+        self.materials = [giCreateMaterial(self.scene, m.closure, m.params, m.name, m.textures, self.textures) for m in desc.materials]
         self.meshes = []
         for m in desc.meshes:
             h = giCreateMesh(self.scene, m.vertices, m.faces, id=m.object_id, isDoubleSided=m.double_sided,
@@ -403,5 +442,7 @@ class BuiltScene:
             giDestroyDomeLight(self.dome)
         for h in self.materials:
             giDestroyMaterial(h)
+        for h in getattr(self, "textures", []):
+            giDestroyTexture(h)
         giDestroyScene(self.scene)
         self.scene = None

@@ -39,10 +39,47 @@ assert VERTEX_DTYPE.itemsize == 48
 
 
 @dataclasses.dataclass
+class Texture:
+    """Decoded image; texels[row, col, channel] with row 0 = bottom (v = 0).  uint8 -> RGBA8 unorm, float16 -> RGBA16F,
+    float32 with 1 channel -> R32F, float32 with 4 channels -> RGBA32F."""
+    texels: np.ndarray
+
+    @property
+    def format(self) -> int:
+        t = self.texels
+        if t.dtype == np.uint8:
+            return 0
+        if t.dtype == np.float16:
+            return 1
+        return 2 if (t.ndim == 2 or t.shape[2] == 1) else 3
+
+
+WRAP_CLAMP, WRAP_REPEAT, WRAP_MIRRORED_REPEAT, WRAP_CLIP = 0, 1, 2, 3
+BIND_NORMAL = -1
+
+
+@dataclasses.dataclass
+class TextureBinding:   # GtlcTextureBinding: UsdUVTexture (+ UsdTransform2d) feeding one material input
+    param: int                      # first index of the parameter block, or BIND_NORMAL
+    texture: int                    # index into SceneDesc.textures
+    channels: tuple = (0, 1, 2)     # one entry per written float
+    wrap_u: int = WRAP_REPEAT
+    wrap_v: int = WRAP_REPEAT
+    srgb: bool = False
+    fallback: tuple = (0.0, 0.0, 0.0, 1.0)
+    scale: tuple = (1.0, 1.0, 1.0, 1.0)
+    bias: tuple = (0.0, 0.0, 0.0, 0.0)
+    uv_rotation: float = 0.0
+    uv_scale: tuple = (1.0, 1.0)
+    uv_translation: tuple = (0.0, 0.0)
+
+
+@dataclasses.dataclass
 class Material:
     closure: int
     params: np.ndarray  # float32[48]
     name: str = ""
+    textures: list = dataclasses.field(default_factory=list)   # TextureBinding
 
 
 def material_diffuse(tint, name="") -> Material:
@@ -198,6 +235,7 @@ class SceneDesc:
     rect_lights: List[RectLight] = dataclasses.field(default_factory=list)
     disk_lights: List[DiskLight] = dataclasses.field(default_factory=list)
     dome_light: Optional[DomeLight] = None
+    textures: List[Texture] = dataclasses.field(default_factory=list)
 
     @property
     def triangle_count(self) -> int:
@@ -343,6 +381,82 @@ def cornell(width=512, height=512, spp=64, max_bounces=4) -> SceneDesc:
         meshes.append(Mesh(v, f, names.index(mat), np.asarray(xf, np.float32), None, True, False, i + 1, name))
     st = RenderSettings(spp=spp, maxBounces=max_bounces)
     return SceneDesc("cornell", meshes, [mats[n] for n in names], cornell_camera(), st, width, height)
+
+
+# ---- textured Cornell box (R15 test scene) ----------------------------------------------------
+def procedural_texture(kind: str, size: int = 64, seed: int = 7) -> Texture:
+    """Deterministic test images (the reference reads files through imgio; none ship with it)."""
+    y, x = np.mgrid[0:size, 0:size]
+    r = pcg32_uniform(seed, size * size * 4).reshape(size, size, 4)
+    if kind == "checker":                       # RGBA8, sRGB-encoded colours
+        c = ((x // (size // 8) + y // (size // 8)) & 1).astype(np.float32)
+        img = np.stack([0.9 * c + 0.1, 0.25 + 0.5 * (1 - c), 0.2 + 0.6 * r[..., 2], np.ones_like(c)], -1)
+        return Texture((img * 255 + 0.5).astype(np.uint8))
+    if kind == "roughness":                     # R32F scalar map
+        return Texture((0.05 + 0.9 * (0.5 + 0.5 * np.sin(x * 0.35) * np.cos(y * 0.23))).astype(np.float32)[..., None])
+    if kind == "normal":                        # RGBA8 tangent-space normals, encoded n * 0.5 + 0.5
+        nx = 0.45 * np.sin(x * 2 * np.pi * 3 / size); ny = 0.45 * np.cos(y * 2 * np.pi * 2 / size)
+        nz = np.sqrt(np.maximum(0.0, 1 - nx * nx - ny * ny))
+        img = np.stack([nx * 0.5 + 0.5, ny * 0.5 + 0.5, nz * 0.5 + 0.5, np.ones_like(nx)], -1)
+        return Texture((img * 255 + 0.5).astype(np.uint8))
+    if kind == "emission":                      # RGBA16F HDR blobs
+        d = np.exp(-(((x - size / 2) ** 2 + (y - size / 2) ** 2) / (0.08 * size * size)))
+        return Texture(np.stack([6.0 * d, 2.5 * d + 0.2 * r[..., 1], 0.5 * d, np.ones_like(d)], -1).astype(np.float16))
+    if kind == "noise":                         # RGBA32F
+        return Texture(r.astype(np.float32))
+    raise ValueError(kind)
+
+
+def assign_planar_uv(mesh: Mesh) -> None:
+    """u, v = the two object-space axes along which the mesh is largest, mapped to [-0.25, 1.25] (so wrap modes matter)."""
+    p = mesh.vertices["pos"]
+    lo, hi = p.min(0), p.max(0)
+    ax = np.argsort(-(hi - lo))[:2]
+    ax.sort()
+    ext = np.maximum(hi - lo, 1e-6)
+    v = mesh.vertices.copy()
+    v["u"] = ((p[:, ax[0]] - lo[ax[0]]) / ext[ax[0]] * 1.5 - 0.25).astype(np.float32)
+    v["v"] = ((p[:, ax[1]] - lo[ax[1]]) / ext[ax[1]] * 1.5 - 0.25).astype(np.float32)
+    mesh.vertices = v
+
+
+def textured_cornell(width=96, height=96, spp=8, max_bounces=5, nee=True) -> SceneDesc:
+    """Cornell box whose surfaces exercise every texture feature: sRGB RGBA8 + UsdTransform2d + repeat (floor), scalar R32F
+    roughness + metallic (back wall), mirrored repeat RGBA32F (left wall), clip + fallback (right wall), tangent-space normal
+    map (tall box, OpenPBR), HDR RGBA16F emission with clamp (short box)."""
+    d = cornell(width, height, spp, max_bounces)
+    for m in d.meshes:
+        assign_planar_uv(m)
+    d.textures = [procedural_texture(k) for k in ("checker", "roughness", "normal", "emission", "noise")]
+    T = TextureBinding
+    mats = list(d.materials)
+    floor = material_usd_preview_surface("FloorTex", diffuse=(0.5, 0.5, 0.5))
+    floor.textures = [T(UPS["diffuse"], 0, (0, 1, 2), WRAP_REPEAT, WRAP_REPEAT, True, uv_rotation=30.0, uv_scale=(3.0, 2.0), uv_translation=(0.13, -0.4))]
+    back = material_usd_preview_surface("BackTex", diffuse=(0.7, 0.7, 0.75), metallic=0.0)
+    back.textures = [T(UPS["roughness"], 1, (0,), WRAP_CLAMP, WRAP_REPEAT), T(UPS["metallic"], 4, (2,), scale=(1, 1, 0.9, 1), bias=(0, 0, 0.05, 0))]
+    left = material_usd_preview_surface("LeftTex", diffuse=(1, 0, 0))
+    left.textures = [T(UPS["diffuse"], 4, (1, 0, 2), WRAP_MIRRORED_REPEAT, WRAP_MIRRORED_REPEAT, uv_scale=(2.5, 2.5))]
+    right = material_usd_preview_surface("RightTex", diffuse=(0, 1, 0))
+    right.textures = [T(UPS["diffuse"], 0, (0, 1, 2), WRAP_CLIP, WRAP_CLIP, True, fallback=(0.05, 0.6, 0.1, 1.0))]
+    tall = material_openpbr("TallNormalMapped", base_color=(0.8, 0.8, 0.85), specular_roughness=0.25, base_metalness=0.6)
+    tall.textures = [T(BIND_NORMAL, 2, (0, 1, 2), scale=(2, 2, 2, 1), bias=(-1, -1, -1, 0), uv_scale=(2.0, 3.0)),
+                     T(OPBR["specular_roughness"], 1, (0,), scale=(0.5, 1, 1, 1), bias=(0.1, 0, 0, 0))]
+    short = material_usd_preview_surface("ShortGlow", diffuse=(0.3, 0.3, 0.3))
+    short.textures = [T(UPS["emissive"], 3, (0, 1, 2), WRAP_CLAMP, WRAP_CLAMP)]
+    base = len(mats)
+    mats += [floor, back, left, right, tall, short]
+    assign = {"bottomplane": 0, "backplane": 1, "leftplane": 2, "rightplane": 3, "box1": 4, "box2": 5}
+    for i, m in enumerate(d.meshes):
+        lname = m.name.lower()
+        for key, k in assign.items():
+            if key in lname:
+                d.meshes[i] = dataclasses.replace(m, material=base + k)
+    d.materials = mats
+    d.name = "textured_cornell"
+    if nee:
+        d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
+        d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
+    return d
 
 
 # ---- C2: 1M random triangles ------------------------------------------------------------------

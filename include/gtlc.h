@@ -180,10 +180,54 @@ enum {
   GTLC_OPBR_PARAM_COUNT /* 43 <= 48 */
 };
 
+/* ---- textures: the reference binds images through MDL resource tables
+ * (src/gi/impl/TextureManager.cpp:100-274) and samples them with tex_lookup_float4_2d
+ * (src/gi/shaders/mdl_interface.glsl:127-145; sampler linear / Repeat, one mip, Gi.cpp:388-392).  Here a
+ * material input is "textured" by a binding that overwrites 1..3 floats of the parameter block per hit.
+ * Decoding image files is imgio's job in the reference (out of scope): the C-ABI takes texels. */
+enum GtlcTextureFormat {
+  GTLC_TEX_RGBA8_UNORM  = 0,   /* CgpuImageFormat::R8G8B8A8Unorm (LDR files) */
+  GTLC_TEX_RGBA16_FLOAT = 1,   /* keepHdr images, 8 bytes per texel (TextureManager.cpp:135) */
+  GTLC_TEX_R32_FLOAT    = 2,   /* MDL binary float payloads (TextureManager.cpp:196) */
+  GTLC_TEX_RGBA32_FLOAT = 3
+};
+typedef struct GtlcTextureDesc {
+  uint32_t    width, height;
+  int32_t     format;          /* GtlcTextureFormat */
+  int32_t     reserved;
+  const void* texels;          /* row 0 = bottom row (v = 0), as imgio delivers images (PngDecoder.cpp:78 flips) */
+} GtlcTextureDesc;
+GTLC_API GtlcHandle gtlc_texture_create(const GtlcTextureDesc* desc);
+GTLC_API void       gtlc_texture_destroy(GtlcHandle texture);   /* deferred while a material still references it */
+
+enum GtlcTextureWrap {           /* mdl_types.glsl:117-120 */
+  GTLC_WRAP_CLAMP = 0, GTLC_WRAP_REPEAT = 1, GTLC_WRAP_MIRRORED_REPEAT = 2, GTLC_WRAP_CLIP = 3
+};
+#define GTLC_BIND_NORMAL (-1)    /* paramIndex: the value is a tangent-space normal (UsdPreviewSurface `normal`, OpenPBR
+                                    `geometry_normal`): shading normal = normalize(T x + B y + N z), then mdl_adapt_normal
+                                    (mdl_interface.glsl:238-256) */
+typedef struct GtlcTextureBinding {
+  int32_t    paramIndex;         /* first float of GtlcMaterialDesc.params that receives the value, or GTLC_BIND_NORMAL */
+  int32_t    componentCount;     /* 1..3 floats written */
+  int32_t    channels[3];        /* source channel per component: 0 r, 1 g, 2 b, 3 a */
+  int32_t    wrapU, wrapV;       /* GtlcTextureWrap.  CLIP returns `fallback` outside [0,1] (UsdUVTexture wrap "black" /
+                                    MaterialX addressmode "constant") */
+  int32_t    srgb;               /* 1: the r, g, b channels are sRGB-encoded ("srgb_texture", MtlxDocumentPatcher.cpp:244-246) */
+  GtlcHandle texture;
+  float      fallback[4];        /* UsdUVTexture.fallback / MaterialX image `default` (rgba) */
+  float      scale[4], bias[4];  /* UsdUVTexture: value = texel * scale + bias, per source channel */
+  float      uvRotation;         /* UsdTransform2d: degrees, counter-clockwise */
+  float      uvScale[2], uvTranslation[2];   /* uv' = rotate(uv * scale) + translation */
+  float      reserved;
+} GtlcTextureBinding;
+
 typedef struct GtlcMaterialDesc {
   int32_t     closure;                           /* GTLC_CLOSURE_* */
   const char* name;                              /* may be NULL */
   float       params[GTLC_MATERIAL_PARAM_COUNT]; /* see enums above */
+  const GtlcTextureBinding* textures;            /* optional; applied in order per shaded hit */
+  uint32_t    textureCount;
+  uint32_t    reserved;
 } GtlcMaterialDesc;
 
 /* Fill `desc` with the closure's spec defaults (UsdPreviewSurface spec / open_pbr_surface.mtlx:4-97). */

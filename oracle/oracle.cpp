@@ -309,16 +309,23 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
   const InstanceDesc& in = s.instances[hit.inst];
   bool isLeftHanded = (in.flags & 1u) != 0;                               // :137
   bool isDoubleSided = (in.flags & 2u) != 0;                              // :138
-  const Material& mat = s.materials[in.material];
+  const Material& base = s.materials[in.material];
 
   State st; bool isFrontFace;
   setup_shading_state(s, hit, worldRayDir, st, isFrontFace);              // :143
   const V3 normal = st.normal;                                            // :147
+  // R15: textured inputs are evaluated once per hit into a private copy of the parameter block (the reference
+  // re-evaluates them inside every generated mdl_* function; same values)
+  Material mat = base;
+  V3 mappedNormal = normal; bool hasMappedNormal = false;
+  if (!s.materialTextures.empty() && !s.materialTextures[in.material].empty())
+    hasMappedNormal = apply_texture_bindings(s.textures, s.materialTextures[in.material], st.text_coords.x, st.text_coords.y, worldRayDir,
+                                             st.geom_normal, st.normal, st.tangent_u, st.tangent_v, mat.p, mappedNormal);
 
   V3 throughput = p.throughput;
   V3 radiance = p.radiance;
   uint32_t mediumIdx = payloadGetMediumIdx(p);                            // :153
-  bool thinWalled = mat_is_thin_walled(mat);                              // :155-158
+  bool thinWalled = mat_is_thin_walled(base);                             // :155-158 (compile-time flag of the material)
 
   if (mediumIdx > 0) {                                                    // :164-186
     float distance = hit.t * c.ubo.metersPerSceneUnit;
@@ -345,7 +352,7 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
     aov->instanceId = in.instanceId;                                      // :243
     aov->doubleSided = isDoubleSided;                                     // :247
     aov->posNormal = (normal + v3(1.0f)) * 0.5f;                          // :252
-    aov->cutoutOpacity = (mat_cutout_opacity(mat) < 1.0f) ? mat_cutout_opacity(mat) : -1.0f;
+    aov->cutoutOpacity = (mat_cutout_opacity(base) < 1.0f) ? mat_cutout_opacity(mat) : -1.0f;
     aov->albedo = bsdf_albedo(mat, -worldRayDir, st);                     // :264-280 (front-face BSDF; no backface BSDFs exist here)
   }
 
@@ -362,6 +369,7 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
     if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
   }
   st.normal = normal;                                                     // :346
+  if (hasMappedNormal) st.normal = mappedNormal;                          // what *_init() leaves in the state (:349-357)
 
   uint32_t eventType;
   {                                                                       // :361-389
@@ -497,6 +505,7 @@ struct OrcSceneDesc {
   const float* domeTexels; uint32_t domeW, domeH;
   float domeRotation[4]; float domeEmission[3]; uint32_t pad;
   const int32_t* faceIds;   // optional: one per face of the global face array (GiMeshDesc.faceIds)
+  const GtlcTextureDesc* textures; uint32_t textureCount; uint32_t pad2;   // R15; GtlcTextureBinding.texture = 1-based index
 };
 
 struct OrcRenderDesc {
@@ -518,6 +527,15 @@ void* orc_scene_create(const OrcSceneDesc* d)
   for (uint32_t i = 0; i < d->materialCount; i++) {
     Material m; m.closure = d->materials[i].closure; memcpy(m.p, d->materials[i].params, sizeof(m.p));
     s->materials.push_back(m);
+    const GtlcMaterialDesc& md = d->materials[i];
+    s->materialTextures.emplace_back(md.textures, md.textures + (md.textures ? md.textureCount : 0));
+  }
+  for (uint32_t i = 0; i < d->textureCount; i++) {
+    const GtlcTextureDesc& td = d->textures[i];
+    Texture t; t.width = td.width; t.height = td.height; t.format = td.format;
+    const size_t bpt = td.format == GTLC_TEX_RGBA8_UNORM ? 4 : td.format == GTLC_TEX_RGBA16_FLOAT ? 8 : td.format == GTLC_TEX_R32_FLOAT ? 4 : 16;
+    t.data.assign((const uint8_t*) td.texels, (const uint8_t*) td.texels + (size_t) td.width * td.height * bpt);
+    s->textures.push_back(t);
   }
   if (d->sphereLightCount) s->sphereLights.assign(d->sphereLights, d->sphereLights + d->sphereLightCount);
   if (d->distantLightCount) s->distantLights.assign(d->distantLights, d->distantLights + d->distantLightCount);
@@ -796,3 +814,16 @@ extern "C" uint32_t orc_lbvh8_build(const float* tris, uint32_t n, uint32_t* nod
 {
   return orc_lbvh8::build(tris, n, nodes, outTris, depth);
 }
+
+// KAT access to the texture restatement: one lookup of `tex` at (u, v); out = rgba, returns 1 when clipped.
+extern "C" int orc_tex_lookup(const GtlcTextureDesc* tex, float u, float v, int wrapU, int wrapV, float* out)
+{
+  Texture t; t.width = tex->width; t.height = tex->height; t.format = tex->format;
+  const size_t bpt = tex->format == GTLC_TEX_RGBA8_UNORM ? 4 : tex->format == GTLC_TEX_RGBA16_FLOAT ? 8 : tex->format == GTLC_TEX_R32_FLOAT ? 4 : 16;
+  t.data.assign((const uint8_t*) tex->texels, (const uint8_t*) tex->texels + (size_t) tex->width * tex->height * bpt);
+  bool clipped;
+  V4 r = tex_lookup_float4_2d(t, u, v, wrapU, wrapV, clipped);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+  return clipped ? 1 : 0;
+}
+extern "C" float orc_srgb_texture_to_linear(float c) { return srgb_texture_to_linear(c); }

@@ -19,8 +19,20 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
 
+class TextureDesc(C.Structure):  # GtlcTextureDesc
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("reserved", C.c_int32), ("texels", C.c_void_p)]
+
+
+class TextureBinding(C.Structure):  # GtlcTextureBinding
+    _fields_ = [("paramIndex", C.c_int32), ("componentCount", C.c_int32), ("channels", C.c_int32 * 3), ("wrapU", C.c_int32),
+                ("wrapV", C.c_int32), ("srgb", C.c_int32), ("texture", C.c_uint64), ("fallback", C.c_float * 4),
+                ("scale", C.c_float * 4), ("bias", C.c_float * 4), ("uvRotation", C.c_float), ("uvScale", C.c_float * 2),
+                ("uvTranslation", C.c_float * 2), ("reserved", C.c_float)]
+
+
 class MaterialDesc(C.Structure):  # GtlcMaterialDesc
-    _fields_ = [("closure", C.c_int32), ("name", C.c_char_p), ("params", C.c_float * 48)]
+    _fields_ = [("closure", C.c_int32), ("name", C.c_char_p), ("params", C.c_float * 48),
+                ("textures", C.POINTER(TextureBinding)), ("textureCount", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class CameraDesc(C.Structure):  # GtlcCameraDesc
@@ -67,7 +79,8 @@ class SceneDescC(C.Structure):
                 ("rectLights", C.c_void_p), ("rectLightCount", C.c_uint32),
                 ("diskLights", C.c_void_p), ("diskLightCount", C.c_uint32),
                 ("domeTexels", C.c_void_p), ("domeW", C.c_uint32), ("domeH", C.c_uint32),
-                ("domeRotation", C.c_float * 4), ("domeEmission", C.c_float * 3), ("pad", C.c_uint32), ("faceIds", C.c_void_p)]
+                ("domeRotation", C.c_float * 4), ("domeEmission", C.c_float * 3), ("pad", C.c_uint32), ("faceIds", C.c_void_p),
+                ("textures", C.POINTER(TextureDesc)), ("textureCount", C.c_uint32), ("pad2", C.c_uint32)]
 
 
 class AovDescC(C.Structure):
@@ -225,11 +238,29 @@ class OracleScene:
         self.vertices = np.ascontiguousarray(np.concatenate(verts))
         self.faces = np.ascontiguousarray(np.concatenate(faces).reshape(-1, 3))
         self.instances = np.ascontiguousarray(np.concatenate(inst))
+        self._keep = []
         self.mats = (MaterialDesc * len(desc.materials))()
         for i, m in enumerate(desc.materials):
             self.mats[i].closure = m.closure
             self.mats[i].name = None
             self.mats[i].params = (C.c_float * 48)(*[float(x) for x in m.params])
+            if getattr(m, "textures", None):
+                arr = (TextureBinding * len(m.textures))()
+                for k, b in enumerate(m.textures):
+                    arr[k].paramIndex = b.param
+                    arr[k].componentCount = len(b.channels)
+                    arr[k].channels = (C.c_int32 * 3)(*(list(b.channels) + [0, 0, 0])[:3])
+                    arr[k].wrapU, arr[k].wrapV, arr[k].srgb = b.wrap_u, b.wrap_v, int(b.srgb)
+                    arr[k].texture = b.texture + 1          # 1-based index into SceneDesc.textures
+                    arr[k].fallback = (C.c_float * 4)(*b.fallback)
+                    arr[k].scale = (C.c_float * 4)(*b.scale)
+                    arr[k].bias = (C.c_float * 4)(*b.bias)
+                    arr[k].uvRotation = b.uv_rotation
+                    arr[k].uvScale = (C.c_float * 2)(*b.uv_scale)
+                    arr[k].uvTranslation = (C.c_float * 2)(*b.uv_translation)
+                self._keep.append(arr)
+                self.mats[i].textures = arr
+                self.mats[i].textureCount = len(m.textures)
         self.sp, self.di, self.re, self.dk = light_arrays(desc)
         d = SceneDescC()
         d.vertices = self.vertices.ctypes.data
@@ -254,6 +285,16 @@ class OracleScene:
             d.domeH, d.domeW = self.dome.shape[0], self.dome.shape[1]
             d.domeRotation = (C.c_float * 4)(*desc.dome_light.rotation)
             d.domeEmission = (C.c_float * 3)(*desc.dome_light.base_emission)
+        if getattr(desc, "textures", None):
+            self.texs = (TextureDesc * len(desc.textures))()
+            for i, t in enumerate(desc.textures):
+                a = np.ascontiguousarray(t.texels)
+                self._keep.append(a)
+                self.texs[i].height, self.texs[i].width = a.shape[0], a.shape[1]
+                self.texs[i].format = t.format
+                self.texs[i].texels = a.ctypes.data
+            d.textures = self.texs
+            d.textureCount = len(desc.textures)
         self.handle = L.orc_scene_create(C.byref(d))
 
     def close(self):
@@ -365,3 +406,24 @@ def lbvh8_build(tris_rank_order):
     depth = C.c_uint32(0)
     count = L.orc_lbvh8_build(t.ctypes.data, n, nodes.ctypes.data, out.ctypes.data, C.byref(depth))
     return nodes[:count * 20].view(np.uint8).copy(), out[:n * 12].copy(), int(depth.value)
+
+
+def tex_lookup(texture, u, v, wrap_u=1, wrap_v=1):
+    """One tex_lookup_float4_2d of the oracle's restatement; returns (rgba float32[4], clipped)."""
+    L = lib()
+    a = np.ascontiguousarray(texture.texels)
+    d = TextureDesc()
+    d.height, d.width = a.shape[0], a.shape[1]
+    d.format = texture.format
+    d.texels = a.ctypes.data
+    out = (C.c_float * 4)()
+    L.orc_tex_lookup.argtypes = [C.POINTER(TextureDesc), C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    clipped = L.orc_tex_lookup(C.byref(d), float(u), float(v), int(wrap_u), int(wrap_v), out)
+    return np.array(out[:], np.float32), bool(clipped)
+
+
+def srgb_texture_to_linear(c):
+    L = lib()
+    L.orc_srgb_texture_to_linear.restype = C.c_float
+    L.orc_srgb_texture_to_linear.argtypes = [C.c_float]
+    return float(L.orc_srgb_texture_to_linear(float(c)))

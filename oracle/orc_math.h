@@ -22,6 +22,7 @@ static const float PI = 3.1415926535897932384626433832795f; // common.glsl:9
 struct V2 { float x, y; };
 struct V3 { float x, y, z; };
 struct V4 { float x, y, z, w; };
+static inline V4 v4(float x, float y, float z, float w) { V4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 static inline V3 v3(float x, float y, float z) { V3 r = { x, y, z }; return r; }
 static inline V3 v3(float s) { V3 r = { s, s, s }; return r; }

@@ -9,6 +9,7 @@
 // break "equal t -> smaller (instanceIndex, primitiveId)".
 #pragma once
 #include "orc_bsdf.h"
+#include "orc_texture.h"
 #include <algorithm>
 #include <vector>
 
@@ -112,6 +113,8 @@ struct Scene {
   std::vector<InstanceDesc> instances;
   std::vector<float> worldToObject;   // 12 per instance
   std::vector<Material> materials;
+  std::vector<Texture> textures;                                   // R15
+  std::vector<std::vector<GtlcTextureBinding>> materialTextures;   // per material; .texture = 1-based index into `textures`
   std::vector<SphereLight> sphereLights;
   std::vector<DistantLight> distantLights;
   std::vector<RectLight> rectLights;
