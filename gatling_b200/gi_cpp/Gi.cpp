@@ -5,8 +5,10 @@
 // Material lowering: the reference hands a MaterialX document to `mc`, which patches it, generates MDL
 // and compiles that with the MDL SDK into per-material GLSL (src/mc, out of scope -- closed SDK).
 // Here MaterialX XML is lowered directly to a closure id + parameter block for the two surface shaders
-// the configs name (UsdPreviewSurface, open_pbr_surface); only constant inputs are honoured, connected
-// inputs (textures, primvar readers) fall back to the node's default with a warning.
+// the configs name (UsdPreviewSurface, open_pbr_surface).  Inputs connected to UsdUVTexture / image nodes
+// (optionally through UsdTransform2d and normalmap) become texture bindings of the C-ABI material; what the
+// reference's patcher decides about colour spaces (MtlxDocumentPatcher.cpp:201-253) is applied here.  Other
+// connected inputs (procedural graphs, primvar readers other than `st`) keep the node's default with a warning.
 #include <gtl/gi/Gi.h>
 
 #include "../../include/gtlc.h"
@@ -17,6 +19,7 @@
 #include <fstream>
 #include <mutex>
 #include <string>
+#include <vector>
 
 namespace gtl
 {
@@ -48,7 +51,7 @@ namespace gtl
     template <typename T> T* wrap(GtlcHandle h) { if (!h) { logError(gtlc_last_error()); return nullptr; } T* o = new T; o->h = h; return o; }
 
     // ---- minimal MaterialX XML scanning -------------------------------------------------------
-    struct XmlInput { std::string name, value; bool connected; };
+    struct XmlInput { std::string name, value, nodename, output, colorspace; bool connected; };
 
     bool attr(const std::string& tag, const char* key, std::string& out)
     {
@@ -85,7 +88,8 @@ namespace gtl
           XmlInput in; in.connected = false;
           std::string dummy;
           if (attr(tag, "name", in.name)) {
-            if (!attr(tag, "value", in.value)) in.connected = attr(tag, "nodename", dummy) || attr(tag, "nodegraph", dummy) || attr(tag, "output", dummy) || attr(tag, "interfacename", dummy);
+            attr(tag, "nodename", in.nodename); attr(tag, "output", in.output); attr(tag, "colorspace", in.colorspace);
+            if (!attr(tag, "value", in.value)) in.connected = !in.nodename.empty() || attr(tag, "nodegraph", dummy) || !in.output.empty() || attr(tag, "interfacename", dummy);
             inputs.push_back(in);
           }
           q = e;
@@ -107,6 +111,102 @@ namespace gtl
       return n;
     }
 
+
+    // Finds the element <category name="nodeName" ...> (any category except input/output) and collects its inputs.
+    bool findNodeByName(const std::string& xml, const std::string& nodeName, std::string& category, std::vector<XmlInput>& inputs)
+    {
+      const std::string key = " name=\"" + nodeName + "\"";
+      size_t p = 0;
+      while ((p = xml.find(key, p)) != std::string::npos) {
+        size_t lt = xml.rfind('<', p);
+        if (lt == std::string::npos) return false;
+        size_t ce = lt + 1;
+        while (ce < xml.size() && xml[ce] != ' ' && xml[ce] != '\t' && xml[ce] != '\n' && xml[ce] != '\r' && xml[ce] != '>') ce++;
+        category = xml.substr(lt + 1, ce - lt - 1);
+        if (category == "input" || category == "output" || xml.find('>', lt) < p) { p += key.size(); continue; }
+        std::string rest = xml.substr(lt);     // re-use the category scanner on the tail that starts at this element
+        return findShaderNode(rest, category.c_str(), inputs);
+      }
+      return false;
+    }
+
+    const XmlInput* findInput(const std::vector<XmlInput>& inputs, const char* name)
+    {
+      for (const XmlInput& in : inputs) if (in.name == name) return &in;
+      return nullptr;
+    }
+
+    int wrapModeOf(const std::string& v)
+    {
+      if (v == "black" || v == "constant") return GTLC_WRAP_CLIP;
+      if (v == "clamp") return GTLC_WRAP_CLAMP;
+      if (v == "mirror") return GTLC_WRAP_MIRRORED_REPEAT;
+      return GTLC_WRAP_REPEAT;     // "repeat" / "periodic" / "useMetadata" (ND_UsdUVTexture default: periodic)
+    }
+
+    // Follows a connected surface-shader input to a texture node.  Returns false if the upstream graph is not
+    // (normalmap ->) UsdUVTexture | image (-> UsdTransform2d -> st reader).
+    bool lowerTextureInput(const std::string& xml, const XmlInput& in, int paramIndex, int count, bool upsSrgbInput,
+                           GtlcTextureBinding& b, std::string& file)
+    {
+      std::string category; std::vector<XmlInput> node;
+      if (in.nodename.empty() || !findNodeByName(xml, in.nodename, category, node)) return false;
+      memset(&b, 0, sizeof(b));
+      for (int k = 0; k < 4; k++) { b.scale[k] = 1.0f; b.bias[k] = 0.0f; }
+      b.fallback[3] = 1.0f; b.uvScale[0] = b.uvScale[1] = 1.0f;
+      b.paramIndex = paramIndex; b.componentCount = count;
+      std::string output = in.output;
+      bool decodeNormal = false;
+      if (category == "normalmap") {                       // MaterialX normalmap decodes value * 2 - 1 itself
+        const XmlInput* src = findInput(node, "in");
+        if (!src || src->nodename.empty()) return false;
+        output = src->output; decodeNormal = true;
+        std::string up = src->nodename;
+        if (!findNodeByName(xml, up, category, node)) return false;
+      }
+      const bool usdUv = category == "UsdUVTexture";
+      if (!usdUv && category != "image") return false;
+      const XmlInput* fileIn = findInput(node, "file");
+      if (!fileIn || fileIn->value.empty()) return false;
+      file = fileIn->value;
+      float v[4];
+      if (usdUv) {
+        if (const XmlInput* i = findInput(node, "wrapS")) b.wrapU = wrapModeOf(i->value); else b.wrapU = GTLC_WRAP_REPEAT;
+        if (const XmlInput* i = findInput(node, "wrapT")) b.wrapV = wrapModeOf(i->value); else b.wrapV = GTLC_WRAP_REPEAT;
+        if (const XmlInput* i = findInput(node, "fallback")) if (parseFloats(i->value, v, 4) == 4) memcpy(b.fallback, v, 16);
+        if (const XmlInput* i = findInput(node, "scale")) if (parseFloats(i->value, v, 4) == 4) memcpy(b.scale, v, 16);
+        if (const XmlInput* i = findInput(node, "bias")) if (parseFloats(i->value, v, 4) == 4) memcpy(b.bias, v, 16);
+        // _PatchUsdUVTextureColorSpaces (MtlxDocumentPatcher.cpp:201-253): an explicit colorspace on the file input wins,
+        // then sourceColorSpace, then "auto" = sRGB for the three UsdPreviewSurface colour inputs
+        std::string cs = "auto";
+        if (const XmlInput* i = findInput(node, "sourceColorSpace")) cs = i->value;
+        if (!fileIn->colorspace.empty()) b.srgb = fileIn->colorspace == "srgb_texture";
+        else b.srgb = (cs == "sRGB") || (cs == "auto" && upsSrgbInput);
+      } else {
+        if (const XmlInput* i = findInput(node, "uaddressmode")) b.wrapU = wrapModeOf(i->value); else b.wrapU = GTLC_WRAP_REPEAT;
+        if (const XmlInput* i = findInput(node, "vaddressmode")) b.wrapV = wrapModeOf(i->value); else b.wrapV = GTLC_WRAP_REPEAT;
+        if (const XmlInput* i = findInput(node, "default")) { int n = parseFloats(i->value, v, 4); for (int k = 0; k < n; k++) b.fallback[k] = v[k]; if (n == 1) b.fallback[1] = b.fallback[2] = v[0]; }
+        b.srgb = fileIn->colorspace == "srgb_texture";
+      }
+      if (decodeNormal) for (int k = 0; k < 3; k++) { b.bias[k] = b.bias[k] * 2.0f - 1.0f; b.scale[k] *= 2.0f; }
+      // which channels feed the input
+      if (output == "r" || output == "g" || output == "b" || output == "a") { const int c = output == "r" ? 0 : output == "g" ? 1 : output == "b" ? 2 : 3; b.channels[0] = b.channels[1] = b.channels[2] = c; }
+      else { b.channels[0] = 0; b.channels[1] = count > 1 ? 1 : 0; b.channels[2] = count > 2 ? 2 : 0; }
+      // texture coordinates: UsdTransform2d in front of the st reader
+      const XmlInput* st = findInput(node, usdUv ? "st" : "texcoord");
+      if (st && !st->nodename.empty()) {
+        std::string c2; std::vector<XmlInput> xf;
+        if (findNodeByName(xml, st->nodename, c2, xf) && c2 == "UsdTransform2d") {
+          if (const XmlInput* i = findInput(xf, "rotation")) if (parseFloats(i->value, v, 1) == 1) b.uvRotation = v[0];
+          if (const XmlInput* i = findInput(xf, "scale")) if (parseFloats(i->value, v, 2) == 2) { b.uvScale[0] = v[0]; b.uvScale[1] = v[1]; }
+          if (const XmlInput* i = findInput(xf, "translation")) if (parseFloats(i->value, v, 2) == 2) { b.uvTranslation[0] = v[0]; b.uvTranslation[1] = v[1]; }
+        }
+      }
+      return true;
+    }
+
+    struct LoweredTextures { std::vector<GtlcTextureBinding> bindings; std::vector<std::string> files; };
+
     struct Slot { const char* name; int index; int count; };
     const Slot kUpsSlots[] = {
       { "diffuseColor", GTLC_UPS_DIFFUSE_R, 3 }, { "emissiveColor", GTLC_UPS_EMISSIVE_R, 3 }, { "useSpecularWorkflow", GTLC_UPS_USE_SPECULAR_WORKFLOW, 1 },
@@ -125,34 +225,102 @@ namespace gtl
       { "thin_film_ior", GTLC_OPBR_THIN_FILM_IOR, 1 }, { "geometry_opacity", GTLC_OPBR_GEOMETRY_OPACITY, 1 }, { "geometry_thin_walled", GTLC_OPBR_GEOMETRY_THIN_WALLED, 1 },
       { "subsurface_weight", GTLC_OPBR_SUBSURFACE_WEIGHT, 1 }, { "subsurface_color", GTLC_OPBR_SUBSURFACE_COLOR_R, 3 } };
 
-    template <size_t N> void applyInputs(const std::vector<XmlInput>& inputs, const Slot (&slots)[N], GtlcMaterialDesc& d, const char* matName)
+    template <size_t N> void applyInputs(const std::string& xml, const std::vector<XmlInput>& inputs, const Slot (&slots)[N], const char* normalInput, bool ups,
+                                         GtlcMaterialDesc& d, const char* matName, LoweredTextures* tex)
     {
       for (const XmlInput& in : inputs) {
         const Slot* slot = nullptr;
         for (const Slot& s : slots) if (in.name == s.name) { slot = &s; break; }
-        if (!slot) continue;   // inputs the closures do not model (normal, displacement, occlusion, ...)
-        if (in.connected) { fprintf(stderr, "[gi] warning: material '%s': input '%s' is connected (texture/primvar); using the default value\n", matName ? matName : "", in.name.c_str()); continue; }
+        const bool isNormal = in.name == normalInput;
+        if (!slot && !isNormal) continue;   // inputs the closures do not model (displacement, occlusion, ...)
+        if (in.connected) {
+          GtlcTextureBinding b; std::string file;
+          const bool srgbInput = ups && (in.name == "diffuseColor" || in.name == "emissiveColor" || in.name == "specularColor");
+          if (tex && lowerTextureInput(xml, in, isNormal ? GTLC_BIND_NORMAL : slot->index, isNormal ? 3 : slot->count, srgbInput, b, file)) { tex->bindings.push_back(b); tex->files.push_back(file); }
+          else fprintf(stderr, "[gi] warning: material '%s': input '%s' is connected to a graph this build cannot lower; using the default value\n", matName ? matName : "", in.name.c_str());
+          continue;
+        }
+        if (isNormal) continue;
         float v[4];
         if (parseFloats(in.value, v, slot->count) == slot->count) memcpy(&d.params[slot->index], v, sizeof(float) * slot->count);
       }
     }
+
+    bool lowerMaterial(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out, LoweredTextures* tex)
+    {
+      std::string xml(mtlxSrc ? mtlxSrc : "");
+      std::vector<XmlInput> inputs;
+      if (findShaderNode(xml, "UsdPreviewSurface", inputs)) {
+        gtlc_material_desc_defaults(GTLC_CLOSURE_USD_PREVIEW_SURFACE, out);
+        applyInputs(xml, inputs, kUpsSlots, "normal", true, *out, name, tex);
+      } else if (findShaderNode(xml, "open_pbr_surface", inputs)) {
+        gtlc_material_desc_defaults(GTLC_CLOSURE_OPENPBR, out);
+        applyInputs(xml, inputs, kOpbrSlots, "geometry_normal", false, *out, name, tex);
+      } else {
+        return false;
+      }
+      out->name = name;
+      return true;
+    }
+
+    // ---- image files: imgio is out of scope; the facade decodes binary PPM (P6, 8 bit) and PFM itself ----
+    bool readFileBytes(const char* path, std::string& bytes)
+    {
+      bytes.clear();
+      if (s_assetReader) {
+        GiAsset* a = s_assetReader->open(path);
+        if (a) { bytes.assign((const char*) s_assetReader->data(a), s_assetReader->size(a)); s_assetReader->close(a); }
+      }
+      if (bytes.empty()) { std::ifstream f(path, std::ios::binary); bytes.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>()); }
+      return !bytes.empty();
+    }
+
+    // rows come out bottom-first (v = 0), as the reference's decoders deliver them (PngDecoder.cpp:78)
+    GtlcHandle loadTextureFile(const char* path)
+    {
+      std::string bytes;
+      if (!readFileBytes(path, bytes) || bytes.size() < 8) return 0;
+      int w = 0, h = 0, maxval = 0, consumed = 0; float scale = 0.0f; char magic[3] = { 0, 0, 0 };
+      GtlcTextureDesc td; memset(&td, 0, sizeof(td));
+      if (bytes[0] == 'P' && bytes[1] == '6') {
+        if (sscanf(bytes.c_str(), "%2s %d %d %d%n", magic, &w, &h, &maxval, &consumed) != 4 || w <= 0 || h <= 0 || maxval != 255) return 0;
+        const size_t off = (size_t) consumed + 1;
+        if (bytes.size() < off + (size_t) w * h * 3) return 0;
+        std::vector<uint8_t> rgba((size_t) w * h * 4);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+          const uint8_t* s = (const uint8_t*) bytes.data() + off + ((size_t) (h - 1 - y) * w + x) * 3;     // PPM rows run top to bottom
+          uint8_t* d = &rgba[((size_t) y * w + x) * 4];
+          d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = 255;
+        }
+        td.width = (uint32_t) w; td.height = (uint32_t) h; td.format = GTLC_TEX_RGBA8_UNORM; td.texels = rgba.data();
+        return gtlc_texture_create(&td);
+      }
+      if (bytes[0] == 'P' && (bytes[1] == 'F' || bytes[1] == 'f')) {
+        if (sscanf(bytes.c_str(), "%2s %d %d %f%n", magic, &w, &h, &scale, &consumed) != 4 || w <= 0 || h <= 0 || scale >= 0.0f) return 0;   // little endian only
+        const int ch = bytes[1] == 'F' ? 3 : 1;
+        const size_t off = (size_t) consumed + 1;
+        if (bytes.size() < off + (size_t) w * h * ch * 4) return 0;
+        const float* src = reinterpret_cast<const float*>(bytes.data() + off);     // PFM rows already run bottom to top
+        std::vector<float> texels((size_t) w * h * (ch == 3 ? 4 : 1));
+        for (size_t i = 0; i < (size_t) w * h; i++) {
+          if (ch == 1) texels[i] = src[i];
+          else { texels[i * 4 + 0] = src[i * 3 + 0]; texels[i * 4 + 1] = src[i * 3 + 1]; texels[i * 4 + 2] = src[i * 3 + 2]; texels[i * 4 + 3] = 1.0f; }
+        }
+        td.width = (uint32_t) w; td.height = (uint32_t) h; td.format = ch == 3 ? GTLC_TEX_RGBA32_FLOAT : GTLC_TEX_R32_FLOAT; td.texels = texels.data();
+        return gtlc_texture_create(&td);
+      }
+      return 0;
+    }
   }
 
-  // Exposed for tests: lowers MaterialX XML to a closure + parameter block.  Returns false if no supported shader node is present.
-  bool giLowerMtlxToClosure(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out)
+  // Exposed for tests: lowers MaterialX XML to a closure + parameter block (constant inputs only / with the texture
+  // bindings and the image files they reference).  Returns false if no supported shader node is present.
+  bool giLowerMtlxToClosure(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out) { return lowerMaterial(mtlxSrc, name, out, nullptr); }
+  bool giLowerMtlxToClosureWithTextures(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out, std::vector<GtlcTextureBinding>* bindings, std::vector<std::string>* files)
   {
-    std::string xml(mtlxSrc ? mtlxSrc : "");
-    std::vector<XmlInput> inputs;
-    if (findShaderNode(xml, "UsdPreviewSurface", inputs)) {
-      gtlc_material_desc_defaults(GTLC_CLOSURE_USD_PREVIEW_SURFACE, out);
-      applyInputs(inputs, kUpsSlots, *out, name);
-    } else if (findShaderNode(xml, "open_pbr_surface", inputs)) {
-      gtlc_material_desc_defaults(GTLC_CLOSURE_OPENPBR, out);
-      applyInputs(inputs, kOpbrSlots, *out, name);
-    } else {
-      return false;
-    }
-    out->name = name;
+    LoweredTextures t;
+    if (!lowerMaterial(mtlxSrc, name, out, &t)) return false;
+    *bindings = t.bindings; *files = t.files;
     return true;
   }
 
@@ -175,9 +343,20 @@ namespace gtl
   GiMaterial* giCreateMaterialFromMtlxStr(GiScene* scene, const char* name, const char* mtlxSrc)
   {
     if (!scene) return nullptr;
-    GtlcMaterialDesc d;
-    if (!giLowerMtlxToClosure(mtlxSrc, name, &d)) { logError(std::string("material '") + (name ? name : "") + "': no UsdPreviewSurface / open_pbr_surface node found (other MaterialX shading models need the mc/MDL path, out of scope)"); return nullptr; }
-    return wrap<GiMaterial>(gtlc_material_create(scene->h, &d));
+    GtlcMaterialDesc d; LoweredTextures t;
+    if (!lowerMaterial(mtlxSrc, name, &d, &t)) { logError(std::string("material '") + (name ? name : "") + "': no UsdPreviewSurface / open_pbr_surface node found (other MaterialX shading models need the mc/MDL path, out of scope)"); return nullptr; }
+    // images: a file that cannot be decoded drops its binding (the input keeps its constant), like the reference's
+    // 1x1 black fallback image keeps rendering going (TextureManager.cpp:245-262)
+    std::vector<GtlcTextureBinding> bound; std::vector<GtlcHandle> textures;
+    for (size_t i = 0; i < t.bindings.size(); i++) {
+      GtlcHandle h = loadTextureFile(t.files[i].c_str());
+      if (!h) { fprintf(stderr, "[gi] warning: material '%s': failed to read image %s (this build decodes binary .ppm / .pfm; imgio is out of scope)\n", name ? name : "", t.files[i].c_str()); continue; }
+      t.bindings[i].texture = h; bound.push_back(t.bindings[i]); textures.push_back(h);
+    }
+    d.textures = bound.empty() ? nullptr : bound.data(); d.textureCount = (uint32_t) bound.size();
+    GiMaterial* m = wrap<GiMaterial>(gtlc_material_create(scene->h, &d));
+    for (GtlcHandle h : textures) gtlc_texture_destroy(h);     // the material holds its own references
+    return m;
   }
   GiMaterial* giCreateMaterialFromMtlxDoc(GiScene* scene, const char* name, const std::shared_ptr<void> doc)
   {

@@ -2,6 +2,7 @@
 // GiMeshDesc with std::vector references, giRender, giGetRenderBufferMem.
 //   gi_facade_main lower            -> CPU only: MaterialX lowering checks, prints "lower ok"
 //   gi_facade_main render out.bin   -> GPU: renders a 48x32 spp 4 two-material scene, writes float32 RGBA
+//   gi_facade_main render out.bin checker.ppm -> same, the floor's diffuseColor read from the image (UsdUVTexture + UsdTransform2d)
 #include <gtl/gi/Gi.h>
 #include "../../include/gtlc.h"
 
@@ -11,7 +12,10 @@
 #include <string>
 #include <vector>
 
-namespace gtl { bool giLowerMtlxToClosure(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out); }
+namespace gtl {
+  bool giLowerMtlxToClosure(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out);
+  bool giLowerMtlxToClosureWithTextures(const char* mtlxSrc, const char* name, GtlcMaterialDesc* out, std::vector<GtlcTextureBinding>* bindings, std::vector<std::string>* files);
+}
 using namespace gtl;
 
 static const char* kUps =
@@ -33,8 +37,61 @@ static const char* kEmissive =
   "<materialx version=\"1.38\"><UsdPreviewSurface name=\"L\" type=\"surfaceshader\"><input name=\"diffuseColor\" type=\"color3\" value=\"0,0,0\"/>"
   "<input name=\"emissiveColor\" type=\"color3\" value=\"6, 5, 4\"/></UsdPreviewSurface></materialx>";
 
+// what hdMtlx emits for a UsdPreviewSurface network with UsdUVTexture / UsdTransform2d / UsdPrimvarReader_float2 prims
+static std::string texturedUps(const char* file)
+{
+  return std::string("<materialx version=\"1.38\">\n"
+    "  <UsdPrimvarReader name=\"stReader\" type=\"vector2\"><input name=\"varname\" type=\"string\" value=\"st\" /></UsdPrimvarReader>\n"
+    "  <UsdTransform2d name=\"xf\" type=\"vector2\"><input name=\"in\" type=\"vector2\" nodename=\"stReader\" />"
+    "<input name=\"rotation\" type=\"float\" value=\"30\" /><input name=\"scale\" type=\"vector2\" value=\"3, 2\" /><input name=\"translation\" type=\"vector2\" value=\"0.13, -0.4\" /></UsdTransform2d>\n"
+    "  <UsdUVTexture name=\"diffuseTex\" type=\"multioutput\"><input name=\"file\" type=\"filename\" value=\"") + file + "\" />"
+    "<input name=\"st\" type=\"vector2\" nodename=\"xf\" /><input name=\"wrapS\" type=\"string\" value=\"mirror\" /><input name=\"wrapT\" type=\"string\" value=\"black\" />"
+    "<input name=\"fallback\" type=\"color4\" value=\"0.05, 0.6, 0.1, 1\" /></UsdUVTexture>\n"
+    "  <UsdUVTexture name=\"dataTex\" type=\"multioutput\"><input name=\"file\" type=\"filename\" value=\"data.pfm\" /><input name=\"sourceColorSpace\" type=\"string\" value=\"raw\" />"
+    "<input name=\"scale\" type=\"color4\" value=\"1, 0.5, 1, 1\" /><input name=\"bias\" type=\"color4\" value=\"0, 0.1, 0, 0\" /></UsdUVTexture>\n"
+    "  <UsdUVTexture name=\"normalTex\" type=\"multioutput\"><input name=\"file\" type=\"filename\" value=\"n.ppm\" /><input name=\"scale\" type=\"color4\" value=\"2, 2, 2, 1\" />"
+    "<input name=\"bias\" type=\"color4\" value=\"-1, -1, -1, 0\" /></UsdUVTexture>\n"
+    "  <UsdPreviewSurface name=\"SR\" type=\"surfaceshader\">\n"
+    "    <input name=\"diffuseColor\" type=\"color3\" nodename=\"diffuseTex\" output=\"rgb\" />\n"
+    "    <input name=\"roughness\" type=\"float\" nodename=\"dataTex\" output=\"g\" />\n"
+    "    <input name=\"normal\" type=\"vector3\" nodename=\"normalTex\" output=\"rgb\" />\n"
+    "    <input name=\"metallic\" type=\"float\" value=\"0.25\" />\n"
+    "    <input name=\"occlusion\" type=\"float\" nodename=\"dataTex\" output=\"r\" />\n"
+    "  </UsdPreviewSurface>\n</materialx>\n";
+}
+static const char* kOpbrNormalMap =
+  "<materialx version=\"1.39\"><image name=\"img\" type=\"vector3\"><input name=\"file\" type=\"filename\" value=\"nrm.ppm\" colorspace=\"lin_rec709\"/>"
+  "<input name=\"uaddressmode\" type=\"string\" value=\"clamp\"/><input name=\"vaddressmode\" type=\"string\" value=\"constant\"/><input name=\"default\" type=\"vector3\" value=\"0.5, 0.5, 1\"/></image>"
+  "<normalmap name=\"nm\" type=\"vector3\"><input name=\"in\" type=\"vector3\" nodename=\"img\"/></normalmap>"
+  "<image name=\"col\" type=\"color3\"><input name=\"file\" type=\"filename\" value=\"c.ppm\" colorspace=\"srgb_texture\"/></image>"
+  "<open_pbr_surface name=\"S\" type=\"surfaceshader\"><input name=\"geometry_normal\" type=\"vector3\" nodename=\"nm\"/>"
+  "<input name=\"base_color\" type=\"color3\" nodename=\"col\"/><input name=\"specular_roughness\" type=\"float\" nodename=\"noise_graph\"/></open_pbr_surface></materialx>";
+
+static int lowerTextureTests()
+{
+  GtlcMaterialDesc d; std::vector<GtlcTextureBinding> b; std::vector<std::string> files;
+  if (!giLowerMtlxToClosureWithTextures(texturedUps("checker.ppm").c_str(), "T", &d, &b, &files)) return 20;
+  if (b.size() != 3 || files.size() != 3 || d.params[GTLC_UPS_METALLIC] != 0.25f || d.params[GTLC_UPS_ROUGHNESS] != 0.5f) return 21;   // connected inputs keep the default constant
+  const GtlcTextureBinding& dc = b[0];
+  if (files[0] != "checker.ppm" || dc.paramIndex != GTLC_UPS_DIFFUSE_R || dc.componentCount != 3 || dc.channels[0] != 0 || dc.channels[1] != 1 || dc.channels[2] != 2) return 22;
+  if (dc.wrapU != GTLC_WRAP_MIRRORED_REPEAT || dc.wrapV != GTLC_WRAP_CLIP || !dc.srgb || dc.fallback[1] != 0.6f) return 23;     // "auto" + diffuseColor -> srgb_texture
+  if (dc.uvRotation != 30.0f || dc.uvScale[0] != 3.0f || dc.uvScale[1] != 2.0f || dc.uvTranslation[0] != 0.13f || dc.uvTranslation[1] != -0.4f) return 24;
+  const GtlcTextureBinding& ro = b[1];
+  if (files[1] != "data.pfm" || ro.paramIndex != GTLC_UPS_ROUGHNESS || ro.componentCount != 1 || ro.channels[0] != 1 || ro.srgb || ro.scale[1] != 0.5f || ro.bias[1] != 0.1f) return 25;
+  if (ro.wrapU != GTLC_WRAP_REPEAT || ro.uvScale[0] != 1.0f || ro.uvRotation != 0.0f) return 26;
+  const GtlcTextureBinding& nm = b[2];
+  if (nm.paramIndex != GTLC_BIND_NORMAL || nm.componentCount != 3 || nm.srgb || nm.scale[0] != 2.0f || nm.bias[2] != -1.0f) return 27;
+  if (!giLowerMtlxToClosureWithTextures(kOpbrNormalMap, "N", &d, &b, &files) || d.closure != GTLC_CLOSURE_OPENPBR) return 28;
+  if (b.size() != 2 || files[0] != "nrm.ppm" || files[1] != "c.ppm") return 29;                 // the procedural roughness graph is not lowered (warning)
+  if (b[0].paramIndex != GTLC_BIND_NORMAL || b[0].scale[0] != 2.0f || b[0].bias[0] != -1.0f || b[0].wrapU != GTLC_WRAP_CLAMP || b[0].wrapV != GTLC_WRAP_CLIP || b[0].fallback[2] != 1.0f || b[0].srgb) return 30;
+  if (b[1].paramIndex != GTLC_OPBR_BASE_COLOR_R || !b[1].srgb || b[1].componentCount != 3) return 31;
+  if (d.params[GTLC_OPBR_SPECULAR_ROUGHNESS] != 0.3f) return 32;
+  return 0;
+}
+
 static int lowerTests()
 {
+  if (int rc = lowerTextureTests()) return rc;
   GtlcMaterialDesc d;
   if (!giLowerMtlxToClosure(kUps, "Red", &d) || d.closure != GTLC_CLOSURE_USD_PREVIEW_SURFACE) return 1;
   if (d.params[GTLC_UPS_DIFFUSE_R] != 0.9f || d.params[GTLC_UPS_DIFFUSE_B] != 0.05f || d.params[GTLC_UPS_ROUGHNESS] != 0.35f || d.params[GTLC_UPS_METALLIC] != 0.25f) return 2;
@@ -57,17 +114,18 @@ static GiVertex vert(float x, float y, float z, float nx, float ny, float nz)
   return v;
 }
 
-static int renderScene(const char* outPath)
+static int renderScene(const char* outPath, const char* texturePath)
 {
   std::vector<std::string> noPaths;
   GiInitParams ip{ "", "", noPaths, nullptr, "" };
   if (giInitialize(ip) != GiStatus::Ok) { fprintf(stderr, "giInitialize failed: %s\n", giGetLastError()); return 10; }
   GiScene* scene = giCreateScene();
-  GiMaterial* red = giCreateMaterialFromMtlxStr(scene, "Red", kUps);
+  GiMaterial* red = texturePath ? giCreateMaterialFromMtlxStr(scene, "Red", texturedUps(texturePath).c_str()) : giCreateMaterialFromMtlxStr(scene, "Red", kUps);
   GiMaterial* light = giCreateMaterialFromMtlxStr(scene, "Light", kEmissive);
   if (!red || !light) return 11;
   // floor quad (two triangles) + emissive quad above it
   std::vector<GiVertex> fv = { vert(-1, -1, 0, 0, 0, 1), vert(1, -1, 0, 0, 0, 1), vert(1, 1, 0, 0, 0, 1), vert(-1, 1, 0, 0, 0, 1) };
+  if (texturePath) for (GiVertex& v : fv) { v.u = (v.pos[0] + 1.0f) * 0.5f; v.v = (v.pos[1] + 1.0f) * 0.5f; }
   std::vector<GiFace> ff = { { { 0, 1, 2 } }, { { 0, 2, 3 } } };
   std::vector<int> faceIds = { 0, 0 };
   std::vector<GiPrimvarData> noPrimvars;
@@ -116,7 +174,7 @@ static int renderScene(const char* outPath)
 int main(int argc, char** argv)
 {
   if (argc >= 2 && !strcmp(argv[1], "lower")) return lowerTests();
-  if (argc >= 3 && !strcmp(argv[1], "render")) return renderScene(argv[2]);
+  if (argc >= 3 && !strcmp(argv[1], "render")) return renderScene(argv[2], argc >= 4 ? argv[3] : nullptr);
   fprintf(stderr, "usage: %s lower | render <out.bin>\n", argv[0]);
   return 2;
 }

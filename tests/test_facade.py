@@ -37,7 +37,7 @@ def test_facade_header_is_self_contained(tmp_path):
     subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++20", "-fsyntax-only", "-I" + inc, str(src)])
 
 
-def _python_twin():
+def _python_twin(textured=False):
     def vert(p, n):
         v = np.zeros(1, scenes.VERTEX_DTYPE)
         v["pos"], v["norm"] = p, n
@@ -56,7 +56,21 @@ def _python_twin():
     st = scenes.RenderSettings(maxBounces=5, nextEventEstimation=True, spp=4)
     d = scenes.SceneDesc("twin", meshes, mats, cam, st, 48, 32, clear_color=(0.25, 0.5, 1.0, 1.0))
     d.sphere_lights.append(scenes.SphereLight(position=(-0.8, 0.2, 0.7), base_emission=(3, 3, 5), radius=(0.1, 0.1, 0.1)))
+    if textured:      # what tests/cpp/gi_facade_main.cpp::texturedUps lowers to; data.pfm / n.ppm do not exist -> those bindings are dropped
+        fv["u"] = (fv["pos"][:, 0] + 1) * 0.5
+        fv["v"] = (fv["pos"][:, 1] + 1) * 0.5
+        d.textures = [scenes.procedural_texture("checker")]
+        mats[0] = scenes.material_usd_preview_surface("Red", metallic=0.25)
+        mats[0].textures = [scenes.TextureBinding(scenes.UPS["diffuse"], 0, (0, 1, 2), scenes.WRAP_MIRRORED_REPEAT, scenes.WRAP_CLIP, True,
+                                                  fallback=(0.05, 0.6, 0.1, 1.0), uv_rotation=30.0, uv_scale=(3.0, 2.0), uv_translation=(0.13, -0.4))]
     return d
+
+
+def write_ppm(path, texture):
+    t = texture.texels[::-1, :, :3]          # PPM rows run top to bottom; Texture rows bottom to top
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (t.shape[1], t.shape[0]))
+        f.write(np.ascontiguousarray(t).tobytes())
 
 
 @pytest.mark.gpu
@@ -76,3 +90,29 @@ def test_facade_renders_like_the_binding(gpu, tmp_path):
     from oracle import orc
     ref, _, _ = orc.OracleScene(d).render()
     assert np.sqrt(np.mean((py[..., :3].astype(np.float64) - ref[..., :3]) ** 2)) < 1e-3
+
+
+@pytest.mark.gpu
+def test_facade_textured_material_renders_like_the_binding(gpu, tmp_path):
+    """MaterialX UsdUVTexture + UsdTransform2d network -> image file read by the facade -> texture binding: identical to
+    the same binding made by hand through the Python harness."""
+    _ensure_built()
+    tex = str(tmp_path / "checker.ppm")
+    write_ppm(tex, scenes.procedural_texture("checker"))
+    out = str(tmp_path / "img.bin")
+    res = subprocess.run([EXE, "render", out, tex], capture_output=True, text=True, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "failed to read image data.pfm" in res.stderr          # missing files drop their binding, loudly
+    cpp = np.fromfile(out, np.float32).reshape(32, 48, 4)
+    d = _python_twin(textured=True)
+    b = gpu.BuiltScene(d)
+    try:
+        py = b.render().copy()
+    finally:
+        b.close()
+    assert np.array_equal(cpp, py), "C++ facade and Python binding disagree (max diff %g)" % np.abs(cpp - py).max()
+    plain = gpu.BuiltScene(_python_twin())
+    try:
+        assert np.abs(plain.render() - py).mean() > 1e-3
+    finally:
+        plain.close()
