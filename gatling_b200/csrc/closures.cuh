@@ -138,15 +138,32 @@ GTLC_D V3 mat_emission_intensity(int closure, const float* p)
     return ((p3(p, GTLC_OPBR_EMISSION_COLOR_R) * p[GTLC_OPBR_EMISSION_LUMINANCE]) * kPi) * mix(v3(1.0f), p3(p, GTLC_OPBR_COAT_COLOR_R), clampf(p[GTLC_OPBR_COAT_WEIGHT], 0.0f, 1.0f));
   return v3(0.0f);
 }
-// mdl_volume_absorption_coefficient
+// mdl_volume_scattering_coefficient (open_pbr_surface.mtlx:238-245,286-292: transmission_scatter / transmission_depth)
+GTLC_D V3 mat_volume_scattering(int closure, const float* p)
+{
+  if (closure != GTLC_CLOSURE_OPENPBR) return v3(0.0f);
+  float depth = p[GTLC_OPBR_TRANSMISSION_DEPTH];
+  if (!(depth > 0.0f)) return v3(0.0f);
+  V3 sc = p3(p, GTLC_OPBR_TRANSMISSION_SCATTER_R);
+  return v3(sc.x / depth, sc.y / depth, sc.z / depth);
+}
+// mdl_volume_absorption_coefficient (open_pbr_surface.mtlx:221-285): extinction - scattering, shifted to be non-negative
 GTLC_D V3 mat_volume_absorption(int closure, const float* p)
 {
   if (closure != GTLC_CLOSURE_OPENPBR) return v3(0.0f);
   float depth = p[GTLC_OPBR_TRANSMISSION_DEPTH];
   if (!(depth > 0.0f)) return v3(0.0f);
   V3 c = p3(p, GTLC_OPBR_TRANSMISSION_COLOR_R);
-  return v3(-logf(fmaxf(c.x, 1.0e-6f)) / depth, -logf(fmaxf(c.y, 1.0e-6f)) / depth, -logf(fmaxf(c.z, 1.0e-6f)) / depth);
+  V3 ext = v3(-logf(fmaxf(c.x, 1.0e-6f)) / depth, -logf(fmaxf(c.y, 1.0e-6f)) / depth, -logf(fmaxf(c.z, 1.0e-6f)) / depth);
+  V3 a = ext - mat_volume_scattering(closure, p);
+  float mn = fminf(fminf(a.x, a.y), a.z);
+  if (0.0f > mn) a = a - v3(mn);
+  return a;
 }
+// mdl_ior: material.ior stays at the MDL default for MaterialX surfaces (open_pbr_surface.mtlx:626-630)
+GTLC_D V3 mat_ior(int, const float*) { return v3(1.0f); }
+// MEDIUM_DIRECTIONAL_BIAS (GlslShaderGen.cpp:212, Frontend.cpp:137-157)
+GTLC_D float mat_directional_bias(int closure, const float* p) { return closure == GTLC_CLOSURE_OPENPBR ? p[GTLC_OPBR_TRANSMISSION_SCATTER_ANISOTROPY] : 0.0f; }
 
 // ---- closure 0: df::diffuse_reflection_bsdf(tint) --------------------------------------------
 GTLC_D void diffuse_sample(const float* p, BsdfSample& d, const ShadingState& s)

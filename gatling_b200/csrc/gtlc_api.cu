@@ -132,7 +132,7 @@ struct Global {
   GtlcTuning tuning;
   GtlcStats stats;
   // path-state pool
-  size_t poolCapacity = 0;
+  size_t poolCapacity = 0, volumeCapacity = 0;
   PathQueue q[2];
   float4* hitTUVP = nullptr; uint32_t* hitInst = nullptr;
   float4 *shO = nullptr, *shD = nullptr, *shC = nullptr; uint32_t* shSeed = nullptr;
@@ -477,7 +477,8 @@ bool uploadLights(Scene* s)
 bool ensurePool(size_t capacity)
 {
   if (capacity <= g.poolCapacity) return true;
-  auto freeQ = [](PathQueue& q) { cudaFree(q.rayO); cudaFree(q.rayD); cudaFree(q.thr); cudaFree(q.rad); cudaFree(q.slot); memset(&q, 0, sizeof(q)); };
+  auto freeQ = [](PathQueue& q) { cudaFree(q.rayO); cudaFree(q.rayD); cudaFree(q.thr); cudaFree(q.rad); cudaFree(q.slot); cudaFree(q.med); cudaFree(q.walk); memset(&q, 0, sizeof(q)); };
+  g.volumeCapacity = 0;
   freeQ(g.q[0]); freeQ(g.q[1]);
   cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.shSeed); cudaFree(g.sampleRad);
   g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.shSeed = nullptr; g.sampleRad = nullptr; g.poolCapacity = 0;
@@ -494,6 +495,17 @@ bool ensurePool(size_t capacity)
   CUDA_OK(cudaMalloc(&g.perm, capacity * 4));
   if (!g.sortHist) { g.sortBlocks = g.smCount * 4; CUDA_OK(cudaMalloc(&g.sortHist, (size_t) kSortBins * g.sortBlocks * 4)); }
   g.poolCapacity = capacity;
+  return true;
+}
+
+// medium stack + walkSegmentPdf of every path (only with mediumStackSize > 0)
+bool ensureVolumePool()
+{
+  if (g.volumeCapacity >= g.poolCapacity && g.q[0].med) return true;
+  for (int k = 0; k < 2; k++) { cudaFree(g.q[k].med); cudaFree(g.q[k].walk); g.q[k].med = nullptr; g.q[k].walk = nullptr; }
+  g.volumeCapacity = 0;
+  for (int k = 0; k < 2; k++) { CUDA_OK(cudaMalloc(&g.q[k].med, g.poolCapacity * 16)); CUDA_OK(cudaMalloc(&g.q[k].walk, g.poolCapacity * 16)); }
+  g.volumeCapacity = g.poolCapacity;
   return true;
 }
 
@@ -1036,7 +1048,7 @@ int gtlc_render(const GtlcRenderParams* params)
   std::lock_guard<std::mutex> l(s->mutex);
   cudaSetDevice(g.device);
   const GtlcRenderSettings& rs = params->renderSettings;
-  if (rs.mediumStackSize != 0) { setError("mediumStackSize > 0 (volume random walk) is not implemented in this build (SURVEY.md 8f rank 4)"); return GTLC_ERROR; }
+  if (rs.mediumStackSize > kMaxMediumStack) { setError("mediumStackSize %u exceeds the %u nested media this build tracks per path", rs.mediumStackSize, kMaxMediumStack); return GTLC_ERROR; }
   if (rs.spp == 0) { setError("spp must be > 0"); return GTLC_ERROR; }
 
   // colour AOV + dimensions (Gi.cpp:2265-2267: the first bound render buffer defines the image size)
@@ -1082,6 +1094,7 @@ int gtlc_render(const GtlcRenderParams* params)
   ubo.maxSampleValue = rs.maxSampleValue; ubo.maxBouncesAndRrBounceOffset = (rs.maxBounces << 16) | rs.rrBounceOffset;
   ubo.rrInvMinTermProb = rs.rrInvMinTermProb; ubo.lightIntensityMultiplier = rs.lightIntensityMultiplier;
   ubo.clipRangePacked = packHalf2x16(params->camera.clipStart, params->camera.clipEnd); ubo.sensorExposure = params->camera.exposure;
+  ubo.mediumStackSize = rs.mediumStackSize; ubo.maxVolumeWalkLength = rs.maxVolumeWalkLength;
   ubo.flags = (rs.jitteredSampling ? FLAG_JITTERED : 0u) | (rs.filterImportanceSampling ? FLAG_FIS : 0u) | (rs.depthOfField ? FLAG_DOF : 0u) |
               (rs.nextEventEstimation ? FLAG_NEE : 0u) | (rs.clippingPlanes ? FLAG_CLIPPING : 0u) | (rs.progressiveAccumulation ? FLAG_PROGRESSIVE : 0u) |
               (rs.domeLightCameraVisible ? FLAG_DOME_CAMERA_VISIBLE : 0u) | (dome ? FLAG_HAS_DOME : 0u);
@@ -1095,6 +1108,8 @@ int gtlc_render(const GtlcRenderParams* params)
     uint32_t samplesPerWave = std::max<uint32_t>(1u, std::min<uint32_t>(rs.spp, pixelsPerWave ? maxPaths / pixelsPerWave : 1u));
     if (pixelsPerWave < localPixels) samplesPerWave = 1;
     if (!ensurePool((size_t) pixelsPerWave * samplesPerWave)) return false;
+    const bool volumes = rs.mediumStackSize > 0;
+    if (volumes && !ensureVolumePool()) return false;
     if (g.accumCapacity < localPixels) { cudaFree(g.accum); g.accum = nullptr; CUDA_OK(cudaMalloc(&g.accum, std::max<size_t>(localPixels, 1) * 16)); g.accumCapacity = localPixels; }
 
     DeviceScene ds; memset(&ds, 0, sizeof(ds));
@@ -1163,7 +1178,9 @@ int gtlc_render(const GtlcRenderParams* params)
           }
           timed(K_SHADE, [&] {
             const uint32_t* permArg = sortByMaterial ? g.perm : nullptr;
-#define GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, TEX) shade_kernel<MAXC, NEE, AOV, TEX><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
+#define GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, VOL) shade_kernel<MAXC, NEE, AOV, TEX, VOL><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
+// the medium stack only ever changes on transmission events, which only the OpenPBR closure produces
+#define GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, TEX) do { if (volumes && MAXC == GTLC_CLOSURE_OPENPBR) GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, (MAXC == GTLC_CLOSURE_OPENPBR)); else GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, false); } while (0)
 #define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) do { if (s->hasTextures) GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, true); else GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, false); } while (0)
 #define GTLC_LAUNCH_SHADE(MAXC, NEE) do { if (aovMode && bounce == 0) GTLC_LAUNCH_SHADE2(MAXC, NEE, true); else GTLC_LAUNCH_SHADE2(MAXC, NEE, false); } while (0)
             const bool nee = rs.nextEventEstimation != 0;
@@ -1173,6 +1190,7 @@ int gtlc_render(const GtlcRenderParams* params)
 #undef GTLC_LAUNCH_SHADE
 #undef GTLC_LAUNCH_SHADE2
 #undef GTLC_LAUNCH_SHADE3
+#undef GTLC_LAUNCH_SHADE4
           });
           if (rs.nextEventEstimation) {
             prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;

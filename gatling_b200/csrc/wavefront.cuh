@@ -26,6 +26,9 @@ constexpr uint32_t kPayloadMediumIdxOffset = 24;
 constexpr uint32_t kPayloadWalkMask = 0x00fff000u;
 constexpr uint32_t kPayloadBouncesMask = 0x00000fffu;
 constexpr uint32_t kPayloadTerminateFlag = 0x80000000u;
+constexpr uint32_t kPayloadVolumeWalkMissFlag = 0x40000000u;
+constexpr uint32_t kPayloadWalkOffset = 12;
+constexpr uint32_t kMaxMediumStack = 4;   // GtlcRenderSettings.mediumStackSize is limited to 4: the stack travels as one uint4 of material indices
 
 // interface/rp_main.h:25-56 UniformData (T1), as kernel launch parameters instead of a UBO.
 struct UniformData {
@@ -42,6 +45,7 @@ struct UniformData {
   // compile-time #defines of the reference (GlslShaderGen.cpp:57-72,95-133) as run-time flags
   uint32_t flags;
   float background[3];   // 1x1 fallback dome texel = u8(clearValue * 255) / 255 (Gi.cpp:2183-2199)
+  uint32_t mediumStackSize, maxVolumeWalkLength;   // MEDIUM_STACK_SIZE (GlslShaderGen.cpp:67), rp_main.h maxVolumeWalkLength
 };
 enum : uint32_t {
   FLAG_JITTERED = 1u, FLAG_FIS = 2u, FLAG_DOF = 4u, FLAG_NEE = 8u, FLAG_CLIPPING = 16u,
@@ -73,7 +77,9 @@ struct DeviceScene {
   const uint2* __restrict__ matTexRange;             // (first binding, binding count) per material
 };
 
-struct PathQueue { float4* rayO; float4* rayD; float4* thr; float4* rad; uint32_t* slot; };
+// med / walk exist only when mediumStackSize > 0 (R14): the medium stack as material indices (the reference stores the
+// 40-byte Medium values, rp_main_payload.glsl:11-17; they are per-material constants) and walkSegmentPdf.
+struct PathQueue { float4* rayO; float4* rayD; float4* thr; float4* rad; uint32_t* slot; uint4* med; float4* walk; };
 
 struct WaveParams {
   uint32_t wavePixelBase;   // first local pixel of this wave
@@ -335,6 +341,47 @@ GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uin
   st.tangent_u = tangent; st.tangent_v = bitangent;
 }
 
+// ---- volume random walk (R14): rp_main.rgen:48-97 ------------------------------------------------------
+GTLC_D float sampleDistance(V3 albedo, V3 throughput, V3 sigma_t, float xi, V3& pdf)
+{
+  const V3 weights = throughput * albedo;
+  const float sum = (weights.x + weights.y) + weights.z;
+  pdf = (sum > 1e-9f) ? (weights / sum) : v3(1.0f / 3.0f);
+  if (xi < pdf.x) return sigma_t.x;
+  else if (xi < (pdf.x + pdf.y)) return sigma_t.y;
+  else return sigma_t.z;
+}
+GTLC_D float sampleHenyeyGreensteinCos(float r, float g)
+{
+  if (fabsf(g) < 1e-3f) return 1.0f - 2.0f * r;
+  const float s = (1.0f - g * g) / ((1.0f - g) + (2.0f * g) * r);
+  return ((1.0f + g * g) - s * s) / (2.0f * g);
+}
+GTLC_D void sampleVolumeScatteringDirection(V2 xi, float bias, V3& dir)
+{
+  const float cos_theta = sampleHenyeyGreensteinCos(xi.x, bias);
+  const float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+  const float phi = (2.0f * kPi) * xi.y;
+  V3 t, b;
+  orthonormal_basis(dir, t, b);
+  dir = ((t * sin_theta) * cosf(phi) + (b * sin_theta) * sinf(phi)) + dir * cos_theta;
+}
+// rp_main_payload.glsl:76-89
+GTLC_D uint32_t payload_medium_idx(uint32_t bitfield, uint32_t mediumStackSize)
+{
+  const uint32_t b = (bitfield & kPayloadMediumIdxMask) >> kPayloadMediumIdxOffset;
+  const uint32_t maxMediumIdx = mediumStackSize > 1u ? mediumStackSize : 1u;
+  return b < maxMediumIdx ? b : maxMediumIdx;
+}
+// the Medium a material defines (rp_main.chit:455-465)
+GTLC_D void medium_of(const DeviceScene& s, uint32_t material, V3& sigma_s, V3& sigma_t)
+{
+  const float* p = s.matParams + (size_t) material * GTLC_MATERIAL_PARAM_COUNT;
+  const int closure = s.matClosure[material];
+  sigma_s = mat_volume_scattering(closure, p);
+  sigma_t = mat_volume_absorption(closure, p) + sigma_s;
+}
+
 // ---- textured material inputs (R15) ------------------------------------------------------------------
 // Evaluates the material's texture bindings at the hit's uv and writes the results into `lp`, the path's private
 // copy of the parameter block.  A GTLC_BIND_NORMAL binding yields the mapped shading normal (returned through
@@ -373,7 +420,7 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
 // ---- shade: rp_main.chit:132-493 + rp_main.miss:55-87 + rp_main.rgen:397-480 ----------------------
 // One thread per live path.  Survivors are compacted into `qout`, shadow rays appended to the shadow
 // queue, finished samples written to sampleRad[slot].
-template <int MAXC, bool NEE, bool AOV, bool TEX>
+template <int MAXC, bool NEE, bool AOV, bool TEX, bool VOL>
 __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
@@ -394,6 +441,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
     V3 ray_origin = v3(0.0f), ray_dir = v3(0.0f), throughput = v3(0.0f), radiance = v3(0.0f);
     V3 neeToLight = v3(0.0f), neeContrib = v3(0.0f);
     uint32_t bitfield = 0, rng_state = 0, slot = 0, shadowSeed = 0;
+    float nextTMax = kFloatMax; V3 nextWalkPdf = v3(1.0f); uint4 nextMedia = make_uint4(0u, 0u, 0u, 0u);
     if (valid) {
       const uint32_t i = perm ? perm[it] : it;
       const float4 ro = qin.rayO[i], rd = qin.rayD[i], th = qin.thr[i], ra = qin.rad[i];
@@ -405,8 +453,29 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
       throughput = v3(th.x, th.y, th.z); bitfield = f2u(th.w);
       radiance = v3(ra.x, ra.y, ra.z); rng_state = f2u(ra.w);
       const uint32_t bounce = bitfield & kPayloadBouncesMask;                          // rgen:298
+      uint32_t media[kMaxMediumStack] = { 0u, 0u, 0u, 0u };
+      V3 walkSegmentPdf = v3(1.0f);
+      uint32_t loopMediumIdx = 0;                                                      // rgen:318 (read before the trace)
+      if (VOL) {
+        const uint4 m4 = qin.med[i]; media[0] = m4.x; media[1] = m4.y; media[2] = m4.z; media[3] = m4.w;
+        const float4 w4 = qin.walk[i]; walkSegmentPdf = v3(w4.x, w4.y, w4.z);
+        loopMediumIdx = payload_medium_idx(bitfield, ubo.mediumStackSize);
+      }
 
-      if (inst == 0xFFFFFFFFu) {
+      if (inst == 0xFFFFFFFFu && VOL && loopMediumIdx > 0) {
+        // ---- rp_main.miss:16-34,57-66: the sampled free-flight distance ended inside the medium ----
+        const float distance = rd.w * ubo.metersPerSceneUnit;                          // gl_RayTmaxEXT
+        V3 sigma_s, sigma_t; medium_of(s, media[loopMediumIdx - 1], sigma_s, sigma_t);
+        const V3 transmittance = v3(expf(sigma_t.x * -distance), expf(sigma_t.y * -distance), expf(sigma_t.z * -distance));
+        const V3 density = sigma_t * transmittance;
+        const float pdf = dot(walkSegmentPdf, density);
+        throughput *= (sigma_s * transmittance) / pdf;
+        ray_origin += worldRayDir * distance;
+        bitfield |= kPayloadVolumeWalkMissFlag;
+        uint32_t wb = bitfield & kPayloadWalkMask;                                     // rp_main_payload.glsl:60-69 (sic: +1 on the unshifted field)
+        wb = (wb + 1u < kPayloadWalkMask) ? wb + 1u : kPayloadWalkMask;
+        bitfield &= ~kPayloadWalkMask; bitfield |= wb;
+      } else if (inst == 0xFFFFFFFFu) {
         // ---- rp_main.miss:55-87 ----
         bitfield |= kPayloadTerminateFlag;                                             // miss:68
         bool useFallbackDomeLight = false;
@@ -435,16 +504,25 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           hasMappedNormal = apply_texture_bindings(s, in.material, worldRayDir, st, lp, mappedNormal);
           mp = lp;
         }
-        uint32_t mediumIdx = (bitfield & kPayloadMediumIdxMask) >> kPayloadMediumIdxOffset; if (mediumIdx > 1u) mediumIdx = 1u;  // chit:153
+        uint32_t mediumIdx = VOL ? loopMediumIdx : payload_medium_idx(bitfield, 0u);   // chit:153
         const bool thinWalled = (mflags & kMatFlagThinWalled) != 0;                    // chit:155-158
+        V3 prevMediumIor = v3(1.0f), nextMediumIor = v3(1.0f);                         // chit:161-162
         if (mediumIdx > 0) {                                                           // chit:164-186
           const float distance = h.x * ubo.metersPerSceneUnit;
-          const V3 sigma_a = mat_volume_absorption(closure, mp);
-          throughput *= v3(expf(-sigma_a.x * distance), expf(-sigma_a.y * distance), expf(-sigma_a.z * distance));
+          if (!VOL) {
+            const V3 sigma_a = mat_volume_absorption(closure, mp);
+            throughput *= v3(expf(-sigma_a.x * distance), expf(-sigma_a.y * distance), expf(-sigma_a.z * distance));
+          } else {
+            const uint32_t top = media[mediumIdx - 1];
+            V3 sigma_s, sigma_t; medium_of(s, top, sigma_s, sigma_t);
+            prevMediumIor = mat_ior(s.matClosure[top], s.matParams + (size_t) top * GTLC_MATERIAL_PARAM_COUNT);
+            if (mediumIdx > 1) { const uint32_t below = media[mediumIdx - 2]; nextMediumIor = mat_ior(s.matClosure[below], s.matParams + (size_t) below * GTLC_MATERIAL_PARAM_COUNT); }
+            throughput *= v3(expf(-sigma_t.x * distance), expf(-sigma_t.y * distance), expf(-sigma_t.z * distance));
+          }
         }
         const float kUseMaterialIor = -1.0f;                                           // mdl_types.glsl:155
-        const V3 iorCurrent = (isFrontFace || thinWalled) ? v3(1.0f) : v3(kUseMaterialIor);   // chit:188
-        const V3 iorOther = (isFrontFace || thinWalled) ? v3(kUseMaterialIor) : v3(1.0f);     // chit:189
+        const V3 iorCurrent = (isFrontFace || thinWalled) ? prevMediumIor : v3(kUseMaterialIor);   // chit:188
+        const V3 iorOther = (isFrontFace || thinWalled) ? v3(kUseMaterialIor) : nextMediumIor;     // chit:189
         if (AOV && bounce == 0) {                                                      // chit:192-290
           const V2 clipRange = unpackHalf2x16(ubo.clipRangePacked);                    // chit:227
           const float logDepth = 2.0f * logf(h.x / clipRange.x) / logf(clipRange.y / clipRange.x) - 1.0f;   // chit:228
@@ -506,11 +584,17 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           }
           neeToLight = ls.dirToLight * ls.dist;                                        // chit:441
         }
-        if (!thinWalled && isTransmissionEvent) {                                      // chit:447-480 (MEDIUM_STACK_SIZE 0)
-          mediumIdx = 1u - mediumIdx;                                                  // chit:473
+        if (!thinWalled && isTransmissionEvent) {                                      // chit:447-480
+          if (VOL) {
+            if (isFrontFace) {                                                         // push (chit:450-467)
+              mediumIdx++;
+              if (mediumIdx <= ubo.mediumStackSize) media[mediumIdx - 1] = in.material;
+            } else if (mediumIdx > 0) mediumIdx--;                                     // pop (chit:468-471)
+          } else mediumIdx = 1u - mediumIdx;                                           // chit:473
           bitfield &= ~kPayloadWalkMask;
           bitfield &= ~kPayloadMediumIdxMask;
-          bitfield |= (mediumIdx << kPayloadMediumIdxOffset);
+          const uint32_t mv = mediumIdx << kPayloadMediumIdxOffset;                    // rp_main_payload.glsl:91-95
+          bitfield |= (mv < kPayloadMediumIdxMask ? mv : kPayloadMediumIdxMask);
         }
         if (eventType == BSDF_EVENT_ABSORB) bitfield |= kPayloadTerminateFlag;         // chit:483-486
         const V3 geomNormal = st.geom_normal * (isTransmissionEvent ? -1.0f : 1.0f);   // chit:488
@@ -531,9 +615,33 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         if (k1 > p) bitfield |= kPayloadTerminateFlag;
         else throughput = throughput / p;
       }
+      if (VOL && (bitfield & kPayloadVolumeWalkMissFlag) != 0) {                       // rgen:462-477
+        const V2 xi = rng1d_next2f(rng_state);
+        const uint32_t top = media[loopMediumIdx - 1];
+        const float bias = mat_directional_bias(s.matClosure[top], s.matParams + (size_t) top * GTLC_MATERIAL_PARAM_COUNT);
+        sampleVolumeScatteringDirection(xi, bias, ray_dir);
+        bitfield &= ~kPayloadVolumeWalkMissFlag;
+      }
       bitfield++;                                                                      // rgen:480
       const uint32_t nextBounce = bitfield & kPayloadBouncesMask;
       survives = !(bitfield & kPayloadTerminateFlag) && nextBounce < maxBounces;       // rgen:301
+      if (VOL && survives) {                                                           // rgen:317-346 of the NEXT loop iteration
+        nextWalkPdf = v3(1.0f);
+        const uint32_t mi = payload_medium_idx(bitfield, ubo.mediumStackSize);
+        if (mi > 0) {
+          V3 sigma_s, sigma_t; medium_of(s, media[mi - 1], sigma_s, sigma_t);
+          const uint32_t walkLength = (bitfield & kPayloadWalkMask) >> kPayloadWalkOffset;
+          const bool hasScattering = sigma_s.x > 0.0f || sigma_s.y > 0.0f || sigma_s.z > 0.0f;
+          if (hasScattering && walkLength <= ubo.maxVolumeWalkLength) {
+            const V3 albedo = v3(safe_div(sigma_s.x, sigma_t.x), safe_div(sigma_s.y, sigma_t.y), safe_div(sigma_s.z, sigma_t.z));
+            const V2 xi = rng1d_next2f(rng_state);
+            float sg = sampleDistance(albedo, throughput, sigma_t, xi.x, nextWalkPdf);
+            sg *= ubo.metersPerSceneUnit;
+            nextTMax = -logf(1.0f - xi.y) / sg;                                        // collision-free distance
+          }
+        }
+        nextMedia = make_uint4(media[0], media[1], media[2], media[3]);
+      }
     }
 
     // ---- compaction: warp ballot + one atomic per warp -------------------------------------------
@@ -558,7 +666,8 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
     if (valid) {
       if (survives) {
         qout.rayO[outPos] = make_float4(ray_origin.x, ray_origin.y, ray_origin.z, 0.0f);   // rgen:306
-        qout.rayD[outPos] = make_float4(ray_dir.x, ray_dir.y, ray_dir.z, kFloatMax);       // rgen:307
+        qout.rayD[outPos] = make_float4(ray_dir.x, ray_dir.y, ray_dir.z, nextTMax);        // rgen:307, :344
+        if (VOL) { qout.med[outPos] = nextMedia; qout.walk[outPos] = make_float4(nextWalkPdf.x, nextWalkPdf.y, nextWalkPdf.z, 0.0f); }
         qout.thr[outPos] = make_float4(throughput.x, throughput.y, throughput.z, u2f(bitfield));
         qout.rad[outPos] = make_float4(radiance.x, radiance.y, radiance.z, u2f(rng_state));
         qout.slot[outPos] = slot;

@@ -223,7 +223,8 @@ namespace gtl
       { "fuzz_color", GTLC_OPBR_FUZZ_COLOR_R, 3 }, { "fuzz_roughness", GTLC_OPBR_FUZZ_ROUGHNESS, 1 }, { "emission_luminance", GTLC_OPBR_EMISSION_LUMINANCE, 1 },
       { "emission_color", GTLC_OPBR_EMISSION_COLOR_R, 3 }, { "thin_film_weight", GTLC_OPBR_THIN_FILM_WEIGHT, 1 }, { "thin_film_thickness", GTLC_OPBR_THIN_FILM_THICKNESS, 1 },
       { "thin_film_ior", GTLC_OPBR_THIN_FILM_IOR, 1 }, { "geometry_opacity", GTLC_OPBR_GEOMETRY_OPACITY, 1 }, { "geometry_thin_walled", GTLC_OPBR_GEOMETRY_THIN_WALLED, 1 },
-      { "subsurface_weight", GTLC_OPBR_SUBSURFACE_WEIGHT, 1 }, { "subsurface_color", GTLC_OPBR_SUBSURFACE_COLOR_R, 3 } };
+      { "subsurface_weight", GTLC_OPBR_SUBSURFACE_WEIGHT, 1 }, { "subsurface_color", GTLC_OPBR_SUBSURFACE_COLOR_R, 3 },
+      { "transmission_scatter", GTLC_OPBR_TRANSMISSION_SCATTER_R, 3 }, { "transmission_scatter_anisotropy", GTLC_OPBR_TRANSMISSION_SCATTER_ANISOTROPY, 1 } };
 
     template <size_t N> void applyInputs(const std::string& xml, const std::vector<XmlInput>& inputs, const Slot (&slots)[N], const char* normalInput, bool ups,
                                          GtlcMaterialDesc& d, const char* matName, LoweredTextures* tex)

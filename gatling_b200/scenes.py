@@ -31,7 +31,8 @@ OPBR = dict(base_weight=0, base_color=1, base_diffuse_roughness=4, base_metalnes
             coat_color=19, coat_roughness=22, coat_ior=23, coat_darkening=24, fuzz_weight=25,
             fuzz_color=26, fuzz_roughness=29, emission_luminance=30, emission_color=31,
             thin_film_weight=34, thin_film_thickness=35, thin_film_ior=36, geometry_opacity=37,
-            geometry_thin_walled=38, subsurface_weight=39, subsurface_color=40)
+            geometry_thin_walled=38, subsurface_weight=39, subsurface_color=40, transmission_scatter=43,
+            transmission_scatter_anisotropy=46)
 
 VERTEX_DTYPE = np.dtype([("pos", "<f4", 3), ("u", "<f4"), ("norm", "<f4", 3), ("v", "<f4"),
                          ("tangent", "<f4", 3), ("bitangentSign", "<f4")])  # GiVertex, Gi.h:109-117
@@ -456,6 +457,31 @@ def textured_cornell(width=96, height=96, spp=8, max_bounces=5, nee=True) -> Sce
     if nee:
         d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
         d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
+    return d
+
+
+# ---- participating media (R14 test scene) ------------------------------------------------------
+def volume_cornell(width=96, height=96, spp=8, max_bounces=12, medium_stack_size=2, nee=True) -> SceneDesc:
+    """Cornell box with three closed OpenPBR dielectrics: a scattering 'milk glass' sphere with a second, differently
+    coloured medium nested inside it (stack depth 2), and a purely absorbing sphere.  medium_stack_size = 0 renders the
+    same scene with the reference's Beer-only inside/outside toggle."""
+    d = cornell(width, height, spp, max_bounces)
+    base = len(d.materials)
+    d.materials = list(d.materials) + [
+        material_openpbr("Milk", base_color=(0.9, 0.9, 0.9), specular_roughness=0.05, transmission_weight=1.0, transmission_color=(0.85, 0.6, 0.4),
+                         transmission_depth=0.25, transmission_scatter=(0.55, 0.5, 0.45), transmission_scatter_anisotropy=0.35),
+        material_openpbr("Core", base_color=(0.9, 0.9, 0.9), specular_roughness=0.1, transmission_weight=1.0, transmission_color=(0.3, 0.7, 0.9),
+                         transmission_depth=0.1, transmission_scatter=(0.2, 0.3, 0.6), transmission_scatter_anisotropy=-0.2),
+        material_openpbr("Amber", base_color=(0.9, 0.9, 0.9), specular_roughness=0.02, transmission_weight=1.0, transmission_color=(0.9, 0.45, 0.1),
+                         transmission_depth=0.3)]
+    for k, (centre, radius, mat) in enumerate((((0.38, -0.35, -0.6), 0.38, 0), ((0.38, -0.35, -0.6), 0.18, 1), ((-0.45, 0.15, -0.25), 0.28, 2))):
+        v, f = sphere_mesh(24, 13, radius)
+        d.meshes.append(Mesh(v, f, base + mat, _trs(1.0, 0.3 * k, centre), None, False, False, 20 + k, "sphere%d" % k))
+    d.meshes = [m for m in d.meshes if m.name not in ("Box1", "Box2")]
+    d.settings = dataclasses.replace(d.settings, mediumStackSize=medium_stack_size, maxVolumeWalkLength=7, nextEventEstimation=nee, rrBounceOffset=4)
+    if nee:
+        d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
+    d.name = "volume_cornell"
     return d
 
 

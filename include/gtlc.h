@@ -177,7 +177,9 @@ enum {
   GTLC_OPBR_GEOMETRY_OPACITY, GTLC_OPBR_GEOMETRY_THIN_WALLED,
   GTLC_OPBR_SUBSURFACE_WEIGHT,
   GTLC_OPBR_SUBSURFACE_COLOR_R, GTLC_OPBR_SUBSURFACE_COLOR_G, GTLC_OPBR_SUBSURFACE_COLOR_B,
-  GTLC_OPBR_PARAM_COUNT /* 43 <= 48 */
+  GTLC_OPBR_TRANSMISSION_SCATTER_R, GTLC_OPBR_TRANSMISSION_SCATTER_G, GTLC_OPBR_TRANSMISSION_SCATTER_B,   /* volume scattering: open_pbr_surface.mtlx:238-245,286-299 */
+  GTLC_OPBR_TRANSMISSION_SCATTER_ANISOTROPY,                                                           /* anisotropic_vdf anisotropy = MEDIUM_DIRECTIONAL_BIAS (Frontend.cpp:137-157) */
+  GTLC_OPBR_PARAM_COUNT /* 47 <= 48 */
 };
 
 /* ---- textures: the reference binds images through MDL resource tables

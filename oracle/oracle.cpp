@@ -27,6 +27,7 @@ using namespace orc;
 
 // rp_main_payload.glsl:3-9
 static const uint32_t PAYLOAD_VOLUME_WALK_MISS_FLAG = 0x40000000u;
+static const uint32_t PAYLOAD_WALK_OFFSET = 12u;
 static const uint32_t PAYLOAD_MEDIUM_IDX_MASK = 0x0f000000u;
 static const uint32_t PAYLOAD_MEDIUM_IDX_OFFSET = 24;
 static const uint32_t PAYLOAD_WALK_MASK = 0x00fff000u;
@@ -34,17 +35,30 @@ static const uint32_t PAYLOAD_BOUNCES_MASK = 0x00000fffu;
 static const uint32_t PAYLOAD_TERMINATE_FLAG = 0x80000000u;
 
 // rp_main_payload.glsl:20-47 (MEDIUM_STACK_SIZE == 0)
+struct Medium { V3 ior, sigma_s, sigma_t; float bias; };                 // rp_main_payload.glsl:11-17
+static const uint32_t MAX_MEDIUM_STACK = 4;                               // GtlcRenderSettings.mediumStackSize is limited to 4 here
 struct ShadeRayPayload {
   V3 throughput; uint32_t bitfield; V3 radiance; uint32_t rng_state;
+  Medium media[MAX_MEDIUM_STACK]; V3 walkSegmentPdf;                      // MEDIUM_STACK_SIZE > 0 (:37-40)
   V3 ray_origin, ray_dir, neeToLight, neeContrib; uint32_t pixelIndex;
 };
 
-// rp_main_payload.glsl:76-89 with MEDIUM_STACK_SIZE 0 -> maxMediumIdx = 1
-static inline uint32_t payloadGetMediumIdx(const ShadeRayPayload& p)
+// rp_main_payload.glsl:76-89: maxMediumIdx = max(1, MEDIUM_STACK_SIZE)
+static inline uint32_t payloadGetMediumIdx(const ShadeRayPayload& p, uint32_t mediumStackSize)
 {
   uint32_t b = (p.bitfield & PAYLOAD_MEDIUM_IDX_MASK) >> PAYLOAD_MEDIUM_IDX_OFFSET;
-  return b < 1u ? b : 1u;
+  uint32_t maxMediumIdx = mediumStackSize > 1u ? mediumStackSize : 1u;
+  return b < maxMediumIdx ? b : maxMediumIdx;
 }
+// rp_main_payload.glsl:60-74
+static inline void payloadIncrementWalk(ShadeRayPayload& p)
+{
+  uint32_t b = p.bitfield & PAYLOAD_WALK_MASK;
+  b = (b + 1u < PAYLOAD_WALK_MASK) ? b + 1u : PAYLOAD_WALK_MASK;          // (sic) the reference adds 1 to the masked, unshifted field
+  p.bitfield &= ~PAYLOAD_WALK_MASK;
+  p.bitfield |= b;
+}
+static inline uint32_t payloadGetWalk(const ShadeRayPayload& p) { return (p.bitfield & PAYLOAD_WALK_MASK) >> PAYLOAD_WALK_OFFSET; }
 // rp_main_payload.glsl:91-95
 static inline void payloadSetMediumIdx(ShadeRayPayload& p, uint32_t idx)
 {
@@ -61,14 +75,14 @@ struct Ubo {
   V3 cameraPosition; uint32_t imageDims; V3 cameraForward; float focusDistance; V3 cameraUp; float cameraVFoV;
   uint32_t sampleOffset; float lensRadius; uint32_t spp; float invTotalSampleCount; float maxSampleValue;
   uint32_t maxBouncesAndRrBounceOffset; float rrInvMinTermProb; float lightIntensityMultiplier;
-  uint32_t clipRangePacked; float sensorExposure;
+  uint32_t clipRangePacked; float sensorExposure; uint32_t maxVolumeWalkLength;
 };
 
 struct Flags { // compile-time #defines of the reference, GlslShaderGen.cpp:57-72,95-133
   bool jittered, fis, dof, nee, clipping, progressive, domeCameraVisible;
 };
 
-struct RenderCtx { const Scene* s; Ubo ubo; Flags fl; V4 background; uint32_t aovMask; };
+struct RenderCtx { const Scene* s; Ubo ubo; Flags fl; V4 background; uint32_t aovMask; uint32_t mediumStackSize; };
 
 // What the closest-hit shader writes into the auxiliary AOVs on the first bounce (rp_main.chit:191-290),
 // captured per sample so that the per-pixel write order of the megakernel can be replayed.
@@ -210,8 +224,26 @@ static inline V3 sampleDomeLight(const RenderCtx& c, uint32_t domeLightIndex, V3
 }
 
 // rp_main.miss:55-87 (MEDIUM_STACK_SIZE == 0, colour AOV bound)
-static inline void miss_shader(const RenderCtx& c, ShadeRayPayload& p, V3 worldRayDir)
+// rp_main.miss:16-34
+static inline void stepVolume(const RenderCtx& c, ShadeRayPayload& p, uint32_t mediumIdx, V3 worldRayDir, float rayTmax)
 {
+  float distance = rayTmax * c.ubo.metersPerSceneUnit;
+  const Medium& m = p.media[mediumIdx - 1];
+  V3 transmittance = v3(expf(m.sigma_t.x * -distance), expf(m.sigma_t.y * -distance), expf(m.sigma_t.z * -distance));
+  V3 density = m.sigma_t * transmittance;
+  float pdf = dot(p.walkSegmentPdf, density);
+  p.throughput *= (m.sigma_s * transmittance) / pdf;
+  p.ray_origin += worldRayDir * distance;
+  p.bitfield |= PAYLOAD_VOLUME_WALK_MISS_FLAG;
+  payloadIncrementWalk(p);
+}
+
+static inline void miss_shader(const RenderCtx& c, ShadeRayPayload& p, V3 worldRayDir, float rayTmax)
+{
+  if (c.mediumStackSize > 0) {                                           // :57-66
+    uint32_t mediumIdx = payloadGetMediumIdx(p, c.mediumStackSize);
+    if (mediumIdx > 0) { stepVolume(c, p, mediumIdx, worldRayDir, rayTmax); return; }
+  }
   p.bitfield |= PAYLOAD_TERMINATE_FLAG;                                  // :68
   bool useFallbackDomeLight = false;
   if (!c.fl.domeCameraVisible) {                                         // :76-80
@@ -324,19 +356,27 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
 
   V3 throughput = p.throughput;
   V3 radiance = p.radiance;
-  uint32_t mediumIdx = payloadGetMediumIdx(p);                            // :153
+  uint32_t mediumIdx = payloadGetMediumIdx(p, c.mediumStackSize);         // :153
   bool thinWalled = mat_is_thin_walled(base);                             // :155-158 (compile-time flag of the material)
 
+  V3 prevMediumIor = v3(1.0f), nextMediumIor = v3(1.0f);                  // :161-162
   if (mediumIdx > 0) {                                                    // :164-186
     float distance = hit.t * c.ubo.metersPerSceneUnit;
-    V3 sigma_a = mat_volume_absorption(mat);
-    V3 transmittance = v3(expf(-sigma_a.x * distance), expf(-sigma_a.y * distance), expf(-sigma_a.z * distance));
+    V3 transmittance;
+    if (c.mediumStackSize == 0) {
+      V3 sigma_a = mat_volume_absorption(mat);
+      transmittance = v3(expf(-sigma_a.x * distance), expf(-sigma_a.y * distance), expf(-sigma_a.z * distance));
+    } else {
+      const Medium& m = p.media[mediumIdx - 1];
+      prevMediumIor = m.ior;
+      if (mediumIdx > 1) nextMediumIor = p.media[mediumIdx - 2].ior;
+      transmittance = v3(expf(-m.sigma_t.x * distance), expf(-m.sigma_t.y * distance), expf(-m.sigma_t.z * distance));
+    }
     throughput *= transmittance;
   }
-  // :188-189 with prev/nextMediumIor = 1 (MEDIUM_STACK_SIZE == 0)
-  const float USE_MATERIAL_IOR = -1.0f;
-  V3 iorCurrent = (isFrontFace || thinWalled) ? v3(1.0f) : v3(USE_MATERIAL_IOR);
-  V3 iorOther = (isFrontFace || thinWalled) ? v3(USE_MATERIAL_IOR) : v3(1.0f);
+  const float USE_MATERIAL_IOR = -1.0f;                                   // :188-189
+  V3 iorCurrent = (isFrontFace || thinWalled) ? prevMediumIor : v3(USE_MATERIAL_IOR);
+  V3 iorOther = (isFrontFace || thinWalled) ? v3(USE_MATERIAL_IOR) : nextMediumIor;
 
   if (aov && (p.bitfield & PAYLOAD_BOUNCES_MASK) == 0) {                  // :192-290 auxiliary AOVs on the first bounce
     aov->hit = true;
@@ -408,6 +448,16 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
   }
 
   if (!thinWalled && isTransmissionEvent) {                               // :447-480
+    if (c.mediumStackSize > 0) {
+      if (isFrontFace) {                                                  // push, :450-467
+        mediumIdx++;
+        if (mediumIdx <= c.mediumStackSize) {
+          V3 sigma_a = mat_volume_absorption(mat), sigma_s = mat_volume_scattering(mat);
+          Medium m; m.ior = mat_ior(mat); m.sigma_s = sigma_s; m.sigma_t = sigma_a + sigma_s; m.bias = mat_directional_bias(mat);
+          p.media[mediumIdx - 1] = m;
+        }
+      } else if (mediumIdx > 0) mediumIdx--;                              // pop, :468-471
+    } else
     mediumIdx = (1u - mediumIdx);                                         // :473
     p.bitfield &= ~PAYLOAD_WALK_MASK;
     payloadSetMediumIdx(p, mediumIdx);
@@ -421,6 +471,32 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
 }
 
 struct RayCounters { uint64_t closest, shadow; };
+
+// rp_main.rgen:48-97
+static inline float sampleDistance(V3 albedo, V3 throughput, V3 sigma_t, float xi, V3& pdf)
+{
+  V3 weights = throughput * albedo;
+  float sum = (weights.x + weights.y) + weights.z;
+  pdf = (sum > 1e-9f) ? (weights / sum) : v3(1.0f / 3.0f);
+  if (xi < pdf.x) return sigma_t.x;
+  else if (xi < (pdf.x + pdf.y)) return sigma_t.y;
+  else return sigma_t.z;
+}
+static inline float sampleHenyeyGreensteinCos(float r, float g)
+{
+  if (fabsf(g) < 1e-3f) return 1.0f - 2.0f * r;
+  float s = (1.0f - g * g) / ((1.0f - g) + (2.0f * g) * r);
+  return ((1.0f + g * g) - s * s) / (2.0f * g);
+}
+static inline void sampleVolumeScatteringDirection(V2 xi, float bias, V3& dir)
+{
+  float cos_theta = sampleHenyeyGreensteinCos(xi.x, bias);
+  float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - cos_theta * cos_theta));
+  float phi = (2.0f * PI) * xi.y;
+  V3 t, b;
+  orthonormal_basis(dir, t, b);
+  dir = ((t * sin_theta) * cosf(phi) + (b * sin_theta) * sinf(phi)) + dir * cos_theta;
+}
 
 // rp_main.rgen:215-499: one sample of one pixel; returns the clamped sample colour.
 static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint32_t pixelIndex, uint32_t s, RayCounters& rc, AovSample* aov = nullptr)
@@ -450,13 +526,30 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
     if (bounce >= maxBounces || terminate) break;                         // :301
     float tMin = 0.0f, tMax = FLOAT_MAX;
     if (c.fl.clipping && bounce == 0) { tMin = clipRange.x; tMax = clipRange.y; } // :308-314
+    uint32_t mediumIdx = 0;
+    if (c.mediumStackSize > 0) {                                          // :317-346
+      mediumIdx = payloadGetMediumIdx(p, c.mediumStackSize);
+      if (mediumIdx > 0) {
+        const Medium& m = p.media[mediumIdx - 1];
+        p.walkSegmentPdf = v3(1.0f);
+        uint32_t walkLength = payloadGetWalk(p);
+        bool hasScattering = m.sigma_s.x > 0.0f || m.sigma_s.y > 0.0f || m.sigma_s.z > 0.0f;
+        if (hasScattering && walkLength <= ubo.maxVolumeWalkLength) {
+          V3 albedo = v3(safe_div(m.sigma_s.x, m.sigma_t.x), safe_div(m.sigma_s.y, m.sigma_t.y), safe_div(m.sigma_s.z, m.sigma_t.z));
+          V2 xi = rng1d_next2f(p.rng_state);
+          float sgm = sampleDistance(albedo, p.throughput, m.sigma_t, xi.x, p.walkSegmentPdf);
+          sgm *= ubo.metersPerSceneUnit;
+          tMax = -logf(1.0f - xi.y) / sgm;                                 // collision free distance
+        }
+      }
+    }
     p.neeContrib = v3(0.0f);                                              // :349
 
     Hit hit;
     V3 d = p.ray_dir, o = p.ray_origin;
     rc.closest++;
     if (scene_trace(*c.s, o, d, tMin, tMax, false, hit, p.rng_state)) closest_hit_shader(c, p, hit, d, aov); // :381-393 (any-hit seed: ahit:159)
-    else miss_shader(c, p, d);
+    else miss_shader(c, p, d, tMax);
 
     if (c.fl.nee) {                                                       // :397-438
       V3 shadowray_origin = p.ray_origin;
@@ -478,6 +571,12 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
     if (bounce > rrBounceOffset) {                                        // :447-459
       float k1 = rng1d_next1f(p.rng_state);
       if (russian_roulette(k1, p.throughput, ubo.rrInvMinTermProb)) p.bitfield |= PAYLOAD_TERMINATE_FLAG;
+    }
+    if (c.mediumStackSize > 0 && (p.bitfield & PAYLOAD_VOLUME_WALK_MISS_FLAG) != 0) {   // :462-477
+      V2 xi = rng1d_next2f(p.rng_state);
+      float bias = p.media[mediumIdx - 1].bias;
+      sampleVolumeScatteringDirection(xi, bias, p.ray_dir);
+      p.bitfield &= ~PAYLOAD_VOLUME_WALK_MISS_FLAG;
     }
     p.bitfield++;                                                         // :480
   }
@@ -581,6 +680,9 @@ static void fill_ctx(RenderCtx& c, const Scene* s, const OrcRenderDesc* r)
   u.lightIntensityMultiplier = rs.lightIntensityMultiplier;
   u.clipRangePacked = packHalf2x16(r->camera.clipStart, r->camera.clipEnd);
   u.sensorExposure = r->camera.exposure;
+  u.maxVolumeWalkLength = rs.maxVolumeWalkLength;                          // Gi.cpp:2391-2423
+  c.mediumStackSize = rs.mediumStackSize < MAX_MEDIUM_STACK ? rs.mediumStackSize : MAX_MEDIUM_STACK;
+  c.aovMask = 0;
   c.fl.jittered = rs.jitteredSampling != 0; c.fl.fis = rs.filterImportanceSampling != 0; c.fl.dof = rs.depthOfField != 0;
   c.fl.nee = rs.nextEventEstimation != 0; c.fl.clipping = rs.clippingPlanes != 0; c.fl.progressive = rs.progressiveAccumulation != 0;
   c.fl.domeCameraVisible = rs.domeLightCameraVisible != 0;

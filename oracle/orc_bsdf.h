@@ -181,15 +181,36 @@ static inline void edf_evaluate(EdfEvaluateData& d, const State& s)
   d.edf = v3(INV_PI);
   d.pdf = d.cos * INV_PI;
 }
-// mdl_volume_absorption_coefficient (OpenPBR: open_pbr_surface.mtlx:221-262, transmission_depth > 0)
+// mdl_volume_scattering_coefficient (OpenPBR: open_pbr_surface.mtlx:238-245,286-292: transmission_scatter / transmission_depth)
+static inline V3 mat_volume_scattering(const Material& m)
+{
+  if (m.closure != GTLC_CLOSURE_OPENPBR) return v3(0.0f);
+  float depth = m.p[GTLC_OPBR_TRANSMISSION_DEPTH];
+  if (!(depth > 0.0f)) return v3(0.0f);
+  V3 sc = p3(m, GTLC_OPBR_TRANSMISSION_SCATTER_R);
+  return v3(sc.x / depth, sc.y / depth, sc.z / depth);
+}
+// mdl_volume_absorption_coefficient (OpenPBR: open_pbr_surface.mtlx:221-285): extinction = -ln(color) / depth,
+// absorption = extinction - scattering, shifted to be non-negative
 static inline V3 mat_volume_absorption(const Material& m)
 {
   if (m.closure != GTLC_CLOSURE_OPENPBR) return v3(0.0f);
   float depth = m.p[GTLC_OPBR_TRANSMISSION_DEPTH];
   if (!(depth > 0.0f)) return v3(0.0f);
   V3 c = p3(m, GTLC_OPBR_TRANSMISSION_COLOR_R);
-  // sigma_a = -ln(color) / depth, colour clamped away from 0
-  return v3(-logf(fmaxf(c.x, 1.0e-6f)) / depth, -logf(fmaxf(c.y, 1.0e-6f)) / depth, -logf(fmaxf(c.z, 1.0e-6f)) / depth);
+  // colour clamped away from 0 (ln(0) would give an infinite coefficient)
+  V3 ext = v3(-logf(fmaxf(c.x, 1.0e-6f)) / depth, -logf(fmaxf(c.y, 1.0e-6f)) / depth, -logf(fmaxf(c.z, 1.0e-6f)) / depth);
+  V3 a = ext - mat_volume_scattering(m);
+  float mn = fminf(fminf(a.x, a.y), a.z);
+  if (0.0f > mn) a = a - v3(mn);                                     // mtlx:263-279
+  return a;
+}
+// mdl_ior: the MaterialX surface constructor (open_pbr_surface.mtlx:626-630) leaves material.ior at the MDL default
+static inline V3 mat_ior(const Material&) { return v3(1.0f); }
+// MEDIUM_DIRECTIONAL_BIAS (GlslShaderGen.cpp:212, Frontend.cpp:137-157): volume.scattering.directional_bias when constant
+static inline float mat_directional_bias(const Material& m)
+{
+  return m.closure == GTLC_CLOSURE_OPENPBR ? m.p[GTLC_OPBR_TRANSMISSION_SCATTER_ANISOTROPY] : 0.0f;
 }
 
 // ---- closure 0: df::diffuse_reflection_bsdf(tint) -------------------------------------------

@@ -163,7 +163,7 @@ static int renderScene(const char* outPath, const char* texturePath)
   fwrite(px, sizeof(float), (size_t) W * H * 4, f);
   fclose(f);
   // an unsupported setting must fail loudly, not render something else
-  rp.renderSettings.mediumStackSize = 1;
+  rp.renderSettings.mediumStackSize = 9;
   if (giRender(rp) != GiStatus::Error) return 16;
   giDestroyRenderBuffer(rb); giDestroySphereLight(scene, sl); giDestroyMesh(floorMesh); giDestroyMesh(lightMesh);
   giDestroyMaterial(red); giDestroyMaterial(light); giDestroyScene(scene); giTerminate();

@@ -188,7 +188,7 @@ def test_errors_are_loud(gpu):
     d = scenes.cornell(16, 16, spp=1)
     b = gpu.BuiltScene(d)
     try:
-        st = dataclasses.replace(d.settings, mediumStackSize=2)
+        st = dataclasses.replace(d.settings, mediumStackSize=9)
         with pytest.raises(RuntimeError):
             b.render(settings=st)
         assert "mediumStackSize" in gpu.giLastError()
@@ -436,3 +436,19 @@ def test_texture_errors_are_loud(gpu):
     gpu.giDestroyTexture(tex)            # deferred: the material still references it
     gpu.giDestroyMaterial(m)
     gpu.giDestroyScene(s)
+
+
+def test_render_parity_volumes(gpu):
+    """R14: medium stack (push / pop, nested media), free-flight sampling, Henyey-Greenstein scattering, NEE from inside
+    nothing special (shadow rays are plain any-hit rays), against the oracle; plus the Beer-only mediumStackSize = 0 path."""
+    for n in (2, 1, 0):
+        _render_parity(gpu, scenes.volume_cornell(96, 96, spp=8, medium_stack_size=n))
+    _render_parity(gpu, scenes.volume_cornell(64, 64, spp=6, medium_stack_size=2, nee=False))
+    _aov_parity(gpu, scenes.volume_cornell(48, 48, spp=4, medium_stack_size=2))
+    d = scenes.volume_cornell(32, 32, spp=2, medium_stack_size=5)
+    b = gpu.BuiltScene(d)
+    try:
+        with pytest.raises(RuntimeError, match="exceeds the 4 nested media"):
+            b.render()
+    finally:
+        b.close()
