@@ -452,3 +452,57 @@ def test_render_parity_volumes(gpu):
             b.render()
     finally:
         b.close()
+
+
+def test_full_size_properties_c2(gpu):
+    """Config C2 at BASELINE.json's full size (1 M triangles, 1920x1080), where the oracle is too slow to compare
+    pixel by pixel: size-independent properties of the path."""
+    d = scenes.random_triangles(1_000_000, 1920, 1080, spp=2, max_bounces=8)
+    b = gpu.BuiltScene(d)
+    try:
+        img = b.render().copy()
+        st = gpu.get_stats()
+        # furnace bound: Lambert 0.8 everywhere, no emitters, white background => every sample is in [0, 1]
+        assert np.isfinite(img).all() and img[..., :3].min() >= 0.0 and img[..., :3].max() <= 1.0 + 1e-6
+        assert np.all(img[..., 3] == 1.0)
+        assert st["paths"] == 1920 * 1080 * 2 and st["paths"] <= st["closestRays"] <= 8 * st["paths"]
+        # the image does not depend on how the work is cut into waves or shards (bitwise)
+        gpu.set_tuning(maxPathsPerWave=1 << 20)
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(b.render(), img)
+        gpu.set_tuning(maxPathsPerWave=1 << 24)
+        acc = np.zeros_like(img)
+        for r in range(3):
+            gpu.set_shard(b.scene, r, 3, 64)
+            part = b.render()
+            acc[..., :3] += part[..., :3]
+            acc[..., 3] = np.maximum(acc[..., 3], part[..., 3])
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(acc, img)
+        # closest-hit queries: shrinking the interval to just beyond / just before the hit
+        rays = random_rays(400000, 77)
+        h = gpu.trace_rays(b.scene, rays)
+        hit = h["t"] > 0
+        assert 0.2 < hit.mean() < 1.0
+        beyond = rays[hit].copy(); beyond[:, 7] = np.nextafter(h["t"][hit], np.float32(np.inf))
+        h2 = gpu.trace_rays(b.scene, beyond)
+        for k in ("t", "u", "v", "prim", "inst"):
+            assert np.array_equal(h2[k], h[k][hit]), k                                        # idempotent
+        before = rays[hit].copy(); before[:, 7] = h["t"][hit]
+        h3 = gpu.trace_rays(b.scene, before)                                                  # open interval: the hit itself is excluded
+        assert np.all((h3["t"] < h["t"][hit]))
+        occl = gpu.trace_rays(b.scene, rays, any_hit=True)
+        assert np.array_equal(occl["t"] >= 0, hit)                                            # any-hit agrees with closest-hit on occlusion
+        # the hit point lies on the reported triangle: barycentric reconstruction == origin + t * direction (to rounding)
+        _, tris = gpu.get_bvh(b.scene)
+        t = tris.reshape(-1, 12)
+        prim_of = np.empty(len(t), np.int64); prim_of[t[:, 3].view(np.uint32)] = np.arange(len(t))
+        rec = t[prim_of[h["prim"][hit]]]
+        v0, v1, v2 = rec[:, 0:3], rec[:, 4:7], rec[:, 8:11]
+        u, v = h["u"][hit, None], h["v"][hit, None]
+        p_bary = v0 * (1 - u - v) + v1 * u + v2 * v
+        p_ray = rays[hit, 0:3] + rays[hit, 4:7] * h["t"][hit, None]
+        assert np.abs(p_bary - p_ray).max() < 2e-5
+    finally:
+        gpu.set_tuning(maxPathsPerWave=1 << 24)
+        b.close()
