@@ -13,6 +13,14 @@ HEADER = os.path.join(HERE, "..", "include", "gtlc.h")
 H = C.c_uint64
 
 
+class PrimvarDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("type", C.c_int32), ("interpolation", C.c_int32), ("data", C.c_void_p), ("dataSize", C.c_uint64)]
+
+
+class PrimvarBinding(C.Structure):
+    _fields_ = [("paramIndex", C.c_int32), ("componentCount", C.c_int32), ("name", C.c_char_p), ("fallback", C.c_float * 4)]
+
+
 class TextureDesc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("reserved", C.c_int32), ("texels", C.c_void_p)]
 
@@ -26,13 +34,15 @@ class TextureBinding(C.Structure):
 
 class MaterialDesc(C.Structure):
     _fields_ = [("closure", C.c_int32), ("name", C.c_char_p), ("params", C.c_float * 48),
-                ("textures", C.POINTER(TextureBinding)), ("textureCount", C.c_uint32), ("reserved", C.c_uint32)]
+                ("textures", C.POINTER(TextureBinding)), ("textureCount", C.c_uint32), ("primvarCount", C.c_uint32),
+                ("primvars", C.POINTER(PrimvarBinding))]
 
 
 class MeshDesc(C.Structure):
     _fields_ = [("faceCount", C.c_uint32), ("faces", C.c_void_p), ("faceIds", C.c_void_p), ("id", C.c_int32),
                 ("isDoubleSided", C.c_int32), ("isLeftHanded", C.c_int32), ("name", C.c_char_p), ("maxFaceId", C.c_uint32),
-                ("vertexCount", C.c_uint32), ("vertices", C.c_void_p)]
+                ("vertexCount", C.c_uint32), ("vertices", C.c_void_p), ("primvars", C.POINTER(PrimvarDesc)),
+                ("primvarCount", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class CameraDesc(C.Structure):
@@ -97,6 +107,7 @@ _SIGNATURES = {
     "gtlc_mesh_create": (H, [H, C.POINTER(MeshDesc)]),
     "gtlc_mesh_set_transform": (None, [H, C.c_void_p]),
     "gtlc_mesh_set_instance_transforms": (None, [H, C.c_uint32, C.c_void_p]),
+    "gtlc_mesh_set_instancer_primvars": (None, [H, C.c_uint32, C.POINTER(PrimvarDesc)]),
     "gtlc_mesh_set_instance_ids": (None, [H, C.c_uint32, C.c_void_p]),
     "gtlc_mesh_set_material": (None, [H, H]),
     "gtlc_mesh_set_visibility": (None, [H, C.c_int32]),

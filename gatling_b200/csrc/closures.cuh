@@ -19,7 +19,7 @@ enum : int {
   BSDF_EVENT_REFLECTION = 8, BSDF_EVENT_TRANSMISSION = 16
 };
 
-struct ShadingState { V3 normal, geom_normal, position, tangent_u, tangent_v; float u, v; };  // mdl_types.glsl:32-113
+struct ShadingState { V3 normal, geom_normal, position, tangent_u, tangent_v; float u, v; uint32_t hitIndices[3]; };  // mdl_types.glsl:32-113 (+ renderer_state.hitIndices)
 struct BsdfSample { V3 ior1, ior2, k1, k2; V4 xi; float pdf; V3 bsdf_over_pdf; int event_type; };  // :158-170
 struct BsdfEval { V3 ior1, ior2, k1, k2; V3 bsdf_diffuse, bsdf_glossy; float pdf; };              // :173-184
 

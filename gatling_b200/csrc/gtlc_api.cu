@@ -54,7 +54,9 @@ struct Scene;
 // Textures are shared between materials (and scenes): reference counted, the creator holds one reference.
 struct Texture : Object { uint32_t width, height; int32_t format; void* dTexels; int refs; };
 struct Material : Object { Scene* scene; int32_t closure; float params[GTLC_MATERIAL_PARAM_COUNT]; std::string name;
-                           std::vector<GtlcTextureBinding> bindings; std::vector<Texture*> boundTextures; };
+                           std::vector<GtlcTextureBinding> bindings; std::vector<Texture*> boundTextures;
+                           struct PrimvarBinding { int32_t paramIndex, componentCount; std::string name; float fallback[4]; };
+                           std::vector<PrimvarBinding> primvarBindings; };
 
 struct Mesh : Object {
   Scene* scene;
@@ -67,6 +69,8 @@ struct Mesh : Object {
   std::vector<float> instanceTransforms;     // 12 per instance
   std::vector<int32_t> instanceIds;
   Material* material;
+  struct Primvar { std::string name; int32_t type, interpolation; std::vector<uint8_t> data; };   // GiPrimvarData
+  std::vector<Primvar> primvars, instancerPrimvars;
 };
 
 // rp_main.h:73-113, 48 bytes each
@@ -110,6 +114,8 @@ struct Scene : Object {
   Bvh8 bvh; bool bvhValid = false;        // host copy of the BVH8 (stale while bvhHostStale: built on the device, not yet read back)
   bool bvhHostStale = false; uint32_t nodeCount = 0, triCount = 0, maxDepth = 0, totalTris = 0;
   std::vector<float> hInstOpacity; DeviceArray<float> dInstOpacity;
+  std::vector<uint2> hPrimvarInfos; std::vector<float> hPrimvarData; DeviceArray<uint2> dPrimvarInfos; DeviceArray<float> dPrimvarData;   // R15 scene data
+  DeviceArray<DevicePrimvarBinding> dPrimvarBindings; DeviceArray<uint2> dMatPrimvarRange;
   std::vector<float> hFverts; std::vector<uint32_t> hFaces;
   std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo; std::vector<int2> hInstIds; std::vector<int32_t> hFaceIds; std::vector<uint32_t> hRankBase;
   std::vector<Material*> flatMaterials;
@@ -238,7 +244,7 @@ void invertAffine(const float* m, float* out)
 bool buildHostGeometry(Scene* s, bool hostBvh = true)
 {
   auto t0 = std::chrono::steady_clock::now();
-  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->hInstOpacity.clear(); s->flatMaterials.clear();
+  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->hInstOpacity.clear(); s->hPrimvarInfos.clear(); s->hPrimvarData.clear(); s->flatMaterials.clear();
   std::vector<BuildTri> tris;
   size_t totalTris = 0;
   for (Mesh* m : s->meshes) if (m->visible && m->material) totalTris += m->faces.size() * (m->instanceTransforms.size() / 12);
@@ -272,7 +278,33 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
         fi[i] = ownIds ? m->faceIds[i] : (int32_t) i;                    // rp_main.chit:232-240
       }
     }
-    const uint32_t flags = (m->flipFacing ? 1u : 0u) | (m->doubleSided ? 2u : 0u);   // Gi.cpp:1135-1143
+    // scene data of this mesh for its material's primvar bindings (Gi.cpp:905-1018): mesh primvars override instancer primvars
+    const uint32_t meshSlot = (uint32_t) (s->hPrimvarInfos.size() / GTLC_MAX_PRIMVAR_BINDINGS);
+    for (int k = 0; k < GTLC_MAX_PRIMVAR_BINDINGS; k++) {
+      uint2 info = make_uint2(0u, 0u);
+      if ((size_t) k < m->material->primvarBindings.size()) {
+        const std::string& want = m->material->primvarBindings[k].name;
+        const Mesh::Primvar* found = nullptr;
+        for (const Mesh::Primvar& p : m->instancerPrimvars) if (p.name == want && !p.data.empty()) { found = &p; break; }
+        for (const Mesh::Primvar& p : m->primvars) if (p.name == want && !p.data.empty()) { found = &p; break; }
+        if (found && found->type <= GTLC_PRIMVAR_VEC4) {           // float types only feed closure inputs
+          const uint32_t stride = (uint32_t) found->type + 1u;
+          size_t need = 1;                                          // elements the lookup may index (get_scene_data_indices)
+          if (found->interpolation == GTLC_INTERP_VERTEX) need = m->vertices.size();
+          else if (found->interpolation == GTLC_INTERP_UNIFORM) need = m->faces.size();
+          else if (found->interpolation == GTLC_INTERP_INSTANCE) {
+            const size_t ic = m->instanceTransforms.size() / 12;
+            for (size_t q = 0; q < ic; q++) { const int32_t id = q < m->instanceIds.size() ? m->instanceIds[q] : (int32_t) q; if (id >= 0) need = std::max(need, (size_t) id + 1); }
+          }
+          if (found->data.size() < need * stride * 4) { setError("primvar '%s' of mesh '%s' holds %zu bytes, its interpolation needs %zu: ignored", want.c_str(), m->name.c_str(), found->data.size(), need * stride * 4); s->hPrimvarInfos.push_back(info); continue; }
+          info = make_uint2((uint32_t) s->hPrimvarData.size(), stride | ((uint32_t) found->interpolation << 4) | 0x100u);
+          const float* src = reinterpret_cast<const float*>(found->data.data());
+          s->hPrimvarData.insert(s->hPrimvarData.end(), src, src + found->data.size() / 4);
+        }
+      }
+      s->hPrimvarInfos.push_back(info);
+    }
+    const uint32_t flags = (m->flipFacing ? 1u : 0u) | (m->doubleSided ? 2u : 0u) | (meshSlot << 8);   // Gi.cpp:1135-1143; bits 8.. = row of the scene-data table
     const size_t instCount = m->instanceTransforms.size() / 12;
     for (size_t k = 0; k < instCount; k++) {                            // Gi.cpp:1188-1202
       float o2w[12], w2o[12];
@@ -322,6 +354,8 @@ bool uploadGeometry(Scene* s, bool hostBvh = true)
     if (!s->dTris.upload((const float4*) s->bvh.tris.data(), s->bvh.tris.size() / 4, st)) return false;
   }
   if (!s->dInstOpacity.upload(s->hInstOpacity.data(), s->hInstOpacity.size(), st)) return false;
+  if (!s->dPrimvarInfos.upload(s->hPrimvarInfos.data(), s->hPrimvarInfos.size(), st)) return false;
+  if (!s->dPrimvarData.upload(s->hPrimvarData.data(), s->hPrimvarData.size(), st)) return false;
   if (!s->dFverts.upload((const float4*) s->hFverts.data(), s->hFverts.size() / 4, st)) return false;
   if (!s->dFaces.upload(s->hFaces.data(), s->hFaces.size(), st)) return false;
   if (!s->dO2W.upload((const float4*) s->hO2W.data(), s->hO2W.size() / 4, st)) return false;
@@ -423,14 +457,17 @@ bool uploadMaterials(Scene* s)
 {
   std::vector<float> params; std::vector<int32_t> closure; std::vector<uint32_t> flags;
   std::vector<DeviceTexture> textures; std::vector<Texture*> textureIndex; std::vector<DeviceTexBinding> bindings; std::vector<uint2> ranges;
+  std::vector<DevicePrimvarBinding> pbindings; std::vector<uint2> pranges;
   const double kPi = 3.14159265358979323846;
   for (Material* m : s->flatMaterials) {
     params.insert(params.end(), m->params, m->params + GTLC_MATERIAL_PARAM_COUNT);
     closure.push_back(m->closure);
-    flags.push_back((mat_is_emissive(m->closure, m->params) || !m->bindings.empty() ? kMatFlagEmissive : 0u) |   // a textured input may be the emission
+    flags.push_back((mat_is_emissive(m->closure, m->params) || !m->bindings.empty() || !m->primvarBindings.empty() ? kMatFlagEmissive : 0u) |   // a textured input may be the emission
                     (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u) |
                     (mat_cutout_opacity(m->closure, m->params) < 1.0f ? kMatFlagCutout : 0u));
     ranges.push_back(make_uint2((uint32_t) bindings.size(), (uint32_t) m->bindings.size()));
+    pranges.push_back(make_uint2((uint32_t) pbindings.size(), (uint32_t) m->primvarBindings.size()));
+    for (const Material::PrimvarBinding& pb : m->primvarBindings) { DevicePrimvarBinding d; memset(&d, 0, sizeof(d)); d.paramIndex = pb.paramIndex; d.componentCount = pb.componentCount; memcpy(d.fallback, pb.fallback, 16); pbindings.push_back(d); }
     for (size_t b = 0; b < m->bindings.size(); b++) {
       const GtlcTextureBinding& src = m->bindings[b];
       Texture* t = m->boundTextures[b];
@@ -447,7 +484,9 @@ bool uploadMaterials(Scene* s)
       bindings.push_back(d);
     }
   }
-  s->hasTextures = !bindings.empty();
+  s->hasTextures = !bindings.empty() || !pbindings.empty();
+  if (!s->dPrimvarBindings.upload(pbindings.data(), pbindings.size(), g.stream)) return false;
+  if (!s->dMatPrimvarRange.upload(pranges.data(), pranges.size(), g.stream)) return false;
   if (!s->dMatParams.upload(params.data(), params.size(), g.stream)) return false;
   if (!s->dMatClosure.upload(closure.data(), closure.size(), g.stream)) return false;
   if (!s->dMatFlags.upload(flags.data(), flags.size(), g.stream)) return false;
@@ -564,6 +603,7 @@ TraceParams makeTraceParams(Scene* s)
 template <int MODE> void launchTrace(const TraceParams& P, bool count, int blocks)
 {
   if (count) { trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // visit counting: variant 0 order = the oracle's walk
+  if (P.aovFlags) { trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // only variant 0 writes the NEE debug AOV
   switch (g.tuning.traceVariant) {
     case 5: trace_kernel_v2<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 6: trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
@@ -669,7 +709,7 @@ void gtlc_scene_destroy(GtlcHandle h)
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
   s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
-  s->dMatParams.release(); s->dTextures.release(); s->dTexBindings.release(); s->dMatTexRange.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
+  s->dMatParams.release(); s->dTextures.release(); s->dTexBindings.release(); s->dMatTexRange.release(); s->dPrimvarInfos.release(); s->dPrimvarData.release(); s->dPrimvarBindings.release(); s->dMatPrimvarRange.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
 }
@@ -716,6 +756,11 @@ GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
   Scene* s = as<Scene>(sh, TAG_SCENE); if (!s || !d) return 0;
   if (d->closure < GTLC_CLOSURE_DIFFUSE || d->closure > GTLC_CLOSURE_OPENPBR) { setError("unknown closure %d", d->closure); return 0; }
   if (d->textureCount && !d->textures) { setError("gtlc_material_create: null texture bindings"); return 0; }
+  if (d->primvarCount > GTLC_MAX_PRIMVAR_BINDINGS || (d->primvarCount && !d->primvars)) { setError("gtlc_material_create: %u primvar bindings (at most %d)", d->primvarCount, GTLC_MAX_PRIMVAR_BINDINGS); return 0; }
+  for (uint32_t b = 0; b < d->primvarCount; b++) {
+    const GtlcPrimvarBinding& pb = d->primvars[b];
+    if (pb.componentCount < 1 || pb.componentCount > 3 || pb.paramIndex < 0 || pb.paramIndex + pb.componentCount > GTLC_MATERIAL_PARAM_COUNT) { setError("gtlc_material_create: primvar binding %u writes outside the parameter block", b); return 0; }
+  }
   std::vector<Texture*> bound;
   for (uint32_t b = 0; b < d->textureCount; b++) {
     const GtlcTextureBinding& tb = d->textures[b];
@@ -730,6 +775,7 @@ GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
   Material* m = new Material(); m->tag = TAG_MATERIAL; m->scene = s; m->closure = d->closure; memcpy(m->params, d->params, sizeof(m->params));
   if (d->name) m->name = d->name;
   if (d->textureCount) m->bindings.assign(d->textures, d->textures + d->textureCount);
+  for (uint32_t b = 0; b < d->primvarCount; b++) { Material::PrimvarBinding pb; pb.paramIndex = d->primvars[b].paramIndex; pb.componentCount = d->primvars[b].componentCount; pb.name = d->primvars[b].name ? d->primvars[b].name : ""; memcpy(pb.fallback, d->primvars[b].fallback, 16); m->primvarBindings.push_back(pb); }
   {
     std::lock_guard<std::mutex> dl(g_destroyMutex);
     for (Texture* t : bound) t->refs++;
@@ -755,6 +801,17 @@ void gtlc_material_destroy(GtlcHandle h)
 }
 
 // ---- meshes --------------------------------------------------------------------------------
+static bool copyPrimvars(const GtlcPrimvarDesc* src, uint32_t count, std::vector<Mesh::Primvar>& dst)
+{
+  dst.clear();
+  for (uint32_t i = 0; i < count; i++) {
+    if (!src[i].name || src[i].type < GTLC_PRIMVAR_FLOAT || src[i].type > GTLC_PRIMVAR_INT4 || src[i].interpolation < GTLC_INTERP_CONSTANT || src[i].interpolation > GTLC_INTERP_VERTEX) return false;
+    Mesh::Primvar p; p.name = src[i].name; p.type = src[i].type; p.interpolation = src[i].interpolation;
+    if (src[i].data && src[i].dataSize) p.data.assign((const uint8_t*) src[i].data, (const uint8_t*) src[i].data + src[i].dataSize);
+    dst.push_back(std::move(p));
+  }
+  return true;
+}
 GtlcHandle gtlc_mesh_create(GtlcHandle sh, const GtlcMeshDesc* d)
 {
   Scene* s = as<Scene>(sh, TAG_SCENE); if (!s || !d) return 0;
@@ -767,6 +824,7 @@ GtlcHandle gtlc_mesh_create(GtlcHandle sh, const GtlcMeshDesc* d)
   if (d->faceIds) m->faceIds.assign(d->faceIds, d->faceIds + d->faceCount);
   m->id = d->id; m->doubleSided = d->isDoubleSided != 0; m->flipFacing = d->isLeftHanded != 0; m->visible = true;
   if (d->name) m->name = d->name;
+  if (d->primvarCount && (!d->primvars || !copyPrimvars(d->primvars, d->primvarCount, m->primvars))) { setError("gtlc_mesh_create: invalid primvar description"); delete m; return 0; }
   const float ident[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
   memcpy(m->transform, ident, sizeof(ident));
   m->instanceTransforms.assign(ident, ident + 12);
@@ -791,6 +849,13 @@ void gtlc_mesh_set_instance_transforms(GtlcHandle h, uint32_t count, const float
   m->instanceTransforms.resize((size_t) count * 12);
   for (uint32_t i = 0; i < count; i++) usdToRow3x4(t16 + (size_t) i * 16, &m->instanceTransforms[(size_t) i * 12]);
   if (m->instanceIds.size() != count) { m->instanceIds.resize(count); for (uint32_t i = 0; i < count; i++) m->instanceIds[i] = (int32_t) i; }
+  m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
+}
+void gtlc_mesh_set_instancer_primvars(GtlcHandle h, uint32_t count, const GtlcPrimvarDesc* primvars)
+{
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  std::lock_guard<std::mutex> l(m->scene->mutex);
+  if (!copyPrimvars(primvars, count, m->instancerPrimvars)) setError("gtlc_mesh_set_instancer_primvars: invalid primvar description");
   m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
 }
 void gtlc_mesh_set_instance_ids(GtlcHandle h, uint32_t count, const int32_t* ids)
@@ -1116,6 +1181,7 @@ int gtlc_render(const GtlcRenderParams* params)
     ds.fverts = s->dFverts.ptr; ds.faces = s->dFaces.ptr; ds.instO2W = s->dO2W.ptr; ds.instW2O = s->dW2O.ptr; ds.instInfo = s->dInstInfo.ptr; ds.instIds = s->dInstIds.ptr; ds.faceIds = s->dFaceIds.ptr;
     ds.matParams = s->dMatParams.ptr; ds.matClosure = s->dMatClosure.ptr; ds.matFlags = s->dMatFlags.ptr;
     ds.textures = s->dTextures.ptr; ds.texBindings = s->dTexBindings.ptr; ds.matTexRange = s->dMatTexRange.ptr;
+    ds.primvarBindings = s->dPrimvarBindings.ptr; ds.matPrimvarRange = s->dMatPrimvarRange.ptr; ds.primvarInfos = s->dPrimvarInfos.ptr; ds.primvarData = s->dPrimvarData.ptr;
     ds.sphereLights = s->dSphere.ptr; ds.distantLights = s->dDistant.ptr; ds.rectLights = s->dRect.ptr; ds.diskLights = s->dDisk.ptr;
     if (dome) { ds.domeTexels = dome->dTexels; ds.domeW = dome->width; ds.domeH = dome->height; }
 
@@ -1197,6 +1263,7 @@ int gtlc_render(const GtlcRenderParams* params)
             TraceParams S = makeTraceParams(s);
             S.rayO = g.shO; S.rayD = g.shD; S.shContrib = g.shC; S.radPath = g.q[inIdx ^ 1].rad; S.radSample = g.sampleRad;
             S.numRays = &g.counters->numShadow; S.workCounter = &g.counters->workCounter; S.seedU32 = g.shSeed;
+            if (aovMode && bounce == 0) { S.aovFlags = g.aovSamples.a[0]; S.aovSlotOf = g.q[inIdx ^ 1].slot; }
             timed(K_SHADOW, [&] { launchTrace<TRACE_SHADOW>(S, countVisits, traceBlocks); });
           }
           inIdx ^= 1;

@@ -50,6 +50,8 @@ struct TraceParams {
   const float4* __restrict__ seedRad;   // cutout any-hit: per-ray RNG seed = bits of seedRad[i].w (path queue `rad`), or
   const uint32_t* __restrict__ seedU32; //   seedU32[i] (shadow queue); both NULL = seed 0
   uint32_t biasWord;                           // 0x47000000 (see biased_byte)
+  float4* aovFlags;                            // NEE debug AOV (first bounce, variant 0 only): per-sample capture word a[0]; bit 3 of .w = shadow ray occluded
+  const uint32_t* __restrict__ aovSlotOf;      //   sample slot of a continuing path (path queue `slot`)
   const uint32_t* __restrict__ instRankBase;   // variant 7: first global (instance, primitive)-ordered triangle rank of every instance
 };
 
@@ -312,6 +314,12 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
               float4 cur = *dst;
               cur.x += c.x; cur.y += c.y; cur.z += c.z;
               *dst = cur;
+            } else if (P.aovFlags) {                                   // rgen:431-436: NeeAov = shadowed ? red : green
+              const uint32_t target = f2u(__ldg(&P.shContrib[rayIdx]).w);
+              const uint32_t slot = (target & 0x80000000u) ? (target & 0x7FFFFFFFu) : P.aovSlotOf[target];
+              float4 a0 = P.aovFlags[slot];
+              a0.w = u2f(f2u(a0.w) | 8u);
+              P.aovFlags[slot] = a0;
             }
           } else {
             P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));

@@ -56,6 +56,8 @@ enum : uint32_t {
 struct InstanceInfo { uint32_t vertexBase, faceBase, flags, material; };
 constexpr uint32_t kMatFlagEmissive = 1u, kMatFlagThinWalled = 2u, kMatFlagCutout = 4u;
 
+struct DevicePrimvarBinding { int32_t paramIndex; int32_t componentCount; float fallback[4]; float pad[2]; };
+
 struct DeviceScene {
   const float4* __restrict__ fverts;     // 2 x float4 per FVertex (rp_main.h:58-64)
   const uint32_t* __restrict__ faces;    // 3 per Face (rp_main.h:66-71)
@@ -75,6 +77,11 @@ struct DeviceScene {
   const DeviceTexture* __restrict__ textures;        // R15: texture table
   const DeviceTexBinding* __restrict__ texBindings;  // all materials' bindings, material-major
   const uint2* __restrict__ matTexRange;             // (first binding, binding count) per material
+  // R15 scene data: column k of a mesh's row belongs to binding k of the mesh's material
+  const DevicePrimvarBinding* __restrict__ primvarBindings;   // all materials' bindings, material-major
+  const uint2* __restrict__ matPrimvarRange;                  // (first binding, binding count) per material
+  const uint2* __restrict__ primvarInfos;                     // [meshSlot * GTLC_MAX_PRIMVAR_BINDINGS + k] = (float offset, stride | interpolation << 4 | valid << 8)
+  const float* __restrict__ primvarData;
 };
 
 // med / walk exist only when mediumStackSize > 0 (R14): the medium stack as material indices (the reference stores the
@@ -91,7 +98,7 @@ struct WaveParams {
 
 // Per-sample capture of what the closest-hit shader writes into the auxiliary AOVs on the first bounce
 // (rp_main.chit:191-290); resolve_aov_kernel replays the megakernel's per-pixel write order from it.
-//   a[0] = (barycentrics.xyz, flags: bit0 hit, bit1 thinWalled, bit2 doubleSided)   a[1] = (texcoords.xyz, depth)
+//   a[0] = (barycentrics.xyz, flags: bit0 hit, bit1 thinWalled, bit2 doubleSided, bit3 NEE shadow ray occluded (set by the shadow kernel), bit4 NEE block ran)   a[1] = (texcoords.xyz, depth)
 //   a[2] = (tangent.xyz, objectId)   a[3] = (bitangent.xyz, faceId)   a[4] = (posNormal.xyz, instanceId)   a[5] = (albedo.xyz, cutout opacity or -1)
 struct AovSampleBuffers { float4* a[6]; };
 
@@ -339,6 +346,7 @@ GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uin
   st.v = (bc.x * a2.w + bc.y * b2.w) + bc.z * c2.w;
   st.normal = normal; st.geom_normal = geomNormal; st.position = pos;                  // :82-90
   st.tangent_u = tangent; st.tangent_v = bitangent;
+  st.hitIndices[0] = i0; st.hitIndices[1] = i1; st.hitIndices[2] = i2;                  // mdl_shading_state.glsl:66-79 (renderer state)
 }
 
 // ---- volume random walk (R14): rp_main.rgen:48-97 ------------------------------------------------------
@@ -380,6 +388,36 @@ GTLC_D void medium_of(const DeviceScene& s, uint32_t material, V3& sigma_s, V3& 
   const int closure = s.matClosure[material];
   sigma_s = mat_volume_scattering(closure, p);
   sigma_t = mat_volume_absorption(closure, p) + sigma_s;
+}
+
+// ---- primvar-driven material inputs (R15): scene_data_lookup_float{,2,3}, mdl_interface.glsl:281-417 ----------
+GTLC_D void apply_primvar_bindings(const DeviceScene& s, const InstanceInfo in, uint32_t inst, uint32_t prim, float hu, float hv,
+                                   const ShadingState& st, float* lp)
+{
+  const uint2 range = s.matPrimvarRange[in.material];
+  const uint32_t meshSlot = in.flags >> 8;
+  const V3 bc = v3((1.0f - hu) - hv, hu, hv);
+  for (uint32_t k = 0; k < range.y; k++) {
+    const DevicePrimvarBinding& pb = s.primvarBindings[range.x + k];
+    const uint2 info = s.primvarInfos[(size_t) meshSlot * GTLC_MAX_PRIMVAR_BINDINGS + k];
+    if (!(info.y & 0x100u)) {                                        // scene_data_isvalid: default_value
+      for (int c = 0; c < pb.componentCount; c++) lp[pb.paramIndex + c] = pb.fallback[c];
+      continue;
+    }
+    const uint32_t stride = info.y & 15u, interpolation = (info.y >> 4) & 15u;
+    uint32_t i0, i1, i2;                                             // get_scene_data_indices :281-301
+    if (interpolation == GTLC_INTERP_UNIFORM) i0 = i1 = i2 = prim;
+    else if (interpolation == GTLC_INTERP_INSTANCE) { const int id = s.instIds[inst].y; i0 = i1 = i2 = id > 0 ? (uint32_t) id : 0u; }   // InstanceIds[gl_InstanceID]
+    else if (interpolation == GTLC_INTERP_CONSTANT) i0 = i1 = i2 = 0u;
+    else { i0 = st.hitIndices[0]; i1 = st.hitIndices[1]; i2 = st.hitIndices[2]; }
+    const float* d = s.primvarData + info.x;
+    for (int c = 0; c < pb.componentCount; c++) {
+      const float v0 = c < (int) stride ? __ldg(d + (size_t) i0 * stride + c) : 0.0f;
+      const float v1 = c < (int) stride ? __ldg(d + (size_t) i1 * stride + c) : 0.0f;
+      const float v2 = c < (int) stride ? __ldg(d + (size_t) i2 * stride + c) : 0.0f;
+      lp[pb.paramIndex + c] = (v0 * bc.x + v1 * bc.y) + v2 * bc.z;
+    }
+  }
 }
 
 // ---- textured material inputs (R15) ------------------------------------------------------------------
@@ -484,7 +522,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         const V3 sampleDir = normalize(quatRotateDir(ubo.domeLightRotation, worldRayDir));   // miss:83
         const V3 rdn = sampleDomeLight(ubo, s, domeLightIndex, sampleDir) * ld3(ubo.domeLightEmissionMultiplier);  // miss:84
         radiance += throughput * rdn;                                                  // miss:86
-        if (AOV && bounce == 0) aov.a[0][slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(0u));
+        if (AOV && bounce == 0) aov.a[0][slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(NEE ? 16u : 0u));
       } else {
         // ---- rp_main.chit:132-493 ----
         const uint32_t prim = f2u(h.w);
@@ -499,8 +537,9 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         const V3 normal = st.normal;                                                   // chit:147
         float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT : 1];                                 // textured inputs: private parameter block
         V3 mappedNormal = normal; bool hasMappedNormal = false;
-        if (TEX && s.matTexRange[in.material].y != 0u) {
+        if (TEX && (s.matTexRange[in.material].y | s.matPrimvarRange[in.material].y) != 0u) {
           for (int k = 0; k < GTLC_MATERIAL_PARAM_COUNT; k++) lp[k] = mp[k];
+          apply_primvar_bindings(s, in, inst, prim, h.y, h.z, st, lp);
           hasMappedNormal = apply_texture_bindings(s, in.material, worldRayDir, st, lp, mappedNormal);
           mp = lp;
         }
@@ -531,7 +570,7 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           const V3 tanAov = (st.tangent_u + v3(1.0f)) * 0.5f, bitAov = (st.tangent_v + v3(1.0f)) * 0.5f;   // chit:208,211
           const V3 posNormal = (normal + v3(1.0f)) * 0.5f;                             // chit:252
           const V3 albedo = bsdf_albedo<MAXC>(closure, mp, -worldRayDir, st);         // chit:264-280
-          const uint32_t fl = 1u | (thinWalled ? 2u : 0u) | (isDoubleSided ? 4u : 0u);
+          const uint32_t fl = 1u | (thinWalled ? 2u : 0u) | (isDoubleSided ? 4u : 0u) | (NEE ? 16u : 0u);
           aov.a[0][slot] = make_float4((1.0f - h.y) - h.z, h.y, h.z, u2f(fl));         // chit:214
           aov.a[1][slot] = make_float4(st.u, st.v, 0.0f, logDepth);                    // chit:217
           aov.a[2][slot] = make_float4(tanAov.x, tanAov.y, tanAov.z, u2f((uint32_t) ids.x));
@@ -797,6 +836,9 @@ __global__ void __launch_bounds__(256) resolve_aov_kernel(UniformData ubo, WaveP
         };
         accumulate(GTLC_AOV_NORMAL, v3(a4.x, a4.y, a4.z));
         accumulate(GTLC_AOV_ALBEDO, v3(a5.x, a5.y, a5.z));
+      }
+      if ((fl & 16u) && tg.buf[GTLC_AOV_NEE]) {                                        // rgen:431-436
+        float4 c = vb[GTLC_AOV_NEE][pix]; c.x = (fl & 8u) ? 1.0f : 0.0f; c.y = (fl & 8u) ? 0.0f : 1.0f; c.z = 0.0f; vb[GTLC_AOV_NEE][pix] = c;
       }
       if (tg.buf[GTLC_AOV_BOUNCES]) {                                                  // rgen:483-486
         const V3 cm = colormap_inferno((float) f2u(sampleRad[slot].w) / (float) maxBounces);

@@ -112,8 +112,8 @@ def texture_binding_c(b: "S.TextureBinding", handle) -> "L.TextureBinding":
     return c
 
 
-def giCreateMaterial(scene, closure: int, params: Sequence[float], name: str = "", textures=(), texture_handles=()):
-    """`textures`: scenes.TextureBinding list whose .texture indexes `texture_handles`."""
+def giCreateMaterial(scene, closure: int, params: Sequence[float], name: str = "", textures=(), texture_handles=(), primvars=()):
+    """`textures`: scenes.TextureBinding list whose .texture indexes `texture_handles`; `primvars`: scenes.PrimvarBinding list."""
     d = L.MaterialDesc()
     d.closure = closure
     d.name = name.encode() if name else None
@@ -124,6 +124,13 @@ def giCreateMaterial(scene, closure: int, params: Sequence[float], name: str = "
         arr_b = (L.TextureBinding * len(textures))(*[texture_binding_c(b, texture_handles[b.texture]) for b in textures])
         d.textures = arr_b
         d.textureCount = len(textures)
+    if primvars:
+        arr_p = (L.PrimvarBinding * len(primvars))()
+        for i, b in enumerate(primvars):
+            arr_p[i].paramIndex, arr_p[i].componentCount, arr_p[i].name = b.param, b.count, b.name.encode()
+            arr_p[i].fallback = (C.c_float * 4)(*b.fallback)
+        d.primvars = arr_p
+        d.primvarCount = len(primvars)
     return _lib().gtlc_material_create(scene, C.byref(d)) or None
 
 
@@ -132,8 +139,24 @@ def giDestroyMaterial(mat):
 
 
 # ---- meshes (Gi.h:209-216) ----------------------------------------------------------------------------
+def _primvar_descs(primvars):
+    """scenes.Primvar list -> (ctypes array, keep-alive list)."""
+    arr = (L.PrimvarDesc * max(len(primvars), 1))()
+    keep = []
+    for i, p in enumerate(primvars):
+        a = np.ascontiguousarray(p.data, np.float32)
+        a = a.reshape(len(a), -1)
+        keep.append(a)
+        arr[i].name = p.name.encode()
+        arr[i].type = a.shape[1] - 1            # GTLC_PRIMVAR_FLOAT .. VEC4
+        arr[i].interpolation = p.interpolation
+        arr[i].data = a.ctypes.data
+        arr[i].dataSize = a.nbytes
+    return arr, keep
+
+
 def giCreateMesh(scene, vertices: np.ndarray, faces: np.ndarray, *, id: int = 0, isDoubleSided=True, isLeftHanded=False,
-                 name: str = "", faceIds: Optional[np.ndarray] = None):
+                 name: str = "", faceIds: Optional[np.ndarray] = None, primvars=()):
     v = np.ascontiguousarray(vertices)
     assert v.dtype.itemsize == 48, "vertices must be GiVertex records (48 bytes)"
     f = np.ascontiguousarray(faces, np.uint32).reshape(-1, 3)
@@ -151,6 +174,10 @@ def giCreateMesh(scene, vertices: np.ndarray, faces: np.ndarray, *, id: int = 0,
     d.maxFaceId = int(fid.max()) if fid is not None and len(fid) else max(len(f) - 1, 0)
     d.vertexCount = len(v)
     d.vertices = v.ctypes.data
+    if primvars:
+        arr, keep = _primvar_descs(primvars)
+        d.primvars = arr
+        d.primvarCount = len(primvars)
     return _lib().gtlc_mesh_create(scene, C.byref(d)) or None
 
 
@@ -162,6 +189,11 @@ def giSetMeshTransform(mesh, mat4x4):
 def giSetMeshInstanceTransforms(mesh, transforms):
     t = np.ascontiguousarray(transforms, np.float32).reshape(-1, 16)
     _lib().gtlc_mesh_set_instance_transforms(mesh, len(t), t.ctypes.data)
+
+
+def giSetMeshInstancerPrimvars(mesh, primvars):
+    arr, keep = _primvar_descs(primvars)
+    _lib().gtlc_mesh_set_instancer_primvars(mesh, len(primvars), arr)
 
 
 def giSetMeshInstanceIds(mesh, ids):
@@ -341,16 +373,22 @@ class BuiltScene:
         self.textures = [giCreateTexture(t.texels) for t in desc.textures]
         if any(t is None for t in self.textures):
             raise RuntimeError("giCreateTexture failed: " + giLastError())
-        self.materials = [giCreateMaterial(self.scene, m.closure, m.params, m.name, m.textures, self.textures) for m in desc.materials]
+        self.materials = [giCreateMaterial(self.scene, m.closure, m.params, m.name, m.textures, self.textures, m.primvars) for m in desc.materials]
+        if any(h is None for h in self.materials):
+            raise RuntimeError("giCreateMaterial failed: " + giLastError())
         self.meshes = []
         for m in desc.meshes:
             h = giCreateMesh(self.scene, m.vertices, m.faces, id=m.object_id, isDoubleSided=m.double_sided,
-                             isLeftHanded=m.left_handed, name=m.name)
+                             isLeftHanded=m.left_handed, name=m.name, primvars=m.primvars)
             if h is None:
                 raise RuntimeError("giCreateMesh failed: " + giLastError())
             giSetMeshTransform(h, m.transform)
             if m.instance_transforms is not None:
                 giSetMeshInstanceTransforms(h, m.instance_transforms)
+            if m.instance_ids is not None:
+                giSetMeshInstanceIds(h, m.instance_ids)
+            if m.instancer_primvars:
+                giSetMeshInstancerPrimvars(h, m.instancer_primvars)
             giSetMeshMaterial(h, self.materials[m.material])
             self.meshes.append(h)
         self.lights = []

@@ -205,7 +205,24 @@ namespace gtl
       return true;
     }
 
-    struct LoweredTextures { std::vector<GtlcTextureBinding> bindings; std::vector<std::string> files; };
+    struct LoweredPrimvar { int paramIndex, componentCount; std::string name; float fallback[4]; };
+    struct LoweredTextures { std::vector<GtlcTextureBinding> bindings; std::vector<std::string> files; std::vector<LoweredPrimvar> primvars; };
+
+    // A surface-shader input fed by UsdPrimvarReader / geompropvalue / geomcolor: the MDL backend turns these into
+    // scene_data_lookup_* calls (mdl_interface.glsl:266-479) on the named primvar.
+    bool lowerPrimvarInput(const std::string& xml, const XmlInput& in, int paramIndex, int count, LoweredPrimvar& out)
+    {
+      std::string category; std::vector<XmlInput> node;
+      if (in.nodename.empty() || !findNodeByName(xml, in.nodename, category, node)) return false;
+      const bool usd = category == "UsdPrimvarReader";
+      if (!usd && category != "geompropvalue") return false;
+      const XmlInput* name = findInput(node, usd ? "varname" : "geomprop");
+      if (!name || name->value.empty()) return false;
+      out.paramIndex = paramIndex; out.componentCount = count; out.name = name->value;
+      out.fallback[0] = out.fallback[1] = out.fallback[2] = out.fallback[3] = 0.0f;
+      if (const XmlInput* fb = findInput(node, usd ? "fallback" : "default")) { float v[4]; const int n = parseFloats(fb->value, v, 4); for (int k = 0; k < n; k++) out.fallback[k] = v[k]; if (n == 1) out.fallback[1] = out.fallback[2] = v[0]; }
+      return true;
+    }
 
     struct Slot { const char* name; int index; int count; };
     const Slot kUpsSlots[] = {
@@ -237,7 +254,9 @@ namespace gtl
         if (in.connected) {
           GtlcTextureBinding b; std::string file;
           const bool srgbInput = ups && (in.name == "diffuseColor" || in.name == "emissiveColor" || in.name == "specularColor");
+          LoweredPrimvar pv;
           if (tex && lowerTextureInput(xml, in, isNormal ? GTLC_BIND_NORMAL : slot->index, isNormal ? 3 : slot->count, srgbInput, b, file)) { tex->bindings.push_back(b); tex->files.push_back(file); }
+          else if (tex && !isNormal && tex->primvars.size() < GTLC_MAX_PRIMVAR_BINDINGS && lowerPrimvarInput(xml, in, slot->index, slot->count, pv)) tex->primvars.push_back(pv);
           else fprintf(stderr, "[gi] warning: material '%s': input '%s' is connected to a graph this build cannot lower; using the default value\n", matName ? matName : "", in.name.c_str());
           continue;
         }
@@ -322,6 +341,8 @@ namespace gtl
     LoweredTextures t;
     if (!lowerMaterial(mtlxSrc, name, out, &t)) return false;
     *bindings = t.bindings; *files = t.files;
+    out->primvarCount = (uint32_t) t.primvars.size();      // test hook: the names are reported through `files` after the image files
+    for (const LoweredPrimvar& p : t.primvars) files->push_back("primvar:" + p.name + ":" + std::to_string(p.paramIndex) + ":" + std::to_string(p.componentCount));
     return true;
   }
 
@@ -355,6 +376,9 @@ namespace gtl
       t.bindings[i].texture = h; bound.push_back(t.bindings[i]); textures.push_back(h);
     }
     d.textures = bound.empty() ? nullptr : bound.data(); d.textureCount = (uint32_t) bound.size();
+    std::vector<GtlcPrimvarBinding> pvs(t.primvars.size());
+    for (size_t i = 0; i < pvs.size(); i++) { pvs[i].paramIndex = t.primvars[i].paramIndex; pvs[i].componentCount = t.primvars[i].componentCount; pvs[i].name = t.primvars[i].name.c_str(); memcpy(pvs[i].fallback, t.primvars[i].fallback, 16); }
+    d.primvars = pvs.empty() ? nullptr : pvs.data(); d.primvarCount = (uint32_t) pvs.size();
     GiMaterial* m = wrap<GiMaterial>(gtlc_material_create(scene->h, &d));
     for (GtlcHandle h : textures) gtlc_texture_destroy(h);     // the material holds its own references
     return m;
@@ -372,6 +396,17 @@ namespace gtl
   }
   void giDestroyMaterial(GiMaterial* m) { if (!m) return; gtlc_material_destroy(m->h); delete m; }
 
+  static std::vector<GtlcPrimvarDesc> toPrimvarDescs(const std::vector<GiPrimvarData>& primvars)
+  {
+    static_assert((int) GiPrimvarType::Int4 == GTLC_PRIMVAR_INT4 && (int) GiPrimvarInterpolation::Vertex == GTLC_INTERP_VERTEX, "enum values must match");
+    std::vector<GtlcPrimvarDesc> out(primvars.size());
+    for (size_t i = 0; i < primvars.size(); i++) {
+      out[i].name = primvars[i].name.c_str(); out[i].type = (int32_t) primvars[i].type; out[i].interpolation = (int32_t) primvars[i].interpolation;
+      out[i].data = primvars[i].data.data(); out[i].dataSize = primvars[i].data.size();
+    }
+    return out;
+  }
+
   GiMesh* giCreateMesh(GiScene* scene, const GiMeshDesc& desc)
   {
     if (!scene) return nullptr;
@@ -381,11 +416,18 @@ namespace gtl
     d.faceIds = desc.faceIds.size() == desc.faceCount ? reinterpret_cast<const int32_t*>(desc.faceIds.data()) : nullptr;
     d.id = desc.id; d.isDoubleSided = desc.isDoubleSided; d.isLeftHanded = desc.isLeftHanded; d.name = desc.name; d.maxFaceId = desc.maxFaceId;
     d.vertexCount = desc.vertexCount; d.vertices = reinterpret_cast<const GtlcVertex*>(desc.vertices.data());
+    std::vector<GtlcPrimvarDesc> pv = toPrimvarDescs(desc.primvars);
+    d.primvars = pv.empty() ? nullptr : pv.data(); d.primvarCount = (uint32_t) pv.size(); d.reserved = 0;
     return wrap<GiMesh>(gtlc_mesh_create(scene->h, &d));
   }
   void giSetMeshTransform(GiMesh* m, const float* mat4x4) { if (m) gtlc_mesh_set_transform(m->h, mat4x4); }
   void giSetMeshInstanceTransforms(GiMesh* m, uint32_t count, const float (*t)[4][4]) { if (m) gtlc_mesh_set_instance_transforms(m->h, count, reinterpret_cast<const float*>(t)); }
-  void giSetMeshInstancerPrimvars(GiMesh*, const std::vector<GiPrimvarData>&) { /* primvar readers: SURVEY.md 8f rank 2 */ }
+  void giSetMeshInstancerPrimvars(GiMesh* m, const std::vector<GiPrimvarData>& primvars)
+  {
+    if (!m) return;
+    std::vector<GtlcPrimvarDesc> pv = toPrimvarDescs(primvars);
+    gtlc_mesh_set_instancer_primvars(m->h, (uint32_t) pv.size(), pv.empty() ? nullptr : pv.data());
+  }
   void giSetMeshInstanceIds(GiMesh* m, uint32_t count, int* ids) { if (m) gtlc_mesh_set_instance_ids(m->h, count, ids); }
   void giSetMeshMaterial(GiMesh* m, GiMaterial* mat) { if (m) gtlc_mesh_set_material(m->h, mat ? mat->h : 0); }
   void giSetMeshVisibility(GiMesh* m, bool visible) { if (m) gtlc_mesh_set_visibility(m->h, visible); }

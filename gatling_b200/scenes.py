@@ -75,12 +75,31 @@ class TextureBinding:   # GtlcTextureBinding: UsdUVTexture (+ UsdTransform2d) fe
     uv_translation: tuple = (0.0, 0.0)
 
 
+INTERP_CONSTANT, INTERP_INSTANCE, INTERP_UNIFORM, INTERP_VERTEX = 0, 1, 2, 3
+
+
+@dataclasses.dataclass
+class Primvar:           # GiPrimvarData (float types): data float32[elements, 1..4]
+    name: str
+    interpolation: int
+    data: np.ndarray
+
+
+@dataclasses.dataclass
+class PrimvarBinding:    # GtlcPrimvarBinding: a material input read from a primvar of the hit mesh
+    param: int
+    count: int
+    name: str
+    fallback: tuple = (0.0, 0.0, 0.0, 0.0)
+
+
 @dataclasses.dataclass
 class Material:
     closure: int
     params: np.ndarray  # float32[48]
     name: str = ""
     textures: list = dataclasses.field(default_factory=list)   # TextureBinding
+    primvars: list = dataclasses.field(default_factory=list)   # PrimvarBinding
 
 
 def material_diffuse(tint, name="") -> Material:
@@ -135,6 +154,9 @@ class Mesh:
     left_handed: bool = False
     object_id: int = 0
     name: str = ""
+    primvars: list = dataclasses.field(default_factory=list)             # Primvar
+    instancer_primvars: list = dataclasses.field(default_factory=list)   # Primvar (giSetMeshInstancerPrimvars)
+    instance_ids: Optional[np.ndarray] = None                            # giSetMeshInstanceIds; None = 0..n-1
 
 
 @dataclasses.dataclass
@@ -457,6 +479,55 @@ def textured_cornell(width=96, height=96, spp=8, max_bounces=5, nee=True) -> Sce
     if nee:
         d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
         d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
+    return d
+
+
+# ---- primvar-driven inputs (R15 scene data test scene) ------------------------------------------
+def primvar_cornell(width=96, height=96, spp=8, max_bounces=5) -> SceneDesc:
+    """Cornell box shaded by one UsdPreviewSurface whose diffuseColor reads the primvar `displayColor` and whose
+    roughness reads `rough`: per-vertex colours (floor), per-face colours (back wall), per-instance colours through
+    instancer primvars and shuffled instance ids (short box, 4 instances), a mesh primvar overriding the instancer's
+    (tall box), constant primvars, a too-short array and a missing primvar (fallbacks)."""
+    d = cornell(width, height, spp, max_bounces)
+    pv = material_usd_preview_surface("Primvars", diffuse=(0.5, 0.5, 0.5), roughness=0.5)
+    pv.primvars = [PrimvarBinding(UPS["diffuse"], 3, "displayColor", (0.1, 0.2, 0.9, 0.0)), PrimvarBinding(UPS["roughness"], 1, "rough", (0.9, 0.0, 0.0, 0.0))]
+    d.materials = list(d.materials) + [pv]
+    mat = len(d.materials) - 1
+    rnd = lambda seed, n, c: pcg32_uniform(seed, n * c).reshape(n, c).astype(np.float32)
+    for i, m in enumerate(d.meshes):
+        if m.name == "Light":
+            continue
+        m = dataclasses.replace(m, material=mat)
+        if m.name == "BottomPlane":
+            m.primvars = [Primvar("displayColor", INTERP_VERTEX, rnd(11, len(m.vertices), 3)), Primvar("rough", INTERP_CONSTANT, np.array([[0.15]], np.float32))]
+        elif m.name == "BackPlane":
+            m.primvars = [Primvar("displayColor", INTERP_UNIFORM, rnd(12, len(m.faces), 3)), Primvar("rough", INTERP_UNIFORM, 0.2 + 0.6 * rnd(13, len(m.faces), 1))]
+        elif m.name == "LeftPlane":
+            m.primvars = [Primvar("displayColor", INTERP_VERTEX, rnd(14, 2, 3))]           # too short for the vertex count: ignored -> fallback
+        elif m.name == "Box2":
+            # four small copies, well separated and of different heights: overlapping or coplanar instances would z-fight,
+            # and which copy wins then depends on the last ulp of the ray (libm vs CUDA sin/cos)
+            mt = np.asarray(m.transform, np.float32)
+            wp = m.vertices["pos"] @ mt[:3, :3] + mt[3, :3]
+            lo, hi = wp.min(0), wp.max(0)
+            pivot = np.array([(lo[0] + hi[0]) / 2, (lo[1] + hi[1]) / 2, lo[2]], np.float64)
+            xf = []
+            for k, (tx, ty) in enumerate(((-0.6, -0.55), (0.05, -0.7), (0.6, -0.2), (0.55, 0.45))):
+                sc = 0.35 + 0.05 * k
+                t = np.eye(4, dtype=np.float64)
+                t[0, 0] = t[1, 1] = t[2, 2] = sc
+                t[3, :3] = np.array([tx, ty, pivot[2]]) - pivot * sc          # p' = (p - pivot) * sc + target
+                xf.append(t.astype(np.float32))
+            m.instance_transforms = np.stack(xf)
+            m.instance_ids = np.array([3, 1, 0, 2], np.int32)
+            m.instancer_primvars = [Primvar("displayColor", INTERP_INSTANCE, rnd(15, 4, 3)), Primvar("rough", INTERP_INSTANCE, 0.25 + 0.6 * rnd(16, 4, 1))]   # (well away from mirror-like: a near-delta GGX lobe amplifies last-ulp differences between CPU and GPU)
+        elif m.name == "Box1":
+            m.instancer_primvars = [Primvar("displayColor", INTERP_CONSTANT, np.array([[1.0, 0.0, 1.0]], np.float32))]
+            m.primvars = [Primvar("displayColor", INTERP_VERTEX, rnd(17, len(m.vertices), 4))]   # vec4 primvar read as colour; overrides the instancer's
+        d.meshes[i] = m            # TopPlane / RightPlane: no primvars at all -> fallbacks
+    d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
+    d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
+    d.name = "primvar_cornell"
     return d
 
 

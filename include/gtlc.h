@@ -58,8 +58,20 @@ typedef struct GtlcFace {
   uint32_t v_i[3];
 } GtlcFace;
 
-/* GiMeshDesc, Gi.h:124-137 with the std::vector references flattened to pointer + count.
- * Primvars (scene data) are a "next" row and not part of this struct yet. */
+/* GiPrimvarData, Gi.h:77-93 ("scene data" of the MDL runtime, mdl_interface.glsl:266-479) */
+enum GtlcPrimvarType { GTLC_PRIMVAR_FLOAT = 0, GTLC_PRIMVAR_VEC2, GTLC_PRIMVAR_VEC3, GTLC_PRIMVAR_VEC4,
+                       GTLC_PRIMVAR_INT, GTLC_PRIMVAR_INT2, GTLC_PRIMVAR_INT3, GTLC_PRIMVAR_INT4 };
+enum GtlcPrimvarInterpolation { GTLC_INTERP_CONSTANT = 0, GTLC_INTERP_INSTANCE, GTLC_INTERP_UNIFORM, GTLC_INTERP_VERTEX };
+typedef struct GtlcPrimvarDesc {
+  const char* name;
+  int32_t     type;            /* GtlcPrimvarType */
+  int32_t     interpolation;   /* GtlcPrimvarInterpolation: constant = element 0, instance = element instanceId,
+                                  uniform = one element per face, vertex = one per vertex (barycentric interpolation) */
+  const void* data;
+  uint64_t    dataSize;        /* bytes */
+} GtlcPrimvarDesc;
+
+/* GiMeshDesc, Gi.h:124-137 with the std::vector references flattened to pointer + count. */
 typedef struct GtlcMeshDesc {
   uint32_t          faceCount;
   const GtlcFace*   faces;
@@ -71,6 +83,9 @@ typedef struct GtlcMeshDesc {
   uint32_t          maxFaceId;
   uint32_t          vertexCount;
   const GtlcVertex* vertices;
+  const GtlcPrimvarDesc* primvars;   /* may be NULL */
+  uint32_t          primvarCount;
+  uint32_t          reserved;
 } GtlcMeshDesc;
 
 /* GiCameraDesc, Gi.h:95-107 */
@@ -223,13 +238,25 @@ typedef struct GtlcTextureBinding {
   float      reserved;
 } GtlcTextureBinding;
 
+/* A material input read from a primvar of the hit mesh (MaterialX geompropvalue / UsdPrimvarReader -> MDL
+ * scene_data_lookup_float{,2,3}, mdl_interface.glsl:266-479): value = v0 bc.x + v1 bc.y + v2 bc.z over the elements the
+ * primvar's interpolation selects; `fallback` when the mesh has no float primvar of that name. */
+#define GTLC_MAX_PRIMVAR_BINDINGS 8
+typedef struct GtlcPrimvarBinding {
+  int32_t     paramIndex;      /* first float of GtlcMaterialDesc.params that receives the value */
+  int32_t     componentCount;  /* 1..3 */
+  const char* name;            /* primvar name, e.g. "displayColor" */
+  float       fallback[4];
+} GtlcPrimvarBinding;
+
 typedef struct GtlcMaterialDesc {
   int32_t     closure;                           /* GTLC_CLOSURE_* */
   const char* name;                              /* may be NULL */
   float       params[GTLC_MATERIAL_PARAM_COUNT]; /* see enums above */
   const GtlcTextureBinding* textures;            /* optional; applied in order per shaded hit */
   uint32_t    textureCount;
-  uint32_t    reserved;
+  uint32_t    primvarCount;                      /* <= GTLC_MAX_PRIMVAR_BINDINGS */
+  const GtlcPrimvarBinding* primvars;            /* optional; applied before the textures */
 } GtlcMaterialDesc;
 
 /* Fill `desc` with the closure's spec defaults (UsdPreviewSurface spec / open_pbr_surface.mtlx:4-97). */
@@ -259,6 +286,7 @@ GTLC_API GtlcHandle gtlc_mesh_create(GtlcHandle scene, const GtlcMeshDesc* desc)
 GTLC_API void gtlc_mesh_set_transform(GtlcHandle mesh, const float* mat4x4);                /* giSetMeshTransform: USD row-major float[16] */
 GTLC_API void gtlc_mesh_set_instance_transforms(GtlcHandle mesh, uint32_t count, const float* transforms4x4); /* giSetMeshInstanceTransforms */
 GTLC_API void gtlc_mesh_set_instance_ids(GtlcHandle mesh, uint32_t count, const int32_t* ids);               /* giSetMeshInstanceIds */
+GTLC_API void gtlc_mesh_set_instancer_primvars(GtlcHandle mesh, uint32_t count, const GtlcPrimvarDesc* primvars);  /* giSetMeshInstancerPrimvars */
 GTLC_API void gtlc_mesh_set_material(GtlcHandle mesh, GtlcHandle material);                 /* giSetMeshMaterial */
 GTLC_API void gtlc_mesh_set_visibility(GtlcHandle mesh, int32_t visible);                   /* giSetMeshVisibility */
 GTLC_API void gtlc_mesh_destroy(GtlcHandle mesh);                                           /* giDestroyMesh */

@@ -92,6 +92,7 @@ struct AovSample {
   bool thinWalled, doubleSided;
   int32_t objectId, faceId, instanceId; float depth;
   float cutoutOpacity;   // < 0: the material has no cutout (chit:202), else ahit:48
+  bool neeRan, neeShadowed;   // rgen:431-436 (first bounce, NEXT_EVENT_ESTIMATION builds only)
 };
 
 // colormap.glsl:42-53
@@ -350,6 +351,26 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
   // re-evaluates them inside every generated mdl_* function; same values)
   Material mat = base;
   V3 mappedNormal = normal; bool hasMappedNormal = false;
+  if (!s.materialPrimvars.empty() && !s.materialPrimvars[in.material].empty() && !s.primvarInfos.empty()) {   // scene_data_lookup_float{,2,3}
+    const std::vector<GtlcPrimvarBinding>& pbs = s.materialPrimvars[in.material];
+    const V3 bc = v3((1.0f - hit.u) - hit.v, hit.u, hit.v);                                     // mdl_interface.glsl:318
+    const uint32_t* f = &s.faces[(size_t) (in.faceBase + hit.prim) * 3];
+    for (size_t k = 0; k < pbs.size(); k++) {
+      const uint32_t* info = &s.primvarInfos[((size_t) hit.inst * GTLC_MAX_PRIMVAR_BINDINGS + k) * 2];
+      if (!(info[1] & 0x100u)) { for (int cidx = 0; cidx < pbs[k].componentCount; cidx++) mat.p[pbs[k].paramIndex + cidx] = pbs[k].fallback[cidx]; continue; }
+      const uint32_t stride = info[1] & 15u, interpolation = (info[1] >> 4) & 15u;
+      uint32_t idx[3] = { f[0], f[1], f[2] };                                                   // :281-301
+      if (interpolation == GTLC_INTERP_UNIFORM) idx[0] = idx[1] = idx[2] = hit.prim;
+      else if (interpolation == GTLC_INTERP_INSTANCE) idx[0] = idx[1] = idx[2] = in.instanceId > 0 ? (uint32_t) in.instanceId : 0u;
+      else if (interpolation == GTLC_INTERP_CONSTANT) idx[0] = idx[1] = idx[2] = 0u;
+      const float* dta = &s.primvarData[info[0]];
+      for (int cidx = 0; cidx < pbs[k].componentCount; cidx++) {
+        float v[3];
+        for (int q = 0; q < 3; q++) v[q] = cidx < (int) stride ? dta[(size_t) idx[q] * stride + cidx] : 0.0f;
+        mat.p[pbs[k].paramIndex + cidx] = (v[0] * bc.x + v[1] * bc.y) + v[2] * bc.z;
+      }
+    }
+  }
   if (!s.materialTextures.empty() && !s.materialTextures[in.material].empty())
     hasMappedNormal = apply_texture_bindings(s.textures, s.materialTextures[in.material], st.text_coords.x, st.text_coords.y, worldRayDir,
                                              st.geom_normal, st.normal, st.tangent_u, st.tangent_v, mat.p, mappedNormal);
@@ -501,7 +522,7 @@ static inline void sampleVolumeScatteringDirection(V2 xi, float bias, V3& dir)
 // rp_main.rgen:215-499: one sample of one pixel; returns the clamped sample colour.
 static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint32_t pixelIndex, uint32_t s, RayCounters& rc, AovSample* aov = nullptr)
 {
-  if (aov) { aov->hit = false; aov->bounces = 0; }
+  if (aov) { aov->hit = false; aov->bounces = 0; aov->neeRan = false; aov->neeShadowed = false; }
   const Ubo& ubo = c.ubo;
   uint32_t sampleIndex = ubo.sampleOffset + s;                            // :217
   uint32_t rng_state = rng1d_init(pixelIndex, sampleIndex);               // :223
@@ -564,8 +585,10 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
         Hit sh;
         shadowed = scene_trace(*c.s, shadowray_origin, shadowray_dir, stMin, stMax, true, sh, p.rng_state);   // :399 shadow payload rng
       }
+      else shadowed = false;              // tMin = tMax = 0: no traversal, the shadow miss shader still runs (rp_main_shadow.miss)
       bool addContrib = traceRay && !shadowed;                            // :426
       if (addContrib) p.radiance += p.neeContrib;                         // :429
+      if (aov && bounce == 0) { aov->neeRan = true; aov->neeShadowed = shadowed; }   // :431-436
     }
     if (length(p.throughput) < 1e-9f) p.bitfield |= PAYLOAD_TERMINATE_FLAG; // :441-444
     if (bounce > rrBounceOffset) {                                        // :447-459
@@ -605,6 +628,9 @@ struct OrcSceneDesc {
   float domeRotation[4]; float domeEmission[3]; uint32_t pad;
   const int32_t* faceIds;   // optional: one per face of the global face array (GiMeshDesc.faceIds)
   const GtlcTextureDesc* textures; uint32_t textureCount; uint32_t pad2;   // R15; GtlcTextureBinding.texture = 1-based index
+  // R15 scene data, resolved by the caller: column k of an instance's row belongs to binding k of its material
+  const uint32_t* primvarInfos;   // instanceCount x GTLC_MAX_PRIMVAR_BINDINGS x (float offset, stride | interpolation << 4 | valid << 8)
+  const float* primvarData; uint64_t primvarDataCount;
 };
 
 struct OrcRenderDesc {
@@ -628,6 +654,7 @@ void* orc_scene_create(const OrcSceneDesc* d)
     s->materials.push_back(m);
     const GtlcMaterialDesc& md = d->materials[i];
     s->materialTextures.emplace_back(md.textures, md.textures + (md.textures ? md.textureCount : 0));
+    s->materialPrimvars.emplace_back(md.primvars, md.primvars + (md.primvars ? md.primvarCount : 0));
   }
   for (uint32_t i = 0; i < d->textureCount; i++) {
     const GtlcTextureDesc& td = d->textures[i];
@@ -636,6 +663,8 @@ void* orc_scene_create(const OrcSceneDesc* d)
     t.data.assign((const uint8_t*) td.texels, (const uint8_t*) td.texels + (size_t) td.width * td.height * bpt);
     s->textures.push_back(t);
   }
+  if (d->primvarInfos) s->primvarInfos.assign(d->primvarInfos, d->primvarInfos + (size_t) d->instanceCount * GTLC_MAX_PRIMVAR_BINDINGS * 2);
+  if (d->primvarData) s->primvarData.assign(d->primvarData, d->primvarData + d->primvarDataCount);
   if (d->sphereLightCount) s->sphereLights.assign(d->sphereLights, d->sphereLights + d->sphereLightCount);
   if (d->distantLightCount) s->distantLights.assign(d->distantLights, d->distantLights + d->distantLightCount);
   if (d->rectLightCount) s->rectLights.assign(d->rectLights, d->rectLights + d->rectLightCount);
@@ -795,6 +824,7 @@ double orc_render_aovs(void* h, const OrcRenderDesc* r, float* rgba, uint64_t* r
           accumulate(GTLC_AOV_NORMAL, as.posNormal);
           accumulate(GTLC_AOV_ALBEDO, as.albedo);
         }
+        if (has(GTLC_AOV_NEE) && as.neeRan) { float* b = v3buf(GTLC_AOV_NEE); b[0] = as.neeShadowed ? 1.0f : 0.0f; b[1] = as.neeShadowed ? 0.0f : 1.0f; b[2] = 0.0f; }   // rgen:431-436
         if (has(GTLC_AOV_BOUNCES)) { V3 cm = colormap_inferno((float) as.bounces / (float) maxBounces); float* b = v3buf(GTLC_AOV_BOUNCES); b[0] = cm.x; b[1] = cm.y; b[2] = cm.z; }   // rgen:483-486
       }
       V3 prevColor = pixel_color;

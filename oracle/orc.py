@@ -30,9 +30,17 @@ class TextureBinding(C.Structure):  # GtlcTextureBinding
                 ("uvTranslation", C.c_float * 2), ("reserved", C.c_float)]
 
 
+class PrimvarBinding(C.Structure):  # GtlcPrimvarBinding
+    _fields_ = [("paramIndex", C.c_int32), ("componentCount", C.c_int32), ("name", C.c_char_p), ("fallback", C.c_float * 4)]
+
+
 class MaterialDesc(C.Structure):  # GtlcMaterialDesc
     _fields_ = [("closure", C.c_int32), ("name", C.c_char_p), ("params", C.c_float * 48),
-                ("textures", C.POINTER(TextureBinding)), ("textureCount", C.c_uint32), ("reserved", C.c_uint32)]
+                ("textures", C.POINTER(TextureBinding)), ("textureCount", C.c_uint32), ("primvarCount", C.c_uint32),
+                ("primvars", C.POINTER(PrimvarBinding))]
+
+
+MAX_PRIMVAR_BINDINGS = 8
 
 
 class CameraDesc(C.Structure):  # GtlcCameraDesc
@@ -80,7 +88,8 @@ class SceneDescC(C.Structure):
                 ("diskLights", C.c_void_p), ("diskLightCount", C.c_uint32),
                 ("domeTexels", C.c_void_p), ("domeW", C.c_uint32), ("domeH", C.c_uint32),
                 ("domeRotation", C.c_float * 4), ("domeEmission", C.c_float * 3), ("pad", C.c_uint32), ("faceIds", C.c_void_p),
-                ("textures", C.POINTER(TextureDesc)), ("textureCount", C.c_uint32), ("pad2", C.c_uint32)]
+                ("textures", C.POINTER(TextureDesc)), ("textureCount", C.c_uint32), ("pad2", C.c_uint32),
+                ("primvarInfos", C.c_void_p), ("primvarData", C.c_void_p), ("primvarDataCount", C.c_uint64)]
 
 
 class AovDescC(C.Structure):
@@ -229,7 +238,7 @@ class OracleScene:
                 rec["faceCount"] = len(m.faces)
                 rec["flags"] = flags
                 rec["material"] = m.material
-                rec["instanceId"] = k
+                rec["instanceId"] = k if getattr(m, "instance_ids", None) is None else int(m.instance_ids[k])
                 rec["objectId"] = m.object_id
                 rec["objectToWorld"] = compose_transform(m.transform, ixf)
                 inst.append(rec)
@@ -261,6 +270,14 @@ class OracleScene:
                 self._keep.append(arr)
                 self.mats[i].textures = arr
                 self.mats[i].textureCount = len(m.textures)
+            if getattr(m, "primvars", None):
+                parr = (PrimvarBinding * len(m.primvars))()
+                for k, b in enumerate(m.primvars):
+                    parr[k].paramIndex, parr[k].componentCount, parr[k].name = b.param, b.count, b.name.encode()
+                    parr[k].fallback = (C.c_float * 4)(*b.fallback)
+                self._keep.append(parr)
+                self.mats[i].primvars = parr
+                self.mats[i].primvarCount = len(m.primvars)
         self.sp, self.di, self.re, self.dk = light_arrays(desc)
         d = SceneDescC()
         d.vertices = self.vertices.ctypes.data
@@ -285,6 +302,41 @@ class OracleScene:
             d.domeH, d.domeW = self.dome.shape[0], self.dome.shape[1]
             d.domeRotation = (C.c_float * 4)(*desc.dome_light.rotation)
             d.domeEmission = (C.c_float * 3)(*desc.dome_light.base_emission)
+        # scene data (Gi.cpp:905-1018): per instance, the primvar each binding of its material resolves to --
+        # mesh primvars override instancer primvars; too-short arrays and integer types count as "not found"
+        if any(getattr(m, "primvars", None) for m in desc.materials):
+            infos = np.zeros((len(self.instances), MAX_PRIMVAR_BINDINGS, 2), np.uint32)
+            chunks, offset, row = [], 0, 0
+            for m in desc.meshes:
+                n_inst = 1 if m.instance_transforms is None else len(m.instance_transforms)
+                ids = np.arange(n_inst) if getattr(m, "instance_ids", None) is None else np.asarray(m.instance_ids)
+                resolved = []
+                for k, b in enumerate(desc.materials[m.material].primvars[:MAX_PRIMVAR_BINDINGS]):
+                    found = None
+                    for p in list(getattr(m, "instancer_primvars", [])) + list(getattr(m, "primvars", [])):
+                        if p.name == b.name and np.size(p.data):
+                            found = p
+                    if found is None:
+                        resolved.append((0, 0))
+                        continue
+                    a = np.ascontiguousarray(found.data, np.float32)
+                    a = a.reshape(len(a), -1)
+                    need = {0: 1, 1: int(max(ids.max(), 0)) + 1, 2: len(m.faces), 3: len(m.vertices)}[found.interpolation]
+                    if len(a) < need:
+                        resolved.append((0, 0))
+                        continue
+                    resolved.append((offset, a.shape[1] | (found.interpolation << 4) | 0x100))
+                    chunks.append(a.reshape(-1))
+                    offset += a.size
+                for _ in range(n_inst):
+                    for k, r in enumerate(resolved):
+                        infos[row, k] = r
+                    row += 1
+            self.pv_infos = np.ascontiguousarray(infos)
+            self.pv_data = np.ascontiguousarray(np.concatenate(chunks)) if chunks else np.zeros(1, np.float32)
+            d.primvarInfos = self.pv_infos.ctypes.data
+            d.primvarData = self.pv_data.ctypes.data
+            d.primvarDataCount = len(self.pv_data)
         if getattr(desc, "textures", None):
             self.texs = (TextureDesc * len(desc.textures))()
             for i, t in enumerate(desc.textures):

@@ -115,6 +115,8 @@ struct Scene {
   std::vector<Material> materials;
   std::vector<Texture> textures;                                   // R15
   std::vector<std::vector<GtlcTextureBinding>> materialTextures;   // per material; .texture = 1-based index into `textures`
+  std::vector<std::vector<GtlcPrimvarBinding>> materialPrimvars;   // per material (names already resolved into primvarInfos)
+  std::vector<uint32_t> primvarInfos; std::vector<float> primvarData;
   std::vector<SphereLight> sphereLights;
   std::vector<DistantLight> distantLights;
   std::vector<RectLight> rectLights;

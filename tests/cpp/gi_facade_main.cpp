@@ -67,8 +67,20 @@ static const char* kOpbrNormalMap =
   "<open_pbr_surface name=\"S\" type=\"surfaceshader\"><input name=\"geometry_normal\" type=\"vector3\" nodename=\"nm\"/>"
   "<input name=\"base_color\" type=\"color3\" nodename=\"col\"/><input name=\"specular_roughness\" type=\"float\" nodename=\"noise_graph\"/></open_pbr_surface></materialx>";
 
+static const char* kPrimvarUps =
+  "<materialx version=\"1.38\"><UsdPrimvarReader name=\"dc\" type=\"color3\"><input name=\"varname\" type=\"string\" value=\"displayColor\"/>"
+  "<input name=\"fallback\" type=\"color3\" value=\"0.1, 0.2, 0.9\"/></UsdPrimvarReader>"
+  "<geompropvalue name=\"r\" type=\"float\"><input name=\"geomprop\" type=\"string\" value=\"rough\"/><input name=\"default\" type=\"float\" value=\"0.9\"/></geompropvalue>"
+  "<UsdPreviewSurface name=\"S\" type=\"surfaceshader\"><input name=\"diffuseColor\" type=\"color3\" nodename=\"dc\"/>"
+  "<input name=\"roughness\" type=\"float\" nodename=\"r\"/></UsdPreviewSurface></materialx>";
+
 static int lowerTextureTests()
 {
+  {
+    GtlcMaterialDesc pd; std::vector<GtlcTextureBinding> pb; std::vector<std::string> pf;
+    if (!giLowerMtlxToClosureWithTextures(kPrimvarUps, "P", &pd, &pb, &pf) || !pb.empty() || pd.primvarCount != 2) return 40;
+    if (pf.size() != 2 || pf[0] != "primvar:displayColor:" + std::to_string((int) GTLC_UPS_DIFFUSE_R) + ":3" || pf[1] != "primvar:rough:" + std::to_string((int) GTLC_UPS_ROUGHNESS) + ":1") return 41;
+  }
   GtlcMaterialDesc d; std::vector<GtlcTextureBinding> b; std::vector<std::string> files;
   if (!giLowerMtlxToClosureWithTextures(texturedUps("checker.ppm").c_str(), "T", &d, &b, &files)) return 20;
   if (b.size() != 3 || files.size() != 3 || d.params[GTLC_UPS_METALLIC] != 0.25f || d.params[GTLC_UPS_ROUGHNESS] != 0.5f) return 21;   // connected inputs keep the default constant

@@ -14,7 +14,7 @@ from gatling_b200 import _lib, gi, scenes
 def test_exports_every_declared_symbol():
     lib = _lib.load()
     names = _lib.declared_symbols()
-    assert len(names) == 59
+    assert len(names) == 60
     for n in names:
         assert hasattr(lib, n), "libgtlc.so does not export %s" % n
     assert set(names) == set(_lib._SIGNATURES), "python binding and header disagree"
@@ -25,7 +25,7 @@ def test_struct_layouts_match_header(tmp_path):
     import subprocess
     names = {"GtlcMaterialDesc": _lib.MaterialDesc, "GtlcCameraDesc": _lib.CameraDesc, "GtlcRenderSettings": _lib.RenderSettings,
              "GtlcAovBinding": _lib.AovBinding, "GtlcMeshDesc": _lib.MeshDesc, "GtlcTextureDesc": _lib.TextureDesc,
-             "GtlcTextureBinding": _lib.TextureBinding, "GtlcTuning": _lib.Tuning, "GtlcStats": _lib.Stats, "GtlcBvhView": _lib.BvhView,
+             "GtlcTextureBinding": _lib.TextureBinding, "GtlcPrimvarDesc": _lib.PrimvarDesc, "GtlcPrimvarBinding": _lib.PrimvarBinding, "GtlcTuning": _lib.Tuning, "GtlcStats": _lib.Stats, "GtlcBvhView": _lib.BvhView,
              "GtlcRenderParams": _lib.RenderParams}
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "gtlc.h"\nint main(void) {\n' +
@@ -35,7 +35,7 @@ def test_struct_layouts_match_header(tmp_path):
     out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
     for n, t in names.items():
         assert C.sizeof(t) == int(out[n]), n
-    assert C.sizeof(_lib.MaterialDesc) == 4 + 4 + 8 + 48 * 4 + 8 + 4 + 4
+    assert C.sizeof(_lib.MaterialDesc) == 4 + 4 + 8 + 48 * 4 + 8 + 4 + 4 + 8
     assert scenes.VERTEX_DTYPE.itemsize == 48
 
 

@@ -69,7 +69,11 @@ def test_trace_edge_cases(gpu):
         b.close()
 
 
-def _render_parity(gi, desc, rmse_bar=1e-3, within_bar=0.999):
+def _render_parity(gi, desc, rmse_bar=1e-3, within_bar=0.999, flipped_samples=0):
+    """`flipped_samples` > 0: the scene makes path decisions (lobe choice, Russian roulette, shadow tests) from values that
+    pass through libm on the CPU and CUDA's math library on the GPU; a last-ulp difference can flip one decision and with
+    it one whole sample (up to maxSampleValue / spp in one pixel).  Such a test tolerates that many outlier pixels in the
+    RMSE and the same number of rays in the counts; the 99.9 % criterion is unchanged."""
     b = gi.BuiltScene(desc)
     try:
         o = orc.OracleScene(desc)
@@ -77,9 +81,13 @@ def _render_parity(gi, desc, rmse_bar=1e-3, within_bar=0.999):
         ref, _, rays = o.render()
         st = gi.get_stats()
         rmse, within = image_metrics(img, ref)
+        if flipped_samples:
+            err = ((img[..., :3].astype(np.float64) - ref[..., :3]) ** 2).sum(-1).reshape(-1)
+            rmse = float(np.sqrt(np.sort(err)[:-flipped_samples].sum() / (3 * err.size)))
         assert rmse < rmse_bar, "RMSE %.3e" % rmse
         assert within >= within_bar, "only %.5f of channels within tolerance" % within
-        assert st["closestRays"] == rays[0] and st["shadowRays"] == rays[1], (st, rays)
+        slack = 8 * flipped_samples
+        assert abs(st["closestRays"] - rays[0]) <= slack and abs(st["shadowRays"] - rays[1]) <= slack, (st, rays)
         assert np.all(img[..., 3] == 1.0)
         return img, ref
     finally:
@@ -222,7 +230,7 @@ def test_material_sort_is_invisible(gpu):
     assert np.array_equal(imgs[0], imgs[1])
 
 
-AOVS = [0, 1, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]   # everything but the NEE / ClockCycles debug AOVs
+AOVS = [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]   # everything but the ClockCycles debug AOV (a per-pixel timer of the megakernel)
 INT_AOVS = (11, 13, 14)
 
 
@@ -238,7 +246,10 @@ def _aov_parity(gi, desc, second_call=False):
             ref = o.render_aovs(AOVS, clear, sample_offset=desc.settings.spp, prev=ref)
         for aov in AOVS:
             g, r = got[gi.GiAovId(aov)], ref[aov]
-            if aov in INT_AOVS:
+            if aov == 2:               # NEE debug AOV: red / green per pixel; a shadow test may flip with the last ulp of the light sample
+                assert (np.abs(g[..., :3] - r[..., :3]).max(-1) > 0).mean() < 2e-3, "NEE AOV differs on %.4f of the pixels" % (np.abs(g[..., :3] - r[..., :3]).max(-1) > 0).mean()
+                assert len(np.unique(g[..., :3].reshape(-1, 3), axis=0)) >= (2 if desc.settings.nextEventEstimation else 1)
+            elif aov in INT_AOVS:
                 assert (g != r).mean() < 1e-3, "integer AOV %d differs on %.4f of the pixels" % (aov, (g != r).mean())
             else:
                 diff = np.abs(g[..., :3 if g.shape[-1] == 4 else 1].astype(np.float64) - r[..., :3 if r.shape[-1] == 4 else 1])
@@ -505,4 +516,25 @@ def test_full_size_properties_c2(gpu):
         assert np.abs(p_bary - p_ray).max() < 2e-5
     finally:
         gpu.set_tuning(maxPathsPerWave=1 << 24)
+        b.close()
+
+
+def test_render_parity_primvars(gpu):
+    """R15 scene data: material inputs read from mesh / instancer primvars (constant, instance, uniform, vertex
+    interpolation; overrides, fallbacks) -- image and AOVs against the oracle."""
+    d = scenes.primvar_cornell(96, 96, spp=8)
+    img, _ = _render_parity(gpu, d, flipped_samples=4)
+    got = _aov_parity(gpu, dataclasses.replace(d, width=48, height=48))
+    alb = got[gpu.GiAovId.Albedo][..., :3]
+    assert len(np.unique(np.round(alb.reshape(-1, 3), 3), axis=0)) > 50
+    # a primvar whose array is too short for its interpolation is ignored, loudly
+    assert "ignored" in gpu.giLastError() and "LeftPlane" in gpu.giLastError()
+    # instancer primvars set after the fact dirty the scene
+    b = gpu.BuiltScene(d)
+    try:
+        first = b.render().copy()
+        box2 = [i for i, m in enumerate(d.meshes) if m.name == "Box2"][0]
+        gpu.giSetMeshInstancerPrimvars(b.meshes[box2], [scenes.Primvar("displayColor", scenes.INTERP_INSTANCE, np.full((4, 3), 0.05, np.float32))])
+        assert np.abs(b.render() - first).mean() > 1e-4
+    finally:
         b.close()

@@ -77,7 +77,7 @@ def test_textured_render_changes_the_albedo_and_the_image():
     ref = p.render()[0]
     assert np.isfinite(img).all() and np.abs(img - ref).mean() > 1e-2
     # the floor's checker shows up in the albedo AOV: two clearly separated populations of red values
-    alb = o.render_aovs([4])[4]
+    alb = o.render_aovs([16])[16]
     floor = alb[2:14, 8:40, 0]
     assert floor.std() > 0.1
     # the unmapped Normal AOV is untouched by the normal map (rp_main.chit:147,252 use the copy taken before *_init)
