@@ -10,6 +10,9 @@
   oracle's outputs; integer functions are additionally cross-checked against an independent numpy
   restatement in tests/test_oracle_kat.py.
 * cornell_oracle_32.npy -- float32 32x32 spp 4 oracle render of C1 (regression anchor for the oracle).
+* feature_anchors.npz  -- 32x32 spp 4 oracle renders of the texture / primvar / volume / cutout test scenes plus
+  their ray counts: the -m gpu suite compares the CUDA path against these committed images as well as against a
+  fresh oracle run, so an accidental change of the oracle itself cannot go unnoticed.
 """
 import ctypes as C
 import hashlib
@@ -105,6 +108,26 @@ def kat():
     return k
 
 
+def feature_scenes():
+    import dataclasses
+    lit = scenes.cornell(32, 32, spp=4, max_bounces=5)
+    lit.settings = dataclasses.replace(lit.settings, nextEventEstimation=True)
+    lit.rect_lights.append(scenes.RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(12, 12, 12), width=0.6, height=0.6))
+    lit.sphere_lights.append(scenes.SphereLight(position=(0.5, -0.5, 0.2), base_emission=(4, 3, 2), radius=(0.1, 0.1, 0.1)))
+    return {"textured": scenes.textured_cornell(32, 32, spp=4), "primvars": scenes.primvar_cornell(32, 32, spp=4),
+            "volumes": scenes.volume_cornell(32, 32, spp=4, medium_stack_size=2), "nee": lit,
+            "stress": scenes.material_stress(tris_per_mesh=200, meshes=12, width=32, height=32, spp=4)}
+
+
+def feature_anchors():
+    out = {}
+    for name, d in feature_scenes().items():
+        img, _, rays = orc.OracleScene(d).render()
+        out[name] = img
+        out[name + "_rays"] = np.array(rays, np.int64)
+    return out
+
+
 def main():
     ref = "/root/reference/cornell.usda"
     desc = usda.load(ref)
@@ -117,6 +140,7 @@ def main():
     np.save(os.path.join(HERE, "cornell_oracle_32.npy"), img)
     with open(os.path.join(HERE, "cornell_oracle_32.json"), "w") as f:
         json.dump({"closest_rays": rays[0], "shadow_rays": rays[1]}, f)
+    np.savez_compressed(os.path.join(HERE, "feature_anchors.npz"), **feature_anchors())
     print("golden fixtures written")
 
 

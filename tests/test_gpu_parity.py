@@ -538,3 +538,31 @@ def test_render_parity_primvars(gpu):
         assert np.abs(b.render() - first).mean() > 1e-4
     finally:
         b.close()
+
+
+def test_committed_golden_images(gpu):
+    """The CUDA path against the oracle images committed under tests/golden/ (made by tests/golden/make_golden.py in the
+    build container), not against an oracle run of the moment."""
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    sys.path.insert(0, golden)
+    import make_golden
+    want = np.load(os.path.join(golden, "feature_anchors.npz"))
+    for name, d in make_golden.feature_scenes().items():
+        b = gpu.BuiltScene(d)
+        try:
+            img = b.render().copy()
+            st = gpu.get_stats()
+        finally:
+            b.close()
+        rmse, within = image_metrics(img, want[name])
+        assert rmse < 1e-3 and within >= 0.999, "%s: RMSE %.3e, %.5f within tolerance" % (name, rmse, within)
+        assert abs(st["closestRays"] - int(want[name + "_rays"][0])) <= 8 and abs(st["shadowRays"] - int(want[name + "_rays"][1])) <= 8, name
+    c1 = np.load(os.path.join(golden, "cornell_oracle_32.npy"))
+    b = gpu.BuiltScene(scenes.cornell(32, 32, spp=4, max_bounces=4))
+    try:
+        rmse, within = image_metrics(b.render(), c1)
+    finally:
+        b.close()
+    assert rmse < 1e-3 and within >= 0.999

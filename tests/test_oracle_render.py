@@ -4,6 +4,7 @@ import ctypes as C
 import dataclasses
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -22,6 +23,17 @@ def test_cornell_regression_anchor():
         meta = json.load(f)
     assert rays[0] == meta["closest_rays"] and rays[1] == meta["shadow_rays"]
     assert np.allclose(img, want, rtol=1e-5, atol=1e-6)
+
+
+def test_feature_regression_anchors():
+    """Textures, primvars, participating media, NEE with every light type, OpenPBR: today's oracle against the committed images."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    want = np.load(os.path.join(GOLDEN, "feature_anchors.npz"))
+    for name, d in make_golden.feature_scenes().items():
+        img, _, rays = orc.OracleScene(d).render()
+        assert list(rays) == list(want[name + "_rays"]), name
+        assert np.allclose(img, want[name], rtol=1e-5, atol=1e-6), name
 
 
 def test_progressive_accumulation_matches_single_pass():
