@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgtlc.so")
+LIB_PATH = os.environ.get("GTLC_LIB_PATH") or os.path.join(HERE, "libgtlc.so")   # the override is for tuning experiments (tools/)
 HEADER = os.path.join(HERE, "..", "include", "gtlc.h")
 
 H = C.c_uint64
