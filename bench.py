@@ -301,7 +301,7 @@ def run_ours(a):
                     "note": "gtlc_render through the C-ABI: GtlcRenderParams (camera + settings + AOV binding) from host memory in, "
                             "full HDR colour AOV copied to pinned host memory every step; scene/BVH stay resident as in the reference (rebuilt only when dirty)"},
             "gpu_launches": int(acc["kernelLaunches"]),
-            "roofline": {"bound": "hbm", "kernel": "trace_kernel<TRACE_CLOSEST>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "trace_kernel_batched<TRACE_CLOSEST>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes_step, "kernel_ms_per_step": trace_ms_step,
                          "nodes_per_ray": s_count["nodeVisits"] / max(rays_c, 1), "tris_per_ray": s_count["triVisits"] / max(rays_c, 1),

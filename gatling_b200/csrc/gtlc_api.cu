@@ -605,10 +605,10 @@ template <int MODE> void launchTrace(const TraceParams& P, bool count, int block
   if (count) { trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // visit counting: variant 0 order = the oracle's walk
   if (P.aovFlags) { trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // only variant 0 writes the NEE debug AOV
   switch (g.tuning.traceVariant) {
+    case 1: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;          // per-lane triangle loop (the order the oracle's walker restates)
     case 5: trace_kernel_v2<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 6: trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
-    case 7: trace_kernel_batched<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
-    default: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    default: trace_kernel_batched<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;        // 0 (default) and 7: warp-batched triangle tests
   }
 }
 

@@ -356,7 +356,7 @@ typedef struct GtlcTuning {
   int32_t  sortByMaterial;    /* -1 auto (on iff >1 material), 0 off, 1 on */
   int32_t  skipReadback;      /* 1: leave AOVs on the device (kernel-only timing) */
   int32_t  countVisits;       /* 1: traversal kernels also count node/triangle visits (slower; roofline bookkeeping) */
-  int32_t  traceVariant;      /* 0 default; experimental: 5 pending-triangle FIFO, 6 TMA-staged ray tiles, 7 warp-batched triangle tests */
+  int32_t  traceVariant;      /* traversal kernel: 0 default (= 7, warp-batched triangle tests); 1 per-lane triangle loop (the walk order of the visit-counting pass and of the oracle); 5 pending-triangle FIFO; 6 TMA-staged ray tiles */
   int32_t  reserved[3];       /* [0] refill threshold (idle lanes), [1] trace CTAs per SM, [2] variant 5 triangle threshold; 0 = default */
   int32_t  bvhBuilder;        /* 0 host binned-SAH build (default, best trace speed); 1 device LBVH build (fast rebuilds; takes effect at the next geometry change) */
 } GtlcTuning;

@@ -15,6 +15,8 @@ ap.add_argument("--configs", default="c1,c3,c5")
 ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale of c3/c5")
 ap.add_argument("--bvh-builder", type=int, default=0, help="0 host binned SAH, 1 device LBVH")
+ap.add_argument("--trace-variant", type=int, default=0)
+ap.add_argument("--tri-threshold", type=int, default=0)
 a = ap.parse_args()
 assert gi.giInitialize(0) == gi.GiStatus.Ok, gi.giLastError()
 
@@ -33,7 +35,8 @@ for name in a.configs.split(","):
     t0 = time.perf_counter()
     d = make(name)
     t_gen = time.perf_counter() - t0
-    gi.set_tuning(bvhBuilder=a.bvh_builder)
+    import ctypes as C
+    gi.set_tuning(bvhBuilder=a.bvh_builder, traceVariant=a.trace_variant, reserved=(C.c_int32 * 3)(0, 0, a.tri_threshold))
     b = gi.BuiltScene(d)
     for sort in ((-1,) if len(d.materials) == 1 else (0, 1)):
         gi.set_tuning(sortByMaterial=sort)
@@ -48,7 +51,7 @@ for name in a.configs.split(","):
         print(json.dumps({"config": name, "scene": d.name, "triangles": d.triangle_count, "materials": len(d.materials), "spp": d.settings.spp,
                           "sort": sort, "Mray_s": rays / best["msTotal"] / 1e3, "ms_total": best["msTotal"], "closest": best["closestRays"],
                           "shadow": best["shadowRays"], "ms_trace": best["msTraceClosest"], "ms_shadow": best["msTraceAny"], "ms_shade": best["msShade"],
-                          "ms_sort": best["msSort"], "bvh_builder": a.bvh_builder, "bvh_build_ms": best["msBvhBuild"], "bvh_device_build_ms": best["msBvhDeviceBuild"], "bvh_nodes": best["bvhNodeCount"], "depth": best["bvhMaxDepth"],
+                          "ms_sort": best["msSort"], "bvh_builder": a.bvh_builder, "trace_variant": a.trace_variant, "bvh_build_ms": best["msBvhBuild"], "bvh_device_build_ms": best["msBvhDeviceBuild"], "bvh_nodes": best["bvhNodeCount"], "depth": best["bvhMaxDepth"],
                           "scene_gen_s": round(t_gen, 2)}), flush=True)
     b.close()
 gi.giTerminate()

@@ -33,7 +33,7 @@ def short(name):
     if "trace_kernel" in name:
         mode = {"0": "CLOSEST", "1": "ANY", "2": "SHADOW"}
         import re
-        m = re.search(r"trace_kernel(_v1)?<(?:\(int\))?(\d)", name)
+        m = re.search(r"trace_kernel(_batched|_v2|_tma)?<(?:\(int\))?(\d)", name)
         if m:
             n = "trace_kernel%s<%s>" % (m.group(1) or "", mode.get(m.group(2), m.group(2)))
         if "(bool)1" in name or re.search(r"trace_kernel<\d, 1>", name):
