@@ -6,7 +6,10 @@
 //   bounds       centroid bounds of the scene (block reduce + ordered-int atomics)
 //   morton       63-bit Morton key of every centroid (21 bits per axis)
 //   radix sort   8 x 8-bit LSD passes over (key, triangle) pairs, stable (sort.cuh's count/scan/scatter scheme)
-//   karras       binary radix tree over the sorted keys (Karras 2012); ties broken by position
+//   karras       binary radix tree over the sorted keys (Karras 2012); ties broken by position          (bvhBuilder = 1)
+//   ploc         or: parallel locally-ordered clustering over the sorted order (Meister & Bittner 2018): every cluster
+//                looks `kPlocRadius` neighbours to each side for the partner with the smallest merged surface area,
+//                mutual pairs merge; ~SAH-builder quality for a few more milliseconds                          (bvhBuilder = 2)
 //   refit + DP   bottom-up with one atomic counter per node: boxes, then the SAH-optimal "present this subtree as
 //                <= i children" table of Ylitie, Karras, Laine 2017 section 3.1 (same recurrence as bvh8_build.cpp)
 //   collapse     breadth-first, one launch pair per level of the wide tree: count -> scan -> emit, so that node and
@@ -38,7 +41,8 @@ struct LbvhTree {
   unsigned long long* keys; uint32_t* vals;
   uint2* children;      // per internal node
   uint32_t* parent;     // per ref
-  uint2* range;         // per internal node: first, last sorted position
+  uint2* range;         // per internal node: first, last sorted position (Karras tree only)
+  uint32_t* total;      // per internal node: triangles in the subtree
   float4* boxLo; float4* boxHi;   // per ref
   uint32_t* visit;      // per internal node
   LbvhDp* dp;           // per internal node
@@ -247,9 +251,124 @@ __global__ void __launch_bounds__(kLbvhBlock) lbvh_karras_kernel(LbvhTree T)
   const uint32_t right = (last == gamma + 1) ? (uint32_t) (n - 1 + gamma + 1) : (uint32_t) (gamma + 1);
   T.children[i] = make_uint2(left, right);
   T.range[i] = make_uint2((uint32_t) first, (uint32_t) last);
+  T.total[i] = (uint32_t) (last - first + 1);
   T.parent[left] = (uint32_t) i; T.parent[right] = (uint32_t) i;
   T.visit[i] = 0;
   if (i == 0) T.parent[0] = 0xFFFFFFFFu;
+}
+
+GTLC_D uint32_t lbvh_subtree_tris(const LbvhTree& T, uint32_t ref)
+{
+  if (ref >= T.n - 1) return 1u;
+  return T.total[ref];
+}
+
+// ---- PLOC (Meister & Bittner 2018): clusters in Morton order merge with their locally best partner ---------------
+constexpr int kPlocRadius = 16;
+
+__global__ void __launch_bounds__(kLbvhBlock) lbvh_leaf_box_kernel(LbvhTree T, uint32_t* __restrict__ clusters)
+{
+  const uint32_t p = blockIdx.x * kLbvhBlock + threadIdx.x;
+  if (p >= T.n) return;
+  float4 lo, hi; lbvh_tri_box(T.inTris, T.vals[p], lo, hi);
+  T.boxLo[T.n - 1 + p] = lo; T.boxHi[T.n - 1 + p] = hi;
+  clusters[p] = T.n - 1 + p;
+}
+
+GTLC_D float lbvh_union_area(float4 alo, float4 ahi, float4 blo, float4 bhi)
+{
+  const float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+  const float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+  return lbvh_area(lo, hi);
+}
+
+// nearest neighbour within the radius; ties go to the smaller position
+__global__ void __launch_bounds__(kLbvhBlock) ploc_nearest_kernel(LbvhTree T, uint32_t count, const uint32_t* __restrict__ clusters, uint32_t* __restrict__ nearest)
+{
+  const uint32_t i = blockIdx.x * kLbvhBlock + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t ci = clusters[i];
+  const float4 lo = T.boxLo[ci], hi = T.boxHi[ci];
+  const uint32_t jb = i > (uint32_t) kPlocRadius ? i - (uint32_t) kPlocRadius : 0u;
+  const uint32_t je = min(count - 1u, i + (uint32_t) kPlocRadius);
+  float best = kLbvhInf; uint32_t bj = i;
+  for (uint32_t j = jb; j <= je; j++) {
+    if (j == i) continue;
+    const uint32_t cj = clusters[j];
+    const float a = lbvh_union_area(lo, hi, T.boxLo[cj], T.boxHi[cj]);
+    if (a < best || bj == i) { best = a; bj = j; }
+  }
+  nearest[i] = bj;
+}
+
+// merge[i] = 1 when i and nearest[i] chose each other and i is the left one; keep[i] = 0 for the right one
+__global__ void __launch_bounds__(kLbvhBlock) ploc_flags_kernel(uint32_t count, const uint32_t* __restrict__ nearest, uint32_t* __restrict__ merge,
+                                                                uint32_t* __restrict__ mergeScan, uint32_t* __restrict__ keepScan)
+{
+  const uint32_t i = blockIdx.x * kLbvhBlock + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t j = nearest[i];
+  const bool mutual = j != i && nearest[j] == i;
+  const uint32_t m = (mutual && i < j) ? 1u : 0u;
+  merge[i] = m; mergeScan[i] = m;
+  keepScan[i] = (mutual && i > j) ? 0u : 1u;
+}
+
+// Internal nodes get descending ids (the last merge, the root, is node 0, as the collapse expects).
+__global__ void __launch_bounds__(kLbvhBlock) ploc_apply_kernel(LbvhTree T, uint32_t count, const uint32_t* __restrict__ clusters, const uint32_t* __restrict__ nearest,
+    const uint32_t* __restrict__ merge, const uint32_t* __restrict__ mergeRank, const uint32_t* __restrict__ keepPos, uint32_t nextId, uint32_t* __restrict__ out)
+{
+  const uint32_t i = blockIdx.x * kLbvhBlock + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t j = nearest[i];
+  const bool removed = j != i && nearest[j] == i && i > j;
+  if (removed) return;
+  uint32_t ref = clusters[i];
+  if (merge[i]) {
+    const uint32_t a = ref, b = clusters[j];
+    const uint32_t id = nextId - mergeRank[i];
+    const float4 alo = T.boxLo[a], ahi = T.boxHi[a], blo = T.boxLo[b], bhi = T.boxHi[b];
+    T.boxLo[id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+    T.boxHi[id] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+    T.children[id] = make_uint2(a, b);
+    T.total[id] = lbvh_subtree_tris(T, a) + lbvh_subtree_tris(T, b);
+    T.parent[a] = id; T.parent[b] = id;
+    T.visit[id] = 0;
+    if (id == 0) T.parent[0] = 0xFFFFFFFFu;
+    ref = id;
+  }
+  out[keepPos[i]] = ref;
+}
+
+// ---- exclusive scan of up to 2^32 elements: tiles of 2048 per CTA, one CTA over the tile sums, add back --------------
+constexpr int kScanTile = 2048;
+__global__ void __launch_bounds__(1024) lbvh_scan_tiles_kernel(uint32_t* __restrict__ a, uint32_t count, uint32_t* __restrict__ tileSums)
+{
+  __shared__ uint32_t warpSums[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i0 = blockIdx.x * kScanTile + threadIdx.x * 2u;
+  const uint32_t v0 = i0 < count ? a[i0] : 0u, v1 = i0 + 1u < count ? a[i0 + 1u] : 0u;
+  uint32_t x = v0 + v1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) warpSums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warpSums[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, d); if (lane >= d) w += y; }
+    warpSums[lane] = w;
+  }
+  __syncthreads();
+  const uint32_t excl = (warp ? warpSums[warp - 1] : 0u) + (x - (v0 + v1));
+  if (i0 < count) a[i0] = excl;
+  if (i0 + 1u < count) a[i0 + 1u] = excl + v0;
+  if (threadIdx.x == 1023) tileSums[blockIdx.x] = warpSums[31];
+}
+__global__ void __launch_bounds__(kLbvhBlock) lbvh_scan_add_kernel(uint32_t* __restrict__ a, uint32_t count, const uint32_t* __restrict__ tileOffsets)
+{
+  const uint32_t i = blockIdx.x * kLbvhBlock + threadIdx.x;
+  if (i < count) a[i] += tileOffsets[i / kScanTile];
 }
 
 // ---- bottom-up: boxes + SAH table --------------------------------------------------------------------------
@@ -285,8 +404,7 @@ __global__ void __launch_bounds__(kLbvhBlock) lbvh_refit_kernel(LbvhTree T)
     const float4 bhi = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
     T.boxLo[cur] = blo; T.boxHi[cur] = bhi;
     const float area = lbvh_area(blo, bhi);
-    const uint2 rg = T.range[cur];
-    const uint32_t total = rg.y - rg.x + 1u;
+    const uint32_t total = T.total[cur];
     const float leafCost = (total <= kLbvhMaxLeaf) ? area * (float) total : kLbvhInf;
     float L[7], R[7];
     lbvh_child_costs(T, ch.x, L); lbvh_child_costs(T, ch.y, R);
@@ -321,12 +439,6 @@ struct LbvhLevel {
   uint32_t nodeBase, triBase;            // first free wide node / triangle index before this level's children
 };
 
-GTLC_D uint32_t lbvh_subtree_tris(const LbvhTree& T, uint32_t ref)
-{
-  if (ref >= T.n - 1) return 1u;
-  const uint2 rg = T.range[ref];
-  return rg.y - rg.x + 1u;
-}
 
 // expands "subtree `ref` as at most `i` children" (bvh8_build.cpp's gather) with an explicit stack, left first
 GTLC_D void lbvh_gather(const LbvhTree& T, uint32_t ref, int i, uint32_t* list, int& n)
@@ -454,12 +566,17 @@ __global__ void __launch_bounds__(kLbvhBlock) lbvh_collapse_emit_kernel(LbvhTree
     }
     if (ch[i] & 0x80000000u) {
       const uint32_t cnt = lbvh_subtree_tris(T, r);
-      const uint32_t first = (r >= T.n - 1) ? (r - (T.n - 1)) : T.range[r].x;
       meta[s >> 2] |= (((((1u << cnt) - 1u) << 5) | triOffset) & 0xFFu) << (8 * (s & 3));
-      for (uint32_t t = 0; t < cnt; t++) {
-        const uint32_t tri = T.vals[first + t];
-        const size_t dst = (size_t) (triBase + triOffset + t) * 3;
-        outTris[dst + 0] = T.inTris[(size_t) tri * 3 + 0]; outTris[dst + 1] = T.inTris[(size_t) tri * 3 + 1]; outTris[dst + 2] = T.inTris[(size_t) tri * 3 + 2];
+      uint32_t walk[4]; int wp = 0; uint32_t t = 0;                   // the <= kLbvhMaxLeaf leaves of the subtree, left to right
+      walk[wp++] = r;
+      while (wp > 0) {
+        const uint32_t x = walk[--wp];
+        if (x >= T.n - 1) {
+          const uint32_t tri = T.vals[x - (T.n - 1)];
+          const size_t dst = (size_t) (triBase + triOffset + t) * 3;
+          outTris[dst + 0] = T.inTris[(size_t) tri * 3 + 0]; outTris[dst + 1] = T.inTris[(size_t) tri * 3 + 1]; outTris[dst + 2] = T.inTris[(size_t) tri * 3 + 2];
+          t++;
+        } else { const uint2 c2 = T.children[x]; walk[wp++] = c2.y; walk[wp++] = c2.x; }
       }
       triOffset += cnt;
     } else {

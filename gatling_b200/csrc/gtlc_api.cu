@@ -394,12 +394,13 @@ bool buildBvhOnDevice(Scene* s)
   const uint32_t grid = (n + kLbvhBlock - 1) / kLbvhBlock;
   const uint32_t sortGrid = std::min<uint32_t>(grid, (uint32_t) g.smCount * 4u);
   ScratchArray<float4> inTris, boxLo, boxHi; ScratchArray<unsigned long long> keys0, keys1; ScratchArray<uint32_t> vals0, vals1, hist, parent, visit, bounds;
+  ScratchArray<uint32_t> total, clusters0, clusters1, nearest, mergeFlag, mergeScan, keepScan, tileSums;
   ScratchArray<uint2> children, range, queue0, queue1; ScratchArray<LbvhDp> dp; ScratchArray<uint32_t> childList, childCount, cntNodes, cntTris, totals; ScratchArray<uint4> nodesTmp;
   const size_t refs = (size_t) 2 * n;
   if (!inTris.alloc((size_t) n * 3) || !boxLo.alloc(refs) || !boxHi.alloc(refs) || !keys0.alloc(n) || !keys1.alloc(n) || !vals0.alloc(n) || !vals1.alloc(n) ||
       !hist.alloc((size_t) 256 * sortGrid) || !parent.alloc(refs) || !visit.alloc(n) || !bounds.alloc(8) || !children.alloc(n) || !range.alloc(n) ||
       !queue0.alloc(n) || !queue1.alloc(n) || !dp.alloc(n) || !childList.alloc((size_t) n * 8) || !childCount.alloc(n) || !cntNodes.alloc(n) || !cntTris.alloc(n) ||
-      !totals.alloc(2) || !nodesTmp.alloc((size_t) n * 5)) { setError("device BVH build: out of memory for %u triangles", n); return false; }
+      !totals.alloc(2) || !nodesTmp.alloc((size_t) n * 5) || !total.alloc(n)) { setError("device BVH build: out of memory for %u triangles", n); return false; }
   if (!s->dTris.reserve((size_t) n * 3)) return false;
 
   lbvh_flatten_kernel<<<grid, kLbvhBlock, 0, st>>>(n, (uint32_t) s->hInstInfo.size(), s->dRankBase.ptr, s->dInstInfo.ptr, s->dO2W.ptr, s->dFverts.ptr, s->dFaces.ptr, s->dInstOpacity.ptr, inTris.ptr);
@@ -417,8 +418,38 @@ bool buildBvhOnDevice(Scene* s)
   g.stats.kernelLaunches += 3 + 8 * 3;
   LbvhTree T; memset(&T, 0, sizeof(T));
   T.n = n; T.inTris = inTris.ptr; T.keys = k[0]; T.vals = v[0]; T.children = children.ptr; T.parent = parent.ptr; T.range = range.ptr;
-  T.boxLo = boxLo.ptr; T.boxHi = boxHi.ptr; T.visit = visit.ptr; T.dp = dp.ptr;
-  if (n > 1) lbvh_karras_kernel<<<grid, kLbvhBlock, 0, st>>>(T);
+  T.boxLo = boxLo.ptr; T.boxHi = boxHi.ptr; T.visit = visit.ptr; T.dp = dp.ptr; T.total = total.ptr;
+  if (n > 1 && g.tuning.bvhBuilder == 2) {
+    // PLOC: iterate nearest-neighbour search / mutual merges / order-preserving compaction until one cluster is left
+    const size_t tiles = (size_t) n / kScanTile + 1;
+    if (!clusters0.alloc(n) || !clusters1.alloc(n) || !nearest.alloc(n) || !mergeFlag.alloc(n) || !mergeScan.alloc(n) || !keepScan.alloc(n) || !tileSums.alloc(tiles)) { setError("device BVH build: out of memory for %u triangles", n); return false; }
+    auto scanLarge = [&](uint32_t* a, uint32_t cnt, uint32_t* totalOut) {
+      const uint32_t nt = (cnt + kScanTile - 1) / kScanTile;
+      lbvh_scan_tiles_kernel<<<nt, 1024, 0, st>>>(a, cnt, tileSums.ptr);
+      lbvh_scan_kernel<<<1, 1024, 0, st>>>(tileSums.ptr, nt, totalOut);
+      if (nt > 1) lbvh_scan_add_kernel<<<(cnt + kLbvhBlock - 1) / kLbvhBlock, kLbvhBlock, 0, st>>>(a, cnt, tileSums.ptr);
+      g.stats.kernelLaunches += nt > 1 ? 3 : 2;
+    };
+    lbvh_leaf_box_kernel<<<grid, kLbvhBlock, 0, st>>>(T, clusters0.ptr);
+    uint32_t* cl[2] = { clusters0.ptr, clusters1.ptr };
+    uint32_t count = n, nextId = n - 2, rounds = 0;
+    while (count > 1) {
+      if (++rounds > 4096) { setError("device BVH build: PLOC did not converge"); return false; }
+      const uint32_t cg = (count + kLbvhBlock - 1) / kLbvhBlock;
+      ploc_nearest_kernel<<<cg, kLbvhBlock, 0, st>>>(T, count, cl[0], nearest.ptr);
+      ploc_flags_kernel<<<cg, kLbvhBlock, 0, st>>>(count, nearest.ptr, mergeFlag.ptr, mergeScan.ptr, keepScan.ptr);
+      scanLarge(mergeScan.ptr, count, totals.ptr);
+      scanLarge(keepScan.ptr, count, nullptr);
+      ploc_apply_kernel<<<cg, kLbvhBlock, 0, st>>>(T, count, cl[0], nearest.ptr, mergeFlag.ptr, mergeScan.ptr, keepScan.ptr, nextId, cl[1]);
+      g.stats.kernelLaunches += 3;
+      uint32_t merges = 0;
+      CUDA_OK(cudaMemcpyAsync(&merges, totals.ptr, sizeof(merges), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      if (merges == 0 || merges > count / 2) { setError("device BVH build: PLOC round merged %u of %u clusters", merges, count); return false; }
+      nextId -= merges; count -= merges;
+      std::swap(cl[0], cl[1]);
+    }
+  } else if (n > 1) lbvh_karras_kernel<<<grid, kLbvhBlock, 0, st>>>(T);
   lbvh_refit_kernel<<<grid, kLbvhBlock, 0, st>>>(T);
   g.stats.kernelLaunches += 2;
 
@@ -1024,7 +1055,7 @@ int gtlc_scene_get_bvh(GtlcHandle h, GtlcBvhView* view)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s || !view) return GTLC_ERROR;
   std::lock_guard<std::mutex> l(s->mutex);
-  if (g.tuning.bvhBuilder == 1) {           // device builder: build if needed, then read the result back once
+  if (g.tuning.bvhBuilder >= 1) {           // device builders: build if needed, then read the result back once
     if (!requireInit()) return GTLC_ERROR;
     cudaSetDevice(g.device);
     if (!syncSceneToDevice(s)) return GTLC_ERROR;
@@ -1043,7 +1074,7 @@ int gtlc_scene_get_bvh(GtlcHandle h, GtlcBvhView* view)
 static bool syncSceneToDevice(Scene* s)
 {
   if (s->geometryDirty || !s->bvhValid || !s->dNodes.ptr) {
-    const bool hostBvh = g.tuning.bvhBuilder != 1;
+    const bool hostBvh = g.tuning.bvhBuilder < 1;
     if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s, hostBvh)) return false; }
     if (!uploadGeometry(s, hostBvh)) return false;
     s->geometryDirty = false; s->materialsDirty = true;

@@ -358,7 +358,7 @@ typedef struct GtlcTuning {
   int32_t  countVisits;       /* 1: traversal kernels also count node/triangle visits (slower; roofline bookkeeping) */
   int32_t  traceVariant;      /* traversal kernel: 0 default (= 7, warp-batched triangle tests); 1 per-lane triangle loop (the walk order of the visit-counting pass and of the oracle); 5 pending-triangle FIFO; 6 TMA-staged ray tiles */
   int32_t  reserved[3];       /* [0] refill threshold (idle lanes), [1] trace CTAs per SM, [2] variant 5 triangle threshold; 0 = default */
-  int32_t  bvhBuilder;        /* 0 host binned-SAH build (default, best trace speed); 1 device LBVH build (fast rebuilds; takes effect at the next geometry change) */
+  int32_t  bvhBuilder;        /* 0 host binned-SAH build (default); 1 device LBVH build (fastest rebuilds); 2 device PLOC build (close to the SAH tree's trace speed); takes effect at the next geometry change */
 } GtlcTuning;
 GTLC_API void gtlc_set_tuning(const GtlcTuning* tuning);
 GTLC_API void gtlc_get_tuning(GtlcTuning* tuning);

@@ -942,9 +942,9 @@ int orc_tri_intersect(const float* o, const float* d, const float* p0, const flo
 #include "orc_lbvh8.h"
 
 // CPU restatement of the device BVH8 builder; see orc_lbvh8.h.  Returns the node count.
-extern "C" uint32_t orc_lbvh8_build(const float* tris, uint32_t n, uint32_t* nodes, float* outTris, uint32_t* depth)
+extern "C" uint32_t orc_lbvh8_build(const float* tris, uint32_t n, uint32_t* nodes, float* outTris, uint32_t* depth, int mode)
 {
-  return orc_lbvh8::build(tris, n, nodes, outTris, depth);
+  return orc_lbvh8::build(tris, n, nodes, outTris, depth, mode);
 }
 
 // KAT access to the texture restatement: one lookup of `tex` at (u, v); out = rgba, returns 1 when clipped.

@@ -140,7 +140,7 @@ def lib():
                                          C.c_void_p, C.c_void_p]
         if hasattr(L, "orc_lbvh8_build"):
             L.orc_lbvh8_build.restype = C.c_uint32
-            L.orc_lbvh8_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.orc_lbvh8_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     return _lib
 
 
@@ -447,16 +447,17 @@ def bvh8_trace(nodes, tris, rays, any_hit=False):
     return hits, visits
 
 
-def lbvh8_build(tris_rank_order):
+def lbvh8_build(tris_rank_order, mode=1):
     """CPU restatement of the device BVH8 builder (orc_lbvh8.h): triangle records (n x 12 float32, in
-    (instance, primitive) order) -> (nodes bytes [nodeCount*80], tris float32 [n*12], depth)."""
+    (instance, primitive) order) -> (nodes bytes [nodeCount*80], tris float32 [n*12], depth).
+    mode 1 = Karras radix tree (bvhBuilder 1), mode 2 = PLOC (bvhBuilder 2)."""
     L = lib()
     t = np.ascontiguousarray(tris_rank_order, np.float32).reshape(-1, 12)
     n = len(t)
     nodes = np.zeros(max(n, 1) * 20, np.uint32)
     out = np.zeros(max(n, 1) * 12, np.float32)
     depth = C.c_uint32(0)
-    count = L.orc_lbvh8_build(t.ctypes.data, n, nodes.ctypes.data, out.ctypes.data, C.byref(depth))
+    count = L.orc_lbvh8_build(t.ctypes.data, n, nodes.ctypes.data, out.ctypes.data, C.byref(depth), int(mode))
     return nodes[:count * 20].view(np.uint8).copy(), out[:n * 12].copy(), int(depth.value)
 
 

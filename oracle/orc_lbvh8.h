@@ -52,7 +52,7 @@ struct Builder {
   uint32_t n;
   const float* in;                         // 12 floats per triangle, rank order
   std::vector<uint64_t> key; std::vector<uint32_t> val;
-  std::vector<uint32_t> left, right, first, last;     // internal nodes 0..n-2
+  std::vector<uint32_t> left, right, total;           // internal nodes 0..n-2: children, triangles in the subtree
   std::vector<Box3> box;                   // refs: internal 0..n-2, leaves n-1..2n-2
   std::vector<Table> tab;                  // internal nodes
   std::vector<uint32_t> outNodes;          // 20 words per wide node
@@ -60,8 +60,12 @@ struct Builder {
   uint32_t depth = 0;
 
   bool is_leaf(uint32_t ref) const { return ref >= n - 1; }
-  uint32_t tri_count(uint32_t ref) const { return is_leaf(ref) ? 1u : last[ref] - first[ref] + 1u; }
-  uint32_t first_pos(uint32_t ref) const { return is_leaf(ref) ? ref - (n - 1) : first[ref]; }
+  uint32_t tri_count(uint32_t ref) const { return is_leaf(ref) ? 1u : total[ref]; }
+  void leaves_of(uint32_t ref, std::vector<uint32_t>& positions) const     // sorted positions of the subtree's triangles, left to right
+  {
+    if (is_leaf(ref)) { positions.push_back(ref - (n - 1)); return; }
+    leaves_of(left[ref], positions); leaves_of(right[ref], positions);
+  }
 
   Box3 tri_box(uint32_t t) const
   {
@@ -108,7 +112,7 @@ struct Builder {
   // Karras 2012, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees", section 4
   void radix_tree()
   {
-    left.assign(n, 0); right.assign(n, 0); first.assign(n, 0); last.assign(n, 0);
+    left.assign(n, 0); right.assign(n, 0); total.assign(n, 0);
     for (int i = 0; i + 1 < (int) n; i++) {
       const int d = common_prefix(i, i + 1) - common_prefix(i, i - 1) >= 0 ? 1 : -1;
       const int floorPrefix = common_prefix(i, i - d);
@@ -124,7 +128,57 @@ struct Builder {
       const int a = std::min(i, j), b = std::max(i, j);
       left[i] = (a == cut) ? (uint32_t) (n - 1 + cut) : (uint32_t) cut;
       right[i] = (b == cut + 1) ? (uint32_t) (n - 1 + cut + 1) : (uint32_t) (cut + 1);
-      first[i] = (uint32_t) a; last[i] = (uint32_t) b;
+      total[i] = (uint32_t) (b - a + 1);
+    }
+  }
+
+  // Meister & Bittner 2018, "Parallel Locally-Ordered Clustering for Bounding Volume Hierarchy Construction": clusters in
+  // Morton order, each looks PLOC_RADIUS positions to either side for the partner with the smallest merged area (first
+  // candidate, then strictly smaller: ties go to the smaller position); mutual pairs merge into the left one's place;
+  // the order of the surviving clusters is kept.  Node ids count down so that the root, the last merge, is node 0.
+  static const int PLOC_RADIUS = 16;
+  static float merged_area(const Box3& a, const Box3& b)
+  {
+    Box3 u;
+    for (int k = 0; k < 3; k++) { u.lo[k] = std::fmin(a.lo[k], b.lo[k]); u.hi[k] = std::fmax(a.hi[k], b.hi[k]); }
+    return box_area(u);
+  }
+  void ploc_tree()
+  {
+    left.assign(n, 0); right.assign(n, 0); total.assign(n, 0);
+    box.resize((size_t) 2 * n);
+    std::vector<uint32_t> cl(n), next;
+    for (uint32_t p = 0; p < n; p++) { box[n - 1 + p] = tri_box(val[p]); cl[p] = n - 1 + p; }
+    uint32_t nextId = n - 2;
+    while (cl.size() > 1) {
+      const uint32_t count = (uint32_t) cl.size();
+      std::vector<uint32_t> nn(count);
+      for (uint32_t i = 0; i < count; i++) {
+        const uint32_t jb = i > (uint32_t) PLOC_RADIUS ? i - PLOC_RADIUS : 0u, je = std::min(count - 1u, i + (uint32_t) PLOC_RADIUS);
+        float best = BIG; uint32_t bj = i;
+        for (uint32_t j = jb; j <= je; j++) {
+          if (j == i) continue;
+          const float a = merged_area(box[cl[i]], box[cl[j]]);
+          if (a < best || bj == i) { best = a; bj = j; }
+        }
+        nn[i] = bj;
+      }
+      next.clear();
+      uint32_t merges = 0;
+      for (uint32_t i = 0; i < count; i++) {
+        const uint32_t j = nn[i];
+        const bool mutual = j != i && nn[j] == i;
+        if (mutual && i > j) continue;                         // absorbed by its partner
+        if (mutual) {
+          const uint32_t id = nextId - merges++;
+          const uint32_t a = cl[i], b = cl[j];
+          left[id] = a; right[id] = b; total[id] = tri_count(a) + tri_count(b);
+          for (int k = 0; k < 3; k++) { box[id].lo[k] = std::fmin(box[a].lo[k], box[b].lo[k]); box[id].hi[k] = std::fmax(box[a].hi[k], box[b].hi[k]); }
+          next.push_back(id);
+        } else next.push_back(cl[i]);
+      }
+      nextId -= merges;
+      cl.swap(next);
     }
   }
 
@@ -155,8 +209,8 @@ struct Builder {
       for (int k = 0; k < 3; k++) { u.lo[k] = std::fmin(a.lo[k], b.lo[k]); u.hi[k] = std::fmax(a.hi[k], b.hi[k]); }
       box[r] = u;
       const float area = box_area(u);
-      const uint32_t total = last[r] - first[r] + 1u;
-      const float asLeaf = total <= MAX_LEAF ? area * (float) total : BIG;
+      const uint32_t tris = total[r];
+      const float asLeaf = tris <= MAX_LEAF ? area * (float) tris : BIG;
       float L[7], R[7];
       slot_costs(left[r], L); slot_costs(right[r], R);
       Table t;
@@ -245,10 +299,11 @@ struct Builder {
         q[k][s] = (uint8_t) ql; q[3 + k][s] = (uint8_t) qh;
       }
       if (ch[i].leaf) {
-        const uint32_t cnt = tri_count(ch[i].ref), p0 = first_pos(ch[i].ref);
+        const uint32_t cnt = tri_count(ch[i].ref);
+        std::vector<uint32_t> pos; leaves_of(ch[i].ref, pos);
         meta[s] = (uint8_t) ((((1u << cnt) - 1u) << 5) | triOffset);
         for (uint32_t t = 0; t < cnt; t++)
-          std::memcpy(&outTris[(size_t) (triBase + triOffset + t) * 12], &in[(size_t) val[p0 + t] * 12], 48);
+          std::memcpy(&outTris[(size_t) (triBase + triOffset + t) * 12], &in[(size_t) val[pos[t]] * 12], 48);
         triOffset += cnt;
       } else {
         meta[s] = (uint8_t) (0x20u | (24u + (uint32_t) s));
@@ -298,12 +353,13 @@ struct Builder {
 
 // tris: n x 12 floats in (instance, primitive) order.  Returns the node count; nodes/outTris sized by the caller
 // for the worst case (n nodes x 20 words, n x 12 floats).
-inline uint32_t build(const float* tris, uint32_t n, uint32_t* nodes, float* outTris, uint32_t* depth)
+// mode 1: Karras radix tree (GtlcTuning.bvhBuilder = 1); mode 2: PLOC (bvhBuilder = 2)
+inline uint32_t build(const float* tris, uint32_t n, uint32_t* nodes, float* outTris, uint32_t* depth, int mode = 1)
 {
   if (n == 0) { std::memset(nodes, 0, 80); if (depth) *depth = 0; return 1; }
   Builder b; b.n = n; b.in = tris;
   b.sort_keys();
-  if (n > 1) b.radix_tree();
+  if (n > 1) { if (mode == 2) b.ploc_tree(); else b.radix_tree(); }
   b.fit_and_cost();
   b.collapse();
   std::memcpy(nodes, b.outNodes.data(), b.outNodes.size() * 4);

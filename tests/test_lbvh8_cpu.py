@@ -16,14 +16,14 @@ def rank_order(tris):
     return t[np.argsort((inst << np.uint64(32)) | prim, kind="stable")]
 
 
-def _check(desc, rays):
+def _check(desc, rays, mode=1):
     b = gi.BuiltScene(desc)
     try:
         _, host_tris = gi.get_bvh(b.scene)          # host builder: only the flattened triangle records are used
     finally:
         b.close()
     recs = rank_order(host_tris)
-    nodes, tris, depth = orc.lbvh8_build(recs)
+    nodes, tris, depth = orc.lbvh8_build(recs, mode)
     n = len(recs)
     assert len(tris) == n * 12 and len(nodes) % 80 == 0
     # every input triangle is referenced exactly once, records unchanged
@@ -77,3 +77,22 @@ def test_instances_duplicates_and_tiny_scenes():
         assert depth == (1 if count <= 8 else 2) or count > 3
     nodes, tris, depth = orc.lbvh8_build(np.zeros((0, 12), np.float32))
     assert len(nodes) == 80 and len(tris) == 0 and depth == 0
+
+
+def test_ploc_trees_are_valid_and_better():
+    """bvhBuilder = 2 (PLOC): same validity checks; on structured geometry (tessellated surfaces) the locally-ordered
+    clustering needs fewer node visits than the Karras radix tree over the same Morton order."""
+    d = scenes.material_stress(tris_per_mesh=1500, meshes=12, width=32, height=32, spp=1)
+    d.dome_light = None
+    cam = orc.camera_rays(d, 0); cam[:, 3] = 0; cam[:, 7] = 3e38
+    rays = np.concatenate([cam, random_rays(8000, 2, scale=3.0)])
+    _, _, depth_l, visits_l = _check(d, rays, mode=1)
+    nodes, tris, depth_p, visits_p = _check(d, rays, mode=2)
+    assert depth_p <= 24
+    assert visits_p[:, 0].mean() < visits_l[:, 0].mean()
+    _check(scenes.random_triangles(20000, 32, 32, spp=1), np.concatenate([random_rays(10000, 2), random_rays(3000, 4, tmax=0.1)]), mode=2)
+    c = scenes.cornell(16, 16, spp=1)
+    cam = orc.camera_rays(c, 0); cam[:, 3] = 0; cam[:, 7] = 3e38
+    _check(c, np.concatenate([cam, random_rays(3000, 5)]), mode=2)
+    for count in (1, 2, 3, 4, 9, 40):
+        _check(scenes.random_triangles(count, 8, 8, spp=1), random_rays(3000, 30 + count), mode=2)

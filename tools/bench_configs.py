@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--configs", default="c1,c3,c5")
 ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale of c3/c5")
-ap.add_argument("--bvh-builder", type=int, default=0, help="0 host binned SAH, 1 device LBVH")
+ap.add_argument("--bvh-builder", type=int, default=0, help="0 host binned SAH, 1 device LBVH, 2 device PLOC")
 ap.add_argument("--trace-variant", type=int, default=0)
 ap.add_argument("--tri-threshold", type=int, default=0)
 a = ap.parse_args()
