@@ -153,6 +153,7 @@ struct Global {
 };
 Global g;
 std::mutex g_destroyMutex;   // Gi.cpp:249
+std::mutex g_renderMutex;    // the path-state pools, counters and the stream are per process: renders / ray queries of different scenes serialise
 
 template <typename T> T* as(GtlcHandle h, uint32_t tag)
 {
@@ -1091,6 +1092,7 @@ int gtlc_trace_rays(GtlcHandle h, const float* rays, uint32_t count, int32_t any
 {
   if (!requireInit()) return GTLC_ERROR;
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return GTLC_ERROR;
+  std::lock_guard<std::mutex> rl(g_renderMutex);
   std::lock_guard<std::mutex> l(s->mutex);
   cudaSetDevice(g.device);
   if (!syncSceneToDevice(s)) return GTLC_ERROR;
@@ -1141,6 +1143,7 @@ int gtlc_render(const GtlcRenderParams* params)
   if (!requireInit()) return GTLC_ERROR;
   if (!params) { setError("gtlc_render: null params"); return GTLC_ERROR; }
   Scene* s = as<Scene>(params->scene, TAG_SCENE); if (!s) return GTLC_ERROR;
+  std::lock_guard<std::mutex> rl(g_renderMutex);
   std::lock_guard<std::mutex> l(s->mutex);
   cudaSetDevice(g.device);
   const GtlcRenderSettings& rs = params->renderSettings;
