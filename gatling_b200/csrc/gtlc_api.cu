@@ -1055,6 +1055,8 @@ static bool syncSceneToDevice(Scene* s);
 int gtlc_scene_get_bvh(GtlcHandle h, GtlcBvhView* view)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s || !view) return GTLC_ERROR;
+  std::unique_lock<std::mutex> rl(g_renderMutex, std::defer_lock);
+  if (g.tuning.bvhBuilder >= 1) rl.lock();     // the device builders run on the shared stream
   std::lock_guard<std::mutex> l(s->mutex);
   if (g.tuning.bvhBuilder >= 1) {           // device builders: build if needed, then read the result back once
     if (!requireInit()) return GTLC_ERROR;
