@@ -1280,7 +1280,7 @@ int gtlc_render(const GtlcRenderParams* params)
           }
           timed(K_SHADE, [&] {
             const uint32_t* permArg = sortByMaterial ? g.perm : nullptr;
-#define GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, VOL) shade_kernel<MAXC, NEE, AOV, TEX, VOL><<<gridElem, 256, 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
+#define GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, VOL) shade_kernel<MAXC, NEE, AOV, TEX, VOL><<<gridElem * 256 / shade_block_size(MAXC), shade_block_size(MAXC), 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
 // the medium stack only ever changes on transmission events, which only the OpenPBR closure produces
 #define GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, TEX) do { if (volumes && MAXC == GTLC_CLOSURE_OPENPBR) GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, (MAXC == GTLC_CLOSURE_OPENPBR)); else GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, false); } while (0)
 #define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) do { if (s->hasTextures) GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, true); else GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, false); } while (0)

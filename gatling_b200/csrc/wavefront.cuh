@@ -458,8 +458,21 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
 // ---- shade: rp_main.chit:132-493 + rp_main.miss:55-87 + rp_main.rgen:397-480 ----------------------
 // One thread per live path.  Survivors are compacted into `qout`, shadow rays appended to the shadow
 // queue, finished samples written to sampleRad[slot].
+// GTLC_SHADE_PHASE_SYNC: the body is cut into five phases (state set-up + emission | BSDF sample | light sample |
+// BSDF evaluate | roulette + compaction) and the 16 warps of a 512-thread CTA -- one CTA per SM at 90 registers -- enter
+// each phase together, so that the SM's instruction cache holds one phase at a time.  The OpenPBR + NEE instantiation is
+// ~190 KB of SASS and was measured stalling on instruction fetch (smsp__average_warps_issue_stalled_no_instruction ~17
+// per issued instruction, issue slots 18 % busy); with the barriers the kernel takes 36 ms instead of 49 ms on the C3
+// stand-in.  The Lambert-only instantiation is small and keeps 256-thread CTAs without barriers.
+#ifndef GTLC_SHADE_PHASE_SYNC
+#define GTLC_SHADE_PHASE_SYNC 1
+#endif
+#ifndef GTLC_SHADE_PHASE_MASK
+#define GTLC_SHADE_PHASE_MASK 2   // bit k: barrier in front of phase k + 2
+#endif
+constexpr int shade_block_size(int maxClosure) { return (GTLC_SHADE_PHASE_SYNC && maxClosure == GTLC_CLOSURE_OPENPBR) ? 512 : 256; }   // Lambert / UsdPreviewSurface: small code, no barrier
 template <int MAXC, bool NEE, bool AOV, bool TEX, bool VOL>
-__global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
+__global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
                                                     float4* shO, float4* shD, float4* shC, uint32_t* shSeed, float4* sampleRad,
@@ -467,10 +480,11 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
 {
   const unsigned FULL = 0xFFFFFFFFu;
   const uint32_t n = ctr->numPaths[inIdx];
-  const uint32_t nRounded = (n + 31u) & ~31u;
+  const uint32_t nRounded = ((n + blockDim.x - 1u) / blockDim.x) * blockDim.x;   // CTA-uniform trip count (warp ballots and the phase barrier need whole CTAs)
   const int lane = threadIdx.x & 31;
   const uint32_t rrBounceOffset = ubo.maxBouncesAndRrBounceOffset & 0xFFFFu;           // rgen:291
   uint32_t maxBounces = ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > kPayloadBouncesMask) maxBounces = kPayloadBouncesMask;
+  constexpr bool kPhaseSync = GTLC_SHADE_PHASE_SYNC && MAXC == GTLC_CLOSURE_OPENPBR;
   const bool nee = NEE;   // NEXT_EVENT_ESTIMATION is a compile-time permutation in the reference too (GlslShaderGen.cpp:107,247)
 
   for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nRounded; it += gridDim.x * blockDim.x) {
@@ -480,6 +494,14 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
     V3 neeToLight = v3(0.0f), neeContrib = v3(0.0f);
     uint32_t bitfield = 0, rng_state = 0, slot = 0, shadowSeed = 0;
     float nextTMax = kFloatMax; V3 nextWalkPdf = v3(1.0f); uint4 nextMedia = make_uint4(0u, 0u, 0u, 0u);
+    // state that lives across the two phases of a hit (BSDF sample | NEE)
+    ShadingState st; V3 normal = v3(0.0f), iorCurrent = v3(1.0f), iorOther = v3(1.0f), worldRayDir = v3(0.0f);
+    const float* mp = nullptr; int closure = 0; bool doNee = false, isHit = false, isFrontFace = false, thinWalled = false, hasMappedNormal = false;
+    V3 mappedNormal = v3(0.0f); uint32_t mediumIdx = 0, hitMaterial = 0;
+    bool neeValid = false; V3 neeDir = v3(0.0f), neeRadiance = v3(0.0f); uint32_t neeDiffuseSpecular = 0;
+    float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT : 1];                                     // textured inputs: private parameter block
+    uint32_t bounce = 0, loopMediumIdx = 0;                                            // rgen:298, :318 (read before the trace)
+    uint32_t media[kMaxMediumStack] = { 0u, 0u, 0u, 0u };
     if (valid) {
       const uint32_t i = perm ? perm[it] : it;
       const float4 ro = qin.rayO[i], rd = qin.rayD[i], th = qin.thr[i], ra = qin.rad[i];
@@ -487,13 +509,11 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
       const uint32_t inst = hitInst[i];
       slot = qin.slot[i];
       ray_origin = v3(ro.x, ro.y, ro.z); ray_dir = v3(rd.x, rd.y, rd.z);
-      const V3 worldRayDir = ray_dir;
+      worldRayDir = ray_dir;
       throughput = v3(th.x, th.y, th.z); bitfield = f2u(th.w);
       radiance = v3(ra.x, ra.y, ra.z); rng_state = f2u(ra.w);
-      const uint32_t bounce = bitfield & kPayloadBouncesMask;                          // rgen:298
-      uint32_t media[kMaxMediumStack] = { 0u, 0u, 0u, 0u };
+      bounce = bitfield & kPayloadBouncesMask;                                         // rgen:298
       V3 walkSegmentPdf = v3(1.0f);
-      uint32_t loopMediumIdx = 0;                                                      // rgen:318 (read before the trace)
       if (VOL) {
         const uint4 m4 = qin.med[i]; media[0] = m4.x; media[1] = m4.y; media[2] = m4.z; media[3] = m4.w;
         const float4 w4 = qin.walk[i]; walkSegmentPdf = v3(w4.x, w4.y, w4.z);
@@ -529,22 +549,21 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
         const InstanceInfo in = s.instInfo[inst];
         const bool isLeftHanded = (in.flags & 1u) != 0;                                // chit:137
         const bool isDoubleSided = (in.flags & 2u) != 0;                               // chit:138
-        const float* mp = s.matParams + (size_t) in.material * GTLC_MATERIAL_PARAM_COUNT;
-        const int closure = s.matClosure[in.material];
+        mp = s.matParams + (size_t) in.material * GTLC_MATERIAL_PARAM_COUNT;
+        closure = s.matClosure[in.material];
         const uint32_t mflags = s.matFlags[in.material];
-        ShadingState st; bool isFrontFace;
+        isHit = true; hitMaterial = in.material;
         setup_shading_state(s, in, inst, prim, h.y, h.z, worldRayDir, st, isFrontFace);   // chit:143
-        const V3 normal = st.normal;                                                   // chit:147
-        float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT : 1];                                 // textured inputs: private parameter block
-        V3 mappedNormal = normal; bool hasMappedNormal = false;
+        normal = st.normal;                                                            // chit:147
+        mappedNormal = normal;
         if (TEX && (s.matTexRange[in.material].y | s.matPrimvarRange[in.material].y) != 0u) {
           for (int k = 0; k < GTLC_MATERIAL_PARAM_COUNT; k++) lp[k] = mp[k];
           apply_primvar_bindings(s, in, inst, prim, h.y, h.z, st, lp);
           hasMappedNormal = apply_texture_bindings(s, in.material, worldRayDir, st, lp, mappedNormal);
           mp = lp;
         }
-        uint32_t mediumIdx = VOL ? loopMediumIdx : payload_medium_idx(bitfield, 0u);   // chit:153
-        const bool thinWalled = (mflags & kMatFlagThinWalled) != 0;                    // chit:155-158
+        mediumIdx = VOL ? loopMediumIdx : payload_medium_idx(bitfield, 0u);            // chit:153
+        thinWalled = (mflags & kMatFlagThinWalled) != 0;                               // chit:155-158
         V3 prevMediumIor = v3(1.0f), nextMediumIor = v3(1.0f);                         // chit:161-162
         if (mediumIdx > 0) {                                                           // chit:164-186
           const float distance = h.x * ubo.metersPerSceneUnit;
@@ -560,8 +579,8 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           }
         }
         const float kUseMaterialIor = -1.0f;                                           // mdl_types.glsl:155
-        const V3 iorCurrent = (isFrontFace || thinWalled) ? prevMediumIor : v3(kUseMaterialIor);   // chit:188
-        const V3 iorOther = (isFrontFace || thinWalled) ? v3(kUseMaterialIor) : nextMediumIor;     // chit:189
+        iorCurrent = (isFrontFace || thinWalled) ? prevMediumIor : v3(kUseMaterialIor);            // chit:188
+        iorOther = (isFrontFace || thinWalled) ? v3(kUseMaterialIor) : nextMediumIor;              // chit:189
         if (AOV && bounce == 0) {                                                      // chit:192-290
           const V2 clipRange = unpackHalf2x16(ubo.clipRangePacked);                    // chit:227
           const float logDepth = 2.0f * logf(h.x / clipRange.x) / logf(clipRange.y / clipRange.x) - 1.0f;   // chit:228
@@ -589,57 +608,67 @@ __global__ void __launch_bounds__(256) shade_kernel(UniformData ubo, DeviceScene
           }
           if (isDoubleSided) st.geom_normal *= (isLeftHanded ? -1.0f : 1.0f);
         }
-        st.normal = normal;                                                            // chit:346
-        if (TEX && hasMappedNormal) st.normal = mappedNormal;                          // what *_init() leaves in the state (chit:349-357)
-        uint32_t eventType;
-        {                                                                              // chit:361-389
-          BsdfSample d;
-          d.ior1 = iorCurrent; d.ior2 = iorOther; d.k1 = -worldRayDir;
-          d.xi = rng1d_next4f(rng_state);                                              // chit:370
-          bsdf_sample<MAXC>(closure, mp, d, st);
-          eventType = (uint32_t) d.event_type;
-          throughput *= d.bsdf_over_pdf;                                               // chit:386
-          ray_dir = d.k2;                                                              // chit:388
-        }
-        const bool isTransmissionEvent = (eventType & BSDF_EVENT_TRANSMISSION) != 0;   // chit:391
-        if (nee && (eventType & (BSDF_EVENT_DIFFUSE | BSDF_EVENT_GLOSSY)) != 0) {      // chit:394-444
-          st.normal = normal;
-          const V4 k4 = rng1d_next4f(rng_state);                                       // chit:404
-          LightSample ls;
-          sampleLight(ubo, s, k4, st.position, ls);
-          bool neeValid = (ls.dist > 0.0f) && dot(ls.dirToLight, st.geom_normal) > 0.0f;   // chit:415
-          if (neeValid) {
-            BsdfEval e;
-            e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = ls.dirToLight;
-            bsdf_evaluate<MAXC>(closure, mp, e, st);                                         // chit:425
-            neeValid = (e.pdf > 0.0f);
-            if (neeValid) {
-              const V2 diffuseSpecular = unpackHalf2x16(ls.diffuseSpecularPacked);
-              const V3 neeRadiance = ls.power * ls.invPdf;
-              const V3 weight = throughput * neeRadiance;
-              neeContrib += (weight * e.bsdf_diffuse) * diffuseSpecular.x;             // chit:436
-              neeContrib += (weight * e.bsdf_glossy) * diffuseSpecular.y;              // chit:437
-            }
-          }
-          neeToLight = ls.dirToLight * ls.dist;                                        // chit:441
-        }
-        if (!thinWalled && isTransmissionEvent) {                                      // chit:447-480
-          if (VOL) {
-            if (isFrontFace) {                                                         // push (chit:450-467)
-              mediumIdx++;
-              if (mediumIdx <= ubo.mediumStackSize) media[mediumIdx - 1] = in.material;
-            } else if (mediumIdx > 0) mediumIdx--;                                     // pop (chit:468-471)
-          } else mediumIdx = 1u - mediumIdx;                                           // chit:473
-          bitfield &= ~kPayloadWalkMask;
-          bitfield &= ~kPayloadMediumIdxMask;
-          const uint32_t mv = mediumIdx << kPayloadMediumIdxOffset;                    // rp_main_payload.glsl:91-95
-          bitfield |= (mv < kPayloadMediumIdxMask ? mv : kPayloadMediumIdxMask);
-        }
-        if (eventType == BSDF_EVENT_ABSORB) bitfield |= kPayloadTerminateFlag;         // chit:483-486
-        const V3 geomNormal = st.geom_normal * (isTransmissionEvent ? -1.0f : 1.0f);   // chit:488
-        ray_origin = offset_ray_origin(st.position, geomNormal);                       // chit:489
       }
-
+    }
+    if (kPhaseSync && (GTLC_SHADE_PHASE_MASK & 1)) __syncthreads();                    // phase 2: BSDF importance sampling
+    if (valid && isHit) {
+      st.normal = normal;                                                            // chit:346
+      if (TEX && hasMappedNormal) st.normal = mappedNormal;                          // what *_init() leaves in the state (chit:349-357)
+      uint32_t eventType;
+      {                                                                              // chit:361-389
+        BsdfSample d;
+        d.ior1 = iorCurrent; d.ior2 = iorOther; d.k1 = -worldRayDir;
+        d.xi = rng1d_next4f(rng_state);                                              // chit:370
+        bsdf_sample<MAXC>(closure, mp, d, st);
+        eventType = (uint32_t) d.event_type;
+        throughput *= d.bsdf_over_pdf;                                               // chit:386
+        ray_dir = d.k2;                                                              // chit:388
+      }
+      const bool isTransmissionEvent = (eventType & BSDF_EVENT_TRANSMISSION) != 0;   // chit:391
+      doNee = nee && (eventType & (BSDF_EVENT_DIFFUSE | BSDF_EVENT_GLOSSY)) != 0;    // chit:394 (the NEE block is phases 3 and 4)
+      if (!thinWalled && isTransmissionEvent) {                                      // chit:447-480
+        if (VOL) {
+          if (isFrontFace) {                                                         // push (chit:450-467)
+            mediumIdx++;
+            if (mediumIdx <= ubo.mediumStackSize) media[mediumIdx - 1] = hitMaterial;
+          } else if (mediumIdx > 0) mediumIdx--;                                     // pop (chit:468-471)
+        } else mediumIdx = 1u - mediumIdx;                                           // chit:473
+        bitfield &= ~kPayloadWalkMask;
+        bitfield &= ~kPayloadMediumIdxMask;
+        const uint32_t mv = mediumIdx << kPayloadMediumIdxOffset;                    // rp_main_payload.glsl:91-95
+        bitfield |= (mv < kPayloadMediumIdxMask ? mv : kPayloadMediumIdxMask);
+      }
+      if (eventType == BSDF_EVENT_ABSORB) bitfield |= kPayloadTerminateFlag;         // chit:483-486
+      const V3 geomNormal = st.geom_normal * (isTransmissionEvent ? -1.0f : 1.0f);   // chit:488
+      ray_origin = offset_ray_origin(st.position, geomNormal);                       // chit:489
+    }
+    if (kPhaseSync && (GTLC_SHADE_PHASE_MASK & 2)) __syncthreads();                    // phase 3: light sampling
+    if (valid && doNee) {                                                              // chit:394-444
+      st.normal = normal;
+      const V4 k4 = rng1d_next4f(rng_state);                                         // chit:404
+      LightSample ls;
+      sampleLight(ubo, s, k4, st.position, ls);
+      neeValid = (ls.dist > 0.0f) && dot(ls.dirToLight, st.geom_normal) > 0.0f;        // chit:415
+      neeToLight = ls.dirToLight * ls.dist;                                          // chit:441
+      neeDir = ls.dirToLight; neeRadiance = ls.power * ls.invPdf; neeDiffuseSpecular = ls.diffuseSpecularPacked;
+    }
+    if (kPhaseSync && (GTLC_SHADE_PHASE_MASK & 4)) __syncthreads();                    // phase 4: BSDF evaluation towards the light
+    if (valid && doNee) {
+      if (neeValid) {
+        BsdfEval e;
+        e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = neeDir;
+        bsdf_evaluate<MAXC>(closure, mp, e, st);                                         // chit:425
+        neeValid = (e.pdf > 0.0f);
+        if (neeValid) {
+          const V2 diffuseSpecular = unpackHalf2x16(neeDiffuseSpecular);
+          const V3 weight = throughput * neeRadiance;
+          neeContrib += (weight * e.bsdf_diffuse) * diffuseSpecular.x;             // chit:436
+          neeContrib += (weight * e.bsdf_glossy) * diffuseSpecular.y;              // chit:437
+        }
+      }
+    }
+    if (kPhaseSync && (GTLC_SHADE_PHASE_MASK & 8)) __syncthreads();                    // phase 5: shadow-ray set-up, roulette, compaction
+    if (valid) {
       // ---- rp_main.rgen:397-480 ----
       shadowSeed = rng_state;                                                          // rgen:399 (before the roulette draw)
       if (nee) {
