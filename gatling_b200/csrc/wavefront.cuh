@@ -470,7 +470,10 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
 #ifndef GTLC_SHADE_PHASE_MASK
 #define GTLC_SHADE_PHASE_MASK 2   // bit k: barrier in front of phase k + 2
 #endif
-constexpr int shade_block_size(int maxClosure) { return (GTLC_SHADE_PHASE_SYNC && maxClosure == GTLC_CLOSURE_OPENPBR) ? 512 : 256; }   // Lambert / UsdPreviewSurface: small code, no barrier
+#ifndef GTLC_SHADE_SYNC_MIN_CLOSURE
+#define GTLC_SHADE_SYNC_MIN_CLOSURE GTLC_CLOSURE_OPENPBR
+#endif
+constexpr int shade_block_size(int maxClosure) { return (GTLC_SHADE_PHASE_SYNC && maxClosure >= GTLC_SHADE_SYNC_MIN_CLOSURE) ? 512 : 256; }   // Lambert / UsdPreviewSurface: small code, no barrier
 template <int MAXC, bool NEE, bool AOV, bool TEX, bool VOL>
 __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
   const int lane = threadIdx.x & 31;
   const uint32_t rrBounceOffset = ubo.maxBouncesAndRrBounceOffset & 0xFFFFu;           // rgen:291
   uint32_t maxBounces = ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > kPayloadBouncesMask) maxBounces = kPayloadBouncesMask;
-  constexpr bool kPhaseSync = GTLC_SHADE_PHASE_SYNC && MAXC == GTLC_CLOSURE_OPENPBR;
+  constexpr bool kPhaseSync = GTLC_SHADE_PHASE_SYNC && MAXC >= GTLC_SHADE_SYNC_MIN_CLOSURE;
   const bool nee = NEE;   // NEXT_EVENT_ESTIMATION is a compile-time permutation in the reference too (GlslShaderGen.cpp:107,247)
 
   for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nRounded; it += gridDim.x * blockDim.x) {

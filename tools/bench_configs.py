@@ -16,6 +16,7 @@ ap.add_argument("--spp", type=int, default=16)
 ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale of c3/c5")
 ap.add_argument("--bvh-builder", type=int, default=0, help="0 host binned SAH, 1 device LBVH, 2 device PLOC")
 ap.add_argument("--trace-variant", type=int, default=0)
+ap.add_argument("--ups", action="store_true", help="replace the OpenPBR materials of c3/c5 by UsdPreviewSurface ones (same colours / roughness / metalness)")
 ap.add_argument("--tri-threshold", type=int, default=0)
 a = ap.parse_args()
 assert gi.giInitialize(0) == gi.GiStatus.Ok, gi.giLastError()
@@ -34,6 +35,10 @@ def make(name):
 for name in a.configs.split(","):
     t0 = time.perf_counter()
     d = make(name)
+    if a.ups:
+        O, U = scenes.OPBR, scenes.UPS
+        d.materials = [m if m.closure != scenes.CLOSURE_OPENPBR else scenes.material_usd_preview_surface(m.name, diffuse=tuple(m.params[O["base_color"]:O["base_color"] + 3]),
+                       roughness=float(m.params[O["specular_roughness"]]), metallic=float(m.params[O["base_metalness"]]), clearcoat=float(m.params[O["coat_weight"]])) for m in d.materials]
     t_gen = time.perf_counter() - t0
     import ctypes as C
     gi.set_tuning(bvhBuilder=a.bvh_builder, traceVariant=a.trace_variant, reserved=(C.c_int32 * 3)(0, 0, a.tri_threshold))
