@@ -1,6 +1,8 @@
 // Drives the C++ facade (include/gtl/gi/Gi.h) exactly the way hdGatling does: MaterialX source in,
 // GiMeshDesc with std::vector references, giRender, giGetRenderBufferMem.
 //   gi_facade_main lower            -> CPU only: MaterialX lowering checks, prints "lower ok"
+//   gi_facade_main objects          -> CPU only: object lifecycle through the facade (meshes with primvars, instancer primvars,
+//                                      materials with primvar readers, lights), host BVH through the C-ABI; prints "objects ok"
 //   gi_facade_main render out.bin   -> GPU: renders a 48x32 spp 4 two-material scene, writes float32 RGBA
 //   gi_facade_main render out.bin checker.ppm -> same, the floor's diffuseColor read from the image (UsdUVTexture + UsdTransform2d)
 #include <gtl/gi/Gi.h>
@@ -183,8 +185,59 @@ static int renderScene(const char* outPath, const char* texturePath)
   return 0;
 }
 
+// No GPU: everything up to (not including) giRender works on the host, like Hydra's parallel prim sync.
+static int objectTests()
+{
+  GiScene* scene = giCreateScene();
+  if (!scene) return 50;
+  GiMaterial* mat = giCreateMaterialFromMtlxStr(scene, "P", kPrimvarUps);
+  if (!mat) return 51;
+  std::vector<GiVertex> v = { vert(-1, -1, 0, 0, 0, 1), vert(1, -1, 0, 0, 0, 1), vert(1, 1, 0, 0, 0, 1), vert(-1, 1, 0, 0, 0, 1) };
+  std::vector<GiFace> f = { { { 0, 1, 2 } }, { { 0, 2, 3 } } };
+  std::vector<int> faceIds = { 7, 9 };
+  const float colours[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 1, 0 };
+  const float rough = 0.4f;
+  std::vector<GiPrimvarData> primvars(2);
+  primvars[0].name = "displayColor"; primvars[0].type = GiPrimvarType::Vec3; primvars[0].interpolation = GiPrimvarInterpolation::Vertex;
+  primvars[0].data.assign((const uint8_t*) colours, (const uint8_t*) colours + sizeof(colours));
+  primvars[1].name = "rough"; primvars[1].type = GiPrimvarType::Float; primvars[1].interpolation = GiPrimvarInterpolation::Constant;
+  primvars[1].data.assign((const uint8_t*) &rough, (const uint8_t*) &rough + 4);
+  GiMeshDesc md{ 2, f, faceIds, 3, true, false, "quad", 9, primvars, 4, v };
+  GiMesh* mesh = giCreateMesh(scene, md);
+  if (!mesh) { fprintf(stderr, "%s\n", giGetLastError()); return 52; }
+  giSetMeshMaterial(mesh, mat);
+  const float two[2][4][4] = { { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 }, { 0, 0, 0, 1 } }, { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 }, { 3, 0, 0, 1 } } };
+  giSetMeshInstanceTransforms(mesh, 2, two);
+  int ids[2] = { 1, 0 };
+  giSetMeshInstanceIds(mesh, 2, ids);
+  std::vector<GiPrimvarData> inst(1);
+  const float instRough[2] = { 0.2f, 0.8f };
+  inst[0].name = "rough"; inst[0].type = GiPrimvarType::Float; inst[0].interpolation = GiPrimvarInterpolation::Instance;
+  inst[0].data.assign((const uint8_t*) instRough, (const uint8_t*) instRough + 8);
+  giSetMeshInstancerPrimvars(mesh, inst);
+  GiRectLight* rl = giCreateRectLight(scene);
+  float o[3] = { 0, 0, 2 }, t0[3] = { 1, 0, 0 }, t1[3] = { 0, 1, 0 }, em[3] = { 5, 5, 5 };
+  giSetRectLightOrigin(rl, o); giSetRectLightTangents(rl, t0, t1); giSetRectLightBaseEmission(rl, em); giSetRectLightDimensions(rl, 1, 1);
+  // the flattened scene through the C-ABI: 2 instances x 2 triangles, second instance shifted by +3 in x
+  struct Peek { GtlcHandle h; };
+  GtlcBvhView view;
+  if (gtlc_scene_get_bvh(reinterpret_cast<Peek*>(scene)->h, &view) != GTLC_OK || view.triCount != 4 || view.nodeCount < 1) return 53;
+  float maxX = -1e30f;
+  for (uint32_t i = 0; i < view.triCount * 3; i++) maxX = std::fmax(maxX, view.triangles[i * 4]);
+  if (maxX != 4.0f) return 54;
+  // a mesh whose primvar description is broken is refused
+  std::vector<GiPrimvarData> bad(1);
+  bad[0].name = "x"; bad[0].type = (GiPrimvarType) 42; bad[0].interpolation = GiPrimvarInterpolation::Vertex;
+  GiMeshDesc bd{ 2, f, faceIds, 4, true, false, "bad", 9, bad, 4, v };
+  if (giCreateMesh(scene, bd) != nullptr) return 55;
+  giDestroyRectLight(scene, rl); giDestroyMesh(mesh); giDestroyMaterial(mat); giDestroyScene(scene);
+  printf("objects ok\n");
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
+  if (argc >= 2 && !strcmp(argv[1], "objects")) return objectTests();
   if (argc >= 2 && !strcmp(argv[1], "lower")) return lowerTests();
   if (argc >= 3 && !strcmp(argv[1], "render")) return renderScene(argv[2], argc >= 4 ? argv[3] : nullptr);
   fprintf(stderr, "usage: %s lower | render <out.bin>\n", argv[0]);

@@ -28,6 +28,15 @@ def test_facade_builds_and_lowers_materialx():
     assert "lower ok" in out.stdout
 
 
+def test_facade_object_lifecycle_without_gpu():
+    """Meshes with primvars, instancer primvars, instance ids, materials with primvar readers, lights: everything Hydra's
+    prim sync does before the first giRender works on the host and reaches the C-ABI with fully initialised structs."""
+    _ensure_built()
+    out = subprocess.run([EXE, "objects"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "objects ok" in out.stdout
+
+
 def test_facade_header_is_self_contained(tmp_path):
     """hdGatling only sees <gtl/gi/Gi.h>: it must compile on its own and keep the reference's aggregate layouts."""
     src = tmp_path / "t.cpp"
