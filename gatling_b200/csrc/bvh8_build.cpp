@@ -9,9 +9,9 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
 
 namespace gtlc {
 namespace {
@@ -172,16 +172,17 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
 #pragma omp single
   b.build(0, 0, N);
 
+  const auto tBinary = std::chrono::steady_clock::now();
   // ---- SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1), dynamic programme bottom-up over the
   // binary tree: cost[n][i-1] = cheapest way to present subtree n to its parent as at most i children
-  // (i = 1..7), each child either a leaf of <= kMaxLeaf triangles or a wide node.  Children of a binary node
-  // always have larger indices than the node itself (allocation order), so a descending index sweep is bottom-up.
+  // (i = 1..7), each child either a leaf of <= kMaxLeaf triangles or a wide node.  Bottom-up = post-order; the two
+  // subtrees of a big node are independent OpenMP tasks.
   const std::vector<BinNode>& bn = b.nodes;
   const uint32_t binCount = b.nodeCount.load();
   struct Dp { float cost[7]; uint8_t split[7]; uint8_t rootSplit; uint8_t rootIsLeaf; };
   std::vector<Dp> dp(binCount);
   const float INF = 3.402823466e38f;
-  for (int64_t ni = (int64_t) binCount - 1; ni >= 0; ni--) {
+  auto solveNode = [&](uint32_t ni) {
     const BinNode& n = bn[ni];
     Dp& d = dp[ni];
     const float area = n.box.area();
@@ -189,7 +190,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     if (n.count > 0) {                       // binary leaf (single triangle or coincident centroids)
       for (int i = 0; i < 7; i++) { d.cost[i] = leafCost; d.split[i] = 0; }
       d.rootSplit = 0; d.rootIsLeaf = 1;
-      continue;
+      return;
     }
     const Dp& L = dp[n.left]; const Dp& R = dp[n.right];
     // as one wide node: distribute 8 child slots between the two binary children
@@ -204,7 +205,26 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
       if (bd < d.cost[i - 2]) { d.cost[i - 1] = bd; d.split[i - 1] = bs; }
       else { d.cost[i - 1] = d.cost[i - 2]; d.split[i - 1] = 0; }   // 0 = same as with one child fewer
     }
-  }
+  };
+  // post-order; big subtrees become OpenMP tasks, small ones run as an explicit-stack walk inside their task
+  auto solveSubtree = [&](auto&& self, uint32_t root) -> void {
+    if (bn[root].count == 0 && bn[root].total > 32768) {
+#pragma omp task default(shared)
+      self(self, bn[root].left);
+#pragma omp task default(shared)
+      self(self, bn[root].right);
+#pragma omp taskwait
+      solveNode(root);
+      return;
+    }
+    std::vector<uint32_t> order; order.reserve(2 * (size_t) bn[root].total);
+    order.push_back(root);
+    for (size_t h = 0; h < order.size(); h++) { const BinNode& n = bn[order[h]]; if (n.count == 0) { order.push_back(n.left); order.push_back(n.right); } }
+    for (size_t h = order.size(); h-- > 0;) solveNode(order[h]);      // children come after their parent in `order`
+  };
+#pragma omp parallel
+#pragma omp single
+  solveSubtree(solveSubtree, 0u);
   // expands "subtree `node` as at most `i` children" into the child list
   struct WideChildList { WideChild ch[8]; int n; };
   auto gather = [&](auto&& self, uint32_t node, int i, WideChildList& out) -> void {
@@ -216,24 +236,45 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     self(self, bn[node].right, i - k, out);
   };
 
+  const auto tDp = std::chrono::steady_clock::now();
+  // ---- emission, one level of the wide tree at a time (the same scheme as the device builder): child lists and their
+  // sizes in parallel, a prefix sum fixes every node's childBase / triBase, then the nodes are written in parallel.
+  // The layout is the breadth-first order a serial queue would produce.
   struct Pending { uint32_t bin, wide, depth; };
-  std::deque<Pending> queue;
-  out.nodes.reserve(N / 4 + 16);
-  out.tris.reserve((size_t) N * 12);
-  out.nodes.emplace_back();
-  queue.push_back({ 0u, 0u, 1u });
-
-  while (!queue.empty()) {
-    Pending cur = queue.front(); queue.pop_front();
-    out.maxDepth = std::max(out.maxDepth, cur.depth);
-    const BinNode& root = bn[cur.bin];
-    WideChildList list; list.n = 0;
-    if (dp[cur.bin].rootIsLeaf) { list.ch[list.n++] = { cur.bin, true }; }       // only possible for the global root
-    else {
-      gather(gather, root.left, dp[cur.bin].rootSplit, list);
-      gather(gather, root.right, 8 - dp[cur.bin].rootSplit, list);
+  std::vector<Pending> level, next;
+  out.nodes.assign(1, Bvh8Node());
+  out.tris.clear();
+  level.push_back({ 0u, 0u, 1u });
+  uint32_t nodeBase = 1, triBaseLevel = 0;
+  while (!level.empty()) {
+    const int64_t M = (int64_t) level.size();
+    out.maxDepth = std::max(out.maxDepth, level[0].depth);
+    std::vector<WideChildList> lists((size_t) M);
+    std::vector<uint32_t> nodeOff((size_t) M), triOff((size_t) M);
+#pragma omp parallel for schedule(static) if (M > 256)
+    for (int64_t e = 0; e < M; e++) {
+      const Pending cur = level[(size_t) e];
+      WideChildList& list = lists[(size_t) e]; list.n = 0;
+      if (dp[cur.bin].rootIsLeaf) { list.ch[list.n++] = { cur.bin, true }; }       // only possible for the global root
+      else {
+        gather(gather, bn[cur.bin].left, dp[cur.bin].rootSplit, list);
+        gather(gather, bn[cur.bin].right, 8 - dp[cur.bin].rootSplit, list);
+      }
+      uint32_t nn = 0, nt = 0;
+      for (int i = 0; i < list.n; i++) { if (list.ch[i].leaf) nt += bn[list.ch[i].bin].total; else nn++; }
+      nodeOff[(size_t) e] = nn; triOff[(size_t) e] = nt;
     }
-    WideChild* ch = list.ch; const int n = list.n;
+    uint32_t totalNodes = 0, totalTris = 0;
+    for (int64_t e = 0; e < M; e++) { const uint32_t a = nodeOff[(size_t) e], t = triOff[(size_t) e]; nodeOff[(size_t) e] = totalNodes; triOff[(size_t) e] = totalTris; totalNodes += a; totalTris += t; }
+    out.nodes.resize((size_t) nodeBase + totalNodes);
+    out.tris.resize((size_t) (triBaseLevel + totalTris) * 12);
+    next.assign(totalNodes, Pending{ 0u, 0u, 0u });
+#pragma omp parallel for schedule(static) if (M > 256)
+    for (int64_t ei = 0; ei < M; ei++) {
+    const size_t e = (size_t) ei;
+    const Pending cur = level[e];
+    const BinNode& root = bn[cur.bin];
+    WideChild* ch = lists[e].ch; const int n = lists[e].n;
     // ---- octant-aware slot assignment (greedy): slot s sits towards the corner whose sign bits are s
     const Box& pb = root.box;
     float pc[3] = { 0.5f * (pb.lo[0] + pb.hi[0]), 0.5f * (pb.lo[1] + pb.hi[1]), 0.5f * (pb.lo[2] + pb.hi[2]) };
@@ -280,8 +321,8 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     std::memcpy(&node.w[0], &porigin[0], 4); std::memcpy(&node.w[1], &porigin[1], 4); std::memcpy(&node.w[2], &porigin[2], 4);
     uint8_t meta[8] = { 0 }; uint8_t q[6][8]; std::memset(q, 0, sizeof(q));
     uint32_t imask = 0;
-    uint32_t childBase = (uint32_t) out.nodes.size();
-    uint32_t triBase = (uint32_t) (out.tris.size() / 12);
+    const uint32_t childBase = nodeBase + nodeOff[e];
+    const uint32_t triBase = triBaseLevel + triOff[e];
     uint32_t nInternal = 0, triOffset = 0;
     for (int s = 0; s < 8; s++) {
       int i = childAtSlot[s];
@@ -305,7 +346,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
           float rec[12];
           for (int v = 0; v < 3; v++) { rec[v * 4 + 0] = tr.v[v][0]; rec[v * 4 + 1] = tr.v[v][1]; rec[v * 4 + 2] = tr.v[v][2]; }
           std::memcpy(&rec[3], &tr.prim, 4); std::memcpy(&rec[7], &tr.inst, 4); rec[11] = tr.opacity;
-          out.tris.insert(out.tris.end(), rec, rec + 12);
+          std::memcpy(&out.tris[(size_t) (triBase + triOffset + t) * 12], rec, sizeof(rec));
         }
         triOffset += cnt;
       } else {
@@ -322,15 +363,22 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     std::memcpy(&node.w[16], q[4], 8); std::memcpy(&node.w[18], q[5], 8);   // qhi_y, qhi_z
     out.nodes[cur.wide] = node;
     // internal children get consecutive indices in slot order
-    uint32_t next = childBase;
-    out.nodes.resize(out.nodes.size() + nInternal);
-    for (int s = 0; s < 8; s++) {
-      int i = childAtSlot[s];
+    uint32_t k = 0;
+    for (int sl = 0; sl < 8; sl++) {
+      const int i = childAtSlot[sl];
       if (i < 0 || ch[i].leaf) continue;
-      queue.push_back({ ch[i].bin, next++, cur.depth + 1 });
+      next[nodeOff[e] + k] = { ch[i].bin, childBase + k, cur.depth + 1 };
+      k++;
     }
+    }
+    nodeBase += totalNodes; triBaseLevel += totalTris;
+    level.swap(next);
   }
   out.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (getenv("GTLC_BUILD_TIMING")) {
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[gtlc] host BVH8: binary SAH %.0f ms, collapse table %.0f ms, wide-node emission %.0f ms\n", ms(t0, tBinary), ms(tBinary, tDp), ms(tDp, std::chrono::steady_clock::now()));
+  }
 }
 
 } // namespace gtlc
