@@ -32,6 +32,7 @@ struct Box {
 struct BinNode { Box box; uint32_t left, right, first, count, total; };   // count > 0: binary leaf; total = triangles in the subtree
 
 constexpr int kBins = 16;
+constexpr uint32_t kParallelRange = 262144;   // ranges at least this long are scanned by several tasks
 // SAH parameters (overridable through GTLC_BVH_MAX_LEAF / GTLC_BVH_NODE_COST for tuning experiments)
 uint32_t kMaxLeaf = 3;
 float kNodeCost = 0.6f;  // relative to one triangle test
@@ -50,15 +51,31 @@ struct Builder {
 
   void build(uint32_t node, uint32_t begin, uint32_t end)
   {
+    const uint32_t count = end - begin;
+    // The top of the tree is a handful of huge ranges: their passes are cut into chunks that run as tasks of the team
+    // (min / max / counts merge exactly, so the tree does not depend on the chunking).
+    const uint32_t chunks = count >= kParallelRange ? 64u : 1u;
+    const uint32_t chunkLen = (count + chunks - 1) / chunks;
     Box box, cbox;
     box.reset(); cbox.reset();
-    for (uint32_t i = begin; i < end; i++) {
-      box.grow(triBox[idx[i]]);
-      cbox.grow(&cen[(size_t) idx[i] * 3]);
+    if (chunks == 1) {
+      for (uint32_t i = begin; i < end; i++) {
+        box.grow(triBox[idx[i]]);
+        cbox.grow(&cen[(size_t) idx[i] * 3]);
+      }
+    } else {
+      std::vector<Box> pb(chunks), pc(chunks);
+#pragma omp taskloop default(shared) grainsize(1)
+      for (uint32_t c = 0; c < chunks; c++) {
+        Box a, d; a.reset(); d.reset();
+        const uint32_t e0 = begin + c * chunkLen, e1 = std::min(end, e0 + chunkLen);
+        for (uint32_t i = e0; i < e1; i++) { a.grow(triBox[idx[i]]); d.grow(&cen[(size_t) idx[i] * 3]); }
+        pb[c] = a; pc[c] = d;
+      }
+      for (uint32_t c = 0; c < chunks; c++) { if (pb[c].lo[0] <= pb[c].hi[0]) box.grow(pb[c]); if (pc[c].lo[0] <= pc[c].hi[0]) cbox.grow(pc[c]); }
     }
     BinNode& n = nodes[node];
     n.box = box;
-    uint32_t count = end - begin;
     auto makeLeaf = [&]() { n.first = begin; n.count = count; n.total = count; n.left = n.right = 0; };
     if (count == 1) { makeLeaf(); return; }
 
@@ -92,10 +109,27 @@ struct Builder {
       float scale = (float) kBins / ext;
       Box bb[kBins]; uint32_t bc[kBins];
       for (int b = 0; b < kBins; b++) { bb[b].reset(); bc[b] = 0; }
-      for (uint32_t i = begin; i < end; i++) {
-        int b = (int) ((cen[(size_t) idx[i] * 3 + axis] - lo) * scale);
-        b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-        bb[b].grow(triBox[idx[i]]); bc[b]++;
+      if (chunks == 1) {
+        for (uint32_t i = begin; i < end; i++) {
+          int b = (int) ((cen[(size_t) idx[i] * 3 + axis] - lo) * scale);
+          b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+          bb[b].grow(triBox[idx[i]]); bc[b]++;
+        }
+      } else {
+        struct Partial { Box bb[kBins]; uint32_t bc[kBins]; };
+        std::vector<Partial> part(chunks);
+#pragma omp taskloop default(shared) grainsize(1)
+        for (uint32_t c = 0; c < chunks; c++) {
+          Partial& pt = part[c];
+          for (int b = 0; b < kBins; b++) { pt.bb[b].reset(); pt.bc[b] = 0; }
+          const uint32_t e0 = begin + c * chunkLen, e1 = std::min(end, e0 + chunkLen);
+          for (uint32_t i = e0; i < e1; i++) {
+            int b = (int) ((cen[(size_t) idx[i] * 3 + axis] - lo) * scale);
+            b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+            pt.bb[b].grow(triBox[idx[i]]); pt.bc[b]++;
+          }
+        }
+        for (uint32_t c = 0; c < chunks; c++) for (int b = 0; b < kBins; b++) if (part[c].bc[b]) { bb[b].grow(part[c].bb[b]); bc[b] += part[c].bc[b]; }
       }
       float rightArea[kBins]; uint32_t rightCount[kBins];
       Box acc; acc.reset(); uint32_t c = 0;
