@@ -302,7 +302,7 @@ def run_ours(a):
                             "full HDR colour AOV copied to pinned host memory every step; scene/BVH stay resident as in the reference (rebuilt only when dirty)"},
             "gpu_launches": int(acc["kernelLaunches"]),
             "roofline": {"bound": "hbm", "kernel": "trace_kernel_batched<TRACE_CLOSEST>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": (traffic or {}).get("mean"), "traffic_detail": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg_bytes_step, "kernel_ms_per_step": trace_ms_step,
                          "nodes_per_ray": s_count["nodeVisits"] / max(rays_c, 1), "tris_per_ray": s_count["triVisits"] / max(rays_c, 1),
                          "note": "algorithmic bytes = 32+20 per ray + 80 per BVH8 node visit + 48 per triangle test (exact device counters of an untimed counting pass over the identical rays); the 68 MB BVH is L2-resident, so DRAM traffic is far below the algorithmic bytes"},
