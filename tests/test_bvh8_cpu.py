@@ -75,3 +75,26 @@ def test_degenerate_inputs():
         assert np.all(h["t"] == -1)
     finally:
         b.close()
+
+
+def test_host_build_is_independent_of_the_thread_count(tmp_path):
+    """The builder runs as OpenMP tasks with atomically allocated node slots; the emitted BVH8 (breadth-first order from the
+    root) must not depend on how many threads took part."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    script = tmp_path / "h.py"
+    script.write_text(
+        "import sys, hashlib\n"
+        "sys.path.insert(0, %r)\n"
+        "from gatling_b200 import gi, scenes\n"
+        "for d in (scenes.random_triangles(300000, 8, 8, 1), scenes.kitchen_standin(tris_per_instance=400, instances=60, meshes=12, materials=4, width=8, height=8, spp=1)):\n"
+        "    d.dome_light = None\n"
+        "    b = gi.BuiltScene(d); n, t = gi.get_bvh(b.scene); b.close()\n"
+        "    print(hashlib.sha256(n.tobytes() + t.tobytes()).hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for threads in ("1", "5"):
+        env = dict(os.environ, OMP_NUM_THREADS=threads)
+        outs.append(subprocess.check_output([sys.executable, str(script)], env=env, text=True))
+    assert outs[0] == outs[1] and len(outs[0].split()) == 2
