@@ -176,3 +176,171 @@ extern "C" void orc_bvh8_trace_delayed(const void* nodesV, const void* trisV, co
   }
   outCounts[0] = totN; outCounts[1] = totT;
 }
+
+// Analysis helper (not a restatement of any kernel): the same BVH8 walked in exact near-to-far order -- every hit child of
+// a node, internal or leaf, is pushed with its entry distance and the closest pending entry is processed next.  Gives the
+// node-visit / triangle-test counts an ideally ordered traversal would need; outCounts = {nodes, triangles}.
+// mode 0: global priority queue (ideal order); mode 1: a stack, the hit children of each node pushed far-to-near (what a
+// kernel that sorts the <= 8 hits of a node would do); mode 2: a stack, children pushed in the kernel's octant order
+// (slot ^ octinv, highest first) but leaf children deferred like internal ones; mode 3: octant order for internal children,
+// the node's leaf triangles tested at once (= the production order, as a cross-check of this helper).  Triangles are tested
+// when their leaf entry is popped.
+extern "C" void orc_bvh8_trace_ordered(const void* nodesV, const void* trisV, const float* rays, uint32_t n, uint64_t* outCounts, int mode)
+{
+  using namespace orc;
+  const uint8_t* nodes = (const uint8_t*) nodesV; const float* tris = (const float*) trisV;
+  uint64_t totalNodes = 0, totalTris = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : totalNodes, totalTris)
+  for (int64_t r = 0; r < (int64_t) n; r++) {
+    const float* ry = rays + r * 8;
+    const V3 o = v3(ry[0], ry[1], ry[2]), d = v3(ry[4], ry[5], ry[6]);
+    const float tmin = ry[3], tmax = ry[7];
+    if (!(tmax > tmin)) continue;
+    RayPre rp = ray_precompute(d);
+    const float kMinDir = 8.271806125530277e-25f;
+    const V3 idir = v3(1.0f / (fabsf(d.x) > kMinDir ? d.x : copysignf(kMinDir, d.x)), 1.0f / (fabsf(d.y) > kMinDir ? d.y : copysignf(kMinDir, d.y)),
+                       1.0f / (fabsf(d.z) > kMinDir ? d.z : copysignf(kMinDir, d.z)));
+    struct Entry { float tn; uint32_t ref; };      // ref: bit 31 = triangle run (base | count << 24), else node index
+    Entry heap[512]; int hn = 0;
+    const uint32_t octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+    auto push = [&](float tn, uint32_t ref) { int i = hn++; heap[i] = { tn, ref }; while (i > 0 && heap[(i - 1) / 2].tn > heap[i].tn) { std::swap(heap[i], heap[(i - 1) / 2]); i = (i - 1) / 2; } };
+    auto pop = [&]() { Entry top = heap[0]; heap[0] = heap[--hn]; int i = 0; while (true) { int l = 2 * i + 1, rr = l + 1, m = i; if (l < hn && heap[l].tn < heap[m].tn) m = l; if (rr < hn && heap[rr].tn < heap[m].tn) m = rr; if (m == i) break; std::swap(heap[i], heap[m]); i = m; } return top; };
+    float bt = tmax;
+    push(tmin, 0u);
+    while (hn > 0) {
+      Entry cur;
+      if (mode == 0) { cur = pop(); if (cur.tn > bt) break; }
+      else { cur = heap[--hn]; if (cur.tn > bt) continue; }
+      if (cur.ref & 0x80000000u) {
+        const uint32_t base = cur.ref & 0x00FFFFFFu, cnt = (cur.ref >> 24) & 0x7Fu;
+        for (uint32_t k = 0; k < cnt; k++) {
+          const float* tp = tris + (size_t) (base + k) * 12;
+          totalTris++;
+          float t, u, v;
+          if (tri_intersect(rp, o, v3(tp[0], tp[1], tp[2]), v3(tp[4], tp[5], tp[6]), v3(tp[8], tp[9], tp[10]), t, u, v) && t > tmin && t < bt) bt = t;
+        }
+        continue;
+      }
+      const uint8_t* nd = nodes + (size_t) cur.ref * 80;
+      totalNodes++;
+      const uint32_t e = ld32(nd + 12);
+      const float sc[3] = { uintBitsToFloat((e & 0xFFu) << 23), uintBitsToFloat(((e >> 8) & 0xFFu) << 23), uintBitsToFloat(((e >> 16) & 0xFFu) << 23) };
+      const float org[3] = { ldf(nd + 0), ldf(nd + 4), ldf(nd + 8) }, oo[3] = { o.x, o.y, o.z }, id[3] = { idir.x, idir.y, idir.z };
+      const uint32_t imask = e >> 24, childBase = ld32(nd + 16), triBase = ld32(nd + 20);
+      Entry local[8]; float key[8]; int nl = 0;
+      for (int i = 0; i < 8; i++) {
+        const uint32_t m = nd[24 + i];
+        if (!m) continue;
+        float tn = tmin, tf = bt;
+        for (int a = 0; a < 3; a++) {
+          const float lo = (org[a] + (float) nd[32 + 8 * a + i] * sc[a] - oo[a]) * id[a], hi = (org[a] + (float) nd[56 + 8 * a + i] * sc[a] - oo[a]) * id[a];
+          tn = fmaxf(tn, fminf(lo, hi)); tf = fminf(tf, fmaxf(lo, hi));
+        }
+        if (tn > tf * 1.0000004f) continue;
+        const uint32_t ref = ((m & 31u) >= 24u) ? childBase + (uint32_t) __builtin_popcount(imask & ((1u << i) - 1u))
+                                                : (0x80000000u | ((uint32_t) __builtin_popcount(m >> 5) << 24) | (triBase + (m & 31u)));
+        if (mode == 0) push(tn, ref);
+        else if (mode == 3 && (ref & 0x80000000u)) {           // immediate triangle tests
+          const uint32_t base = ref & 0x00FFFFFFu, cnt = (ref >> 24) & 0x7Fu;
+          for (uint32_t k = 0; k < cnt; k++) {
+            const float* tp = tris + (size_t) (base + k) * 12;
+            totalTris++;
+            float t, u, v;
+            if (tri_intersect(rp, o, v3(tp[0], tp[1], tp[2]), v3(tp[4], tp[5], tp[6]), v3(tp[8], tp[9], tp[10]), t, u, v) && t > tmin && t < bt) bt = t;
+          }
+        }
+        else { local[nl].tn = (mode == 1) ? tn : -(float) ((uint32_t) i ^ octinv); local[nl].ref = ref; key[nl] = tn; nl++; }
+      }
+      if (mode != 0) {                       // lowest priority first onto the stack
+        int ord[8]; for (int q = 0; q < nl; q++) ord[q] = q;
+        for (int a = 1; a < nl; a++) { const int v = ord[a]; int b = a - 1; while (b >= 0 && local[ord[b]].tn < local[v].tn) { ord[b + 1] = ord[b]; b--; } ord[b + 1] = v; }   // descending priority key
+        for (int q = 0; q < nl; q++) { heap[hn].tn = key[ord[q]]; heap[hn].ref = local[ord[q]].ref; hn++; }
+      }
+    }
+    if (tmax > tmin) { totalNodes += 0; }
+  }
+  outCounts[0] = totalNodes; outCounts[1] = totalTris;
+}
+
+// Analysis helper: the production walk (octant order, node groups on the stack, a node's triangles tested at once) with ONE
+// extra float per stack entry -- the smallest entry distance among the group's remaining children.  A popped group whose
+// bound lies beyond the current best hit is dropped without fetching any of its nodes.  outCounts = {nodes, triangles}.
+// mode 0: bound = smallest entry distance of the children still in the group; mode 1: bound = smallest entry distance of all
+// internal children the node step found (computed once, never updated -- cheaper in a kernel, weaker).
+extern "C" void orc_bvh8_trace_groupcull(const void* nodesV, const void* trisV, const float* rays, uint32_t n, uint64_t* outCounts, int mode)
+{
+  using namespace orc;
+  const uint8_t* nodes = (const uint8_t*) nodesV; const float* tris = (const float*) trisV;
+  uint64_t totalNodes = 0, totalTris = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : totalNodes, totalTris)
+  for (int64_t r = 0; r < (int64_t) n; r++) {
+    const float* ry = rays + r * 8;
+    const V3 o = v3(ry[0], ry[1], ry[2]), d = v3(ry[4], ry[5], ry[6]);
+    const float tmin = ry[3], tmax = ry[7];
+    if (!(tmax > tmin)) continue;
+    RayPre rp = ray_precompute(d);
+    const float kMinDir = 8.271806125530277e-25f;
+    const V3 idir = v3(1.0f / (fabsf(d.x) > kMinDir ? d.x : copysignf(kMinDir, d.x)), 1.0f / (fabsf(d.y) > kMinDir ? d.y : copysignf(kMinDir, d.y)),
+                       1.0f / (fabsf(d.z) > kMinDir ? d.z : copysignf(kMinDir, d.z)));
+    const uint32_t octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+    struct Group { uint32_t base, imask, hits; float tn[8]; float minAll, minRest; };       // hits: bit (s ^ octinv) per hit internal child in slot s; tn by slot
+    Group stack[64]; int sp = 0;
+    float bt = tmax;
+    Group G; G.base = 0; G.imask = 1; G.hits = 1u << (0 ^ octinv); for (int k = 0; k < 8; k++) G.tn[k] = tmin;
+    G.minAll = tmin; G.minRest = tmin;
+    bool haveG = true;
+    while (true) {
+      if (!haveG) {
+        if (sp == 0) break;
+        G = stack[--sp]; haveG = true;
+        float mn = 3.4e38f;                                          // the one float a real stack entry would carry
+        for (int k = 0; k < 8; k++) if (G.hits & (1u << (k ^ octinv))) mn = fminf(mn, G.tn[k]);
+        if (mode == 1) mn = G.minAll;
+        if (mode == 2) mn = G.minRest;
+        if (mn > bt) { haveG = false; continue; }
+      }
+      uint32_t bit = 31; while (!(G.hits & (1u << bit))) bit--;
+      G.hits &= ~(1u << bit);
+      const uint32_t slot = bit ^ octinv;
+      const uint32_t node = G.base + (uint32_t) __builtin_popcount(G.imask & ((1u << slot) - 1u));
+      if (G.hits) {
+        if (G.minRest < 0.0f) {   // first push of this group: one float = min over the children that stay behind (mode 2)
+          float m2 = 3.4e38f; for (int k = 0; k < 8; k++) if (G.hits & (1u << (k ^ octinv))) m2 = fminf(m2, G.tn[k]);
+          G.minRest = m2;
+        }
+        stack[sp++] = G;
+      }
+      haveG = false;
+      const uint8_t* nd = nodes + (size_t) node * 80;
+      totalNodes++;
+      const uint32_t e = ld32(nd + 12);
+      const float sc[3] = { uintBitsToFloat((e & 0xFFu) << 23), uintBitsToFloat(((e >> 8) & 0xFFu) << 23), uintBitsToFloat(((e >> 16) & 0xFFu) << 23) };
+      const float org[3] = { ldf(nd + 0), ldf(nd + 4), ldf(nd + 8) }, oo[3] = { o.x, o.y, o.z }, id[3] = { idir.x, idir.y, idir.z };
+      Group C; C.base = ld32(nd + 16); C.imask = e >> 24; C.hits = 0; C.minAll = 3.4e38f; C.minRest = -1.0f;
+      const uint32_t triBase = ld32(nd + 20);
+      for (int i = 0; i < 8; i++) {
+        const uint32_t m = nd[24 + i];
+        C.tn[i] = 3.4e38f;
+        if (!m) continue;
+        float tn = tmin, tf = bt;
+        for (int a = 0; a < 3; a++) {
+          const float lo = (org[a] + (float) nd[32 + 8 * a + i] * sc[a] - oo[a]) * id[a], hi = (org[a] + (float) nd[56 + 8 * a + i] * sc[a] - oo[a]) * id[a];
+          tn = fmaxf(tn, fminf(lo, hi)); tf = fminf(tf, fmaxf(lo, hi));
+        }
+        if (tn > tf * 1.0000004f) continue;
+        if ((m & 31u) >= 24u) { C.hits |= 1u << ((uint32_t) i ^ octinv); C.tn[i] = tn; C.minAll = fminf(C.minAll, tn); }
+        else {
+          const uint32_t base = triBase + (m & 31u), cnt = (uint32_t) __builtin_popcount(m >> 5);
+          for (uint32_t k = 0; k < cnt; k++) {
+            const float* tp = tris + (size_t) (base + k) * 12;
+            totalTris++;
+            float t, u, v;
+            if (tri_intersect(rp, o, v3(tp[0], tp[1], tp[2]), v3(tp[4], tp[5], tp[6]), v3(tp[8], tp[9], tp[10]), t, u, v) && t > tmin && t < bt) bt = t;
+          }
+        }
+      }
+      if (C.hits) { G = C; haveG = true; }
+    }
+  }
+  outCounts[0] = totalNodes; outCounts[1] = totalTris;
+}
