@@ -98,3 +98,30 @@ def test_host_build_is_independent_of_the_thread_count(tmp_path):
         env = dict(os.environ, OMP_NUM_THREADS=threads)
         outs.append(subprocess.check_output([sys.executable, str(script)], env=env, text=True))
     assert outs[0] == outs[1] and len(outs[0].split()) == 2
+
+
+def test_analysis_walkers_bound_the_production_walk():
+    """The oracle's analysis walkers (ideal near-to-far order, culling deferred node groups at pop) only count visits; they
+    must never need MORE node visits than the production order they are compared with in DESIGN.md section 8."""
+    import ctypes as C
+    d = scenes.random_triangles(40000, 16, 16, spp=1)
+    b = gi.BuiltScene(d)
+    try:
+        nodes, tris = gi.get_bvh(b.scene)
+    finally:
+        b.close()
+    rays = np.ascontiguousarray(random_rays(20000, 3), np.float32)
+    _, visits = orc.bvh8_trace(nodes, tris, rays)
+    L = orc.lib()
+    L.orc_bvh8_trace_ordered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+    L.orc_bvh8_trace_groupcull.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+    production = int(visits[:, 0].sum())
+    counts = {}
+    for name, fn, mode in (("queue", L.orc_bvh8_trace_ordered, 0), ("sorted", L.orc_bvh8_trace_ordered, 1), ("group", L.orc_bvh8_trace_groupcull, 0),
+                           ("group1", L.orc_bvh8_trace_groupcull, 2), ("all", L.orc_bvh8_trace_groupcull, 1)):
+        out = (C.c_uint64 * 2)()
+        fn(nodes.ctypes.data, tris.ctypes.data, rays.ctypes.data, len(rays), out, mode)
+        counts[name] = int(out[0])
+    assert counts["queue"] <= counts["sorted"] <= production
+    assert counts["queue"] <= counts["group"] <= counts["group1"] <= counts["all"] <= production
+    assert counts["group"] < production                  # culling at pop saves node fetches whenever rays hit something
