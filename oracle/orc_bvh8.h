@@ -344,3 +344,68 @@ extern "C" void orc_bvh8_trace_groupcull(const void* nodesV, const void* trisV, 
   }
   outCounts[0] = totalNodes; outCounts[1] = totalTris;
 }
+
+// Analysis helper: of the nodes the production walk fetches, how many could be rejected by a slab test against the node's
+// own quantisation grid [p, p + 255 * 2^e] (available from the first 16 bytes of the node) before any child is looked at?
+// outCounts = {node visits, of which the grid box is missed or starts beyond the current best hit, of which no child is hit}.
+extern "C" void orc_bvh8_grid_earlyout(const void* nodesV, const void* trisV, const float* rays, uint32_t n, uint64_t* outCounts)
+{
+  using namespace orc;
+  const uint8_t* nodes = (const uint8_t*) nodesV; const float* tris = (const float*) trisV;
+  uint64_t visits = 0, gridCulled = 0, emptyHit = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : visits, gridCulled, emptyHit)
+  for (int64_t r = 0; r < (int64_t) n; r++) {
+    const float* ry = rays + r * 8;
+    const V3 o = v3(ry[0], ry[1], ry[2]), d = v3(ry[4], ry[5], ry[6]);
+    const float tmin = ry[3], tmax = ry[7];
+    if (!(tmax > tmin)) continue;
+    RayPre rp = ray_precompute(d);
+    const float kMinDir = 8.271806125530277e-25f;
+    const V3 idir = v3(1.0f / (fabsf(d.x) > kMinDir ? d.x : copysignf(kMinDir, d.x)), 1.0f / (fabsf(d.y) > kMinDir ? d.y : copysignf(kMinDir, d.y)),
+                       1.0f / (fabsf(d.z) > kMinDir ? d.z : copysignf(kMinDir, d.z)));
+    const uint32_t octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+    float bt = tmax;
+    uint32_t stackX[64], stackY[64]; int sp = 0;
+    uint32_t Gx = 0, Gy = 0x80000000u;
+    while (true) {
+      uint32_t Tx = 0, Ty = 0;
+      if (Gy & 0xFF000000u) {
+        const uint32_t hits_imask = Gy;
+        uint32_t bit = 31; while (!(hits_imask & (1u << bit))) bit--;
+        Gy &= ~(1u << bit);
+        if (Gy & 0xFF000000u) { stackX[sp] = Gx; stackY[sp] = Gy; sp++; }
+        const uint32_t slot = (bit - 24u) ^ octinv;
+        const uint32_t below = (slot == 0) ? 0u : (hits_imask & ((1u << slot) - 1u));
+        const uint8_t* nd = nodes + (size_t) (Gx + (uint32_t) __builtin_popcount(below)) * 80;
+        visits++;
+        {  // the early-out candidate
+          const uint32_t e = ld32(nd + 12);
+          const float sc[3] = { uintBitsToFloat((e & 0xFFu) << 23), uintBitsToFloat(((e >> 8) & 0xFFu) << 23), uintBitsToFloat(((e >> 16) & 0xFFu) << 23) };
+          const float org[3] = { ldf(nd + 0), ldf(nd + 4), ldf(nd + 8) }, oo[3] = { o.x, o.y, o.z }, id[3] = { idir.x, idir.y, idir.z };
+          float tn = tmin, tf = bt;
+          for (int a = 0; a < 3; a++) {
+            const float lo = (org[a] - oo[a]) * id[a], hi = (org[a] + 255.0f * sc[a] - oo[a]) * id[a];
+            tn = fmaxf(tn, fminf(lo, hi)); tf = fminf(tf, fmaxf(lo, hi));
+          }
+          if (tn > tf * 1.0000004f) gridCulled++;
+        }
+        const uint32_t hm = bvh8_node_hitmask(nd, o, d, idir, tmin, bt, octinv);
+        if (hm == 0) emptyHit++;
+        Gx = ld32(nd + 16); Gy = (hm & 0xFF000000u) | (ld32(nd + 12) >> 24);
+        Tx = ld32(nd + 20); Ty = hm & 0x00FFFFFFu;
+      }
+      while (Ty) {
+        const uint32_t j = (uint32_t) __builtin_ctz(Ty);
+        Ty &= Ty - 1u;
+        const float* tp = tris + (size_t) (Tx + j) * 12;
+        float t, u, v;
+        if (tri_intersect(rp, o, v3(tp[0], tp[1], tp[2]), v3(tp[4], tp[5], tp[6]), v3(tp[8], tp[9], tp[10]), t, u, v) && t > tmin && t < bt) bt = t;
+      }
+      if (!(Gy & 0xFF000000u)) {
+        if (sp == 0) break;
+        sp--; Gx = stackX[sp]; Gy = stackY[sp];
+      }
+    }
+  }
+  outCounts[0] = visits; outCounts[1] = gridCulled; outCounts[2] = emptyHit;
+}
