@@ -347,13 +347,15 @@ extern "C" void orc_bvh8_trace_groupcull(const void* nodesV, const void* trisV, 
 
 // Analysis helper: of the nodes the production walk fetches, how many could be rejected by a slab test against the node's
 // own quantisation grid [p, p + 255 * 2^e] (available from the first 16 bytes of the node) before any child is looked at?
-// outCounts = {node visits, of which the grid box is missed or starts beyond the current best hit, of which no child is hit}.
+// outCounts = {node visits, of which the grid box is missed or starts beyond the current best hit, of which no child is hit,
+// of which even the union of the children's boxes is missed or beyond the best hit, of which that union is missed
+// whatever the best hit (quantisation slack of the parent's box for this node)}.
 extern "C" void orc_bvh8_grid_earlyout(const void* nodesV, const void* trisV, const float* rays, uint32_t n, uint64_t* outCounts)
 {
   using namespace orc;
   const uint8_t* nodes = (const uint8_t*) nodesV; const float* tris = (const float*) trisV;
-  uint64_t visits = 0, gridCulled = 0, emptyHit = 0;
-#pragma omp parallel for schedule(dynamic, 256) reduction(+ : visits, gridCulled, emptyHit)
+  uint64_t visits = 0, gridCulled = 0, emptyHit = 0, unionMissed = 0, unionMissedGeom = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : visits, gridCulled, emptyHit, unionMissed, unionMissedGeom)
   for (int64_t r = 0; r < (int64_t) n; r++) {
     const float* ry = rays + r * 8;
     const V3 o = v3(ry[0], ry[1], ry[2]), d = v3(ry[4], ry[5], ry[6]);
@@ -391,6 +393,20 @@ extern "C" void orc_bvh8_grid_earlyout(const void* nodesV, const void* trisV, co
         }
         const uint32_t hm = bvh8_node_hitmask(nd, o, d, idir, tmin, bt, octinv);
         if (hm == 0) emptyHit++;
+        {  // does the ray at least cross the union of the children's boxes (the node's real extent)?
+          const uint32_t e = ld32(nd + 12);
+          const float sc[3] = { uintBitsToFloat((e & 0xFFu) << 23), uintBitsToFloat(((e >> 8) & 0xFFu) << 23), uintBitsToFloat(((e >> 16) & 0xFFu) << 23) };
+          const float org[3] = { ldf(nd + 0), ldf(nd + 4), ldf(nd + 8) }, oo[3] = { o.x, o.y, o.z }, id[3] = { idir.x, idir.y, idir.z };
+          float tn = tmin, tf = bt, tf0 = 3e38f;
+          for (int a = 0; a < 3; a++) {
+            uint32_t qlo = 255, qhi = 0;
+            for (int i = 0; i < 8; i++) if (nd[24 + i]) { qlo = std::min<uint32_t>(qlo, nd[32 + 8 * a + i]); qhi = std::max<uint32_t>(qhi, nd[56 + 8 * a + i]); }
+            const float lo = (org[a] + (float) qlo * sc[a] - oo[a]) * id[a], hi = (org[a] + (float) qhi * sc[a] - oo[a]) * id[a];
+            tn = fmaxf(tn, fminf(lo, hi)); tf = fminf(tf, fmaxf(lo, hi)); tf0 = fminf(tf0, fmaxf(lo, hi));
+          }
+          if (tn > tf * 1.0000004f) unionMissed++;
+          if (tn > fminf(tf0, 3e38f) * 1.0000004f) unionMissedGeom++;
+        }
         Gx = ld32(nd + 16); Gy = (hm & 0xFF000000u) | (ld32(nd + 12) >> 24);
         Tx = ld32(nd + 20); Ty = hm & 0x00FFFFFFu;
       }
@@ -407,5 +423,5 @@ extern "C" void orc_bvh8_grid_earlyout(const void* nodesV, const void* trisV, co
       }
     }
   }
-  outCounts[0] = visits; outCounts[1] = gridCulled; outCounts[2] = emptyHit;
+  outCounts[0] = visits; outCounts[1] = gridCulled; outCounts[2] = emptyHit; outCounts[3] = unionMissed; outCounts[4] = unionMissedGeom;
 }

@@ -125,3 +125,12 @@ def test_analysis_walkers_bound_the_production_walk():
     assert counts["queue"] <= counts["sorted"] <= production
     assert counts["queue"] <= counts["group"] <= counts["group1"] <= counts["all"] <= production
     assert counts["group"] < production                  # culling at pop saves node fetches whenever rays hit something
+    # where the wasted node fetches come from: grid-box miss <= union-of-children miss <= no child hit, and the purely
+    # geometric part (the parent's quantised box is looser than the node's own extent) is small
+    L.orc_bvh8_grid_earlyout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    out = (C.c_uint64 * 5)()
+    L.orc_bvh8_grid_earlyout(nodes.ctypes.data, tris.ctypes.data, rays.ctypes.data, len(rays), out)
+    visited, grid, empty, union, union_geom = (int(x) for x in out)
+    assert visited == production
+    assert grid <= union <= empty < visited
+    assert union_geom <= union and union_geom < 0.05 * visited
