@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <emmintrin.h>
 
 namespace gtlc {
 namespace {
@@ -32,6 +33,7 @@ struct Box {
 struct BinNode { Box box; uint32_t left, right, first, count, total; };   // count > 0: binary leaf; total = triangles in the subtree
 
 constexpr int kBins = 16;
+constexpr uint32_t kSmallNode = 4;           // nodes up to this size pick their split without bin arrays
 constexpr uint32_t kParallelRange = 262144;   // ranges at least this long are scanned by several tasks
 // SAH parameters (overridable through GTLC_BVH_MAX_LEAF / GTLC_BVH_NODE_COST for tuning experiments)
 uint32_t kMaxLeaf = 3;
@@ -39,138 +41,306 @@ float kNodeCost = 0.6f;  // relative to one triangle test
 float kBigTriFraction = 0.4f;   // GTLC_BVH_BIG_TRIS: a triangle is "big" when its extent sum exceeds this fraction of the node's (0 = off)
 constexpr float kTriCost = 1.0f;
 
+// One record per triangle, moved (not indexed) by the partition passes so that every pass of the builder streams
+// through memory: bounds in the first three lanes of two SSE registers, the triangle's index in the fourth lane of `lo`.
+struct alignas(16) Prim { float lo[3]; uint32_t id; float hi[3]; uint32_t pad; };
+
+// lower corner with the index lane cleared (an integer reinterpreted as float is a denormal: slow in arithmetic)
+inline __m128 loadLo(const Prim& p) { return _mm_and_ps(_mm_load_ps(p.lo), _mm_castsi128_ps(_mm_setr_epi32(-1, -1, -1, 0))); }
+
+// Box::area() on registers: the same products and the same order of additions
+inline float area4(__m128 lo, __m128 hi)
+{
+  const __m128 d = _mm_sub_ps(hi, lo);
+  if (_mm_cvtss_f32(d) < 0.0f) return 0.0f;
+  const __m128 p = _mm_mul_ps(d, _mm_shuffle_ps(d, d, _MM_SHUFFLE(3, 0, 2, 1)));   // (dx dy, dy dz, dz dx, .)
+  const float p0 = _mm_cvtss_f32(p), p1 = _mm_cvtss_f32(_mm_shuffle_ps(p, p, 1)), p2 = _mm_cvtss_f32(_mm_shuffle_ps(p, p, 2));
+  return 2.0f * ((p0 + p1) + p2);
+}
+
+struct Bounds4 {           // box of the triangles and box of their centroids, as SSE registers (lane 3 unused)
+  __m128 blo, bhi, clo, chi;
+  void reset()
+  {
+    blo = clo = _mm_set1_ps(3.402823466e38f);
+    bhi = chi = _mm_set1_ps(-3.402823466e38f);
+  }
+  void grow(const Prim& p)
+  {
+    const __m128 lo = loadLo(p), hi = _mm_load_ps(p.hi);
+    const __m128 c = _mm_mul_ps(_mm_set1_ps(0.5f), _mm_add_ps(lo, hi));
+    blo = _mm_min_ps(blo, lo); bhi = _mm_max_ps(bhi, hi);
+    clo = _mm_min_ps(clo, c);  chi = _mm_max_ps(chi, c);
+  }
+  void grow(const Bounds4& o)
+  {
+    blo = _mm_min_ps(blo, o.blo); bhi = _mm_max_ps(bhi, o.bhi);
+    clo = _mm_min_ps(clo, o.clo); chi = _mm_max_ps(chi, o.chi);
+  }
+  static Box toBox(__m128 lo, __m128 hi)
+  {
+    alignas(16) float a[4], b[4];
+    _mm_store_ps(a, lo); _mm_store_ps(b, hi);
+    Box r;
+    for (int k = 0; k < 3; k++) { r.lo[k] = a[k]; r.hi[k] = b[k]; }
+    return r;
+  }
+  Box box() const { return toBox(blo, bhi); }
+  Box centroidBox() const { return toBox(clo, chi); }
+};
+
 struct Builder {
-  const std::vector<BuildTri>& tris;
-  std::vector<Box> triBox;
-  std::vector<float> cen;  // 3 per tri
-  std::vector<uint32_t> idx;
+  std::vector<Prim> prims;
   std::vector<BinNode> nodes;
-  std::atomic<uint32_t> nodeCount{ 0 };
 
-  explicit Builder(const std::vector<BuildTri>& t) : tris(t) {}
+  // The top of the tree is a handful of huge ranges: their passes are cut into chunks that run as tasks of the team
+  // (min / max / counts merge exactly, so the tree does not depend on the chunking).
+  static uint32_t chunksOf(uint32_t count) { return count >= kParallelRange ? 64u : 1u; }
 
-  void build(uint32_t node, uint32_t begin, uint32_t end)
+  Bounds4 boundsOf(uint32_t begin, uint32_t end)
+  {
+    const uint32_t count = end - begin, chunks = chunksOf(count), chunkLen = (count + chunks - 1) / chunks;
+    Bounds4 r; r.reset();
+    if (chunks == 1) {
+      for (uint32_t i = begin; i < end; i++) r.grow(prims[i]);
+      return r;
+    }
+    std::vector<Bounds4> part(chunks);
+#pragma omp taskloop default(shared) grainsize(1)
+    for (uint32_t c = 0; c < chunks; c++) {
+      Bounds4 a; a.reset();
+      const uint32_t e0 = begin + c * chunkLen, e1 = std::min(end, e0 + chunkLen);
+      for (uint32_t i = e0; i < e1; i++) a.grow(prims[i]);
+      part[c] = a;
+    }
+    for (uint32_t c = 0; c < chunks; c++) r.grow(part[c]);
+    return r;
+  }
+
+  struct Bins {
+    __m128 lo[3][kBins], hi[3][kBins];
+    uint32_t count[3][kBins];
+    uint32_t big;
+    void reset()
+    {
+      for (int a = 0; a < 3; a++) for (int b = 0; b < kBins; b++) { lo[a][b] = _mm_set1_ps(3.402823466e38f); hi[a][b] = _mm_set1_ps(-3.402823466e38f); count[a][b] = 0; }
+      big = 0;
+    }
+    void merge(const Bins& o)
+    {
+      for (int a = 0; a < 3; a++) for (int b = 0; b < kBins; b++) {
+        lo[a][b] = _mm_min_ps(lo[a][b], o.lo[a][b]); hi[a][b] = _mm_max_ps(hi[a][b], o.hi[a][b]); count[a][b] += o.count[a][b];
+      }
+      big += o.big;
+    }
+  };
+
+  // one pass over [e0, e1): all three axes binned at once, big triangles counted on the way
+  void binRange(uint32_t e0, uint32_t e1, __m128 cLo, __m128 scale, float bigLimit, Bins& bins) const
+  {
+    for (uint32_t i = e0; i < e1; i++) {
+      const Prim& p = prims[i];
+      const __m128 lo = loadLo(p), hi = _mm_load_ps(p.hi);
+      const __m128 c = _mm_mul_ps(_mm_set1_ps(0.5f), _mm_add_ps(lo, hi));
+      alignas(16) int b[4]; alignas(16) float d[4];
+      _mm_store_si128((__m128i*) b, _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, cLo), scale)));
+      _mm_store_ps(d, _mm_sub_ps(hi, lo));
+      for (int a = 0; a < 3; a++) {
+        const int k = b[a] < 0 ? 0 : (b[a] >= kBins ? kBins - 1 : b[a]);
+        bins.lo[a][k] = _mm_min_ps(bins.lo[a][k], lo); bins.hi[a][k] = _mm_max_ps(bins.hi[a][k], hi); bins.count[a][k]++;
+      }
+      bins.big += ((d[0] + d[1]) + d[2]) > bigLimit ? 1u : 0u;
+    }
+  }
+
+  // Node ids are the pre-order of the binary tree: every leaf holds one triangle, so the subtree over `c` triangles has
+  // exactly 2c - 1 nodes and the right child of `node` sits 2 (mid - begin) after it.  No shared counter, and a subtree is
+  // one contiguous block for the collapse and emission passes that walk it afterwards.
+  void split(uint32_t node, uint32_t begin, uint32_t mid, uint32_t end, const Bounds4& lb, const Bounds4& rb, bool leftInline)
+  {
+    BinNode& n = nodes[node];
+    const uint32_t l = node + 1, r = node + 2 * (mid - begin);
+    n.left = l; n.right = r; n.count = 0; n.first = begin; n.total = end - begin;
+    if (end - begin > 16384) {
+      if (leftInline) build(l, begin, mid, lb);
+      else {
+#pragma omp task default(shared) firstprivate(l, begin, mid, lb)
+        build(l, begin, mid, lb);
+      }
+#pragma omp task default(shared) firstprivate(r, mid, end, rb)
+      build(r, mid, end, rb);
+#pragma omp taskwait
+    } else {
+      build(l, begin, mid, lb);
+      build(r, mid, end, rb);
+    }
+  }
+
+  // `bounds` = box of the triangles in [begin, end) and of their centroids, handed down by whoever partitioned them
+  void build(uint32_t node, uint32_t begin, uint32_t end, const Bounds4& bounds)
   {
     const uint32_t count = end - begin;
-    // The top of the tree is a handful of huge ranges: their passes are cut into chunks that run as tasks of the team
-    // (min / max / counts merge exactly, so the tree does not depend on the chunking).
-    const uint32_t chunks = count >= kParallelRange ? 64u : 1u;
-    const uint32_t chunkLen = (count + chunks - 1) / chunks;
-    Box box, cbox;
-    box.reset(); cbox.reset();
-    if (chunks == 1) {
-      for (uint32_t i = begin; i < end; i++) {
-        box.grow(triBox[idx[i]]);
-        cbox.grow(&cen[(size_t) idx[i] * 3]);
-      }
-    } else {
-      std::vector<Box> pb(chunks), pc(chunks);
-#pragma omp taskloop default(shared) grainsize(1)
-      for (uint32_t c = 0; c < chunks; c++) {
-        Box a, d; a.reset(); d.reset();
-        const uint32_t e0 = begin + c * chunkLen, e1 = std::min(end, e0 + chunkLen);
-        for (uint32_t i = e0; i < e1; i++) { a.grow(triBox[idx[i]]); d.grow(&cen[(size_t) idx[i] * 3]); }
-        pb[c] = a; pc[c] = d;
-      }
-      for (uint32_t c = 0; c < chunks; c++) { if (pb[c].lo[0] <= pb[c].hi[0]) box.grow(pb[c]); if (pc[c].lo[0] <= pc[c].hi[0]) cbox.grow(pc[c]); }
-    }
+    const uint32_t chunks = chunksOf(count), chunkLen = (count + chunks - 1) / chunks;
+    const Box box = bounds.box(), cbox = bounds.centroidBox();
     BinNode& n = nodes[node];
     n.box = box;
     auto makeLeaf = [&]() { n.first = begin; n.count = count; n.total = count; n.left = n.right = 0; };
     if (count == 1) { makeLeaf(); return; }
 
-    // Triangles that span most of this node (room walls around furniture, a table top over what stands on it) go into a
-    // subtree of their own: sorted by centroid they would sit deep inside one child and inflate every box on the way.
-    // Measured in BVH8 node visits per ray (oracle walker): kitchen stand-in 6.59 -> 5.03, nothing lost elsewhere.
-    if (count >= 64 && kBigTriFraction > 0.0f) {
+    float scaleA[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    bool axisOk[3];
+    for (int axis = 0; axis < 3; axis++) {
+      const float ext = cbox.hi[axis] - cbox.lo[axis];
+      axisOk[axis] = ext > 0.0f;
+      if (axisOk[axis]) scaleA[axis] = (float) kBins / ext;
+    }
+    const __m128 cLo = _mm_setr_ps(cbox.lo[0], cbox.lo[1], cbox.lo[2], 0.0f), scale = _mm_loadu_ps(scaleA);
+    float bestCost = 3.402823466e38f; int bestAxis = -1; int bestBin = -1;
+
+    if (count <= kSmallNode) {
+      // ---- the bottom of the tree (most nodes hold a handful of triangles): no bin arrays.  A split after an empty bin
+      // separates the same two sets as the split after the occupied bin below it and loses the strict comparison, so only
+      // the occupied bins are candidates; their two boxes are gathered directly (min / max are exact in any order). ----
+      uint8_t binOf[3][kSmallNode];
+      uint32_t occupied[3] = { 0u, 0u, 0u };
+      for (uint32_t i = 0; i < count; i++) {
+        const Prim& p = prims[begin + i];
+        const __m128 c = _mm_mul_ps(_mm_set1_ps(0.5f), _mm_add_ps(loadLo(p), _mm_load_ps(p.hi)));
+        alignas(16) int b[4];
+        _mm_store_si128((__m128i*) b, _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(c, cLo), scale)));
+        for (int a = 0; a < 3; a++) {
+          const int k = b[a] < 0 ? 0 : (b[a] >= kBins ? kBins - 1 : b[a]);
+          binOf[a][i] = (uint8_t) k; occupied[a] |= 1u << k;
+        }
+      }
+      for (int axis = 0; axis < 3; axis++) {
+        if (!axisOk[axis]) continue;
+        uint32_t m = occupied[axis];
+        while (m & (m - 1)) {                         // every occupied bin but the highest
+          const int b = __builtin_ctz(m); m &= m - 1;
+          __m128 llo = _mm_set1_ps(3.402823466e38f), lhi = _mm_set1_ps(-3.402823466e38f), rlo = llo, rhi = lhi;
+          uint32_t cl = 0;
+          for (uint32_t i = 0; i < count; i++) {
+            const Prim& p = prims[begin + i];
+            const __m128 lo = loadLo(p), hi = _mm_load_ps(p.hi);
+            if (binOf[axis][i] <= b) { llo = _mm_min_ps(llo, lo); lhi = _mm_max_ps(lhi, hi); cl++; }
+            else { rlo = _mm_min_ps(rlo, lo); rhi = _mm_max_ps(rhi, hi); }
+          }
+          const float cost = area4(llo, lhi) * (float) cl + area4(rlo, rhi) * (float) (count - cl);
+          if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+        }
+      }
+    } else {
+      // ---- binning pass (three axes at once) ----
       const float sd = (box.hi[0] - box.lo[0]) + (box.hi[1] - box.lo[1]) + (box.hi[2] - box.lo[2]);
-      auto isBig = [&](uint32_t t) { const Box& x = triBox[t]; return ((x.hi[0] - x.lo[0]) + (x.hi[1] - x.lo[1]) + (x.hi[2] - x.lo[2])) > kBigTriFraction * sd; };
-      uint32_t big = 0;
-      for (uint32_t i = begin; i < end && big <= count / 16; i++) big += isBig(idx[i]) ? 1u : 0u;
-      if (big > 0 && big <= count / 16) {
-        const uint32_t mid = (uint32_t) (std::stable_partition(idx.begin() + begin, idx.begin() + end, isBig) - idx.begin());
-        const uint32_t l = nodeCount.fetch_add(2);
-        n.left = l; n.right = l + 1; n.count = 0; n.first = begin; n.total = count;
-        build(l, begin, mid);
-        if (count > 16384) {
-#pragma omp task default(shared)
-          build(l + 1, mid, end);
-#pragma omp taskwait
-        } else build(l + 1, mid, end);
+      const bool wantBig = count >= 64 && kBigTriFraction > 0.0f;
+      const float bigLimit = wantBig ? kBigTriFraction * sd : 3.402823466e38f;
+      Bins bins; bins.reset();
+      if (chunks == 1) binRange(begin, end, cLo, scale, bigLimit, bins);
+      else {
+        std::vector<Bins> part(chunks);
+#pragma omp taskloop default(shared) grainsize(1)
+        for (uint32_t c = 0; c < chunks; c++) {
+          part[c].reset();
+          const uint32_t e0 = begin + c * chunkLen, e1 = std::min(end, e0 + chunkLen);
+          binRange(e0, e1, cLo, scale, bigLimit, part[c]);
+        }
+        for (uint32_t c = 0; c < chunks; c++) bins.merge(part[c]);
+      }
+
+      // Triangles that span most of this node (room walls around furniture, a table top over what stands on it) go into a
+      // subtree of their own: sorted by centroid they would sit deep inside one child and inflate every box on the way.
+      // Measured in BVH8 node visits per ray (oracle walker): kitchen stand-in 6.59 -> 5.03, nothing lost elsewhere.
+      if (wantBig && bins.big > 0 && bins.big <= count / 16) {
+        auto isBig = [&](const Prim& x) { return ((x.hi[0] - x.lo[0]) + (x.hi[1] - x.lo[1]) + (x.hi[2] - x.lo[2])) > bigLimit; };
+        const uint32_t mid = (uint32_t) (std::stable_partition(prims.begin() + begin, prims.begin() + end, isBig) - prims.begin());
+        const Bounds4 lb = boundsOf(begin, mid), rb = boundsOf(mid, end);
+        split(node, begin, mid, end, lb, rb, true);      // the few big triangles are built on the spot
         return;
+      }
+
+      // ---- SAH sweep over the OCCUPIED bins of each axis (a split after an empty bin repeats the previous candidate) ----
+      for (int axis = 0; axis < 3; axis++) {
+        if (!axisOk[axis]) continue;
+        const uint32_t* bc = bins.count[axis];
+        uint32_t occupied = 0;
+        for (int b = 0; b < kBins; b++) occupied |= (bc[b] != 0u ? 1u : 0u) << b;
+        float rightArea[kBins]; uint32_t rightCount[kBins];
+        __m128 alo = _mm_set1_ps(3.402823466e38f), ahi = _mm_set1_ps(-3.402823466e38f); uint32_t c = 0;
+        for (uint32_t m = occupied; m;) {             // descending: rightArea[b] = area of everything in bins >= b
+          const int b = 31 - __builtin_clz(m); m ^= 1u << b;
+          alo = _mm_min_ps(alo, bins.lo[axis][b]); ahi = _mm_max_ps(ahi, bins.hi[axis][b]); c += bc[b];
+          rightArea[b] = area4(alo, ahi); rightCount[b] = c;
+        }
+        alo = _mm_set1_ps(3.402823466e38f); ahi = _mm_set1_ps(-3.402823466e38f); c = 0;
+        for (uint32_t m = occupied; m & (m - 1);) {   // ascending, every occupied bin but the highest
+          const int b = __builtin_ctz(m); m &= m - 1;
+          const int nb = __builtin_ctz(m);
+          alo = _mm_min_ps(alo, bins.lo[axis][b]); ahi = _mm_max_ps(ahi, bins.hi[axis][b]); c += bc[b];
+          const float cost = area4(alo, ahi) * (float) c + rightArea[nb] * (float) rightCount[nb];
+          if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+        }
       }
     }
 
-    // binned SAH over the three axes
-    float bestCost = 3.402823466e38f; int bestAxis = -1; int bestBin = -1;
-    for (int axis = 0; axis < 3; axis++) {
-      float lo = cbox.lo[axis], ext = cbox.hi[axis] - cbox.lo[axis];
-      if (!(ext > 0.0f)) continue;
-      float scale = (float) kBins / ext;
-      Box bb[kBins]; uint32_t bc[kBins];
-      for (int b = 0; b < kBins; b++) { bb[b].reset(); bc[b] = 0; }
-      if (chunks == 1) {
-        for (uint32_t i = begin; i < end; i++) {
-          int b = (int) ((cen[(size_t) idx[i] * 3 + axis] - lo) * scale);
-          b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-          bb[b].grow(triBox[idx[i]]); bc[b]++;
-        }
-      } else {
-        struct Partial { Box bb[kBins]; uint32_t bc[kBins]; };
-        std::vector<Partial> part(chunks);
-#pragma omp taskloop default(shared) grainsize(1)
-        for (uint32_t c = 0; c < chunks; c++) {
-          Partial& pt = part[c];
-          for (int b = 0; b < kBins; b++) { pt.bb[b].reset(); pt.bc[b] = 0; }
-          const uint32_t e0 = begin + c * chunkLen, e1 = std::min(end, e0 + chunkLen);
-          for (uint32_t i = e0; i < e1; i++) {
-            int b = (int) ((cen[(size_t) idx[i] * 3 + axis] - lo) * scale);
-            b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
-            pt.bb[b].grow(triBox[idx[i]]); pt.bc[b]++;
-          }
-        }
-        for (uint32_t c = 0; c < chunks; c++) for (int b = 0; b < kBins; b++) if (part[c].bc[b]) { bb[b].grow(part[c].bb[b]); bc[b] += part[c].bc[b]; }
-      }
-      float rightArea[kBins]; uint32_t rightCount[kBins];
-      Box acc; acc.reset(); uint32_t c = 0;
-      for (int b = kBins - 1; b > 0; b--) { acc.grow(bb[b]); c += bc[b]; rightArea[b] = acc.area(); rightCount[b] = c; }
-      acc.reset(); c = 0;
-      for (int b = 0; b < kBins - 1; b++) {
-        acc.grow(bb[b]); c += bc[b];
-        if (c == 0 || rightCount[b + 1] == 0) continue;
-        float cost = acc.area() * (float) c + rightArea[b + 1] * (float) rightCount[b + 1];
-        if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
-      }
-    }
+    // ---- partition; the children's bounds are gathered while the records move ----
     uint32_t mid;
+    Bounds4 lb, rb;
+    bool haveBounds = false;
     if (bestAxis < 0) {
       mid = begin + count / 2;  // identical centroids: split by index
     } else {
-      float lo = cbox.lo[bestAxis], scale = (float) kBins / (cbox.hi[bestAxis] - cbox.lo[bestAxis]);
-      auto it = std::partition(idx.begin() + begin, idx.begin() + end, [&](uint32_t t) {
-        int b = (int) ((cen[(size_t) t * 3 + bestAxis] - lo) * scale);
+      const float lo = cbox.lo[bestAxis], sc = scaleA[bestAxis];
+      lb.reset(); rb.reset();
+      auto goesLeft = [&](const Prim& p) {
+        int b = (int) ((0.5f * (p.lo[bestAxis] + p.hi[bestAxis]) - lo) * sc);
         b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
         return b <= bestBin;
-      });
-      mid = (uint32_t) (it - idx.begin());
-      if (mid == begin || mid == end) mid = begin + count / 2;
+      };
+      // the two-pointer scheme of std::partition, with every record looked at exactly once
+      Prim* first = prims.data() + begin; Prim* last = prims.data() + end;
+      for (;;) {
+        for (;;) {
+          if (first == last) goto done;
+          if (goesLeft(*first)) { lb.grow(*first); ++first; } else break;
+        }
+        rb.grow(*first);
+        --last;
+        for (;;) {
+          if (first == last) goto done;
+          if (!goesLeft(*last)) { rb.grow(*last); --last; } else break;
+        }
+        lb.grow(*last);
+        std::swap(*first, *last);
+        ++first;
+      }
+done:
+      mid = (uint32_t) (first - prims.data());
+      haveBounds = true;
+      if (mid == begin || mid == end) { mid = begin + count / 2; haveBounds = false; }
     }
-    uint32_t l = nodeCount.fetch_add(2);
-    n.left = l; n.right = l + 1; n.count = 0; n.first = begin; n.total = count;
-    if (count > 16384) {
-#pragma omp task default(shared)
-      build(l, begin, mid);
-#pragma omp task default(shared)
-      build(l + 1, mid, end);
-#pragma omp taskwait
-    } else {
-      build(l, begin, mid);
-      build(l + 1, mid, end);
-    }
+    if (!haveBounds) { lb = boundsOf(begin, mid); rb = boundsOf(mid, end); }
+    split(node, begin, mid, end, lb, rb, false);
   }
 };
 
 struct WideChild { uint32_t bin; bool leaf; };
+
+// floor / ceil without the library call for the values that occur here (a few hundred at most)
+inline double floorSmall(double x)
+{
+  if (!(x > -1e9 && x < 1e9)) return std::floor(x);
+  double f = (double) (int) x;
+  if (f > x) f -= 1.0;
+  return f;
+}
+inline double ceilSmall(double x)
+{
+  if (!(x > -1e9 && x < 1e9)) return std::ceil(x);
+  double f = (double) (int) x;
+  if (f < x) f += 1.0;
+  return f;
+}
 
 inline uint32_t floatExponentBits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return (u >> 23) & 0xFFu; }
 
@@ -190,21 +360,23 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
   if (const char* e = getenv("GTLC_BVH_MAX_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 3) kMaxLeaf = (uint32_t) v; }
   if (const char* e = getenv("GTLC_BVH_NODE_COST")) { float v = (float) atof(e); if (v > 0.0f) kNodeCost = v; }
   if (const char* e = getenv("GTLC_BVH_BIG_TRIS")) kBigTriFraction = (float) atof(e);
-  Builder b(tris);
-  b.triBox.resize(N); b.cen.resize((size_t) N * 3); b.idx.resize(N);
+  Builder b;
+  b.prims.resize(N);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t) N; i++) {
     Box bx; bx.reset();
     for (int k = 0; k < 3; k++) bx.grow(tris[i].v[k]);
-    b.triBox[i] = bx;
-    for (int k = 0; k < 3; k++) b.cen[(size_t) i * 3 + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
-    b.idx[i] = (uint32_t) i;
+    Prim& p = b.prims[(size_t) i];
+    for (int k = 0; k < 3; k++) { p.lo[k] = bx.lo[k]; p.hi[k] = bx.hi[k]; }
+    p.id = (uint32_t) i; p.pad = 0;
   }
-  b.nodes.resize((size_t) 2 * N);
-  b.nodeCount = 1;
+  b.nodes.resize((size_t) 2 * N - 1);
 #pragma omp parallel
 #pragma omp single
-  b.build(0, 0, N);
+  {
+    const Bounds4 all = b.boundsOf(0, N);
+    b.build(0, 0, N, all);
+  }
 
   const auto tBinary = std::chrono::steady_clock::now();
   // ---- SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1), dynamic programme bottom-up over the
@@ -212,7 +384,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
   // (i = 1..7), each child either a leaf of <= kMaxLeaf triangles or a wide node.  Bottom-up = post-order; the two
   // subtrees of a big node are independent OpenMP tasks.
   const std::vector<BinNode>& bn = b.nodes;
-  const uint32_t binCount = b.nodeCount.load();
+  const uint32_t binCount = 2 * N - 1;
   struct Dp { float cost[7]; uint8_t split[7]; uint8_t rootSplit; uint8_t rootIsLeaf; };
   std::vector<Dp> dp(binCount);
   const float INF = 3.402823466e38f;
@@ -276,8 +448,10 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
   // The layout is the breadth-first order a serial queue would produce.
   struct Pending { uint32_t bin, wide, depth; };
   std::vector<Pending> level, next;
+  out.nodes.reserve((size_t) N + 1);                  // a wide node has at least two children (virtual memory until used)
   out.nodes.assign(1, Bvh8Node());
   out.tris.clear();
+  out.tris.reserve((size_t) N * 12);
   level.push_back({ 0u, 0u, 1u });
   uint32_t nodeBase = 1, triBaseLevel = 0;
   while (!level.empty()) {
@@ -321,16 +495,21 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
       for (int s = 0; s < 8; s++)
         cost[i][s] = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
     }
+    // n rounds of "take the largest entry of the matrix whose row and column are still free" (ties: first in row-major
+    // order).  Every row remembers its best free column; a round only rescans the rows that just lost theirs.
+    float rowBest[8]; int rowSlot[8];
+    auto rescan = [&](int i) {
+      float bc = -3.402823466e38f; int bs = -1;
+      for (int s = 0; s < 8; s++) if (!slotUsed[s] && cost[i][s] > bc) { bc = cost[i][s]; bs = s; }
+      rowBest[i] = bc; rowSlot[i] = bs;
+    };
+    for (int i = 0; i < n; i++) rescan(i);
     for (int k = 0; k < n; k++) {
-      int bi = -1, bs = -1; float bc = -3.402823466e38f;
-      for (int i = 0; i < n; i++) {
-        if (childDone[i]) continue;
-        for (int s = 0; s < 8; s++) {
-          if (slotUsed[s]) continue;
-          if (cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
-        }
-      }
+      int bi = -1; float bc = -3.402823466e38f;
+      for (int i = 0; i < n; i++) if (!childDone[i] && rowBest[i] > bc) { bc = rowBest[i]; bi = i; }
+      const int bs = rowSlot[bi];
       slotOf[bi] = bs; childDone[bi] = true; slotUsed[bs] = true;
+      for (int i = 0; i < n; i++) if (!childDone[i] && rowSlot[i] == bs) rescan(i);
     }
     int childAtSlot[8]; for (int s = 0; s < 8; s++) childAtSlot[s] = -1;
     for (int i = 0; i < n; i++) childAtSlot[slotOf[i]] = i;
@@ -338,15 +517,16 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     // ---- quantisation grid: origin one quantum below the node's lower corner and 251 quanta of extent,
     // so that every child bound can be padded by a safety quantum on BOTH sides (the slab test's
     // 2^15-bias arithmetic is accurate to ~1/512 quantum; see traverse.cuh) ----------------------
-    uint32_t ebits[3]; double scale[3]; float porigin[3];
+    uint32_t ebits[3]; double scale[3], invScale[3]; float porigin[3];
     for (int k = 0; k < 3; k++) {
-      double ext = (double) pb.hi[k] - (double) pb.lo[k];
-      int e = (ext > 0.0) ? (int) std::ceil(std::log2(ext / 250.0)) : -100;
+      // smallest e with ext <= 250 * 2^e, kept inside [-100, 100]: ext = m * 2^x with m in [0.5, 1), 250 = 0.9765625 * 2^8
+      const double ext = (double) pb.hi[k] - (double) pb.lo[k];
+      int e = -100;
+      if (ext > 0.0) { int x; const double m = std::frexp(ext, &x); e = (m <= 0.9765625) ? x - 8 : x - 7; }
       if (e < -100) e = -100;
       if (e > 100) e = 100;
-      while (ext / std::ldexp(1.0, e) > 250.0 && e < 100) e++;
       ebits[k] = (uint32_t) (e + 127);
-      scale[k] = std::ldexp(1.0, e);
+      scale[k] = std::ldexp(1.0, e); invScale[k] = std::ldexp(1.0, -e);
       float po = (float) ((double) pb.lo[k] - scale[k]);
       while ((double) po > (double) pb.lo[k] - 0.75 * scale[k]) po = std::nextafterf(po, -3.402823466e38f);
       porigin[k] = po;
@@ -363,9 +543,9 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
       if (i < 0) continue;
       const BinNode& c = bn[ch[i].bin];
       for (int k = 0; k < 3; k++) {
-        double lo = ((double) c.box.lo[k] - (double) porigin[k]) / scale[k];
-        double hi = ((double) c.box.hi[k] - (double) porigin[k]) / scale[k];
-        double ql = std::floor(lo), qh = std::ceil(hi);
+        double lo = ((double) c.box.lo[k] - (double) porigin[k]) * invScale[k];   // power of two: exact
+        double hi = ((double) c.box.hi[k] - (double) porigin[k]) * invScale[k];
+        double ql = floorSmall(lo), qh = ceilSmall(hi);
         if (lo - ql < 1.0 / 64.0 && ql > 0.0) ql -= 1.0;   // safety quantum when the bound sits on a grid line
         if (qh - hi < 1.0 / 64.0 && qh < 255.0) qh += 1.0;
         if (ql < 0.0) ql = 0.0;
@@ -376,7 +556,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
         uint32_t cnt = c.total;  // 1..kMaxLeaf triangles: the whole binary subtree becomes one leaf
         meta[s] = (uint8_t) ((((1u << cnt) - 1u) << 5) | triOffset);
         for (uint32_t t = 0; t < cnt; t++) {
-          const BuildTri& tr = tris[b.idx[c.first + t]];
+          const BuildTri& tr = tris[b.prims[c.first + t].id];
           float rec[12];
           for (int v = 0; v < 3; v++) { rec[v * 4 + 0] = tr.v[v][0]; rec[v * 4 + 1] = tr.v[v][1]; rec[v * 4 + 2] = tr.v[v][2]; }
           std::memcpy(&rec[3], &tr.prim, 4); std::memcpy(&rec[7], &tr.inst, 4); rec[11] = tr.opacity;
