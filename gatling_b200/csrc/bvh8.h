@@ -25,16 +25,32 @@
 // Triangle = 48 bytes = 3 x float4: (v0.xyz, bits primitiveId) (v1.xyz, bits instanceIndex) (v2.xyz, cutout opacity; 1 = opaque).
 #pragma once
 #include <stdint.h>
+#include <memory>
+#include <new>
+#include <utility>
 #include <vector>
 
 namespace gtlc {
+
+// std::vector whose resize() leaves new trivially-constructible elements untouched: the arrays below run to hundreds of
+// megabytes, every element is written by whoever sized them, and the pages should be first touched by the threads that
+// fill them rather than zeroed by the one that called resize().
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+  DefaultInitAllocator() = default;
+  template <class U> DefaultInitAllocator(const DefaultInitAllocator<U>&) {}
+  template <class U> void construct(U* p) { ::new ((void*) p) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*) p) U(std::forward<A>(a)...); }
+};
+template <class T> using RawVector = std::vector<T, DefaultInitAllocator<T>>;
 
 struct Bvh8Node { uint32_t w[20]; };
 static_assert(sizeof(Bvh8Node) == 80, "BVH8 node must be 80 bytes");
 
 struct Bvh8 {
-  std::vector<Bvh8Node> nodes;
-  std::vector<float> tris;      // 12 floats per triangle, leaf order
+  RawVector<Bvh8Node> nodes;
+  RawVector<float> tris;        // 12 floats per triangle, leaf order
   uint32_t maxDepth = 0;        // depth of the wide tree (bounds the traversal stack)
   double buildSeconds = 0.0;
 };

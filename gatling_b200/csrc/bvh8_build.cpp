@@ -90,8 +90,8 @@ struct Bounds4 {           // box of the triangles and box of their centroids, a
 };
 
 struct Builder {
-  std::vector<Prim> prims;
-  std::vector<BinNode> nodes;
+  RawVector<Prim> prims;
+  RawVector<BinNode> nodes;
 
   // The top of the tree is a handful of huge ranges: their passes are cut into chunks that run as tasks of the team
   // (min / max / counts merge exactly, so the tree does not depend on the chunking).
@@ -151,6 +151,63 @@ struct Builder {
       }
       bins.big += ((d[0] + d[1]) + d[2]) > bigLimit ? 1u : 0u;
     }
+  }
+
+  // std::partition's result for a huge range, computed by the whole team.  The two-pointer scheme swaps the k-th misplaced
+  // record from the left (predicate false, position before the final boundary) with the k-th misplaced record from the
+  // right (predicate true, position at or after it) and touches nothing else; so: flag everything, count, list the two
+  // kinds of misplaced positions with prefix sums, swap the pairs.  Also returns the bounds of the two sides.
+  template <class Pred>
+  uint32_t partitionChunked(uint32_t begin, uint32_t end, const Pred& goesLeft, Bounds4& lb, Bounds4& rb)
+  {
+    const uint32_t count = end - begin, chunks = chunksOf(count), chunkLen = (count + chunks - 1) / chunks;
+    struct Part { Bounds4 side[2]; uint32_t trues, misplacedLeft, misplacedRight; };
+    std::vector<Part> part(chunks);
+    std::vector<uint8_t> flag(count);
+#pragma omp taskloop default(shared) grainsize(1)
+    for (uint32_t c = 0; c < chunks; c++) {
+      Part& pt = part[c];
+      pt.side[0].reset(); pt.side[1].reset(); pt.trues = 0;
+      const uint32_t e0 = std::min(end, begin + c * chunkLen), e1 = std::min(end, e0 + chunkLen);
+      for (uint32_t i = e0; i < e1; i++) {
+        const bool f = goesLeft(prims[i]);
+        flag[i - begin] = f ? 1 : 0;
+        pt.side[f ? 0 : 1].grow(prims[i]);
+        pt.trues += f ? 1u : 0u;
+      }
+    }
+    uint32_t trues = 0;
+    for (uint32_t c = 0; c < chunks; c++) { trues += part[c].trues; lb.grow(part[c].side[0]); rb.grow(part[c].side[1]); }
+    const uint32_t mid = begin + trues;
+#pragma omp taskloop default(shared) grainsize(1)
+    for (uint32_t c = 0; c < chunks; c++) {
+      const uint32_t e0 = std::min(end, begin + c * chunkLen), e1 = std::min(end, e0 + chunkLen);
+      uint32_t nl = 0, nr = 0;
+      for (uint32_t i = e0; i < std::min(e1, mid); i++) nl += 1u - flag[i - begin];
+      for (uint32_t i = std::max(e0, mid); i < e1; i++) nr += flag[i - begin];
+      part[c].misplacedLeft = nl; part[c].misplacedRight = nr;
+    }
+    uint32_t swaps = 0, swapsRight = 0;
+    for (uint32_t c = 0; c < chunks; c++) {
+      const uint32_t nl = part[c].misplacedLeft, nr = part[c].misplacedRight;
+      part[c].misplacedLeft = swaps; part[c].misplacedRight = swapsRight;
+      swaps += nl; swapsRight += nr;
+    }
+    std::vector<uint32_t> fromLeft(swaps), fromRight(swaps);     // both ascending; swapsRight == swaps
+#pragma omp taskloop default(shared) grainsize(1)
+    for (uint32_t c = 0; c < chunks; c++) {
+      const uint32_t e0 = std::min(end, begin + c * chunkLen), e1 = std::min(end, e0 + chunkLen);
+      uint32_t kl = part[c].misplacedLeft, kr = part[c].misplacedRight;
+      for (uint32_t i = e0; i < std::min(e1, mid); i++) if (!flag[i - begin]) fromLeft[kl++] = i;
+      for (uint32_t i = std::max(e0, mid); i < e1; i++) if (flag[i - begin]) fromRight[kr++] = i;
+    }
+    const uint32_t swapChunk = (swaps + chunks - 1) / chunks;
+#pragma omp taskloop default(shared) grainsize(1)
+    for (uint32_t c = 0; c < chunks; c++) {
+      const uint32_t k0 = std::min(swaps, c * swapChunk), k1 = std::min(swaps, k0 + swapChunk);
+      for (uint32_t k = k0; k < k1; k++) std::swap(prims[fromLeft[k]], prims[fromRight[swaps - 1 - k]]);
+    }
+    return mid;
   }
 
   // Node ids are the pre-order of the binary tree: every leaf holds one triangle, so the subtree over `c` triangles has
@@ -297,25 +354,28 @@ struct Builder {
         b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
         return b <= bestBin;
       };
-      // the two-pointer scheme of std::partition, with every record looked at exactly once
-      Prim* first = prims.data() + begin; Prim* last = prims.data() + end;
-      for (;;) {
+      if (chunks > 1) mid = partitionChunked(begin, end, goesLeft, lb, rb);
+      else {
+        // the two-pointer scheme of std::partition, with every record looked at exactly once
+        Prim* first = prims.data() + begin; Prim* last = prims.data() + end;
         for (;;) {
-          if (first == last) goto done;
-          if (goesLeft(*first)) { lb.grow(*first); ++first; } else break;
+          for (;;) {
+            if (first == last) goto done;
+            if (goesLeft(*first)) { lb.grow(*first); ++first; } else break;
+          }
+          rb.grow(*first);
+          --last;
+          for (;;) {
+            if (first == last) goto done;
+            if (!goesLeft(*last)) { rb.grow(*last); --last; } else break;
+          }
+          lb.grow(*last);
+          std::swap(*first, *last);
+          ++first;
         }
-        rb.grow(*first);
-        --last;
-        for (;;) {
-          if (first == last) goto done;
-          if (!goesLeft(*last)) { rb.grow(*last); --last; } else break;
-        }
-        lb.grow(*last);
-        std::swap(*first, *last);
-        ++first;
-      }
 done:
-      mid = (uint32_t) (first - prims.data());
+        mid = (uint32_t) (first - prims.data());
+      }
       haveBounds = true;
       if (mid == begin || mid == end) { mid = begin + count / 2; haveBounds = false; }
     }
@@ -383,10 +443,10 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
   // binary tree: cost[n][i-1] = cheapest way to present subtree n to its parent as at most i children
   // (i = 1..7), each child either a leaf of <= kMaxLeaf triangles or a wide node.  Bottom-up = post-order; the two
   // subtrees of a big node are independent OpenMP tasks.
-  const std::vector<BinNode>& bn = b.nodes;
+  const RawVector<BinNode>& bn = b.nodes;
   const uint32_t binCount = 2 * N - 1;
   struct Dp { float cost[7]; uint8_t split[7]; uint8_t rootSplit; uint8_t rootIsLeaf; };
-  std::vector<Dp> dp(binCount);
+  RawVector<Dp> dp(binCount);                  // every entry is written by solveNode
   const float INF = 3.402823466e38f;
   auto solveNode = [&](uint32_t ni) {
     const BinNode& n = bn[ni];
@@ -447,18 +507,19 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
   // sizes in parallel, a prefix sum fixes every node's childBase / triBase, then the nodes are written in parallel.
   // The layout is the breadth-first order a serial queue would produce.
   struct Pending { uint32_t bin, wide, depth; };
-  std::vector<Pending> level, next;
+  RawVector<Pending> level, next;
   out.nodes.reserve((size_t) N + 1);                  // a wide node has at least two children (virtual memory until used)
-  out.nodes.assign(1, Bvh8Node());
+  out.nodes.resize(1);
   out.tris.clear();
-  out.tris.reserve((size_t) N * 12);
+  out.tris.resize((size_t) N * 12);                   // every triangle lands in exactly one leaf
   level.push_back({ 0u, 0u, 1u });
+  RawVector<WideChildList> lists;                     // per-level scratch, reused so its pages are touched once
+  RawVector<uint32_t> nodeOff, triOff;
   uint32_t nodeBase = 1, triBaseLevel = 0;
   while (!level.empty()) {
     const int64_t M = (int64_t) level.size();
     out.maxDepth = std::max(out.maxDepth, level[0].depth);
-    std::vector<WideChildList> lists((size_t) M);
-    std::vector<uint32_t> nodeOff((size_t) M), triOff((size_t) M);
+    lists.resize((size_t) M); nodeOff.resize((size_t) M); triOff.resize((size_t) M);
 #pragma omp parallel for schedule(static) if (M > 256)
     for (int64_t e = 0; e < M; e++) {
       const Pending cur = level[(size_t) e];
@@ -475,8 +536,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     uint32_t totalNodes = 0, totalTris = 0;
     for (int64_t e = 0; e < M; e++) { const uint32_t a = nodeOff[(size_t) e], t = triOff[(size_t) e]; nodeOff[(size_t) e] = totalNodes; triOff[(size_t) e] = totalTris; totalNodes += a; totalTris += t; }
     out.nodes.resize((size_t) nodeBase + totalNodes);
-    out.tris.resize((size_t) (triBaseLevel + totalTris) * 12);
-    next.assign(totalNodes, Pending{ 0u, 0u, 0u });
+    next.resize(totalNodes);                          // one entry per internal child, all written below
 #pragma omp parallel for schedule(static) if (M > 256)
     for (int64_t ei = 0; ei < M; ei++) {
     const size_t e = (size_t) ei;
@@ -588,6 +648,7 @@ void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
     nodeBase += totalNodes; triBaseLevel += totalTris;
     level.swap(next);
   }
+  out.tris.resize((size_t) triBaseLevel * 12);
   out.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (getenv("GTLC_BUILD_TIMING")) {
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
