@@ -100,6 +100,21 @@ def test_host_build_is_independent_of_the_thread_count(tmp_path):
     assert outs[0] == outs[1] and len(outs[0].split()) == 2
 
 
+def test_host_builder_output_is_pinned():
+    """The host builder was restructured for speed several times under the rule "same bytes out"; these two trees pin it.
+    (An intended change of the tree -- a new SAH heuristic -- updates the hashes together with DESIGN.md.)"""
+    import hashlib
+    want = {1000: "9e6f71296d08a507a07e5836e05fec4a47e48620ef2868939eafd47abf056885",
+            20000: "adfabed4cd37a402d1da5d8de01d3805b7980685e450c058fa613388c08373bd"}
+    for n, digest in want.items():
+        b = gi.BuiltScene(scenes.random_triangles(n, 8, 8, 1))
+        try:
+            nodes, tris = gi.get_bvh(b.scene)
+        finally:
+            b.close()
+        assert hashlib.sha256(nodes.tobytes() + tris.tobytes()).hexdigest() == digest
+
+
 def test_analysis_walkers_bound_the_production_walk():
     """The oracle's analysis walkers (ideal near-to-far order, culling deferred node groups at pop) only count visits; they
     must never need MORE node visits than the production order they are compared with in DESIGN.md section 8."""
