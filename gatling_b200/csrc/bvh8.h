@@ -57,7 +57,7 @@ struct Bvh8 {
 
 struct BuildTri { float v[3][3]; uint32_t prim, inst; float opacity; };   // opacity < 1: stochastic cutout (rp_main.ahit)
 
-// Builds the BVH8 over `tris` (world space).  Deterministic for a given input.
-void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out);
+// Builds the BVH8 over `count` world-space triangles.  Deterministic for a given input, whatever the thread count.
+void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out);
 
 } // namespace gtlc

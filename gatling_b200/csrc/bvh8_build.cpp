@@ -406,11 +406,11 @@ inline uint32_t floatExponentBits(float f) { uint32_t u; std::memcpy(&u, &f, 4);
 
 } // namespace
 
-void bvh8_build(const std::vector<BuildTri>& tris, Bvh8& out)
+void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
 {
   auto t0 = std::chrono::steady_clock::now();
   out.nodes.clear(); out.tris.clear(); out.maxDepth = 0;
-  const uint32_t N = (uint32_t) tris.size();
+  const uint32_t N = (uint32_t) count;
   if (N == 0) {
     Bvh8Node empty; std::memset(&empty, 0, sizeof(empty));
     out.nodes.push_back(empty);

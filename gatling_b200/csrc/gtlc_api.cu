@@ -246,10 +246,9 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
 {
   auto t0 = std::chrono::steady_clock::now();
   s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->hInstOpacity.clear(); s->hPrimvarInfos.clear(); s->hPrimvarData.clear(); s->flatMaterials.clear();
-  std::vector<BuildTri> tris;
-  size_t totalTris = 0;
-  for (Mesh* m : s->meshes) if (m->visible && m->material) totalTris += m->faces.size() * (m->instanceTransforms.size() / 12);
-  if (hostBvh) tris.reserve(totalTris);
+  // world-space triangles for the host builder: one job per (instance, block of faces), filled by the whole team below
+  struct FlattenJob { const Mesh* mesh; uint32_t inst, firstFace, lastFace, firstTri; float opacity; float o2w[12]; };
+  std::vector<FlattenJob> jobs;
   uint32_t rank = 0;
   for (Mesh* m : s->meshes) {
     if (!m->visible) continue;                                          // Gi.cpp:801-804
@@ -318,23 +317,35 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
       s->hRankBase.push_back(rank);   // rank of (inst, prim) = rankBase[inst] + prim, ascending in (inst, prim)
       s->hInstOpacity.push_back(mat_cutout_opacity(m->material->closure, m->material->params));
       rank += (uint32_t) m->faces.size();
-      if (!hostBvh) continue;   // the device builder flattens on the GPU (lbvh_flatten_kernel, same arithmetic)
       s->hInstIds.push_back(make_int2(m->id, k < m->instanceIds.size() ? m->instanceIds[k] : (int32_t) k));
-      for (uint32_t f = 0; f < m->faces.size(); f++) {
-        BuildTri t; t.prim = f; t.inst = inst; t.opacity = mat_cutout_opacity(m->material->closure, m->material->params);
-        for (int c = 0; c < 3; c++) {
-          const float* p = m->vertices[m->faces[f].v_i[c]].pos;
-          t.v[c][0] = ((o2w[0] * p[0] + o2w[1] * p[1]) + o2w[2] * p[2]) + o2w[3];
-          t.v[c][1] = ((o2w[4] * p[0] + o2w[5] * p[1]) + o2w[6] * p[2]) + o2w[7];
-          t.v[c][2] = ((o2w[8] * p[0] + o2w[9] * p[1]) + o2w[10] * p[2]) + o2w[11];
-        }
-        tris.push_back(t);
+      if (!hostBvh) continue;   // the device builder flattens on the GPU (lbvh_flatten_kernel, same arithmetic)
+      const uint32_t faceCount = (uint32_t) m->faces.size(), firstTri = rank - faceCount;
+      for (uint32_t f0 = 0; f0 < faceCount; f0 += 65536u) {
+        FlattenJob j; j.mesh = m; j.inst = inst; j.firstFace = f0; j.lastFace = std::min(faceCount, f0 + 65536u); j.firstTri = firstTri + f0;
+        j.opacity = s->hInstOpacity.back(); memcpy(j.o2w, o2w, sizeof(o2w));
+        jobs.push_back(j);
       }
     }
   }
   s->totalTris = rank;
   if (hostBvh) {
-    bvh8_build(tris, s->bvh);
+    RawVector<BuildTri> tris((size_t) rank);      // triangle index = rankBase[inst] + prim
+#pragma omp parallel for schedule(dynamic, 1) if (rank > 50000)
+    for (int64_t ji = 0; ji < (int64_t) jobs.size(); ji++) {
+      const FlattenJob& j = jobs[(size_t) ji];
+      const float* o2w = j.o2w;
+      for (uint32_t f = j.firstFace; f < j.lastFace; f++) {
+        BuildTri t; t.prim = f; t.inst = j.inst; t.opacity = j.opacity;
+        for (int c = 0; c < 3; c++) {
+          const float* p = j.mesh->vertices[j.mesh->faces[f].v_i[c]].pos;
+          t.v[c][0] = ((o2w[0] * p[0] + o2w[1] * p[1]) + o2w[2] * p[2]) + o2w[3];
+          t.v[c][1] = ((o2w[4] * p[0] + o2w[5] * p[1]) + o2w[6] * p[2]) + o2w[7];
+          t.v[c][2] = ((o2w[8] * p[0] + o2w[9] * p[1]) + o2w[10] * p[2]) + o2w[11];
+        }
+        tris[(size_t) j.firstTri + (f - j.firstFace)] = t;
+      }
+    }
+    bvh8_build(tris.data(), tris.size(), s->bvh);
     if (s->bvh.maxDepth > (uint32_t) kStackSize) { setError("BVH8 depth %u exceeds the traversal stack (%d entries)", s->bvh.maxDepth, kStackSize); return false; }
     s->nodeCount = (uint32_t) s->bvh.nodes.size(); s->triCount = (uint32_t) (s->bvh.tris.size() / 12); s->maxDepth = s->bvh.maxDepth;
     s->bvhHostStale = false;

@@ -369,6 +369,7 @@ def test_device_bvh_build_parity(gpu):
             try:
                 _, host_tris = gpu.get_bvh(b.scene)
                 img_host = b.render().copy()
+                ids_host = b.render_aovs([0, 11, 14]) if d is inst_scene else None     # Color, ObjectId, InstanceId
             finally:
                 b.close()
             gpu.set_tuning(bvhBuilder=builder)
@@ -389,6 +390,11 @@ def test_device_bvh_build_parity(gpu):
                     assert np.array_equal(h_gpu[k], h_walk[k]), k
                 assert np.array_equal(v_gpu, v_walk)
                 assert np.array_equal(b.render(), img_host), "image changed with the device-built BVH"
+                if ids_host is not None:       # the per-instance id table does not come from the builder: it must survive a device build
+                    ids = b.render_aovs([0, 11, 14])
+                    for aov in (gpu.GiAovId.ObjectId, gpu.GiAovId.InstanceId):
+                        assert np.array_equal(ids[aov], ids_host[aov]), aov
+                    assert len(np.unique(ids[gpu.GiAovId.InstanceId])) > 1
             finally:
                 b.close()
         # an empty scene
