@@ -1080,7 +1080,13 @@ int gtlc_scene_get_bvh(GtlcHandle h, GtlcBvhView* view)
           cudaMemcpy(s->bvh.tris.data(), s->dTris.ptr, (size_t) s->triCount * 48, cudaMemcpyDeviceToHost) != cudaSuccess) { setError("BVH read-back failed"); return GTLC_ERROR; }
       s->bvhHostStale = false;
     }
-  } else if (s->geometryDirty || !s->bvhValid) { if (!buildHostGeometry(s)) return GTLC_ERROR; /* device upload happens lazily in render/trace */ }
+  } else if (s->geometryDirty || !s->bvhValid || s->bvhHostStale) {
+    // (stale = the tree in HBM came from a device builder and the tuning went back to the host builder: rebuild here and
+    // drop the device copy so that the next render / ray query uploads the tree this call returns)
+    const bool wasStale = s->bvhHostStale;
+    if (!buildHostGeometry(s)) return GTLC_ERROR;          // device upload happens lazily in render/trace
+    if (wasStale) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); s->dNodes.release(); }
+  }
   view->nodes = s->bvh.nodes.data(); view->nodeCount = (uint32_t) s->bvh.nodes.size();
   view->triangles = s->bvh.tris.data(); view->triCount = (uint32_t) (s->bvh.tris.size() / 12);
   return GTLC_OK;
