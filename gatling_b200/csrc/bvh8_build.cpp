@@ -210,6 +210,38 @@ struct Builder {
     return mid;
   }
 
+  // The same permutation by one thread, without a data-dependent branch per record (the predicate is a coin flip for
+  // the branch predictor): pass 1 flags every record and grows the bounds of its side through an indexed accumulator,
+  // pass 2 lists the misplaced positions of both sides with unconditional stores, then the pairs are swapped.
+  template <class Pred>
+  uint32_t partitionSerial(uint32_t begin, uint32_t end, const Pred& goesLeft, Bounds4& lb, Bounds4& rb)
+  {
+    const uint32_t count = end - begin;
+    static thread_local std::vector<uint8_t> flagScratch;
+    static thread_local std::vector<uint32_t> listScratch;
+    uint8_t flagSmall[256]; uint32_t listSmall[512];
+    uint8_t* flag = flagSmall; uint32_t* fromLeft = listSmall;
+    if (count > 256) {
+      if (flagScratch.size() < count) { flagScratch.resize(count); listScratch.resize((size_t) 2 * count); }
+      flag = flagScratch.data(); fromLeft = listScratch.data();
+    }
+    uint32_t* fromRight = fromLeft + count;
+    Bounds4 side[2]; side[0].reset(); side[1].reset();
+    uint32_t trues = 0;
+    Prim* base = prims.data() + begin;
+    for (uint32_t i = 0; i < count; i++) {
+      const uint32_t f = goesLeft(base[i]) ? 1u : 0u;
+      flag[i] = (uint8_t) f; trues += f;
+      side[1u - f].grow(base[i]);
+    }
+    lb = side[0]; rb = side[1];
+    uint32_t nl = 0, nr = 0;
+    for (uint32_t i = 0; i < trues; i++) { fromLeft[nl] = i; nl += 1u - flag[i]; }
+    for (uint32_t i = count; i-- > trues;) { fromRight[nr] = i; nr += flag[i]; }
+    for (uint32_t k = 0; k < nl; k++) std::swap(base[fromLeft[k]], base[fromRight[k]]);
+    return begin + trues;
+  }
+
   // Node ids are the pre-order of the binary tree: every leaf holds one triangle, so the subtree over `c` triangles has
   // exactly 2c - 1 nodes and the right child of `node` sits 2 (mid - begin) after it.  No shared counter, and a subtree is
   // one contiguous block for the collapse and emission passes that walk it afterwards.
@@ -355,27 +387,7 @@ struct Builder {
         return b <= bestBin;
       };
       if (chunks > 1) mid = partitionChunked(begin, end, goesLeft, lb, rb);
-      else {
-        // the two-pointer scheme of std::partition, with every record looked at exactly once
-        Prim* first = prims.data() + begin; Prim* last = prims.data() + end;
-        for (;;) {
-          for (;;) {
-            if (first == last) goto done;
-            if (goesLeft(*first)) { lb.grow(*first); ++first; } else break;
-          }
-          rb.grow(*first);
-          --last;
-          for (;;) {
-            if (first == last) goto done;
-            if (!goesLeft(*last)) { rb.grow(*last); --last; } else break;
-          }
-          lb.grow(*last);
-          std::swap(*first, *last);
-          ++first;
-        }
-done:
-        mid = (uint32_t) (first - prims.data());
-      }
+      else mid = partitionSerial(begin, end, goesLeft, lb, rb);
       haveBounds = true;
       if (mid == begin || mid == end) { mid = begin + count / 2; haveBounds = false; }
     }
