@@ -105,7 +105,8 @@ def test_host_builder_output_is_pinned():
     (An intended change of the tree -- a new SAH heuristic -- updates the hashes together with DESIGN.md.)"""
     import hashlib
     want = {1000: "9e6f71296d08a507a07e5836e05fec4a47e48620ef2868939eafd47abf056885",
-            20000: "adfabed4cd37a402d1da5d8de01d3805b7980685e450c058fa613388c08373bd"}
+            20000: "adfabed4cd37a402d1da5d8de01d3805b7980685e450c058fa613388c08373bd",
+            300000: "bfcc74ef60a9e5325835051bda411eddc07d229130825babb84c7ff6635714fb"}     # large enough for the team-wide binning / partition passes
     for n, digest in want.items():
         b = gi.BuiltScene(scenes.random_triangles(n, 8, 8, 1))
         try:
