@@ -214,6 +214,8 @@ typedef struct GtlcTextureDesc {
   int32_t     reserved;
   const void* texels;          /* row 0 = bottom row (v = 0), as imgio delivers images (PngDecoder.cpp:78 flips) */
 } GtlcTextureDesc;
+/* No Gi.h counterpart: the reference creates images inside giCreateMaterialFrom* through its TextureManager
+ * (TextureManager.cpp:100-274); here the caller decodes and hands texels over. */
 GTLC_API GtlcHandle gtlc_texture_create(const GtlcTextureDesc* desc);
 GTLC_API void       gtlc_texture_destroy(GtlcHandle texture);   /* deferred while a material still references it */
 
@@ -292,6 +294,7 @@ GTLC_API void gtlc_mesh_set_visibility(GtlcHandle mesh, int32_t visible);       
 GTLC_API void gtlc_mesh_destroy(GtlcHandle mesh);                                           /* giDestroyMesh */
 
 /* ---- analytic lights: Gi.h:223-251 ------------------------------------------------------- */
+/* sphere: Gi.h:223-228 (host encodings Gi.cpp:2573-2661) */
 GTLC_API GtlcHandle gtlc_sphere_light_create(GtlcHandle scene);
 GTLC_API void gtlc_sphere_light_destroy(GtlcHandle scene, GtlcHandle light);
 GTLC_API void gtlc_sphere_light_set_position(GtlcHandle light, const float* position);
@@ -299,6 +302,7 @@ GTLC_API void gtlc_sphere_light_set_base_emission(GtlcHandle light, const float*
 GTLC_API void gtlc_sphere_light_set_radius(GtlcHandle light, float radiusX, float radiusY, float radiusZ);
 GTLC_API void gtlc_sphere_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
 
+/* distant: Gi.h:230-235 (Gi.cpp:2663-2745) */
 GTLC_API GtlcHandle gtlc_distant_light_create(GtlcHandle scene);
 GTLC_API void gtlc_distant_light_destroy(GtlcHandle scene, GtlcHandle light);
 GTLC_API void gtlc_distant_light_set_direction(GtlcHandle light, const float* direction);
@@ -306,6 +310,7 @@ GTLC_API void gtlc_distant_light_set_base_emission(GtlcHandle light, const float
 GTLC_API void gtlc_distant_light_set_angle(GtlcHandle light, float angle);
 GTLC_API void gtlc_distant_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
 
+/* rect: Gi.h:237-243 (Gi.cpp:2747-2843) */
 GTLC_API GtlcHandle gtlc_rect_light_create(GtlcHandle scene);
 GTLC_API void gtlc_rect_light_destroy(GtlcHandle scene, GtlcHandle light);
 GTLC_API void gtlc_rect_light_set_origin(GtlcHandle light, const float* origin);
@@ -314,6 +319,7 @@ GTLC_API void gtlc_rect_light_set_base_emission(GtlcHandle light, const float* r
 GTLC_API void gtlc_rect_light_set_dimensions(GtlcHandle light, float width, float height);
 GTLC_API void gtlc_rect_light_set_diffuse_specular(GtlcHandle light, float diffuse, float specular);
 
+/* disk: Gi.h:245-251 (Gi.cpp:2845-2941) */
 GTLC_API GtlcHandle gtlc_disk_light_create(GtlcHandle scene);
 GTLC_API void gtlc_disk_light_destroy(GtlcHandle scene, GtlcHandle light);
 GTLC_API void gtlc_disk_light_set_origin(GtlcHandle light, const float* origin);
