@@ -35,6 +35,7 @@ struct BinNode { Box box; uint32_t left, right, first, count, total; };   // cou
 constexpr int kBins = 16;
 constexpr uint32_t kSmallNode = 4;           // nodes up to this size pick their split without bin arrays
 constexpr uint32_t kParallelRange = 262144;   // ranges at least this long are scanned by several tasks
+constexpr uint32_t kTaskRange = 4096;          // subtrees larger than this become OpenMP tasks (a few hundred tasks per million triangles)
 // SAH parameters (overridable through GTLC_BVH_MAX_LEAF / GTLC_BVH_NODE_COST for tuning experiments)
 uint32_t kMaxLeaf = 3;
 float kNodeCost = 0.6f;  // relative to one triangle test
@@ -250,7 +251,7 @@ struct Builder {
     BinNode& n = nodes[node];
     const uint32_t l = node + 1, r = node + 2 * (mid - begin);
     n.left = l; n.right = r; n.count = 0; n.first = begin; n.total = end - begin;
-    if (end - begin > 16384) {
+    if (end - begin > kTaskRange) {
       if (leftInline) build(l, begin, mid, lb);
       else {
 #pragma omp task default(shared) firstprivate(l, begin, mid, lb)
@@ -486,7 +487,7 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
   };
   // post-order; big subtrees become OpenMP tasks, small ones run as an explicit-stack walk inside their task
   auto solveSubtree = [&](auto&& self, uint32_t root) -> void {
-    if (bn[root].count == 0 && bn[root].total > 32768) {
+    if (bn[root].count == 0 && bn[root].total > 2 * kTaskRange) {
 #pragma omp task default(shared)
       self(self, bn[root].left);
 #pragma omp task default(shared)
