@@ -244,9 +244,15 @@ class OracleScene:
                 inst.append(rec)
             vbase += len(m.vertices)
             fbase += len(m.faces)
-        self.vertices = np.ascontiguousarray(np.concatenate(verts))
-        self.faces = np.ascontiguousarray(np.concatenate(faces).reshape(-1, 3))
-        self.instances = np.ascontiguousarray(np.concatenate(inst))
+        if verts:
+            self.vertices = np.ascontiguousarray(np.concatenate(verts))
+            self.faces = np.ascontiguousarray(np.concatenate(faces).reshape(-1, 3))
+            self.instances = np.ascontiguousarray(np.concatenate(inst))
+        else:                                             # an empty stage (the reference's Render.Empty1x1 test)
+            from gatling_b200.scenes import VERTEX_DTYPE
+            self.vertices = np.zeros(0, VERTEX_DTYPE)
+            self.faces = np.zeros((0, 3), np.uint32)
+            self.instances = np.zeros(0, INSTANCE_DTYPE)
         self._keep = []
         self.mats = (MaterialDesc * len(desc.materials))()
         for i, m in enumerate(desc.materials):

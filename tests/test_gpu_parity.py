@@ -128,6 +128,15 @@ def test_render_parity_settings_variants(gpu):
     _render_parity(gpu, d)
 
 
+def test_render_empty_1x1(gpu):
+    """Render.Empty1x1 of the reference's test-suite (src/hdGatling/main.cpp:584): no geometry, one pixel."""
+    e = scenes.cornell(1, 1, spp=4)
+    e.meshes = []
+    e.clear_color = (0.25, 0.5, 1.0, 1.0)
+    img, ref = _render_parity(gpu, e)
+    assert img.shape == (1, 1, 4) and np.allclose(img[0, 0], [63 / 255, 127 / 255, 1.0, 1.0], atol=1e-6)
+
+
 def test_progressive_accumulation(gpu):
     d = scenes.cornell(64, 64, spp=4, max_bounces=4)
     b = gpu.BuiltScene(d)

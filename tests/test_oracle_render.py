@@ -36,6 +36,18 @@ def test_feature_regression_anchors():
         assert np.allclose(img, want[name], rtol=1e-5, atol=1e-6), name
 
 
+def test_empty_stage_1x1():
+    """The reference's Render.Empty1x1 case (src/hdGatling/main.cpp:584): an empty stage at 1x1 is the colour AOV's clear
+    value after its trip through the RGBA8 fallback dome texture (Gi.cpp:2183-2199)."""
+    e = scenes.cornell(1, 1, spp=4)
+    e.meshes = []
+    e.clear_color = (0.25, 0.5, 1.0, 1.0)
+    img, _, rays = orc.OracleScene(e).render()
+    assert img.shape == (1, 1, 4)
+    assert np.allclose(img[0, 0], [63 / 255, 127 / 255, 1.0, 1.0], atol=1e-6)
+    assert rays[0] == 4 and rays[1] == 0            # one primary ray per sample, all of them escape
+
+
 def test_progressive_accumulation_matches_single_pass():
     d = scenes.cornell(24, 24, spp=8, max_bounces=3)
     o = orc.OracleScene(d)
