@@ -100,6 +100,7 @@ _SIGNATURES = {
     "gtlc_initialize": (C.c_int, [C.POINTER(InitParams)]),
     "gtlc_terminate": (None, []),
     "gtlc_last_error": (C.c_char_p, []),
+    "gtlc_error_count": (C.c_uint64, []),
     "gtlc_scene_create": (H, []),
     "gtlc_scene_destroy": (None, [H]),
     "gtlc_material_create": (H, [H, C.POINTER(MaterialDesc)]),

@@ -29,6 +29,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 std::mutex g_errMutex;
 std::string g_lastError;
+uint64_t g_errorCount = 0;
 
 void setError(const char* fmt, ...)
 {
@@ -36,6 +37,7 @@ void setError(const char* fmt, ...)
   va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
   std::lock_guard<std::mutex> g(g_errMutex);
   g_lastError = buf;
+  g_errorCount++;
   fprintf(stderr, "[gtlc] error: %s\n", buf);
 }
 
@@ -681,6 +683,7 @@ bool paramsResetAccumulation(Scene* s, const GtlcRenderParams* p)
 // =============================================================================================
 extern "C" {
 
+uint64_t gtlc_error_count(void) { std::lock_guard<std::mutex> l(g_errMutex); return g_errorCount; }
 const char* gtlc_last_error(void) { std::lock_guard<std::mutex> l(g_errMutex); static thread_local std::string copy; copy = g_lastError; return copy.c_str(); }
 
 void gtlc_material_desc_defaults(int32_t closure, GtlcMaterialDesc* d)

@@ -60,6 +60,11 @@ def giLastError() -> str:
     return (_lib().gtlc_last_error() or b"").decode()
 
 
+def giErrorCount() -> int:
+    """Error lines logged so far (gtlc_error_count): lets a test fail on any error line like the reference's fixture."""
+    return int(_lib().gtlc_error_count())
+
+
 # ---- lifecycle (Gi.h:199-200) ---------------------------------------------------------------------
 def giInitialize(device_index: int = -1) -> GiStatus:
     p = L.InitParams(device_index, 0)

@@ -274,6 +274,9 @@ GTLC_API int  gtlc_initialize(const GtlcInitParams* params);
 GTLC_API void gtlc_terminate(void);
 /* Last error text (reference logs through GB_ERROR; the C-ABI keeps the line for the binding to log). */
 GTLC_API const char* gtlc_last_error(void);
+/* Error lines logged since the library was loaded: what a test fixture needs to fail on ANY error line the way the
+ * reference's does with its log sink (src/hdGatling/main.cpp:78-100,531-549). */
+GTLC_API uint64_t gtlc_error_count(void);
 
 /* ---- scene: giCreateScene / giDestroyScene (Gi.h:220-221) -------------------------------- */
 GTLC_API GtlcHandle gtlc_scene_create(void);

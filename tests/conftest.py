@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "logs_errors: the test provokes error lines on purpose")
 
 
 @pytest.fixture(scope="session", autouse=True)
@@ -34,3 +35,18 @@ def gpu():
     assert st == gi.GiStatus.Ok, "giInitialize failed: " + gi.giLastError()
     yield gi
     gi.giTerminate()
+
+
+@pytest.fixture(autouse=True)
+def _no_error_lines(request, _built_libraries):
+    """The reference's graphical fixture fails a test on any GB_ERROR log line (src/hdGatling/main.cpp:78-100,531-549).
+    Same rule for the host-side tests here: a test that does not announce it (`logs_errors`) must not make the
+    library log an error.  (GPU tests are exempt until each has been looked at on the box.)"""
+    if request.node.get_closest_marker("gpu") or request.node.get_closest_marker("logs_errors"):
+        yield
+        return
+    from gatling_b200 import gi
+    before = gi.giErrorCount()
+    yield
+    after = gi.giErrorCount()
+    assert after == before, "the library logged %d error line(s), last: %s" % (after - before, gi.giLastError())

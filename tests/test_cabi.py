@@ -14,7 +14,7 @@ from gatling_b200 import _lib, gi, scenes
 def test_exports_every_declared_symbol():
     lib = _lib.load()
     names = _lib.declared_symbols()
-    assert len(names) == 60
+    assert len(names) == 61
     for n in names:
         assert hasattr(lib, n), "libgtlc.so does not export %s" % n
     assert set(names) == set(_lib._SIGNATURES), "python binding and header disagree"
@@ -50,6 +50,7 @@ def test_material_defaults():
     assert np.array_equal(np.array(d.params[:], np.float32), scenes.material_openpbr().params)   # open_pbr_surface.mtlx:11-84
 
 
+@pytest.mark.logs_errors
 def test_object_lifecycle_without_gpu():
     s = gi.giCreateScene()
     assert s
@@ -81,6 +82,7 @@ def test_object_lifecycle_without_gpu():
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
+@pytest.mark.logs_errors
 def test_no_cpu_fallback():
     """Without a CUDA device the product refuses to initialise and every compute entry point fails loudly."""
     assert gi.giInitialize(0) == gi.GiStatus.Error
