@@ -41,6 +41,7 @@ uint32_t kMaxLeaf = 3;
 float kNodeCost = 0.6f;  // relative to one triangle test
 float kBigTriFraction = 0.4f;   // GTLC_BVH_BIG_TRIS: a triangle is "big" when its extent sum exceeds this fraction of the node's (0 = off)
 constexpr float kTriCost = 1.0f;
+constexpr float kMaxCoordinate = 1.0e18f;   // beyond this, surface areas leave the float range
 
 // One record per triangle, moved (not indexed) by the partition passes so that every pass of the builder streams
 // through memory: bounds in the first three lanes of two SSE registers, the triangle's index in the fourth lane of `lo`.
@@ -439,6 +440,12 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
   for (int64_t i = 0; i < (int64_t) N; i++) {
     Box bx; bx.reset();
     for (int k = 0; k < 3; k++) bx.grow(tris[i].v[k]);
+    // A triangle with a NaN / infinite / absurdly large coordinate can never be hit (every comparison of the watertight
+    // test fails; Vulkan calls such triangles inactive) but would poison the boxes and the SAH arithmetic above it:
+    // it enters the tree as a point at the origin.
+    bool finite = true;
+    for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) finite = finite && (std::fabs(tris[i].v[v][k]) <= kMaxCoordinate);
+    if (!finite) for (int k = 0; k < 3; k++) bx.lo[k] = bx.hi[k] = 0.0f;
     Prim& p = b.prims[(size_t) i];
     for (int k = 0; k < 3; k++) { p.lo[k] = bx.lo[k]; p.hi[k] = bx.hi[k]; }
     p.id = (uint32_t) i; p.pad = 0;
@@ -476,7 +483,7 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
     float best = INF; uint8_t bk = 1;
     for (int k = 1; k <= 7; k++) { const float c = L.cost[k - 1] + R.cost[8 - k - 1]; if (c < best) { best = c; bk = (uint8_t) k; } }
     const float internalCost = best + area * kNodeCost;
-    d.rootSplit = bk; d.rootIsLeaf = leafCost <= internalCost;
+    d.rootSplit = bk; d.rootIsLeaf = n.total <= kMaxLeaf && leafCost <= internalCost;
     d.cost[0] = d.rootIsLeaf ? leafCost : internalCost; d.split[0] = 0;
     for (int i = 2; i <= 7; i++) {            // as at most i children of the parent
       float bd = INF; uint8_t bs = 0;
@@ -580,7 +587,9 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
     for (int k = 0; k < n; k++) {
       int bi = -1; float bc = -3.402823466e38f;
       for (int i = 0; i < n; i++) if (!childDone[i] && rowBest[i] > bc) { bc = rowBest[i]; bi = i; }
-      const int bs = rowSlot[bi];
+      if (bi < 0) { for (int i = 0; i < n && bi < 0; i++) if (!childDone[i]) bi = i; }          // no finite entry left: any order will do
+      int bs = rowSlot[bi];
+      if (bs < 0 || slotUsed[bs]) { bs = 0; while (slotUsed[bs]) bs++; }
       slotOf[bi] = bs; childDone[bi] = true; slotUsed[bs] = true;
       for (int i = 0; i < n; i++) if (!childDone[i] && rowSlot[i] == bs) rescan(i);
     }

@@ -150,3 +150,42 @@ def test_analysis_walkers_bound_the_production_walk():
     assert visited == production
     assert grid <= union <= empty < visited
     assert union_geom <= union and union_geom < 0.05 * visited
+
+
+def test_non_finite_triangles_are_inactive():
+    """Triangles with NaN / infinite / absurdly large coordinates must neither crash the builder nor disturb the tree
+    around them (Vulkan calls them inactive, and the watertight test can never report them): the finite triangles are
+    found exactly as in the scene without the bad ones."""
+    d = scenes.random_triangles(3000, 8, 8, spp=1)
+    m = d.meshes[0]
+    good = m.vertices.copy()
+    bad = good.copy()
+    rng = np.random.default_rng(5)
+    victims = rng.choice(len(m.faces), 200, replace=False)
+    specials = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 1e30], np.float32)
+    for k, f in enumerate(victims):
+        v = m.faces[f][k % 3]
+        bad["pos"][v, k % 3] = specials[k % len(specials)]
+    m.vertices = bad
+    b = gi.BuiltScene(d)
+    try:
+        nodes, tris = gi.get_bvh(b.scene)
+    finally:
+        b.close()
+    assert len(tris) == 3000 * 12
+    rays = np.ascontiguousarray(random_rays(20000, 9), np.float32)
+    hits, _ = orc.bvh8_trace(nodes, tris, rays)
+    assert not np.isin(hits["prim"][hits["t"] >= 0], victims).any()
+    # reference: the same scene with the bad triangles removed (primitive ids keep their meaning through faceIds order)
+    keep = np.setdiff1d(np.arange(len(m.faces)), victims)
+    m.vertices = good
+    m.faces = m.faces[keep]
+    b = gi.BuiltScene(d)
+    try:
+        nodes2, tris2 = gi.get_bvh(b.scene)
+    finally:
+        b.close()
+    hits2, _ = orc.bvh8_trace(nodes2, tris2, rays)
+    assert np.array_equal(hits["t"], hits2["t"])
+    hit = hits["t"] >= 0
+    assert np.array_equal(hits["prim"][hit], keep[hits2["prim"][hit]])
