@@ -851,6 +851,7 @@ void gtlc_material_destroy(GtlcHandle h)
 static bool copyPrimvars(const GtlcPrimvarDesc* src, uint32_t count, std::vector<Mesh::Primvar>& dst)
 {
   dst.clear();
+  if (count && !src) return false;
   for (uint32_t i = 0; i < count; i++) {
     if (!src[i].name || src[i].type < GTLC_PRIMVAR_FLOAT || src[i].type > GTLC_PRIMVAR_INT4 || src[i].interpolation < GTLC_INTERP_CONSTANT || src[i].interpolation > GTLC_INTERP_VERTEX) return false;
     Mesh::Primvar p; p.name = src[i].name; p.type = src[i].type; p.interpolation = src[i].interpolation;
@@ -862,7 +863,7 @@ static bool copyPrimvars(const GtlcPrimvarDesc* src, uint32_t count, std::vector
 GtlcHandle gtlc_mesh_create(GtlcHandle sh, const GtlcMeshDesc* d)
 {
   Scene* s = as<Scene>(sh, TAG_SCENE); if (!s || !d) return 0;
-  if (d->faceCount && (!d->faces || !d->vertices)) { setError("gtlc_mesh_create: null geometry"); return 0; }
+  if ((d->faceCount && (!d->faces || !d->vertices)) || (d->vertexCount && !d->vertices)) { setError("gtlc_mesh_create: null geometry"); return 0; }
   for (uint32_t f = 0; f < d->faceCount; f++) for (int c = 0; c < 3; c++)
     if (d->faces[f].v_i[c] >= d->vertexCount) { setError("gtlc_mesh_create: face %u references vertex %u >= %u", f, d->faces[f].v_i[c], d->vertexCount); return 0; }
   Mesh* m = new Mesh(); m->tag = TAG_MESH; m->scene = s;
@@ -891,7 +892,7 @@ void gtlc_mesh_set_transform(GtlcHandle h, const float* m16)
 }
 void gtlc_mesh_set_instance_transforms(GtlcHandle h, uint32_t count, const float* t16)
 {
-  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m || (count && !t16)) return;
   std::lock_guard<std::mutex> l(m->scene->mutex);
   m->instanceTransforms.resize((size_t) count * 12);
   for (uint32_t i = 0; i < count; i++) usdToRow3x4(t16 + (size_t) i * 16, &m->instanceTransforms[(size_t) i * 12]);
@@ -907,7 +908,7 @@ void gtlc_mesh_set_instancer_primvars(GtlcHandle h, uint32_t count, const GtlcPr
 }
 void gtlc_mesh_set_instance_ids(GtlcHandle h, uint32_t count, const int32_t* ids)
 {
-  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m) return;
+  Mesh* m = as<Mesh>(h, TAG_MESH); if (!m || (count && !ids)) return;
   std::lock_guard<std::mutex> l(m->scene->mutex);
   m->instanceIds.assign(ids, ids + count);
   m->scene->geometryDirty = true; m->scene->framebufferDirty = true;
@@ -961,8 +962,8 @@ GtlcHandle gtlc_sphere_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_sphere_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (s && l) destroy_SphereLight(s, l); }
-void gtlc_sphere_light_set_position(GtlcHandle h, const float* p) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return; memcpy(l->data.pos, p, 12); TOUCH(l); }
-void gtlc_sphere_light_set_base_emission(GtlcHandle h, const float* c) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_sphere_light_set_position(GtlcHandle h, const float* p) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l || !p) return; memcpy(l->data.pos, p, 12); TOUCH(l); }
+void gtlc_sphere_light_set_base_emission(GtlcHandle h, const float* c) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
 void gtlc_sphere_light_set_radius(GtlcHandle h, float rx, float ry, float rz)
 {
   SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return;
@@ -981,8 +982,8 @@ GtlcHandle gtlc_distant_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_distant_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (s && l) destroy_DistantLight(s, l); }
-void gtlc_distant_light_set_direction(GtlcHandle h, const float* d) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return; memcpy(l->data.direction, d, 12); TOUCH(l); }
-void gtlc_distant_light_set_base_emission(GtlcHandle h, const float* c) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_distant_light_set_direction(GtlcHandle h, const float* d) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l || !d) return; memcpy(l->data.direction, d, 12); TOUCH(l); }
+void gtlc_distant_light_set_base_emission(GtlcHandle h, const float* c) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
 void gtlc_distant_light_set_angle(GtlcHandle h, float angle)
 {
   DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return;
@@ -1003,9 +1004,9 @@ GtlcHandle gtlc_rect_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_rect_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); RectLight* l = as<RectLight>(h, TAG_RECT); if (s && l) destroy_RectLight(s, l); }
-void gtlc_rect_light_set_origin(GtlcHandle h, const float* o) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
-void gtlc_rect_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
-void gtlc_rect_light_set_base_emission(GtlcHandle h, const float* c) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_rect_light_set_origin(GtlcHandle h, const float* o) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !o) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
+void gtlc_rect_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !t0 || !t1) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
+void gtlc_rect_light_set_base_emission(GtlcHandle h, const float* c) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
 void gtlc_rect_light_set_dimensions(GtlcHandle h, float w, float hh) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.width = w; l->data.height = hh; TOUCH(l); }
 void gtlc_rect_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
 
@@ -1020,9 +1021,9 @@ GtlcHandle gtlc_disk_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_disk_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); DiskLight* l = as<DiskLight>(h, TAG_DISK); if (s && l) destroy_DiskLight(s, l); }
-void gtlc_disk_light_set_origin(GtlcHandle h, const float* o) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
-void gtlc_disk_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
-void gtlc_disk_light_set_base_emission(GtlcHandle h, const float* c) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_disk_light_set_origin(GtlcHandle h, const float* o) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !o) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
+void gtlc_disk_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !t0 || !t1) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
+void gtlc_disk_light_set_base_emission(GtlcHandle h, const float* c) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
 void gtlc_disk_light_set_radius(GtlcHandle h, float rx, float ry) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.radiusX = rx; l->data.radiusY = ry; TOUCH(l); }
 void gtlc_disk_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
 
@@ -1042,8 +1043,8 @@ GtlcHandle gtlc_dome_light_create(GtlcHandle sh, uint32_t w, uint32_t hgt, const
   return handleOf(d);
 }
 void gtlc_dome_light_destroy(GtlcHandle h) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; if (d->dTexels) cudaFree(d->dTexels); { std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; } d->tag = 0; delete d; }
-void gtlc_dome_light_set_rotation(GtlcHandle h, const float* q) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; memcpy(d->rotation, q, 16); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
-void gtlc_dome_light_set_base_emission(GtlcHandle h, const float* c) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; memcpy(d->baseEmission, c, 12); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
+void gtlc_dome_light_set_rotation(GtlcHandle h, const float* q) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d || !q) return; memcpy(d->rotation, q, 16); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
+void gtlc_dome_light_set_base_emission(GtlcHandle h, const float* c) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d || !c) return; memcpy(d->baseEmission, c, 12); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
 void gtlc_dome_light_set_diffuse_specular(GtlcHandle h, float df, float sp) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; d->diffuse = df; d->specular = sp; std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
 
 // ---- render buffers (Gi.cpp:2995-3006) -------------------------------------------------------

@@ -106,3 +106,42 @@ def test_product_never_touches_the_oracle():
                     if "oracle/" in txt.replace("tests/, oracle/", "") and ("#include \"../../oracle" in txt or "from oracle" in txt or "import oracle" in txt or "liboracle" in txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+@pytest.mark.logs_errors
+def test_hostile_arguments_do_not_crash():
+    """Null pointers with non-zero counts, null descriptors, handles of the wrong kind: every host-side entry point
+    answers with an error (or ignores the call) instead of dereferencing."""
+    lib = gi._lib()
+    scene = gi.giCreateScene()
+    mat = gi.giCreateMaterial(scene, 0, [0.8] * 3 + [0.0] * 45)
+    d = scenes.random_triangles(10, 8, 8, 1)
+    mesh = gi.giCreateMesh(scene, d.meshes[0].vertices, d.meshes[0].faces)
+    gi.giSetMeshMaterial(mesh, mat)
+    sp, di = lib.gtlc_sphere_light_create(scene), lib.gtlc_distant_light_create(scene)
+    re, dk = lib.gtlc_rect_light_create(scene), lib.gtlc_disk_light_create(scene)
+    lib.gtlc_mesh_set_transform(mesh, None)
+    lib.gtlc_mesh_set_instance_transforms(mesh, 3, None)
+    lib.gtlc_mesh_set_instance_ids(mesh, 3, None)
+    lib.gtlc_mesh_set_instancer_primvars(mesh, 2, None)
+    lib.gtlc_sphere_light_set_position(sp, None); lib.gtlc_sphere_light_set_base_emission(sp, None)
+    lib.gtlc_distant_light_set_direction(di, None); lib.gtlc_distant_light_set_base_emission(di, None)
+    lib.gtlc_rect_light_set_origin(re, None); lib.gtlc_rect_light_set_tangents(re, None, None); lib.gtlc_rect_light_set_base_emission(re, None)
+    lib.gtlc_disk_light_set_origin(dk, None); lib.gtlc_disk_light_set_tangents(dk, None, None); lib.gtlc_disk_light_set_base_emission(dk, None)
+    for h in (0, scene, mat, sp):                      # not a mesh
+        lib.gtlc_mesh_set_visibility(h, 1)
+        lib.gtlc_mesh_set_material(h, mat)
+        lib.gtlc_mesh_destroy(h)
+    for h in (0, scene, mesh, sp):                     # not a material / texture / sphere light
+        lib.gtlc_material_destroy(h)
+        lib.gtlc_texture_destroy(h)
+        if h != sp:
+            lib.gtlc_sphere_light_set_radius(h, 1.0, 1.0, 1.0)
+    assert lib.gtlc_mesh_create(scene, None) == 0 and lib.gtlc_mesh_create(0, None) == 0
+    assert lib.gtlc_material_create(scene, None) == 0 and lib.gtlc_texture_create(None) == 0
+    view = _lib.BvhView()
+    assert lib.gtlc_scene_get_bvh(0, C.byref(view)) != 0 and lib.gtlc_scene_get_bvh(scene, None) != 0
+    assert lib.gtlc_render(None) != 0
+    nodes, tris = gi.get_bvh(scene)                    # the scene survived all of it: its one mesh is still there
+    assert len(tris) == 10 * 12
+    gi.giDestroyScene(scene)
