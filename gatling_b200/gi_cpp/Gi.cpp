@@ -320,7 +320,9 @@ namespace gtl
         const int ch = bytes[1] == 'F' ? 3 : 1;
         const size_t off = (size_t) consumed + 1;
         if (bytes.size() < off + (size_t) w * h * ch * 4) return 0;
-        const float* src = reinterpret_cast<const float*>(bytes.data() + off);     // PFM rows already run bottom to top
+        std::vector<float> payload((size_t) w * h * ch);                            // PFM rows already run bottom to top
+        memcpy(payload.data(), bytes.data() + off, payload.size() * 4);             // (the header leaves the floats unaligned)
+        const float* src = payload.data();
         std::vector<float> texels((size_t) w * h * (ch == 3 ? 4 : 1));
         for (size_t i = 0; i < (size_t) w * h; i++) {
           if (ch == 1) texels[i] = src[i];
