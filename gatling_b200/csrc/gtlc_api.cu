@@ -137,6 +137,7 @@ struct Global {
   int device = 0;
   cudaStream_t stream = nullptr;
   int smCount = 148;
+  uint32_t currentTriCount = 0;   // of the scene about to be traced (syncSceneToDevice)
   GtlcTuning tuning;
   GtlcStats stats;
   // path-state pool
@@ -654,7 +655,11 @@ template <int MODE> void launchTrace(const TraceParams& P, bool count, int block
     case 1: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;          // per-lane triangle loop (the order the oracle's walker restates)
     case 5: trace_kernel_v2<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 6: trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
-    default: trace_kernel_batched<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;        // 0 (default) and 7: warp-batched triangle tests
+    default:                                                                                    // 0 (default) and 7: warp-batched triangle tests
+      // its queue entries pack (owner lane << 27 | triangle index): beyond 2^27 triangles the per-lane kernel takes over
+      if (g.currentTriCount >= (1u << 27)) trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+      else trace_kernel_batched<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+      break;
   }
 }
 
@@ -1108,6 +1113,7 @@ static bool syncSceneToDevice(Scene* s)
   if (s->materialsDirty) { if (!uploadMaterials(s)) return false; s->materialsDirty = false; }
   if (s->lightsDirty) { if (!uploadLights(s)) return false; s->lightsDirty = false; }
   g.stats.bvhNodeCount = s->nodeCount; g.stats.bvhTriCount = s->triCount; g.stats.bvhMaxDepth = s->maxDepth;
+  g.currentTriCount = s->triCount;
   return true;
 }
 
