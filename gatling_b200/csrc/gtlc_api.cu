@@ -252,6 +252,9 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
   // world-space triangles for the host builder: one job per (instance, block of faces), filled by the whole team below
   struct FlattenJob { const Mesh* mesh; uint32_t inst, firstFace, lastFace, firstTri; float opacity; float o2w[12]; };
   std::vector<FlattenJob> jobs;
+  uint64_t wanted = 0;
+  for (Mesh* m : s->meshes) if (m->visible && m->material) wanted += (uint64_t) m->faces.size() * (m->instanceTransforms.size() / 12);
+  if (wanted >= 0x80000000ull) { setError("scene flattens to %llu triangles; indices are 32-bit (2^31 at most)", (unsigned long long) wanted); return false; }
   uint32_t rank = 0;
   for (Mesh* m : s->meshes) {
     if (!m->visible) continue;                                          // Gi.cpp:801-804
