@@ -32,6 +32,12 @@ struct Box {
 
 struct BinNode { Box box; uint32_t left, right, first, count, total; };   // count > 0: binary leaf; total = triangles in the subtree
 
+// SAH-optimal collapse to 8-wide nodes (Ylitie, Karras, Laine 2017, section 3.1) as a dynamic programme over the binary
+// tree: cost[i-1] = cheapest way to present this subtree to its parent as at most i children (i = 1..7), each child
+// either a leaf of <= kMaxLeaf triangles or a wide node; split[i-1] = how many of them the left subtree gets (0 = same
+// as with one child fewer); rootSplit / rootIsLeaf describe the subtree as ONE child.
+struct Dp { float cost[7]; uint8_t split[7]; uint8_t rootSplit; uint8_t rootIsLeaf; };
+
 constexpr int kBins = 16;
 constexpr uint32_t kSmallNode = 4;           // nodes up to this size pick their split without bin arrays
 constexpr uint32_t kParallelRange = 262144;   // ranges at least this long are scanned by several tasks
@@ -94,6 +100,7 @@ struct Bounds4 {           // box of the triangles and box of their centroids, a
 struct Builder {
   RawVector<Prim> prims;
   RawVector<BinNode> nodes;
+  RawVector<Dp> dp;                      // filled bottom-up as the recursion unwinds: a node's row right after its children's
 
   // The top of the tree is a handful of huge ranges: their passes are cut into chunks that run as tasks of the team
   // (min / max / counts merge exactly, so the tree does not depend on the chunking).
@@ -244,6 +251,34 @@ struct Builder {
     return begin + trues;
   }
 
+  // the collapse table row of `ni`; both children's rows are complete (post-order)
+  void solveNode(uint32_t ni)
+  {
+    const float INF = 3.402823466e38f;
+    const BinNode& n = nodes[ni];
+    Dp& d = dp[ni];
+    const float area = n.box.area();
+    const float leafCost = (n.total <= kMaxLeaf) ? area * (float) n.total * kTriCost : INF;
+    if (n.count > 0) {                       // binary leaf (single triangle)
+      for (int i = 0; i < 7; i++) { d.cost[i] = leafCost; d.split[i] = 0; }
+      d.rootSplit = 0; d.rootIsLeaf = 1;
+      return;
+    }
+    const Dp& L = dp[n.left]; const Dp& R = dp[n.right];
+    // as one wide node: distribute 8 child slots between the two binary children
+    float best = INF; uint8_t bk = 1;
+    for (int k = 1; k <= 7; k++) { const float c = L.cost[k - 1] + R.cost[8 - k - 1]; if (c < best) { best = c; bk = (uint8_t) k; } }
+    const float internalCost = best + area * kNodeCost;
+    d.rootSplit = bk; d.rootIsLeaf = n.total <= kMaxLeaf && leafCost <= internalCost;
+    d.cost[0] = d.rootIsLeaf ? leafCost : internalCost; d.split[0] = 0;
+    for (int i = 2; i <= 7; i++) {            // as at most i children of the parent
+      float bd = INF; uint8_t bs = 0;
+      for (int k = 1; k < i; k++) { const float c = L.cost[k - 1] + R.cost[i - k - 1]; if (c < bd) { bd = c; bs = (uint8_t) k; } }
+      if (bd < d.cost[i - 2]) { d.cost[i - 1] = bd; d.split[i - 1] = bs; }
+      else { d.cost[i - 1] = d.cost[i - 2]; d.split[i - 1] = 0; }   // 0 = same as with one child fewer
+    }
+  }
+
   // Node ids are the pre-order of the binary tree: every leaf holds one triangle, so the subtree over `c` triangles has
   // exactly 2c - 1 nodes and the right child of `node` sits 2 (mid - begin) after it.  No shared counter, and a subtree is
   // one contiguous block for the collapse and emission passes that walk it afterwards.
@@ -265,6 +300,7 @@ struct Builder {
       build(l, begin, mid, lb);
       build(r, mid, end, rb);
     }
+    solveNode(node);
   }
 
   // `bounds` = box of the triangles in [begin, end) and of their centroids, handed down by whoever partitioned them
@@ -276,7 +312,7 @@ struct Builder {
     BinNode& n = nodes[node];
     n.box = box;
     auto makeLeaf = [&]() { n.first = begin; n.count = count; n.total = count; n.left = n.right = 0; };
-    if (count == 1) { makeLeaf(); return; }
+    if (count == 1) { makeLeaf(); solveNode(node); return; }
 
     float scaleA[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
     bool axisOk[3];
@@ -451,6 +487,7 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
     p.id = (uint32_t) i; p.pad = 0;
   }
   b.nodes.resize((size_t) 2 * N - 1);
+  b.dp.resize((size_t) 2 * N - 1);
 #pragma omp parallel
 #pragma omp single
   {
@@ -459,58 +496,8 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
   }
 
   const auto tBinary = std::chrono::steady_clock::now();
-  // ---- SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1), dynamic programme bottom-up over the
-  // binary tree: cost[n][i-1] = cheapest way to present subtree n to its parent as at most i children
-  // (i = 1..7), each child either a leaf of <= kMaxLeaf triangles or a wide node.  Bottom-up = post-order; the two
-  // subtrees of a big node are independent OpenMP tasks.
   const RawVector<BinNode>& bn = b.nodes;
-  const uint32_t binCount = 2 * N - 1;
-  struct Dp { float cost[7]; uint8_t split[7]; uint8_t rootSplit; uint8_t rootIsLeaf; };
-  RawVector<Dp> dp(binCount);                  // every entry is written by solveNode
-  const float INF = 3.402823466e38f;
-  auto solveNode = [&](uint32_t ni) {
-    const BinNode& n = bn[ni];
-    Dp& d = dp[ni];
-    const float area = n.box.area();
-    const float leafCost = (n.total <= kMaxLeaf) ? area * (float) n.total * kTriCost : INF;
-    if (n.count > 0) {                       // binary leaf (single triangle or coincident centroids)
-      for (int i = 0; i < 7; i++) { d.cost[i] = leafCost; d.split[i] = 0; }
-      d.rootSplit = 0; d.rootIsLeaf = 1;
-      return;
-    }
-    const Dp& L = dp[n.left]; const Dp& R = dp[n.right];
-    // as one wide node: distribute 8 child slots between the two binary children
-    float best = INF; uint8_t bk = 1;
-    for (int k = 1; k <= 7; k++) { const float c = L.cost[k - 1] + R.cost[8 - k - 1]; if (c < best) { best = c; bk = (uint8_t) k; } }
-    const float internalCost = best + area * kNodeCost;
-    d.rootSplit = bk; d.rootIsLeaf = n.total <= kMaxLeaf && leafCost <= internalCost;
-    d.cost[0] = d.rootIsLeaf ? leafCost : internalCost; d.split[0] = 0;
-    for (int i = 2; i <= 7; i++) {            // as at most i children of the parent
-      float bd = INF; uint8_t bs = 0;
-      for (int k = 1; k < i; k++) { const float c = L.cost[k - 1] + R.cost[i - k - 1]; if (c < bd) { bd = c; bs = (uint8_t) k; } }
-      if (bd < d.cost[i - 2]) { d.cost[i - 1] = bd; d.split[i - 1] = bs; }
-      else { d.cost[i - 1] = d.cost[i - 2]; d.split[i - 1] = 0; }   // 0 = same as with one child fewer
-    }
-  };
-  // post-order; big subtrees become OpenMP tasks, small ones run as an explicit-stack walk inside their task
-  auto solveSubtree = [&](auto&& self, uint32_t root) -> void {
-    if (bn[root].count == 0 && bn[root].total > 2 * kTaskRange) {
-#pragma omp task default(shared)
-      self(self, bn[root].left);
-#pragma omp task default(shared)
-      self(self, bn[root].right);
-#pragma omp taskwait
-      solveNode(root);
-      return;
-    }
-    std::vector<uint32_t> order; order.reserve(2 * (size_t) bn[root].total);
-    order.push_back(root);
-    for (size_t h = 0; h < order.size(); h++) { const BinNode& n = bn[order[h]]; if (n.count == 0) { order.push_back(n.left); order.push_back(n.right); } }
-    for (size_t h = order.size(); h-- > 0;) solveNode(order[h]);      // children come after their parent in `order`
-  };
-#pragma omp parallel
-#pragma omp single
-  solveSubtree(solveSubtree, 0u);
+  const RawVector<Dp>& dp = b.dp;
   // expands "subtree `node` as at most `i` children" into the child list
   struct WideChildList { WideChild ch[8]; int n; };
   auto gather = [&](auto&& self, uint32_t node, int i, WideChildList& out) -> void {
@@ -522,7 +509,6 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
     self(self, bn[node].right, i - k, out);
   };
 
-  const auto tDp = std::chrono::steady_clock::now();
   // ---- emission, one level of the wide tree at a time (the same scheme as the device builder): child lists and their
   // sizes in parallel, a prefix sum fixes every node's childBase / triBase, then the nodes are written in parallel.
   // The layout is the breadth-first order a serial queue would produce.
@@ -674,7 +660,7 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
   out.buildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (getenv("GTLC_BUILD_TIMING")) {
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    fprintf(stderr, "[gtlc] host BVH8: binary SAH %.0f ms, collapse table %.0f ms, wide-node emission %.0f ms\n", ms(t0, tBinary), ms(tBinary, tDp), ms(tDp, std::chrono::steady_clock::now()));
+    fprintf(stderr, "[gtlc] host BVH8: binary SAH + collapse table %.0f ms, wide-node emission %.0f ms\n", ms(t0, tBinary), ms(tBinary, std::chrono::steady_clock::now()));
   }
 }
 
