@@ -57,6 +57,11 @@ struct Bvh8 {
 
 struct BuildTri { float v[3][3]; uint32_t prim, inst; float opacity; };   // opacity < 1: stochastic cutout (rp_main.ahit)
 
+// Starts the OpenMP team the builder will use and keeps it busy for a fraction of a millisecond.  Some container
+// schedulers leave freshly created threads on their creator's core for hundreds of milliseconds; a team that was
+// created when the first scene was (long before its first build) has been spread over the cores by then.
+void bvh8_warm_up_threads();
+
 // Builds the BVH8 over `count` world-space triangles.  Deterministic for a given input, whatever the thread count.
 void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out);
 

@@ -456,6 +456,15 @@ inline uint32_t floatExponentBits(float f) { uint32_t u; std::memcpy(&u, &f, 4);
 
 } // namespace
 
+void bvh8_warm_up_threads()
+{
+#pragma omp parallel
+  {
+    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(300);
+    while (std::chrono::steady_clock::now() < until) {}
+  }
+}
+
 void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
 {
   auto t0 = std::chrono::steady_clock::now();

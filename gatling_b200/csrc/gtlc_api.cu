@@ -757,7 +757,12 @@ void gtlc_get_tuning(GtlcTuning* t) { if (t) *t = g.tuning; }
 void gtlc_get_stats(GtlcStats* s) { if (s) *s = g.stats; }
 
 // ---- scene ---------------------------------------------------------------------------------
-GtlcHandle gtlc_scene_create(void) { Scene* s = new Scene(); s->tag = TAG_SCENE; return handleOf(s); }
+GtlcHandle gtlc_scene_create(void)
+{
+  static std::once_flag warm;
+  std::call_once(warm, [] { bvh8_warm_up_threads(); });    // see bvh8.h: the builder's thread team exists before its first build
+  Scene* s = new Scene(); s->tag = TAG_SCENE; return handleOf(s);
+}
 
 void gtlc_scene_destroy(GtlcHandle h)
 {
