@@ -84,7 +84,8 @@ class Stats(C.Structure):
                 ("msTraceAny", C.c_float), ("msShade", C.c_float), ("msRaygen", C.c_float), ("msSort", C.c_float),
                 ("msResolve", C.c_float), ("msBvhBuild", C.c_float), ("bvhNodeCount", C.c_uint32), ("bvhTriCount", C.c_uint32),
                 ("bvhMaxDepth", C.c_uint32), ("maxNodeVisitsPerRay", C.c_uint32), ("nonFiniteRays", C.c_uint64),
-                ("msBvhDeviceBuild", C.c_float), ("reservedStats", C.c_float)]
+                ("msBvhDeviceBuild", C.c_float), ("reservedStats", C.c_float), ("closestHits", C.c_uint64),
+                ("shadowNodeVisits", C.c_uint64), ("shadowTriVisits", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

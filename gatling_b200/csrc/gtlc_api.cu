@@ -122,7 +122,9 @@ struct Scene : Object {
   std::vector<float> hO2W, hW2O; std::vector<InstanceInfo> hInstInfo; std::vector<int2> hInstIds; std::vector<int32_t> hFaceIds; std::vector<uint32_t> hRankBase;
   std::vector<Material*> flatMaterials;
   // device
-  DeviceArray<uint4> dNodes; DeviceArray<float4> dTris; DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;
+  DeviceArray<uint4> dNodes; DeviceArray<float4> dTris;     // canonical BVH8 (bvh8.h): what the builders write and gtlc_scene_get_bvh returns
+  DeviceArray<uint4> dNodesT; DeviceArray<float4> dTrisT;   // traversal layout (traverse.cuh): 96-byte nodes, 64-byte triangles
+  DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;
   DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo; DeviceArray<int2> dInstIds; DeviceArray<int32_t> dFaceIds; DeviceArray<uint32_t> dRankBase;
   DeviceArray<float> dMatParams; DeviceArray<int32_t> dMatClosure; DeviceArray<uint32_t> dMatFlags;
   DeviceArray<DeviceTexture> dTextures; DeviceArray<DeviceTexBinding> dTexBindings; DeviceArray<uint2> dMatTexRange; bool hasTextures = false;
@@ -364,6 +366,25 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
 
 bool buildBvhOnDevice(Scene* s);
 
+// Canonical BVH8 in HBM (host-built and uploaded, or built on the device) -> the layout the traversal kernels read.
+bool repackBvh(Scene* s)
+{
+  cudaStream_t st = g.stream;
+  const uint32_t nodeCount = s->nodeCount, triCount = s->triCount;
+  if (!s->dNodesT.reserve((size_t) std::max(nodeCount, 1u) * 6) || !s->dTrisT.reserve((size_t) std::max(triCount, 1u) * 4)) return false;
+  uint32_t* dErr = &g.counters->repackErrors;
+  CUDA_OK(cudaMemsetAsync(dErr, 0, sizeof(uint32_t), st));
+  if (nodeCount) bvh8_repack_nodes_kernel<<<std::min<uint32_t>((nodeCount + 255u) / 256u, (uint32_t) g.smCount * 16u), 256, 0, st>>>(s->dNodes.ptr, nodeCount, s->dNodesT.ptr, dErr);
+  if (triCount) bvh8_repack_tris_kernel<<<std::min<uint32_t>((triCount + 255u) / 256u, (uint32_t) g.smCount * 16u), 256, 0, st>>>(s->dTris.ptr, triCount, s->dRankBase.ptr, s->dTrisT.ptr);
+  uint32_t errors = 0;
+  CUDA_OK(cudaMemcpyAsync(&errors, dErr, sizeof(errors), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  if (errors) { setError("BVH8 re-pack: %u nodes do not number their triangles in slot order", errors); return false; }
+  g.stats.kernelLaunches += 2;
+  return true;
+}
+
 bool uploadGeometry(Scene* s, bool hostBvh = true)
 {
   cudaStream_t st = g.stream;
@@ -385,6 +406,7 @@ bool uploadGeometry(Scene* s, bool hostBvh = true)
   if (!s->dRankBase.upload(s->hRankBase.data(), s->hRankBase.size(), st)) return false;
   CUDA_OK(cudaStreamSynchronize(st));
   if (!hostBvh && !buildBvhOnDevice(s)) return false;
+  if (!repackBvh(s)) return false;
   s->lastBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return true;
 }
@@ -643,7 +665,7 @@ bool buildPixelMap(Scene* s, uint32_t W, uint32_t H)
 TraceParams makeTraceParams(Scene* s)
 {
   TraceParams P; memset(&P, 0, sizeof(P));
-  P.nodes = s->dNodes.ptr; P.tris = s->dTris.ptr; P.instRankBase = s->dRankBase.ptr; P.biasWord = 0x47000000u;
+  P.nodes = (const uint32_t*) s->dNodesT.ptr; P.tris = (const uint32_t*) s->dTrisT.ptr; P.biasWord = 0x47000000u;
   P.stats = g.counters->stats;
   P.refillThreshold = g.tuning.reserved[0] > 0 ? g.tuning.reserved[0] : kRefillThreshold;
   P.triThreshold = g.tuning.reserved[2] > 0 ? g.tuning.reserved[2] : 8;
@@ -656,7 +678,6 @@ template <int MODE> void launchTrace(const TraceParams& P, bool count, int block
   if (P.aovFlags) { trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // only variant 0 writes the NEE debug AOV
   switch (g.tuning.traceVariant) {
     case 1: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;          // per-lane triangle loop (the order the oracle's walker restates)
-    case 5: trace_kernel_v2<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     case 6: trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
     default:                                                                                    // 0 (default) and 7: warp-batched triangle tests
       // its queue entries pack (owner lane << 27 | triangle index): beyond 2^27 triangles the per-lane kernel takes over
@@ -768,7 +789,7 @@ void gtlc_scene_destroy(GtlcHandle h)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
-  s->dNodes.release(); s->dTris.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
+  s->dNodes.release(); s->dTris.release(); s->dNodesT.release(); s->dTrisT.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
   s->dMatParams.release(); s->dTextures.release(); s->dTexBindings.release(); s->dMatTexRange.release(); s->dPrimvarInfos.release(); s->dPrimvarData.release(); s->dPrimvarBindings.release(); s->dMatPrimvarRange.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
@@ -1301,8 +1322,8 @@ int gtlc_render(const GtlcRenderParams* params)
         timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.q[0], g.counters); });
         int inIdx = 0;
         for (uint32_t bounce = 0; bounce < rs.maxBounces; bounce++) {
-          prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 0); launches++;
           TraceParams P = makeTraceParams(s);
+          P.zeroA = &g.counters->numPaths[inIdx ^ 1]; P.zeroB = &g.counters->numShadow; P.rayStat = &g.counters->stats[0];
           P.rayO = g.q[inIdx].rayO; P.rayD = g.q[inIdx].rayD; P.hitTUVP = g.hitTUVP; P.hitInst = g.hitInst;
           P.numRays = &g.counters->numPaths[inIdx]; P.workCounter = &g.counters->workCounter; P.seedRad = g.q[inIdx].rad;
           timed(K_TRACE, [&] { launchTrace<TRACE_CLOSEST>(P, countVisits, traceBlocks); });
@@ -1331,10 +1352,10 @@ int gtlc_render(const GtlcRenderParams* params)
 #undef GTLC_LAUNCH_SHADE4
           });
           if (rs.nextEventEstimation) {
-            prep_kernel<<<1, 1, 0, g.stream>>>(g.counters, inIdx, 1); launches++;
             TraceParams S = makeTraceParams(s);
+            S.rayStat = &g.counters->stats[3];
             S.rayO = g.shO; S.rayD = g.shD; S.shContrib = g.shC; S.radPath = g.q[inIdx ^ 1].rad; S.radSample = g.sampleRad;
-            S.numRays = &g.counters->numShadow; S.workCounter = &g.counters->workCounter; S.seedU32 = g.shSeed;
+            S.numRays = &g.counters->numShadow; S.workCounter = &g.counters->workCounterShadow; S.seedU32 = g.shSeed;
             if (aovMode && bounce == 0) { S.aovFlags = g.aovSamples.a[0]; S.aovSlotOf = g.q[inIdx ^ 1].slot; }
             timed(K_SHADOW, [&] { launchTrace<TRACE_SHADOW>(S, countVisits, traceBlocks); });
           }
@@ -1371,6 +1392,7 @@ int gtlc_render(const GtlcRenderParams* params)
     g.stats.closestRays = c.stats[0]; g.stats.shadowRays = c.stats[3]; g.stats.nodeVisits = c.stats[1]; g.stats.triVisits = c.stats[2];
     g.stats.kernelLaunches = launches; g.stats.paths = paths;
     g.stats.maxNodeVisitsPerRay = (uint32_t) c.stats[4]; g.stats.nonFiniteRays = c.stats[5];
+    g.stats.closestHits = c.stats[6]; g.stats.shadowNodeVisits = c.stats[7]; g.stats.shadowTriVisits = c.stats[8];
     return true;
   };
   if (!body()) return GTLC_ERROR;

@@ -29,31 +29,71 @@ constexpr float kBoxPad = 1.0000004f;    // Ize 2013 robust slab padding
 
 enum { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_SHADOW = 2 };
 
+// ---- traversal layout of the BVH8 in HBM --------------------------------------------------------------
+// The builders (host SAH, device LBVH / PLOC) and the oracle speak the canonical format of bvh8.h: 80-byte nodes,
+// 48-byte triangles.  bvh8_repack_*_kernel re-packs both once per build into what the traversal kernels read:
+//
+//   node, 96 bytes = 3 x 32-byte sectors, fetched with three 256-bit loads (ld.global.nc.v8 = LDG.E.ENL2.256):
+//     words  0..7 : p.x p.y p.z  valid32 | 2^ex 2^ey 2^ez (as floats)  childBase
+//     words  8..15: triBase  -  | qlo_x[8] qlo_y[8] qlo_z[8]
+//     words 16..23: qhi_x[8] qhi_y[8] qhi_z[8] | -  -
+//   valid32 = imask << 24 | triValid24, bit 3 s + k of triValid24 set iff slot s is a leaf with more than k triangles.
+//   A hit child sets its whole field (bit 24 + s and bits 3 s .. 3 s + 2) with ONE predicated OR of a compile-time
+//   constant; `& valid32` then keeps what exists.  Triangle `b` of the node is triBase + popc(triValid24 below b) --
+//   the canonical builders number a node's triangles in slot order, so this is the canonical index.  Against the
+//   meta-byte decode of the 80-byte node (a variable shift per child) the node step shrinks from ~264 to ~215 SASS
+//   instructions; five 128-bit loads become three 256-bit ones (the L1 data pipe counts wavefronts per load instruction).
+//
+//   triangle, 64 bytes = 2 sectors, never straddling a 128-byte line (a 48-byte record touches 2.5 sectors on average):
+//     (v0.xyz, primitiveId) (v1.xyz, instanceIndex) (v2.xyz, cutout opacity) (rank of (instance, primitive), -, -, -)
+//
+// The algorithmic bytes of SURVEY.md 8d stay 80 per node visit and 48 per triangle test (the padding is not "useful").
+constexpr int kDevNodeWords = 24;
+constexpr int kDevTriWords = 16;
+
 struct TraceParams {
-  const uint4* __restrict__ nodes;      // 5 x uint4 per BVH8 node
-  const float4* __restrict__ tris;      // 3 x float4 per triangle
+  const uint32_t* __restrict__ nodes;   // kDevNodeWords per BVH8 node (traversal layout)
+  const uint32_t* __restrict__ tris;    // kDevTriWords per triangle (traversal layout)
   const float4* __restrict__ rayO;      // (origin.xyz, tMin)
   const float4* __restrict__ rayD;      // (direction.xyz, tMax)
   float4* __restrict__ hitTUVP;         // (t, u, v, bits primitiveId); miss: t = -1
   uint32_t* __restrict__ hitInst;       // instance index; miss: 0xFFFFFFFF
   const uint32_t* __restrict__ numRays; // device-resident queue length
-  uint32_t* workCounter;                // zeroed before the launch
+  uint32_t* workCounter;                // zero at launch (reset by the kernel that ran before: raygen / shade)
   // TRACE_SHADOW epilogue: unoccluded -> target.xyz += contrib
   const float4* __restrict__ shContrib; // (contrib.xyz, bits target): target bit31 = sample slot, else path queue position
   float4* __restrict__ radPath;         // (radiance.xyz, rng) of the continuing paths
   float4* __restrict__ radSample;       // (radiance.xyz, -) of finished samples
   // bookkeeping
-  unsigned long long* stats;            // [1] node visits, [2] triangle tests, [4] max node visits of one ray, [5] non-finite rays
+  unsigned long long* stats;            // COUNT only: [1] node visits, [2] triangle tests of closest / any rays, [7], [8] the same of shadow rays, [4] max node visits of one ray, [6] closest hits; always: [5] non-finite rays
   uint32_t* visitsPerRay;               // optional 2 x uint32 per ray
   int refillThreshold;                  // idle lanes that trigger a refill (kRefillThreshold by default)
-  int triThreshold;                     // variant 5: lanes with pending triangles that trigger a triangle phase
+  int triThreshold;                     // unused (was variant 5)
   const float4* __restrict__ seedRad;   // cutout any-hit: per-ray RNG seed = bits of seedRad[i].w (path queue `rad`), or
   const uint32_t* __restrict__ seedU32; //   seedU32[i] (shadow queue); both NULL = seed 0
   uint32_t biasWord;                           // 0x47000000 (see biased_byte)
-  float4* aovFlags;                            // NEE debug AOV (first bounce, variant 0 only): per-sample capture word a[0]; bit 3 of .w = shadow ray occluded
+  float4* aovFlags;                            // NEE debug AOV (first bounce, per-lane kernel only): per-sample capture word a[0]; bit 3 of .w = shadow ray occluded
   const uint32_t* __restrict__ aovSlotOf;      //   sample slot of a continuing path (path queue `slot`)
-  const uint32_t* __restrict__ instRankBase;   // variant 7: first global (instance, primitive)-ordered triangle rank of every instance
+  // Launch prologue (thread 0 of CTA 0), the wave loop's per-bounce bookkeeping folded into the kernel that needs it --
+  // nothing in this kernel reads what it writes:  *zeroA = 0, *zeroB = 0, *rayStat += *numRays.
+  uint32_t* zeroA; uint32_t* zeroB; unsigned long long* rayStat;
 };
+
+GTLC_D void trace_prologue(const TraceParams& P)
+{
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (P.zeroA) *P.zeroA = 0u;
+    if (P.zeroB) *P.zeroB = 0u;
+    if (P.rayStat) *P.rayStat += (unsigned long long) *P.numRays;
+  }
+}
+
+// 256-bit read-only load (sm_100: one LDG.E.ENL2.256.CONSTANT); `p` must be 32-byte aligned.
+GTLC_D void ldg256(const uint32_t* p, uint32_t (&v)[8])
+{
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
 
 // Quantised byte q (0..255) taken from byte `j` of `w`, as the float 32768 + q: one PRMT builds
 // 0x4700qq00 (exponent 2^15, q in mantissa bits 8..15), no integer->float conversion pipe involved.
@@ -73,10 +113,11 @@ GTLC_D bool ray_is_finite(float4 ro, float4 rd)
 }
 
 struct RaySetup {
-  V3 o, d;
+  V3 o;
   float tmin;
   V3 idir;
-  uint32_t octinv;
+  uint32_t octinv;          // 7 - octant; bit k clear <=> direction component k is negative
+  uint32_t pm1, pm2, pm4;   // delta-swap masks (top byte) that move hit bit 24 + s to 24 + (s ^ octinv)
   // Woop shear as three sparse basis vectors: mx = e_kx - Sx e_kz, my = e_ky - Sy e_kz, mz = Sz e_kz, so that
   // the per-triangle code needs no data-dependent component selection (same definition in the CPU oracle).
   V3 mx, my, mz;
@@ -84,24 +125,28 @@ struct RaySetup {
 
 GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
 {
-  r.o = v3(ro.x, ro.y, ro.z); r.d = v3(rd.x, rd.y, rd.z); r.tmin = ro.w;
+  const V3 d = v3(rd.x, rd.y, rd.z);
+  r.o = v3(ro.x, ro.y, ro.z); r.tmin = ro.w;
   // |d| is clamped to 2^-80 for the slab tests only (Ylitie et al. 2017): with an exactly-zero or denormal
   // component 1/d = inf turns the quantised slab arithmetic q*s + o into inf - inf = NaN, the NaN-dropping
   // min/max then never cull along that axis and the ray walks a whole slice of the tree.
   const float kMinDir = 8.271806125530277e-25f;   // 2^-80
-  r.idir = v3(1.0f / (fabsf(r.d.x) > kMinDir ? r.d.x : copysignf(kMinDir, r.d.x)),
-              1.0f / (fabsf(r.d.y) > kMinDir ? r.d.y : copysignf(kMinDir, r.d.y)),
-              1.0f / (fabsf(r.d.z) > kMinDir ? r.d.z : copysignf(kMinDir, r.d.z)));
-  uint32_t oct = (r.d.x < 0.0f ? 1u : 0u) | (r.d.y < 0.0f ? 2u : 0u) | (r.d.z < 0.0f ? 4u : 0u);
+  r.idir = v3(1.0f / (fabsf(d.x) > kMinDir ? d.x : copysignf(kMinDir, d.x)),
+              1.0f / (fabsf(d.y) > kMinDir ? d.y : copysignf(kMinDir, d.y)),
+              1.0f / (fabsf(d.z) > kMinDir ? d.z : copysignf(kMinDir, d.z)));
+  uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
   r.octinv = 7u - oct;
-  float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
+  r.pm1 = (r.octinv & 1u) ? 0x55000000u : 0u;
+  r.pm2 = (r.octinv & 2u) ? 0x33000000u : 0u;
+  r.pm4 = (r.octinv & 4u) ? 0x0F000000u : 0u;
+  float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
   int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
   int kx = kz + 1; if (kx == 3) kx = 0;
   int ky = kx + 1; if (ky == 3) ky = 0;
-  if (comp(r.d, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
+  if (comp(d, kz) < 0.0f) { int t = kx; kx = ky; ky = t; }
   const float Sz = comp(r.idir, kz);          // = 1 / d[kz] exactly (the dominant component is never clamped): no extra division
-  const float Sx = comp(r.d, kx) * Sz;
-  const float Sy = comp(r.d, ky) * Sz;
+  const float Sx = comp(d, kx) * Sz;
+  const float Sy = comp(d, ky) * Sz;
   r.mx = v3(kx == 0 ? 1.0f : (kz == 0 ? -Sx : 0.0f), kx == 1 ? 1.0f : (kz == 1 ? -Sx : 0.0f), kx == 2 ? 1.0f : (kz == 2 ? -Sx : 0.0f));
   r.my = v3(ky == 0 ? 1.0f : (kz == 0 ? -Sy : 0.0f), ky == 1 ? 1.0f : (kz == 1 ? -Sy : 0.0f), ky == 2 ? 1.0f : (kz == 2 ? -Sy : 0.0f));
   r.mz = v3(kz == 0 ? Sz : 0.0f, kz == 1 ? Sz : 0.0f, kz == 2 ? Sz : 0.0f);
@@ -162,32 +207,34 @@ GTLC_D bool tri_intersect(const RaySetup& r, V3 p0, V3 p1, V3 p2, float& t, floa
   return true;
 }
 
-// Slab-tests the 8 quantised child boxes of one node; returns the 32-bit hit mask
-// (bits 31..24: internal children in traversal priority order, bits 23..0: triangles).
-// t = (32768 + q) * s + (o - 32768 s) with s = 2^e / d, o = (p - origin) / d; branch-free.
-GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4,
-                             const RaySetup& r, float tbest, uint32_t k47)
+// One BVH8 node in registers (three 256-bit loads) and its slab test.
+struct NodeRegs { uint32_t a[8], b[8], c[8]; };
+
+GTLC_D void node_fetch(const uint32_t* __restrict__ nodes, uint32_t node, NodeRegs& n)
 {
-  const uint32_t e = n0.w;
-  const float sx = u2f((e & 0xFFu) << 23) * r.idir.x;
-  const float sy = u2f(((e >> 8) & 0xFFu) << 23) * r.idir.y;
-  const float sz = u2f(((e >> 16) & 0xFFu) << 23) * r.idir.z;
-  const float ox = (u2f(n0.x) - r.o.x) * r.idir.x - 32768.0f * sx;
-  const float oy = (u2f(n0.y) - r.o.y) * r.idir.y - 32768.0f * sy;
-  const float oz = (u2f(n0.z) - r.o.z) * r.idir.z - 32768.0f * sz;
-  const bool nx = r.d.x < 0.0f, ny = r.d.y < 0.0f, nz = r.d.z < 0.0f;
-  const uint32_t octinv4 = r.octinv * 0x01010101u;
-  uint32_t hitmask = 0;
+  const uint32_t* p = nodes + (size_t) node * kDevNodeWords;
+  ldg256(p, n.a); ldg256(p + 8, n.b); ldg256(p + 16, n.c);
+}
+
+// Slab-tests the 8 quantised child boxes of one node; returns the 32-bit hit mask
+// (bits 31..24: hit internal children in traversal priority order, bit 24 + (slot ^ octinv); bits 23..0: the
+// triangle fields 3 slot + k of hit leaf children).
+// t = (32768 + q) * s + (o - 32768 s) with s = 2^e / d, o = (p - origin) / d; branch-free.  Same arithmetic, in the
+// same order, as the oracle's walk of the canonical node (oracle/orc_bvh8.h: bvh8_node_hitmask).
+GTLC_D uint32_t node_hitmask(const NodeRegs& n, const RaySetup& r, float tbest, uint32_t k47)
+{
+  const float sx = u2f(n.a[4]) * r.idir.x;
+  const float sy = u2f(n.a[5]) * r.idir.y;
+  const float sz = u2f(n.a[6]) * r.idir.z;
+  const float ox = (u2f(n.a[0]) - r.o.x) * r.idir.x - 32768.0f * sx;
+  const float oy = (u2f(n.a[1]) - r.o.y) * r.idir.y - 32768.0f * sy;
+  const float oz = (u2f(n.a[2]) - r.o.z) * r.idir.z - 32768.0f * sz;
+  const bool nx = (r.octinv & 1u) == 0u, ny = (r.octinv & 2u) == 0u, nz = (r.octinv & 4u) == 0u;   // direction component negative
+  uint32_t hm = 0;
 #pragma unroll
   for (int half = 0; half < 2; half++) {
-    const uint32_t meta4 = half ? n1.w : n1.z;
-    // word-level decode of the 4 meta bytes (Ylitie et al. 2017, listing 2)
-    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;          // bit 4 set iff low5 >= 24
-    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;                     // 0xFF in every internal-child byte
-    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-    const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
-    const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+    const uint32_t qlox = n.b[2 + half], qloy = n.b[4 + half], qloz = n.b[6 + half];
+    const uint32_t qhix = n.c[0 + half], qhiy = n.c[2 + half], qhiz = n.c[4 + half];
     const uint32_t nearx = nx ? qhix : qlox, farx = nx ? qlox : qhix;
     const uint32_t neary = ny ? qhiy : qloy, fary = ny ? qloy : qhiy;
     const uint32_t nearz = nz ? qhiz : qloz, farz = nz ? qloz : qhiz;
@@ -202,13 +249,85 @@ GTLC_D uint32_t node_hitmask(const uint4 n0, const uint4 n1, const uint4 n2, con
       const float tfz = fmaf(biased_byte(farz, k47, sel), sz, oz);
       const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
       const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest)) * kBoxPad;
-      const uint32_t bits = __byte_perm(child_bits4, 0u, 0x4440u | (uint32_t) j);
-      const uint32_t idx = (bit_index4 >> (8 * j)) & 0xFFu;
-      hitmask |= (tn <= tf) ? (bits << idx) : 0u;
+      const int s = 4 * half + j;
+      if (tn <= tf) hm |= (1u << (24 + s)) | (7u << (3 * s));      // one predicated OR of an immediate
     }
   }
-  return hitmask;
+  hm &= n.a[3];
+  // internal hits: slot order -> traversal priority order, bit 24 + s -> 24 + (s ^ octinv): three delta swaps whose masks
+  // are zero for the octant bits that are clear (the triangle bits below bit 24 never pass a mask)
+  uint32_t t;
+  t = (hm ^ (hm >> 1)) & r.pm1; hm ^= t ^ (t << 1);
+  t = (hm ^ (hm >> 2)) & r.pm2; hm ^= t ^ (t << 2);
+  t = (hm ^ (hm >> 4)) & r.pm4; hm ^= t ^ (t << 4);
+  return hm;
 }
+
+// Index of triangle bit `b` (0..23) of a node: the canonical builders store a node's triangles in slot order.
+GTLC_D uint32_t tri_index(uint32_t triBase, uint32_t valid32, uint32_t b) { return triBase + (uint32_t) __popc(valid32 & ~(0xFFFFFFFFu << b)); }
+
+struct TriRegs { uint32_t a[8], b[8]; };
+GTLC_D void tri_fetch(const uint32_t* __restrict__ tris, uint32_t tri, TriRegs& t)
+{
+  const uint32_t* p = tris + (size_t) tri * kDevTriWords;
+  ldg256(p, t.a); ldg256(p + 8, t.b);
+}
+
+// ---- re-packing kernels: canonical (bvh8.h) -> traversal layout -----------------------------------------
+__global__ void __launch_bounds__(256) bvh8_repack_nodes_kernel(const uint4* __restrict__ canon, uint32_t nodeCount, uint4* __restrict__ out, uint32_t* __restrict__ errors)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nodeCount; i += gridDim.x * blockDim.x) {
+    const uint4 n0 = canon[(size_t) i * 5 + 0], n1 = canon[(size_t) i * 5 + 1], n2 = canon[(size_t) i * 5 + 2], n3 = canon[(size_t) i * 5 + 3], n4 = canon[(size_t) i * 5 + 4];
+    const uint32_t imask = n0.w >> 24;
+    uint32_t valid = imask << 24, running = 0;
+    bool bad = false;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      const uint32_t m = ((s < 4 ? n1.z : n1.w) >> (8 * (s & 3))) & 0xFFu;
+      if (m == 0u) { if (imask & (1u << s)) bad = true; continue; }
+      if (imask & (1u << s)) { if (m != (0x20u | (24u + (uint32_t) s))) bad = true; continue; }
+      const uint32_t cnt = (uint32_t) __popc(m >> 5), off = m & 31u;
+      if (off != running || cnt > 3u || (m >> 5) != ((1u << cnt) - 1u)) bad = true;     // triangles in slot order, unary counts
+      valid |= ((1u << cnt) - 1u) << (3 * s);
+      running += cnt;
+    }
+    if (bad) atomicAdd(errors, 1u);
+    uint4* o = out + (size_t) i * 6;
+    o[0] = make_uint4(n0.x, n0.y, n0.z, valid);
+    o[1] = make_uint4((n0.w & 0xFFu) << 23, ((n0.w >> 8) & 0xFFu) << 23, ((n0.w >> 16) & 0xFFu) << 23, n1.x);
+    o[2] = make_uint4(n1.y, 0u, n2.x, n2.y);        // triBase, -, qlo_x
+    o[3] = make_uint4(n2.z, n2.w, n3.x, n3.y);      // qlo_y, qlo_z
+    o[4] = make_uint4(n3.z, n3.w, n4.x, n4.y);      // qhi_x, qhi_y
+    o[5] = make_uint4(n4.z, n4.w, 0u, 0u);          // qhi_z
+  }
+}
+
+__global__ void __launch_bounds__(256) bvh8_repack_tris_kernel(const float4* __restrict__ canon, uint32_t triCount, const uint32_t* __restrict__ instRankBase, float4* __restrict__ out)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < triCount; i += gridDim.x * blockDim.x) {
+    const float4 a = canon[(size_t) i * 3 + 0], b = canon[(size_t) i * 3 + 1], c = canon[(size_t) i * 3 + 2];
+    float4* o = out + (size_t) i * 4;
+    o[0] = a; o[1] = b; o[2] = c;
+    o[3] = make_float4(u2f(instRankBase[f2u(b.w)] + f2u(a.w)), 0.0f, 0.0f, 0.0f);   // rank of (instance, primitive): the closest-hit tie-break
+  }
+}
+
+// The shared body of "one node step": pops the next child of the lane's current node group G (deferring the siblings),
+// fetches and slab-tests it.  Returns the new group in G and the node's triangle hits in (triBase, triMask, valid).
+#define GTLC_NODE_STEP(G, stack, sp, r, bt, k47, triBase, triMask, triValid)                                  \
+  do {                                                                                                         \
+    const uint32_t hits_imask = G.y;                                                                           \
+    const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);                                                   \
+    G.y &= ~(1u << bit);                                                                                       \
+    if (G.y & 0xFF000000u) stack[sp++] = G;                                                                    \
+    const uint32_t slot = (bit - 24u) ^ r.octinv;                                                              \
+    const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));                               \
+    NodeRegs nr;                                                                                               \
+    node_fetch(P.nodes, G.x + rel, nr);                                                                        \
+    const uint32_t hm = node_hitmask(nr, r, bt, k47);                                                          \
+    G = make_uint2(nr.a[7], (hm & 0xFF000000u) | (nr.a[3] >> 24));                                             \
+    triBase = nr.b[0]; triMask = hm & 0x00FFFFFFu; triValid = nr.a[3];                                         \
+  } while (0)
 
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kernel(TraceParams P)
@@ -217,6 +336,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
   const int lane = threadIdx.x & 31;
   const uint32_t n = *P.numRays;
   const uint32_t k47 = P.biasWord;
+  trace_prologue(P);
 
   uint2 stack[kStackSize];
   int sp = 0;
@@ -265,35 +385,22 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
     // ---- traversal steps until enough lanes went idle ------------------------------------------
     while (true) {
       if (active) {
-        uint2 T;
+        uint32_t triBase = 0, triMask = 0, triValid = 0;
         if (G.y & 0xFF000000u) {
-          const uint32_t hits_imask = G.y;
-          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
-          G.y &= ~(1u << bit);
-          if (G.y & 0xFF000000u) stack[sp++] = G;
-          const uint32_t slot = (bit - 24u) ^ r.octinv;
-          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
-          const uint32_t node = G.x + rel;
-          const uint4* np = P.nodes + (size_t) node * 5;
-          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          GTLC_NODE_STEP(G, stack, sp, r, bt, k47, triBase, triMask, triValid);
           if (COUNT) cNodes++;
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
-          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-          T = make_uint2(n1.y, hm & 0x00FFFFFFu);
-        } else {
-          T = make_uint2(0u, 0u);
         }
         bool done = false;
-        while (T.y) {
-          const uint32_t j = (uint32_t) __ffs(T.y) - 1u;
-          T.y &= T.y - 1u;
-          const float4* tp = P.tris + (size_t) (T.x + j) * 3;
-          const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        while (triMask) {
+          const uint32_t j = (uint32_t) __ffs(triMask) - 1u;
+          triMask &= triMask - 1u;
+          TriRegs tr;
+          tri_fetch(P.tris, tri_index(triBase, triValid, j), tr);
           if (COUNT) cTris++;
           float t, u, v;
-          if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
-              const uint32_t prim = f2u(a.w), inst = f2u(b.w);
+          if (tri_intersect(r, v3(u2f(tr.a[0]), u2f(tr.a[1]), u2f(tr.a[2])), v3(u2f(tr.a[4]), u2f(tr.a[5]), u2f(tr.a[6])), v3(u2f(tr.b[0]), u2f(tr.b[1]), u2f(tr.b[2])), t, u, v)) {
+            const uint32_t prim = tr.a[3], inst = tr.a[7];
+            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, u2f(tr.b[3]), prim, inst)) {
               if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
               const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
               if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
@@ -326,137 +433,14 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
             if (P.hitInst) P.hitInst[rayIdx] = binst;
           }
           if (COUNT) {
-            atomicAdd(&P.stats[1], (unsigned long long) cNodes);
-            atomicAdd(&P.stats[2], (unsigned long long) cTris);
+            atomicAdd(&P.stats[MODE == TRACE_SHADOW ? 7 : 1], (unsigned long long) cNodes);
+            atomicAdd(&P.stats[MODE == TRACE_SHADOW ? 8 : 2], (unsigned long long) cTris);
             atomicMax(&P.stats[4], (unsigned long long) cNodes);
+            if (MODE == TRACE_CLOSEST && hit) atomicAdd(&P.stats[6], 1ull);
             if (P.visitsPerRay) { P.visitsPerRay[2 * (size_t) rayIdx] = cNodes; P.visitsPerRay[2 * (size_t) rayIdx + 1] = cTris; }
           }
           active = false;
         }
-      }
-      const unsigned idle = __ballot_sync(FULL, !active);
-      if (idle == FULL) break;
-      if (!exhausted && __popc(idle) >= P.refillThreshold) break;
-    }
-  }
-}
-
-// ---- variant 5: two-deep pending-triangle FIFO ------------------------------------------------------
-// A lane keeps up to two triangle groups (T0, T1) in registers and goes on with node steps while it has
-// room; the warp enters a triangle phase only when >= triThreshold lanes have triangles pending or nobody
-// can make progress on nodes.  Culling is delayed by at most one node step per lane (unlike variant 1,
-// which parks triangle groups on the stack indefinitely).  Hits are identical to variant 0.
-template <int MODE>
-__global__ void __launch_bounds__(kTraceBlock) trace_kernel_v2(TraceParams P)
-{
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const uint32_t n = *P.numRays;
-  const uint32_t k47 = P.biasWord;
-  const int triThr = P.triThreshold;
-
-  uint2 stack[kStackSize];
-  int sp = 0;
-  bool active = false;
-  bool exhausted = false;
-  uint32_t rayIdx = 0;
-  RaySetup r;
-  float bt = 0.0f, bu = 0.0f, bv = 0.0f; uint32_t bprim = 0xFFFFFFFFu, binst = 0xFFFFFFFFu;
-  float tmax = 0.0f;
-  uint2 G = make_uint2(0u, 0u), T0 = make_uint2(0u, 0u), T1 = make_uint2(0u, 0u);
-
-  while (true) {
-    if (!exhausted) {
-      const unsigned need = __ballot_sync(FULL, !active);
-      if (need) {
-        const int leader = __ffs(need) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(P.workCounter, (uint32_t) __popc(need));
-        base = __shfl_sync(FULL, base, leader);
-        if (!active) {
-          rayIdx = base + (uint32_t) __popc(need & ((1u << lane) - 1u));
-          if (rayIdx < n) {
-            const float4 ro = __ldg(&P.rayO[rayIdx]);
-            const float4 rd = __ldg(&P.rayD[rayIdx]);
-            ray_setup(r, ro, rd);
-            tmax = rd.w;
-            bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
-            sp = 0;
-            active = tmax > r.tmin;
-            if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
-            G = make_uint2(0u, 0x80000000u); T0 = make_uint2(0u, 0u); T1 = make_uint2(0u, 0u);
-            if (!active && MODE != TRACE_SHADOW) { P.hitTUVP[rayIdx] = make_float4(-1.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu)); if (P.hitInst) P.hitInst[rayIdx] = 0xFFFFFFFFu; }
-          }
-        }
-        if (base + (uint32_t) __popc(need) >= n) exhausted = true;
-      }
-    }
-    if (!__any_sync(FULL, active)) { if (exhausted) break; else continue; }
-
-    while (true) {
-      bool done = false;
-      // ---- A: one node step for every lane that has node work and room for its triangles ----
-      if (active && T1.y == 0u) {
-        if (!(G.y & 0xFF000000u) && sp > 0) G = stack[--sp];
-        if (G.y & 0xFF000000u) {
-          const uint32_t hits_imask = G.y;
-          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
-          G.y &= ~(1u << bit);
-          if (G.y & 0xFF000000u) stack[sp++] = G;
-          const uint32_t slot = (bit - 24u) ^ r.octinv;
-          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
-          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
-          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
-          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-          const uint2 Tn = make_uint2(n1.y, hm & 0x00FFFFFFu);
-          if (Tn.y) { if (T0.y == 0u) T0 = Tn; else T1 = Tn; }
-        }
-      }
-      // ---- B: triangle phase when enough lanes wait for it, or when nothing else can progress ----
-      const bool canNode = active && T1.y == 0u && ((G.y & 0xFF000000u) != 0u || sp > 0);
-      unsigned pendMask = __ballot_sync(FULL, active && T0.y != 0u);
-      const unsigned nodeMask = __ballot_sync(FULL, canNode);
-      if (pendMask && (__popc(pendMask) >= triThr || nodeMask == 0u)) {
-        do {
-          if (active && !done && T0.y != 0u) {
-            const uint32_t j = (uint32_t) __ffs(T0.y) - 1u;
-            T0.y &= T0.y - 1u;
-            const float4* tp = P.tris + (size_t) (T0.x + j) * 3;
-            const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            float t, u, v;
-            if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-              if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
-                const uint32_t prim = f2u(a.w), inst = f2u(b.w);
-                if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; }
-                else {
-                  const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
-                  if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
-                }
-              }
-            }
-            if (T0.y == 0u) { T0 = T1; T1 = make_uint2(0u, 0u); }
-          }
-          pendMask = __ballot_sync(FULL, active && !done && T0.y != 0u);
-        } while (pendMask);
-      }
-      if (active && !done && T0.y == 0u && !(G.y & 0xFF000000u) && sp == 0) done = true;
-      if (done) {
-        const bool hit = bprim != 0xFFFFFFFFu;
-        if (MODE == TRACE_SHADOW) {
-          if (!hit) {
-            const float4 c = __ldg(&P.shContrib[rayIdx]);
-            const uint32_t target = f2u(c.w);
-            float4* dst = (target & 0x80000000u) ? (P.radSample + (target & 0x7FFFFFFFu)) : (P.radPath + target);
-            float4 cur = *dst;
-            cur.x += c.x; cur.y += c.y; cur.z += c.z;
-            *dst = cur;
-          }
-        } else {
-          P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
-          if (P.hitInst) P.hitInst[rayIdx] = binst;
-        }
-        active = false;
       }
       const unsigned idle = __ballot_sync(FULL, !active);
       if (idle == FULL) break;
@@ -470,7 +454,7 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel_v2(TraceParams P)
 // the next 32 rays of the SoA queue with one atomic and issues two `cp.async.bulk` (TMA, 1-D) copies that
 // complete on an mbarrier; while the warp traverses, the following tile is already in flight, so a refill
 // reads its rays from shared memory instead of waiting for an HBM round trip with the whole warp stalled.
-// Traversal itself is variant 0.
+// Traversal itself is the per-lane loop above.
 GTLC_D uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
 GTLC_D void mbar_wait(uint32_t bar, uint32_t parity)
@@ -496,6 +480,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n = *P.numRays;
   const uint32_t k47 = P.biasWord;
+  trace_prologue(P);
 
   // claims the next tile and starts its copy into `stage`; returns (base, count) to the whole warp
   auto issue = [&](int stage, uint32_t& base, uint32_t& cnt) {
@@ -584,32 +569,18 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
 
     while (true) {
       if (active) {
-        uint2 T;
-        if (G.y & 0xFF000000u) {
-          const uint32_t hits_imask = G.y;
-          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
-          G.y &= ~(1u << bit);
-          if (G.y & 0xFF000000u) stack[sp++] = G;
-          const uint32_t slot = (bit - 24u) ^ r.octinv;
-          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
-          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
-          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
-          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-          T = make_uint2(n1.y, hm & 0x00FFFFFFu);
-        } else {
-          T = make_uint2(0u, 0u);
-        }
+        uint32_t triBase = 0, triMask = 0, triValid = 0;
+        if (G.y & 0xFF000000u) GTLC_NODE_STEP(G, stack, sp, r, bt, k47, triBase, triMask, triValid);
         bool done = false;
-        while (T.y) {
-          const uint32_t j = (uint32_t) __ffs(T.y) - 1u;
-          T.y &= T.y - 1u;
-          const float4* tp = P.tris + (size_t) (T.x + j) * 3;
-          const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        while (triMask) {
+          const uint32_t j = (uint32_t) __ffs(triMask) - 1u;
+          triMask &= triMask - 1u;
+          TriRegs tr;
+          tri_fetch(P.tris, tri_index(triBase, triValid, j), tr);
           float t, u, v;
-          if (tri_intersect(r, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, c.w, f2u(a.w), f2u(b.w))) {
-              const uint32_t prim = f2u(a.w), inst = f2u(b.w);
+          if (tri_intersect(r, v3(u2f(tr.a[0]), u2f(tr.a[1]), u2f(tr.a[2])), v3(u2f(tr.a[4]), u2f(tr.a[5]), u2f(tr.a[6])), v3(u2f(tr.b[0]), u2f(tr.b[1]), u2f(tr.b[2])), t, u, v)) {
+            const uint32_t prim = tr.a[3], inst = tr.a[7];
+            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, u2f(tr.b[3]), prim, inst)) {
               if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
               const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
               if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
@@ -645,14 +616,14 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
   }
 }
 
-// ---- variant 7: warp-cooperative batched triangle tests ----------------------------------------------
-// The per-lane triangle loop of variant 0 runs with ~3 of 32 lanes active and was 37 % of all issued
+// ---- variant 7 (default): warp-cooperative batched triangle tests ---------------------------------------
+// The per-lane triangle loop above runs with ~3 of 32 lanes active and was 37 % of all issued
 // instructions.  Here a lane only APPENDS the triangles its node step found to a per-warp queue in shared
 // memory ((owner lane << 27) | triangle index) and goes on traversing; once the queue holds >= 32 entries (or
 // nobody has node work left) the whole warp drains it 32 tests at a time: lane L tests entry L against the
 // OWNER's ray, whose origin / shear basis / interval live in shared memory, and publishes a hit with one 64-bit
 // shared-memory atomicMin on (t bits << 32 | (instance, primitive) rank) -- the same closest-hit order as
-// variant 0, so results are bit-identical.  Culling sees a new t a few node steps late (measured on the CPU
+// the per-lane loop, so results are bit-identical.  Culling sees a new t a few node steps late (measured on the CPU
 // walker: +2.5 % node visits per step of delay), which the 32-wide triangle tests more than pay for.
 constexpr int kBatchQueueCap = 832;   // 31 left-overs + 32 lanes x 24 triangles of one node step, rounded up
 
@@ -670,6 +641,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t n = *P.numRays;
   const uint32_t k47 = P.biasWord;
+  trace_prologue(P);
 
   uint2 stack[kStackSize];
   int sp = 0;
@@ -720,22 +692,10 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
 
     while (true) {
       // ---- A: one node step per lane with node work; its triangles go to the warp queue ----
-      uint32_t triBase = 0, triMask = 0;
+      uint32_t triBase = 0, triMask = 0, triValid = 0;
       if (active) {
         if (!(G.y & 0xFF000000u) && sp > 0) G = stack[--sp];
-        if (G.y & 0xFF000000u) {
-          const uint32_t hits_imask = G.y;
-          const uint32_t bit = 31u - (uint32_t) __clz(hits_imask);
-          G.y &= ~(1u << bit);
-          if (G.y & 0xFF000000u) stack[sp++] = G;
-          const uint32_t slot = (bit - 24u) ^ r.octinv;
-          const uint32_t rel = (uint32_t) __popc(hits_imask & ~(0xFFFFFFFFu << slot));
-          const uint4* np = P.nodes + (size_t) (G.x + rel) * 5;
-          const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          const uint32_t hm = node_hitmask(n0, n1, n2, n3, n4, r, bt, k47);
-          G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-          triBase = n1.y; triMask = hm & 0x00FFFFFFu;
-        }
+        if (G.y & 0xFF000000u) GTLC_NODE_STEP(G, stack, sp, r, bt, k47, triBase, triMask, triValid);
       }
       // enqueue, one triangle per lane per round (owners interleave in the queue)
       unsigned have = __ballot_sync(FULL, triMask != 0u);
@@ -743,7 +703,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
         if (triMask) {
           const uint32_t j = (uint32_t) __ffs(triMask) - 1u;
           triMask &= triMask - 1u;
-          sQueue[w][qCount + (uint32_t) __popc(have & ((1u << lane) - 1u))] = ((uint32_t) lane << 27) | (triBase + j);
+          sQueue[w][qCount + (uint32_t) __popc(have & ((1u << lane) - 1u))] = ((uint32_t) lane << 27) | tri_index(triBase, triValid, j);
           pending = true;
         }
         qCount += (uint32_t) __popc(have);
@@ -759,16 +719,16 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
           if (qi < qCount) {
             const uint32_t e = sQueue[w][qi];
             owner = e >> 27;
-            const float4* tp = P.tris + (size_t) (e & 0x07FFFFFFu) * 3;
-            const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            TriRegs tr;
+            tri_fetch(P.tris, e & 0x07FFFFFFu, tr);
             const float4 r0 = sRay[w][0][owner], r1 = sRay[w][1][owner], r2 = sRay[w][2][owner], r3 = sRay[w][3][owner];
             RaySetup q;
             q.o = v3(r0.x, r0.y, r0.z); q.mx = v3(r1.x, r1.y, r1.z); q.my = v3(r2.x, r2.y, r2.z); q.mz = v3(r3.x, r3.y, r3.z);
             float t, u, v;
-            if (tri_intersect(q, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), t, u, v)) {
-              hprim = f2u(a.w); hinst = f2u(b.w);
-              if (t > r0.w && t < r1.w && !cutout_ignored(P, f2u(r2.w), c.w, hprim, hinst)) {
-                key = ((unsigned long long) f2u(t) << 32) | (unsigned long long) (__ldg(&P.instRankBase[hinst]) + hprim);
+            if (tri_intersect(q, v3(u2f(tr.a[0]), u2f(tr.a[1]), u2f(tr.a[2])), v3(u2f(tr.a[4]), u2f(tr.a[5]), u2f(tr.a[6])), v3(u2f(tr.b[0]), u2f(tr.b[1]), u2f(tr.b[2])), t, u, v)) {
+              hprim = tr.a[3]; hinst = tr.a[7];
+              if (t > r0.w && t < r1.w && !cutout_ignored(P, f2u(r2.w), u2f(tr.b[3]), hprim, hinst)) {
+                key = ((unsigned long long) f2u(t) << 32) | (unsigned long long) tr.b[4];
                 won = key < atomicMin(&sKey[w][owner], key);
                 hu = u; hv = v;
               }

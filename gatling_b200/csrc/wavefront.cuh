@@ -105,8 +105,10 @@ struct AovSampleBuffers { float4* a[6]; };
 struct Counters {          // device-resident
   uint32_t numPaths[2];    // path-queue lengths (double buffered)
   uint32_t numShadow;
-  uint32_t workCounter;
-  unsigned long long stats[6];  // [0] closest rays, [1] node visits, [2] tri tests, [3] shadow rays, [4] max node visits of one ray, [5] non-finite rays
+  uint32_t workCounter;         // ray fetch counter of trace_closest: zeroed by raygen / the shade kernel in front of it
+  uint32_t workCounterShadow;   // ... of trace_shadow: zeroed by the shade kernel in front of it
+  uint32_t repackErrors;        // bvh8_repack_nodes_kernel
+  unsigned long long stats[10]; // [0] closest rays, [1] node visits, [2] tri tests (closest), [3] shadow rays, [4] max node visits of one ray, [5] non-finite rays; counting pass: [6] closest hits, [7] node visits, [8] tri tests (shadow)
 };
 
 // ---- rp_main.rgen:118-130 ---------------------------------------------------------------------
@@ -180,20 +182,12 @@ __global__ void __launch_bounds__(256) raygen_kernel(UniformData ubo, WaveParams
     q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(rng_state));        // :276-277
     q.slot[slot] = slot;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->numPaths[0] = total; ctr->numPaths[1] = 0; ctr->numShadow = 0; ctr->workCounter = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->numPaths[0] = total; ctr->numPaths[1] = 0; ctr->numShadow = 0; ctr->workCounter = 0; ctr->workCounterShadow = 0; }
 }
 
-// Resets the per-bounce counters and accumulates ray statistics (one thread).
-__global__ void prep_kernel(Counters* ctr, int inIdx, int phase)
-{
-  if (phase == 0) {   // before trace_closest of a bounce
-    ctr->workCounter = 0; ctr->numPaths[inIdx ^ 1] = 0; ctr->numShadow = 0;
-    ctr->stats[0] += ctr->numPaths[inIdx];
-  } else {            // before trace_shadow
-    ctr->workCounter = 0;
-    ctr->stats[3] += ctr->numShadow;
-  }
-}
+// Per-bounce bookkeeping needs no kernel of its own: trace_closest's prologue zeroes the OUT queue length and the shadow
+// queue length and adds its ray count to the statistics (TraceParams.zeroA / zeroB / rayStat), trace_shadow's adds its
+// own, and the shade kernel -- which runs between the two -- zeroes both ray-fetch counters for the launches behind it.
 
 // ---- rp_main.miss:39-53 -------------------------------------------------------------------------
 GTLC_D V3 quatRotateDir(const float* q, V3 dir)
@@ -489,6 +483,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
   uint32_t maxBounces = ubo.maxBouncesAndRrBounceOffset >> 16; if (maxBounces > kPayloadBouncesMask) maxBounces = kPayloadBouncesMask;
   constexpr bool kPhaseSync = GTLC_SHADE_PHASE_SYNC && MAXC >= GTLC_SHADE_SYNC_MIN_CLOSURE;
   const bool nee = NEE;   // NEXT_EVENT_ESTIMATION is a compile-time permutation in the reference too (GlslShaderGen.cpp:107,247)
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->workCounter = 0; ctr->workCounterShadow = 0; }   // trace_closest of this bounce is done, trace_shadow not started
 
   for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nRounded; it += gridDim.x * blockDim.x) {
     bool valid = it < n;

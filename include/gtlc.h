@@ -365,8 +365,8 @@ typedef struct GtlcTuning {
   int32_t  sortByMaterial;    /* -1 auto (on iff >1 material), 0 off, 1 on */
   int32_t  skipReadback;      /* 1: leave AOVs on the device (kernel-only timing) */
   int32_t  countVisits;       /* 1: traversal kernels also count node/triangle visits (slower; roofline bookkeeping) */
-  int32_t  traceVariant;      /* traversal kernel: 0 default (= 7, warp-batched triangle tests); 1 per-lane triangle loop (the walk order of the visit-counting pass and of the oracle); 5 pending-triangle FIFO; 6 TMA-staged ray tiles */
-  int32_t  reserved[3];       /* [0] refill threshold (idle lanes), [1] trace CTAs per SM, [2] variant 5 triangle threshold; 0 = default */
+  int32_t  traceVariant;      /* traversal kernel: 0 default (= 7, warp-batched triangle tests); 1 per-lane triangle loop (the walk order of the visit-counting pass and of the oracle); 6 TMA-staged ray tiles */
+  int32_t  reserved[3];       /* [0] refill threshold (idle lanes), [1] trace CTAs per SM, [2] unused; 0 = default */
   int32_t  bvhBuilder;        /* 0 host binned-SAH build (default); 1 device LBVH build (fastest rebuilds); 2 device PLOC build (close to the SAH tree's trace speed); takes effect at the next geometry change */
 } GtlcTuning;
 GTLC_API void gtlc_set_tuning(const GtlcTuning* tuning);
@@ -376,8 +376,8 @@ GTLC_API void gtlc_get_tuning(GtlcTuning* tuning);
 typedef struct GtlcStats {
   uint64_t closestRays;       /* rays traced by trace_closest */
   uint64_t shadowRays;        /* rays traced by trace_any (tMax > 0 only) */
-  uint64_t nodeVisits;        /* BVH8 nodes fetched (valid iff countVisits) */
-  uint64_t triVisits;         /* triangles tested   (valid iff countVisits) */
+  uint64_t nodeVisits;        /* BVH8 nodes fetched by closest-hit (gtlc_trace_rays: any-hit) rays (valid iff countVisits) */
+  uint64_t triVisits;         /* triangles tested by them                                           (valid iff countVisits) */
   uint64_t kernelLaunches;    /* number of __global__ launches issued */
   uint64_t paths;             /* camera paths started */
   float    msTotal;           /* CUDA-event time of the whole call on the render stream */
@@ -395,6 +395,9 @@ typedef struct GtlcStats {
   uint64_t nonFiniteRays;       /* rays with a NaN/Inf origin or direction (answered as misses without traversal) */
   float    msBvhDeviceBuild;    /* bvhBuilder = 1: wall clock of the device build alone (scratch allocation .. final node copy), part of msBvhBuild */
   float    reservedStats;
+  uint64_t closestHits;         /* closest-hit rays that found a surface = hits the shade kernel shades (valid iff countVisits) */
+  uint64_t shadowNodeVisits;    /* BVH8 nodes fetched / triangles tested by shadow rays (valid iff countVisits) */
+  uint64_t shadowTriVisits;
 } GtlcStats;
 GTLC_API void gtlc_get_stats(GtlcStats* stats);
 

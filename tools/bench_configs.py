@@ -43,6 +43,14 @@ for name in a.configs.split(","):
     import ctypes as C
     gi.set_tuning(bvhBuilder=a.bvh_builder, traceVariant=a.trace_variant, reserved=(C.c_int32 * 3)(0, 0, a.tri_threshold))
     b = gi.BuiltScene(d)
+    gi.set_tuning(countVisits=1)                     # untimed counting pass: exact visit counts of the identical rays (algorithmic bytes)
+    b.render()
+    cs = gi.get_stats()
+    gi.set_tuning(countVisits=0)
+    visits = {"closest_nodes_per_ray": cs["nodeVisits"] / max(cs["closestRays"], 1), "closest_tris_per_ray": cs["triVisits"] / max(cs["closestRays"], 1),
+              "shadow_nodes_per_ray": cs["shadowNodeVisits"] / max(cs["shadowRays"], 1), "shadow_tris_per_ray": cs["shadowTriVisits"] / max(cs["shadowRays"], 1),
+              "closest_hits": cs["closestHits"], "node_visits": cs["nodeVisits"], "tri_visits": cs["triVisits"],
+              "shadow_node_visits": cs["shadowNodeVisits"], "shadow_tri_visits": cs["shadowTriVisits"]}
     for sort in ((-1,) if len(d.materials) == 1 else (0, 1)):
         gi.set_tuning(sortByMaterial=sort)
         best = None
@@ -57,6 +65,6 @@ for name in a.configs.split(","):
                           "sort": sort, "Mray_s": rays / best["msTotal"] / 1e3, "ms_total": best["msTotal"], "closest": best["closestRays"],
                           "shadow": best["shadowRays"], "ms_trace": best["msTraceClosest"], "ms_shadow": best["msTraceAny"], "ms_shade": best["msShade"],
                           "ms_sort": best["msSort"], "bvh_builder": a.bvh_builder, "trace_variant": a.trace_variant, "bvh_build_ms": best["msBvhBuild"], "bvh_device_build_ms": best["msBvhDeviceBuild"], "bvh_nodes": best["bvhNodeCount"], "depth": best["bvhMaxDepth"],
-                          "scene_gen_s": round(t_gen, 2)}), flush=True)
+                          "scene_gen_s": round(t_gen, 2), "launches": best["kernelLaunches"], **visits}), flush=True)
     b.close()
 gi.giTerminate()

@@ -13,7 +13,7 @@ from gatling_b200 import gi, scenes  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--tris", type=int, default=1_000_000)
 ap.add_argument("--spp", type=int, default=16)
-ap.add_argument("--variants", default="0,1,5")
+ap.add_argument("--variants", default="0,1,6")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--refill", default="0")
 ap.add_argument("--ctas", default="0")
