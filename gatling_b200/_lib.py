@@ -138,6 +138,8 @@ _SIGNATURES = {
     "gtlc_render_buffer_mem": (C.c_void_p, [H]), "gtlc_render_buffer_device_mem": (C.c_void_p, [H]),
     "gtlc_render": (C.c_int, [C.POINTER(RenderParams)]),
     "gtlc_scene_set_shard": (None, [H, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "gtlc_comm_get_unique_id": (C.c_int, [C.c_void_p]), "gtlc_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "gtlc_comm_destroy": (None, []), "gtlc_comm_world_size": (C.c_int, []),
     "gtlc_set_tuning": (None, [C.POINTER(Tuning)]), "gtlc_get_tuning": (None, [C.POINTER(Tuning)]),
     "gtlc_get_stats": (None, [C.POINTER(Stats)]),
     "gtlc_trace_rays": (C.c_int, [H, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -47,7 +47,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), "-ccbin", _host_cxx(), "-shared", "-o", LIB] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-lgomp"]
+    cmd = [_nvcc(), "-ccbin", _host_cxx(), "-shared", "-o", LIB] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-lgomp", "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

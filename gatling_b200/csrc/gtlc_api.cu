@@ -8,6 +8,9 @@
 #include "sort.cuh"
 #include "bvh8_gpu.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen'ed (gtlc_comm_*)
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -154,6 +157,16 @@ struct Global {
   uint32_t* perm = nullptr; uint32_t* sortHist = nullptr; int sortBlocks = 0;
   AovSampleBuffers aovSamples; size_t aovCapacity = 0;
   std::vector<cudaEvent_t> events; size_t eventsUsed = 0;
+  // multi-GPU: one NCCL communicator per process, entry points resolved from libnccl.so.2 at gtlc_comm_init
+  struct Nccl {
+    void* lib = nullptr; ncclComm_t comm = nullptr; int rank = 0, world = 0;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  } nccl;
+  float4* reduced = nullptr; size_t reducedCapacity = 0;   // root: the reduced colour AOV (the shard buffers keep foreign pixels at 0)
   Global() { memset(&aovSamples, 0, sizeof(aovSamples)); memset(&tuning, 0, sizeof(tuning)); tuning.maxPathsPerWave = 1u << 24; tuning.sortByMaterial = -1; memset(&stats, 0, sizeof(stats)); memset(q, 0, sizeof(q)); }
 };
 Global g;
@@ -639,6 +652,23 @@ cudaEvent_t nextEvent()
 struct TimedSpan { cudaEvent_t a, b; int kind; };
 enum { K_RAYGEN, K_TRACE, K_SHADE, K_SHADOW, K_RESOLVE, K_SORT, K_COUNT };
 
+bool loadNccl()
+{
+  if (g.nccl.lib) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);      // an already loaded copy with this SONAME (e.g. the host application's) is reused
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { setError("multi-GPU: cannot open libnccl.so.2 (%s)", dlerror()); return false; }
+  g.nccl.GetUniqueId = (decltype(g.nccl.GetUniqueId)) dlsym(lib, "ncclGetUniqueId");
+  g.nccl.CommInitRank = (decltype(g.nccl.CommInitRank)) dlsym(lib, "ncclCommInitRank");
+  g.nccl.Reduce = (decltype(g.nccl.Reduce)) dlsym(lib, "ncclReduce");
+  g.nccl.CommDestroy = (decltype(g.nccl.CommDestroy)) dlsym(lib, "ncclCommDestroy");
+  g.nccl.GetErrorString = (decltype(g.nccl.GetErrorString)) dlsym(lib, "ncclGetErrorString");
+  if (!g.nccl.GetUniqueId || !g.nccl.CommInitRank || !g.nccl.Reduce || !g.nccl.CommDestroy || !g.nccl.GetErrorString) { setError("multi-GPU: libnccl.so.2 lacks an entry point"); dlclose(lib); return false; }
+  g.nccl.lib = lib;
+  return true;
+}
+#define NCCL_OK(expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) { setError("%s failed: %s", #expr, g.nccl.GetErrorString(_r)); return false; } } while (0)
+
 bool requireInit()
 {
   if (!g.initialized) { setError("gtlc_initialize() has not been called (or failed: no CUDA device) -- there is no CPU fallback"); return false; }
@@ -769,9 +799,46 @@ void gtlc_terminate(void)
   g.poolCapacity = 0; g.accumCapacity = 0; g.visitsCapacity = 0;
   for (cudaEvent_t e : g.events) cudaEventDestroy(e);
   g.events.clear(); g.eventsUsed = 0;
+  if (g.nccl.comm) { g.nccl.CommDestroy(g.nccl.comm); g.nccl.comm = nullptr; g.nccl.world = 0; }
+  cudaFree(g.reduced); g.reduced = nullptr; g.reducedCapacity = 0;
   cudaStreamDestroy(g.stream); g.stream = nullptr;
   g.initialized = false;
 }
+
+// ---- multi-GPU communicator ----------------------------------------------------------------
+int gtlc_comm_get_unique_id(void* id)
+{
+  if (!id) { setError("gtlc_comm_get_unique_id: null id"); return GTLC_ERROR; }
+  if (!loadNccl()) return GTLC_ERROR;
+  ncclUniqueId u;
+  ncclResult_t r = g.nccl.GetUniqueId(&u);
+  if (r != ncclSuccess) { setError("ncclGetUniqueId failed: %s", g.nccl.GetErrorString(r)); return GTLC_ERROR; }
+  static_assert(sizeof(u) == GTLC_COMM_ID_BYTES, "ncclUniqueId size");
+  memcpy(id, &u, sizeof(u));
+  return GTLC_OK;
+}
+int gtlc_comm_init(const void* id, int32_t rank, int32_t worldSize)
+{
+  if (!requireInit()) return GTLC_ERROR;
+  if (!id || worldSize < 1 || rank < 0 || rank >= worldSize) { setError("gtlc_comm_init: invalid arguments (rank %d of %d)", rank, worldSize); return GTLC_ERROR; }
+  std::lock_guard<std::mutex> rl(g_renderMutex);
+  if (g.nccl.comm) { setError("gtlc_comm_init: a communicator exists already"); return GTLC_ERROR; }
+  if (!loadNccl()) return GTLC_ERROR;
+  cudaSetDevice(g.device);
+  ncclUniqueId u; memcpy(&u, id, sizeof(u));
+  ncclResult_t r = g.nccl.CommInitRank(&g.nccl.comm, worldSize, u, rank);
+  if (r != ncclSuccess) { setError("ncclCommInitRank failed: %s", g.nccl.GetErrorString(r)); g.nccl.comm = nullptr; return GTLC_ERROR; }
+  g.nccl.rank = rank; g.nccl.world = worldSize;
+  return GTLC_OK;
+}
+void gtlc_comm_destroy(void)
+{
+  std::lock_guard<std::mutex> rl(g_renderMutex);
+  if (!g.nccl.comm) return;
+  cudaSetDevice(g.device); cudaStreamSynchronize(g.stream);
+  g.nccl.CommDestroy(g.nccl.comm); g.nccl.comm = nullptr; g.nccl.world = 0;
+}
+int gtlc_comm_world_size(void) { return g.nccl.comm ? g.nccl.world : 0; }
 
 void gtlc_set_tuning(const GtlcTuning* t) { if (t) { g.tuning = *t; if (g.tuning.maxPathsPerWave == 0) g.tuning.maxPathsPerWave = 1u << 24; } }
 void gtlc_get_tuning(GtlcTuning* t) { if (t) *t = g.tuning; }
@@ -1366,6 +1433,17 @@ int gtlc_render(const GtlcRenderParams* params)
         if (aovMode) timed(K_RESOLVE, [&] { resolve_aov_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, g.aovSamples, targets, sBase == 0 ? 1 : 0, lastWave); });
       }
     }
+    // the single collective of the path: every rank's colour AOV holds its own tiles and zeros elsewhere;
+    // one sum-reduce to rank 0, on the render stream, before the device->host copy.  The result goes to a buffer of its
+    // own on the root so that the shard buffers keep "foreign pixels = 0" for the next progressive call.
+    const bool reduceColor = g.nccl.comm && s->shardCount > 1 && colorDev;
+    if (reduceColor) {
+      if ((uint32_t) g.nccl.world != s->shardCount || (uint32_t) g.nccl.rank != s->shardRank) { setError("gtlc_render: the scene's shard (%u of %u) does not match the communicator (%d of %d)", s->shardRank, s->shardCount, g.nccl.rank, g.nccl.world); return false; }
+      const size_t px = (size_t) W * H;
+      if (g.nccl.rank == 0 && g.reducedCapacity < px) { cudaFree(g.reduced); g.reduced = nullptr; g.reducedCapacity = 0; CUDA_OK(cudaMalloc(&g.reduced, px * 16)); g.reducedCapacity = px; }
+      NCCL_OK(g.nccl.Reduce(colorDev, g.nccl.rank == 0 ? (void*) g.reduced : (void*) colorDev, px * 4, ncclFloat, ncclSum, 0, g.nccl.comm, g.stream));
+      launches++;
+    }
     cudaEventRecord(evEnd, g.stream);
     CUDA_OK(cudaGetLastError());
     // readback of every bound AOV (Gi.cpp:2439-2489) + blocking wait (Gi.cpp:2492-2502)
@@ -1374,6 +1452,10 @@ int gtlc_render(const GtlcRenderParams* params)
     if (!g.tuning.skipReadback) {
       for (uint32_t i = 0; i < params->aovBindingCount; i++) {
         RenderBuffer* rb = as<RenderBuffer>(params->aovBindings[i].renderBuffer, TAG_RB);
+        if (reduceColor && rb == colorRb) {           // the assembled image exists on rank 0 only
+          if (g.nccl.rank == 0) CUDA_OK(cudaMemcpyAsync(rb->hostMem, g.reduced, rb->size, cudaMemcpyDeviceToHost, g.stream));
+          continue;
+        }
         CUDA_OK(cudaMemcpyAsync(rb->hostMem, rb->devMem, rb->size, cudaMemcpyDeviceToHost, g.stream));
       }
     }

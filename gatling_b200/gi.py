@@ -332,6 +332,29 @@ def set_shard(scene, rank, world_size, tile=64):
     _lib().gtlc_scene_set_shard(scene, rank, world_size, tile)
 
 
+COMM_ID_BYTES = 128
+
+
+def comm_get_unique_id() -> bytes:
+    """Rank 0: the NCCL unique id (128 bytes) the other ranks need for comm_init; carry it with any host-side channel."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    if _lib().gtlc_comm_get_unique_id(buf) != 0:
+        raise RuntimeError("gtlc_comm_get_unique_id failed: " + giLastError())
+    return buf.raw
+
+
+def comm_init(unique_id: bytes, rank: int, world_size: int):
+    """Joins the library's NCCL communicator: giRender of a sharded scene then ends with the HDR sum-reduce to rank 0."""
+    assert len(unique_id) == COMM_ID_BYTES
+    buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
+    if _lib().gtlc_comm_init(buf, rank, world_size) != 0:
+        raise RuntimeError("gtlc_comm_init failed: " + giLastError())
+
+
+def comm_destroy():
+    _lib().gtlc_comm_destroy()
+
+
 def set_tuning(**kw):
     t = L.Tuning()
     _lib().gtlc_get_tuning(C.byref(t))

@@ -359,6 +359,20 @@ GTLC_API int gtlc_render(const GtlcRenderParams* params);
  * single sum-reduce over ranks yields the full image.  tileSize in pixels (square tiles). */
 GTLC_API void gtlc_scene_set_shard(GtlcHandle scene, uint32_t rank, uint32_t worldSize, uint32_t tileSize);
 
+/* The one collective of the path: with a communicator in place, gtlc_render() of a sharded scene ends
+ * with ncclReduce(sum, float, W x H x 4, root 0) of the HDR colour accumulator on the render stream, BEFORE the
+ * device->host copy, so rank 0's render buffer holds the complete image when the call returns (the other ranks' host
+ * buffers are not written).  Every rank of the communicator must call gtlc_render() for the same image size, in the
+ * same order.  libnccl.so.2 is opened at gtlc_comm_get_unique_id / gtlc_comm_init (no link-time dependency: a
+ * single-GPU host never needs NCCL).  Bootstrap: rank 0 creates the id, the host's own control plane (MPI, a TCP
+ * store, torch.distributed, a file) carries its GTLC_COMM_ID_BYTES bytes to the other ranks, everybody calls
+ * gtlc_comm_init.  The reference has a single device (CgpuVk.cpp:959-1000): no counterpart in Gi.h. */
+#define GTLC_COMM_ID_BYTES 128
+GTLC_API int  gtlc_comm_get_unique_id(void* id);                                   /* ncclGetUniqueId */
+GTLC_API int  gtlc_comm_init(const void* id, int32_t rank, int32_t worldSize);     /* ncclCommInitRank on the library's device (after gtlc_initialize) */
+GTLC_API void gtlc_comm_destroy(void);
+GTLC_API int  gtlc_comm_world_size(void);                                          /* 0 = no communicator */
+
 /* Render-loop tuning knobs (all have defaults; the bench records the values it used). */
 typedef struct GtlcTuning {
   uint32_t maxPathsPerWave;   /* path-state pool size; default 1<<24 */

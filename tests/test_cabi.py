@@ -14,7 +14,7 @@ from gatling_b200 import _lib, gi, scenes
 def test_exports_every_declared_symbol():
     lib = _lib.load()
     names = _lib.declared_symbols()
-    assert len(names) == 61
+    assert len(names) == 65
     for n in names:
         assert hasattr(lib, n), "libgtlc.so does not export %s" % n
     assert set(names) == set(_lib._SIGNATURES), "python binding and header disagree"
