@@ -8,12 +8,20 @@ namespace gtlc {
 
 GTLC_D float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 
+// What the closure needs of a material: constants of the parameter block, NOT of the hit.  For materials without
+// textured / primvar-driven inputs lower_materials_kernel evaluates opbr_lobes() once per material at upload (the same
+// device code, hence the same bits) and the shade kernel loads the 32-float record instead of spending ~10 IEEE divisions
+// and 3 square roots per call -- the instance-compiled MDL of the reference folds these at material compile time too
+// (MdlMaterialCompiler.cpp:262).  Textured materials (TEX instantiation) keep evaluating it per hit.
 struct OpbrLobes {
   float coat_w, a_c, coat_ior; V3 coat_att;
   float metal; V3 m_f0, m_f82; float spec_w;
   float eta; V3 spec_color; float a;
   float trans_w; V3 trans_tint; V3 Kd;
+  V3 m_b;     // F82-tint edge term of the metal Fresnel (opbr_metal_fresnel)
 };
+constexpr int kLobeFloats = 32;    // record size of the lowered-material table (>= sizeof(OpbrLobes) / 4, 128-byte rows)
+static_assert(sizeof(OpbrLobes) <= kLobeFloats * 4, "lobe record too small");
 
 GTLC_D OpbrLobes opbr_lobes(const float* p)
 {
@@ -57,16 +65,41 @@ GTLC_D OpbrLobes opbr_lobes(const float* p)
   const V3 darkening = v3((1.0f - Kcoat) / (1.0f - Ebase.x * Kcoat), (1.0f - Kcoat) / (1.0f - Ebase.y * Kcoat), (1.0f - Kcoat) / (1.0f - Ebase.z * Kcoat));
   const V3 modulated = mix(v3(1.0f), darkening, coat_w * p[GTLC_OPBR_COAT_DARKENING]);
   o.coat_att = modulated * mix(v3(1.0f), p3(p, GTLC_OPBR_COAT_COLOR_R), coat_w);
+  {  // generalized_schlick with the OpenPBR "F82-tint" edge colour (OpenPBR spec 1.1, metal base): the hit-independent part
+    const float mu = 1.0f / 7.0f;
+    const float k = mu * ((1.0f - mu) * (1.0f - mu)) * ((1.0f - mu) * (1.0f - mu)) * ((1.0f - mu) * (1.0f - mu));   // mu (1-mu)^6
+    const V3 fbar = schlick(o.m_f0, v3(1.0f), mu);
+    o.m_b = (fbar * (v3(1.0f) - o.m_f82)) * (1.0f / k);
+  }
   return o;
 }
+GTLC_D OpbrLobes opbr_lobes_of(const float* p, const float* lowered)
+{
+  if (lowered) {
+    OpbrLobes o;
+    const float4* q = reinterpret_cast<const float4*>(lowered);
+    const float4 a = __ldg(q + 0), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5), g = __ldg(q + 6);
+    o.coat_w = a.x; o.a_c = a.y; o.coat_ior = a.z; o.coat_att = v3(a.w, b.x, b.y);
+    o.metal = b.z; o.m_f0 = v3(b.w, c.x, c.y); o.m_f82 = v3(c.z, c.w, d.x); o.spec_w = d.y;
+    o.eta = d.z; o.spec_color = v3(d.w, e.x, e.y); o.a = e.z;
+    o.trans_w = e.w; o.trans_tint = v3(f.x, f.y, f.z); o.Kd = v3(f.w, g.x, g.y);
+    o.m_b = v3(g.z, g.w, __ldg(lowered + 28));
+    return o;
+  }
+  return opbr_lobes(p);
+}
+GTLC_D void opbr_lobes_store(const OpbrLobes& o, float* dst)
+{
+  const float v[kLobeFloats] = { o.coat_w, o.a_c, o.coat_ior, o.coat_att.x, o.coat_att.y, o.coat_att.z, o.metal, o.m_f0.x, o.m_f0.y, o.m_f0.z,
+                                 o.m_f82.x, o.m_f82.y, o.m_f82.z, o.spec_w, o.eta, o.spec_color.x, o.spec_color.y, o.spec_color.z, o.a,
+                                 o.trans_w, o.trans_tint.x, o.trans_tint.y, o.trans_tint.z, o.Kd.x, o.Kd.y, o.Kd.z, o.m_b.x, o.m_b.y, o.m_b.z, 0.0f, 0.0f, 0.0f };
+  for (int k = 0; k < kLobeFloats; k++) dst[k] = v[k];
+}
 
-// generalized_schlick with the OpenPBR "F82-tint" edge colour (OpenPBR spec 1.1, metal base)
+// generalized_schlick with the OpenPBR "F82-tint" edge colour (OpenPBR spec 1.1, metal base); b = o.m_b (opbr_lobes)
 GTLC_D V3 opbr_metal_fresnel(const OpbrLobes& o, float c)
 {
-  const float mu = 1.0f / 7.0f;
-  const float k = mu * ((1.0f - mu) * (1.0f - mu)) * ((1.0f - mu) * (1.0f - mu)) * ((1.0f - mu) * (1.0f - mu));   // mu (1-mu)^6
-  const V3 fbar = schlick(o.m_f0, v3(1.0f), mu);
-  const V3 b = (fbar * (v3(1.0f) - o.m_f82)) * (1.0f / k);
+  const V3 b = o.m_b;
   c = clampf(c, 0.0f, 1.0f);
   const float om = 1.0f - c;
   const float w6 = c * ((om * om) * (om * om) * (om * om));
@@ -81,9 +114,9 @@ GTLC_D float opbr_rel_eta(const V3& ior1, const V3& ior2, float material_ior)
   return n2 / n1;
 }
 
-GTLC_D void openpbr_sample(const float* p, BsdfSample& d, const ShadingState& s)
+GTLC_D void openpbr_sample(const float* p, const float* lowered, BsdfSample& d, const ShadingState& s)
 {
-  const OpbrLobes o = opbr_lobes(p);
+  const OpbrLobes o = opbr_lobes_of(p, lowered);
   const Frame f = make_frame(s);
   const V3 k1 = to_local(f, d.k1);
   d.bsdf_over_pdf = v3(0.0f); d.pdf = 0.0f; d.event_type = BSDF_EVENT_ABSORB; d.k2 = v3(0.0f);
@@ -160,9 +193,9 @@ GTLC_D void openpbr_sample(const float* p, BsdfSample& d, const ShadingState& s)
   d.pdf = 1.0f;
 }
 
-GTLC_D void openpbr_evaluate(const float* p, BsdfEval& d, const ShadingState& s)
+GTLC_D void openpbr_evaluate(const float* p, const float* lowered, BsdfEval& d, const ShadingState& s)
 {
-  const OpbrLobes o = opbr_lobes(p);
+  const OpbrLobes o = opbr_lobes_of(p, lowered);
   const Frame f = make_frame(s);
   const V3 k1 = to_local(f, d.k1), k2 = to_local(f, d.k2);
   d.bsdf_diffuse = v3(0.0f); d.bsdf_glossy = v3(0.0f); d.pdf = 0.0f;
@@ -196,9 +229,9 @@ GTLC_D void openpbr_evaluate(const float* p, BsdfEval& d, const ShadingState& s)
 
 
 // mdl_bsdf_scattering_auxiliary: albedo_diffuse + albedo_glossy at the viewing angle
-GTLC_D V3 openpbr_albedo(const float* p, V3 k1, const ShadingState& s)
+GTLC_D V3 openpbr_albedo(const float* p, const float* lowered, V3 k1, const ShadingState& s)
 {
-  const OpbrLobes o = opbr_lobes(p);
+  const OpbrLobes o = opbr_lobes_of(p, lowered);
   const float nk1 = clampf(dot(k1, s.normal), 0.0f, 1.0f);
   const float fs = fresnel_dielectric(nk1, o.eta);
   const V3 substrate = o.Kd * (1.0f - o.trans_w) + o.trans_tint * o.trans_w;

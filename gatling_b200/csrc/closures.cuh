@@ -301,12 +301,14 @@ namespace gtlc {
 // closure id present in the scene: kernels are instantiated per closure set so that a diffuse-only scene does
 // not pay the registers of the layered closures (the counterpart of the reference's per-material shader
 // permutations, GlslShaderGen.cpp:211-262).
+// `lowered`: the material's row of the lowered-material table (closure_openpbr.cuh: OpbrLobes), or NULL when the
+// parameter block was patched per hit (textured / primvar-driven inputs).
 template <int MAXC>
-GTLC_D void bsdf_sample(int closure, const float* p, BsdfSample& d, const ShadingState& s)
+GTLC_D void bsdf_sample(int closure, const float* p, const float* lowered, BsdfSample& d, const ShadingState& s)
 {
   if (MAXC == GTLC_CLOSURE_DIFFUSE || closure == GTLC_CLOSURE_DIFFUSE) { diffuse_sample(p, d, s); return; }
   if (MAXC == GTLC_CLOSURE_USD_PREVIEW_SURFACE || closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { ups_sample(p, d, s); return; }
-  openpbr_sample(p, d, s);
+  openpbr_sample(p, lowered, d, s);
 }
 GTLC_D V3 ups_albedo(const float* p, V3 k1, const ShadingState& s)
 {
@@ -320,18 +322,28 @@ GTLC_D V3 ups_albedo(const float* p, V3 k1, const ShadingState& s)
 }
 // mdl_bsdf_scattering_auxiliary (rp_main.chit:264-280): albedo_diffuse + albedo_glossy
 template <int MAXC>
-GTLC_D V3 bsdf_albedo(int closure, const float* p, V3 k1, const ShadingState& s)
+GTLC_D V3 bsdf_albedo(int closure, const float* p, const float* lowered, V3 k1, const ShadingState& s)
 {
   if (MAXC == GTLC_CLOSURE_DIFFUSE || closure == GTLC_CLOSURE_DIFFUSE) return p3(p, GTLC_DIFFUSE_TINT_R);
   if (MAXC == GTLC_CLOSURE_USD_PREVIEW_SURFACE || closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) return ups_albedo(p, k1, s);
-  return openpbr_albedo(p, k1, s);
+  return openpbr_albedo(p, lowered, k1, s);
 }
 template <int MAXC>
-GTLC_D void bsdf_evaluate(int closure, const float* p, BsdfEval& d, const ShadingState& s)
+GTLC_D void bsdf_evaluate(int closure, const float* p, const float* lowered, BsdfEval& d, const ShadingState& s)
 {
   if (MAXC == GTLC_CLOSURE_DIFFUSE || closure == GTLC_CLOSURE_DIFFUSE) { diffuse_evaluate(p, d, s); return; }
   if (MAXC == GTLC_CLOSURE_USD_PREVIEW_SURFACE || closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { ups_evaluate(p, d, s); return; }
-  openpbr_evaluate(p, d, s);
+  openpbr_evaluate(p, lowered, d, s);
+}
+
+// One thread per material: evaluates the hit-independent part of the OpenPBR closure once (see OpbrLobes).
+__global__ void lower_materials_kernel(const float* __restrict__ params, const int32_t* __restrict__ closure, uint32_t count, float* __restrict__ lowered)
+{
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= count) return;
+  float* dst = lowered + (size_t) m * kLobeFloats;
+  if (closure[m] == GTLC_CLOSURE_OPENPBR) opbr_lobes_store(opbr_lobes(params + (size_t) m * GTLC_MATERIAL_PARAM_COUNT), dst);
+  else for (int k = 0; k < kLobeFloats; k++) dst[k] = 0.0f;
 }
 
 } // namespace gtlc

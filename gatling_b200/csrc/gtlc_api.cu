@@ -127,7 +127,9 @@ struct Scene : Object {
   // device
   DeviceArray<uint4> dNodes; DeviceArray<float4> dTris;     // canonical BVH8 (bvh8.h): what the builders write and gtlc_scene_get_bvh returns
   DeviceArray<uint4> dNodesT; DeviceArray<float4> dTrisT;   // traversal layout (traverse.cuh): 96-byte nodes, 64-byte triangles
-  DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;
+  DeviceArray<float4> dFverts; DeviceArray<uint32_t> dFaces;   // the reference's packed FVertex / Face arrays (canonical; input of the device BVH builders)
+  DeviceArray<uint4> dSverts, dSfaces; DeviceArray<float> dMatLowered;   // shading records + lowered materials (wavefront.cuh: DeviceScene)
+  struct MeshRange { uint32_t faceBase, faceCount, vertexBase; }; std::vector<MeshRange> meshRanges;
   DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo; DeviceArray<int2> dInstIds; DeviceArray<int32_t> dFaceIds; DeviceArray<uint32_t> dRankBase;
   DeviceArray<float> dMatParams; DeviceArray<int32_t> dMatClosure; DeviceArray<uint32_t> dMatFlags;
   DeviceArray<DeviceTexture> dTextures; DeviceArray<DeviceTexBinding> dTexBindings; DeviceArray<uint2> dMatTexRange; bool hasTextures = false;
@@ -263,7 +265,7 @@ void invertAffine(const float* m, float* out)
 bool buildHostGeometry(Scene* s, bool hostBvh = true)
 {
   auto t0 = std::chrono::steady_clock::now();
-  s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->hInstOpacity.clear(); s->hPrimvarInfos.clear(); s->hPrimvarData.clear(); s->flatMaterials.clear();
+  s->meshRanges.clear(); s->hFverts.clear(); s->hFaces.clear(); s->hO2W.clear(); s->hW2O.clear(); s->hInstInfo.clear(); s->hInstIds.clear(); s->hFaceIds.clear(); s->hRankBase.clear(); s->hInstOpacity.clear(); s->hPrimvarInfos.clear(); s->hPrimvarData.clear(); s->flatMaterials.clear();
   // world-space triangles for the host builder: one job per (instance, block of faces), filled by the whole team below
   struct FlattenJob { const Mesh* mesh; uint32_t inst, firstFace, lastFace, firstTri; float opacity; float o2w[12]; };
   std::vector<FlattenJob> jobs;
@@ -280,6 +282,7 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
     if (matIndex == s->flatMaterials.size()) s->flatMaterials.push_back(m->material);
     const uint32_t vertexBase = (uint32_t) (s->hFverts.size() / 8);
     const uint32_t faceBase = (uint32_t) (s->hFaces.size() / 3);
+    s->meshRanges.push_back({ faceBase, (uint32_t) m->faces.size(), vertexBase });
     {                                                                   // FVertex packing, Gi.cpp:845-859
       const size_t nv = m->vertices.size(), nf = m->faces.size(), fv0 = s->hFverts.size(), ff0 = s->hFaces.size(), fi0 = s->hFaceIds.size();
       s->hFverts.resize(fv0 + nv * 8); s->hFaces.resize(ff0 + nf * 3); s->hFaceIds.resize(fi0 + nf);
@@ -417,7 +420,15 @@ bool uploadGeometry(Scene* s, bool hostBvh = true)
   if (!s->dInstIds.upload(s->hInstIds.data(), s->hInstIds.size(), st)) return false;
   if (!s->dFaceIds.upload(s->hFaceIds.data(), s->hFaceIds.size(), st)) return false;
   if (!s->dRankBase.upload(s->hRankBase.data(), s->hRankBase.size(), st)) return false;
+  // shading records: decoded normals / tangents per vertex, indices + face id + geometric normal per face
+  const uint32_t vertexCount = (uint32_t) (s->hFverts.size() / 8), faceCount = (uint32_t) (s->hFaces.size() / 3);
+  if (!s->dSverts.reserve((size_t) std::max(vertexCount, 1u) * 4) || !s->dSfaces.reserve((size_t) std::max(faceCount, 1u) * 2)) return false;
+  if (vertexCount) shading_vertices_kernel<<<std::min<uint32_t>((vertexCount + 255u) / 256u, (uint32_t) g.smCount * 16u), 256, 0, st>>>(s->dFverts.ptr, vertexCount, s->dSverts.ptr);
+  for (const Scene::MeshRange& r : s->meshRanges)
+    if (r.faceCount) shading_faces_kernel<<<std::min<uint32_t>((r.faceCount + 255u) / 256u, (uint32_t) g.smCount * 16u), 256, 0, st>>>(s->dFaces.ptr, s->dFaceIds.ptr, s->dFverts.ptr, r.faceBase, r.faceCount, r.vertexBase, s->dSfaces.ptr);
+  g.stats.kernelLaunches += 1 + s->meshRanges.size();
   CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
   if (!hostBvh && !buildBvhOnDevice(s)) return false;
   if (!repackBvh(s)) return false;
   s->lastBuildMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -578,7 +589,11 @@ bool uploadMaterials(Scene* s)
   if (!s->dTextures.upload(textures.data(), textures.size(), g.stream)) return false;
   if (!s->dTexBindings.upload(bindings.data(), bindings.size(), g.stream)) return false;
   if (!s->dMatTexRange.upload(ranges.data(), ranges.size(), g.stream)) return false;
+  const uint32_t matCount = (uint32_t) closure.size();
+  if (!s->dMatLowered.reserve((size_t) std::max(matCount, 1u) * kLobeFloats)) return false;
+  if (matCount) lower_materials_kernel<<<(matCount + 63u) / 64u, 64, 0, g.stream>>>(s->dMatParams.ptr, s->dMatClosure.ptr, matCount, s->dMatLowered.ptr);
   CUDA_OK(cudaStreamSynchronize(g.stream));
+  CUDA_OK(cudaGetLastError());
   return true;
 }
 
@@ -856,7 +871,7 @@ void gtlc_scene_destroy(GtlcHandle h)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
-  s->dNodes.release(); s->dTris.release(); s->dNodesT.release(); s->dTrisT.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
+  s->dNodes.release(); s->dTris.release(); s->dNodesT.release(); s->dTrisT.release(); s->dSverts.release(); s->dSfaces.release(); s->dMatLowered.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
   s->dMatParams.release(); s->dTextures.release(); s->dTexBindings.release(); s->dMatTexRange.release(); s->dPrimvarInfos.release(); s->dPrimvarData.release(); s->dPrimvarBindings.release(); s->dMatPrimvarRange.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
@@ -1338,7 +1353,8 @@ int gtlc_render(const GtlcRenderParams* params)
     if (g.accumCapacity < localPixels) { cudaFree(g.accum); g.accum = nullptr; CUDA_OK(cudaMalloc(&g.accum, std::max<size_t>(localPixels, 1) * 16)); g.accumCapacity = localPixels; }
 
     DeviceScene ds; memset(&ds, 0, sizeof(ds));
-    ds.fverts = s->dFverts.ptr; ds.faces = s->dFaces.ptr; ds.instO2W = s->dO2W.ptr; ds.instW2O = s->dW2O.ptr; ds.instInfo = s->dInstInfo.ptr; ds.instIds = s->dInstIds.ptr; ds.faceIds = s->dFaceIds.ptr;
+    ds.sverts = (const uint32_t*) s->dSverts.ptr; ds.sfaces = (const uint32_t*) s->dSfaces.ptr; ds.matLowered = s->dMatLowered.ptr;
+    ds.instO2W = s->dO2W.ptr; ds.instW2O = s->dW2O.ptr; ds.instInfo = s->dInstInfo.ptr; ds.instIds = s->dInstIds.ptr;
     ds.matParams = s->dMatParams.ptr; ds.matClosure = s->dMatClosure.ptr; ds.matFlags = s->dMatFlags.ptr;
     ds.textures = s->dTextures.ptr; ds.texBindings = s->dTexBindings.ptr; ds.matTexRange = s->dMatTexRange.ptr;
     ds.primvarBindings = s->dPrimvarBindings.ptr; ds.matPrimvarRange = s->dMatPrimvarRange.ptr; ds.primvarInfos = s->dPrimvarInfos.ptr; ds.primvarData = s->dPrimvarData.ptr;

@@ -58,14 +58,22 @@ constexpr uint32_t kMatFlagEmissive = 1u, kMatFlagThinWalled = 2u, kMatFlagCutou
 
 struct DevicePrimvarBinding { int32_t paramIndex; int32_t componentCount; float fallback[4]; float pad[2]; };
 
+// Shading records derived ONCE per geometry upload from the reference's packed FVertex / Face arrays (which stay in HBM as
+// the canonical input, and as what the device BVH builders read):
+//   shading vertex, 64 bytes = two 256-bit loads: (pos.xyz, bitangentSign, normal.xyz, u) (tangent.xyz, v, -, -, -, -) -- the
+//     octahedral normal / tangent already decoded (decode_direction: 2 IEEE divisions + a normalize each, six per hit);
+//   shading face, 32 bytes = one 256-bit load: (i0, i1, i2, faceId, object-space geometric normal.xyz, -).
+// Same device functions, evaluated per vertex / face instead of per hit: the bits a hit sees do not change.
+constexpr int kShadeVertexWords = 16, kShadeFaceWords = 8;
+
 struct DeviceScene {
-  const float4* __restrict__ fverts;     // 2 x float4 per FVertex (rp_main.h:58-64)
-  const uint32_t* __restrict__ faces;    // 3 per Face (rp_main.h:66-71)
+  const uint32_t* __restrict__ sverts;   // kShadeVertexWords per vertex
+  const uint32_t* __restrict__ sfaces;   // kShadeFaceWords per face
+  const float* __restrict__ matLowered;  // kLobeFloats per material (closure_openpbr.cuh), valid for materials without per-hit inputs
   const float4* __restrict__ instO2W;    // 3 x float4 per instance (gl_ObjectToWorldEXT rows)
   const float4* __restrict__ instW2O;    // 3 x float4 per instance (gl_WorldToObjectEXT rows)
   const InstanceInfo* __restrict__ instInfo;
   const int2* __restrict__ instIds;       // (objectId, instanceId) per instance (preamble.objectId, InstanceIds[], rp_main.chit:223,243)
-  const int32_t* __restrict__ faceIds;    // one per face of the global face array (rp_main.chit:232-240)
   const float* __restrict__ matParams;   // GTLC_MATERIAL_PARAM_COUNT floats per material
   const int32_t* __restrict__ matClosure;
   const uint32_t* __restrict__ matFlags;
@@ -307,37 +315,68 @@ GTLC_D void sampleLight(const UniformData& ubo, const DeviceScene& s, V4 k4, V3 
   ls.invPdf *= (float) ubo.totalLightCount;                                                  // :128
 }
 
+// ---- shading records (see DeviceScene) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shading_vertices_kernel(const float4* __restrict__ fverts, uint32_t count, uint4* __restrict__ out)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const float4 f1 = fverts[(size_t) i * 2], f2 = fverts[(size_t) i * 2 + 1];      // FVertex, rp_main.h:58-64
+    const V3 n = decode_direction(f2u(f2.x)), t = decode_direction(f2u(f2.y));      // mdl_shading_state.glsl:30-32, 47-49
+    uint4* o = out + (size_t) i * 4;
+    o[0] = make_uint4(f2u(f1.x), f2u(f1.y), f2u(f1.z), f2u(f1.w));
+    o[1] = make_uint4(f2u(n.x), f2u(n.y), f2u(n.z), f2u(f2.z));
+    o[2] = make_uint4(f2u(t.x), f2u(t.y), f2u(t.z), f2u(f2.w));
+    o[3] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+// one launch per mesh: faces [faceBase, faceBase + faceCount) index the vertices from vertexBase on
+__global__ void __launch_bounds__(256) shading_faces_kernel(const uint32_t* __restrict__ faces, const int32_t* __restrict__ faceIds, const float4* __restrict__ fverts,
+                                                            uint32_t faceBase, uint32_t faceCount, uint32_t vertexBase, uint4* __restrict__ out)
+{
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < faceCount; k += gridDim.x * blockDim.x) {
+    const uint32_t f = faceBase + k;
+    const uint32_t i0 = faces[(size_t) f * 3], i1 = faces[(size_t) f * 3 + 1], i2 = faces[(size_t) f * 3 + 2];
+    const float4 a = fverts[(size_t) (vertexBase + i0) * 2], b = fverts[(size_t) (vertexBase + i1) * 2], c = fverts[(size_t) (vertexBase + i2) * 2];
+    const V3 p0 = v3(a.x, a.y, a.z), p1 = v3(b.x, b.y, b.z), p2 = v3(c.x, c.y, c.z);
+    const V3 ng = normalize(cross(p1 - p0, p2 - p0));                                // mdl_shading_state.glsl:26
+    out[(size_t) f * 2] = make_uint4(i0, i1, i2, (uint32_t) faceIds[f]);
+    out[(size_t) f * 2 + 1] = make_uint4(f2u(ng.x), f2u(ng.y), f2u(ng.z), 0u);
+  }
+}
+
 // ---- mdl_shading_state.glsl:4-98 (R4) -----------------------------------------------------------
 GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uint32_t inst, uint32_t prim, float hu, float hv,
-                                V3 rayDir, ShadingState& st, bool& isFrontFace)
+                                V3 rayDir, ShadingState& st, bool& isFrontFace, int32_t& faceId)
 {
   const float4 o0 = __ldg(&s.instO2W[inst * 3 + 0]), o1 = __ldg(&s.instO2W[inst * 3 + 1]), o2 = __ldg(&s.instO2W[inst * 3 + 2]);
   const float4 w0 = __ldg(&s.instW2O[inst * 3 + 0]), w1 = __ldg(&s.instW2O[inst * 3 + 1]), w2 = __ldg(&s.instW2O[inst * 3 + 2]);
-  const uint32_t* f = s.faces + (size_t) (in.faceBase + prim) * 3;                     // :10
-  const uint32_t i0 = __ldg(f + 0), i1 = __ldg(f + 1), i2 = __ldg(f + 2);
-  const float4* vb = s.fverts + (size_t) in.vertexBase * 2;
-  const float4 a1 = __ldg(vb + (size_t) i0 * 2), a2 = __ldg(vb + (size_t) i0 * 2 + 1);   // :12-14
-  const float4 b1 = __ldg(vb + (size_t) i1 * 2), b2 = __ldg(vb + (size_t) i1 * 2 + 1);
-  const float4 c1 = __ldg(vb + (size_t) i2 * 2), c2 = __ldg(vb + (size_t) i2 * 2 + 1);
+  uint32_t fr[8];
+  ldg256(s.sfaces + (size_t) (in.faceBase + prim) * kShadeFaceWords, fr);              // :10 (+ the face's geometric normal)
+  const uint32_t i0 = fr[0], i1 = fr[1], i2 = fr[2];
+  faceId = (int32_t) fr[3];
+  const uint32_t* vb = s.sverts + (size_t) in.vertexBase * kShadeVertexWords;
+  uint32_t a1[8], a2[8], b1[8], b2[8], c1[8], c2[8];                                   // :12-14
+  ldg256(vb + (size_t) i0 * kShadeVertexWords, a1); ldg256(vb + (size_t) i0 * kShadeVertexWords + 8, a2);
+  ldg256(vb + (size_t) i1 * kShadeVertexWords, b1); ldg256(vb + (size_t) i1 * kShadeVertexWords + 8, b2);
+  ldg256(vb + (size_t) i2 * kShadeVertexWords, c1); ldg256(vb + (size_t) i2 * kShadeVertexWords + 8, c2);
   const V3 bc = v3((1.0f - hu) - hv, hu, hv);                                          // :16
-  const V3 p0 = v3(a1.x, a1.y, a1.z), p1 = v3(b1.x, b1.y, b1.z), p2 = v3(c1.x, c1.y, c1.z);
+  const V3 p0 = v3(u2f(a1[0]), u2f(a1[1]), u2f(a1[2])), p1 = v3(u2f(b1[0]), u2f(b1[1]), u2f(b1[2])), p2 = v3(u2f(c1[0]), u2f(c1[1]), u2f(c1[2]));
   const V3 localPos = (p0 * bc.x + p1 * bc.y) + p2 * bc.z;                             // :23
   const V3 pos = xform_point(o0, o1, o2, localPos);                                    // :24
-  V3 geomNormal = normalize(cross(p1 - p0, p2 - p0));                                  // :26
+  V3 geomNormal = v3(u2f(fr[4]), u2f(fr[5]), u2f(fr[6]));                              // :26 normalize(cross(p1 - p0, p2 - p0)), per face
   geomNormal = normalize(xform_dir_transposed(w0, w1, w2, geomNormal));                // :27
-  const V3 n0 = decode_direction(f2u(a2.x)), n1 = decode_direction(f2u(b2.x)), n2 = decode_direction(f2u(c2.x));  // :30-32
+  const V3 n0 = v3(u2f(a1[4]), u2f(a1[5]), u2f(a1[6])), n1 = v3(u2f(b1[4]), u2f(b1[5]), u2f(b1[6])), n2 = v3(u2f(c1[4]), u2f(c1[5]), u2f(c1[6]));  // :30-32 (decoded per vertex)
   const V3 localNormal = normalize((n0 * bc.x + n1 * bc.y) + n2 * bc.z);               // :34
   V3 normal = normalize(xform_dir_transposed(w0, w1, w2, localNormal));                // :35
   isFrontFace = dot(geomNormal, -rayDir) >= 0.0f;                                      // :38
   if (!isFrontFace) { geomNormal = -geomNormal; normal = -normal; }                    // :40-44
-  const V3 t0 = decode_direction(f2u(a2.y)), t1 = decode_direction(f2u(b2.y)), t2 = decode_direction(f2u(c2.y));  // :47-49
+  const V3 t0 = v3(u2f(a2[0]), u2f(a2[1]), u2f(a2[2])), t1 = v3(u2f(b2[0]), u2f(b2[1]), u2f(b2[2])), t2 = v3(u2f(c2[0]), u2f(c2[1]), u2f(c2[2]));  // :47-49
   const V3 localTangent = normalize((t0 * bc.x + t1 * bc.y) + t2 * bc.z);              // :51
   V3 tangent = normalize(xform_dir(o0, o1, o2, localTangent));                         // :52
   tangent = normalize(tangent - normal * dot(tangent, normal));                        // :55
-  const float bitangentSign = (bc.x * a1.w + bc.y * b1.w) + bc.z * c1.w;               // :57
+  const float bitangentSign = (bc.x * u2f(a1[3]) + bc.y * u2f(b1[3])) + bc.z * u2f(c1[3]);   // :57
   const V3 bitangent = cross(normal, tangent) * bitangentSign;                         // :58
-  st.u = (bc.x * a2.z + bc.y * b2.z) + bc.z * c2.z;                                    // :61-64
-  st.v = (bc.x * a2.w + bc.y * b2.w) + bc.z * c2.w;
+  st.u = (bc.x * u2f(a1[7]) + bc.y * u2f(b1[7])) + bc.z * u2f(c1[7]);                  // :61-64
+  st.v = (bc.x * u2f(a2[3]) + bc.y * u2f(b2[3])) + bc.z * u2f(c2[3]);
   st.normal = normal; st.geom_normal = geomNormal; st.position = pos;                  // :82-90
   st.tangent_u = tangent; st.tangent_v = bitangent;
   st.hitIndices[0] = i0; st.hitIndices[1] = i1; st.hitIndices[2] = i2;                  // mdl_shading_state.glsl:66-79 (renderer state)
@@ -494,7 +533,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
     float nextTMax = kFloatMax; V3 nextWalkPdf = v3(1.0f); uint4 nextMedia = make_uint4(0u, 0u, 0u, 0u);
     // state that lives across the two phases of a hit (BSDF sample | NEE)
     ShadingState st; V3 normal = v3(0.0f), iorCurrent = v3(1.0f), iorOther = v3(1.0f), worldRayDir = v3(0.0f);
-    const float* mp = nullptr; int closure = 0; bool doNee = false, isHit = false, isFrontFace = false, thinWalled = false, hasMappedNormal = false;
+    const float* mp = nullptr; const float* lowered = nullptr; int closure = 0; bool doNee = false, isHit = false, isFrontFace = false, thinWalled = false, hasMappedNormal = false;
     V3 mappedNormal = v3(0.0f); uint32_t mediumIdx = 0, hitMaterial = 0;
     bool neeValid = false; V3 neeDir = v3(0.0f), neeRadiance = v3(0.0f); uint32_t neeDiffuseSpecular = 0;
     float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT : 1];                                     // textured inputs: private parameter block
@@ -551,14 +590,16 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
         closure = s.matClosure[in.material];
         const uint32_t mflags = s.matFlags[in.material];
         isHit = true; hitMaterial = in.material;
-        setup_shading_state(s, in, inst, prim, h.y, h.z, worldRayDir, st, isFrontFace);   // chit:143
+        int32_t faceId;
+        setup_shading_state(s, in, inst, prim, h.y, h.z, worldRayDir, st, isFrontFace, faceId);   // chit:143
+        lowered = s.matLowered + (size_t) in.material * kLobeFloats;
         normal = st.normal;                                                            // chit:147
         mappedNormal = normal;
         if (TEX && (s.matTexRange[in.material].y | s.matPrimvarRange[in.material].y) != 0u) {
           for (int k = 0; k < GTLC_MATERIAL_PARAM_COUNT; k++) lp[k] = mp[k];
           apply_primvar_bindings(s, in, inst, prim, h.y, h.z, st, lp);
           hasMappedNormal = apply_texture_bindings(s, in.material, worldRayDir, st, lp, mappedNormal);
-          mp = lp;
+          mp = lp; lowered = nullptr;                                                  // per-hit inputs: the closure evaluates its constants itself
         }
         mediumIdx = VOL ? loopMediumIdx : payload_medium_idx(bitfield, 0u);            // chit:153
         thinWalled = (mflags & kMatFlagThinWalled) != 0;                               // chit:155-158
@@ -583,10 +624,9 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
           const V2 clipRange = unpackHalf2x16(ubo.clipRangePacked);                    // chit:227
           const float logDepth = 2.0f * logf(h.x / clipRange.x) / logf(clipRange.y / clipRange.x) - 1.0f;   // chit:228
           const int2 ids = s.instIds[inst];
-          const int32_t faceId = s.faceIds[in.faceBase + prim];
           const V3 tanAov = (st.tangent_u + v3(1.0f)) * 0.5f, bitAov = (st.tangent_v + v3(1.0f)) * 0.5f;   // chit:208,211
           const V3 posNormal = (normal + v3(1.0f)) * 0.5f;                             // chit:252
-          const V3 albedo = bsdf_albedo<MAXC>(closure, mp, -worldRayDir, st);         // chit:264-280
+          const V3 albedo = bsdf_albedo<MAXC>(closure, mp, lowered, -worldRayDir, st);         // chit:264-280
           const uint32_t fl = 1u | (thinWalled ? 2u : 0u) | (isDoubleSided ? 4u : 0u) | (NEE ? 16u : 0u);
           aov.a[0][slot] = make_float4((1.0f - h.y) - h.z, h.y, h.z, u2f(fl));         // chit:214
           aov.a[1][slot] = make_float4(st.u, st.v, 0.0f, logDepth);                    // chit:217
@@ -617,7 +657,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
         BsdfSample d;
         d.ior1 = iorCurrent; d.ior2 = iorOther; d.k1 = -worldRayDir;
         d.xi = rng1d_next4f(rng_state);                                              // chit:370
-        bsdf_sample<MAXC>(closure, mp, d, st);
+        bsdf_sample<MAXC>(closure, mp, lowered, d, st);
         eventType = (uint32_t) d.event_type;
         throughput *= d.bsdf_over_pdf;                                               // chit:386
         ray_dir = d.k2;                                                              // chit:388
@@ -655,7 +695,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
       if (neeValid) {
         BsdfEval e;
         e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = neeDir;
-        bsdf_evaluate<MAXC>(closure, mp, e, st);                                         // chit:425
+        bsdf_evaluate<MAXC>(closure, mp, lowered, e, st);                                         // chit:425
         neeValid = (e.pdf > 0.0f);
         if (neeValid) {
           const V2 diffuseSpecular = unpackHalf2x16(neeDiffuseSpecular);
