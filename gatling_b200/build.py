@@ -21,8 +21,7 @@ NVCC_FLAGS = [
     "-fmad=false",                      # explicit fmaf only: see device_math.cuh (bit-reproducible vs the CPU oracle)
     "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off,-fvisibility=hidden,-O3",
     "-Xptxas", "-v",
-] + (["-DGTLC_TRACE_MIN_BLOCKS=" + os.environ["GTLC_TRACE_MIN_BLOCKS"]] if os.environ.get("GTLC_TRACE_MIN_BLOCKS") else []) + [
-]
+] + ["-D%s=%s" % (k, os.environ[k]) for k in ("GTLC_TRACE_MIN_BLOCKS", "GTLC_SHADE_BIG_BLOCK", "GTLC_SHADE_PHASE_MASK") if os.environ.get(k)]
 
 
 def _nvcc():

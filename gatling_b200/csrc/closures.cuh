@@ -20,8 +20,10 @@ enum : int {
 };
 
 struct ShadingState { V3 normal, geom_normal, position, tangent_u, tangent_v; float u, v; uint32_t hitIndices[3]; };  // mdl_types.glsl:32-113 (+ renderer_state.hitIndices)
-struct BsdfSample { V3 ior1, ior2, k1, k2; V4 xi; float pdf; V3 bsdf_over_pdf; int event_type; };  // :158-170
-struct BsdfEval { V3 ior1, ior2, k1, k2; V3 bsdf_diffuse, bsdf_glossy; float pdf; };              // :173-184
+struct BsdfSample { V3 ior1, ior2, k1, k2; V4 xi; float pdf; V3 bsdf_over_pdf; int event_type; float memo[2]; };  // :158-170; memo: see BsdfEval
+// memo: view-dependent Fresnel terms (coat, base) that *_sample() already evaluated for the same state, k1 and IORs; a negative
+// entry means "not available" (the evaluation then computes it -- the same expression, hence the same bits)
+struct BsdfEval { V3 ior1, ior2, k1, k2; V3 bsdf_diffuse, bsdf_glossy; float pdf; float memo[2]; };              // :173-184
 
 constexpr float kMinAlpha = 1.0e-4f;
 
@@ -39,7 +41,8 @@ GTLC_D V3 cosine_hemisphere(float u, float v)
   float r, phi;
   if ((a * a) > (b * b)) { r = a; phi = (kPi / 4.0f) * (b / a); }
   else { r = b; phi = (kPi / 2.0f) - (kPi / 4.0f) * (a / b); }
-  float x = r * cosf(phi), y = r * sinf(phi);
+  const SinCos sc = sincos_of(phi);
+  float x = r * sc.c, y = r * sc.s;
   float z = sqrtf(fmaxf(0.0f, 1.0f - r * r));
   return v3(x, y, z);
 }
@@ -68,8 +71,9 @@ GTLC_D V3 ggx_sample_vndf(V3 Ve, float a, float u1, float u2)
   V3 T2 = cross(Vh, T1);
   float r = sqrtf(u1);
   float phi = (2.0f * kPi) * u2;
-  float t1 = r * cosf(phi);
-  float t2 = r * sinf(phi);
+  const SinCos sc = sincos_of(phi);
+  float t1 = r * sc.c;
+  float t2 = r * sc.s;
   float s = 0.5f * (1.0f + Vh.z);
   t2 = (1.0f - s) * sqrtf(fmaxf(0.0f, 1.0f - t1 * t1)) + s * t2;
   V3 Nh = (T1 * t1 + T2 * t2) + Vh * sqrtf(fmaxf(0.0f, (1.0f - t1 * t1) - t2 * t2));
@@ -168,6 +172,7 @@ GTLC_D float mat_directional_bias(int closure, const float* p) { return closure 
 // ---- closure 0: df::diffuse_reflection_bsdf(tint) --------------------------------------------
 GTLC_D void diffuse_sample(const float* p, BsdfSample& d, const ShadingState& s)
 {
+  d.memo[0] = -1.0f; d.memo[1] = -1.0f;
   Frame f = make_frame(s);
   V3 l = cosine_hemisphere(d.xi.x, d.xi.y);
   d.k2 = normalize(to_world(f, l));
@@ -207,6 +212,7 @@ GTLC_D UpsLobes ups_lobes(const float* p)
 
 GTLC_D void ups_sample(const float* p, BsdfSample& d, const ShadingState& s)
 {
+  d.memo[0] = -1.0f; d.memo[1] = -1.0f;
   UpsLobes u = ups_lobes(p);
   Frame f = make_frame(s);
   V3 k1 = to_local(f, d.k1);

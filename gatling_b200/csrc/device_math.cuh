@@ -47,6 +47,10 @@ GTLC_HD V3 mix(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
 GTLC_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 GTLC_HD float comp(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 
+// sin and cos of one angle with ONE argument reduction (CUDA sincosf: same 2-ulp bound as sinf / cosf)
+struct SinCos { float s, c; };
+GTLC_D SinCos sincos_of(float a) { SinCos r; sincosf(a, &r.s, &r.c); return r; }
+
 GTLC_D uint32_t f2u(float f) { return __float_as_uint(f); }
 GTLC_D float u2f(uint32_t u) { return __uint_as_float(u); }
 
@@ -120,7 +124,8 @@ GTLC_D V3 sample_hemisphere(V2 xi)
 {
   float a = sqrtf(xi.x);
   float b = kPi * 2.0f * xi.y;
-  return v3(a * cosf(b), a * sinf(b), sqrtf(1.0f - xi.x));
+  const SinCos sc = sincos_of(b);
+  return v3(a * sc.c, a * sc.s, sqrtf(1.0f - xi.x));
 }
 // common.glsl:223-230
 GTLC_D V3 sample_sphere(V2 xi, V3 radius)
@@ -128,7 +133,8 @@ GTLC_D V3 sample_sphere(V2 xi, V3 radius)
   float a = 1.0f - 2.0f * xi.x;
   float b = sqrtf(1.0f - a * a);
   float phi = 2.0f * kPi * xi.y;
-  return v3(b * cosf(phi), b * sinf(phi), a) * radius;
+  const SinCos sc = sincos_of(phi);
+  return v3(b * sc.c, b * sc.s, a) * radius;
 }
 // common.glsl:233-252
 GTLC_D V2 sample_disk(V2 xi, V2 radius)
@@ -138,7 +144,8 @@ GTLC_D V2 sample_disk(V2 xi, V2 radius)
   V2 r; float phi;
   if ((a * a) > (b * b)) { r.x = radius.x * a; r.y = radius.y * a; phi = (kPi / 4.0f) * (b / a); }
   else { r.x = radius.x * b; r.y = radius.y * b; phi = (kPi / 2.0f) - (kPi / 4.0f) * safe_div(a, b); }
-  V2 o; o.x = r.x * cosf(phi); o.y = r.y * sinf(phi);
+  const SinCos sc = sincos_of(phi);
+  V2 o; o.x = r.x * sc.c; o.y = r.y * sc.s;
   return o;
 }
 // common.glsl:254-257

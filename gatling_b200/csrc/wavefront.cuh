@@ -127,7 +127,8 @@ GTLC_D V2 fisGauss(V2 xi)
   float sigma = 0.375f;
   float r = sigma * sqrtf(-2.0f * logf(u1));
   float phi = 2.0f * kPi * u2;
-  V2 o; o.x = cosf(phi) * r; o.y = sinf(phi) * r;
+  const SinCos sc = sincos_of(phi);
+  V2 o; o.x = sc.c * r; o.y = sc.s * r;
   return o;
 }
 
@@ -271,7 +272,8 @@ GTLC_D void sampleLight(const UniformData& ubo, const DeviceScene& s, V4 k4, V3 
       orthonormal_basis(ls.dirToLight, t1, t2);
       float phi = ((k4.z * 2.0f) * kPi) - kPi;
       float theta = k4.w * angle;
-      ls.dirToLight = normalize(((t1 * cosf(phi) + t2 * sinf(phi)) * sinf(theta)) + ls.dirToLight * cosf(theta));
+      const SinCos sp = sincos_of(phi), st = sincos_of(theta);
+      ls.dirToLight = normalize(((t1 * sp.c + t2 * sp.s) * st.s) + ls.dirToLight * st.c);
     }
   } else if ((k4.x * total) <= (float) (ubo.sphereLightCount + ubo.distantLightCount + ubo.rectLightCount)) {   // :76
     const uint32_t n = ubo.rectLightCount;
@@ -405,7 +407,8 @@ GTLC_D void sampleVolumeScatteringDirection(V2 xi, float bias, V3& dir)
   const float phi = (2.0f * kPi) * xi.y;
   V3 t, b;
   orthonormal_basis(dir, t, b);
-  dir = ((t * sin_theta) * cosf(phi) + (b * sin_theta) * sinf(phi)) + dir * cos_theta;
+  const SinCos sc = sincos_of(phi);
+  dir = ((t * sin_theta) * sc.c + (b * sin_theta) * sc.s) + dir * cos_theta;
 }
 // rp_main_payload.glsl:76-89
 GTLC_D uint32_t payload_medium_idx(uint32_t bitfield, uint32_t mediumStackSize)
@@ -506,7 +509,10 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
 #ifndef GTLC_SHADE_SYNC_MIN_CLOSURE
 #define GTLC_SHADE_SYNC_MIN_CLOSURE GTLC_CLOSURE_OPENPBR
 #endif
-constexpr int shade_block_size(int maxClosure) { return (GTLC_SHADE_PHASE_SYNC && maxClosure >= GTLC_SHADE_SYNC_MIN_CLOSURE) ? 512 : 256; }   // Lambert / UsdPreviewSurface: small code, no barrier
+#ifndef GTLC_SHADE_BIG_BLOCK
+#define GTLC_SHADE_BIG_BLOCK 512
+#endif
+constexpr int shade_block_size(int maxClosure) { return (GTLC_SHADE_PHASE_SYNC && maxClosure >= GTLC_SHADE_SYNC_MIN_CLOSURE) ? GTLC_SHADE_BIG_BLOCK : 256; }   // Lambert / UsdPreviewSurface: small code, no barrier
 template <int MAXC, bool NEE, bool AOV, bool TEX, bool VOL>
 __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
@@ -536,6 +542,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
     const float* mp = nullptr; const float* lowered = nullptr; int closure = 0; bool doNee = false, isHit = false, isFrontFace = false, thinWalled = false, hasMappedNormal = false;
     V3 mappedNormal = v3(0.0f); uint32_t mediumIdx = 0, hitMaterial = 0;
     bool neeValid = false; V3 neeDir = v3(0.0f), neeRadiance = v3(0.0f); uint32_t neeDiffuseSpecular = 0;
+    float memo0 = -1.0f, memo1 = -1.0f;                                                // BsdfSample.memo -> BsdfEval.memo
     float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT : 1];                                     // textured inputs: private parameter block
     uint32_t bounce = 0, loopMediumIdx = 0;                                            // rgen:298, :318 (read before the trace)
     uint32_t media[kMaxMediumStack] = { 0u, 0u, 0u, 0u };
@@ -659,6 +666,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
         d.xi = rng1d_next4f(rng_state);                                              // chit:370
         bsdf_sample<MAXC>(closure, mp, lowered, d, st);
         eventType = (uint32_t) d.event_type;
+        if (!(TEX && hasMappedNormal)) { memo0 = d.memo[0]; memo1 = d.memo[1]; }      // the NEE evaluation below uses the unmapped normal (chit:397)
         throughput *= d.bsdf_over_pdf;                                               // chit:386
         ray_dir = d.k2;                                                              // chit:388
       }
@@ -694,7 +702,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformDa
     if (valid && doNee) {
       if (neeValid) {
         BsdfEval e;
-        e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = neeDir;
+        e.ior1 = iorCurrent; e.ior2 = iorOther; e.k1 = -worldRayDir; e.k2 = neeDir; e.memo[0] = memo0; e.memo[1] = memo1;
         bsdf_evaluate<MAXC>(closure, mp, lowered, e, st);                                         // chit:425
         neeValid = (e.pdf > 0.0f);
         if (neeValid) {
