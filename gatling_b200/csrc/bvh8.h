@@ -45,6 +45,8 @@ struct DefaultInitAllocator : std::allocator<T> {
 };
 template <class T> using RawVector = std::vector<T, DefaultInitAllocator<T>>;
 
+constexpr uint32_t kBvh8MaxDepth = 48;   // wide-tree depth the traversal kernels' stacks hold (traverse.cuh: kStackSize)
+
 struct Bvh8Node { uint32_t w[20]; };
 static_assert(sizeof(Bvh8Node) == 80, "BVH8 node must be 80 bytes");
 

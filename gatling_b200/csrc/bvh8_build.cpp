@@ -101,6 +101,8 @@ struct Builder {
   RawVector<Prim> prims;
   RawVector<BinNode> nodes;
   RawVector<Dp> dp;                      // filled bottom-up as the recursion unwinds: a node's row right after its children's
+  uint32_t depthCap = 0;                 // 0 = plain SAH; else no binary leaf below this depth (median splits where needed)
+  static uint32_t ceilLog2(uint32_t c) { return c <= 1u ? 0u : 32u - (uint32_t) __builtin_clz(c - 1u); }
 
   // The top of the tree is a handful of huge ranges: their passes are cut into chunks that run as tasks of the team
   // (min / max / counts merge exactly, so the tree does not depend on the chunking).
@@ -282,29 +284,29 @@ struct Builder {
   // Node ids are the pre-order of the binary tree: every leaf holds one triangle, so the subtree over `c` triangles has
   // exactly 2c - 1 nodes and the right child of `node` sits 2 (mid - begin) after it.  No shared counter, and a subtree is
   // one contiguous block for the collapse and emission passes that walk it afterwards.
-  void split(uint32_t node, uint32_t begin, uint32_t mid, uint32_t end, const Bounds4& lb, const Bounds4& rb, bool leftInline)
+  void split(uint32_t node, uint32_t begin, uint32_t mid, uint32_t end, const Bounds4& lb, const Bounds4& rb, bool leftInline, uint32_t depth)
   {
     BinNode& n = nodes[node];
     const uint32_t l = node + 1, r = node + 2 * (mid - begin);
     n.left = l; n.right = r; n.count = 0; n.first = begin; n.total = end - begin;
     if (end - begin > kTaskRange) {
-      if (leftInline) build(l, begin, mid, lb);
+      if (leftInline) build(l, begin, mid, lb, depth + 1);
       else {
-#pragma omp task default(shared) firstprivate(l, begin, mid, lb)
-        build(l, begin, mid, lb);
+#pragma omp task default(shared) firstprivate(l, begin, mid, lb, depth)
+        build(l, begin, mid, lb, depth + 1);
       }
-#pragma omp task default(shared) firstprivate(r, mid, end, rb)
-      build(r, mid, end, rb);
+#pragma omp task default(shared) firstprivate(r, mid, end, rb, depth)
+      build(r, mid, end, rb, depth + 1);
 #pragma omp taskwait
     } else {
-      build(l, begin, mid, lb);
-      build(r, mid, end, rb);
+      build(l, begin, mid, lb, depth + 1);
+      build(r, mid, end, rb, depth + 1);
     }
     solveNode(node);
   }
 
   // `bounds` = box of the triangles in [begin, end) and of their centroids, handed down by whoever partitioned them
-  void build(uint32_t node, uint32_t begin, uint32_t end, const Bounds4& bounds)
+  void build(uint32_t node, uint32_t begin, uint32_t end, const Bounds4& bounds, uint32_t depth)
   {
     const uint32_t count = end - begin;
     const uint32_t chunks = chunksOf(count), chunkLen = (count + chunks - 1) / chunks;
@@ -313,6 +315,13 @@ struct Builder {
     n.box = box;
     auto makeLeaf = [&]() { n.first = begin; n.count = count; n.total = count; n.left = n.right = 0; };
     if (count == 1) { makeLeaf(); solveNode(node); return; }
+    // Depth-capped rebuild (bvh8_build's second attempt, only after a first tree came out deeper than the traversal stack):
+    // once the levels left under the cap are just enough for a balanced subtree, split by index.
+    if (depthCap && depth + ceilLog2(count) >= depthCap) {
+      const uint32_t half = begin + count / 2;
+      split(node, begin, half, end, boundsOf(begin, half), boundsOf(half, end), false, depth);
+      return;
+    }
 
     float scaleA[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
     bool axisOk[3];
@@ -323,6 +332,18 @@ struct Builder {
     }
     const __m128 cLo = _mm_setr_ps(cbox.lo[0], cbox.lo[1], cbox.lo[2], 0.0f), scale = _mm_loadu_ps(scaleA);
     float bestCost = 3.402823466e38f; int bestAxis = -1; int bestBin = -1;
+    // Zero-area clusters (point triangles, axis-aligned collinear segments) make EVERY candidate cost 0; the strict
+    // comparison alone would then keep the lowest occupied bin and peel 1/16 of the range per level (depth in the
+    // hundreds).  Among zero-cost candidates the most balanced one wins; non-zero ties keep the first candidate.
+    uint32_t bestSkew = 0xFFFFFFFFu;
+    auto better = [&](float cost, uint32_t leftCount) {
+      if (cost < bestCost) { bestSkew = leftCount > count - leftCount ? 2 * leftCount - count : count - 2 * leftCount; return true; }
+      if (cost == 0.0f && bestCost == 0.0f) {
+        const uint32_t skew = leftCount > count - leftCount ? 2 * leftCount - count : count - 2 * leftCount;
+        if (skew < bestSkew) { bestSkew = skew; return true; }
+      }
+      return false;
+    };
 
     if (count <= kSmallNode) {
       // ---- the bottom of the tree (most nodes hold a handful of triangles): no bin arrays.  A split after an empty bin
@@ -354,7 +375,7 @@ struct Builder {
             else { rlo = _mm_min_ps(rlo, lo); rhi = _mm_max_ps(rhi, hi); }
           }
           const float cost = area4(llo, lhi) * (float) cl + area4(rlo, rhi) * (float) (count - cl);
-          if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+          if (better(cost, cl)) { bestCost = cost; bestAxis = axis; bestBin = b; }
         }
       }
     } else {
@@ -382,7 +403,7 @@ struct Builder {
         auto isBig = [&](const Prim& x) { return ((x.hi[0] - x.lo[0]) + (x.hi[1] - x.lo[1]) + (x.hi[2] - x.lo[2])) > bigLimit; };
         const uint32_t mid = (uint32_t) (std::stable_partition(prims.begin() + begin, prims.begin() + end, isBig) - prims.begin());
         const Bounds4 lb = boundsOf(begin, mid), rb = boundsOf(mid, end);
-        split(node, begin, mid, end, lb, rb, true);      // the few big triangles are built on the spot
+        split(node, begin, mid, end, lb, rb, true, depth);      // the few big triangles are built on the spot
         return;
       }
 
@@ -405,7 +426,7 @@ struct Builder {
           const int nb = __builtin_ctz(m);
           alo = _mm_min_ps(alo, bins.lo[axis][b]); ahi = _mm_max_ps(ahi, bins.hi[axis][b]); c += bc[b];
           const float cost = area4(alo, ahi) * (float) c + rightArea[nb] * (float) rightCount[nb];
-          if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+          if (better(cost, c)) { bestCost = cost; bestAxis = axis; bestBin = b; }
         }
       }
     }
@@ -430,7 +451,7 @@ struct Builder {
       if (mid == begin || mid == end) { mid = begin + count / 2; haveBounds = false; }
     }
     if (!haveBounds) { lb = boundsOf(begin, mid); rb = boundsOf(mid, end); }
-    split(node, begin, mid, end, lb, rb, false);
+    split(node, begin, mid, end, lb, rb, false, depth);
   }
 };
 
@@ -465,7 +486,7 @@ void bvh8_warm_up_threads()
   }
 }
 
-void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
+static void bvh8_build_once(const BuildTri* tris, size_t count, Bvh8& out, uint32_t depthCap)
 {
   auto t0 = std::chrono::steady_clock::now();
   out.nodes.clear(); out.tris.clear(); out.maxDepth = 0;
@@ -480,6 +501,7 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
   if (const char* e = getenv("GTLC_BVH_NODE_COST")) { float v = (float) atof(e); if (v > 0.0f) kNodeCost = v; }
   if (const char* e = getenv("GTLC_BVH_BIG_TRIS")) kBigTriFraction = (float) atof(e);
   Builder b;
+  b.depthCap = depthCap;
   b.prims.resize(N);
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < (int64_t) N; i++) {
@@ -501,7 +523,7 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
 #pragma omp single
   {
     const Bounds4 all = b.boundsOf(0, N);
-    b.build(0, 0, N, all);
+    b.build(0, 0, N, all, 0);
   }
 
   const auto tBinary = std::chrono::steady_clock::now();
@@ -670,6 +692,22 @@ void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
   if (getenv("GTLC_BUILD_TIMING")) {
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     fprintf(stderr, "[gtlc] host BVH8: binary SAH + collapse table %.0f ms, wide-node emission %.0f ms\n", ms(t0, tBinary), ms(tBinary, std::chrono::steady_clock::now()));
+  }
+}
+
+void bvh8_build(const BuildTri* tris, size_t count, Bvh8& out)
+{
+  uint32_t cap = 0u;
+  if (const char* e = getenv("GTLC_BVH_DEPTH_CAP")) cap = (uint32_t) std::max(0, atoi(e));    // tests: exercise the capped build directly
+  bvh8_build_once(tris, count, out, cap);
+  if (out.maxDepth > kBvh8MaxDepth) {
+    // SAH can legitimately produce chains (geometric progressions of triangle sizes peel one triangle per level).  The
+    // traversal stack is fixed, so such a scene is built again with a depth cap: SAH splits until the levels left are just
+    // enough for a balanced subtree, median splits below.  The wide tree is never deeper than the binary one.
+    const double first = out.buildSeconds;
+    if (getenv("GTLC_BUILD_TIMING")) fprintf(stderr, "[gtlc] host BVH8: wide depth %u > %u, rebuilding with a depth cap\n", out.maxDepth, kBvh8MaxDepth);
+    bvh8_build_once(tris, count, out, kBvh8MaxDepth - 4u);
+    out.buildSeconds += first;
   }
 }
 

@@ -8,6 +8,8 @@
 #include "sort.cuh"
 #include "bvh8_gpu.cuh"
 
+static_assert(gtlc::kStackSize == (int) gtlc::kBvh8MaxDepth, "traversal stack and builder depth limit must agree");
+
 #include <dlfcn.h>
 #include <nccl.h>   // types only: the library is dlopen'ed (gtlc_comm_*)
 
@@ -805,8 +807,9 @@ void gtlc_terminate(void)
   if (!g.initialized) return;
   cudaSetDevice(g.device);
   cudaDeviceSynchronize();
-  for (int k = 0; k < 2; k++) { cudaFree(g.q[k].rayO); cudaFree(g.q[k].rayD); cudaFree(g.q[k].thr); cudaFree(g.q[k].rad); cudaFree(g.q[k].slot); }
+  for (int k = 0; k < 2; k++) { cudaFree(g.q[k].rayO); cudaFree(g.q[k].rayD); cudaFree(g.q[k].thr); cudaFree(g.q[k].rad); cudaFree(g.q[k].slot); cudaFree(g.q[k].med); cudaFree(g.q[k].walk); }
   memset(g.q, 0, sizeof(g.q));
+  g.volumeCapacity = 0;
   cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.shSeed); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits); cudaFree(g.perm); cudaFree(g.sortHist); g.perm = nullptr; g.sortHist = nullptr;
   for (int k = 0; k < 6; k++) { cudaFree(g.aovSamples.a[k]); g.aovSamples.a[k] = nullptr; }
   g.aovCapacity = 0;
@@ -1066,7 +1069,9 @@ LIGHT_COMMON(SphereLight, TAG_SPHERE, sphereLights)
 LIGHT_COMMON(DistantLight, TAG_DISTANT, distantLights)
 LIGHT_COMMON(RectLight, TAG_RECT, rectLights)
 LIGHT_COMMON(DiskLight, TAG_DISK, diskLights)
-#define TOUCH(l) do { std::lock_guard<std::mutex> g2((l)->scene->mutex); (l)->scene->lightsDirty = true; (l)->scene->framebufferDirty = true; } while (0)
+// setters write the light's record under the scene lock: uploadLights / gtlc_render read it under the same lock
+#define LIGHT_LOCK(l) std::lock_guard<std::mutex> g2((l)->scene->mutex)
+#define LIGHT_MARK(l) do { (l)->scene->lightsDirty = true; (l)->scene->framebufferDirty = true; } while (0)
 
 GtlcHandle gtlc_sphere_light_create(GtlcHandle sh)
 {
@@ -1078,16 +1083,17 @@ GtlcHandle gtlc_sphere_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_sphere_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (s && l) destroy_SphereLight(s, l); }
-void gtlc_sphere_light_set_position(GtlcHandle h, const float* p) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l || !p) return; memcpy(l->data.pos, p, 12); TOUCH(l); }
-void gtlc_sphere_light_set_base_emission(GtlcHandle h, const float* c) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_sphere_light_set_position(GtlcHandle h, const float* p) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l || !p) return; LIGHT_LOCK(l); memcpy(l->data.pos, p, 12); LIGHT_MARK(l); }
+void gtlc_sphere_light_set_base_emission(GtlcHandle h, const float* c) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l || !c) return; LIGHT_LOCK(l); memcpy(l->data.baseEmission, c, 12); LIGHT_MARK(l); }
 void gtlc_sphere_light_set_radius(GtlcHandle h, float rx, float ry, float rz)
 {
   SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return;
   float ab = powf(rx * ry, 1.6f), ac = powf(rx * rz, 1.6f), bc = powf(ry * rz, 1.6f);    // Knud Thomsen, Gi.cpp:2637-2640
   float area = float(powf((ab + ac + bc) / 3.0f, 1.0f / 1.6f) * 4.0f * M_PI);
-  l->data.radiusXYZ[0] = rx; l->data.radiusXYZ[1] = ry; l->data.radiusXYZ[2] = rz; l->data.area = area; TOUCH(l);
+  LIGHT_LOCK(l);
+  l->data.radiusXYZ[0] = rx; l->data.radiusXYZ[1] = ry; l->data.radiusXYZ[2] = rz; l->data.area = area; LIGHT_MARK(l);
 }
-void gtlc_sphere_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+void gtlc_sphere_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { SphereLight* l = as<SphereLight>(h, TAG_SPHERE); if (!l) return; LIGHT_LOCK(l); l->data.diffuseSpecularPacked = packHalf2x16(d, sp); LIGHT_MARK(l); }
 
 GtlcHandle gtlc_distant_light_create(GtlcHandle sh)
 {
@@ -1098,16 +1104,17 @@ GtlcHandle gtlc_distant_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_distant_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (s && l) destroy_DistantLight(s, l); }
-void gtlc_distant_light_set_direction(GtlcHandle h, const float* d) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l || !d) return; memcpy(l->data.direction, d, 12); TOUCH(l); }
-void gtlc_distant_light_set_base_emission(GtlcHandle h, const float* c) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
+void gtlc_distant_light_set_direction(GtlcHandle h, const float* d) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l || !d) return; LIGHT_LOCK(l); memcpy(l->data.direction, d, 12); LIGHT_MARK(l); }
+void gtlc_distant_light_set_base_emission(GtlcHandle h, const float* c) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l || !c) return; LIGHT_LOCK(l); memcpy(l->data.baseEmission, c, 12); LIGHT_MARK(l); }
 void gtlc_distant_light_set_angle(GtlcHandle h, float angle)
 {
   DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return;
   float halfAngle = 0.5f * angle;                                       // Gi.cpp:2723-2726
   float invPdf = (halfAngle > 0.0f) ? float(2.0f * M_PI * (1.0f - cosf(halfAngle))) : 1.0f;
-  l->data.angle = angle; l->data.invPdf = invPdf; TOUCH(l);
+  LIGHT_LOCK(l);
+  l->data.angle = angle; l->data.invPdf = invPdf; LIGHT_MARK(l);
 }
-void gtlc_distant_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+void gtlc_distant_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { DistantLight* l = as<DistantLight>(h, TAG_DISTANT); if (!l) return; LIGHT_LOCK(l); l->data.diffuseSpecularPacked = packHalf2x16(d, sp); LIGHT_MARK(l); }
 
 GtlcHandle gtlc_rect_light_create(GtlcHandle sh)
 {
@@ -1120,11 +1127,11 @@ GtlcHandle gtlc_rect_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_rect_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); RectLight* l = as<RectLight>(h, TAG_RECT); if (s && l) destroy_RectLight(s, l); }
-void gtlc_rect_light_set_origin(GtlcHandle h, const float* o) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !o) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
-void gtlc_rect_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !t0 || !t1) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
-void gtlc_rect_light_set_base_emission(GtlcHandle h, const float* c) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
-void gtlc_rect_light_set_dimensions(GtlcHandle h, float w, float hh) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.width = w; l->data.height = hh; TOUCH(l); }
-void gtlc_rect_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+void gtlc_rect_light_set_origin(GtlcHandle h, const float* o) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !o) return; LIGHT_LOCK(l); memcpy(l->data.origin, o, 12); LIGHT_MARK(l); }
+void gtlc_rect_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !t0 || !t1) return; LIGHT_LOCK(l); l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); LIGHT_MARK(l); }
+void gtlc_rect_light_set_base_emission(GtlcHandle h, const float* c) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l || !c) return; LIGHT_LOCK(l); memcpy(l->data.baseEmission, c, 12); LIGHT_MARK(l); }
+void gtlc_rect_light_set_dimensions(GtlcHandle h, float w, float hh) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; LIGHT_LOCK(l); l->data.width = w; l->data.height = hh; LIGHT_MARK(l); }
+void gtlc_rect_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { RectLight* l = as<RectLight>(h, TAG_RECT); if (!l) return; LIGHT_LOCK(l); l->data.diffuseSpecularPacked = packHalf2x16(d, sp); LIGHT_MARK(l); }
 
 GtlcHandle gtlc_disk_light_create(GtlcHandle sh)
 {
@@ -1137,11 +1144,11 @@ GtlcHandle gtlc_disk_light_create(GtlcHandle sh)
   return handleOf(l);
 }
 void gtlc_disk_light_destroy(GtlcHandle sh, GtlcHandle h) { Scene* s = as<Scene>(sh, TAG_SCENE); DiskLight* l = as<DiskLight>(h, TAG_DISK); if (s && l) destroy_DiskLight(s, l); }
-void gtlc_disk_light_set_origin(GtlcHandle h, const float* o) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !o) return; memcpy(l->data.origin, o, 12); TOUCH(l); }
-void gtlc_disk_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !t0 || !t1) return; l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); TOUCH(l); }
-void gtlc_disk_light_set_base_emission(GtlcHandle h, const float* c) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !c) return; memcpy(l->data.baseEmission, c, 12); TOUCH(l); }
-void gtlc_disk_light_set_radius(GtlcHandle h, float rx, float ry) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.radiusX = rx; l->data.radiusY = ry; TOUCH(l); }
-void gtlc_disk_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; l->data.diffuseSpecularPacked = packHalf2x16(d, sp); TOUCH(l); }
+void gtlc_disk_light_set_origin(GtlcHandle h, const float* o) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !o) return; LIGHT_LOCK(l); memcpy(l->data.origin, o, 12); LIGHT_MARK(l); }
+void gtlc_disk_light_set_tangents(GtlcHandle h, const float* t0, const float* t1) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !t0 || !t1) return; LIGHT_LOCK(l); l->data.tangentFramePacked[0] = encodeDirection(t0); l->data.tangentFramePacked[1] = encodeDirection(t1); LIGHT_MARK(l); }
+void gtlc_disk_light_set_base_emission(GtlcHandle h, const float* c) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l || !c) return; LIGHT_LOCK(l); memcpy(l->data.baseEmission, c, 12); LIGHT_MARK(l); }
+void gtlc_disk_light_set_radius(GtlcHandle h, float rx, float ry) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; LIGHT_LOCK(l); l->data.radiusX = rx; l->data.radiusY = ry; LIGHT_MARK(l); }
+void gtlc_disk_light_set_diffuse_specular(GtlcHandle h, float d, float sp) { DiskLight* l = as<DiskLight>(h, TAG_DISK); if (!l) return; LIGHT_LOCK(l); l->data.diffuseSpecularPacked = packHalf2x16(d, sp); LIGHT_MARK(l); }
 
 // ---- dome light (Gi.cpp:2943-3000) -----------------------------------------------------------
 GtlcHandle gtlc_dome_light_create(GtlcHandle sh, uint32_t w, uint32_t hgt, const float* rgba)
@@ -1158,10 +1165,17 @@ GtlcHandle gtlc_dome_light_create(GtlcHandle sh, uint32_t w, uint32_t hgt, const
   }
   return handleOf(d);
 }
-void gtlc_dome_light_destroy(GtlcHandle h) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; if (d->dTexels) cudaFree(d->dTexels); { std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; } d->tag = 0; delete d; }
-void gtlc_dome_light_set_rotation(GtlcHandle h, const float* q) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d || !q) return; memcpy(d->rotation, q, 16); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
-void gtlc_dome_light_set_base_emission(GtlcHandle h, const float* c) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d || !c) return; memcpy(d->baseEmission, c, 12); std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
-void gtlc_dome_light_set_diffuse_specular(GtlcHandle h, float df, float sp) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; d->diffuse = df; d->specular = sp; std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
+void gtlc_dome_light_destroy(GtlcHandle h)
+{
+  DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return;
+  std::lock_guard<std::mutex> rl(g_renderMutex);      // a render in flight may be sampling the texels (gtlc_render holds this lock until its stream is idle)
+  { std::lock_guard<std::mutex> l(d->scene->mutex); d->scene->framebufferDirty = true; }
+  if (d->dTexels) { cudaSetDevice(g.device); cudaFree(d->dTexels); }
+  d->tag = 0; delete d;
+}
+void gtlc_dome_light_set_rotation(GtlcHandle h, const float* q) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d || !q) return; std::lock_guard<std::mutex> l(d->scene->mutex); memcpy(d->rotation, q, 16); d->scene->framebufferDirty = true; }
+void gtlc_dome_light_set_base_emission(GtlcHandle h, const float* c) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d || !c) return; std::lock_guard<std::mutex> l(d->scene->mutex); memcpy(d->baseEmission, c, 12); d->scene->framebufferDirty = true; }
+void gtlc_dome_light_set_diffuse_specular(GtlcHandle h, float df, float sp) { DomeLight* d = as<DomeLight>(h, TAG_DOME); if (!d) return; std::lock_guard<std::mutex> l(d->scene->mutex); d->diffuse = df; d->specular = sp; d->scene->framebufferDirty = true; }
 
 // ---- render buffers (Gi.cpp:2995-3006) -------------------------------------------------------
 GtlcHandle gtlc_render_buffer_create(uint32_t w, uint32_t h, int32_t format)
@@ -1233,6 +1247,12 @@ int gtlc_trace_rays(GtlcHandle h, const float* rays, uint32_t count, int32_t any
 {
   if (!requireInit()) return GTLC_ERROR;
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return GTLC_ERROR;
+  if ((count && !rays) || !hitsOut) { setError("gtlc_trace_rays: null ray / hit array"); return GTLC_ERROR; }
+  // tMin >= 0 is Vulkan's rule for traceRayEXT (VUID-RuntimeSpirv-OpRayQueryInitializeKHR-06351 / -RayTmin-06351), and the
+  // batched kernel relies on it: it orders hits by the raw bits of t, which equals float order only for t >= 0.
+  for (uint32_t i = 0; i < count; i++) {
+    if (rays[(size_t) i * 8 + 3] < 0.0f) { setError("gtlc_trace_rays: ray %u has tMin %g < 0 (tMin must be non-negative, as for traceRayEXT)", i, (double) rays[(size_t) i * 8 + 3]); return GTLC_ERROR; }
+  }
   std::lock_guard<std::mutex> rl(g_renderMutex);
   std::lock_guard<std::mutex> l(s->mutex);
   cudaSetDevice(g.device);
@@ -1404,6 +1424,12 @@ int gtlc_render(const GtlcRenderParams* params)
         paths += (uint64_t) wp.wavePixels * wp.waveSamples;
         timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.q[0], g.counters); });
         int inIdx = 0;
+        if (rs.maxBounces == 0) {
+          // The bounce loop never runs (as in rgen:290 the payload's radiance stays 0): the finished-sample slots the
+          // resolve kernels read would otherwise hold an earlier render's values.
+          CUDA_OK(cudaMemsetAsync(g.sampleRad, 0, (size_t) wp.wavePixels * wp.waveSamples * 16, g.stream));
+          if (aovMode) CUDA_OK(cudaMemsetAsync(g.aovSamples.a[0], 0, (size_t) wp.wavePixels * wp.waveSamples * 16, g.stream));
+        }
         for (uint32_t bounce = 0; bounce < rs.maxBounces; bounce++) {
           TraceParams P = makeTraceParams(s);
           P.zeroA = &g.counters->numPaths[inIdx ^ 1]; P.zeroB = &g.counters->numShadow; P.rayStat = &g.counters->stats[0];

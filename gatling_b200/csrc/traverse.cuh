@@ -23,7 +23,7 @@ namespace gtlc {
 #define GTLC_TRACE_MIN_BLOCKS 7   // 72 registers: 7 CTAs = 28 warps per SM (measured best of 6/7/8 on C2)
 #endif
 constexpr int kTraceBlock = 128;         // threads per CTA
-constexpr int kStackSize = 48;           // >= 2 x wide-tree depth (node groups + postponed triangle groups; checked on the host)
+constexpr int kStackSize = 48;           // >= wide-tree depth (one deferred node group per level; = kBvh8MaxDepth, checked on the host)
 constexpr int kRefillThreshold = 8;      // idle lanes that trigger a refill
 constexpr float kBoxPad = 1.0000004f;    // Ize 2013 robust slab padding
 

@@ -500,8 +500,11 @@ namespace gtl
     }
     size_t off = (size_t) consumed + 1;
     if (bytes.size() < off + (size_t) w * h * 12) { logError("truncated .pfm dome light texture"); return nullptr; }
+    if (!(scale < 0.0f)) { logError(std::string("big-endian .pfm dome light texture is not supported: ") + filePath); return nullptr; }   // scale < 0 marks little-endian samples
+    std::vector<float> rgb((size_t) w * h * 3);                       // the payload starts at an arbitrary byte offset: copy, do not alias
+    memcpy(rgb.data(), bytes.data() + off, rgb.size() * sizeof(float));
     std::vector<float> rgba((size_t) w * h * 4);
-    const float* src = reinterpret_cast<const float*>(bytes.data() + off);
+    const float* src = rgb.data();
     for (int y = 0; y < h; y++)          // PFM rows run bottom to top; the sampler's v = 0 row is the top of the image
       for (int x = 0; x < w; x++) {
         const float* s = src + ((size_t) (h - 1 - y) * w + x) * 3;

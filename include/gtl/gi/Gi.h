@@ -1,3 +1,21 @@
+//
+// The declarations in this header reproduce the public interface of gatling's gi library
+// (src/gi/gtl/gi/Gi.h), Copyright (C) 2019-2022 Pablo Delgado Krämer, so that its callers build
+// unchanged.  That interface is licensed as follows, and this header is distributed under the same terms:
+//
+// This program is free software: you can redistribute it and/or modify
+// it under the terms of the GNU General Public License as published by
+// the Free Software Foundation, either version 3 of the License, or
+// (at your option) any later version.
+//
+// This program is distributed in the hope that it will be useful,
+// but WITHOUT ANY WARRANTY; without even the implied warranty of
+// MERCHANTABILITY or FITNESS FOR A PARTICULAR PURPOSE. See the
+// GNU General Public License for more details.
+//
+// You should have received a copy of the GNU General Public License
+// along with this program. If not, see <https://www.gnu.org/licenses/>.
+//
 // gtl/gi/Gi.h -- source-compatible `gi` renderer API of the B200-native wavefront core.
 //
 // hdGatling (the Hydra render delegate) and the gatling CLI include <gtl/gi/Gi.h> and link the

@@ -420,7 +420,8 @@ GTLC_API void gtlc_get_stats(GtlcStats* stats);
  *   rays : count x 8 floats  (ox, oy, oz, tMin, dx, dy, dz, tMax)          [32 B, SURVEY 8d]
  *   hits : count x 5 x 4 B   (t, u, v, primitiveId(u32), instanceIndex(u32)) [20 B]; miss: t = -1,
  *          prim = inst = 0xFFFFFFFF.  For anyHit != 0 only `t` is meaningful (>=0 occluded, -1 free).
- *   visits : optional count x 2 uint32 (nodes, triangles) per-ray visit counts, or NULL. */
+ *   visits : optional count x 2 uint32 (nodes, triangles) per-ray visit counts, or NULL.
+ * tMin must be >= 0 (Vulkan's rule for traceRayEXT); a negative tMin is refused with GTLC_ERROR. */
 GTLC_API int gtlc_trace_rays(GtlcHandle scene, const float* rays, uint32_t count, int32_t anyHit,
                              void* hits, uint32_t* visits);
 

@@ -40,9 +40,9 @@ def gpu():
 @pytest.fixture(autouse=True)
 def _no_error_lines(request, _built_libraries):
     """The reference's graphical fixture fails a test on any GB_ERROR log line (src/hdGatling/main.cpp:78-100,531-549).
-    Same rule for the host-side tests here: a test that does not announce it (`logs_errors`) must not make the
-    library log an error.  (GPU tests are exempt until each has been looked at on the box.)"""
-    if request.node.get_closest_marker("gpu") or request.node.get_closest_marker("logs_errors"):
+    Same rule here, GPU tests included: a test that does not announce it (`logs_errors`) must not make the library log
+    an error."""
+    if request.node.get_closest_marker("logs_errors"):
         yield
         return
     from gatling_b200 import gi

@@ -189,3 +189,63 @@ def test_non_finite_triangles_are_inactive():
     assert np.array_equal(hits["t"], hits2["t"])
     hit = hits["t"] >= 0
     assert np.array_equal(hits["prim"][hit], keep[hits2["prim"][hit]])
+
+
+def _scene_with_extra_triangles(n_random, extra_pos):
+    """random_triangles(n_random) plus the triangles given as (k, 3, 3) positions, appended to the same mesh."""
+    d = scenes.random_triangles(n_random, 8, 8, spp=1)
+    m = d.meshes[0]
+    nv = len(m.vertices)
+    extra = np.zeros(len(extra_pos) * 3, m.vertices.dtype)
+    extra[:] = m.vertices[0]
+    extra["pos"] = np.asarray(extra_pos, np.float32).reshape(-1, 3)
+    m.vertices = np.concatenate([m.vertices, extra])
+    m.faces = np.concatenate([m.faces, (nv + np.arange(len(extra_pos) * 3, dtype=m.faces.dtype)).reshape(-1, 3)])
+    return d
+
+
+@pytest.mark.parametrize("case", ["collinear_in_soup", "points_on_a_line", "geometric_progression"])
+def test_degenerate_clusters_stay_shallow(case):
+    """Zero-area clusters make every SAH candidate cost 0 (the strict comparison alone peels 1/16 of the range per level),
+    and a geometric progression of sizes makes SAH peel ONE triangle per level: both used to exceed the traversal stack
+    and gtlc_scene_get_bvh refused the scene.  The reference's driver BVH renders such meshes."""
+    if case == "collinear_in_soup":
+        x = np.linspace(-0.9, 0.9, 200, dtype=np.float32)
+        pos = np.zeros((200, 3, 3), np.float32)
+        pos[:, 0, 0] = x; pos[:, 1, 0] = x + 0.001; pos[:, 2, 0] = x + 0.002     # segments on the x axis: zero-area boxes
+        d = _scene_with_extra_triangles(50000, pos)
+    elif case == "points_on_a_line":
+        x = np.linspace(-1, 1, 100000, dtype=np.float32)
+        pos = np.zeros((100000, 3, 3), np.float32)
+        pos[:, :, 1] = x[:, None]
+        d = _scene_with_extra_triangles(16, pos)
+    else:
+        k = np.arange(400)
+        s = (2.0 ** (-k * 0.25)).astype(np.float32)                              # each triangle 16 % smaller, nested at one corner
+        pos = np.zeros((400, 3, 3), np.float32)
+        pos[:, 1, 0] = s; pos[:, 2, 1] = s; pos[:, :, 2] = (k * 1e-4)[:, None]
+        d = _scene_with_extra_triangles(16, pos)
+    b = gi.BuiltScene(d)
+    try:
+        nodes, tris = gi.get_bvh(b.scene)          # raises when the builder refuses the scene
+    finally:
+        b.close()
+    assert len(tris) // 12 == d.triangle_count
+    rays = np.ascontiguousarray(random_rays(4000, 21), np.float32)
+    o = orc.OracleScene(d)
+    ref = o.trace(rays)
+    walk, visits = orc.bvh8_trace(nodes, tris, rays)
+    for key in ("prim", "inst", "t", "u", "v"):
+        assert np.array_equal(ref[key], walk[key]), key
+    o.close()
+
+
+def test_depth_capped_build_is_a_valid_tree(monkeypatch):
+    """The safety net behind the builder (a second build with a binary-depth cap when the first wide tree is deeper than the
+    traversal stack) cannot be reached with float coordinates once zero-cost ties are balanced, so it is exercised directly."""
+    d = scenes.random_triangles(30000, 8, 8, spp=1)
+    rays = np.ascontiguousarray(random_rays(8000, 5), np.float32)
+    _, _, plain = _check(d, rays)
+    monkeypatch.setenv("GTLC_BVH_DEPTH_CAP", "16")       # ceil(log2 30000) = 15: SAH only while its splits stay balanced, median splits otherwise
+    _, _, capped = _check(d, rays)
+    assert capped[:, 0].mean() > plain[:, 0].mean()     # a worse tree, but the same hits (checked by _check)

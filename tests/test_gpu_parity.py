@@ -128,6 +128,38 @@ def test_render_parity_settings_variants(gpu):
     _render_parity(gpu, d)
 
 
+def test_render_parity_dome_light(gpu):
+    """R11 (rp_main.miss:39-87) with data that can fail: a gradient lat-long dome with one hot texel, a rotation about all
+    three axes, and domeLightCameraVisible on / off, over an empty stage (pure mapping) and over the Cornell geometry (bounce
+    rays see the dome, primary rays the fallback).  The CPU suite pins the oracle's mapping to numpy (tests/test_dome_cpu.py)."""
+    from test_dome_cpu import empty_scene, gradient_dome
+    q = np.array([0.18, -0.37, 0.11, 0.0]); q[3] = np.sqrt(1.0 - (q[:3] ** 2).sum())
+    dome = scenes.DomeLight(gradient_dome(32, 16, hot=(9, 21)), rotation=tuple(float(x) for x in q), base_emission=(0.5, 2.0, 1.5))
+    for visible in (True, False):
+        e = empty_scene(96, 64, dome, domeLightCameraVisible=visible)
+        e.clear_color = (0.2, 0.4, 0.6, 1.0)
+        img, ref = _render_parity(gpu, e, rmse_bar=1e-4)
+        assert (img[..., :3].std() > 0.1) == visible              # a picture of the dome, or the flat fallback colour
+        c = scenes.cornell(64, 64, spp=8, max_bounces=4)
+        c.meshes = c.meshes[:3]                                   # open box: most bounce rays escape to the dome
+        c.dome_light = dome
+        c.clear_color = (0.2, 0.4, 0.6, 1.0)
+        c.settings = dataclasses.replace(c.settings, domeLightCameraVisible=visible)
+        _render_parity(gpu, c)
+    identity = scenes.DomeLight(dome.texels)                      # the rotation is not ignored
+    b = gpu.BuiltScene(empty_scene(96, 64, identity))
+    try:
+        plain = b.render().copy()
+    finally:
+        b.close()
+    b = gpu.BuiltScene(empty_scene(96, 64, dome))
+    try:
+        rotated = b.render().copy()
+    finally:
+        b.close()
+    assert np.abs(plain[..., :3] - rotated[..., :3] / np.array(dome.base_emission, np.float32)).max() > 0.3
+
+
 def test_render_empty_1x1(gpu):
     """Render.Empty1x1 of the reference's test-suite (src/hdGatling/main.cpp:584): no geometry, one pixel."""
     e = scenes.cornell(1, 1, spp=4)
@@ -201,6 +233,7 @@ def test_shard_sum_equals_full(gpu):
     assert np.array_equal(acc, full)
 
 
+@pytest.mark.logs_errors
 def test_errors_are_loud(gpu):
     d = scenes.cornell(16, 16, spp=1)
     b = gpu.BuiltScene(d)
@@ -447,6 +480,7 @@ def test_render_parity_textured_materials(gpu):
     assert np.array_equal(imgs[0], imgs[1])
 
 
+@pytest.mark.logs_errors
 def test_texture_errors_are_loud(gpu):
     assert gpu.giCreateTexture(np.zeros((0, 4, 4), np.uint8)) is None and "empty texture" in gpu.giLastError()
     s = gpu.giCreateScene()
@@ -464,6 +498,7 @@ def test_texture_errors_are_loud(gpu):
     gpu.giDestroyScene(s)
 
 
+@pytest.mark.logs_errors      # ends with a refused mediumStackSize
 def test_render_parity_volumes(gpu):
     """R14: medium stack (push / pop, nested media), free-flight sampling, Henyey-Greenstein scattering, NEE from inside
     nothing special (shadow rays are plain any-hit rays), against the oracle; plus the Beer-only mediumStackSize = 0 path."""
@@ -534,6 +569,7 @@ def test_full_size_properties_c2(gpu):
         b.close()
 
 
+@pytest.mark.logs_errors      # a too-short primvar is ignored, loudly
 def test_render_parity_primvars(gpu):
     """R15 scene data: material inputs read from mesh / instancer primvars (constant, instance, uniform, vertex
     interpolation; overrides, fallbacks) -- image and AOVs against the oracle."""
