@@ -10,6 +10,7 @@
   oracle's outputs; integer functions are additionally cross-checked against an independent numpy
   restatement in tests/test_oracle_kat.py.
 * cornell_oracle_32.npy -- float32 32x32 spp 4 oracle render of C1 (regression anchor for the oracle).
+* reference_lfs.json -- the Git-LFS pointers (sha256, size) of the reference's golden test images.
 * feature_anchors.npz  -- 32x32 spp 4 oracle renders of the texture / primvar / volume / cutout test scenes plus
   their ray counts: the -m gpu suite compares the CUDA path against these committed images as well as against a
   fresh oracle run, so an accidental change of the oracle itself cannot go unnoticed.
@@ -128,7 +129,32 @@ def feature_anchors():
     return out
 
 
+def reference_lfs_pointers():
+    """sha256 + size of every golden image of the reference's graphical tests (src/hdGatling/testenv/*/ref*.png).  The repository
+    snapshot holds Git-LFS pointers only; a pointer still pins the file bit for bit (tests/test_reference_pin.py reproduces the
+    one small enough to be reconstructed, Render.Empty1x1/ref.png)."""
+    base = "/root/reference/src/hdGatling/testenv"
+    out = {}
+    for case in sorted(os.listdir(base)):
+        d = os.path.join(base, case)
+        if not os.path.isdir(d):
+            continue
+        for f in sorted(os.listdir(d)):
+            if f.startswith("ref") and f.endswith(".png"):
+                with open(os.path.join(d, f), "rb") as fh:
+                    head = fh.read(200).decode("ascii", "replace")
+                if head.startswith("version https://git-lfs"):
+                    oid = [ln.split(":", 1)[1].strip() for ln in head.splitlines() if ln.startswith("oid sha256:")][0]
+                    size = [int(ln.split()[1]) for ln in head.splitlines() if ln.startswith("size ")][0]
+                    out["%s/%s" % (case, f)] = {"sha256": oid, "size": size}
+    return out
+
+
 def main():
+    with open(os.path.join(HERE, "reference_lfs.json"), "w") as f:
+        json.dump(reference_lfs_pointers(), f, indent=1, sort_keys=True)
+    if "--lfs-only" in sys.argv:
+        return
     ref = "/root/reference/cornell.usda"
     desc = usda.load(ref)
     with open(os.path.join(HERE, "scene_hashes.json"), "w") as f:
