@@ -22,14 +22,15 @@ class PrimvarBinding(C.Structure):
 
 
 class TextureDesc(C.Structure):
-    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("reserved", C.c_int32), ("texels", C.c_void_p)]
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("depth", C.c_uint32), ("texels", C.c_void_p)]
 
 
 class TextureBinding(C.Structure):
     _fields_ = [("paramIndex", C.c_int32), ("componentCount", C.c_int32), ("channels", C.c_int32 * 3), ("wrapU", C.c_int32),
                 ("wrapV", C.c_int32), ("srgb", C.c_int32), ("texture", C.c_uint64), ("fallback", C.c_float * 4),
                 ("scale", C.c_float * 4), ("bias", C.c_float * 4), ("uvRotation", C.c_float), ("uvScale", C.c_float * 2),
-                ("uvTranslation", C.c_float * 2), ("reserved", C.c_float)]
+                ("uvTranslation", C.c_float * 2), ("lookup", C.c_int32), ("wrapW", C.c_int32), ("xyzScale", C.c_float * 3),
+                ("xyzOffset", C.c_float * 3), ("reserved", C.c_int32)]
 
 
 class MaterialDesc(C.Structure):

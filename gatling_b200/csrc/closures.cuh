@@ -19,7 +19,7 @@ enum : int {
   BSDF_EVENT_REFLECTION = 8, BSDF_EVENT_TRANSMISSION = 16
 };
 
-struct ShadingState { V3 normal, geom_normal, position, tangent_u, tangent_v; float u, v; uint32_t hitIndices[3]; };  // mdl_types.glsl:32-113 (+ renderer_state.hitIndices)
+struct ShadingState { V3 normal, geom_normal, position, tangent_u, tangent_v; float u, v; uint32_t hitIndices[3]; V3 local_position; };  // mdl_types.glsl:32-113 (+ renderer_state.hitIndices)
 struct BsdfSample { V3 ior1, ior2, k1, k2; V4 xi; float pdf; V3 bsdf_over_pdf; int event_type; float memo[2]; };  // :158-170; memo: see BsdfEval
 // memo: view-dependent Fresnel terms (coat, base) that *_sample() already evaluated for the same state, k1 and IORs; a negative
 // entry means "not available" (the evaluation then computes it -- the same expression, hence the same bits)

@@ -59,11 +59,13 @@ struct Object { uint32_t tag; };
 struct Scene;
 
 // Textures are shared between materials (and scenes): reference counted, the creator holds one reference.
-struct Texture : Object { uint32_t width, height; int32_t format; void* dTexels; int refs; };
+struct Texture : Object { uint32_t width, height, depth; int32_t format; void* dTexels; int refs; };
 struct Material : Object { Scene* scene; int32_t closure; float params[GTLC_MATERIAL_PARAM_COUNT]; std::string name;
                            std::vector<GtlcTextureBinding> bindings; std::vector<Texture*> boundTextures;
                            struct PrimvarBinding { int32_t paramIndex, componentCount; std::string name; float fallback[4]; };
-                           std::vector<PrimvarBinding> primvarBindings; };
+                           std::vector<PrimvarBinding> primvarBindings;
+                           int opacityBinding = -1;   // index into `bindings` of the binding that feeds the cutout input (textured cutout), or -1
+                         };
 
 struct Mesh : Object {
   Scene* scene;
@@ -121,6 +123,7 @@ struct Scene : Object {
   Bvh8 bvh; bool bvhValid = false;        // host copy of the BVH8 (stale while bvhHostStale: built on the device, not yet read back)
   bool bvhHostStale = false; uint32_t nodeCount = 0, triCount = 0, maxDepth = 0, totalTris = 0;
   std::vector<float> hInstOpacity; DeviceArray<float> dInstOpacity;
+  DeviceArray<uint32_t> dMatOpacityBinding; DeviceArray<float> dMatOpacityConst; DeviceArray<CutoutScene> dCutoutScene;   // textured cutouts
   std::vector<uint2> hPrimvarInfos; std::vector<float> hPrimvarData; DeviceArray<uint2> dPrimvarInfos; DeviceArray<float> dPrimvarData;   // R15 scene data
   DeviceArray<DevicePrimvarBinding> dPrimvarBindings; DeviceArray<uint2> dMatPrimvarRange;
   std::vector<float> hFverts; std::vector<uint32_t> hFaces;
@@ -134,7 +137,7 @@ struct Scene : Object {
   struct MeshRange { uint32_t faceBase, faceCount, vertexBase; }; std::vector<MeshRange> meshRanges;
   DeviceArray<float4> dO2W, dW2O; DeviceArray<InstanceInfo> dInstInfo; DeviceArray<int2> dInstIds; DeviceArray<int32_t> dFaceIds; DeviceArray<uint32_t> dRankBase;
   DeviceArray<float> dMatParams; DeviceArray<int32_t> dMatClosure; DeviceArray<uint32_t> dMatFlags;
-  DeviceArray<DeviceTexture> dTextures; DeviceArray<DeviceTexBinding> dTexBindings; DeviceArray<uint2> dMatTexRange; bool hasTextures = false;
+  DeviceArray<DeviceTexture> dTextures; DeviceArray<DeviceTexBinding> dTexBindings; DeviceArray<uint2> dMatTexRange; bool hasTextures = false, hasTexturedCutout = false;
   DeviceArray<float4> dSphere, dDistant, dRect, dDisk;
   DeviceArray<uint32_t> dPixelMap; uint32_t pixelMapW = 0, pixelMapH = 0, pixelMapRank = 0, pixelMapCount = 1, pixelMapTile = 0, localPixels = 0;
   double lastBuildMs = 0.0;
@@ -313,8 +316,9 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
         const Mesh::Primvar* found = nullptr;
         for (const Mesh::Primvar& p : m->instancerPrimvars) if (p.name == want && !p.data.empty()) { found = &p; break; }
         for (const Mesh::Primvar& p : m->primvars) if (p.name == want && !p.data.empty()) { found = &p; break; }
-        if (found && found->type <= GTLC_PRIMVAR_VEC4) {           // float types only feed closure inputs
-          const uint32_t stride = (uint32_t) found->type + 1u;
+        if (found && found->type >= GTLC_PRIMVAR_FLOAT && found->type <= GTLC_PRIMVAR_INT4) {
+          const bool isInt = found->type >= GTLC_PRIMVAR_INT;        // read through scene_data_lookup_int (no interpolation), stored as its 32-bit patterns
+          const uint32_t stride = (uint32_t) (isInt ? found->type - GTLC_PRIMVAR_INT : found->type) + 1u;
           size_t need = 1;                                          // elements the lookup may index (get_scene_data_indices)
           if (found->interpolation == GTLC_INTERP_VERTEX) need = m->vertices.size();
           else if (found->interpolation == GTLC_INTERP_UNIFORM) need = m->faces.size();
@@ -323,7 +327,7 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
             for (size_t q = 0; q < ic; q++) { const int32_t id = q < m->instanceIds.size() ? m->instanceIds[q] : (int32_t) q; if (id >= 0) need = std::max(need, (size_t) id + 1); }
           }
           if (found->data.size() < need * stride * 4) { setError("primvar '%s' of mesh '%s' holds %zu bytes, its interpolation needs %zu: ignored", want.c_str(), m->name.c_str(), found->data.size(), need * stride * 4); s->hPrimvarInfos.push_back(info); continue; }
-          info = make_uint2((uint32_t) s->hPrimvarData.size(), stride | ((uint32_t) found->interpolation << 4) | 0x100u);
+          info = make_uint2((uint32_t) s->hPrimvarData.size(), stride | ((uint32_t) found->interpolation << 4) | 0x100u | (isInt ? 0x200u : 0u));
           const float* src = reinterpret_cast<const float*>(found->data.data());
           s->hPrimvarData.insert(s->hPrimvarData.end(), src, src + found->data.size() / 4);
         }
@@ -341,7 +345,7 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
       s->hW2O.insert(s->hW2O.end(), w2o, w2o + 12);
       s->hInstInfo.push_back({ vertexBase, faceBase, flags, matIndex });
       s->hRankBase.push_back(rank);   // rank of (inst, prim) = rankBase[inst] + prim, ascending in (inst, prim)
-      s->hInstOpacity.push_back(mat_cutout_opacity(m->material->closure, m->material->params));
+      s->hInstOpacity.push_back(m->material->opacityBinding >= 0 ? -1.0f : mat_cutout_opacity(m->material->closure, m->material->params));   // < 0: evaluated per hit
       rank += (uint32_t) m->faces.size();
       s->hInstIds.push_back(make_int2(m->id, k < m->instanceIds.size() ? m->instanceIds[k] : (int32_t) k));
       if (!hostBvh) continue;   // the device builder flattens on the GPU (lbvh_flatten_kernel, same arithmetic)
@@ -556,13 +560,16 @@ bool uploadMaterials(Scene* s)
   std::vector<float> params; std::vector<int32_t> closure; std::vector<uint32_t> flags;
   std::vector<DeviceTexture> textures; std::vector<Texture*> textureIndex; std::vector<DeviceTexBinding> bindings; std::vector<uint2> ranges;
   std::vector<DevicePrimvarBinding> pbindings; std::vector<uint2> pranges;
+  std::vector<uint32_t> opacityBinding; std::vector<float> opacityConst;
   const double kPi = 3.14159265358979323846;
   for (Material* m : s->flatMaterials) {
     params.insert(params.end(), m->params, m->params + GTLC_MATERIAL_PARAM_COUNT);
     closure.push_back(m->closure);
     flags.push_back((mat_is_emissive(m->closure, m->params) || !m->bindings.empty() || !m->primvarBindings.empty() ? kMatFlagEmissive : 0u) |   // a textured input may be the emission
                     (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u) |
-                    (mat_cutout_opacity(m->closure, m->params) < 1.0f ? kMatFlagCutout : 0u));
+                    (mat_cutout_opacity(m->closure, m->params) < 1.0f || m->opacityBinding >= 0 ? kMatFlagCutout : 0u));
+    opacityBinding.push_back(m->opacityBinding >= 0 ? (uint32_t) (bindings.size() + (size_t) m->opacityBinding) : 0xFFFFFFFFu);
+    opacityConst.push_back(mat_cutout_opacity(m->closure, m->params));
     ranges.push_back(make_uint2((uint32_t) bindings.size(), (uint32_t) m->bindings.size()));
     pranges.push_back(make_uint2((uint32_t) pbindings.size(), (uint32_t) m->primvarBindings.size()));
     for (const Material::PrimvarBinding& pb : m->primvarBindings) { DevicePrimvarBinding d; memset(&d, 0, sizeof(d)); d.paramIndex = pb.paramIndex; d.componentCount = pb.componentCount; memcpy(d.fallback, pb.fallback, 16); pbindings.push_back(d); }
@@ -571,11 +578,12 @@ bool uploadMaterials(Scene* s)
       Texture* t = m->boundTextures[b];
       uint32_t ti = 0;
       for (; ti < textureIndex.size(); ti++) if (textureIndex[ti] == t) break;
-      if (ti == textureIndex.size()) { textureIndex.push_back(t); textures.push_back({ t->dTexels, t->width, t->height, (uint32_t) t->format, 0u }); }
+      if (ti == textureIndex.size()) { textureIndex.push_back(t); textures.push_back({ t->dTexels, t->width, t->height, (uint32_t) t->format, t->depth }); }
       DeviceTexBinding d; memset(&d, 0, sizeof(d));
       d.paramIndex = src.paramIndex; d.texture = ti;
       d.packed = (uint32_t) src.componentCount | ((uint32_t) src.channels[0] << 4) | ((uint32_t) src.channels[1] << 6) | ((uint32_t) src.channels[2] << 8) |
-                 ((uint32_t) src.wrapU << 10) | ((uint32_t) src.wrapV << 12) | ((src.srgb ? 1u : 0u) << 14);
+                 ((uint32_t) src.wrapU << 10) | ((uint32_t) src.wrapV << 12) | ((src.srgb ? 1u : 0u) << 14) | ((uint32_t) src.lookup << 15) | (((uint32_t) src.wrapW & 3u) << 17);
+      for (int k = 0; k < 3; k++) { d.xyzScale[k] = src.xyzScale[k]; d.xyzOffset[k] = src.xyzOffset[k]; }
       memcpy(d.fallback, src.fallback, 16); memcpy(d.scale, src.scale, 16); memcpy(d.bias, src.bias, 16);
       d.uvCos = (float) cos((double) src.uvRotation * kPi / 180.0); d.uvSin = (float) sin((double) src.uvRotation * kPi / 180.0);
       d.uvScale[0] = src.uvScale[0]; d.uvScale[1] = src.uvScale[1]; d.uvTranslation[0] = src.uvTranslation[0]; d.uvTranslation[1] = src.uvTranslation[1];
@@ -583,6 +591,8 @@ bool uploadMaterials(Scene* s)
     }
   }
   s->hasTextures = !bindings.empty() || !pbindings.empty();
+  s->hasTexturedCutout = false;
+  for (uint32_t ob : opacityBinding) s->hasTexturedCutout = s->hasTexturedCutout || ob != 0xFFFFFFFFu;
   if (!s->dPrimvarBindings.upload(pbindings.data(), pbindings.size(), g.stream)) return false;
   if (!s->dMatPrimvarRange.upload(pranges.data(), pranges.size(), g.stream)) return false;
   if (!s->dMatParams.upload(params.data(), params.size(), g.stream)) return false;
@@ -591,6 +601,13 @@ bool uploadMaterials(Scene* s)
   if (!s->dTextures.upload(textures.data(), textures.size(), g.stream)) return false;
   if (!s->dTexBindings.upload(bindings.data(), bindings.size(), g.stream)) return false;
   if (!s->dMatTexRange.upload(ranges.data(), ranges.size(), g.stream)) return false;
+  if (!s->dMatOpacityBinding.upload(opacityBinding.data(), opacityBinding.size(), g.stream)) return false;
+  if (!s->dMatOpacityConst.upload(opacityConst.data(), opacityConst.size(), g.stream)) return false;
+  CutoutScene cut;                                    // what a textured cutout's any-hit test reads (geometry arrays are uploaded before the materials)
+  cut.sverts = (const uint32_t*) s->dSverts.ptr; cut.sfaces = (const uint32_t*) s->dSfaces.ptr; cut.instInfo = s->dInstInfo.ptr;
+  cut.texBindings = s->dTexBindings.ptr; cut.textures = s->dTextures.ptr;
+  cut.matOpacityBinding = s->dMatOpacityBinding.ptr; cut.matOpacityConst = s->dMatOpacityConst.ptr;
+  if (!s->dCutoutScene.upload(&cut, 1, g.stream)) return false;
   const uint32_t matCount = (uint32_t) closure.size();
   if (!s->dMatLowered.reserve((size_t) std::max(matCount, 1u) * kLobeFloats)) return false;
   if (matCount) lower_materials_kernel<<<(matCount + 63u) / 64u, 64, 0, g.stream>>>(s->dMatParams.ptr, s->dMatClosure.ptr, matCount, s->dMatLowered.ptr);
@@ -716,22 +733,30 @@ TraceParams makeTraceParams(Scene* s)
   P.stats = g.counters->stats;
   P.refillThreshold = g.tuning.reserved[0] > 0 ? g.tuning.reserved[0] : kRefillThreshold;
   P.triThreshold = g.tuning.reserved[2] > 0 ? g.tuning.reserved[2] : 8;
+  P.cut = s->hasTexturedCutout ? s->dCutoutScene.ptr : nullptr;
   return P;
 }
 
-template <int MODE> void launchTrace(const TraceParams& P, bool count, int blocks)
+template <int MODE, bool TEXCUT> void launchTraceT(const TraceParams& P, bool count, int blocks)
 {
-  if (count) { trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // visit counting: variant 0 order = the oracle's walk
-  if (P.aovFlags) { trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // only variant 0 writes the NEE debug AOV
+  if (count) { trace_kernel<MODE, true, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // visit counting: variant 0 order = the oracle's walk
+  if (P.aovFlags) { trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // only variant 0 writes the NEE debug AOV
   switch (g.tuning.traceVariant) {
-    case 1: trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;          // per-lane triangle loop (the order the oracle's walker restates)
-    case 6: trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;
+    case 1: trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;          // per-lane triangle loop (the order the oracle's walker restates)
+    case 6: if (TEXCUT) trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P);      // (the TMA variant has no textured-cutout form)
+            else trace_kernel_tma<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+            break;
     default:                                                                                    // 0 (default) and 7: warp-batched triangle tests
       // its queue entries pack (owner lane << 27 | triangle index): beyond 2^27 triangles the per-lane kernel takes over
-      if (g.currentTriCount >= (1u << 27)) trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, g.stream>>>(P);
-      else trace_kernel_batched<MODE><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+      if (g.currentTriCount >= (1u << 27)) trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P);
+      else trace_kernel_batched<MODE, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P);
       break;
   }
+}
+// Scenes with a textured cutout (TraceParams.cut set) run the instantiations whose any-hit test can evaluate a material input.
+template <int MODE> void launchTrace(const TraceParams& P, bool count, int blocks)
+{
+  if (P.cut) launchTraceT<MODE, true>(P, count, blocks); else launchTraceT<MODE, false>(P, count, blocks);
 }
 
 // _CalcDirtyFlagsForRenderParams (Gi.cpp:1859-1987), reduced to "does the accumulated image survive?"
@@ -874,7 +899,7 @@ void gtlc_scene_destroy(GtlcHandle h)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
-  s->dNodes.release(); s->dTris.release(); s->dNodesT.release(); s->dTrisT.release(); s->dSverts.release(); s->dSfaces.release(); s->dMatLowered.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release();
+  s->dNodes.release(); s->dTris.release(); s->dNodesT.release(); s->dTrisT.release(); s->dSverts.release(); s->dSfaces.release(); s->dMatLowered.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release(); s->dMatOpacityBinding.release(); s->dMatOpacityConst.release(); s->dCutoutScene.release();
   s->dMatParams.release(); s->dTextures.release(); s->dTexBindings.release(); s->dMatTexRange.release(); s->dPrimvarInfos.release(); s->dPrimvarData.release(); s->dPrimvarBindings.release(); s->dMatPrimvarRange.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
@@ -903,8 +928,8 @@ GtlcHandle gtlc_texture_create(const GtlcTextureDesc* d)
   if (!d || !d->texels || d->width == 0 || d->height == 0) { setError("gtlc_texture_create: empty texture"); return 0; }
   if (d->format < GTLC_TEX_RGBA8_UNORM || d->format > GTLC_TEX_RGBA32_FLOAT) { setError("gtlc_texture_create: unknown format %d", d->format); return 0; }
   cudaSetDevice(g.device);
-  Texture* t = new Texture(); t->tag = TAG_TEXTURE; t->width = d->width; t->height = d->height; t->format = d->format; t->refs = 1; t->dTexels = nullptr;
-  const size_t bytes = (size_t) d->width * d->height * texelBytes(d->format);
+  Texture* t = new Texture(); t->tag = TAG_TEXTURE; t->width = d->width; t->height = d->height; t->depth = d->depth > 1u ? d->depth : 1u; t->format = d->format; t->refs = 1; t->dTexels = nullptr;
+  const size_t bytes = (size_t) d->width * d->height * t->depth * texelBytes(d->format);
   if (cudaMalloc(&t->dTexels, bytes) != cudaSuccess || cudaMemcpy(t->dTexels, d->texels, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
     setError("gtlc_texture_create: device allocation of %zu bytes failed", bytes); cudaFree(t->dTexels); delete t; return 0;
   }
@@ -936,11 +961,24 @@ GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
     if (!okIndex || tb.componentCount < 1 || tb.componentCount > 3 || (tb.paramIndex == GTLC_BIND_NORMAL && tb.componentCount != 3)) { setError("gtlc_material_create: binding %u writes outside the parameter block", b); return 0; }
     for (int k = 0; k < 3; k++) if (tb.channels[k] < 0 || tb.channels[k] > 3) { setError("gtlc_material_create: binding %u has an invalid channel", b); return 0; }
     if (tb.wrapU < GTLC_WRAP_CLAMP || tb.wrapU > GTLC_WRAP_CLIP || tb.wrapV < GTLC_WRAP_CLAMP || tb.wrapV > GTLC_WRAP_CLIP) { setError("gtlc_material_create: binding %u has an invalid wrap mode", b); return 0; }
+    if (tb.lookup < GTLC_LOOKUP_FILTERED_2D || tb.lookup > GTLC_LOOKUP_TEXEL_3D) { setError("gtlc_material_create: binding %u has an invalid lookup mode %d", b, tb.lookup); return 0; }
+    if (tb.lookup >= GTLC_LOOKUP_FILTERED_3D && (tb.wrapW < GTLC_WRAP_CLAMP || tb.wrapW > GTLC_WRAP_CLIP)) { setError("gtlc_material_create: binding %u has an invalid wrap mode", b); return 0; }
+    if (tb.lookup < GTLC_LOOKUP_FILTERED_3D && t->depth > 1u) { setError("gtlc_material_create: binding %u reads a 3-D texture with a 2-D lookup", b); return 0; }
     bound.push_back(t);
   }
   Material* m = new Material(); m->tag = TAG_MATERIAL; m->scene = s; m->closure = d->closure; memcpy(m->params, d->params, sizeof(m->params));
   if (d->name) m->name = d->name;
   if (d->textureCount) m->bindings.assign(d->textures, d->textures + d->textureCount);
+  {                                                   // a binding that feeds the cutout input makes the any-hit test evaluate it per hit (the last one wins, as in shading)
+    const int opacityParam = d->closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE ? (int) GTLC_UPS_OPACITY : (d->closure == GTLC_CLOSURE_OPENPBR ? (int) GTLC_OPBR_GEOMETRY_OPACITY : -2);
+    for (uint32_t b = 0; b < d->textureCount; b++) {
+      const GtlcTextureBinding& tb = d->textures[b];
+      if (tb.paramIndex >= 0 && tb.paramIndex <= opacityParam && opacityParam < tb.paramIndex + tb.componentCount) {
+        if (tb.componentCount != 1) { setError("gtlc_material_create: binding %u writes the cutout input as part of a %d-component value; bind it on its own", b, tb.componentCount); delete m; return 0; }
+        m->opacityBinding = (int) b;
+      }
+    }
+  }
   for (uint32_t b = 0; b < d->primvarCount; b++) { Material::PrimvarBinding pb; pb.paramIndex = d->primvars[b].paramIndex; pb.componentCount = d->primvars[b].componentCount; pb.name = d->primvars[b].name ? d->primvars[b].name : ""; memcpy(pb.fallback, d->primvars[b].fallback, 16); m->primvarBindings.push_back(pb); }
   {
     std::lock_guard<std::mutex> dl(g_destroyMutex);

@@ -16,6 +16,7 @@
 // not depend on traversal order.
 #pragma once
 #include "device_math.cuh"
+#include "textures.cuh"
 
 namespace gtlc {
 
@@ -51,6 +52,22 @@ enum { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_SHADOW = 2 };
 constexpr int kDevNodeWords = 24;
 constexpr int kDevTriWords = 16;
 
+// Per-instance record (BlasPayload, rp_main.h:118-123, + CgpuBlasInstance hit-group index)
+struct InstanceInfo { uint32_t vertexBase, faceBase, flags, material; };
+constexpr int kShadeVertexWords = 16, kShadeFaceWords = 8;   // shading records, see wavefront.cuh (DeviceScene)
+
+// What the any-hit test of a TEXTURED cutout needs (rp_main.ahit:35-61 runs mdl_cutout_opacity on a full shading state;
+// the opacity input only ever depends on the texture coordinate / object-space position of the candidate hit).
+struct CutoutScene {
+  const uint32_t* __restrict__ sverts;              // kShadeVertexWords per vertex
+  const uint32_t* __restrict__ sfaces;              // kShadeFaceWords per face
+  const InstanceInfo* __restrict__ instInfo;
+  const DeviceTexBinding* __restrict__ texBindings;
+  const DeviceTexture* __restrict__ textures;
+  const uint32_t* __restrict__ matOpacityBinding;   // per material: index into texBindings of the binding that feeds the cutout input, or 0xFFFFFFFF
+  const float* __restrict__ matOpacityConst;        // per material: the constant cutout opacity (what a missing binding falls back to)
+};
+
 struct TraceParams {
   const uint32_t* __restrict__ nodes;   // kDevNodeWords per BVH8 node (traversal layout)
   const uint32_t* __restrict__ tris;    // kDevTriWords per triangle (traversal layout)
@@ -77,6 +94,7 @@ struct TraceParams {
   // Launch prologue (thread 0 of CTA 0), the wave loop's per-bounce bookkeeping folded into the kernel that needs it --
   // nothing in this kernel reads what it writes:  *zeroA = 0, *zeroB = 0, *rayStat += *numRays.
   uint32_t* zeroA; uint32_t* zeroB; unsigned long long* rayStat;
+  const CutoutScene* __restrict__ cut;          // device-resident; read by textured cutouts only (triangle opacity word < 0)
 };
 
 GTLC_D void trace_prologue(const TraceParams& P)
@@ -157,9 +175,42 @@ GTLC_D void ray_setup(RaySetup& r, float4 ro, float4 rd)
 // decision is a pure function of (ray seed, primitive, instance), so it does not depend on traversal order:
 // xi = uintAsFloat(hash_pcg32(seed ^ hash_theironborn(prim ^ inst * 0x9E3779B1))).  `opacity` rides in the spare
 // .w of the triangle record (1.0 = opaque, the common case costs one compare).
-GTLC_D bool cutout_ignored(const TraceParams& P, uint32_t rayIdx, float opacity, uint32_t prim, uint32_t inst)
+// mdl_cutout_opacity at a candidate hit of a textured-cutout triangle: the hit's uv / object-space position as
+// setup_shading_state computes them (mdl_shading_state.glsl:16-23, 61-64; same expressions as wavefront.cuh), then the
+// material's opacity binding, clamped like mat_cutout_opacity.  Out of line: the common any-hit test is one compare.
+__device__ __noinline__ float cutout_opacity_at(const CutoutScene* __restrict__ cs, uint32_t prim, uint32_t inst, float hu, float hv)
+{
+  const CutoutScene c = *cs;
+  const InstanceInfo in = c.instInfo[inst];
+  const uint32_t bi = c.matOpacityBinding[in.material];
+  if (bi == 0xFFFFFFFFu) return c.matOpacityConst[in.material];
+  const uint4 fr = __ldg((const uint4*) (c.sfaces + (size_t) (in.faceBase + prim) * kShadeFaceWords));
+  const uint32_t* vb = c.sverts + (size_t) in.vertexBase * kShadeVertexWords;
+  // words 0..2 position, 7 u, 11 v of each shading vertex
+  const uint4 a0 = __ldg((const uint4*) (vb + (size_t) fr.x * kShadeVertexWords)), a1 = __ldg((const uint4*) (vb + (size_t) fr.x * kShadeVertexWords + 4)), a2 = __ldg((const uint4*) (vb + (size_t) fr.x * kShadeVertexWords + 8));
+  const uint4 b0 = __ldg((const uint4*) (vb + (size_t) fr.y * kShadeVertexWords)), b1 = __ldg((const uint4*) (vb + (size_t) fr.y * kShadeVertexWords + 4)), b2 = __ldg((const uint4*) (vb + (size_t) fr.y * kShadeVertexWords + 8));
+  const uint4 c0 = __ldg((const uint4*) (vb + (size_t) fr.z * kShadeVertexWords)), c1 = __ldg((const uint4*) (vb + (size_t) fr.z * kShadeVertexWords + 4)), c2 = __ldg((const uint4*) (vb + (size_t) fr.z * kShadeVertexWords + 8));
+  const V3 bc = v3((1.0f - hu) - hv, hu, hv);
+  const V3 p0 = v3(u2f(a0.x), u2f(a0.y), u2f(a0.z)), p1 = v3(u2f(b0.x), u2f(b0.y), u2f(b0.z)), p2 = v3(u2f(c0.x), u2f(c0.y), u2f(c0.z));
+  const V3 localPos = (p0 * bc.x + p1 * bc.y) + p2 * bc.z;
+  const float stu = (bc.x * u2f(a1.w) + bc.y * u2f(b1.w)) + bc.z * u2f(c1.w);
+  const float stv = (bc.x * u2f(a2.w) + bc.y * u2f(b2.w)) + bc.z * u2f(c2.w);
+  const DeviceTexBinding& tb = c.texBindings[bi];
+  float ch[4];
+  eval_tex_binding(tb, c.textures, stu, stv, localPos, ch);
+  const float o = ch[(tb.packed >> 4) & 3u];
+  return o < 0.0f ? 0.0f : (o > 1.0f ? 1.0f : o);
+}
+
+// TEXCUT: the scene has textured cutouts (host dispatch on TraceParams.cut); the kernels of every other scene carry no call.
+template <bool TEXCUT>
+GTLC_D bool cutout_ignored(const TraceParams& P, uint32_t rayIdx, float opacity, uint32_t prim, uint32_t inst, float hu, float hv)
 {
   if (opacity >= 1.0f) return false;
+  if (TEXCUT && opacity < 0.0f) {                           // textured cutout: evaluate the material's opacity input at this hit
+    opacity = cutout_opacity_at(P.cut, prim, inst, hu, hv);
+    if (opacity >= 1.0f) return false;
+  }
   uint32_t seed = 0u;
   if (P.seedRad) seed = f2u(__ldg(&P.seedRad[rayIdx]).w);
   else if (P.seedU32) seed = __ldg(&P.seedU32[rayIdx]);
@@ -329,7 +380,7 @@ __global__ void __launch_bounds__(256) bvh8_repack_tris_kernel(const float4* __r
     triBase = nr.b[0]; triMask = hm & 0x00FFFFFFu; triValid = nr.a[3];                                         \
   } while (0)
 
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool TEXCUT = false>
 __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kernel(TraceParams P)
 {
   const unsigned FULL = 0xFFFFFFFFu;
@@ -400,7 +451,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
           float t, u, v;
           if (tri_intersect(r, v3(u2f(tr.a[0]), u2f(tr.a[1]), u2f(tr.a[2])), v3(u2f(tr.a[4]), u2f(tr.a[5]), u2f(tr.a[6])), v3(u2f(tr.b[0]), u2f(tr.b[1]), u2f(tr.b[2])), t, u, v)) {
             const uint32_t prim = tr.a[3], inst = tr.a[7];
-            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, u2f(tr.b[3]), prim, inst)) {
+            if (t > r.tmin && t < tmax && !cutout_ignored<TEXCUT>(P, rayIdx, u2f(tr.b[3]), prim, inst, u, v)) {
               if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
               const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
               if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
@@ -580,7 +631,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
           float t, u, v;
           if (tri_intersect(r, v3(u2f(tr.a[0]), u2f(tr.a[1]), u2f(tr.a[2])), v3(u2f(tr.a[4]), u2f(tr.a[5]), u2f(tr.a[6])), v3(u2f(tr.b[0]), u2f(tr.b[1]), u2f(tr.b[2])), t, u, v)) {
             const uint32_t prim = tr.a[3], inst = tr.a[7];
-            if (t > r.tmin && t < tmax && !cutout_ignored(P, rayIdx, u2f(tr.b[3]), prim, inst)) {
+            if (t > r.tmin && t < tmax && !cutout_ignored<false>(P, rayIdx, u2f(tr.b[3]), prim, inst, u, v)) {
               if (MODE != TRACE_CLOSEST) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; done = true; break; }
               const bool better = (bprim == 0xFFFFFFFFu) || (t < bt) || (t == bt && (inst < binst || (inst == binst && prim < bprim)));
               if (better) { bt = t; bu = u; bv = v; bprim = prim; binst = inst; }
@@ -627,7 +678,7 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
 // walker: +2.5 % node visits per step of delay), which the 32-wide triangle tests more than pay for.
 constexpr int kBatchQueueCap = 832;   // 31 left-overs + 32 lanes x 24 triangles of one node step, rounded up
 
-template <int MODE>
+template <int MODE, bool TEXCUT = false>
 __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kernel_batched(TraceParams P)
 {
   constexpr int kWarps = kTraceBlock / 32;
@@ -727,7 +778,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
             float t, u, v;
             if (tri_intersect(q, v3(u2f(tr.a[0]), u2f(tr.a[1]), u2f(tr.a[2])), v3(u2f(tr.a[4]), u2f(tr.a[5]), u2f(tr.a[6])), v3(u2f(tr.b[0]), u2f(tr.b[1]), u2f(tr.b[2])), t, u, v)) {
               hprim = tr.a[3]; hinst = tr.a[7];
-              if (t > r0.w && t < r1.w && !cutout_ignored(P, f2u(r2.w), u2f(tr.b[3]), hprim, hinst)) {
+              if (t > r0.w && t < r1.w && !cutout_ignored<TEXCUT>(P, f2u(r2.w), u2f(tr.b[3]), hprim, hinst, u, v)) {
                 key = ((unsigned long long) f2u(t) << 32) | (unsigned long long) tr.b[4];
                 won = key < atomicMin(&sKey[w][owner], key);
                 hu = u; hv = v;

@@ -52,8 +52,7 @@ enum : uint32_t {
   FLAG_PROGRESSIVE = 32u, FLAG_DOME_CAMERA_VISIBLE = 64u, FLAG_HAS_DOME = 128u
 };
 
-// Per-instance record (BlasPayload, rp_main.h:118-123, + CgpuBlasInstance hit-group index)
-struct InstanceInfo { uint32_t vertexBase, faceBase, flags, material; };
+// (InstanceInfo, the per-instance record, lives in traverse.cuh: the any-hit test of a textured cutout reads it too)
 constexpr uint32_t kMatFlagEmissive = 1u, kMatFlagThinWalled = 2u, kMatFlagCutout = 4u;
 
 struct DevicePrimvarBinding { int32_t paramIndex; int32_t componentCount; float fallback[4]; float pad[2]; };
@@ -64,7 +63,7 @@ struct DevicePrimvarBinding { int32_t paramIndex; int32_t componentCount; float 
 //     octahedral normal / tangent already decoded (decode_direction: 2 IEEE divisions + a normalize each, six per hit);
 //   shading face, 32 bytes = one 256-bit load: (i0, i1, i2, faceId, object-space geometric normal.xyz, -).
 // Same device functions, evaluated per vertex / face instead of per hit: the bits a hit sees do not change.
-constexpr int kShadeVertexWords = 16, kShadeFaceWords = 8;
+// (kShadeVertexWords = 16, kShadeFaceWords = 8: traverse.cuh)
 
 struct DeviceScene {
   const uint32_t* __restrict__ sverts;   // kShadeVertexWords per vertex
@@ -380,6 +379,7 @@ GTLC_D void setup_shading_state(const DeviceScene& s, const InstanceInfo in, uin
   st.u = (bc.x * u2f(a1[7]) + bc.y * u2f(b1[7])) + bc.z * u2f(c1[7]);                  // :61-64
   st.v = (bc.x * u2f(a2[3]) + bc.y * u2f(b2[3])) + bc.z * u2f(c2[3]);
   st.normal = normal; st.geom_normal = geomNormal; st.position = pos;                  // :82-90
+  st.local_position = localPos;                                                        // object space: the coordinate of 3-D texture bindings
   st.tangent_u = tangent; st.tangent_v = bitangent;
   st.hitIndices[0] = i0; st.hitIndices[1] = i1; st.hitIndices[2] = i2;                  // mdl_shading_state.glsl:66-79 (renderer state)
 }
@@ -447,6 +447,12 @@ GTLC_D void apply_primvar_bindings(const DeviceScene& s, const InstanceInfo in, 
     else if (interpolation == GTLC_INTERP_CONSTANT) i0 = i1 = i2 = 0u;
     else { i0 = st.hitIndices[0]; i1 = st.hitIndices[1]; i2 = st.hitIndices[2]; }
     const float* d = s.primvarData + info.x;
+    if (info.y & 0x200u) {                                           // scene_data_lookup_int{,2,3} :417-479: "nearest interpolation"
+      const uint32_t pick = bc.x > bc.y ? (bc.x > bc.z ? i0 : i2) : (bc.y > bc.z ? i1 : i2);
+      for (int c = 0; c < pb.componentCount; c++)
+        lp[pb.paramIndex + c] = c < (int) stride ? (float) (int32_t) f2u(__ldg(d + (size_t) pick * stride + c)) : pb.fallback[c];
+      continue;
+    }
     for (int c = 0; c < pb.componentCount; c++) {
       const float v0 = c < (int) stride ? __ldg(d + (size_t) i0 * stride + c) : 0.0f;
       const float v1 = c < (int) stride ? __ldg(d + (size_t) i1 * stride + c) : 0.0f;
@@ -466,17 +472,8 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
   bool hasNormal = false;
   for (uint32_t b = 0; b < range.y; b++) {
     const DeviceTexBinding& tb = s.texBindings[range.x + b];
-    const float su = st.u * tb.uvScale[0], sv = st.v * tb.uvScale[1];                   // UsdTransform2d: scale, rotate, translate
-    const float u = (su * tb.uvCos - sv * tb.uvSin) + tb.uvTranslation[0];
-    const float v = (su * tb.uvSin + sv * tb.uvCos) + tb.uvTranslation[1];
-    const int wrapU = (int) ((tb.packed >> 10) & 3u), wrapV = (int) ((tb.packed >> 12) & 3u);
-    bool clipped;
-    const V4 c = tex_lookup_float4_2d(s.textures[tb.texture], u, v, wrapU, wrapV, clipped);
-    float ch[4] = { c.x, c.y, c.z, c.w };
-    if (clipped) { ch[0] = tb.fallback[0]; ch[1] = tb.fallback[1]; ch[2] = tb.fallback[2]; ch[3] = tb.fallback[3]; }
-    if ((tb.packed >> 14) & 1u) { ch[0] = srgb_texture_to_linear(ch[0]); ch[1] = srgb_texture_to_linear(ch[1]); ch[2] = srgb_texture_to_linear(ch[2]); }
-#pragma unroll
-    for (int k = 0; k < 4; k++) ch[k] = ch[k] * tb.scale[k] + tb.bias[k];               // UsdUVTexture scale / bias
+    float ch[4];
+    eval_tex_binding(tb, s.textures, st.u, st.v, st.local_position, ch);
     const int count = (int) (tb.packed & 15u);
     float val[3] = { 0.0f, 0.0f, 0.0f };
     for (int k = 0; k < count && k < 3; k++) val[k] = ch[(tb.packed >> (4 + 2 * k)) & 3u];

@@ -89,9 +89,11 @@ def giDestroyScene(scene):
 def giCreateTexture(texels: np.ndarray):
     """Decoded image -> texture handle.  texels[row, col, channels], row 0 = bottom; dtype uint8 (RGBA8), float16 (RGBA16F),
     float32 with 1 channel (R32F) or 4 channels (RGBA32F).  (The reference decodes files through imgio, out of scope.)"""
-    t = S.Texture(np.ascontiguousarray(texels))
+    t = texels if isinstance(texels, S.Texture) else S.Texture(np.ascontiguousarray(texels))
+    t = S.Texture(np.ascontiguousarray(t.texels), t.depth)
     d = L.TextureDesc()
-    d.height, d.width = t.texels.shape[0], t.texels.shape[1]
+    d.height, d.width = t.rows_cols
+    d.depth = t.depth
     d.format = t.format
     d.texels = t.texels.ctypes.data
     return _lib().gtlc_texture_create(C.byref(d)) or None
@@ -114,6 +116,9 @@ def texture_binding_c(b: "S.TextureBinding", handle) -> "L.TextureBinding":
     c.uvRotation = b.uv_rotation
     c.uvScale = (C.c_float * 2)(*b.uv_scale)
     c.uvTranslation = (C.c_float * 2)(*b.uv_translation)
+    c.lookup, c.wrapW = b.lookup, b.wrap_w
+    c.xyzScale = (C.c_float * 3)(*b.xyz_scale)
+    c.xyzOffset = (C.c_float * 3)(*b.xyz_offset)
     return c
 
 
@@ -149,11 +154,12 @@ def _primvar_descs(primvars):
     arr = (L.PrimvarDesc * max(len(primvars), 1))()
     keep = []
     for i, p in enumerate(primvars):
-        a = np.ascontiguousarray(p.data, np.float32)
+        is_int = np.issubdtype(np.asarray(p.data).dtype, np.integer)
+        a = np.ascontiguousarray(p.data, np.int32 if is_int else np.float32)
         a = a.reshape(len(a), -1)
         keep.append(a)
         arr[i].name = p.name.encode()
-        arr[i].type = a.shape[1] - 1            # GTLC_PRIMVAR_FLOAT .. VEC4
+        arr[i].type = a.shape[1] - 1 + (4 if is_int else 0)    # GTLC_PRIMVAR_FLOAT .. VEC4, GTLC_PRIMVAR_INT .. INT4
         arr[i].interpolation = p.interpolation
         arr[i].data = a.ctypes.data
         arr[i].dataSize = a.nbytes
@@ -398,7 +404,7 @@ class BuiltScene:
     def __init__(self, desc: S.SceneDesc):
         self.desc = desc
         self.scene = giCreateScene()
-        self.textures = [giCreateTexture(t.texels) for t in desc.textures]
+        self.textures = [giCreateTexture(t) for t in desc.textures]
         if any(t is None for t in self.textures):
             raise RuntimeError("giCreateTexture failed: " + giLastError())
         self.materials = [giCreateMaterial(self.scene, m.closure, m.params, m.name, m.textures, self.textures, m.primvars) for m in desc.materials]

@@ -42,8 +42,9 @@ assert VERTEX_DTYPE.itemsize == 48
 @dataclasses.dataclass
 class Texture:
     """Decoded image; texels[row, col, channel] with row 0 = bottom (v = 0).  uint8 -> RGBA8 unorm, float16 -> RGBA16F,
-    float32 with 1 channel -> R32F, float32 with 4 channels -> RGBA32F."""
+    float32 with 1 channel -> R32F, float32 with 4 channels -> RGBA32F.  depth > 1: a 3-D texture, texels[slice, row, col, channel]."""
     texels: np.ndarray
+    depth: int = 1
 
     @property
     def format(self) -> int:
@@ -52,10 +53,16 @@ class Texture:
             return 0
         if t.dtype == np.float16:
             return 1
-        return 2 if (t.ndim == 2 or t.shape[2] == 1) else 3
+        return 2 if (t.ndim == 2 or t.shape[-1] == 1) else 3
+
+    @property
+    def rows_cols(self):
+        t = self.texels
+        return (t.shape[1], t.shape[2]) if self.depth > 1 else (t.shape[0], t.shape[1])
 
 
 WRAP_CLAMP, WRAP_REPEAT, WRAP_MIRRORED_REPEAT, WRAP_CLIP = 0, 1, 2, 3
+LOOKUP_FILTERED_2D, LOOKUP_TEXEL_2D, LOOKUP_FILTERED_3D, LOOKUP_TEXEL_3D = 0, 1, 2, 3    # GtlcTextureLookup
 BIND_NORMAL = -1
 
 
@@ -73,13 +80,17 @@ class TextureBinding:   # GtlcTextureBinding: UsdUVTexture (+ UsdTransform2d) fe
     uv_rotation: float = 0.0
     uv_scale: tuple = (1.0, 1.0)
     uv_translation: tuple = (0.0, 0.0)
+    lookup: int = LOOKUP_FILTERED_2D
+    wrap_w: int = WRAP_REPEAT
+    xyz_scale: tuple = (1.0, 1.0, 1.0)      # 3-D lookups: coordinate = object-space position * scale + offset
+    xyz_offset: tuple = (0.0, 0.0, 0.0)
 
 
 INTERP_CONSTANT, INTERP_INSTANCE, INTERP_UNIFORM, INTERP_VERTEX = 0, 1, 2, 3
 
 
 @dataclasses.dataclass
-class Primvar:           # GiPrimvarData (float types): data float32[elements, 1..4]
+class Primvar:           # GiPrimvarData: data float32[elements, 1..4] (Float..Vec4) or int32[elements, 1..4] (Int..Int4)
     name: str
     interpolation: int
     data: np.ndarray
@@ -528,6 +539,73 @@ def primvar_cornell(width=96, height=96, spp=8, max_bounces=5) -> SceneDesc:
     d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
     d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
     d.name = "primvar_cornell"
+    return d
+
+
+# ---- the other MDL runtime lookups + per-hit cutouts (R13 / R15 test scene) ----------------------------------
+def procedural_volume(size=8, seed=21, channels=4) -> Texture:
+    """Smooth RGBA32F (or R32F) 3-D texture, texels[slice, row, col, channel]."""
+    z, y, x = np.mgrid[0:size, 0:size, 0:size].astype(np.float32) / np.float32(size)
+    r = pcg32_uniform(seed, size ** 3 * 4).reshape(size, size, size, 4).astype(np.float32)
+    vol = np.stack([0.5 + 0.5 * np.sin(6.0 * x + 2.0 * z), 0.5 + 0.5 * np.cos(5.0 * y - 3.0 * x), 0.2 + 0.6 * r[..., 2], np.ones_like(x)], -1).astype(np.float32)
+    return Texture(np.ascontiguousarray(vol[..., :channels]), depth=size)
+
+
+def lookup_cornell(width=96, height=96, spp=8, max_bounces=5) -> SceneDesc:
+    """Cornell box that exercises what textured_cornell / primvar_cornell leave out: a cutout whose opacity is a TEXTURE
+    (alpha mask, filtered; rp_main.ahit:35-61 on both closest and shadow rays) on the tall box, a TEXEL-fetched blocky mask
+    on the short box together with a base colour from a filtered 3-D texture of the object-space position, a texel-fetched
+    3-D voxel colour on the back wall, a 3-D lookup with CLIP along w and its fallback on the left wall, and INTEGER primvars
+    (scene_data_lookup_int / _int3: nearest vertex, no interpolation) on the floor."""
+    d = cornell(width, height, spp, max_bounces)
+    for m in d.meshes:
+        assign_planar_uv(m)
+    size = 32
+    y, x = np.mgrid[0:size, 0:size]
+    holes = (((x // 4 + y // 4) % 3) != 0).astype(np.float32)                                        # 1/3 of the 4x4 blocks are holes
+    soft = np.clip(0.5 + 0.5 * np.sin(x * 0.9) * np.sin(y * 0.7), 0.0, 1.0).astype(np.float32)       # a soft-edged alpha in [0, 1]
+    mask_rgba = np.stack([np.full_like(soft, 0.8), np.full_like(soft, 0.7), np.full_like(soft, 0.3), soft], -1)
+    d.textures = [Texture((mask_rgba * 255 + 0.5).astype(np.uint8)),            # 0: RGBA8, opacity in alpha
+                  Texture(holes[::4, ::4][..., None].copy()),                    # 1: 8x8 R32F blocky mask (texel fetch)
+                  procedural_volume(8, 21),                                      # 2: 8^3 RGBA32F
+                  procedural_volume(4, 22)]                                      # 3: 4^3 RGBA32F (voxels)
+    T = TextureBinding
+    tall = material_usd_preview_surface("TallAlphaMask", diffuse=(0.2, 0.5, 0.9), opacity=1.0)
+    tall.textures = [T(UPS["opacity"], 0, (3,), WRAP_REPEAT, WRAP_REPEAT, uv_scale=(2.0, 2.0), uv_rotation=20.0),
+                     T(UPS["diffuse"], 0, (0, 1, 2), WRAP_REPEAT, WRAP_REPEAT, True, uv_scale=(2.0, 2.0), uv_rotation=20.0)]
+    short = material_openpbr("ShortBlockyMask", base_color=(0.8, 0.8, 0.8), specular_roughness=0.5)
+    short.textures = [T(OPBR["geometry_opacity"], 1, (0,), WRAP_REPEAT, WRAP_REPEAT, lookup=LOOKUP_TEXEL_2D, uv_scale=(0.6, 0.6), uv_translation=(0.2, 0.2)),
+                      T(OPBR["base_color"], 2, (0, 1, 2), WRAP_REPEAT, WRAP_MIRRORED_REPEAT, lookup=LOOKUP_FILTERED_3D, wrap_w=WRAP_CLAMP,
+                        xyz_scale=(0.9, 1.1, 0.7), xyz_offset=(0.3, 0.1, 0.25))]
+    back = material_usd_preview_surface("BackVoxels", diffuse=(0.5, 0.5, 0.5))
+    back.textures = [T(UPS["diffuse"], 3, (2, 0, 1), lookup=LOOKUP_TEXEL_3D, xyz_scale=(0.45, 0.45, 0.45), xyz_offset=(0.5, 0.5, 0.5))]     # outside the volume: (0, 0, 0)
+    left = material_usd_preview_surface("LeftClipW", diffuse=(1, 0, 0))
+    left.textures = [T(UPS["diffuse"], 2, (0, 1, 2), WRAP_REPEAT, WRAP_REPEAT, lookup=LOOKUP_FILTERED_3D, wrap_w=WRAP_CLIP, fallback=(0.9, 0.1, 0.6, 1.0),
+                       xyz_scale=(0.7, 0.7, 0.9), xyz_offset=(0.5, 0.5, 0.35))]
+    floor = material_usd_preview_surface("FloorIntPrimvars", diffuse=(0.5, 0.5, 0.5), roughness=0.6)
+    floor.primvars = [PrimvarBinding(UPS["diffuse"], 3, "colorBits", (0.1, 0.2, 0.9, 0.0)), PrimvarBinding(UPS["metallic"], 1, "metalFlag", (0.0, 0.0, 0.0, 0.0)),
+                      PrimvarBinding(UPS["clearcoat"], 1, "missingInt", (0.25, 0.0, 0.0, 0.0))]
+    mats = list(d.materials)
+    base = len(mats)
+    mats += [tall, short, back, left, floor]
+    assign = {"box1": 0, "box2": 1, "backplane": 2, "leftplane": 3, "bottomplane": 4}
+    for i, m in enumerate(d.meshes):
+        lname = m.name.lower()
+        for key, k in assign.items():
+            if key in lname:
+                m = dataclasses.replace(m, material=base + k)
+                if key in ("box1", "box2"):                  # see-through boxes must not z-fight with the floor they stand on
+                    xf = np.asarray(m.transform, np.float32).copy(); xf[3, 2] += 0.03
+                    m.transform = xf
+                if key == "bottomplane":
+                    nv = len(m.vertices)
+                    m.primvars = [Primvar("colorBits", INTERP_VERTEX, (np.arange(nv * 3).reshape(nv, 3) % 2).astype(np.int32)),      # int3 per vertex: nearest vertex wins
+                                  Primvar("metalFlag", INTERP_UNIFORM, (np.arange(len(m.faces)) % 2).astype(np.int32)[:, None])]     # int per face
+                d.meshes[i] = m
+    d.materials = mats
+    d.name = "lookup_cornell"
+    d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
+    d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
     return d
 
 

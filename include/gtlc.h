@@ -211,8 +211,8 @@ enum GtlcTextureFormat {
 typedef struct GtlcTextureDesc {
   uint32_t    width, height;
   int32_t     format;          /* GtlcTextureFormat */
-  int32_t     reserved;
-  const void* texels;          /* row 0 = bottom row (v = 0), as imgio delivers images (PngDecoder.cpp:78 flips) */
+  uint32_t    depth;           /* 0 or 1: 2-D image; > 1: 3-D texture of `depth` slices (textures_3d[], mdl_interface.glsl:45-125) */
+  const void* texels;          /* row 0 = bottom row (v = 0), as imgio delivers images (PngDecoder.cpp:78 flips); slices follow each other */
 } GtlcTextureDesc;
 /* No Gi.h counterpart: the reference creates images inside giCreateMaterialFrom* through its TextureManager
  * (TextureManager.cpp:100-274); here the caller decodes and hands texels over. */
@@ -222,6 +222,12 @@ GTLC_API void       gtlc_texture_destroy(GtlcHandle texture);   /* deferred whil
 enum GtlcTextureWrap {           /* mdl_types.glsl:117-120 */
   GTLC_WRAP_CLAMP = 0, GTLC_WRAP_REPEAT = 1, GTLC_WRAP_MIRRORED_REPEAT = 2, GTLC_WRAP_CLIP = 3
 };
+/* Which MDL runtime lookup a binding performs (the reference's generated code picks one per call site):
+ *   FILTERED_2D  tex_lookup_float4_2d (mdl_interface.glsl:127-145) at the transformed uv
+ *   TEXEL_2D     tex_texel_float4_2d  (:167-185) at ivec2(floor(uv' * resolution)); (0,0,0,0) outside the image
+ *   FILTERED_3D  tex_lookup_float4_3d (:45-64) at xyz = object-space hit position * xyzScale + xyzOffset
+ *   TEXEL_3D     tex_texel_float4_3d  (:91-110) at ivec3(floor(xyz * resolution)); (0,0,0,0) outside the volume */
+enum GtlcTextureLookup { GTLC_LOOKUP_FILTERED_2D = 0, GTLC_LOOKUP_TEXEL_2D = 1, GTLC_LOOKUP_FILTERED_3D = 2, GTLC_LOOKUP_TEXEL_3D = 3 };
 #define GTLC_BIND_NORMAL (-1)    /* paramIndex: the value is a tangent-space normal (UsdPreviewSurface `normal`, OpenPBR
                                     `geometry_normal`): shading normal = normalize(T x + B y + N z), then mdl_adapt_normal
                                     (mdl_interface.glsl:238-256) */
@@ -237,12 +243,20 @@ typedef struct GtlcTextureBinding {
   float      scale[4], bias[4];  /* UsdUVTexture: value = texel * scale + bias, per source channel */
   float      uvRotation;         /* UsdTransform2d: degrees, counter-clockwise */
   float      uvScale[2], uvTranslation[2];   /* uv' = rotate(uv * scale) + translation */
-  float      reserved;
+  int32_t    lookup;             /* GtlcTextureLookup (0 = filtered 2-D, the MaterialX image node) */
+  int32_t    wrapW;              /* 3-D lookups: GtlcTextureWrap along the third axis */
+  float      xyzScale[3], xyzOffset[3];      /* 3-D lookups: texture coordinate = object-space position * scale + offset */
+  int32_t    reserved;
 } GtlcTextureBinding;
+/* A binding whose paramIndex is the closure's cutout input (GTLC_UPS_OPACITY / GTLC_OPBR_GEOMETRY_OPACITY) makes the
+ * cutout per hit: the traversal kernels evaluate it in their any-hit test from the candidate hit's barycentrics, as
+ * rp_main.ahit:35-61 evaluates mdl_cutout_opacity on a full shading state. */
 
 /* A material input read from a primvar of the hit mesh (MaterialX geompropvalue / UsdPrimvarReader -> MDL
  * scene_data_lookup_float{,2,3}, mdl_interface.glsl:266-479): value = v0 bc.x + v1 bc.y + v2 bc.z over the elements the
- * primvar's interpolation selects; `fallback` when the mesh has no float primvar of that name. */
+ * primvar's interpolation selects; `fallback` when the mesh has no primvar of that name.  Integer primvars
+ * (GTLC_PRIMVAR_INT..INT4) go through scene_data_lookup_int{,2,3} (:417-479): no interpolation, the element of the vertex
+ * with the largest barycentric weight, converted to float as it enters the parameter block. */
 #define GTLC_MAX_PRIMVAR_BINDINGS 8
 typedef struct GtlcPrimvarBinding {
   int32_t     paramIndex;      /* first float of GtlcMaterialDesc.params that receives the value */

@@ -364,6 +364,12 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
       else if (interpolation == GTLC_INTERP_INSTANCE) idx[0] = idx[1] = idx[2] = in.instanceId > 0 ? (uint32_t) in.instanceId : 0u;
       else if (interpolation == GTLC_INTERP_CONSTANT) idx[0] = idx[1] = idx[2] = 0u;
       const float* dta = &s.primvarData[info[0]];
+      if (info[1] & 0x200u) {                                                                   // scene_data_lookup_int{,2,3} :417-479: nearest vertex, no interpolation
+        const uint32_t pick = bc.x > bc.y ? (bc.x > bc.z ? idx[0] : idx[2]) : (bc.y > bc.z ? idx[1] : idx[2]);
+        for (int cidx = 0; cidx < pbs[k].componentCount; cidx++)
+          mat.p[pbs[k].paramIndex + cidx] = cidx < (int) stride ? (float) (int32_t) floatBitsToUint(dta[(size_t) pick * stride + cidx]) : pbs[k].fallback[cidx];
+        continue;
+      }
       for (int cidx = 0; cidx < pbs[k].componentCount; cidx++) {
         float v[3];
         for (int q = 0; q < 3; q++) v[q] = cidx < (int) stride ? dta[(size_t) idx[q] * stride + cidx] : 0.0f;
@@ -372,7 +378,7 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
     }
   }
   if (!s.materialTextures.empty() && !s.materialTextures[in.material].empty())
-    hasMappedNormal = apply_texture_bindings(s.textures, s.materialTextures[in.material], st.text_coords.x, st.text_coords.y, worldRayDir,
+    hasMappedNormal = apply_texture_bindings(s.textures, s.materialTextures[in.material], st.text_coords.x, st.text_coords.y, st.local_position, worldRayDir,
                                              st.geom_normal, st.normal, st.tangent_u, st.tangent_v, mat.p, mappedNormal);
 
   V3 throughput = p.throughput;
@@ -413,7 +419,7 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
     aov->instanceId = in.instanceId;                                      // :243
     aov->doubleSided = isDoubleSided;                                     // :247
     aov->posNormal = (normal + v3(1.0f)) * 0.5f;                          // :252
-    aov->cutoutOpacity = (mat_cutout_opacity(base) < 1.0f) ? mat_cutout_opacity(mat) : -1.0f;
+    aov->cutoutOpacity = (mat_cutout_opacity(base) < 1.0f || s.materialOpacityBinding[in.material] >= 0) ? mat_cutout_opacity(mat) : -1.0f;
     aov->albedo = bsdf_albedo(mat, -worldRayDir, st);                     // :264-280 (front-face BSDF; no backface BSDFs exist here)
   }
 
@@ -655,12 +661,17 @@ void* orc_scene_create(const OrcSceneDesc* d)
     const GtlcMaterialDesc& md = d->materials[i];
     s->materialTextures.emplace_back(md.textures, md.textures + (md.textures ? md.textureCount : 0));
     s->materialPrimvars.emplace_back(md.primvars, md.primvars + (md.primvars ? md.primvarCount : 0));
+    int ob = -1;                                          // the binding that feeds the cutout input (the last one wins, as in shading)
+    const int opacityParam = m.closure == GTLC_CLOSURE_USD_PREVIEW_SURFACE ? (int) GTLC_UPS_OPACITY : (m.closure == GTLC_CLOSURE_OPENPBR ? (int) GTLC_OPBR_GEOMETRY_OPACITY : -2);
+    for (uint32_t b = 0; md.textures && b < md.textureCount; b++)
+      if (md.textures[b].componentCount == 1 && md.textures[b].paramIndex == opacityParam) ob = (int) b;
+    s->materialOpacityBinding.push_back(ob);
   }
   for (uint32_t i = 0; i < d->textureCount; i++) {
     const GtlcTextureDesc& td = d->textures[i];
-    Texture t; t.width = td.width; t.height = td.height; t.format = td.format;
+    Texture t; t.width = td.width; t.height = td.height; t.depth = td.depth > 1u ? td.depth : 1u; t.format = td.format;
     const size_t bpt = td.format == GTLC_TEX_RGBA8_UNORM ? 4 : td.format == GTLC_TEX_RGBA16_FLOAT ? 8 : td.format == GTLC_TEX_R32_FLOAT ? 4 : 16;
-    t.data.assign((const uint8_t*) td.texels, (const uint8_t*) td.texels + (size_t) td.width * td.height * bpt);
+    t.data.assign((const uint8_t*) td.texels, (const uint8_t*) td.texels + (size_t) td.width * td.height * t.depth * bpt);
     s->textures.push_back(t);
   }
   if (d->primvarInfos) s->primvarInfos.assign(d->primvarInfos, d->primvarInfos + (size_t) d->instanceCount * GTLC_MAX_PRIMVAR_BINDINGS * 2);
@@ -957,5 +968,27 @@ extern "C" int orc_tex_lookup(const GtlcTextureDesc* tex, float u, float v, int 
   V4 r = tex_lookup_float4_2d(t, u, v, wrapU, wrapV, clipped);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
   return clipped ? 1 : 0;
+}
+static Texture texture_from_desc(const GtlcTextureDesc* tex)
+{
+  Texture t; t.width = tex->width; t.height = tex->height; t.depth = tex->depth > 1u ? tex->depth : 1u; t.format = tex->format;
+  const size_t bpt = tex->format == GTLC_TEX_RGBA8_UNORM ? 4 : tex->format == GTLC_TEX_RGBA16_FLOAT ? 8 : tex->format == GTLC_TEX_R32_FLOAT ? 4 : 16;
+  t.data.assign((const uint8_t*) tex->texels, (const uint8_t*) tex->texels + (size_t) tex->width * tex->height * t.depth * bpt);
+  return t;
+}
+// ... the 3-D lookup (mdl_interface.glsl:45-64) and the texel fetches (:91-110, :167-185)
+extern "C" int orc_tex_lookup_3d(const GtlcTextureDesc* tex, float u, float v, float w, int wrapU, int wrapV, int wrapW, float* out)
+{
+  const Texture t = texture_from_desc(tex);
+  bool clipped;
+  V4 r = tex_lookup_float4_3d(t, u, v, w, wrapU, wrapV, wrapW, clipped);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+  return clipped ? 1 : 0;
+}
+extern "C" void orc_tex_texel(const GtlcTextureDesc* tex, int x, int y, int z, float* out)
+{
+  const Texture t = texture_from_desc(tex);
+  V4 r = tex_texel_float4(t, x, y, z);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 extern "C" float orc_srgb_texture_to_linear(float c) { return srgb_texture_to_linear(c); }

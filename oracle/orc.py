@@ -20,14 +20,15 @@ def build(force=False):
 
 
 class TextureDesc(C.Structure):  # GtlcTextureDesc
-    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("reserved", C.c_int32), ("texels", C.c_void_p)]
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_int32), ("depth", C.c_uint32), ("texels", C.c_void_p)]
 
 
 class TextureBinding(C.Structure):  # GtlcTextureBinding
     _fields_ = [("paramIndex", C.c_int32), ("componentCount", C.c_int32), ("channels", C.c_int32 * 3), ("wrapU", C.c_int32),
                 ("wrapV", C.c_int32), ("srgb", C.c_int32), ("texture", C.c_uint64), ("fallback", C.c_float * 4),
                 ("scale", C.c_float * 4), ("bias", C.c_float * 4), ("uvRotation", C.c_float), ("uvScale", C.c_float * 2),
-                ("uvTranslation", C.c_float * 2), ("reserved", C.c_float)]
+                ("uvTranslation", C.c_float * 2), ("lookup", C.c_int32), ("wrapW", C.c_int32), ("xyzScale", C.c_float * 3),
+                ("xyzOffset", C.c_float * 3), ("reserved", C.c_int32)]
 
 
 class PrimvarBinding(C.Structure):  # GtlcPrimvarBinding
@@ -273,6 +274,9 @@ class OracleScene:
                     arr[k].uvRotation = b.uv_rotation
                     arr[k].uvScale = (C.c_float * 2)(*b.uv_scale)
                     arr[k].uvTranslation = (C.c_float * 2)(*b.uv_translation)
+                    arr[k].lookup, arr[k].wrapW = b.lookup, b.wrap_w
+                    arr[k].xyzScale = (C.c_float * 3)(*b.xyz_scale)
+                    arr[k].xyzOffset = (C.c_float * 3)(*b.xyz_offset)
                 self._keep.append(arr)
                 self.mats[i].textures = arr
                 self.mats[i].textureCount = len(m.textures)
@@ -309,7 +313,7 @@ class OracleScene:
             d.domeRotation = (C.c_float * 4)(*desc.dome_light.rotation)
             d.domeEmission = (C.c_float * 3)(*desc.dome_light.base_emission)
         # scene data (Gi.cpp:905-1018): per instance, the primvar each binding of its material resolves to --
-        # mesh primvars override instancer primvars; too-short arrays and integer types count as "not found"
+        # mesh primvars override instancer primvars; too-short arrays count as "not found"
         if any(getattr(m, "primvars", None) for m in desc.materials):
             infos = np.zeros((len(self.instances), MAX_PRIMVAR_BINDINGS, 2), np.uint32)
             chunks, offset, row = [], 0, 0
@@ -325,13 +329,14 @@ class OracleScene:
                     if found is None:
                         resolved.append((0, 0))
                         continue
-                    a = np.ascontiguousarray(found.data, np.float32)
+                    is_int = np.issubdtype(np.asarray(found.data).dtype, np.integer)       # Int..Int4: scene_data_lookup_int, stored as bit patterns
+                    a = np.ascontiguousarray(found.data, np.int32).view(np.float32) if is_int else np.ascontiguousarray(found.data, np.float32)
                     a = a.reshape(len(a), -1)
                     need = {0: 1, 1: int(max(ids.max(), 0)) + 1, 2: len(m.faces), 3: len(m.vertices)}[found.interpolation]
                     if len(a) < need:
                         resolved.append((0, 0))
                         continue
-                    resolved.append((offset, a.shape[1] | (found.interpolation << 4) | 0x100))
+                    resolved.append((offset, a.shape[1] | (found.interpolation << 4) | 0x100 | (0x200 if is_int else 0)))
                     chunks.append(a.reshape(-1))
                     offset += a.size
                 for _ in range(n_inst):
@@ -348,7 +353,8 @@ class OracleScene:
             for i, t in enumerate(desc.textures):
                 a = np.ascontiguousarray(t.texels)
                 self._keep.append(a)
-                self.texs[i].height, self.texs[i].width = a.shape[0], a.shape[1]
+                self.texs[i].height, self.texs[i].width = t.rows_cols
+                self.texs[i].depth = t.depth
                 self.texs[i].format = t.format
                 self.texs[i].texels = a.ctypes.data
             d.textures = self.texs
@@ -470,15 +476,42 @@ def lbvh8_build(tris_rank_order, mode=1):
 def tex_lookup(texture, u, v, wrap_u=1, wrap_v=1):
     """One tex_lookup_float4_2d of the oracle's restatement; returns (rgba float32[4], clipped)."""
     L = lib()
-    a = np.ascontiguousarray(texture.texels)
-    d = TextureDesc()
-    d.height, d.width = a.shape[0], a.shape[1]
-    d.format = texture.format
-    d.texels = a.ctypes.data
+    d, keep = _texture_desc(texture)
     out = (C.c_float * 4)()
     L.orc_tex_lookup.argtypes = [C.POINTER(TextureDesc), C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
     clipped = L.orc_tex_lookup(C.byref(d), float(u), float(v), int(wrap_u), int(wrap_v), out)
     return np.array(out[:], np.float32), bool(clipped)
+
+
+def _texture_desc(texture):
+    a = np.ascontiguousarray(texture.texels)
+    d = TextureDesc()
+    d.height, d.width = texture.rows_cols
+    d.depth = texture.depth
+    d.format = texture.format
+    d.texels = a.ctypes.data
+    return d, a
+
+
+def tex_lookup_3d(texture, u, v, w, wrap_u, wrap_v, wrap_w):
+    """tex_lookup_float4_3d (mdl_interface.glsl:45-64) of the oracle: (rgba, clipped)."""
+    L = lib()
+    d, keep = _texture_desc(texture)
+    out = (C.c_float * 4)()
+    L.orc_tex_lookup_3d.argtypes = [C.POINTER(TextureDesc), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    clipped = L.orc_tex_lookup_3d(C.byref(d), float(u), float(v), float(w), int(wrap_u), int(wrap_v), int(wrap_w), out)
+    return np.array(out[:], np.float32), bool(clipped)
+
+
+def tex_texel(texture, x, y, z=0):
+    """tex_texel_float4_2d / _3d (mdl_interface.glsl:167-185, 91-110) of the oracle."""
+    L = lib()
+    d, keep = _texture_desc(texture)
+    out = (C.c_float * 4)()
+    L.orc_tex_texel.argtypes = [C.POINTER(TextureDesc), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.orc_tex_texel.restype = None
+    L.orc_tex_texel(C.byref(d), int(x), int(y), int(z), out)
+    return np.array(out[:], np.float32)
 
 
 def srgb_texture_to_linear(c):

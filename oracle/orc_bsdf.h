@@ -30,6 +30,7 @@ enum {
 struct State {
   V3 normal, geom_normal, position, tangent_u, tangent_v;
   V3 text_coords;
+  V3 local_position;   // object space (mdl_shading_state.glsl:23): the coordinate of 3-D texture bindings
 };
 
 // mdl_types.glsl:158-170

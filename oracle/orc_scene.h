@@ -115,6 +115,7 @@ struct Scene {
   std::vector<Material> materials;
   std::vector<Texture> textures;                                   // R15
   std::vector<std::vector<GtlcTextureBinding>> materialTextures;   // per material; .texture = 1-based index into `textures`
+  std::vector<int> materialOpacityBinding;                         // per material: index of the binding that feeds the cutout input, or -1
   std::vector<std::vector<GtlcPrimvarBinding>> materialPrimvars;   // per material (names already resolved into primvarInfos)
   std::vector<uint32_t> primvarInfos; std::vector<float> primvarData;
   std::vector<SphereLight> sphereLights;
@@ -226,7 +227,8 @@ static void scene_build(Scene& s)
       t.v0 = xform_point(in.objectToWorld, v3(a.pos[0], a.pos[1], a.pos[2]));
       t.v1 = xform_point(in.objectToWorld, v3(b.pos[0], b.pos[1], b.pos[2]));
       t.v2 = xform_point(in.objectToWorld, v3(c.pos[0], c.pos[1], c.pos[2]));
-      t.prim = f; t.inst = (uint32_t) ii; t.opacity = mat_cutout_opacity(s.materials[in.material]);
+      t.prim = f; t.inst = (uint32_t) ii;
+      t.opacity = (!s.materialOpacityBinding.empty() && s.materialOpacityBinding[in.material] >= 0) ? -1.0f : mat_cutout_opacity(s.materials[in.material]);   // < 0: per hit
       s.tris.push_back(t);
     }
   }
@@ -258,6 +260,10 @@ static inline bool box_hit(const BNode& n, V3 o, V3 inv, float tmin, float tmax,
 // Stochastic cutout, rp_main.ahit:35-61 (`if (k > opacity) ignoreIntersectionEXT`).  The reference draws k from
 // the path RNG once per any-hit invocation in an order Vulkan leaves undefined; the oracle (and the kernel) decide
 // with a pure function of (ray seed, primitive, instance) instead -- ORACLE_DEVIATIONS.md #10.
+// mdl_cutout_opacity at a candidate hit of a textured cutout (rp_main.ahit:35-42): uv and object-space position as
+// setup_mdl_shading_state computes them (mdl_shading_state.glsl:16-23, 61-64), then the material's opacity binding.
+static inline float cutout_opacity_at(const struct Scene& s, uint32_t prim, uint32_t inst, float hu, float hv);
+
 static inline bool cutout_ignored(uint32_t seed, float opacity, uint32_t prim, uint32_t inst)
 {
   if (opacity >= 1.0f) return false;
@@ -294,7 +300,9 @@ static inline bool scene_trace(const Scene& s, V3 o, V3 d, float tMin, float tMa
         float t, u, v;
         if (!tri_intersect(rp, o, tr.v0, tr.v1, tr.v2, t, u, v)) continue;
         if (!(t > tMin && t < tMax)) continue;
-        if (cutout_ignored(seed, tr.opacity, tr.prim, tr.inst)) continue;
+        float opacity = tr.opacity;
+        if (opacity < 0.0f) opacity = cutout_opacity_at(s, tr.prim, tr.inst, u, v);
+        if (cutout_ignored(seed, opacity, tr.prim, tr.inst)) continue;
         if (anyHit) { best.t = t; best.u = u; best.v = v; best.prim = tr.prim; best.inst = tr.inst; return true; }
         if (hit_better(t, tr.inst, tr.prim, best)) { best.t = t; best.u = u; best.v = v; best.prim = tr.prim; best.inst = tr.inst; tlimit = t; }
       }
@@ -341,6 +349,27 @@ static inline void setup_shading_state(const Scene& s, const Hit& h, V3 rayDir, 
   float vv = (bc.x * v0.f2[3] + bc.y * v1.f2[3]) + bc.z * v2.f2[3];
   st.normal = normal; st.geom_normal = geomNormal; st.position = pos;              // :82-90
   st.tangent_u = tangent; st.tangent_v = bitangent; st.text_coords = v3(uu, vv, 0.0f);
+  st.local_position = localPos;
+}
+
+static inline float cutout_opacity_at(const Scene& s, uint32_t prim, uint32_t inst, float hu, float hv)
+{
+  const InstanceDesc& in = s.instances[inst];
+  const int bi = s.materialOpacityBinding[in.material];
+  const uint32_t* f = &s.faces[(size_t) (in.faceBase + prim) * 3];
+  const FVertex& v0 = s.fverts[in.vertexBase + f[0]];
+  const FVertex& v1 = s.fverts[in.vertexBase + f[1]];
+  const FVertex& v2 = s.fverts[in.vertexBase + f[2]];
+  const V3 bc = v3((1.0f - hu) - hv, hu, hv);
+  const V3 p0 = v3(v0.f1[0], v0.f1[1], v0.f1[2]), p1 = v3(v1.f1[0], v1.f1[1], v1.f1[2]), p2 = v3(v2.f1[0], v2.f1[1], v2.f1[2]);
+  const V3 localPos = (p0 * bc.x + p1 * bc.y) + p2 * bc.z;
+  const float uu = (bc.x * v0.f2[2] + bc.y * v1.f2[2]) + bc.z * v2.f2[2];
+  const float vv = (bc.x * v0.f2[3] + bc.y * v1.f2[3]) + bc.z * v2.f2[3];
+  const GtlcTextureBinding& b = s.materialTextures[in.material][(size_t) bi];
+  float ch[4];
+  eval_binding(s.textures, b, uu, vv, localPos, ch);
+  const float o = ch[b.channels[0]];
+  return o < 0.0f ? 0.0f : (o > 1.0f ? 1.0f : o);
 }
 
 } // namespace orc

@@ -117,7 +117,8 @@ def feature_scenes():
     lit.sphere_lights.append(scenes.SphereLight(position=(0.5, -0.5, 0.2), base_emission=(4, 3, 2), radius=(0.1, 0.1, 0.1)))
     return {"textured": scenes.textured_cornell(32, 32, spp=4), "primvars": scenes.primvar_cornell(32, 32, spp=4),
             "volumes": scenes.volume_cornell(32, 32, spp=4, medium_stack_size=2), "nee": lit,
-            "stress": scenes.material_stress(tris_per_mesh=200, meshes=12, width=32, height=32, spp=4)}
+            "stress": scenes.material_stress(tris_per_mesh=200, meshes=12, width=32, height=32, spp=4),
+            "lookups": scenes.lookup_cornell(32, 32, spp=4)}
 
 
 def feature_anchors():

@@ -362,6 +362,42 @@ def test_cutout_trace_and_render_parity(gpu):
     assert len(np.unique(op.reshape(-1, 3), axis=0)) >= 3      # clear, opaque red (chit:202), viridis(0.4) / viridis(0.85)
 
 
+def test_textured_cutout_and_lookup_modes_parity(gpu):
+    """R13 with an opacity that is a material INPUT (rp_main.ahit:35-61: mdl_cutout_opacity on a shading state) and the rest
+    of R15: filtered / texel-fetched 2-D and 3-D lookups (mdl_interface.glsl:45-64, 91-110, 167-185), integer primvars
+    (:417-479).  Hit records bit-exact for closest and any-hit rays, image + AOVs against the oracle; every traversal kernel
+    that can meet such a triangle (batched default, per-lane, counting) gives the same hits."""
+    d = scenes.lookup_cornell(96, 96, spp=8)
+    cam = orc.camera_rays(d, 0)
+    cam[:, 3] = 0.0
+    cam[:, 7] = 3.0e38
+    rays = np.concatenate([cam, random_rays(40000, 23)])
+    h = _trace_parity(gpu, d, rays)                                # per-lane counting kernel + any-hit, seed 0 on both sides
+    b = gpu.BuiltScene(d)
+    try:
+        for variant in (0, 1):
+            gpu.set_tuning(traceVariant=variant)
+            hv = gpu.trace_rays(b.scene, rays)
+            for k in ("prim", "inst", "t", "u", "v"):
+                assert np.array_equal(hv[k], h[k]), (variant, k)
+    finally:
+        gpu.set_tuning(traceVariant=0)
+        b.close()
+    img, ref = _render_parity(gpu, d, flipped_samples=4)
+    got = _aov_parity(gpu, dataclasses.replace(d, width=48, height=48))
+    op = got[gpu.GiAovId.Opacity][..., :3]
+    assert len(np.unique(np.round(op.reshape(-1, 3), 3), axis=0)) > 20         # viridis over a soft-edged alpha mask
+    solid = scenes.lookup_cornell(96, 96, spp=8)
+    for m in solid.materials:
+        m.textures = [t for t in m.textures if t.param not in (scenes.UPS["opacity"], scenes.OPBR["geometry_opacity"])]
+    bs = gpu.BuiltScene(solid)
+    try:
+        img_solid = bs.render().copy()
+    finally:
+        bs.close()
+    assert np.abs(img - img_solid).mean() > 1e-3, "the opacity textures changed nothing"
+
+
 def test_traversal_variants_are_invisible(gpu):
     """The traversal kernels (GtlcTuning.traceVariant 0 = 7 batched default, 1 per-lane loop, 6 TMA-staged ray tiles) walk the BVH in a different order; the
     closest hit is order-independent (smallest t, ties by (instance, primitive)), so hit records and images must be

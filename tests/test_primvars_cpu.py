@@ -65,3 +65,31 @@ def test_primvar_cornell_renders():
     assert np.isfinite(img).all() and rays[0] > 0
     alb = orc.OracleScene(d).render_aovs([16])[16][..., :3]
     assert len(np.unique(np.round(alb.reshape(-1, 3), 3), axis=0)) > 50
+
+
+def test_integer_primvars_take_the_nearest_vertex():
+    """scene_data_lookup_int / _int3 (mdl_interface.glsl:417-479): no interpolation -- the element of the vertex with the largest
+    barycentric weight, per face for uniform data; the value enters the parameter block as a float."""
+    base = scenes.cornell(8, 8).meshes[3]
+    nv, nf = len(base.vertices), len(base.faces)
+    ids = (np.arange(nv * 3).reshape(nv, 3) % 5).astype(np.int32)                 # small integers, distinct per vertex
+    d = _one_quad([scenes.Primvar("tag", scenes.INTERP_VERTEX, ids)], scenes.PrimvarBinding(0, 3, "tag", (9, 9, 9, 0)))
+    a = orc.OracleScene(d).render_aovs([16, 3])
+    alb, bary = a[16][..., :3], a[3][..., :3]
+    hit = bary.sum(-1) > 0.5
+    seen = np.unique(alb[hit], axis=0)
+    assert len(seen) <= nv and all((ids.astype(np.float32) == s).all(1).any() for s in seen)      # only whole vertex records, never blends
+    assert len(seen) >= 3
+    # the record is the one of the dominant barycentric weight
+    f = base.faces
+    face_aov = orc.OracleScene(d).render_aovs([13])[13][..., 0]
+    ys, xs = np.nonzero(hit)
+    for y, x in list(zip(ys, xs))[::7]:
+        b = bary[y, x]
+        k = (0 if b[0] > b[2] else 2) if b[0] > b[1] else (1 if b[1] > b[2] else 2)          # mdl_interface.glsl:436-443
+        assert np.array_equal(alb[y, x], ids[f[face_aov[y, x]][k]].astype(np.float32))
+    # uniform int, scalar, and the fallback for a missing name
+    per_face = np.array([[3], [7]], np.int32)[:nf]
+    d = _one_quad([scenes.Primvar("k", scenes.INTERP_UNIFORM, per_face)], scenes.PrimvarBinding(2, 1, "k"))
+    alb = orc.OracleScene(d).render_aovs([16])[16][..., :3]
+    assert set(np.unique(alb[hit][:, 2]).tolist()) <= {3.0, 7.0}
