@@ -651,7 +651,7 @@ bool ensurePool(size_t capacity)
   CUDA_OK(cudaMalloc(&g.sampleRad, capacity * 16));
   cudaFree(g.perm); g.perm = nullptr;
   CUDA_OK(cudaMalloc(&g.perm, capacity * 4));
-  if (!g.sortHist) { g.sortBlocks = g.smCount * 4; CUDA_OK(cudaMalloc(&g.sortHist, (size_t) kSortBins * g.sortBlocks * 4)); }
+  if (!g.sortHist) { g.sortBlocks = g.smCount * 4; CUDA_OK(cudaMalloc(&g.sortHist, ((size_t) kSortBins * g.sortBlocks + kSortBins) * 4)); }   // per-CTA counts + the 256 bin totals
   g.poolCapacity = capacity;
   return true;
 }
@@ -1477,8 +1477,8 @@ int gtlc_render(const GtlcRenderParams* params)
           if (sortByMaterial) {
             timed(K_SORT, [&] {
               sort_count_kernel<<<g.sortBlocks, kSortBlock, 0, g.stream>>>(g.counters, inIdx, g.hitInst, ds.instInfo, g.sortHist);
-              sort_scan_kernel<<<1, 1024, 0, g.stream>>>(g.sortHist, (uint32_t) (kSortBins * g.sortBlocks));
-              sort_scatter_kernel<<<g.sortBlocks, kSortBlock, 0, g.stream>>>(g.counters, inIdx, g.hitInst, ds.instInfo, g.sortHist, g.perm);
+              sort_scan_kernel<<<kSortBins, 1024, 0, g.stream>>>(g.sortHist, (uint32_t) g.sortBlocks, g.sortHist + (size_t) kSortBins * g.sortBlocks);
+              sort_scatter_kernel<<<g.sortBlocks, kSortBlock, 0, g.stream>>>(g.counters, inIdx, g.hitInst, ds.instInfo, g.sortHist, g.sortHist + (size_t) kSortBins * g.sortBlocks, g.perm);
             });
             launches += 2;
           }

@@ -139,7 +139,7 @@ def test_render_parity_dome_light(gpu):
         e = empty_scene(96, 64, dome, domeLightCameraVisible=visible)
         e.clear_color = (0.2, 0.4, 0.6, 1.0)
         img, ref = _render_parity(gpu, e, rmse_bar=1e-4)
-        assert (img[..., :3].std() > 0.1) == visible              # a picture of the dome, or the flat fallback colour
+        assert (img[..., :3].std(axis=(0, 1)).max() > 0.05) == visible   # a picture of the dome, or the flat fallback colour
         c = scenes.cornell(64, 64, spp=8, max_bounces=4)
         c.meshes = c.meshes[:3]                                   # open box: most bounce rays escape to the dome
         c.dome_light = dome
