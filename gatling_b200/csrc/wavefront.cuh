@@ -509,9 +509,12 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
 #ifndef GTLC_SHADE_BIG_BLOCK
 #define GTLC_SHADE_BIG_BLOCK 512
 #endif
+#ifndef GTLC_SHADE_MIN_BLOCKS
+#define GTLC_SHADE_MIN_BLOCKS 1
+#endif
 constexpr int shade_block_size(int maxClosure) { return (GTLC_SHADE_PHASE_SYNC && maxClosure >= GTLC_SHADE_SYNC_MIN_CLOSURE) ? GTLC_SHADE_BIG_BLOCK : 256; }   // Lambert / UsdPreviewSurface: small code, no barrier
 template <int MAXC, bool NEE, bool AOV, bool TEX, bool VOL>
-__global__ void __launch_bounds__(shade_block_size(MAXC)) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
+__global__ void __launch_bounds__(shade_block_size(MAXC), GTLC_SHADE_MIN_BLOCKS) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
                                                     float4* shO, float4* shD, float4* shC, uint32_t* shSeed, float4* sampleRad,

@@ -15,8 +15,12 @@ _lib = None
 
 
 def build(force=False):
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    """`make` decides: the library is rebuilt whenever a source or include/gtlc.h is newer (a stale liboracle.so read the
+    C-ABI structs with an old layout once).  Without make / a compiler the existing library is used as it is."""
+    import shutil
+    if shutil.which("make") is None and os.path.exists(_LIB_PATH) and not force:
+        return
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
 
 class TextureDesc(C.Structure):  # GtlcTextureDesc
