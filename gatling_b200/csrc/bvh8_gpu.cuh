@@ -88,6 +88,12 @@ GTLC_D void lbvh_tri_box(const float4* __restrict__ inTris, uint32_t tri, float4
   const float4 a = inTris[(size_t) tri * 3 + 0], b = inTris[(size_t) tri * 3 + 1], c = inTris[(size_t) tri * 3 + 2];
   lo = make_float4(fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z), 0.0f);
   hi = make_float4(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z), 0.0f);
+  // A triangle with a NaN / infinite / absurdly large coordinate is inactive (Vulkan's term: the watertight test can never
+  // report it) but would poison the centroid bounds, the Morton keys and every box above it: it enters the tree as a point
+  // at the origin, exactly as in the host builder (bvh8_build.cpp).  fmaxf / fminf drop NaNs, so the sum carries them.
+  const float m = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(lo.y)), fabsf(lo.z)), fmaxf(fmaxf(fabsf(hi.x), fabsf(hi.y)), fabsf(hi.z)));
+  const float sum = (((a.x + a.y) + a.z) + ((b.x + b.y) + b.z)) + ((c.x + c.y) + c.z);
+  if (!(m <= 1.0e18f) || sum != sum) { lo = make_float4(0.0f, 0.0f, 0.0f, 0.0f); hi = lo; }
 }
 
 // bounds[0..2] = min, bounds[3..5] = max of the centroids, as ordered uints (initialised to 0xFFFFFFFF / 0)
@@ -289,14 +295,21 @@ __global__ void __launch_bounds__(kLbvhBlock) ploc_nearest_kernel(LbvhTree T, ui
   if (i >= count) return;
   const uint32_t ci = clusters[i];
   const float4 lo = T.boxLo[ci], hi = T.boxHi[ci];
-  const uint32_t jb = i > (uint32_t) kPlocRadius ? i - (uint32_t) kPlocRadius : 0u;
-  const uint32_t je = min(count - 1u, i + (uint32_t) kPlocRadius);
+  // Candidates in order of distance along the Morton curve, and at equal distance the side of the pair (2k, 2k + 1) first:
+  // with strict comparisons a TIE therefore goes to the closest position, and among coincident or otherwise equal boxes
+  // (zero-area clusters, regular grids) even and odd neighbours choose each other.  Scanning the window left to right
+  // instead made every such cluster pick the far left end: one mutual pair per round, a chain as deep as the cluster is large.
   float best = kLbvhInf; uint32_t bj = i;
-  for (uint32_t j = jb; j <= je; j++) {
-    if (j == i) continue;
-    const uint32_t cj = clusters[j];
-    const float a = lbvh_union_area(lo, hi, T.boxLo[cj], T.boxHi[cj]);
-    if (a < best || bj == i) { best = a; bj = j; }
+  for (uint32_t d = 1; d <= (uint32_t) kPlocRadius; d++) {
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const bool right = ((i & 1u) == 0u) == (side == 0);
+      if (right ? (i + d > count - 1u) : (d > i)) continue;
+      const uint32_t j = right ? i + d : i - d;
+      const uint32_t cj = clusters[j];
+      const float a = lbvh_union_area(lo, hi, T.boxLo[cj], T.boxHi[cj]);
+      if (a < best || bj == i) { best = a; bj = j; }
+    }
   }
   nearest[i] = bj;
 }

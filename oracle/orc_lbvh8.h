@@ -75,6 +75,10 @@ struct Builder {
       b.lo[k] = std::fmin(std::fmin(a, bb), c);
       b.hi[k] = std::fmax(std::fmax(a, bb), c);
     }
+    // inactive triangles (NaN / infinite / > 1e18 coordinates) enter the tree as a point at the origin (bvh8_gpu.cuh: lbvh_tri_box)
+    bool finite = true;
+    for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) finite = finite && (std::fabs(in[(size_t) t * 12 + 4 * v + k]) <= 1.0e18f);
+    if (!finite) for (int k = 0; k < 3; k++) b.lo[k] = b.hi[k] = 0.0f;
     return b;
   }
 
@@ -133,8 +137,8 @@ struct Builder {
   }
 
   // Meister & Bittner 2018, "Parallel Locally-Ordered Clustering for Bounding Volume Hierarchy Construction": clusters in
-  // Morton order, each looks PLOC_RADIUS positions to either side for the partner with the smallest merged area (first
-  // candidate, then strictly smaller: ties go to the smaller position); mutual pairs merge into the left one's place;
+  // Morton order, each looks PLOC_RADIUS positions to either side for the partner with the smallest merged area (candidates by
+  // distance, the side of the pair (2k, 2k + 1) first, strictly smaller wins: ties go to the closest position); mutual pairs merge into the left one's place;
   // the order of the surviving clusters is kept.  Node ids count down so that the root, the last merge, is node 0.
   static const int PLOC_RADIUS = 16;
   static float merged_area(const Box3& a, const Box3& b)
@@ -154,12 +158,15 @@ struct Builder {
       const uint32_t count = (uint32_t) cl.size();
       std::vector<uint32_t> nn(count);
       for (uint32_t i = 0; i < count; i++) {
-        const uint32_t jb = i > (uint32_t) PLOC_RADIUS ? i - PLOC_RADIUS : 0u, je = std::min(count - 1u, i + (uint32_t) PLOC_RADIUS);
         float best = BIG; uint32_t bj = i;
-        for (uint32_t j = jb; j <= je; j++) {
-          if (j == i) continue;
-          const float a = merged_area(box[cl[i]], box[cl[j]]);
-          if (a < best || bj == i) { best = a; bj = j; }
+        for (uint32_t d = 1; d <= (uint32_t) PLOC_RADIUS; d++) {
+          for (int side = 0; side < 2; side++) {
+            const bool right = ((i & 1u) == 0u) == (side == 0);            // the pair (2k, 2k + 1) looks at each other first
+            if (right ? (i + d > count - 1u) : (d > i)) continue;
+            const uint32_t j = right ? i + d : i - d;
+            const float a = merged_area(box[cl[i]], box[cl[j]]);
+            if (a < best || bj == i) { best = a; bj = j; }
+          }
         }
         nn[i] = bj;
       }

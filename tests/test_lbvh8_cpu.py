@@ -96,3 +96,43 @@ def test_ploc_trees_are_valid_and_better():
     _check(c, np.concatenate([cam, random_rays(3000, 5)]), mode=2)
     for count in (1, 2, 3, 4, 9, 40):
         _check(scenes.random_triangles(count, 8, 8, spp=1), random_rays(3000, 30 + count), mode=2)
+
+
+def with_non_finite_triangles(n=3000, bad=200, seed=5):
+    """random_triangles(n) with `bad` triangles given a NaN / infinite / absurdly large coordinate; returns (scene, victims)."""
+    d = scenes.random_triangles(n, 8, 8, spp=1)
+    m = d.meshes[0]
+    v = m.vertices.copy()
+    rng = np.random.default_rng(seed)
+    victims = rng.choice(len(m.faces), bad, replace=False)
+    specials = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, 1e30], np.float32)
+    for k, f in enumerate(victims):
+        v["pos"][m.faces[f][k % 3], k % 3] = specials[k % len(specials)]
+    m.vertices = v
+    return d, victims
+
+
+def test_non_finite_triangles_are_inactive_in_the_device_builders():
+    """The restated device builders (LBVH and PLOC) with inactive triangles in the input: a valid tree of sane depth whose
+    walk never reports a victim and finds every other triangle exactly as the scene without the victims does."""
+    d, victims = with_non_finite_triangles()
+    b = gi.BuiltScene(d)
+    try:
+        _, host_tris = gi.get_bvh(b.scene)
+    finally:
+        b.close()
+    recs = rank_order(host_tris)
+    rays = np.ascontiguousarray(random_rays(20000, 9), np.float32)
+    m = d.meshes[0]
+    keep = np.setdiff1d(np.arange(len(m.faces)), victims)
+    clean = scenes.random_triangles(3000, 8, 8, spp=1)
+    clean.meshes[0].faces = clean.meshes[0].faces[keep]
+    ref = orc.OracleScene(clean).trace(rays)
+    for mode in (1, 2):
+        nodes, tris, depth = orc.lbvh8_build(recs, mode)
+        assert np.array_equal(rank_order(tris), recs, equal_nan=True) and depth <= 24
+        assert np.isfinite(nodes.view(np.float32).reshape(-1, 20)[:, :3]).all()       # grid origins: no NaN reached a node
+        hits, _ = orc.bvh8_trace(nodes, tris, rays)
+        hit = hits["t"] >= 0
+        assert not np.isin(hits["prim"][hit], victims).any()
+        assert np.array_equal(hits["t"], ref["t"]) and np.array_equal(hits["prim"][hit], keep[ref["prim"][hit]])
