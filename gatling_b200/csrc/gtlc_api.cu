@@ -671,8 +671,10 @@ bool ensureAovSamples(size_t capacity)
 {
   if (capacity <= g.aovCapacity) return true;
   for (int k = 0; k < 6; k++) { cudaFree(g.aovSamples.a[k]); g.aovSamples.a[k] = nullptr; }
+  cudaFree(g.aovSamples.clk); g.aovSamples.clk = nullptr;
   g.aovCapacity = 0;
   for (int k = 0; k < 6; k++) CUDA_OK(cudaMalloc(&g.aovSamples.a[k], capacity * 16));
+  CUDA_OK(cudaMalloc(&g.aovSamples.clk, capacity * 4));
   g.aovCapacity = capacity;
   return true;
 }
@@ -740,7 +742,7 @@ TraceParams makeTraceParams(Scene* s)
 template <int MODE, bool TEXCUT> void launchTraceT(const TraceParams& P, bool count, int blocks)
 {
   if (count) { trace_kernel<MODE, true, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // visit counting: variant 0 order = the oracle's walk
-  if (P.aovFlags) { trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // only variant 0 writes the NEE debug AOV
+  if (P.aovFlags || P.clk) { trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P); return; }   // only the per-lane kernel writes the NEE debug AOV / the ClockCycles AOV
   switch (g.tuning.traceVariant) {
     case 1: trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P); break;          // per-lane triangle loop (the order the oracle's walker restates)
     case 6: if (TEXCUT) trace_kernel<MODE, false, TEXCUT><<<blocks, kTraceBlock, 0, g.stream>>>(P);      // (the TMA variant has no textured-cutout form)
@@ -837,6 +839,7 @@ void gtlc_terminate(void)
   g.volumeCapacity = 0;
   cudaFree(g.hitTUVP); cudaFree(g.hitInst); cudaFree(g.shO); cudaFree(g.shD); cudaFree(g.shC); cudaFree(g.shSeed); cudaFree(g.sampleRad); cudaFree(g.accum); cudaFree(g.counters); cudaFree(g.visits); cudaFree(g.perm); cudaFree(g.sortHist); g.perm = nullptr; g.sortHist = nullptr;
   for (int k = 0; k < 6; k++) { cudaFree(g.aovSamples.a[k]); g.aovSamples.a[k] = nullptr; }
+  cudaFree(g.aovSamples.clk); g.aovSamples.clk = nullptr;
   g.aovCapacity = 0;
   g.hitTUVP = nullptr; g.hitInst = nullptr; g.shO = g.shD = g.shC = nullptr; g.shSeed = nullptr; g.sampleRad = nullptr; g.accum = nullptr; g.counters = nullptr; g.visits = nullptr;
   g.poolCapacity = 0; g.accumCapacity = 0; g.visitsCapacity = 0;
@@ -1446,6 +1449,8 @@ int gtlc_render(const GtlcRenderParams* params)
       aovMode = true;
     }
     if (aovMode && !ensureAovSamples(g.poolCapacity)) return false;
+    const bool clockMode = targets.buf[GTLC_AOV_CLOCK_CYCLES] != nullptr;          // every kernel then adds its cycles to the sample's counter
+    AovSampleBuffers aovBufs = g.aovSamples; aovBufs.clk = clockMode ? g.aovSamples.clk : nullptr;
 
     const int gridElem = g.smCount * 8;
     const int traceBlocks = g.smCount * (g.tuning.reserved[1] > 0 ? g.tuning.reserved[1] : 8);
@@ -1460,7 +1465,7 @@ int gtlc_render(const GtlcRenderParams* params)
         WaveParams wp; wp.wavePixelBase = pixBase; wp.wavePixels = wavePixels; wp.waveSamples = std::min(samplesPerWave, rs.spp - sBase);
         wp.waveSampleBase = sBase; wp.pixelMap = (s->shardCount > 1) ? s->dPixelMap.ptr : nullptr;
         paths += (uint64_t) wp.wavePixels * wp.waveSamples;
-        timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.q[0], g.counters); });
+        timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.q[0], g.counters, aovBufs.clk); });
         int inIdx = 0;
         if (rs.maxBounces == 0) {
           // The bounce loop never runs (as in rgen:290 the payload's radiance stays 0): the finished-sample slots the
@@ -1473,6 +1478,7 @@ int gtlc_render(const GtlcRenderParams* params)
           P.zeroA = &g.counters->numPaths[inIdx ^ 1]; P.zeroB = &g.counters->numShadow; P.rayStat = &g.counters->stats[0];
           P.rayO = g.q[inIdx].rayO; P.rayD = g.q[inIdx].rayD; P.hitTUVP = g.hitTUVP; P.hitInst = g.hitInst;
           P.numRays = &g.counters->numPaths[inIdx]; P.workCounter = &g.counters->workCounter; P.seedRad = g.q[inIdx].rad;
+          if (clockMode) { P.clk = aovBufs.clk; P.aovSlotOf = g.q[inIdx].slot; }
           timed(K_TRACE, [&] { launchTrace<TRACE_CLOSEST>(P, countVisits, traceBlocks); });
           if (sortByMaterial) {
             timed(K_SORT, [&] {
@@ -1484,11 +1490,12 @@ int gtlc_render(const GtlcRenderParams* params)
           }
           timed(K_SHADE, [&] {
             const uint32_t* permArg = sortByMaterial ? g.perm : nullptr;
-#define GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, VOL) shade_kernel<MAXC, NEE, AOV, TEX, VOL><<<gridElem * 256 / shade_block_size(MAXC), shade_block_size(MAXC), 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, g.aovSamples)
+#define GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, VOL) shade_kernel<MAXC, NEE, AOV, TEX, VOL><<<gridElem * 256 / shade_block_size(MAXC), shade_block_size(MAXC), 0, g.stream>>>(ubo, ds, g.q[inIdx], g.q[inIdx ^ 1], g.hitTUVP, g.hitInst, permArg, g.shO, g.shD, g.shC, g.shSeed, g.sampleRad, g.counters, inIdx, aovBufs)
 // the medium stack only ever changes on transmission events, which only the OpenPBR closure produces
 #define GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, TEX) do { if (volumes && MAXC == GTLC_CLOSURE_OPENPBR) GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, (MAXC == GTLC_CLOSURE_OPENPBR)); else GTLC_LAUNCH_SHADE4(MAXC, NEE, AOV, TEX, false); } while (0)
 #define GTLC_LAUNCH_SHADE2(MAXC, NEE, AOV) do { if (s->hasTextures) GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, true); else GTLC_LAUNCH_SHADE3(MAXC, NEE, AOV, false); } while (0)
-#define GTLC_LAUNCH_SHADE(MAXC, NEE) do { if (aovMode && bounce == 0) GTLC_LAUNCH_SHADE2(MAXC, NEE, true); else GTLC_LAUNCH_SHADE2(MAXC, NEE, false); } while (0)
+// (with the ClockCycles AOV bound the AOV instantiation runs on every bounce: its first-bounce captures test the path's own bounce count)
+#define GTLC_LAUNCH_SHADE(MAXC, NEE) do { if (aovMode && (bounce == 0 || clockMode)) GTLC_LAUNCH_SHADE2(MAXC, NEE, true); else GTLC_LAUNCH_SHADE2(MAXC, NEE, false); } while (0)
             const bool nee = rs.nextEventEstimation != 0;
             if (maxClosure == GTLC_CLOSURE_DIFFUSE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_DIFFUSE, false); }
             else if (maxClosure == GTLC_CLOSURE_USD_PREVIEW_SURFACE) { if (nee) GTLC_LAUNCH_SHADE(GTLC_CLOSURE_USD_PREVIEW_SURFACE, true); else GTLC_LAUNCH_SHADE(GTLC_CLOSURE_USD_PREVIEW_SURFACE, false); }
@@ -1504,13 +1511,14 @@ int gtlc_render(const GtlcRenderParams* params)
             S.rayO = g.shO; S.rayD = g.shD; S.shContrib = g.shC; S.radPath = g.q[inIdx ^ 1].rad; S.radSample = g.sampleRad;
             S.numRays = &g.counters->numShadow; S.workCounter = &g.counters->workCounterShadow; S.seedU32 = g.shSeed;
             if (aovMode && bounce == 0) { S.aovFlags = g.aovSamples.a[0]; S.aovSlotOf = g.q[inIdx ^ 1].slot; }
+            if (clockMode) { S.clk = aovBufs.clk; S.aovSlotOf = g.q[inIdx ^ 1].slot; }
             timed(K_SHADOW, [&] { launchTrace<TRACE_SHADOW>(S, countVisits, traceBlocks); });
           }
           inIdx ^= 1;
         }
         const int lastWave = (sBase + samplesPerWave >= rs.spp) ? 1 : 0;
         timed(K_RESOLVE, [&] { resolve_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, g.accum, colorDev, lastWave); });
-        if (aovMode) timed(K_RESOLVE, [&] { resolve_aov_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, g.aovSamples, targets, sBase == 0 ? 1 : 0, lastWave); });
+        if (aovMode) timed(K_RESOLVE, [&] { resolve_aov_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, aovBufs, targets, sBase == 0 ? 1 : 0, lastWave); });
       }
     }
     // the single collective of the path: every rank's colour AOV holds its own tiles and zeros elsewhere;

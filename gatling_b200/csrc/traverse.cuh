@@ -94,6 +94,7 @@ struct TraceParams {
   // Launch prologue (thread 0 of CTA 0), the wave loop's per-bounce bookkeeping folded into the kernel that needs it --
   // nothing in this kernel reads what it writes:  *zeroA = 0, *zeroB = 0, *rayStat += *numRays.
   uint32_t* zeroA; uint32_t* zeroB; unsigned long long* rayStat;
+  float* clk;                                   // ClockCycles AOV (per-lane kernel only): cycles a ray spent here are added to its sample's counter
   const CutoutScene* __restrict__ cut;          // device-resident; read by textured cutouts only (triangle opacity word < 0)
 };
 
@@ -399,6 +400,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
   float tmax = 0.0f;
   uint2 G = make_uint2(0u, 0u);
   uint32_t cNodes = 0, cTris = 0;
+  uint32_t clk0 = 0;
 
   while (true) {
     // ---- refill idle lanes from the global queue (one atomic per warp) -----------------------
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
             tmax = rd.w;
             bt = tmax; bprim = 0xFFFFFFFFu; binst = 0xFFFFFFFFu; bu = 0.0f; bv = 0.0f;
             sp = 0; cNodes = 0; cTris = 0;
+            if (P.clk) clk0 = (uint32_t) clock();
             active = tmax > r.tmin;   // empty interval (e.g. disabled shadow ray): immediate miss
             if (!ray_is_finite(ro, rd)) { active = false; atomicAdd(&P.stats[5], 1ull); }
             G = make_uint2(0u, 0x80000000u);
@@ -482,6 +485,12 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
           } else {
             P.hitTUVP[rayIdx] = make_float4(hit ? bt : -1.0f, bu, bv, u2f(bprim));
             if (P.hitInst) P.hitInst[rayIdx] = binst;
+          }
+          if (P.clk) {                                                    // rgen:187-189,501-504: the megakernel's per-pixel timer, per ray here
+            uint32_t slot;
+            if (MODE == TRACE_SHADOW) { const uint32_t target = f2u(__ldg(&P.shContrib[rayIdx]).w); slot = (target & 0x80000000u) ? (target & 0x7FFFFFFFu) : P.aovSlotOf[target]; }
+            else slot = P.aovSlotOf[rayIdx];
+            P.clk[slot] += (float) ((uint32_t) clock() - clk0);
           }
           if (COUNT) {
             atomicAdd(&P.stats[MODE == TRACE_SHADOW ? 7 : 1], (unsigned long long) cNodes);

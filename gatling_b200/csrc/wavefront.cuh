@@ -107,7 +107,8 @@ struct WaveParams {
 // (rp_main.chit:191-290); resolve_aov_kernel replays the megakernel's per-pixel write order from it.
 //   a[0] = (barycentrics.xyz, flags: bit0 hit, bit1 thinWalled, bit2 doubleSided, bit3 NEE shadow ray occluded (set by the shadow kernel), bit4 NEE block ran)   a[1] = (texcoords.xyz, depth)
 //   a[2] = (tangent.xyz, objectId)   a[3] = (bitangent.xyz, faceId)   a[4] = (posNormal.xyz, instanceId)   a[5] = (albedo.xyz, cutout opacity or -1)
-struct AovSampleBuffers { float4* a[6]; };
+//   clk  = clock cycles this sample's path has spent in the kernels so far (ClockCycles AOV, rgen:187-189,501-504), or NULL
+struct AovSampleBuffers { float4* a[6]; float* clk; };
 
 struct Counters {          // device-resident
   uint32_t numPaths[2];    // path-queue lengths (double buffered)
@@ -134,7 +135,7 @@ GTLC_D V2 fisGauss(V2 xi)
 GTLC_D V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
 
 // ---- raygen: rp_main.rgen:191-288 -------------------------------------------------------------
-__global__ void __launch_bounds__(256) raygen_kernel(UniformData ubo, WaveParams wp, PathQueue q, Counters* ctr)
+__global__ void __launch_bounds__(256) raygen_kernel(UniformData ubo, WaveParams wp, PathQueue q, Counters* ctr, float* clk)
 {
   const uint32_t total = wp.wavePixels * wp.waveSamples;
   const uint32_t imageWidth = ubo.imageDims & 0xFFFFu;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256) raygen_kernel(UniformData ubo, WaveParams
   const V3 L = (C - (camera_right * W) * 0.5f) - (camUp * H) * 0.5f;     // :210
 
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+    const uint32_t clk0 = clk ? (uint32_t) clock() : 0u;
     const uint32_t j = slot / wp.wavePixels;
     const uint32_t lp = wp.wavePixelBase + (slot - j * wp.wavePixels);
     const uint32_t pixelIndex = wp.pixelMap ? wp.pixelMap[lp] : lp;      // :195
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(256) raygen_kernel(UniformData ubo, WaveParams
     q.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));               // :274-275
     q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(rng_state));        // :276-277
     q.slot[slot] = slot;
+    if (clk) clk[slot] = (float) ((uint32_t) clock() - clk0);            // the ClockCycles AOV starts counting here (rgen:187-189)
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->numPaths[0] = total; ctr->numPaths[1] = 0; ctr->numShadow = 0; ctr->workCounter = 0; ctr->workCounterShadow = 0; }
 }
@@ -509,12 +512,22 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
 #ifndef GTLC_SHADE_BIG_BLOCK
 #define GTLC_SHADE_BIG_BLOCK 512
 #endif
+// Resident CTAs per SM asked of the compiler for the OpenPBR instantiations without per-hit inputs (the ones a production frame
+// spends its time in): 2 x 512 threads = 64 registers.  ptxas then spills ~360 bytes per thread, and the kernel is still 11 %
+// (C3 stand-in) to 18 % (C5 stand-in) faster than one 512-thread CTA at 108 registers: it waits on dependent IEEE division /
+// square-root sequences (issue slots 50 % busy at 16 warps per SM), so twice the warps win more than the spills cost.  Measured
+// on the C3 stand-in, shade ms per 173 M hits: 1 x 512 @ 108 regs 27.9 | 1 x 640 @ 96 30.2 | 1 x 768 @ 80 27.5 | 1 x 896 @ 72 31.3 |
+// 1 x 1024 @ 64 25.9 | 2 x 512 @ 64 24.7.
 #ifndef GTLC_SHADE_MIN_BLOCKS
-#define GTLC_SHADE_MIN_BLOCKS 1
+#define GTLC_SHADE_MIN_BLOCKS 2
 #endif
+constexpr int shade_min_blocks(int maxClosure, bool aov, bool tex, bool vol)
+{
+  return (GTLC_SHADE_PHASE_SYNC && maxClosure >= GTLC_SHADE_SYNC_MIN_CLOSURE && !aov && !tex && !vol) ? GTLC_SHADE_MIN_BLOCKS : 1;
+}
 constexpr int shade_block_size(int maxClosure) { return (GTLC_SHADE_PHASE_SYNC && maxClosure >= GTLC_SHADE_SYNC_MIN_CLOSURE) ? GTLC_SHADE_BIG_BLOCK : 256; }   // Lambert / UsdPreviewSurface: small code, no barrier
 template <int MAXC, bool NEE, bool AOV, bool TEX, bool VOL>
-__global__ void __launch_bounds__(shade_block_size(MAXC), GTLC_SHADE_MIN_BLOCKS) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
+__global__ void __launch_bounds__(shade_block_size(MAXC), shade_min_blocks(MAXC, AOV, TEX, VOL)) shade_kernel(UniformData ubo, DeviceScene s, PathQueue qin, PathQueue qout,
                                                     const float4* __restrict__ hitTUVP, const uint32_t* __restrict__ hitInst,
                                                     const uint32_t* __restrict__ perm,
                                                     float4* shO, float4* shD, float4* shC, uint32_t* shSeed, float4* sampleRad,
@@ -532,6 +545,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC), GTLC_SHADE_MIN_BLOCKS)
 
   for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < nRounded; it += gridDim.x * blockDim.x) {
     bool valid = it < n;
+    const uint32_t clk0 = (AOV && aov.clk) ? (uint32_t) clock() : 0u;
     bool survives = false, wantShadow = false;
     V3 ray_origin = v3(0.0f), ray_dir = v3(0.0f), throughput = v3(0.0f), radiance = v3(0.0f);
     V3 neeToLight = v3(0.0f), neeContrib = v3(0.0f);
@@ -797,6 +811,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC), GTLC_SHADE_MIN_BLOCKS)
         shC[shPos] = make_float4(neeContrib.x, neeContrib.y, neeContrib.z, u2f(target));
         shSeed[shPos] = shadowSeed;                                                    // rgen:399 shadowRayPayload.rng_state
       }
+      if (AOV && aov.clk) aov.clk[slot] += (float) ((uint32_t) clock() - clk0);          // ClockCycles AOV: this bounce's shading
     }
   }
 }
@@ -883,6 +898,11 @@ __global__ void __launch_bounds__(256) resolve_aov_kernel(UniformData ubo, WaveP
         if (tg.buf[GTLC_AOV_NORMAL]) vb[GTLC_AOV_NORMAL][pix] = tg.clear[GTLC_AOV_NORMAL];
         if (tg.buf[GTLC_AOV_ALBEDO]) vb[GTLC_AOV_ALBEDO][pix] = tg.clear[GTLC_AOV_ALBEDO];
       }
+    }
+    if (smp.clk && tg.buf[GTLC_AOV_CLOCK_CYCLES]) {                                       // rgen:501-504: cycles this pixel's invocation took
+      float cycles = firstWave ? 0.0f : vb[GTLC_AOV_CLOCK_CYCLES][pix].x;                // (summed over the waves of one giRender call)
+      for (uint32_t j = 0; j < wp.waveSamples; j++) cycles += smp.clk[(size_t) j * wp.wavePixels + q];
+      vb[GTLC_AOV_CLOCK_CYCLES][pix] = make_float4(cycles, 0.0f, 0.0f, tg.clear[GTLC_AOV_CLOCK_CYCLES].w);
     }
     for (uint32_t j = 0; j < wp.waveSamples; j++) {
       const size_t slot = (size_t) j * wp.wavePixels + q;

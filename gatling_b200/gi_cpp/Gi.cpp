@@ -32,7 +32,7 @@ namespace gtl
   struct GiRectLight { GtlcHandle h; };
   struct GiDiskLight { GtlcHandle h; };
   struct GiDomeLight { GtlcHandle h; };
-  struct GiRenderBuffer { GtlcHandle h; };
+  struct GiRenderBuffer { GtlcHandle h; uint32_t width = 0, height = 0; };
 
   namespace
   {
@@ -435,6 +435,38 @@ namespace gtl
   void giSetMeshVisibility(GiMesh* m, bool visible) { if (m) gtlc_mesh_set_visibility(m->h, visible); }
   void giDestroyMesh(GiMesh* m) { if (!m) return; gtlc_mesh_destroy(m->h); delete m; }
 
+  // _EncodeRenderBufferAsHeatmap (Gi.cpp:327-343): x / max(x) over the image -> a 256-step Turbo colour, alpha 255.  The
+  // reference indexes Google's 256-entry Turbo table; here the published polynomial fit of the same map (Mikhailov 2019) is
+  // evaluated at the 256 table positions -- within ~1/255 of the table, and this is a debug visualisation, not a parity target.
+  static void turboColor(float x, float* rgb)
+  {
+    const float r4[4] = { 0.13572138f, 4.61539260f, -42.66032258f, 132.13108234f }, g4[4] = { 0.09140261f, 2.19418839f, 4.84296658f, -14.18503333f },
+                b4[4] = { 0.10667330f, 12.64194608f, -60.58204836f, 110.36276771f };
+    const float r2[2] = { -152.94239396f, 59.28637943f }, g2[2] = { 4.27729857f, 2.82956604f }, b2[2] = { -89.90310912f, 27.34824973f };
+    x = x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x);
+    const float v4[4] = { 1.0f, x, x * x, x * x * x };
+    const float v2[2] = { v4[2] * v4[2], v4[3] * v4[2] };
+    auto dot4 = [&](const float* c) { return v4[0] * c[0] + v4[1] * c[1] + v4[2] * c[2] + v4[3] * c[3]; };
+    rgb[0] = dot4(r4) + v2[0] * r2[0] + v2[1] * r2[1];
+    rgb[1] = dot4(g4) + v2[0] * g2[0] + v2[1] * g2[1];
+    rgb[2] = dot4(b4) + v2[0] * b2[0] + v2[1] * b2[1];
+    for (int k = 0; k < 3; k++) rgb[k] = rgb[k] < 0.0f ? 0.0f : (rgb[k] > 1.0f ? 1.0f : rgb[k]);
+  }
+  static void encodeRenderBufferAsHeatmap(GiRenderBuffer* rb)
+  {
+    float* rgba = (float*) gtlc_render_buffer_mem(rb->h);
+    const uint32_t w = rb->width, h = rb->height;
+    if (!rgba || !w || !h) return;
+    const size_t channelCount = (size_t) w * h * 4;
+    float maxValue = 0.0f;
+    for (size_t i = 0; i < channelCount; i += 4) maxValue = std::max(maxValue, rgba[i]);          // only the first channel counts
+    for (size_t i = 0; i < channelCount && maxValue > 0.0f; i += 4) {
+      const int valIndex = std::min(int((rgba[i] / maxValue) * 255.0), 255);
+      turboColor((float) valIndex / 255.0f, &rgba[i]);
+      rgba[i + 3] = 255.0f;
+    }
+  }
+
   GiStatus giRender(const GiRenderParams& params)
   {
     std::vector<GtlcAovBinding> bindings(params.aovBindings.size());
@@ -458,6 +490,9 @@ namespace gtl
     r.rrInvMinTermProb = s.rrInvMinTermProb; r.spp = s.spp; r.time = s.time;
     p.scene = params.scene ? params.scene->h : 0;
     if (gtlc_render(&p) != GTLC_OK) { logError(gtlc_last_error()); return GiStatus::Error; }
+    // Gi.cpp:2504-2512: the ClockCycles AOV leaves giRender as a heat map of the per-pixel cycle counts
+    for (size_t i = 0; i < bindings.size(); i++)
+      if (bindings[i].aovId == GTLC_AOV_CLOCK_CYCLES && params.aovBindings[i].renderBuffer) encodeRenderBufferAsHeatmap(params.aovBindings[i].renderBuffer);
     return GiStatus::Ok;
   }
 
@@ -518,7 +553,12 @@ namespace gtl
   void giSetDomeLightBaseEmission(GiDomeLight* l, float* rgb) { if (l) gtlc_dome_light_set_base_emission(l->h, rgb); }
   void giSetDomeLightDiffuseSpecular(GiDomeLight* l, float d, float s) { if (l) gtlc_dome_light_set_diffuse_specular(l->h, d, s); }
 
-  GiRenderBuffer* giCreateRenderBuffer(uint32_t w, uint32_t h, GiRenderBufferFormat f) { return wrap<GiRenderBuffer>(gtlc_render_buffer_create(w, h, (int32_t) f)); }
+  GiRenderBuffer* giCreateRenderBuffer(uint32_t w, uint32_t h, GiRenderBufferFormat f)
+  {
+    GiRenderBuffer* rb = wrap<GiRenderBuffer>(gtlc_render_buffer_create(w, h, (int32_t) f));
+    if (rb) { rb->width = w; rb->height = h; }
+    return rb;
+  }
   void giDestroyRenderBuffer(GiRenderBuffer* rb) { if (!rb) return; gtlc_render_buffer_destroy(rb->h); delete rb; }
   void* giGetRenderBufferMem(GiRenderBuffer* rb) { return rb ? gtlc_render_buffer_mem(rb->h) : nullptr; }
 }

@@ -14,17 +14,20 @@ from helpers import image_metrics, random_rays
 pytestmark = pytest.mark.gpu
 
 
-def _trace_parity(gi, desc, rays):
+def _trace_parity(gi, desc, rays, walker=True):
+    """`walker=False`: scenes with TEXTURED cutouts -- the oracle's stand-alone BVH8 walker sees node and triangle bytes only and
+    cannot evaluate a material input, so visit counts are not compared there (hits still are, against the oracle's scene query)."""
     b = gi.BuiltScene(desc)
     try:
         o = orc.OracleScene(desc)
         nodes, tris = gi.get_bvh(b.scene)
         h_gpu, v_gpu = gi.trace_rays(b.scene, rays, want_visits=True)
         h_ref = o.trace(rays)
-        h_walk, v_walk = orc.bvh8_trace(nodes, tris, rays)
         for k in ("prim", "inst", "t", "u", "v"):
             assert np.array_equal(h_gpu[k], h_ref[k]), "closest hit field %s differs from the oracle" % k
-        assert np.array_equal(v_gpu, v_walk), "node/triangle visit counts differ from the oracle's BVH8 walk"
+        if walker:
+            h_walk, v_walk = orc.bvh8_trace(nodes, tris, rays)
+            assert np.array_equal(v_gpu, v_walk), "node/triangle visit counts differ from the oracle's BVH8 walk"
         a_gpu = gi.trace_rays(b.scene, rays, any_hit=True)
         a_ref = o.trace(rays, any_hit=True)
         assert np.array_equal(a_gpu["t"] >= 0, a_ref["t"] >= 0), "any-hit occlusion differs"
@@ -314,6 +317,36 @@ def test_aov_parity_instances_and_progressive(gpu):
     assert got[gpu.GiAovId.InstanceId].max() >= 3      # instanced props carry their instance index
 
 
+def test_clock_cycles_aov(gpu):
+    """The reference's in-tree profiler (rp_main.rgen:187-189,501-504): per pixel, the cycles its samples' paths spent in the
+    kernels.  Not a parity quantity (it is a timer); what must hold: every pixel counts something, pixels whose paths bounce
+    around the box cost more than pixels that leave through the open front, and binding the AOV leaves the image alone."""
+    d = scenes.cornell(64, 64, spp=4, max_bounces=6)
+    d.meshes = d.meshes[:4]                              # light + floor + ceiling + back wall: half the camera rays escape at once
+    b = gpu.BuiltScene(d)
+    try:
+        plain = b.render().copy()
+    finally:
+        b.close()
+    b = gpu.BuiltScene(d)
+    try:
+        got = b.render_aovs([gpu.GiAovId.Color, gpu.GiAovId.ClockCycles, gpu.GiAovId.Bounces])
+    finally:
+        b.close()
+    assert np.array_equal(got[gpu.GiAovId.Color], plain)
+    clk = got[gpu.GiAovId.ClockCycles][..., 0]
+    assert np.isfinite(clk).all() and clk.min() > 0.0
+    assert not got[gpu.GiAovId.ClockCycles][..., 1:3].any()                 # uvec3(cycles, 0, 0)
+    ids = b_ids = None
+    bb = gpu.BuiltScene(d)
+    try:
+        hit = bb.render_aovs([gpu.GiAovId.Barycentrics])[gpu.GiAovId.Barycentrics][..., :3].sum(-1) > 0.5
+    finally:
+        bb.close()
+    assert hit.any() and (~hit).any()
+    assert clk[hit].mean() > 1.5 * clk[~hit].mean()
+
+
 def test_color_only_render_is_unchanged_by_aov_support(gpu):
     d = scenes.cornell(48, 48, spp=2, max_bounces=3)
     b = gpu.BuiltScene(d)
@@ -372,7 +405,7 @@ def test_textured_cutout_and_lookup_modes_parity(gpu):
     cam[:, 3] = 0.0
     cam[:, 7] = 3.0e38
     rays = np.concatenate([cam, random_rays(40000, 23)])
-    h = _trace_parity(gpu, d, rays)                                # per-lane counting kernel + any-hit, seed 0 on both sides
+    h = _trace_parity(gpu, d, rays, walker=False)                  # per-lane counting kernel + any-hit, seed 0 on both sides
     b = gpu.BuiltScene(d)
     try:
         for variant in (0, 1):
@@ -628,6 +661,7 @@ def test_render_parity_primvars(gpu):
         b.close()
 
 
+@pytest.mark.logs_errors      # the primvar scene carries a too-short primvar, ignored loudly
 def test_committed_golden_images(gpu):
     """The CUDA path against the oracle images committed under tests/golden/ (made by tests/golden/make_golden.py in the
     build container), not against an oracle run of the moment."""
