@@ -51,7 +51,10 @@ def family(name):
     return n.split("<")[0]
 
 
-raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if a.report.endswith(".csv"):          # the raw page exported on the GPU box (`ncu -i X.ncu-rep --page raw --csv`) when the report itself was too large to bring back
+    raw = open(a.report).read()
+else:
+    raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 ki = hdr.index("Kernel Name")
