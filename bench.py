@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "c5"])
     ap.add_argument("--sub-configs", default=None, help="comma list measured after the headline config (default: the other two of c2,c3,c5; '' = none)")
     ap.add_argument("--sub-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end leg (host buffers in the timed region); 0 = as many as --steps")
     ap.add_argument("--spp", type=int, default=0, help="override the config's sample count (profiling runs only: the number is then not the headline)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
@@ -279,7 +280,8 @@ def measure(name, a, gi, torch, dist, rank, world, local_rank, steps, warmup, sa
     barrier()
     t2 = time.perf_counter()
     e2e_rays = 0
-    for _ in range(steps):
+    e2e_steps = min(steps, a.e2e_steps) if a.e2e_steps > 0 else steps
+    for _ in range(e2e_steps):
         s = step(True)
         e2e_rays += s["closestRays"] + s["shadowRays"]
     barrier()
@@ -346,7 +348,7 @@ def measure(name, a, gi, torch, dist, rank, world, local_rank, steps, warmup, sa
         "device_ms_per_step": dev_ms / steps,
         "rays_per_step": total_rays / steps,
         "e2e": {"value": total_e2e / wall_e2e / 1e6, "unit": METRIC, "h2d_bytes_per_step": 240 + 24,
-                "d2h_bytes_per_step": desc.width * desc.height * 16, "ms_per_step": 1000.0 * wall_e2e / steps,
+                "d2h_bytes_per_step": desc.width * desc.height * 16, "ms_per_step": 1000.0 * wall_e2e / e2e_steps, "steps": e2e_steps,
                 "note": "gtlc_render through the C-ABI: GtlcRenderParams (camera + settings + AOV binding) from host memory in, the full HDR colour AOV copied to pinned host memory "
                         "every step" + (" -- on rank 0, after the in-library ncclReduce of all shards" if world > 1 else "") +
                         "; scene/BVH stay resident as in the reference (rebuilt only when dirty)"},
@@ -360,7 +362,22 @@ def measure(name, a, gi, torch, dist, rank, world, local_rank, steps, warmup, sa
     return rec
 
 
+class StdoutForJsonOnly:
+    """Libraries print to fd 1 behind Python's back (NCCL writes its version line there at the first communicator).  The
+    bench's stdout carries ONE JSON line: everything else goes to stderr, the line is written to the saved descriptor."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+
 def run_ours(a):
+    out_fd = StdoutForJsonOnly()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -399,7 +416,7 @@ def run_ours(a):
         out["sub_configs"] = subs
         if world == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_subprocess(a)
-        print(json.dumps(out))
+        out_fd.emit(json.dumps(out))
     if world > 1:
         gi.comm_destroy()
     gi.giTerminate()
