@@ -329,7 +329,7 @@ def measure(name, a, gi, torch, dist, rank, world, local_rank, steps, warmup, sa
             "32+20 per closest ray, 32+4+16 per shadow ray, 80 per BVH8 node visit, 48 per triangle test; per shaded hit 124 (R4 gathers) + 168 (path state in+out) + 32 (ray out) + "
             "P_mat (16 / 64 / 192 B), 100 per miss, 52 per shadow-queue entry.  `bound` names the yardstick SURVEY 8d prescribes; `limiter` is what ncu says actually binds the kernel")
     roofline = roof("trace_kernel_batched<CLOSEST>", closest_bytes, acc["msTraceClosest"] / steps, bounce_launches,
-                    "issue slots + L1 data pipe (software BVH8 traversal: ~230 SASS instructions per node step at ~22-25 of 32 lanes); DRAM far below peak -- see dram_pct_of_peak_ncu",
+                    "instruction issue (67-72 % of the issue slots, ALU pipe 55-64 %) + L1 data pipe (60-71 %): software BVH8 traversal, ~215 SASS instructions per node step at 21-25 of 32 lanes; DRAM far below peak -- see dram_pct_of_peak_ncu (profiles/r02_trace_c3.md, r02_trace_c2.md)",
                     {"nodes_per_ray": s_count["nodeVisits"] / max(rays_c, 1), "tris_per_ray": s_count["triVisits"] / max(rays_c, 1), "rays_per_step": rays_c, "note": note})
     others = []
     if rays_s:
@@ -337,7 +337,7 @@ def measure(name, a, gi, torch, dist, rank, world, local_rank, steps, warmup, sa
                            "issue slots + L1 data pipe, shorter walks (any-hit): per-ray fixed costs weigh more",
                            {"nodes_per_ray": s_count["shadowNodeVisits"] / max(rays_s, 1), "tris_per_ray": s_count["shadowTriVisits"] / max(rays_s, 1), "rays_per_step": rays_s}))
     others.append(roof("shade_kernel", shade_bytes, acc["msShade"] / steps, bounce_launches,
-                       "instruction issue at low occupancy (IEEE-exact closure arithmetic, ~90 registers); DRAM far below peak",
+                       "instruction issue (56-65 % of the issue slots at 47 % occupancy: IEEE-exact closure arithmetic, 64 registers with spills) on top of incoherent shading gathers; DRAM at ~38 % of peak over a whole wave (profiles/r02_shade_c3.md, r02_traffic.json)",
                        {"hits_per_step": hits, "misses_per_step": rays_c - hits, "bytes_per_hit": BYTES_HIT[max_closure]}))
     value = total_rays / wall / 1e6
     rec = {
