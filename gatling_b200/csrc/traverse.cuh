@@ -685,6 +685,9 @@ __global__ void __launch_bounds__(kTraceBlock, 6) trace_kernel_tma(TraceParams P
 // shared-memory atomicMin on (t bits << 32 | (instance, primitive) rank) -- the same closest-hit order as
 // the per-lane loop, so results are bit-identical.  Culling sees a new t a few node steps late (measured on the CPU
 // walker: +2.5 % node visits per step of delay), which the 32-wide triangle tests more than pay for.
+#ifndef GTLC_ENQUEUE_UNROLL
+#define GTLC_ENQUEUE_UNROLL 1   // C3 stand-in: closest trace 65.1 -> 64.3 ms, shadow 19.1 -> 18.9 ms; C2 33.5 -> 33.2 ms (identical queue content)
+#endif
 constexpr int kBatchQueueCap = 832;   // 31 left-overs + 32 lanes x 24 triangles of one node step, rounded up
 
 template <int MODE, bool TEXCUT = false>
@@ -758,6 +761,41 @@ __global__ void __launch_bounds__(kTraceBlock, GTLC_TRACE_MIN_BLOCKS) trace_kern
         if (G.y & 0xFF000000u) GTLC_NODE_STEP(G, stack, sp, r, bt, k47, triBase, triMask, triValid);
       }
       // enqueue, one triangle per lane per round (owners interleave in the queue)
+#if GTLC_ENQUEUE_UNROLL
+      {
+        // the first three rounds without the loop: their ballots are taken up front from the lanes' triangle counts (a node step
+        // rarely finds more than three triangles per lane); queue content and order are those of the loop below
+        const uint32_t cnt = (uint32_t) __popc(triMask);
+        const unsigned b0 = __ballot_sync(FULL, cnt > 0u);
+        if (b0) {
+          const unsigned b1 = __ballot_sync(FULL, cnt > 1u), b2 = __ballot_sync(FULL, cnt > 2u);
+          const unsigned lt = (1u << lane) - 1u;
+          const uint32_t owner = (uint32_t) lane << 27;
+          if (cnt > 0u) {
+            const uint32_t m = triMask & (0u - triMask);                       // lowest set bit
+            sQueue[w][qCount + (uint32_t) __popc(b0 & lt)] = owner | (triBase + (uint32_t) __popc(triValid & (m - 1u)));
+            triMask ^= m; pending = true;
+          }
+          qCount += (uint32_t) __popc(b0);
+          if (b1) {
+            if (cnt > 1u) {
+              const uint32_t m = triMask & (0u - triMask);
+              sQueue[w][qCount + (uint32_t) __popc(b1 & lt)] = owner | (triBase + (uint32_t) __popc(triValid & (m - 1u)));
+              triMask ^= m;
+            }
+            qCount += (uint32_t) __popc(b1);
+            if (b2) {
+              if (cnt > 2u) {
+                const uint32_t m = triMask & (0u - triMask);
+                sQueue[w][qCount + (uint32_t) __popc(b2 & lt)] = owner | (triBase + (uint32_t) __popc(triValid & (m - 1u)));
+                triMask ^= m;
+              }
+              qCount += (uint32_t) __popc(b2);
+            }
+          }
+        }
+      }
+#endif
       unsigned have = __ballot_sync(FULL, triMask != 0u);
       while (have) {
         if (triMask) {
