@@ -563,6 +563,28 @@ def test_texture_errors_are_loud(gpu):
     assert gpu.giCreateMaterial(s, scenes.CLOSURE_DIFFUSE, [0.5] * 3, "m", [ok], [s]) is None         # a handle, but not a texture
     m = gpu.giCreateMaterial(s, scenes.CLOSURE_DIFFUSE, [0.5] * 3, "m", [ok], [tex])
     assert m
+    # the lookup modes: an unknown mode, a 3-D texture read with a 2-D lookup, a bad wrap mode along w, and a cutout input
+    # that is bound as part of a colour are refused; rays with tMin < 0 are refused by the ray query
+    vol = gpu.giCreateTexture(scenes.procedural_volume(4, 3))
+    assert vol
+    assert gpu.giCreateMaterial(s, scenes.CLOSURE_DIFFUSE, [0.5] * 3, "m", [scenes.TextureBinding(0, 0, (0, 1, 2), lookup=7)], [tex]) is None
+    assert "lookup mode" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, scenes.CLOSURE_DIFFUSE, [0.5] * 3, "m", [ok], [vol]) is None
+    assert "3-D texture with a 2-D lookup" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, scenes.CLOSURE_DIFFUSE, [0.5] * 3, "m", [scenes.TextureBinding(0, 0, (0, 1, 2), lookup=scenes.LOOKUP_FILTERED_3D, wrap_w=9)], [vol]) is None
+    assert "wrap mode" in gpu.giLastError()
+    ups = scenes.material_usd_preview_surface("x")
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [scenes.TextureBinding(scenes.UPS["opacity"] - 1, 0, (0, 1, 2))], [tex]) is None
+    assert "cutout input" in gpu.giLastError()
+    d = scenes.cornell(8, 8, spp=1)
+    b = gpu.BuiltScene(d)
+    try:
+        rays = random_rays(4, 1); rays[2, 3] = -0.5
+        with pytest.raises(RuntimeError, match="tMin"):
+            gpu.trace_rays(b.scene, rays)
+    finally:
+        b.close()
+    gpu.giDestroyTexture(vol)
     gpu.giDestroyTexture(tex)            # deferred: the material still references it
     gpu.giDestroyMaterial(m)
     gpu.giDestroyScene(s)
