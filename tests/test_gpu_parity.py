@@ -661,6 +661,57 @@ def test_full_size_properties_c2(gpu):
         b.close()
 
 
+def test_full_size_c1_parity(gpu):
+    """Config C1 exactly as BASELINE.json states it (cornell.usda, 512x512, spp 64, max-bounces 4, UsdPreviewSurface): the whole
+    image against the oracle, traced-ray counts equal."""
+    _render_parity(gpu, scenes.cornell(512, 512, spp=64, max_bounces=4))
+
+
+def test_full_size_c3_band_parity_and_properties(gpu):
+    """The headline config C3 at BASELINE.json's full geometry and resolution (4.97 M triangles in 401 instances, 24 OpenPBR
+    materials, NEE, 1920x1080).  The oracle is too slow for the whole frame: it renders a band of rows in the middle of the
+    image, which must agree with the same rows of the GPU frame; hit records of random rays are bit-exact against the oracle;
+    and the frame does not depend on wave size, material sort or traversal kernel (bitwise)."""
+    d = scenes.kitchen_standin(width=1920, height=1080, spp=2, max_bounces=8)
+    assert d.triangle_count > 4_900_000
+    b = gpu.BuiltScene(d)
+    try:
+        img = b.render().copy()
+        st = gpu.get_stats()
+        assert np.isfinite(img).all() and np.all(img[..., 3] == 1.0) and img[..., :3].min() >= 0.0
+        assert st["paths"] == 1920 * 1080 * 2 and st["shadowRays"] > 0
+        o = orc.OracleScene(d)
+        r0, r1 = 536, 544
+        band, _, rays = o.render(rows=(r0, r1), spp=2)
+        got, ref = img[r0:r1, :, :3].astype(np.float64), band[r0:r1, :, :3].astype(np.float64)
+        err = ((got - ref) ** 2).sum(-1).reshape(-1)
+        rmse = float(np.sqrt(np.sort(err)[:-8].sum() / (3 * err.size)))          # up to 8 samples may flip on a last-ulp decision (see _render_parity)
+        assert rmse < 1e-3, "band RMSE %.3e" % rmse
+        within = float((np.abs(got - ref) <= 1e-3 + 1e-3 * np.abs(ref)).mean())
+        assert within >= 0.999, within
+        assert rays[0] > (r1 - r0) * 1920 * 2
+        probe = random_rays(60000, 41)
+        probe[:, 0:3] *= np.array([3.5, 2.5, 1.2], np.float32); probe[:, 2] += 1.5          # inside the room
+        h = gpu.trace_rays(b.scene, probe)
+        h_ref = o.trace(probe)
+        for k in ("prim", "inst", "t", "u", "v"):
+            assert np.array_equal(h[k], h_ref[k]), k
+        assert (h["t"] > 0).mean() > 0.9
+        o.close()
+        gpu.set_tuning(maxPathsPerWave=1 << 21)
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(b.render(), img), "wave size changed the image"
+        gpu.set_tuning(maxPathsPerWave=1 << 24, sortByMaterial=0)
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(b.render(), img), "the material sort changed the image"
+        gpu.set_tuning(sortByMaterial=-1, traceVariant=1)
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(b.render(), img), "the traversal kernel changed the image"
+    finally:
+        gpu.set_tuning(maxPathsPerWave=1 << 24, sortByMaterial=-1, traceVariant=0)
+        b.close()
+
+
 @pytest.mark.logs_errors      # a too-short primvar is ignored, loudly
 def test_render_parity_primvars(gpu):
     """R15 scene data: material inputs read from mesh / instancer primvars (constant, instance, uniform, vertex
