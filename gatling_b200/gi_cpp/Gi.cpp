@@ -145,7 +145,12 @@ namespace gtl
     }
 
     // Follows a connected surface-shader input to a texture node.  Returns false if the upstream graph is not
-    // (normalmap ->) UsdUVTexture | image (-> UsdTransform2d -> st reader).
+    // (arithmetic with constants ->) (normalmap ->) UsdUVTexture | image (-> UsdTransform2d -> st reader).
+    // "Arithmetic with constants": multiply / add / subtract / divide / invert nodes whose other operand is a value -- what
+    // authoring tools put between an image and a shader input to tint, scale or invert it.  They compose to one affine map per
+    // component, which folds into the binding's per-channel scale / bias (UsdUVTexture semantics: value = texel * scale + bias,
+    // after the colour-space transform, as in the graph).  Anything that is not affine in ONE lookup (texture x texture, mix,
+    // noise, ...) is not lowered: the input keeps its constant and the caller warns.
     bool lowerTextureInput(const std::string& xml, const XmlInput& in, int paramIndex, int count, bool upsSrgbInput,
                            GtlcTextureBinding& b, std::string& file)
     {
@@ -156,6 +161,34 @@ namespace gtl
       b.fallback[3] = 1.0f; b.uvScale[0] = b.uvScale[1] = 1.0f;
       b.paramIndex = paramIndex; b.componentCount = count;
       std::string output = in.output;
+      float mulK[3] = { 1.0f, 1.0f, 1.0f }, addK[3] = { 0.0f, 0.0f, 0.0f };    // input = node output * mulK + addK, per component
+      for (int hops = 0; hops < 16; hops++) {
+        const bool isMul = category == "multiply", isAdd = category == "add", isSub = category == "subtract", isDiv = category == "divide", isInv = category == "invert";
+        if (!isMul && !isAdd && !isSub && !isDiv && !isInv) break;
+        const XmlInput* a = findInput(node, isInv ? "in" : "in1");
+        const XmlInput* c = findInput(node, isInv ? "amount" : "in2");
+        const bool aConn = a && !a->nodename.empty(), cConn = c && !c->nodename.empty();
+        if (aConn == cConn) return false;                                          // both connected (not affine in one lookup) or none
+        const XmlInput* conn = aConn ? a : c;
+        const XmlInput* konst = aConn ? c : a;
+        float k[3]; const float dflt = (isMul || isDiv || isInv) ? 1.0f : 0.0f;
+        k[0] = k[1] = k[2] = dflt;
+        if (konst && !konst->value.empty()) { float v3[4]; const int n = parseFloats(konst->value, v3, 4); if (n == 1) k[0] = k[1] = k[2] = v3[0]; else for (int q = 0; q < n && q < 3; q++) k[q] = v3[q]; }
+        for (int q = 0; q < 3; q++) {
+          if (isMul) mulK[q] *= k[q];
+          else if (isAdd) addK[q] += k[q] * mulK[q];
+          else if (isSub || isInv) {
+            if (aConn && isSub) addK[q] -= k[q] * mulK[q];                           // upstream - k
+            else { addK[q] += k[q] * mulK[q]; mulK[q] = -mulK[q]; }                  // k - upstream (subtract with in2 connected, invert: amount - in)
+          } else {                                                                  // divide
+            if (!aConn || k[q] == 0.0f) return false;                               // k / upstream is not affine
+            mulK[q] /= k[q];
+          }
+        }
+        output = conn->output;
+        const std::string up = conn->nodename;
+        if (!findNodeByName(xml, up, category, node)) return false;
+      }
       bool decodeNormal = false;
       if (category == "normalmap") {                       // MaterialX normalmap decodes value * 2 - 1 itself
         const XmlInput* src = findInput(node, "in");
@@ -192,6 +225,17 @@ namespace gtl
       // which channels feed the input
       if (output == "r" || output == "g" || output == "b" || output == "a") { const int c = output == "r" ? 0 : output == "g" ? 1 : output == "b" ? 2 : 3; b.channels[0] = b.channels[1] = b.channels[2] = c; }
       else { b.channels[0] = 0; b.channels[1] = count > 1 ? 1 : 0; b.channels[2] = count > 2 ? 2 : 0; }
+      // fold the arithmetic between the lookup and the input into scale / bias of the source channels it reads
+      {
+        bool seen[4] = { false, false, false, false }; float ns[4], nb[4];
+        for (int k = 0; k < count && k < 3; k++) {
+          const int ch = b.channels[k];
+          const float sc = b.scale[ch] * mulK[k], bi = b.bias[ch] * mulK[k] + addK[k];
+          if (seen[ch] && (ns[ch] != sc || nb[ch] != bi)) return false;             // one source channel feeding two components with different maps
+          seen[ch] = true; ns[ch] = sc; nb[ch] = bi;
+        }
+        for (int ch = 0; ch < 4; ch++) if (seen[ch]) { b.scale[ch] = ns[ch]; b.bias[ch] = nb[ch]; }
+      }
       // texture coordinates: UsdTransform2d in front of the st reader
       const XmlInput* st = findInput(node, usdUv ? "st" : "texcoord");
       if (st && !st->nodename.empty()) {

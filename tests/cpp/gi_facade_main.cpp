@@ -69,6 +69,22 @@ static const char* kOpbrNormalMap =
   "<open_pbr_surface name=\"S\" type=\"surfaceshader\"><input name=\"geometry_normal\" type=\"vector3\" nodename=\"nm\"/>"
   "<input name=\"base_color\" type=\"color3\" nodename=\"col\"/><input name=\"specular_roughness\" type=\"float\" nodename=\"noise_graph\"/></open_pbr_surface></materialx>";
 
+// arithmetic with constants between the lookup and the input: roughness = (tex.g * 0.5 + 0.1) * 2, diffuseColor = (1 - tex.rgb) * (0.5, 1, 2),
+// metallic = 0.9 - tex.b / 4; clearcoat = tex.r * tex.g is not affine in one lookup and is not lowered
+static const char* kArithUps =
+  "<materialx version=\"1.38\">"
+  "<image name=\"img\" type=\"color3\"><input name=\"file\" type=\"filename\" value=\"a.ppm\" colorspace=\"lin_rec709\"/></image>"
+  "<multiply name=\"m1\" type=\"float\"><input name=\"in1\" type=\"float\" nodename=\"img\" output=\"g\"/><input name=\"in2\" type=\"float\" value=\"0.5\"/></multiply>"
+  "<add name=\"a1\" type=\"float\"><input name=\"in1\" type=\"float\" value=\"0.1\"/><input name=\"in2\" type=\"float\" nodename=\"m1\"/></add>"
+  "<multiply name=\"m2\" type=\"float\"><input name=\"in1\" type=\"float\" nodename=\"a1\"/><input name=\"in2\" type=\"float\" value=\"2\"/></multiply>"
+  "<invert name=\"inv\" type=\"color3\"><input name=\"in\" type=\"color3\" nodename=\"img\"/></invert>"
+  "<multiply name=\"tint\" type=\"color3\"><input name=\"in1\" type=\"color3\" nodename=\"inv\"/><input name=\"in2\" type=\"color3\" value=\"0.5, 1, 2\"/></multiply>"
+  "<divide name=\"d1\" type=\"float\"><input name=\"in1\" type=\"float\" nodename=\"img\" output=\"b\"/><input name=\"in2\" type=\"float\" value=\"4\"/></divide>"
+  "<subtract name=\"s1\" type=\"float\"><input name=\"in1\" type=\"float\" value=\"0.9\"/><input name=\"in2\" type=\"float\" nodename=\"d1\"/></subtract>"
+  "<multiply name=\"tt\" type=\"float\"><input name=\"in1\" type=\"float\" nodename=\"img\" output=\"r\"/><input name=\"in2\" type=\"float\" nodename=\"img\" output=\"g\"/></multiply>"
+  "<UsdPreviewSurface name=\"S\" type=\"surfaceshader\"><input name=\"roughness\" type=\"float\" nodename=\"m2\"/><input name=\"diffuseColor\" type=\"color3\" nodename=\"tint\"/>"
+  "<input name=\"metallic\" type=\"float\" nodename=\"s1\"/><input name=\"clearcoat\" type=\"float\" nodename=\"tt\"/></UsdPreviewSurface></materialx>";
+
 static const char* kPrimvarUps =
   "<materialx version=\"1.38\"><UsdPrimvarReader name=\"dc\" type=\"color3\"><input name=\"varname\" type=\"string\" value=\"displayColor\"/>"
   "<input name=\"fallback\" type=\"color3\" value=\"0.1, 0.2, 0.9\"/></UsdPrimvarReader>"
@@ -82,6 +98,17 @@ static int lowerTextureTests()
     GtlcMaterialDesc pd; std::vector<GtlcTextureBinding> pb; std::vector<std::string> pf;
     if (!giLowerMtlxToClosureWithTextures(kPrimvarUps, "P", &pd, &pb, &pf) || !pb.empty() || pd.primvarCount != 2) return 40;
     if (pf.size() != 2 || pf[0] != "primvar:displayColor:" + std::to_string((int) GTLC_UPS_DIFFUSE_R) + ":3" || pf[1] != "primvar:rough:" + std::to_string((int) GTLC_UPS_ROUGHNESS) + ":1") return 41;
+  }
+  {
+    GtlcMaterialDesc ad; std::vector<GtlcTextureBinding> ab; std::vector<std::string> af;
+    if (!giLowerMtlxToClosureWithTextures(kArithUps, "A", &ad, &ab, &af) || ab.size() != 3) return 50;      // clearcoat (texture x texture) is not lowered
+    const GtlcTextureBinding *ro = nullptr, *dc = nullptr, *me = nullptr;
+    for (const GtlcTextureBinding& x : ab) { if (x.paramIndex == GTLC_UPS_ROUGHNESS) ro = &x; if (x.paramIndex == GTLC_UPS_DIFFUSE_R) dc = &x; if (x.paramIndex == GTLC_UPS_METALLIC) me = &x; }
+    if (!ro || !dc || !me) return 51;
+    if (ro->channels[0] != 1 || ro->scale[1] != 1.0f || ro->bias[1] != 0.2f) return 52;                     // (g * 0.5 + 0.1) * 2 = g * 1 + 0.2
+    if (dc->scale[0] != -0.5f || dc->bias[0] != 0.5f || dc->scale[1] != -1.0f || dc->bias[1] != 1.0f || dc->scale[2] != -2.0f || dc->bias[2] != 2.0f) return 53;   // (1 - c) * k
+    if (me->channels[0] != 2 || me->scale[2] != -0.25f || me->bias[2] != 0.9f) return 54;                    // 0.9 - b / 4
+    if (ad.params[GTLC_UPS_CLEARCOAT] != 0.0f) return 55;
   }
   GtlcMaterialDesc d; std::vector<GtlcTextureBinding> b; std::vector<std::string> files;
   if (!giLowerMtlxToClosureWithTextures(texturedUps("checker.ppm").c_str(), "T", &d, &b, &files)) return 20;
