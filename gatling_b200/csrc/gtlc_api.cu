@@ -65,6 +65,7 @@ struct Material : Object { Scene* scene; int32_t closure; float params[GTLC_MATE
                            struct PrimvarBinding { int32_t paramIndex, componentCount; std::string name; float fallback[4]; };
                            std::vector<PrimvarBinding> primvarBindings;
                            int opacityBinding = -1;   // index into `bindings` of the binding that feeds the cutout input (textured cutout), or -1
+                           int opacityPrimvar = -1;   // index into `primvarBindings` of the reader that feeds the cutout input (e.g. displayOpacity), or -1
                          };
 
 struct Mesh : Object {
@@ -123,7 +124,7 @@ struct Scene : Object {
   Bvh8 bvh; bool bvhValid = false;        // host copy of the BVH8 (stale while bvhHostStale: built on the device, not yet read back)
   bool bvhHostStale = false; uint32_t nodeCount = 0, triCount = 0, maxDepth = 0, totalTris = 0;
   std::vector<float> hInstOpacity; DeviceArray<float> dInstOpacity;
-  DeviceArray<uint32_t> dMatOpacityBinding; DeviceArray<float> dMatOpacityConst; DeviceArray<CutoutScene> dCutoutScene;   // textured cutouts
+  DeviceArray<uint32_t> dMatOpacityBinding; DeviceArray<float> dMatOpacityConst; DeviceArray<uint2> dMatOpacityPrimvar; DeviceArray<float> dPrimvarFallback; DeviceArray<CutoutScene> dCutoutScene;   // textured cutouts
   std::vector<uint2> hPrimvarInfos; std::vector<float> hPrimvarData; DeviceArray<uint2> dPrimvarInfos; DeviceArray<float> dPrimvarData;   // R15 scene data
   DeviceArray<DevicePrimvarBinding> dPrimvarBindings; DeviceArray<uint2> dMatPrimvarRange;
   std::vector<float> hFverts; std::vector<uint32_t> hFaces;
@@ -345,7 +346,7 @@ bool buildHostGeometry(Scene* s, bool hostBvh = true)
       s->hW2O.insert(s->hW2O.end(), w2o, w2o + 12);
       s->hInstInfo.push_back({ vertexBase, faceBase, flags, matIndex });
       s->hRankBase.push_back(rank);   // rank of (inst, prim) = rankBase[inst] + prim, ascending in (inst, prim)
-      s->hInstOpacity.push_back(m->material->opacityBinding >= 0 ? -1.0f : mat_cutout_opacity(m->material->closure, m->material->params));   // < 0: evaluated per hit
+      s->hInstOpacity.push_back((m->material->opacityBinding >= 0 || m->material->opacityPrimvar >= 0) ? -1.0f : mat_cutout_opacity(m->material->closure, m->material->params));   // < 0: evaluated per hit
       rank += (uint32_t) m->faces.size();
       s->hInstIds.push_back(make_int2(m->id, k < m->instanceIds.size() ? m->instanceIds[k] : (int32_t) k));
       if (!hostBvh) continue;   // the device builder flattens on the GPU (lbvh_flatten_kernel, same arithmetic)
@@ -560,19 +561,20 @@ bool uploadMaterials(Scene* s)
   std::vector<float> params; std::vector<int32_t> closure; std::vector<uint32_t> flags;
   std::vector<DeviceTexture> textures; std::vector<Texture*> textureIndex; std::vector<DeviceTexBinding> bindings; std::vector<uint2> ranges;
   std::vector<DevicePrimvarBinding> pbindings; std::vector<uint2> pranges;
-  std::vector<uint32_t> opacityBinding; std::vector<float> opacityConst;
+  std::vector<uint32_t> opacityBinding; std::vector<float> opacityConst; std::vector<uint2> opacityPrimvar; std::vector<float> pfallback;
   const double kPi = 3.14159265358979323846;
   for (Material* m : s->flatMaterials) {
     params.insert(params.end(), m->params, m->params + GTLC_MATERIAL_PARAM_COUNT);
     closure.push_back(m->closure);
     flags.push_back((mat_is_emissive(m->closure, m->params) || !m->bindings.empty() || !m->primvarBindings.empty() ? kMatFlagEmissive : 0u) |   // a textured input may be the emission
                     (mat_is_thin_walled(m->closure, m->params) ? kMatFlagThinWalled : 0u) |
-                    (mat_cutout_opacity(m->closure, m->params) < 1.0f || m->opacityBinding >= 0 ? kMatFlagCutout : 0u));
+                    (mat_cutout_opacity(m->closure, m->params) < 1.0f || m->opacityBinding >= 0 || m->opacityPrimvar >= 0 ? kMatFlagCutout : 0u));
     opacityBinding.push_back(m->opacityBinding >= 0 ? (uint32_t) (bindings.size() + (size_t) m->opacityBinding) : 0xFFFFFFFFu);
     opacityConst.push_back(mat_cutout_opacity(m->closure, m->params));
+    opacityPrimvar.push_back(m->opacityPrimvar >= 0 ? make_uint2((uint32_t) (pbindings.size() + (size_t) m->opacityPrimvar), (uint32_t) m->opacityPrimvar) : make_uint2(0xFFFFFFFFu, 0u));
     ranges.push_back(make_uint2((uint32_t) bindings.size(), (uint32_t) m->bindings.size()));
     pranges.push_back(make_uint2((uint32_t) pbindings.size(), (uint32_t) m->primvarBindings.size()));
-    for (const Material::PrimvarBinding& pb : m->primvarBindings) { DevicePrimvarBinding d; memset(&d, 0, sizeof(d)); d.paramIndex = pb.paramIndex; d.componentCount = pb.componentCount; memcpy(d.fallback, pb.fallback, 16); pbindings.push_back(d); }
+    for (const Material::PrimvarBinding& pb : m->primvarBindings) { DevicePrimvarBinding d; memset(&d, 0, sizeof(d)); d.paramIndex = pb.paramIndex; d.componentCount = pb.componentCount; memcpy(d.fallback, pb.fallback, 16); pbindings.push_back(d); pfallback.push_back(pb.fallback[0]); }
     for (size_t b = 0; b < m->bindings.size(); b++) {
       const GtlcTextureBinding& src = m->bindings[b];
       Texture* t = m->boundTextures[b];
@@ -593,6 +595,7 @@ bool uploadMaterials(Scene* s)
   s->hasTextures = !bindings.empty() || !pbindings.empty();
   s->hasTexturedCutout = false;
   for (uint32_t ob : opacityBinding) s->hasTexturedCutout = s->hasTexturedCutout || ob != 0xFFFFFFFFu;
+  for (const uint2& op : opacityPrimvar) s->hasTexturedCutout = s->hasTexturedCutout || op.x != 0xFFFFFFFFu;
   if (!s->dPrimvarBindings.upload(pbindings.data(), pbindings.size(), g.stream)) return false;
   if (!s->dMatPrimvarRange.upload(pranges.data(), pranges.size(), g.stream)) return false;
   if (!s->dMatParams.upload(params.data(), params.size(), g.stream)) return false;
@@ -603,10 +606,14 @@ bool uploadMaterials(Scene* s)
   if (!s->dMatTexRange.upload(ranges.data(), ranges.size(), g.stream)) return false;
   if (!s->dMatOpacityBinding.upload(opacityBinding.data(), opacityBinding.size(), g.stream)) return false;
   if (!s->dMatOpacityConst.upload(opacityConst.data(), opacityConst.size(), g.stream)) return false;
+  if (!s->dMatOpacityPrimvar.upload(opacityPrimvar.data(), opacityPrimvar.size(), g.stream)) return false;
+  if (!s->dPrimvarFallback.upload(pfallback.data(), pfallback.size(), g.stream)) return false;
   CutoutScene cut;                                    // what a textured cutout's any-hit test reads (geometry arrays are uploaded before the materials)
   cut.sverts = (const uint32_t*) s->dSverts.ptr; cut.sfaces = (const uint32_t*) s->dSfaces.ptr; cut.instInfo = s->dInstInfo.ptr;
   cut.texBindings = s->dTexBindings.ptr; cut.textures = s->dTextures.ptr;
   cut.matOpacityBinding = s->dMatOpacityBinding.ptr; cut.matOpacityConst = s->dMatOpacityConst.ptr;
+  cut.matOpacityPrimvar = s->dMatOpacityPrimvar.ptr; cut.primvarFallback = s->dPrimvarFallback.ptr;
+  cut.primvarInfos = s->dPrimvarInfos.ptr; cut.primvarData = s->dPrimvarData.ptr; cut.instIds = s->dInstIds.ptr;
   if (!s->dCutoutScene.upload(&cut, 1, g.stream)) return false;
   const uint32_t matCount = (uint32_t) closure.size();
   if (!s->dMatLowered.reserve((size_t) std::max(matCount, 1u) * kLobeFloats)) return false;
@@ -902,7 +909,7 @@ void gtlc_scene_destroy(GtlcHandle h)
 {
   Scene* s = as<Scene>(h, TAG_SCENE); if (!s) return;
   if (g.initialized) { cudaSetDevice(g.device); cudaStreamSynchronize(g.stream); }
-  s->dNodes.release(); s->dTris.release(); s->dNodesT.release(); s->dTrisT.release(); s->dSverts.release(); s->dSfaces.release(); s->dMatLowered.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release(); s->dMatOpacityBinding.release(); s->dMatOpacityConst.release(); s->dCutoutScene.release();
+  s->dNodes.release(); s->dTris.release(); s->dNodesT.release(); s->dTrisT.release(); s->dSverts.release(); s->dSfaces.release(); s->dMatLowered.release(); s->dFverts.release(); s->dFaces.release(); s->dO2W.release(); s->dW2O.release(); s->dInstInfo.release(); s->dInstIds.release(); s->dFaceIds.release(); s->dRankBase.release(); s->dInstOpacity.release(); s->dMatOpacityBinding.release(); s->dMatOpacityConst.release(); s->dMatOpacityPrimvar.release(); s->dPrimvarFallback.release(); s->dCutoutScene.release();
   s->dMatParams.release(); s->dTextures.release(); s->dTexBindings.release(); s->dMatTexRange.release(); s->dPrimvarInfos.release(); s->dPrimvarData.release(); s->dPrimvarBindings.release(); s->dMatPrimvarRange.release(); s->dMatClosure.release(); s->dMatFlags.release(); s->dSphere.release(); s->dDistant.release(); s->dRect.release(); s->dDisk.release(); s->dPixelMap.release();
   s->tag = 0;
   delete s;
@@ -981,6 +988,8 @@ GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
         m->opacityBinding = (int) b;
       }
     }
+    for (uint32_t b = 0; b < d->primvarCount; b++)
+      if (d->primvars[b].componentCount == 1 && d->primvars[b].paramIndex == opacityParam) m->opacityPrimvar = (int) b;
   }
   for (uint32_t b = 0; b < d->primvarCount; b++) { Material::PrimvarBinding pb; pb.paramIndex = d->primvars[b].paramIndex; pb.componentCount = d->primvars[b].componentCount; pb.name = d->primvars[b].name ? d->primvars[b].name : ""; memcpy(pb.fallback, d->primvars[b].fallback, 16); m->primvarBindings.push_back(pb); }
   {

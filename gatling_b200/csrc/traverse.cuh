@@ -66,6 +66,12 @@ struct CutoutScene {
   const DeviceTexture* __restrict__ textures;
   const uint32_t* __restrict__ matOpacityBinding;   // per material: index into texBindings of the binding that feeds the cutout input, or 0xFFFFFFFF
   const float* __restrict__ matOpacityConst;        // per material: the constant cutout opacity (what a missing binding falls back to)
+  // ... or a primvar reader (UsdPreviewSurface.opacity <- displayOpacity is the common case): scene_data_lookup_float / _int at the hit
+  const uint2* __restrict__ matOpacityPrimvar;      // per material: (index into primvarFallback, column k of the mesh's scene-data row) or (0xFFFFFFFF, -)
+  const float* __restrict__ primvarFallback;        // fallback[0] of every primvar binding
+  const uint2* __restrict__ primvarInfos;           // as DeviceScene.primvarInfos
+  const float* __restrict__ primvarData;
+  const int2* __restrict__ instIds;
 };
 
 struct TraceParams {
@@ -184,7 +190,8 @@ __device__ __noinline__ float cutout_opacity_at(const CutoutScene* __restrict__ 
   const CutoutScene c = *cs;
   const InstanceInfo in = c.instInfo[inst];
   const uint32_t bi = c.matOpacityBinding[in.material];
-  if (bi == 0xFFFFFFFFu) return c.matOpacityConst[in.material];
+  const uint2 pv = c.matOpacityPrimvar[in.material];
+  if (bi == 0xFFFFFFFFu && pv.x == 0xFFFFFFFFu) return c.matOpacityConst[in.material];
   const uint4 fr = __ldg((const uint4*) (c.sfaces + (size_t) (in.faceBase + prim) * kShadeFaceWords));
   const uint32_t* vb = c.sverts + (size_t) in.vertexBase * kShadeVertexWords;
   // words 0..2 position, 7 u, 11 v of each shading vertex
@@ -192,6 +199,27 @@ __device__ __noinline__ float cutout_opacity_at(const CutoutScene* __restrict__ 
   const uint4 b0 = __ldg((const uint4*) (vb + (size_t) fr.y * kShadeVertexWords)), b1 = __ldg((const uint4*) (vb + (size_t) fr.y * kShadeVertexWords + 4)), b2 = __ldg((const uint4*) (vb + (size_t) fr.y * kShadeVertexWords + 8));
   const uint4 c0 = __ldg((const uint4*) (vb + (size_t) fr.z * kShadeVertexWords)), c1 = __ldg((const uint4*) (vb + (size_t) fr.z * kShadeVertexWords + 4)), c2 = __ldg((const uint4*) (vb + (size_t) fr.z * kShadeVertexWords + 8));
   const V3 bc = v3((1.0f - hu) - hv, hu, hv);
+  if (bi == 0xFFFFFFFFu) {                          // primvar-driven (a texture binding on the same input is applied later and wins, as in shading)
+    const uint2 info = c.primvarInfos[(size_t) (in.flags >> 8) * GTLC_MAX_PRIMVAR_BINDINGS + pv.y];
+    float o;
+    if (!(info.y & 0x100u)) o = c.primvarFallback[pv.x];                               // scene_data_isvalid: default_value
+    else {
+      const uint32_t stride = info.y & 15u, interpolation = (info.y >> 4) & 15u;
+      uint32_t i0 = fr.x, i1 = fr.y, i2 = fr.z;                                        // get_scene_data_indices, mdl_interface.glsl:281-301
+      if (interpolation == GTLC_INTERP_UNIFORM) i0 = i1 = i2 = prim;
+      else if (interpolation == GTLC_INTERP_INSTANCE) { const int id = c.instIds[inst].y; i0 = i1 = i2 = id > 0 ? (uint32_t) id : 0u; }
+      else if (interpolation == GTLC_INTERP_CONSTANT) i0 = i1 = i2 = 0u;
+      const float* d = c.primvarData + info.x;
+      if (info.y & 0x200u) {                                                           // scene_data_lookup_int: nearest vertex
+        const uint32_t pick = bc.x > bc.y ? (bc.x > bc.z ? i0 : i2) : (bc.y > bc.z ? i1 : i2);
+        o = (float) (int32_t) f2u(__ldg(d + (size_t) pick * stride));
+      } else {
+        const float v0 = __ldg(d + (size_t) i0 * stride), v1 = __ldg(d + (size_t) i1 * stride), v2 = __ldg(d + (size_t) i2 * stride);
+        o = (v0 * bc.x + v1 * bc.y) + v2 * bc.z;
+      }
+    }
+    return o < 0.0f ? 0.0f : (o > 1.0f ? 1.0f : o);
+  }
   const V3 p0 = v3(u2f(a0.x), u2f(a0.y), u2f(a0.z)), p1 = v3(u2f(b0.x), u2f(b0.y), u2f(b0.z)), p2 = v3(u2f(c0.x), u2f(c0.y), u2f(c0.z));
   const V3 localPos = (p0 * bc.x + p1 * bc.y) + p2 * bc.z;
   const float stu = (bc.x * u2f(a1.w) + bc.y * u2f(b1.w)) + bc.z * u2f(c1.w);

@@ -419,7 +419,7 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
     aov->instanceId = in.instanceId;                                      // :243
     aov->doubleSided = isDoubleSided;                                     // :247
     aov->posNormal = (normal + v3(1.0f)) * 0.5f;                          // :252
-    aov->cutoutOpacity = (mat_cutout_opacity(base) < 1.0f || s.materialOpacityBinding[in.material] >= 0) ? mat_cutout_opacity(mat) : -1.0f;
+    aov->cutoutOpacity = (mat_cutout_opacity(base) < 1.0f || s.materialOpacityBinding[in.material] >= 0 || s.materialOpacityPrimvar[in.material] >= 0) ? mat_cutout_opacity(mat) : -1.0f;
     aov->albedo = bsdf_albedo(mat, -worldRayDir, st);                     // :264-280 (front-face BSDF; no backface BSDFs exist here)
   }
 
@@ -666,6 +666,10 @@ void* orc_scene_create(const OrcSceneDesc* d)
     for (uint32_t b = 0; md.textures && b < md.textureCount; b++)
       if (md.textures[b].componentCount == 1 && md.textures[b].paramIndex == opacityParam) ob = (int) b;
     s->materialOpacityBinding.push_back(ob);
+    int op = -1;
+    for (uint32_t b = 0; md.primvars && b < md.primvarCount; b++)
+      if (md.primvars[b].componentCount == 1 && md.primvars[b].paramIndex == opacityParam) op = (int) b;
+    s->materialOpacityPrimvar.push_back(op);
   }
   for (uint32_t i = 0; i < d->textureCount; i++) {
     const GtlcTextureDesc& td = d->textures[i];

@@ -116,6 +116,7 @@ struct Scene {
   std::vector<Texture> textures;                                   // R15
   std::vector<std::vector<GtlcTextureBinding>> materialTextures;   // per material; .texture = 1-based index into `textures`
   std::vector<int> materialOpacityBinding;                         // per material: index of the binding that feeds the cutout input, or -1
+  std::vector<int> materialOpacityPrimvar;                         // per material: index of the primvar reader that feeds it (e.g. displayOpacity), or -1
   std::vector<std::vector<GtlcPrimvarBinding>> materialPrimvars;   // per material (names already resolved into primvarInfos)
   std::vector<uint32_t> primvarInfos; std::vector<float> primvarData;
   std::vector<SphereLight> sphereLights;
@@ -228,7 +229,8 @@ static void scene_build(Scene& s)
       t.v1 = xform_point(in.objectToWorld, v3(b.pos[0], b.pos[1], b.pos[2]));
       t.v2 = xform_point(in.objectToWorld, v3(c.pos[0], c.pos[1], c.pos[2]));
       t.prim = f; t.inst = (uint32_t) ii;
-      t.opacity = (!s.materialOpacityBinding.empty() && s.materialOpacityBinding[in.material] >= 0) ? -1.0f : mat_cutout_opacity(s.materials[in.material]);   // < 0: per hit
+      const bool perHit = (!s.materialOpacityBinding.empty() && s.materialOpacityBinding[in.material] >= 0) || (!s.materialOpacityPrimvar.empty() && s.materialOpacityPrimvar[in.material] >= 0);
+      t.opacity = perHit ? -1.0f : mat_cutout_opacity(s.materials[in.material]);   // < 0: per hit
       s.tris.push_back(t);
     }
   }
@@ -357,6 +359,28 @@ static inline float cutout_opacity_at(const Scene& s, uint32_t prim, uint32_t in
   const InstanceDesc& in = s.instances[inst];
   const int bi = s.materialOpacityBinding[in.material];
   const uint32_t* f = &s.faces[(size_t) (in.faceBase + prim) * 3];
+  if (bi < 0) {                                   // primvar-driven: scene_data_lookup_float / _int (mdl_interface.glsl:281-301, 417-479) at this hit
+    const int k = s.materialOpacityPrimvar[in.material];
+    const GtlcPrimvarBinding& pb = s.materialPrimvars[in.material][(size_t) k];
+    const V3 bc = v3((1.0f - hu) - hv, hu, hv);
+    float o = pb.fallback[0];
+    if (!s.primvarInfos.empty()) {
+      const uint32_t* info = &s.primvarInfos[((size_t) inst * GTLC_MAX_PRIMVAR_BINDINGS + (size_t) k) * 2];
+      if (info[1] & 0x100u) {
+        const uint32_t stride = info[1] & 15u, interpolation = (info[1] >> 4) & 15u;
+        uint32_t idx[3] = { f[0], f[1], f[2] };
+        if (interpolation == GTLC_INTERP_UNIFORM) idx[0] = idx[1] = idx[2] = prim;
+        else if (interpolation == GTLC_INTERP_INSTANCE) idx[0] = idx[1] = idx[2] = in.instanceId > 0 ? (uint32_t) in.instanceId : 0u;
+        else if (interpolation == GTLC_INTERP_CONSTANT) idx[0] = idx[1] = idx[2] = 0u;
+        const float* dta = &s.primvarData[info[0]];
+        if (info[1] & 0x200u) {
+          const uint32_t pick = bc.x > bc.y ? (bc.x > bc.z ? idx[0] : idx[2]) : (bc.y > bc.z ? idx[1] : idx[2]);
+          o = (float) (int32_t) floatBitsToUint(dta[(size_t) pick * stride]);
+        } else o = (dta[(size_t) idx[0] * stride] * bc.x + dta[(size_t) idx[1] * stride] * bc.y) + dta[(size_t) idx[2] * stride] * bc.z;
+      }
+    }
+    return o < 0.0f ? 0.0f : (o > 1.0f ? 1.0f : o);
+  }
   const FVertex& v0 = s.fverts[in.vertexBase + f[0]];
   const FVertex& v1 = s.fverts[in.vertexBase + f[1]];
   const FVertex& v2 = s.fverts[in.vertexBase + f[2]];

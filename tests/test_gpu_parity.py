@@ -431,6 +431,39 @@ def test_textured_cutout_and_lookup_modes_parity(gpu):
     assert np.abs(img - img_solid).mean() > 1e-3, "the opacity textures changed nothing"
 
 
+def test_primvar_driven_cutout_parity(gpu):
+    """UsdPreviewSurface.opacity <- displayOpacity: the cutout input read from a primvar (vertex ramp on the tall box, per-face
+    integer flags on the short one, a missing primvar with fallback 0.3 on the back wall) inside the any-hit test."""
+    d = _lit_cornell(96, 96, 6)
+    mats = list(d.materials)
+
+    def cut(name, fallback):
+        m = scenes.material_usd_preview_surface(name, diffuse=(0.3, 0.6, 0.8))
+        m.primvars = [scenes.PrimvarBinding(scenes.UPS["opacity"], 1, "displayOpacity", (fallback, 0, 0, 0))]
+        return m
+    mats += [cut("ramp", 1.0), cut("flags", 1.0), cut("missing", 0.3)]
+    for i, m in enumerate(d.meshes):
+        if m.name in ("Box1", "Box2"):
+            xf = np.asarray(m.transform, np.float32).copy(); xf[3, 2] += 0.03          # no z-fighting with the floor once see-through
+            if m.name == "Box1":
+                pv = scenes.Primvar("displayOpacity", scenes.INTERP_VERTEX, np.linspace(0.05, 1.0, len(m.vertices), dtype=np.float32)[:, None])
+                d.meshes[i] = dataclasses.replace(m, material=len(mats) - 3, transform=xf, primvars=[pv])
+            else:
+                pv = scenes.Primvar("displayOpacity", scenes.INTERP_UNIFORM, (np.arange(len(m.faces)) % 2).astype(np.int32)[:, None])
+                d.meshes[i] = dataclasses.replace(m, material=len(mats) - 2, transform=xf, primvars=[pv])
+        elif m.name == "BackPlane":
+            d.meshes[i] = dataclasses.replace(m, material=len(mats) - 1)
+    d.materials = mats
+    cam = orc.camera_rays(d, 0)
+    cam[:, 3] = 0.0
+    cam[:, 7] = 3.0e38
+    h = _trace_parity(gpu, d, np.concatenate([cam, random_rays(30000, 29)]), walker=False)
+    assert (h["t"] > 0).any()
+    _render_parity(gpu, d)
+    got = _aov_parity(gpu, dataclasses.replace(d, width=48, height=48))
+    assert len(np.unique(np.round(got[gpu.GiAovId.Opacity][..., :3].reshape(-1, 3), 3), axis=0)) > 10
+
+
 def test_traversal_variants_are_invisible(gpu):
     """The traversal kernels (GtlcTuning.traceVariant 0 = 7 batched default, 1 per-lane loop, 6 TMA-staged ray tiles) walk the BVH in a different order; the
     closest hit is order-independent (smallest t, ties by (instance, primitive)), so hit records and images must be

@@ -93,3 +93,48 @@ def test_integer_primvars_take_the_nearest_vertex():
     d = _one_quad([scenes.Primvar("k", scenes.INTERP_UNIFORM, per_face)], scenes.PrimvarBinding(2, 1, "k"))
     alb = orc.OracleScene(d).render_aovs([16])[16][..., :3]
     assert set(np.unique(alb[hit][:, 2]).tolist()) <= {3.0, 7.0}
+
+
+def test_primvar_driven_cutout_opacity():
+    """UsdPreviewSurface.opacity <- UsdPrimvarReader(displayOpacity): the any-hit test evaluates the reader at the candidate hit
+    (rp_main.ahit:35-61 runs mdl_cutout_opacity on a shading state, which can read scene data).  Per-face opacities 0 / 1 let
+    exactly one triangle of the quad stop rays; a vertex ramp lets more rays through where it is low."""
+    base = scenes.cornell(8, 8).meshes[3]
+    nv, nf = len(base.vertices), len(base.faces)
+    ups = scenes.material_usd_preview_surface("op", diffuse=(0.5, 0.5, 0.5))
+
+    def scene(primvars, fallback=1.0):
+        d = scenes.cornell(48, 48, spp=1)
+        quad = [m for m in d.meshes if m.name == "BackPlane"][0]
+        mat = scenes.material_usd_preview_surface("op", diffuse=(0.5, 0.5, 0.5))
+        mat.primvars = [scenes.PrimvarBinding(scenes.UPS["opacity"], 1, "displayOpacity", (fallback, 0, 0, 0))]
+        d.materials = [mat]
+        d.meshes = [dataclasses.replace(quad, material=0, primvars=list(primvars))]
+        d.settings = dataclasses.replace(d.settings, jitteredSampling=False)
+        return d
+    rays = orc.camera_rays(scene([]), 0); rays[:, 3] = 0.0; rays[:, 7] = 3.0e38
+    solid = orc.OracleScene(scene([])).trace(rays)                      # missing primvar -> fallback 1 -> opaque
+    on = solid["t"] >= 0
+    assert on.mean() > 0.3
+    assert not (orc.OracleScene(scene([], fallback=0.0)).trace(rays)["t"] >= 0).any()      # fallback 0: fully transparent
+    per_face = np.array([[0.0], [1.0]], np.float32)[:nf]
+    h = orc.OracleScene(scene([scenes.Primvar("displayOpacity", scenes.INTERP_UNIFORM, per_face)])).trace(rays)
+    assert np.array_equal(h["t"] >= 0, on & (solid["prim"] == 1))
+    a = orc.OracleScene(scene([scenes.Primvar("displayOpacity", scenes.INTERP_UNIFORM, per_face)])).trace(rays, any_hit=True)
+    assert np.array_equal(a["t"] >= 0, h["t"] >= 0)
+    flags = np.array([[1], [0]], np.int32)[:nf]                          # the same through an integer primvar
+    hi = orc.OracleScene(scene([scenes.Primvar("displayOpacity", scenes.INTERP_UNIFORM, flags)])).trace(rays)
+    assert np.array_equal(hi["t"] >= 0, on & (solid["prim"] == 0))
+    ramp = np.linspace(0.0, 1.0, nv, dtype=np.float32)[:, None]
+    hr = orc.OracleScene(scene([scenes.Primvar("displayOpacity", scenes.INTERP_VERTEX, ramp)])).trace(rays)
+    # with the ray-query seed (0) the acceptance draw is one number per triangle: a hit survives iff the opacity interpolated at
+    # it reaches that threshold -- per triangle, every surviving hit has a higher opacity than every ignored one
+    f = base.faces
+    op = ((1.0 - solid["u"] - solid["v"]) * ramp[f[np.minimum(solid["prim"], nf - 1), 0], 0] + solid["u"] * ramp[f[np.minimum(solid["prim"], nf - 1), 1], 0]
+          + solid["v"] * ramp[f[np.minimum(solid["prim"], nf - 1), 2], 0])
+    kept = hr["t"] >= 0
+    assert np.array_equal(kept & ~on, np.zeros_like(on)) and (on & ~kept).any() and kept.any()
+    for tri in range(nf):
+        m = on & (solid["prim"] == tri)
+        if (m & kept).any() and (m & ~kept).any():
+            assert op[m & kept].min() >= op[m & ~kept].max() - 1e-6
