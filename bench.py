@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--tile", type=int, default=64)
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "samples"], help="N>1: framebuffer tiles (default; bit-identical image) or sample ranges (SURVEY.md 8e alternative)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the bounded oracle sample")
     ap.add_argument("--cpu-sample-only", action="store_true", help="(internal) reference arm: print the cpu_baseline object of one bounded sample and exit")
@@ -77,8 +78,10 @@ def workload_config(label, d, a, n_gpus):
     return {
         "workload": label, "triangles": d.triangle_count, "materials": len(d.materials), "width": d.width, "height": d.height,
         "spp": d.settings.spp, "max_bounces": d.settings.maxBounces, "nee": bool(d.settings.nextEventEstimation),
-        "parallelism": ("tile-sharded framebuffer (%dx%d tiles, tile %% n_gpus == rank) x%d + one ncclReduce(sum) of the HDR accumulator to rank 0 inside gtlc_render" % (a.tile, a.tile, n_gpus))
-                       if n_gpus > 1 else "single GPU",
+        "parallelism": "single GPU" if n_gpus <= 1 else
+                       ("sample-range sharding (every pixel, samples [spp*rank/n_gpus, spp*(rank+1)/n_gpus)) x%d + one ncclReduce(sum) of the HDR accumulator to rank 0 inside gtlc_render" % n_gpus)
+                       if a.shard == "samples" else
+                       ("tile-sharded framebuffer (%dx%d tiles, tile %% n_gpus == rank) x%d + one ncclReduce(sum) of the HDR accumulator to rank 0 inside gtlc_render" % (a.tile, a.tile, n_gpus)),
         "l2_policy": "inputs larger than L2: every wave streams ~2.3 GB of path-state / ray / hit queues (L2 = 126 MB); scene data stays resident in HBM as in production",
     }
 
@@ -250,7 +253,7 @@ def measure(name, a, gi, torch, dist, rank, world, local_rank, steps, warmup, sa
 
     def step(readback):
         gi.set_tuning(skipReadback=0 if readback else 1)
-        gi.set_shard(built.scene, rank, world, a.tile)     # resets the accumulation: every step renders samples [0, spp)
+        gi.set_shard(built.scene, rank, world, gi.SHARD_SAMPLES if a.shard == "samples" else a.tile)     # resets the accumulation: every step renders samples [0, spp)
         built.render()                                      # at N>1 ends with the library's ncclReduce to rank 0 (and rank 0's D2H copy when readback is on)
         return gi.get_stats()
 

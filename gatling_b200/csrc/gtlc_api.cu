@@ -720,7 +720,7 @@ bool requireInit()
 
 bool buildPixelMap(Scene* s, uint32_t W, uint32_t H)
 {
-  if (s->shardCount <= 1) { s->localPixels = W * H; s->pixelMapCount = 1; s->pixelMapW = W; s->pixelMapH = H; return true; }
+  if (s->shardCount <= 1 || s->shardTile == GTLC_SHARD_SAMPLES) { s->localPixels = W * H; s->pixelMapCount = 1; s->pixelMapW = W; s->pixelMapH = H; return true; }
   if (s->pixelMapW == W && s->pixelMapH == H && s->pixelMapRank == s->shardRank && s->pixelMapCount == s->shardCount && s->pixelMapTile == s->shardTile) return true;
   std::vector<uint32_t> map;
   const uint32_t T = s->shardTile, tilesX = (W + T - 1) / T;
@@ -1413,9 +1413,13 @@ int gtlc_render(const GtlcRenderParams* params)
   auto body = [&]() -> bool {
     if (!buildPixelMap(s, W, H)) return false;
     const uint32_t localPixels = s->localPixels;
+    // tiles: this rank's pixels, all samples.  sample ranges: all pixels, this rank's share of the call's samples (gtlc.h)
+    const bool sampleShard = s->shardCount > 1 && s->shardTile == GTLC_SHARD_SAMPLES, tileShard = s->shardCount > 1 && !sampleShard;
+    const uint32_t sBegin = sampleShard ? (uint32_t) ((uint64_t) rs.spp * s->shardRank / s->shardCount) : 0u;
+    const uint32_t sEnd = sampleShard ? (uint32_t) ((uint64_t) rs.spp * (s->shardRank + 1) / s->shardCount) : rs.spp;
     const uint32_t maxPaths = std::max<uint32_t>(g.tuning.maxPathsPerWave, 1024u);
     uint32_t pixelsPerWave = std::min(localPixels, maxPaths);
-    uint32_t samplesPerWave = std::max<uint32_t>(1u, std::min<uint32_t>(rs.spp, pixelsPerWave ? maxPaths / pixelsPerWave : 1u));
+    uint32_t samplesPerWave = std::max<uint32_t>(1u, std::min<uint32_t>(std::max(sEnd - sBegin, 1u), pixelsPerWave ? maxPaths / pixelsPerWave : 1u));
     if (pixelsPerWave < localPixels) samplesPerWave = 1;
     if (!ensurePool((size_t) pixelsPerWave * samplesPerWave)) return false;
     const bool volumes = rs.mediumStackSize > 0;
@@ -1441,7 +1445,7 @@ int gtlc_render(const GtlcRenderParams* params)
     cudaEvent_t evStart = nextEvent(), evEnd = nextEvent();
     cudaEventRecord(evStart, g.stream);
     // sharded render: pixels of other ranks are 0 so that one sum-reduce assembles the image
-    if (colorDev && s->shardCount > 1 && s->sampleOffset == 0) CUDA_OK(cudaMemsetAsync(colorDev, 0, (size_t) W * H * 16, g.stream));
+    if (colorDev && tileShard && s->sampleOffset == 0) CUDA_OK(cudaMemsetAsync(colorDev, 0, (size_t) W * H * 16, g.stream));
     // auxiliary AOVs (everything but Color): device targets + clear values for resolve_aov_kernel
     AovTargets targets; memset(&targets, 0, sizeof(targets));
     bool aovMode = false;
@@ -1470,9 +1474,11 @@ int gtlc_render(const GtlcRenderParams* params)
     uint64_t paths = 0;
     for (uint32_t pixBase = 0; pixBase < localPixels; pixBase += pixelsPerWave) {
       const uint32_t wavePixels = std::min(pixelsPerWave, localPixels - pixBase);
-      for (uint32_t sBase = 0; sBase < rs.spp; sBase += samplesPerWave) {
-        WaveParams wp; wp.wavePixelBase = pixBase; wp.wavePixels = wavePixels; wp.waveSamples = std::min(samplesPerWave, rs.spp - sBase);
-        wp.waveSampleBase = sBase; wp.pixelMap = (s->shardCount > 1) ? s->dPixelMap.ptr : nullptr;
+      // (a rank whose sample range is empty -- spp < worldSize -- still runs one wave of zero samples: its pixels blend to the previous partial)
+      for (uint32_t sBase = sBegin; sBase < sEnd || sBase == sBegin; sBase += samplesPerWave) {
+        WaveParams wp; wp.wavePixelBase = pixBase; wp.wavePixels = wavePixels; wp.waveSamples = std::min(samplesPerWave, sEnd - sBase);
+        wp.waveSampleBase = sBase; wp.pixelMap = tileShard ? s->dPixelMap.ptr : nullptr;
+        wp.firstWave = sBase == sBegin ? 1u : 0u; wp.alpha = (sampleShard && s->shardRank != 0) ? 0.0f : 1.0f;
         paths += (uint64_t) wp.wavePixels * wp.waveSamples;
         timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.q[0], g.counters, aovBufs.clk); });
         int inIdx = 0;
@@ -1525,9 +1531,9 @@ int gtlc_render(const GtlcRenderParams* params)
           }
           inIdx ^= 1;
         }
-        const int lastWave = (sBase + samplesPerWave >= rs.spp) ? 1 : 0;
+        const int lastWave = (sBase + samplesPerWave >= sEnd) ? 1 : 0;
         timed(K_RESOLVE, [&] { resolve_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, g.accum, colorDev, lastWave); });
-        if (aovMode) timed(K_RESOLVE, [&] { resolve_aov_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, aovBufs, targets, sBase == 0 ? 1 : 0, lastWave); });
+        if (aovMode) timed(K_RESOLVE, [&] { resolve_aov_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.sampleRad, aovBufs, targets, sBase == sBegin ? 1 : 0, lastWave); });
       }
     }
     // the single collective of the path: every rank's colour AOV holds its own tiles and zeros elsewhere;

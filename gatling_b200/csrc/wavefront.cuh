@@ -101,6 +101,8 @@ struct WaveParams {
   uint32_t waveSamples;     // samples per pixel in this wave
   uint32_t waveSampleBase;  // index of the wave's first sample within this giRender call (s in rgen:215)
   const uint32_t* __restrict__ pixelMap;  // local pixel -> global pixel index (NULL = identity)
+  uint32_t firstWave;       // this pixel range's first wave of the call (the sample sum starts at 0)
+  float alpha;              // w of the colour AOV: 1, or 0 on the ranks > 0 of a sample-range shard (gtlc.h)
 };
 
 // Per-sample capture of what the closest-hit shader writes into the auxiliary AOVs on the first bounce
@@ -823,7 +825,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(UniformData ubo, WaveParam
   const float invSpp = 1.0f / (float) ubo.spp;                                         // :212
   for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < wp.wavePixels; q += gridDim.x * blockDim.x) {
     const uint32_t lp = wp.wavePixelBase + q;
-    float4 a4 = (wp.waveSampleBase == 0) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : accum[lp];
+    float4 a4 = wp.firstWave ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : accum[lp];
     V3 pixel_color = v3(a4.x, a4.y, a4.z);
     for (uint32_t j = 0; j < wp.waveSamples; j++) {
       const float4 r4 = sampleRad[(size_t) j * wp.wavePixels + q];
@@ -839,7 +841,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(UniformData ubo, WaveParam
     V3 prevColor = pixel_color;                                                        // :507
     if ((ubo.flags & FLAG_PROGRESSIVE) && ubo.sampleOffset > 0) { const float4 p4 = colorAov[pixelIndex]; prevColor = v3(p4.x, p4.y, p4.z); }  // :508-513
     const V3 o = (prevColor * (float) ubo.sampleOffset + pixel_color * (float) ubo.spp) * ubo.invTotalSampleCount;   // :514
-    colorAov[pixelIndex] = make_float4(o.x, o.y, o.z, 1.0f);
+    colorAov[pixelIndex] = make_float4(o.x, o.y, o.z, wp.alpha);
   }
 }
 

@@ -334,6 +334,9 @@ def giRender(scene, camera: S.Camera, settings: S.RenderSettings, aov_bindings, 
 
 
 # ---- extensions (no Gi.h counterpart) ---------------------------------------------------
+SHARD_SAMPLES = 0xFFFFFFFF   # GTLC_SHARD_SAMPLES: as `tile`, selects sample-range sharding (every pixel, a share of the samples)
+
+
 def set_shard(scene, rank, world_size, tile=64):
     _lib().gtlc_scene_set_shard(scene, rank, world_size, tile)
 

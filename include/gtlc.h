@@ -370,7 +370,14 @@ GTLC_API int gtlc_render(const GtlcRenderParams* params);
 
 /* Multi-GPU framebuffer sharding: this process renders only the tiles with
  * (tileIndex % worldSize == rank); all other pixels of the colour AOV are written as 0 so that a
- * single sum-reduce over ranks yields the full image.  tileSize in pixels (square tiles). */
+ * single sum-reduce over ranks yields the full image.  tileSize in pixels (square tiles; 0 = 64).
+ * tileSize == GTLC_SHARD_SAMPLES selects the alternative of SURVEY.md 8e, sample-range sharding: the process renders
+ * EVERY pixel but only the samples [spp * rank / worldSize, spp * (rank + 1) / worldSize) of each gtlc_render call, scaled
+ * by the call's full sample count (every term of rp_main.rgen:498 and :514 is linear in the samples), with w = 1 on rank 0
+ * and 0 elsewhere -- the same sum-reduce yields the image.  Tiles give bit-identical pixels (x + 0); sample ranges agree to
+ * rounding (a + b summed in another order) and balance ranks on scenes whose cost varies across the frame.  Auxiliary
+ * AOVs are not reduced: under sample-range sharding each rank's are those of its own samples. */
+#define GTLC_SHARD_SAMPLES 0xFFFFFFFFu
 GTLC_API void gtlc_scene_set_shard(GtlcHandle scene, uint32_t rank, uint32_t worldSize, uint32_t tileSize);
 
 /* The one collective of the path: with a communicator in place, gtlc_render() of a sharded scene ends

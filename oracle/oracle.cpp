@@ -646,7 +646,7 @@ struct OrcRenderDesc {
   uint32_t width, height;
   uint32_t sampleOffset;
   uint32_t rowBegin, rowEnd;      // bounded samples for the CPU baseline: render rows [rowBegin, rowEnd)
-  uint32_t shardRank, shardCount, shardTile; // shardCount <= 1: everything
+  uint32_t shardRank, shardCount, shardTile; // shardCount <= 1: everything; shardTile == GTLC_SHARD_SAMPLES: every pixel, samples [spp*rank/count, spp*(rank+1)/count)
 };
 
 void* orc_scene_create(const OrcSceneDesc* d)
@@ -743,6 +743,11 @@ double orc_render(void* h, const OrcRenderDesc* r, float* rgba, uint64_t* rayCou
   uint32_t W = r->width, H = r->height, spp = r->settings.spp;
   uint32_t rowEnd = r->rowEnd ? r->rowEnd : H;
   float invSpp = 1.0f / (float) spp;                                      // :212
+  // Sample-range sharding (the alternative to tiles): this rank's share of the call's samples, every term of
+  // :498 and :514 linear in the samples, so that the sum over ranks is the image (w: 1 on rank 0, 0 elsewhere).
+  const bool sampleShard = r->shardCount > 1 && r->shardTile == GTLC_SHARD_SAMPLES;
+  const uint32_t sBegin = sampleShard ? (uint32_t) ((uint64_t) spp * r->shardRank / r->shardCount) : 0u;
+  const uint32_t sEnd = sampleShard ? (uint32_t) ((uint64_t) spp * (r->shardRank + 1) / r->shardCount) : spp;
   uint64_t nClosest = 0, nShadow = 0;
   auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nClosest, nShadow)
@@ -751,20 +756,20 @@ double orc_render(void* h, const OrcRenderDesc* r, float* rgba, uint64_t* rayCou
     for (uint32_t x = 0; x < W; x++) {
       uint32_t pixelIndex = x + (uint32_t) y * W;                         // :195
       float* out = &rgba[(size_t) pixelIndex * 4];
-      if (r->shardCount > 1) {
+      if (r->shardCount > 1 && !sampleShard) {
         uint32_t tilesX = (W + r->shardTile - 1) / r->shardTile;
         uint32_t tile = ((uint32_t) y / r->shardTile) * tilesX + (x / r->shardTile);
         if (tile % r->shardCount != r->shardRank) { out[0] = out[1] = out[2] = out[3] = 0.0f; continue; }
       }
       V3 pixel_color = v3(0.0f);
-      for (uint32_t sIdx = 0; sIdx < spp; sIdx++) {
+      for (uint32_t sIdx = sBegin; sIdx < sEnd; sIdx++) {
         V3 sample_color = trace_sample(c, x, (uint32_t) y, pixelIndex, sIdx, rc);
         pixel_color += sample_color * invSpp;                             // :498
       }
       V3 prevColor = pixel_color;                                         // :507-514
       if (c.fl.progressive && c.ubo.sampleOffset > 0) prevColor = v3(out[0], out[1], out[2]);
       V3 o = (prevColor * (float) c.ubo.sampleOffset + pixel_color * (float) c.ubo.spp) * c.ubo.invTotalSampleCount;
-      out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = 1.0f;
+      out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = (sampleShard && r->shardRank != 0) ? 0.0f : 1.0f;
     }
     nClosest += rc.closest; nShadow += rc.shadow;
   }

@@ -376,6 +376,8 @@ class OracleScene:
         except Exception:
             pass
 
+    SHARD_SAMPLES = 0xFFFFFFFF   # as the tile size of `shard=(rank, world, tile)`: sample-range sharding (gtlc.h GTLC_SHARD_SAMPLES)
+
     def render_desc(self, sample_offset=0, rows=None, shard=None, spp=None) -> RenderDescC:
         d = self.desc
         r = RenderDescC()

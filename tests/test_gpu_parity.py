@@ -236,6 +236,37 @@ def test_shard_sum_equals_full(gpu):
     assert np.array_equal(acc, full)
 
 
+def test_sample_range_shards_sum_to_the_image(gpu):
+    """SURVEY.md 8e, the alternative to tiles: every rank renders all pixels and a share of the samples; the partial images
+    (each equal to the oracle's partial) sum to the single-GPU image up to the order of the float additions, also across
+    progressive calls and with an empty sample range (5 ranks, 4 samples)."""
+    d = _lit_cornell(72, 56, spp=4)
+    b = gpu.BuiltScene(d)
+    try:
+        full = [b.render().copy(), b.render().copy()]
+        o = orc.OracleScene(d)
+        for world in (3, 5):
+            acc = [np.zeros_like(full[0]), np.zeros_like(full[0])]
+            for rank in range(world):
+                gpu.set_shard(b.scene, rank, world, gpu.SHARD_SAMPLES)
+                one = b.render().copy()
+                two = b.render().copy()
+                o1, _, _ = o.render(shard=(rank, world, o.SHARD_SAMPLES))
+                o2, _, _ = o.render(sample_offset=4, prev=o1, shard=(rank, world, o.SHARD_SAMPLES))
+                for part, want in ((one, o1), (two, o2)):
+                    rmse, within = image_metrics(part, want)
+                    assert rmse < 1e-3 and within >= 0.999
+                    assert np.all(part[..., 3] == (1.0 if rank == 0 else 0.0))
+                acc[0] += one; acc[1] += two
+            for a, f in zip(acc, full):
+                assert np.all(a[..., 3] == 1.0)
+                assert np.allclose(a[..., :3], f[..., :3], rtol=2e-6, atol=1e-7)
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(b.render(), full[0])
+    finally:
+        b.close()
+
+
 @pytest.mark.logs_errors
 def test_errors_are_loud(gpu):
     d = scenes.cornell(16, 16, spp=1)

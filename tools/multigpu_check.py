@@ -5,7 +5,9 @@
 
 Every rank renders its tiles of the same scene; gtlc_render ends with ncclReduce(sum) to rank 0 before the device->host
 copy.  Rank 0 then renders the whole frame alone and demands the two host images be BIT-IDENTICAL (x + 0 = x), for a
-single call and for two progressive calls.  torch.distributed (gloo) only carries the 128-byte NCCL id.
+single call and for two progressive calls; then the same with sample-range sharding (every pixel, a share of the samples),
+where the sum runs in another order and the images must agree to rounding.  torch.distributed (gloo) only carries the
+128-byte NCCL id.
 """
 import dataclasses
 import os
@@ -46,6 +48,18 @@ for tile in (16, 64):
         print("tile %d: sharded over %d GPUs == single GPU: %s (mean %.4f)" % (tile, world, same, lit), flush=True)
         ok = ok and same and lit > 0.05 and not np.array_equal(ref_one, ref_two)
     dist.barrier()
+gi.set_shard(b.scene, rank, world, gi.SHARD_SAMPLES)
+one = b.render().copy()
+two = b.render().copy()
+dist.barrier()
+if rank == 0:
+    gi.set_shard(b.scene, 0, 1, 64)
+    ref_one = b.render().copy()
+    ref_two = b.render().copy()
+    close = all(np.allclose(x[..., :3], y[..., :3], rtol=2e-6, atol=1e-7) and np.all(x[..., 3] == 1.0) for x, y in ((one, ref_one), (two, ref_two)))
+    print("sample ranges: sharded over %d GPUs ~= single GPU: %s (max abs diff %.3g)" % (world, close, float(np.abs(two - ref_two).max())), flush=True)
+    ok = ok and close
+dist.barrier()
 b.close()
 gi.comm_destroy()
 gi.giTerminate()
