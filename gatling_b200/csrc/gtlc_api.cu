@@ -1480,7 +1480,9 @@ int gtlc_render(const GtlcRenderParams* params)
         wp.waveSampleBase = sBase; wp.pixelMap = tileShard ? s->dPixelMap.ptr : nullptr;
         wp.firstWave = sBase == sBegin ? 1u : 0u; wp.alpha = (sampleShard && s->shardRank != 0) ? 0.0f : 1.0f;
         paths += (uint64_t) wp.wavePixels * wp.waveSamples;
-        timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, g.q[0], g.counters, aovBufs.clk); });
+        PathQueue q0 = g.q[0];
+        if (!volumes) { q0.med = nullptr; q0.walk = nullptr; }             // (the pool may exist from an earlier render with media)
+        timed(K_RAYGEN, [&] { raygen_kernel<<<gridElem, 256, 0, g.stream>>>(ubo, wp, q0, g.counters, aovBufs.clk); });
         int inIdx = 0;
         if (rs.maxBounces == 0) {
           // The bounce loop never runs (as in rgen:290 the payload's radiance stays 0): the finished-sample slots the

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(256) raygen_kernel(UniformData ubo, WaveParams
     q.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, u2f(0u));               // :274-275
     q.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, u2f(rng_state));        // :276-277
     q.slot[slot] = slot;
+    if (q.med) { q.med[slot] = make_uint4(0u, 0u, 0u, 0u); q.walk[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f); }   // :280-282 (MEDIUM_STACK_SIZE > 0)
     if (clk) clk[slot] = (float) ((uint32_t) clock() - clk0);            // the ClockCycles AOV starts counting here (rgen:187-189)
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { ctr->numPaths[0] = total; ctr->numPaths[1] = 0; ctr->numShadow = 0; ctr->workCounter = 0; ctr->workCounterShadow = 0; }

@@ -539,6 +539,7 @@ static inline V3 trace_sample(const RenderCtx& c, uint32_t px, uint32_t py, uint
   p.throughput = v3(1.0f); p.bitfield = 0; p.radiance = v3(0.0f); p.rng_state = rng_state;
   p.ray_origin = ray_origin; p.ray_dir = ray_dir; p.pixelIndex = pixelIndex;
   p.neeToLight = v3(0.0f); p.neeContrib = v3(0.0f);
+  p.walkSegmentPdf = v3(1.0f);                                            // :280-282
 
   float cosConeAngle = fmaxf(1e-5f, dot(ray_dir, ubo.cameraForward));     // :287
   V2 clipRange = unpackHalf2x16(ubo.clipRangePacked);
