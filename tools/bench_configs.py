@@ -18,6 +18,7 @@ ap.add_argument("--bvh-builder", type=int, default=0, help="0 host binned SAH, 1
 ap.add_argument("--trace-variant", type=int, default=0)
 ap.add_argument("--ups", action="store_true", help="replace the OpenPBR materials of c3/c5 by UsdPreviewSurface ones (same colours / roughness / metalness)")
 ap.add_argument("--tri-threshold", type=int, default=0)
+ap.add_argument("--refill-sweep", default="", help="comma list of refill thresholds (idle lanes at which a warp fetches new rays) measured after the normal lines, sort as in the last of them")
 a = ap.parse_args()
 assert gi.giInitialize(0) == gi.GiStatus.Ok, gi.giLastError()
 
@@ -66,5 +67,15 @@ for name in a.configs.split(","):
                           "shadow": best["shadowRays"], "ms_trace": best["msTraceClosest"], "ms_shadow": best["msTraceAny"], "ms_shade": best["msShade"],
                           "ms_sort": best["msSort"], "bvh_builder": a.bvh_builder, "trace_variant": a.trace_variant, "bvh_build_ms": best["msBvhBuild"], "bvh_device_build_ms": best["msBvhDeviceBuild"], "bvh_nodes": best["bvhNodeCount"], "depth": best["bvhMaxDepth"],
                           "scene_gen_s": round(t_gen, 2), "launches": best["kernelLaunches"], **visits}), flush=True)
+    for rf in [int(x) for x in a.refill_sweep.split(",") if x]:
+        gi.set_tuning(reserved=(C.c_int32 * 3)(rf, 0, a.tri_threshold))
+        best = None
+        for rep in range(3):
+            gi.set_shard(b.scene, 0, 1, 64)
+            b.render()
+            s = gi.get_stats()
+            if best is None or s["msTotal"] < best["msTotal"]:
+                best = s
+        print(json.dumps({"config": name, "refill": rf, "ms_total": best["msTotal"], "ms_trace": best["msTraceClosest"], "ms_shadow": best["msTraceAny"], "ms_shade": best["msShade"]}), flush=True)
     b.close()
 gi.giTerminate()
