@@ -30,7 +30,7 @@ class TextureBinding(C.Structure):
                 ("wrapV", C.c_int32), ("srgb", C.c_int32), ("texture", C.c_uint64), ("fallback", C.c_float * 4),
                 ("scale", C.c_float * 4), ("bias", C.c_float * 4), ("uvRotation", C.c_float), ("uvScale", C.c_float * 2),
                 ("uvTranslation", C.c_float * 2), ("lookup", C.c_int32), ("wrapW", C.c_int32), ("xyzScale", C.c_float * 3),
-                ("xyzOffset", C.c_float * 3), ("reserved", C.c_int32)]
+                ("xyzOffset", C.c_float * 3), ("combine", C.c_int32)]
 
 
 class MaterialDesc(C.Structure):

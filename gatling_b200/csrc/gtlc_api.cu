@@ -579,10 +579,10 @@ bool uploadMaterials(Scene* s)
       const GtlcTextureBinding& src = m->bindings[b];
       Texture* t = m->boundTextures[b];
       uint32_t ti = 0;
-      for (; ti < textureIndex.size(); ti++) if (textureIndex[ti] == t) break;
-      if (ti == textureIndex.size()) { textureIndex.push_back(t); textures.push_back({ t->dTexels, t->width, t->height, (uint32_t) t->format, t->depth }); }
+      for (; t && ti < textureIndex.size(); ti++) if (textureIndex[ti] == t) break;     // (t == NULL: a constant operand, no lookup)
+      if (t && ti == textureIndex.size()) { textureIndex.push_back(t); textures.push_back({ t->dTexels, t->width, t->height, (uint32_t) t->format, t->depth }); }
       DeviceTexBinding d; memset(&d, 0, sizeof(d));
-      d.paramIndex = src.paramIndex; d.texture = ti;
+      d.paramIndex = src.paramIndex; d.texture = ti; d.combine = (uint32_t) src.combine;
       d.packed = (uint32_t) src.componentCount | ((uint32_t) src.channels[0] << 4) | ((uint32_t) src.channels[1] << 6) | ((uint32_t) src.channels[2] << 8) |
                  ((uint32_t) src.wrapU << 10) | ((uint32_t) src.wrapV << 12) | ((src.srgb ? 1u : 0u) << 14) | ((uint32_t) src.lookup << 15) | (((uint32_t) src.wrapW & 3u) << 17);
       for (int k = 0; k < 3; k++) { d.xyzScale[k] = src.xyzScale[k]; d.xyzOffset[k] = src.xyzOffset[k]; }
@@ -965,15 +965,20 @@ GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
   std::vector<Texture*> bound;
   for (uint32_t b = 0; b < d->textureCount; b++) {
     const GtlcTextureBinding& tb = d->textures[b];
-    Texture* t = as<Texture>(tb.texture, TAG_TEXTURE);
-    if (!t) { setError("gtlc_material_create: binding %u has no valid texture", b); return 0; }
-    const bool okIndex = tb.paramIndex == GTLC_BIND_NORMAL || (tb.paramIndex >= 0 && tb.paramIndex + tb.componentCount <= GTLC_MATERIAL_PARAM_COUNT);
+    const int op = tb.combine & 15, factorParam = (tb.combine >> 8) & 255;
+    const bool constant = (tb.combine & GTLC_COMBINE_CONSTANT) != 0;
+    if (op > GTLC_COMBINE_MIX || (tb.combine & ~(0xFF1F)) != 0 || (op == GTLC_COMBINE_MIX && factorParam >= GTLC_MATERIAL_PARAM_COUNT + GTLC_BIND_SCRATCH_COUNT)) { setError("gtlc_material_create: binding %u has an invalid combine word 0x%x", b, (unsigned) tb.combine); return 0; }
+    if (tb.paramIndex == GTLC_BIND_NORMAL && tb.combine != 0) { setError("gtlc_material_create: binding %u: the normal takes one plain lookup (combine must be 0)", b); return 0; }
+    Texture* t = (constant && !tb.texture) ? nullptr : as<Texture>(tb.texture, TAG_TEXTURE);
+    if (!t && !constant) { setError("gtlc_material_create: binding %u has no valid texture", b); return 0; }
+    const bool okIndex = tb.paramIndex == GTLC_BIND_NORMAL || (tb.paramIndex >= 0 && tb.paramIndex + tb.componentCount <= GTLC_MATERIAL_PARAM_COUNT) ||
+                         (tb.paramIndex >= GTLC_BIND_SCRATCH && tb.paramIndex + tb.componentCount <= GTLC_BIND_SCRATCH + GTLC_BIND_SCRATCH_COUNT);   // inside the block or inside the scratch floats, not across
     if (!okIndex || tb.componentCount < 1 || tb.componentCount > 3 || (tb.paramIndex == GTLC_BIND_NORMAL && tb.componentCount != 3)) { setError("gtlc_material_create: binding %u writes outside the parameter block", b); return 0; }
     for (int k = 0; k < 3; k++) if (tb.channels[k] < 0 || tb.channels[k] > 3) { setError("gtlc_material_create: binding %u has an invalid channel", b); return 0; }
     if (tb.wrapU < GTLC_WRAP_CLAMP || tb.wrapU > GTLC_WRAP_CLIP || tb.wrapV < GTLC_WRAP_CLAMP || tb.wrapV > GTLC_WRAP_CLIP) { setError("gtlc_material_create: binding %u has an invalid wrap mode", b); return 0; }
     if (tb.lookup < GTLC_LOOKUP_FILTERED_2D || tb.lookup > GTLC_LOOKUP_TEXEL_3D) { setError("gtlc_material_create: binding %u has an invalid lookup mode %d", b, tb.lookup); return 0; }
     if (tb.lookup >= GTLC_LOOKUP_FILTERED_3D && (tb.wrapW < GTLC_WRAP_CLAMP || tb.wrapW > GTLC_WRAP_CLIP)) { setError("gtlc_material_create: binding %u has an invalid wrap mode", b); return 0; }
-    if (tb.lookup < GTLC_LOOKUP_FILTERED_3D && t->depth > 1u) { setError("gtlc_material_create: binding %u reads a 3-D texture with a 2-D lookup", b); return 0; }
+    if (t && tb.lookup < GTLC_LOOKUP_FILTERED_3D && t->depth > 1u) { setError("gtlc_material_create: binding %u reads a 3-D texture with a 2-D lookup", b); return 0; }
     bound.push_back(t);
   }
   Material* m = new Material(); m->tag = TAG_MATERIAL; m->scene = s; m->closure = d->closure; memcpy(m->params, d->params, sizeof(m->params));
@@ -985,6 +990,7 @@ GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
       const GtlcTextureBinding& tb = d->textures[b];
       if (tb.paramIndex >= 0 && tb.paramIndex <= opacityParam && opacityParam < tb.paramIndex + tb.componentCount) {
         if (tb.componentCount != 1) { setError("gtlc_material_create: binding %u writes the cutout input as part of a %d-component value; bind it on its own", b, tb.componentCount); delete m; return 0; }
+        if (tb.combine != 0 || m->opacityBinding >= 0) { setError("gtlc_material_create: binding %u: the cutout input takes ONE plain lookup (the any-hit test evaluates it at every candidate hit)", b); delete m; return 0; }
         m->opacityBinding = (int) b;
       }
     }
@@ -994,7 +1000,7 @@ GtlcHandle gtlc_material_create(GtlcHandle sh, const GtlcMaterialDesc* d)
   for (uint32_t b = 0; b < d->primvarCount; b++) { Material::PrimvarBinding pb; pb.paramIndex = d->primvars[b].paramIndex; pb.componentCount = d->primvars[b].componentCount; pb.name = d->primvars[b].name ? d->primvars[b].name : ""; memcpy(pb.fallback, d->primvars[b].fallback, 16); m->primvarBindings.push_back(pb); }
   {
     std::lock_guard<std::mutex> dl(g_destroyMutex);
-    for (Texture* t : bound) t->refs++;
+    for (Texture* t : bound) if (t) t->refs++;
   }
   m->boundTextures = bound;
   std::lock_guard<std::mutex> l(s->mutex);
@@ -1012,7 +1018,7 @@ void gtlc_material_destroy(GtlcHandle h)
     for (Mesh* mesh : s->meshes) if (mesh->material == m) mesh->material = nullptr;
     s->geometryDirty = true; s->framebufferDirty = true;
   }
-  for (Texture* t : m->boundTextures) releaseTexture(t);
+  for (Texture* t : m->boundTextures) if (t) releaseTexture(t);
   m->tag = 0; delete m;
 }
 

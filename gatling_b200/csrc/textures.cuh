@@ -20,7 +20,7 @@ struct DeviceTexBinding {
   int32_t paramIndex;
   uint32_t packed;          // componentCount | ch0 << 4 | ch1 << 6 | ch2 << 8 | wrapU << 10 | wrapV << 12 | srgb << 14 | lookup << 15 | wrapW << 17
   uint32_t texture;         // index into DeviceScene.textures
-  uint32_t pad;
+  uint32_t combine;         // GtlcTextureBinding.combine: op | constant << 4 | factorParam << 8
   float fallback[4], scale[4], bias[4];
   float uvCos, uvSin, uvScale[2], uvTranslation[2], pad2[2];
   float xyzScale[3], xyzOffset[3], pad3[2];   // 3-D lookups: coordinate = object-space position * scale + offset
@@ -175,6 +175,7 @@ GTLC_D V3 mdl_adapt_normal(V3 worldRayDir, V3 geomNormal, V3 normal)
 // ch[0..3] = the four source channels; the caller picks the ones the binding routes to its input.
 GTLC_D void eval_tex_binding(const DeviceTexBinding& tb, const DeviceTexture* __restrict__ textures, float stu, float stv, V3 localPos, float (&ch)[4])
 {
+  if (tb.combine & GTLC_COMBINE_CONSTANT) { ch[0] = tb.bias[0]; ch[1] = tb.bias[1]; ch[2] = tb.bias[2]; ch[3] = tb.bias[3]; return; }
   const DeviceTexture& t = textures[tb.texture];
   const int wrapU = (int) ((tb.packed >> 10) & 3u), wrapV = (int) ((tb.packed >> 12) & 3u), wrapW = (int) ((tb.packed >> 17) & 3u);
   const int lookup = (int) ((tb.packed >> 15) & 3u);

@@ -488,7 +488,15 @@ GTLC_D bool apply_texture_bindings(const DeviceScene& s, uint32_t material, V3 w
       mappedNormal = mdl_adapt_normal(worldRayDir, st.geom_normal, n);
       hasNormal = true;
     } else {
-      for (int k = 0; k < count && k < 3; k++) lp[tb.paramIndex + k] = val[k];
+      const uint32_t op = tb.combine & 15u;                                           // gtlc.h GtlcCombineOp
+      const float f = (op == GTLC_COMBINE_MIX) ? lp[(tb.combine >> 8) & 255u] : 0.0f;
+      for (int k = 0; k < count && k < 3; k++) {
+        float& x = lp[tb.paramIndex + k];
+        if (op == GTLC_COMBINE_SET) x = val[k];
+        else if (op == GTLC_COMBINE_MULTIPLY) x = x * val[k];
+        else if (op == GTLC_COMBINE_ADD) x = x + val[k];
+        else x = x * (1.0f - f) + val[k] * f;
+      }
     }
   }
   return hasNormal;
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC), shade_min_blocks(MAXC,
     V3 mappedNormal = v3(0.0f); uint32_t mediumIdx = 0, hitMaterial = 0;
     bool neeValid = false; V3 neeDir = v3(0.0f), neeRadiance = v3(0.0f); uint32_t neeDiffuseSpecular = 0;
     float memo0 = -1.0f, memo1 = -1.0f;                                                // BsdfSample.memo -> BsdfEval.memo
-    float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT : 1];                                     // textured inputs: private parameter block
+    float lp[TEX ? GTLC_MATERIAL_PARAM_COUNT + GTLC_BIND_SCRATCH_COUNT : 1];                                     // textured inputs: private parameter block
     uint32_t bounce = 0, loopMediumIdx = 0;                                            // rgen:298, :318 (read before the trace)
     uint32_t media[kMaxMediumStack] = { 0u, 0u, 0u, 0u };
     if (valid) {
@@ -621,6 +629,7 @@ __global__ void __launch_bounds__(shade_block_size(MAXC), shade_min_blocks(MAXC,
         mappedNormal = normal;
         if (TEX && (s.matTexRange[in.material].y | s.matPrimvarRange[in.material].y) != 0u) {
           for (int k = 0; k < GTLC_MATERIAL_PARAM_COUNT; k++) lp[k] = mp[k];
+          for (int k = 0; k < GTLC_BIND_SCRATCH_COUNT; k++) lp[GTLC_MATERIAL_PARAM_COUNT + k] = 0.0f;
           apply_primvar_bindings(s, in, inst, prim, h.y, h.z, st, lp);
           hasMappedNormal = apply_texture_bindings(s, in.material, worldRayDir, st, lp, mappedNormal);
           mp = lp; lowered = nullptr;                                                  // per-hit inputs: the closure evaluates its constants itself

@@ -119,6 +119,7 @@ def texture_binding_c(b: "S.TextureBinding", handle) -> "L.TextureBinding":
     c.lookup, c.wrapW = b.lookup, b.wrap_w
     c.xyzScale = (C.c_float * 3)(*b.xyz_scale)
     c.xyzOffset = (C.c_float * 3)(*b.xyz_offset)
+    c.combine = b.combine
     return c
 
 
@@ -131,7 +132,7 @@ def giCreateMaterial(scene, closure: int, params: Sequence[float], name: str = "
     arr[:len(params)] = params
     d.params = (C.c_float * 48)(*[float(x) for x in arr])
     if textures:
-        arr_b = (L.TextureBinding * len(textures))(*[texture_binding_c(b, texture_handles[b.texture]) for b in textures])
+        arr_b = (L.TextureBinding * len(textures))(*[texture_binding_c(b, texture_handles[b.texture] if b.texture >= 0 else 0) for b in textures])
         d.textures = arr_b
         d.textureCount = len(textures)
     if primvars:

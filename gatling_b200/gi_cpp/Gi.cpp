@@ -144,36 +144,41 @@ namespace gtl
       return GTLC_WRAP_REPEAT;     // "repeat" / "periodic" / "useMetadata" (ND_UsdUVTexture default: periodic)
     }
 
-    // Follows a connected surface-shader input to a texture node.  Returns false if the upstream graph is not
-    // (arithmetic with constants ->) (normalmap ->) UsdUVTexture | image (-> UsdTransform2d -> st reader).
-    // "Arithmetic with constants": multiply / add / subtract / divide / invert nodes whose other operand is a value -- what
+    // ---- lowering of the graph in front of a surface-shader input ----
+    // Supported: (arithmetic with constants ->) (normalmap ->) UsdUVTexture | image (-> UsdTransform2d -> st reader), and ONE
+    // multiply / add / subtract of two such chains or ONE mix of them (constant or image operands, constant or image mask) on the
+    // way.  "Arithmetic with constants": multiply / add / subtract / divide / invert nodes whose other operand is a value -- what
     // authoring tools put between an image and a shader input to tint, scale or invert it.  They compose to one affine map per
-    // component, which folds into the binding's per-channel scale / bias (UsdUVTexture semantics: value = texel * scale + bias,
-    // after the colour-space transform, as in the graph).  Anything that is not affine in ONE lookup (texture x texture, mix,
-    // noise, ...) is not lowered: the input keeps its constant and the caller warns.
-    bool lowerTextureInput(const std::string& xml, const XmlInput& in, int paramIndex, int count, bool upsSrgbInput,
-                           GtlcTextureBinding& b, std::string& file)
+    // component, which folds into a binding's per-channel scale / bias (UsdUVTexture semantics: value = texel * scale + bias,
+    // after the colour-space transform, as in the graph).  Two lookups meet through the combine word of the bindings
+    // (gtlc.h GtlcCombineOp), which the library applies in order; a mask image waits in a scratch float.  Anything else
+    // (noise, nested mixes, ...) is not lowered: the input keeps its constant and the caller warns.  (The reference compiles
+    // the whole graph to MDL: mc/impl/MtlxMdlCodeGen.cpp:189-278.)
+    int parseConstant3(const XmlInput* in, float dflt, float k[3])
     {
-      std::string category; std::vector<XmlInput> node;
-      if (in.nodename.empty() || !findNodeByName(xml, in.nodename, category, node)) return false;
-      memset(&b, 0, sizeof(b));
-      for (int k = 0; k < 4; k++) { b.scale[k] = 1.0f; b.bias[k] = 0.0f; }
-      b.fallback[3] = 1.0f; b.uvScale[0] = b.uvScale[1] = 1.0f;
-      b.paramIndex = paramIndex; b.componentCount = count;
-      std::string output = in.output;
-      float mulK[3] = { 1.0f, 1.0f, 1.0f }, addK[3] = { 0.0f, 0.0f, 0.0f };    // input = node output * mulK + addK, per component
+      k[0] = k[1] = k[2] = dflt;
+      if (!in || in->value.empty()) return 0;
+      float v[4]; const int n = parseFloats(in->value, v, 4);
+      if (n == 1) k[0] = k[1] = k[2] = v[0]; else for (int q = 0; q < n && q < 3; q++) k[q] = v[q];
+      return n;
+    }
+    bool isConnected(const XmlInput* in) { return in && !in->nodename.empty(); }
+
+    // Walks the constant-arithmetic nodes starting at (category, node), composing input = upstream * mulK + addK.  Stops at the
+    // first node of another kind, or at a multiply / add / subtract whose operands are BOTH connected (`binary`).
+    bool walkConstantArithmetic(const std::string& xml, std::string& category, std::vector<XmlInput>& node, std::string& output, float mulK[3], float addK[3], bool& binary)
+    {
+      binary = false;
       for (int hops = 0; hops < 16; hops++) {
         const bool isMul = category == "multiply", isAdd = category == "add", isSub = category == "subtract", isDiv = category == "divide", isInv = category == "invert";
-        if (!isMul && !isAdd && !isSub && !isDiv && !isInv) break;
+        if (!isMul && !isAdd && !isSub && !isDiv && !isInv) return true;
         const XmlInput* a = findInput(node, isInv ? "in" : "in1");
         const XmlInput* c = findInput(node, isInv ? "amount" : "in2");
-        const bool aConn = a && !a->nodename.empty(), cConn = c && !c->nodename.empty();
-        if (aConn == cConn) return false;                                          // both connected (not affine in one lookup) or none
+        const bool aConn = isConnected(a), cConn = isConnected(c);
+        if (aConn && cConn) { binary = isMul || isAdd || isSub; return binary; }
+        if (!aConn && !cConn) return false;
         const XmlInput* conn = aConn ? a : c;
-        const XmlInput* konst = aConn ? c : a;
-        float k[3]; const float dflt = (isMul || isDiv || isInv) ? 1.0f : 0.0f;
-        k[0] = k[1] = k[2] = dflt;
-        if (konst && !konst->value.empty()) { float v3[4]; const int n = parseFloats(konst->value, v3, 4); if (n == 1) k[0] = k[1] = k[2] = v3[0]; else for (int q = 0; q < n && q < 3; q++) k[q] = v3[q]; }
+        float k[3]; parseConstant3(aConn ? c : a, (isMul || isDiv || isInv) ? 1.0f : 0.0f, k);
         for (int q = 0; q < 3; q++) {
           if (isMul) mulK[q] *= k[q];
           else if (isAdd) addK[q] += k[q] * mulK[q];
@@ -189,6 +194,28 @@ namespace gtl
         const std::string up = conn->nodename;
         if (!findNodeByName(xml, up, category, node)) return false;
       }
+      return false;
+    }
+
+    void initBinding(GtlcTextureBinding& b, int paramIndex, int count, int combine)
+    {
+      memset(&b, 0, sizeof(b));
+      for (int k = 0; k < 4; k++) { b.scale[k] = 1.0f; b.bias[k] = 0.0f; }
+      b.fallback[3] = 1.0f; b.uvScale[0] = b.uvScale[1] = 1.0f;
+      b.paramIndex = paramIndex; b.componentCount = count; b.combine = combine;
+    }
+
+    // One lookup chain: the node `nodename` (output `output`) must lead through constant arithmetic (and a normalmap) to an image.
+    // value written = chain value * mulK0 + addK0, combined with the input's current value as `combine` says.
+    bool lowerLookupChain(const std::string& xml, const std::string& nodename, std::string output, int paramIndex, int count, bool upsSrgbInput,
+                          const float mulK0[3], const float addK0[3], int combine, GtlcTextureBinding& b, std::string& file)
+    {
+      std::string category; std::vector<XmlInput> node;
+      if (nodename.empty() || !findNodeByName(xml, nodename, category, node)) return false;
+      initBinding(b, paramIndex, count, combine);
+      float mulK[3] = { mulK0[0], mulK0[1], mulK0[2] }, addK[3] = { addK0[0], addK0[1], addK0[2] };
+      bool binary = false;
+      if (!walkConstantArithmetic(xml, category, node, output, mulK, addK, binary) || binary) return false;
       bool decodeNormal = false;
       if (category == "normalmap") {                       // MaterialX normalmap decodes value * 2 - 1 itself
         const XmlInput* src = findInput(node, "in");
@@ -249,8 +276,74 @@ namespace gtl
       return true;
     }
 
+    // The bindings (and their image files; "" for a constant operand) that compute one shader input.  `scratchUsed` counts the
+    // scratch floats this material's masks occupy so far.
+    bool lowerTextureInput(const std::string& xml, const XmlInput& in, int paramIndex, int count, bool upsSrgbInput,
+                           std::vector<GtlcTextureBinding>& bs, std::vector<std::string>& files, int& scratchUsed)
+    {
+      const float one[3] = { 1.0f, 1.0f, 1.0f }, zero[3] = { 0.0f, 0.0f, 0.0f };
+      bs.clear(); files.clear();
+      GtlcTextureBinding b; std::string file;
+      if (lowerLookupChain(xml, in.nodename, in.output, paramIndex, count, upsSrgbInput, one, zero, GTLC_COMBINE_SET, b, file)) { bs.push_back(b); files.push_back(file); return true; }
+      if (paramIndex == GTLC_BIND_NORMAL) return false;                              // the normal takes one plain lookup
+      std::string category, output = in.output; std::vector<XmlInput> node;
+      if (in.nodename.empty() || !findNodeByName(xml, in.nodename, category, node)) return false;
+      float mulK[3] = { 1.0f, 1.0f, 1.0f }, addK[3] = { 0.0f, 0.0f, 0.0f };
+      bool binary = false;
+      if (!walkConstantArithmetic(xml, category, node, output, mulK, addK, binary)) return false;
+      auto chain = [&](const XmlInput* operand, int param, int n, const float* mk, const float* ak, int combine) {
+        GtlcTextureBinding cb; std::string cf;
+        if (!lowerLookupChain(xml, operand->nodename, operand->output, param, n, upsSrgbInput, mk, ak, combine, cb, cf)) return false;
+        bs.push_back(cb); files.push_back(cf); return true;
+      };
+      auto constant = [&](const float k[3], int combine) {
+        GtlcTextureBinding cb; initBinding(cb, paramIndex, count, combine | GTLC_COMBINE_CONSTANT);
+        cb.channels[0] = 0; cb.channels[1] = 1; cb.channels[2] = 2;
+        for (int q = 0; q < 3; q++) cb.bias[q] = k[q];
+        bs.push_back(cb); files.push_back("");
+      };
+      if (binary) {
+        const XmlInput* a = findInput(node, "in1");
+        const XmlInput* c = findInput(node, "in2");
+        if (category == "multiply") {                                               // (a * c) * mulK + addK
+          if (!chain(a, paramIndex, count, mulK, zero, GTLC_COMBINE_SET) || !chain(c, paramIndex, count, one, zero, GTLC_COMBINE(GTLC_COMBINE_MULTIPLY, 0))) return false;
+          if (addK[0] != 0.0f || addK[1] != 0.0f || addK[2] != 0.0f) constant(addK, GTLC_COMBINE(GTLC_COMBINE_ADD, 0));
+          return true;
+        }
+        float neg[3] = { -mulK[0], -mulK[1], -mulK[2] };                             // add: a mulK + addK + c mulK; subtract: ... - c mulK
+        return chain(a, paramIndex, count, mulK, addK, GTLC_COMBINE_SET) && chain(c, paramIndex, count, category == "add" ? mulK : neg, zero, GTLC_COMBINE(GTLC_COMBINE_ADD, 0));
+      }
+      if (category != "mix") return false;
+      const XmlInput* bg = findInput(node, "bg");
+      const XmlInput* fg = findInput(node, "fg");
+      const XmlInput* mx = findInput(node, "mix");
+      float bgK[3], fgK[3], mK[3];
+      parseConstant3(bg, 0.0f, bgK); parseConstant3(fg, 0.0f, fgK); parseConstant3(mx, 0.0f, mK);
+      const bool bgConn = isConnected(bg), fgConn = isConnected(fg);
+      if (!bgConn && !fgConn && !isConnected(mx)) return false;
+      if (!isConnected(mx)) {                                                       // constant mask m: bg (1 - m) + fg m is affine in the two lookups
+        float wb[3], wf[3], add[3];
+        for (int q = 0; q < 3; q++) {
+          wb[q] = (1.0f - mK[q]) * mulK[q]; wf[q] = mK[q] * mulK[q];
+          add[q] = addK[q] + (bgConn ? 0.0f : bgK[q] * wb[q]) + (fgConn ? 0.0f : fgK[q] * wf[q]);
+        }
+        if (bgConn && fgConn) return chain(bg, paramIndex, count, wb, add, GTLC_COMBINE_SET) && chain(fg, paramIndex, count, wf, zero, GTLC_COMBINE(GTLC_COMBINE_ADD, 0));
+        return bgConn ? chain(bg, paramIndex, count, wb, add, GTLC_COMBINE_SET) : chain(fg, paramIndex, count, wf, add, GTLC_COMBINE_SET);
+      }
+      // an image mask: it waits in a scratch float while bg is written, then fg is mixed in (math::lerp)
+      for (int q = 0; q < 3; q++) if (mulK[q] != 1.0f || addK[q] != 0.0f) return false;
+      if (scratchUsed >= GTLC_BIND_SCRATCH_COUNT) return false;
+      const int slot = GTLC_BIND_SCRATCH + scratchUsed;
+      if (!chain(mx, slot, 1, one, zero, GTLC_COMBINE_SET)) return false;
+      if (bgConn) { if (!chain(bg, paramIndex, count, one, zero, GTLC_COMBINE_SET)) return false; } else constant(bgK, GTLC_COMBINE_SET);
+      if (fgConn) { if (!chain(fg, paramIndex, count, one, zero, GTLC_COMBINE(GTLC_COMBINE_MIX, slot))) return false; } else constant(fgK, GTLC_COMBINE(GTLC_COMBINE_MIX, slot));
+      scratchUsed++;
+      return true;
+    }
+
     struct LoweredPrimvar { int paramIndex, componentCount; std::string name; float fallback[4]; };
-    struct LoweredTextures { std::vector<GtlcTextureBinding> bindings; std::vector<std::string> files; std::vector<LoweredPrimvar> primvars; };
+    // bindings[i] reads files[i] ("" = a constant operand); groups[i] = the shader input it helps to compute (bindings of one input stand or fall together)
+    struct LoweredTextures { std::vector<GtlcTextureBinding> bindings; std::vector<std::string> files; std::vector<int> groups; std::vector<LoweredPrimvar> primvars; int scratchUsed = 0, groupCount = 0; };
 
     // A surface-shader input fed by UsdPrimvarReader / geompropvalue / geomcolor: the MDL backend turns these into
     // scene_data_lookup_* calls (mdl_interface.glsl:266-479) on the named primvar.
@@ -296,10 +389,13 @@ namespace gtl
         const bool isNormal = in.name == normalInput;
         if (!slot && !isNormal) continue;   // inputs the closures do not model (displacement, occlusion, ...)
         if (in.connected) {
-          GtlcTextureBinding b; std::string file;
+          std::vector<GtlcTextureBinding> bs; std::vector<std::string> files;
           const bool srgbInput = ups && (in.name == "diffuseColor" || in.name == "emissiveColor" || in.name == "specularColor");
           LoweredPrimvar pv;
-          if (tex && lowerTextureInput(xml, in, isNormal ? GTLC_BIND_NORMAL : slot->index, isNormal ? 3 : slot->count, srgbInput, b, file)) { tex->bindings.push_back(b); tex->files.push_back(file); }
+          if (tex && lowerTextureInput(xml, in, isNormal ? GTLC_BIND_NORMAL : slot->index, isNormal ? 3 : slot->count, srgbInput, bs, files, tex->scratchUsed)) {
+            for (size_t k = 0; k < bs.size(); k++) { tex->bindings.push_back(bs[k]); tex->files.push_back(files[k]); tex->groups.push_back(tex->groupCount); }
+            tex->groupCount++;
+          }
           else if (tex && !isNormal && tex->primvars.size() < GTLC_MAX_PRIMVAR_BINDINGS && lowerPrimvarInput(xml, in, slot->index, slot->count, pv)) tex->primvars.push_back(pv);
           else fprintf(stderr, "[gi] warning: material '%s': input '%s' is connected to a graph this build cannot lower; using the default value\n", matName ? matName : "", in.name.c_str());
           continue;
@@ -415,12 +511,16 @@ namespace gtl
     if (!lowerMaterial(mtlxSrc, name, &d, &t)) { logError(std::string("material '") + (name ? name : "") + "': no UsdPreviewSurface / open_pbr_surface node found (other MaterialX shading models need the mc/MDL path, out of scope)"); return nullptr; }
     // images: a file that cannot be decoded drops its binding (the input keeps its constant), like the reference's
     // 1x1 black fallback image keeps rendering going (TextureManager.cpp:245-262)
+    // (an input computed from several lookups loses all of its bindings when one of its images is missing)
     std::vector<GtlcTextureBinding> bound; std::vector<GtlcHandle> textures;
+    std::vector<char> groupFailed((size_t) t.groupCount, 0);
     for (size_t i = 0; i < t.bindings.size(); i++) {
+      if (t.files[i].empty()) continue;                                             // a constant operand
       GtlcHandle h = loadTextureFile(t.files[i].c_str());
-      if (!h) { fprintf(stderr, "[gi] warning: material '%s': failed to read image %s (this build decodes binary .ppm / .pfm; imgio is out of scope)\n", name ? name : "", t.files[i].c_str()); continue; }
-      t.bindings[i].texture = h; bound.push_back(t.bindings[i]); textures.push_back(h);
+      if (!h) { fprintf(stderr, "[gi] warning: material '%s': failed to read image %s (this build decodes binary .ppm / .pfm; imgio is out of scope)\n", name ? name : "", t.files[i].c_str()); groupFailed[(size_t) t.groups[i]] = 1; continue; }
+      t.bindings[i].texture = h; textures.push_back(h);
     }
+    for (size_t i = 0; i < t.bindings.size(); i++) if (!groupFailed[(size_t) t.groups[i]]) bound.push_back(t.bindings[i]);
     d.textures = bound.empty() ? nullptr : bound.data(); d.textureCount = (uint32_t) bound.size();
     std::vector<GtlcPrimvarBinding> pvs(t.primvars.size());
     for (size_t i = 0; i < pvs.size(); i++) { pvs[i].paramIndex = t.primvars[i].paramIndex; pvs[i].componentCount = t.primvars[i].componentCount; pvs[i].name = t.primvars[i].name.c_str(); memcpy(pvs[i].fallback, t.primvars[i].fallback, 16); }

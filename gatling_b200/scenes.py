@@ -64,12 +64,19 @@ class Texture:
 WRAP_CLAMP, WRAP_REPEAT, WRAP_MIRRORED_REPEAT, WRAP_CLIP = 0, 1, 2, 3
 LOOKUP_FILTERED_2D, LOOKUP_TEXEL_2D, LOOKUP_FILTERED_3D, LOOKUP_TEXEL_3D = 0, 1, 2, 3    # GtlcTextureLookup
 BIND_NORMAL = -1
+BIND_SCRATCH, BIND_SCRATCH_COUNT = MATERIAL_PARAM_COUNT, 4                               # scratch floats behind the parameter block
+COMBINE_SET, COMBINE_MULTIPLY, COMBINE_ADD, COMBINE_MIX, COMBINE_CONSTANT = 0, 1, 2, 3, 0x10   # GtlcCombineOp
+
+
+def combine(op, factor_param=0, constant=False) -> int:
+    """GTLC_COMBINE(op, factorParam) [| GTLC_COMBINE_CONSTANT]"""
+    return int(op) | (int(factor_param) << 8) | (COMBINE_CONSTANT if constant else 0)
 
 
 @dataclasses.dataclass
 class TextureBinding:   # GtlcTextureBinding: UsdUVTexture (+ UsdTransform2d) feeding one material input
     param: int                      # first index of the parameter block, or BIND_NORMAL
-    texture: int                    # index into SceneDesc.textures
+    texture: int                    # index into SceneDesc.textures (-1 with a constant operand)
     channels: tuple = (0, 1, 2)     # one entry per written float
     wrap_u: int = WRAP_REPEAT
     wrap_v: int = WRAP_REPEAT
@@ -84,6 +91,7 @@ class TextureBinding:   # GtlcTextureBinding: UsdUVTexture (+ UsdTransform2d) fe
     wrap_w: int = WRAP_REPEAT
     xyz_scale: tuple = (1.0, 1.0, 1.0)      # 3-D lookups: coordinate = object-space position * scale + offset
     xyz_offset: tuple = (0.0, 0.0, 0.0)
+    combine: int = 0                # combine(op, factor_param, constant): how the value meets what the input already holds (gtlc.h)
 
 
 INTERP_CONSTANT, INTERP_INSTANCE, INTERP_UNIFORM, INTERP_VERTEX = 0, 1, 2, 3
@@ -604,6 +612,73 @@ def lookup_cornell(width=96, height=96, spp=8, max_bounces=5) -> SceneDesc:
                 d.meshes[i] = m
     d.materials = mats
     d.name = "lookup_cornell"
+    d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
+    d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
+    return d
+
+
+def layered_cornell(width=96, height=96, spp=8, max_bounces=5, baked=False) -> SceneDesc:
+    """Cornell box whose inputs are built from SEVERAL lookups by the combine word of the bindings (gtlc.h GtlcCombineOp): image x image
+    (floor), mix(image, constant, mask image) through a scratch float (back wall), image + image (left wall), mix(image, image, mask)
+    plus a product roughness on an OpenPBR box, and a constant SET followed by a multiply (right wall).  All lookups are texel fetches
+    of float images, so the same scene can be expressed with ONE pre-combined image per input: `baked=True` builds that form (same
+    float32 operations in numpy), and the two must render bit-identically."""
+    d = cornell(width, height, spp, max_bounces)
+    for m in d.meshes:
+        assign_planar_uv(m)
+    size = 16
+    f32 = np.float32
+    A = pcg32_uniform(11, size * size * 4).reshape(size, size, 4).astype(f32)
+    B = pcg32_uniform(12, size * size * 4).reshape(size, size, 4).astype(f32)
+    y, x = np.mgrid[0:size, 0:size]
+    M = (0.5 + 0.5 * np.sin(x * 0.8) * np.cos(y * 0.6)).astype(f32)                        # soft mask in [0, 1]
+    K = np.array([0.9, 0.15, 0.1], f32)
+    tint = np.array([0.6, 0.8, 1.0], f32)
+    one = f32(1.0)
+    T = TextureBinding
+    tx = dict(lookup=LOOKUP_TEXEL_2D, wrap_u=WRAP_REPEAT, wrap_v=WRAP_REPEAT, uv_scale=(0.7, 0.7), uv_translation=(0.15, 0.15))
+    S0, S1 = BIND_SCRATCH, BIND_SCRATCH + 1
+    Mc = M[..., None]
+    if not baked:
+        d.textures = [Texture(A), Texture(B), Texture(M[..., None].copy())]
+        floor_t = [T(UPS["diffuse"], 0, (0, 1, 2), **tx), T(UPS["diffuse"], 1, (0, 1, 2), combine=combine(COMBINE_MULTIPLY), **tx)]
+        back_t = [T(S0, 2, (0,), **tx), T(UPS["diffuse"], 0, (2, 1, 0), **tx),
+                  T(UPS["diffuse"], -1, (0, 1, 2), bias=(float(K[0]), float(K[1]), float(K[2]), 0.0), combine=combine(COMBINE_MIX, S0, constant=True))]
+        left_t = [T(UPS["diffuse"], 0, (0, 1, 2), scale=(0.5, 0.5, 0.5, 1.0), **tx), T(UPS["diffuse"], 1, (1, 2, 0), scale=(0.5, 0.5, 0.5, 1.0), combine=combine(COMBINE_ADD), **tx)]
+        tall_t = [T(S1, 2, (0,), **tx), T(OPBR["base_color"], 0, (0, 1, 2), **tx), T(OPBR["base_color"], 1, (0, 1, 2), combine=combine(COMBINE_MIX, S1), **tx),
+                  T(OPBR["specular_roughness"], 0, (3,), **tx), T(OPBR["specular_roughness"], 1, (3,), combine=combine(COMBINE_MULTIPLY), **tx)]
+        right_t = [T(UPS["diffuse"], -1, (0, 1, 2), bias=(float(tint[0]), float(tint[1]), float(tint[2]), 0.0), combine=combine(COMBINE_SET, constant=True)),
+                   T(UPS["diffuse"], 1, (0, 0, 0), combine=combine(COMBINE_MULTIPLY), **tx)]
+    else:
+        rgb = lambda img: np.concatenate([img, np.ones((size, size, 1), f32)], -1).astype(f32)
+        floor_i = A[..., :3] * B[..., :3]
+        back_i = A[..., [2, 1, 0]] * (one - Mc) + K[None, None, :] * Mc
+        left_i = A[..., :3] * f32(0.5) + B[..., [1, 2, 0]] * f32(0.5)
+        tall_i = A[..., :3] * (one - Mc) + B[..., :3] * Mc
+        rough_i = (A[..., 3] * B[..., 3])[..., None]
+        right_i = tint[None, None, :] * B[..., [0, 0, 0]]
+        d.textures = [Texture(rgb(floor_i)), Texture(rgb(back_i)), Texture(rgb(left_i)), Texture(rgb(tall_i)), Texture(rough_i.astype(f32).copy()), Texture(rgb(right_i))]
+        floor_t = [T(UPS["diffuse"], 0, (0, 1, 2), **tx)]
+        back_t = [T(UPS["diffuse"], 1, (0, 1, 2), **tx)]
+        left_t = [T(UPS["diffuse"], 2, (0, 1, 2), **tx)]
+        tall_t = [T(OPBR["base_color"], 3, (0, 1, 2), **tx), T(OPBR["specular_roughness"], 4, (0,), **tx)]
+        right_t = [T(UPS["diffuse"], 5, (0, 1, 2), **tx)]
+    floor = material_usd_preview_surface("FloorProduct", diffuse=(0.5, 0.5, 0.5)); floor.textures = floor_t
+    back = material_usd_preview_surface("BackMixConstant", diffuse=(0.5, 0.5, 0.5)); back.textures = back_t
+    left = material_usd_preview_surface("LeftSum", diffuse=(0.5, 0.5, 0.5)); left.textures = left_t
+    tall = material_openpbr("TallMixImages", base_color=(0.8, 0.8, 0.8), specular_roughness=0.4, base_metalness=0.3); tall.textures = tall_t
+    right = material_usd_preview_surface("RightConstantTimesImage", diffuse=(0.5, 0.5, 0.5)); right.textures = right_t
+    mats = list(d.materials)
+    base = len(mats)
+    mats += [floor, back, left, tall, right]
+    assign = {"bottomplane": 0, "backplane": 1, "leftplane": 2, "box1": 3, "rightplane": 4}
+    for i, m in enumerate(d.meshes):
+        lname = m.name.lower()
+        for key, k in assign.items():
+            if key in lname:
+                d.meshes[i] = dataclasses.replace(m, material=base + k)
+    d.materials = mats
+    d.name = "layered_cornell" + ("_baked" if baked else "")
     d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
     d.rect_lights.append(RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
     return d

@@ -246,8 +246,28 @@ typedef struct GtlcTextureBinding {
   int32_t    lookup;             /* GtlcTextureLookup (0 = filtered 2-D, the MaterialX image node) */
   int32_t    wrapW;              /* 3-D lookups: GtlcTextureWrap along the third axis */
   float      xyzScale[3], xyzOffset[3];      /* 3-D lookups: texture coordinate = object-space position * scale + offset */
-  int32_t    reserved;
+  int32_t    combine;            /* 0 = the value overwrites the input; otherwise GTLC_COMBINE(op, factorParam) [| GTLC_COMBINE_CONSTANT] */
 } GtlcTextureBinding;
+/* Bindings are applied in order, so several of them can build one input from several lookups -- what a MaterialX graph with
+ * `multiply` / `add` / `mix` nodes between images and a surface-shader input compiles to in the reference (mc generates MDL
+ * for the whole graph).  With x = the input's current value (the material's constant, or what earlier bindings left) and
+ * v = this binding's value:
+ *   GTLC_COMBINE_SET       x = v
+ *   GTLC_COMBINE_MULTIPLY  x = x * v
+ *   GTLC_COMBINE_ADD       x = x + v
+ *   GTLC_COMBINE_MIX       x = x * (1 - f) + v * f     (MDL math::lerp), f = the float at params[factorParam]
+ * GTLC_COMBINE_CONSTANT: v = bias, no lookup (`texture` may be 0) -- a constant operand of mix.
+ * paramIndex and factorParam may also name one of GTLC_BIND_SCRATCH_COUNT scratch floats behind the parameter block
+ * (GTLC_BIND_SCRATCH + k; 0 at every hit before the first binding runs), e.g. a mask:
+ *   { paramIndex = GTLC_BIND_SCRATCH, ... mask image, r }                                   scratch0 = mask
+ *   { paramIndex = BASE_COLOR, ... image A }                                                base = A
+ *   { paramIndex = BASE_COLOR, ... image B, combine = GTLC_COMBINE(GTLC_COMBINE_MIX, GTLC_BIND_SCRATCH) }   base = mix(A, B, mask)
+ * The normal binding and the cutout input take GTLC_COMBINE_SET only (the any-hit test evaluates ONE lookup). */
+enum GtlcCombineOp { GTLC_COMBINE_SET = 0, GTLC_COMBINE_MULTIPLY = 1, GTLC_COMBINE_ADD = 2, GTLC_COMBINE_MIX = 3 };
+#define GTLC_COMBINE_CONSTANT 0x10
+#define GTLC_COMBINE(op, factorParam) ((int32_t) (op) | ((int32_t) (factorParam) << 8))
+#define GTLC_BIND_SCRATCH GTLC_MATERIAL_PARAM_COUNT
+#define GTLC_BIND_SCRATCH_COUNT 4
 /* A binding whose paramIndex is the closure's cutout input (GTLC_UPS_OPACITY / GTLC_OPBR_GEOMETRY_OPACITY) makes the
  * cutout per hit: the traversal kernels evaluate it in their any-hit test from the candidate hit's barycentrics, as
  * rp_main.ahit:35-61 evaluates mdl_cutout_opacity on a full shading state. */

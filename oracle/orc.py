@@ -32,7 +32,7 @@ class TextureBinding(C.Structure):  # GtlcTextureBinding
                 ("wrapV", C.c_int32), ("srgb", C.c_int32), ("texture", C.c_uint64), ("fallback", C.c_float * 4),
                 ("scale", C.c_float * 4), ("bias", C.c_float * 4), ("uvRotation", C.c_float), ("uvScale", C.c_float * 2),
                 ("uvTranslation", C.c_float * 2), ("lookup", C.c_int32), ("wrapW", C.c_int32), ("xyzScale", C.c_float * 3),
-                ("xyzOffset", C.c_float * 3), ("reserved", C.c_int32)]
+                ("xyzOffset", C.c_float * 3), ("combine", C.c_int32)]
 
 
 class PrimvarBinding(C.Structure):  # GtlcPrimvarBinding
@@ -281,6 +281,7 @@ class OracleScene:
                     arr[k].lookup, arr[k].wrapW = b.lookup, b.wrap_w
                     arr[k].xyzScale = (C.c_float * 3)(*b.xyz_scale)
                     arr[k].xyzOffset = (C.c_float * 3)(*b.xyz_offset)
+                    arr[k].combine = b.combine
                 self._keep.append(arr)
                 self.mats[i].textures = arr
                 self.mats[i].textureCount = len(m.textures)

@@ -132,6 +132,7 @@ static inline V3 mdl_adapt_normal(V3 worldRayDir, V3 geomNormal, V3 normal)
 static inline void eval_binding(const std::vector<Texture>& textures, const GtlcTextureBinding& b, float u0, float v0, V3 localPos, float ch[4])
 {
   const double PI_D = 3.14159265358979323846;
+  if (b.combine & GTLC_COMBINE_CONSTANT) { for (int k = 0; k < 4; k++) ch[k] = b.bias[k]; return; }   // a constant operand: no lookup
   const Texture& tex = textures[(size_t) b.texture - 1];
   bool clipped = false;
   V4 t;
@@ -163,6 +164,8 @@ static inline bool apply_texture_bindings(const std::vector<Texture>& textures, 
                                           float* params, V3& mappedNormal)
 {
   bool hasNormal = false;
+  float scratch[GTLC_BIND_SCRATCH_COUNT] = { 0.0f, 0.0f, 0.0f, 0.0f };
+  auto slot = [&](int i) -> float& { return i < GTLC_MATERIAL_PARAM_COUNT ? params[i] : scratch[i - GTLC_MATERIAL_PARAM_COUNT]; };
   for (const GtlcTextureBinding& b : bindings) {
     float ch[4];
     eval_binding(textures, b, u0, v0, localPos, ch);
@@ -172,8 +175,16 @@ static inline bool apply_texture_bindings(const std::vector<Texture>& textures, 
       V3 n = normalize((tangentU * val[0] + tangentV * val[1]) + normal * val[2]);
       mappedNormal = mdl_adapt_normal(worldRayDir, geomNormal, n);
       hasNormal = true;
-    } else {
-      for (int k = 0; k < b.componentCount && k < 3; k++) params[b.paramIndex + k] = val[k];
+    } else {                                                              // gtlc.h GtlcCombineOp: bindings applied in order build an input from several lookups
+      const int op = b.combine & 15;
+      const float f = (op == GTLC_COMBINE_MIX) ? slot((b.combine >> 8) & 255) : 0.0f;
+      for (int k = 0; k < b.componentCount && k < 3; k++) {
+        float& x = slot(b.paramIndex + k);
+        if (op == GTLC_COMBINE_SET) x = val[k];
+        else if (op == GTLC_COMBINE_MULTIPLY) x = x * val[k];
+        else if (op == GTLC_COMBINE_ADD) x = x + val[k];
+        else x = x * (1.0f - f) + val[k] * f;                             // MDL math::lerp
+      }
     }
   }
   return hasNormal;

@@ -70,7 +70,7 @@ static const char* kOpbrNormalMap =
   "<input name=\"base_color\" type=\"color3\" nodename=\"col\"/><input name=\"specular_roughness\" type=\"float\" nodename=\"noise_graph\"/></open_pbr_surface></materialx>";
 
 // arithmetic with constants between the lookup and the input: roughness = (tex.g * 0.5 + 0.1) * 2, diffuseColor = (1 - tex.rgb) * (0.5, 1, 2),
-// metallic = 0.9 - tex.b / 4; clearcoat = tex.r * tex.g is not affine in one lookup and is not lowered
+// metallic = 0.9 - tex.b / 4; clearcoat = tex.r * tex.g is not affine in one lookup: two bindings, the second one multiplies
 static const char* kArithUps =
   "<materialx version=\"1.38\">"
   "<image name=\"img\" type=\"color3\"><input name=\"file\" type=\"filename\" value=\"a.ppm\" colorspace=\"lin_rec709\"/></image>"
@@ -84,6 +84,24 @@ static const char* kArithUps =
   "<multiply name=\"tt\" type=\"float\"><input name=\"in1\" type=\"float\" nodename=\"img\" output=\"r\"/><input name=\"in2\" type=\"float\" nodename=\"img\" output=\"g\"/></multiply>"
   "<UsdPreviewSurface name=\"S\" type=\"surfaceshader\"><input name=\"roughness\" type=\"float\" nodename=\"m2\"/><input name=\"diffuseColor\" type=\"color3\" nodename=\"tint\"/>"
   "<input name=\"metallic\" type=\"float\" nodename=\"s1\"/><input name=\"clearcoat\" type=\"float\" nodename=\"tt\"/></UsdPreviewSurface></materialx>";
+
+// inputs computed from two or three lookups: mix(image, image, image mask), mix with a constant mask (folds into scale / bias),
+// (image + image) * 0.5, image - image, mix(image, constant, image mask); a mix nested in a multiply is not lowered
+static const char* kLayeredOpbr =
+  "<materialx version=\"1.39\">"
+  "<image name=\"A\" type=\"color3\"><input name=\"file\" type=\"filename\" value=\"a.ppm\"/></image>"
+  "<image name=\"B\" type=\"color3\"><input name=\"file\" type=\"filename\" value=\"b.ppm\"/></image>"
+  "<image name=\"M\" type=\"color3\"><input name=\"file\" type=\"filename\" value=\"m.pfm\"/></image>"
+  "<mix name=\"mx\" type=\"color3\"><input name=\"bg\" type=\"color3\" nodename=\"A\"/><input name=\"fg\" type=\"color3\" nodename=\"B\"/><input name=\"mix\" type=\"float\" nodename=\"M\" output=\"r\"/></mix>"
+  "<mix name=\"mr\" type=\"float\"><input name=\"bg\" type=\"float\" value=\"0.2\"/><input name=\"fg\" type=\"float\" nodename=\"A\" output=\"g\"/><input name=\"mix\" type=\"float\" value=\"0.25\"/></mix>"
+  "<add name=\"sum\" type=\"color3\"><input name=\"in1\" type=\"color3\" nodename=\"A\"/><input name=\"in2\" type=\"color3\" nodename=\"B\"/></add>"
+  "<multiply name=\"half\" type=\"color3\"><input name=\"in1\" type=\"color3\" nodename=\"sum\"/><input name=\"in2\" type=\"float\" value=\"0.5\"/></multiply>"
+  "<subtract name=\"dif\" type=\"color3\"><input name=\"in1\" type=\"color3\" nodename=\"A\"/><input name=\"in2\" type=\"color3\" nodename=\"B\"/></subtract>"
+  "<mix name=\"mc\" type=\"color3\"><input name=\"bg\" type=\"color3\" nodename=\"A\"/><input name=\"fg\" type=\"color3\" value=\"1, 0, 0.5\"/><input name=\"mix\" type=\"float\" nodename=\"M\" output=\"g\"/></mix>"
+  "<multiply name=\"nest\" type=\"float\"><input name=\"in1\" type=\"float\" nodename=\"mr\"/><input name=\"in2\" type=\"float\" nodename=\"B\" output=\"r\"/></multiply>"
+  "<open_pbr_surface name=\"S\" type=\"surfaceshader\"><input name=\"base_color\" type=\"color3\" nodename=\"mx\"/><input name=\"specular_roughness\" type=\"float\" nodename=\"mr\"/>"
+  "<input name=\"coat_color\" type=\"color3\" nodename=\"half\"/><input name=\"emission_color\" type=\"color3\" nodename=\"dif\"/><input name=\"fuzz_color\" type=\"color3\" nodename=\"mc\"/>"
+  "<input name=\"base_metalness\" type=\"float\" nodename=\"nest\"/></open_pbr_surface></materialx>";
 
 static const char* kPrimvarUps =
   "<materialx version=\"1.38\"><UsdPrimvarReader name=\"dc\" type=\"color3\"><input name=\"varname\" type=\"string\" value=\"displayColor\"/>"
@@ -101,14 +119,34 @@ static int lowerTextureTests()
   }
   {
     GtlcMaterialDesc ad; std::vector<GtlcTextureBinding> ab; std::vector<std::string> af;
-    if (!giLowerMtlxToClosureWithTextures(kArithUps, "A", &ad, &ab, &af) || ab.size() != 3) return 50;      // clearcoat (texture x texture) is not lowered
+    if (!giLowerMtlxToClosureWithTextures(kArithUps, "A", &ad, &ab, &af) || ab.size() != 5) return 50;      // three plain inputs + clearcoat (texture x texture) as SET, MULTIPLY
     const GtlcTextureBinding *ro = nullptr, *dc = nullptr, *me = nullptr;
-    for (const GtlcTextureBinding& x : ab) { if (x.paramIndex == GTLC_UPS_ROUGHNESS) ro = &x; if (x.paramIndex == GTLC_UPS_DIFFUSE_R) dc = &x; if (x.paramIndex == GTLC_UPS_METALLIC) me = &x; }
-    if (!ro || !dc || !me) return 51;
+    const GtlcTextureBinding *cc0 = nullptr, *cc1 = nullptr;
+    for (const GtlcTextureBinding& x : ab) {
+      if (x.paramIndex == GTLC_UPS_ROUGHNESS) ro = &x; if (x.paramIndex == GTLC_UPS_DIFFUSE_R) dc = &x; if (x.paramIndex == GTLC_UPS_METALLIC) me = &x;
+      if (x.paramIndex == GTLC_UPS_CLEARCOAT) { if (!cc0) cc0 = &x; else cc1 = &x; }
+    }
+    if (!ro || !dc || !me || !cc0 || !cc1) return 51;
+    if (cc0->combine != 0 || cc0->channels[0] != 0 || cc1->combine != GTLC_COMBINE(GTLC_COMBINE_MULTIPLY, 0) || cc1->channels[0] != 1 || cc1->scale[1] != 1.0f || cc1->bias[1] != 0.0f) return 56;
     if (ro->channels[0] != 1 || ro->scale[1] != 1.0f || ro->bias[1] != 0.2f) return 52;                     // (g * 0.5 + 0.1) * 2 = g * 1 + 0.2
     if (dc->scale[0] != -0.5f || dc->bias[0] != 0.5f || dc->scale[1] != -1.0f || dc->bias[1] != 1.0f || dc->scale[2] != -2.0f || dc->bias[2] != 2.0f) return 53;   // (1 - c) * k
     if (me->channels[0] != 2 || me->scale[2] != -0.25f || me->bias[2] != 0.9f) return 54;                    // 0.9 - b / 4
     if (ad.params[GTLC_UPS_CLEARCOAT] != 0.0f) return 55;
+  }
+  {
+    GtlcMaterialDesc ld; std::vector<GtlcTextureBinding> lb; std::vector<std::string> lf;
+    if (!giLowerMtlxToClosureWithTextures(kLayeredOpbr, "L", &ld, &lb, &lf) || ld.closure != GTLC_CLOSURE_OPENPBR) return 60;
+    // base_color: mask -> scratch0, A, B mixed in; roughness: one binding; coat: A/2 then + B/2; emission: A then - B; fuzz: mask -> scratch1, A, constant mixed in
+    if (lb.size() != 3 + 1 + 2 + 2 + 3 || lf.size() != lb.size()) return 61;
+    const int S0 = GTLC_BIND_SCRATCH, S1 = GTLC_BIND_SCRATCH + 1;
+    if (lb[0].paramIndex != S0 || lb[0].componentCount != 1 || lb[0].channels[0] != 0 || lb[0].combine != 0 || lf[0] != "m.pfm") return 62;
+    if (lb[1].paramIndex != GTLC_OPBR_BASE_COLOR_R || lb[1].combine != 0 || lf[1] != "a.ppm" || lb[2].paramIndex != GTLC_OPBR_BASE_COLOR_R || lb[2].combine != GTLC_COMBINE(GTLC_COMBINE_MIX, S0) || lf[2] != "b.ppm") return 63;
+    if (lb[3].paramIndex != GTLC_OPBR_SPECULAR_ROUGHNESS || lb[3].combine != 0 || lb[3].channels[0] != 1 || lb[3].scale[1] != 0.25f || lb[3].bias[1] != 0.2f * 0.75f) return 64;   // 0.2 (1 - 0.25) + g 0.25
+    if (lb[4].paramIndex != GTLC_OPBR_COAT_COLOR_R || lb[4].combine != 0 || lb[4].scale[0] != 0.5f || lb[5].combine != GTLC_COMBINE(GTLC_COMBINE_ADD, 0) || lb[5].scale[2] != 0.5f || lf[5] != "b.ppm") return 65;
+    if (lb[6].paramIndex != GTLC_OPBR_EMISSION_COLOR_R || lb[6].scale[1] != 1.0f || lb[7].combine != GTLC_COMBINE(GTLC_COMBINE_ADD, 0) || lb[7].scale[1] != -1.0f) return 66;
+    if (lb[8].paramIndex != S1 || lb[8].channels[0] != 1 || lb[9].paramIndex != GTLC_OPBR_FUZZ_COLOR_R || lb[9].combine != 0) return 67;
+    if (lb[10].combine != (GTLC_COMBINE(GTLC_COMBINE_MIX, S1) | GTLC_COMBINE_CONSTANT) || lb[10].bias[0] != 1.0f || lb[10].bias[1] != 0.0f || lb[10].bias[2] != 0.5f || !lf[10].empty() || lb[10].texture != 0) return 68;
+    if (ld.params[GTLC_OPBR_BASE_METALNESS] != 0.0f) return 69;                            // the nested graph is not lowered: default constant (with a warning)
   }
   GtlcMaterialDesc d; std::vector<GtlcTextureBinding> b; std::vector<std::string> files;
   if (!giLowerMtlxToClosureWithTextures(texturedUps("checker.ppm").c_str(), "T", &d, &b, &files)) return 20;

@@ -118,7 +118,7 @@ def feature_scenes():
     return {"textured": scenes.textured_cornell(32, 32, spp=4), "primvars": scenes.primvar_cornell(32, 32, spp=4),
             "volumes": scenes.volume_cornell(32, 32, spp=4, medium_stack_size=2), "nee": lit,
             "stress": scenes.material_stress(tris_per_mesh=200, meshes=12, width=32, height=32, spp=4),
-            "lookups": scenes.lookup_cornell(32, 32, spp=4)}
+            "lookups": scenes.lookup_cornell(32, 32, spp=4), "layered": scenes.layered_cornell(32, 32, spp=4)}
 
 
 def feature_anchors():
@@ -155,6 +155,17 @@ def main():
     with open(os.path.join(HERE, "reference_lfs.json"), "w") as f:
         json.dump(reference_lfs_pointers(), f, indent=1, sort_keys=True)
     if "--lfs-only" in sys.argv:
+        return
+    if "--add-missing-anchors" in sys.argv:        # a new feature scene: the committed anchors stay byte for byte, only the missing ones are rendered
+        path = os.path.join(HERE, "feature_anchors.npz")
+        have = dict(np.load(path))
+        for name, d_ in feature_scenes().items():
+            if name not in have:
+                img, _, rays = orc.OracleScene(d_).render()
+                have[name] = img
+                have[name + "_rays"] = np.array(rays, np.int64)
+                print("added anchor", name)
+        np.savez_compressed(path, **have)
         return
     ref = "/root/reference/cornell.usda"
     desc = usda.load(ref)

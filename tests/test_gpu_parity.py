@@ -614,6 +614,27 @@ def test_render_parity_textured_materials(gpu):
     assert np.array_equal(imgs[0], imgs[1])
 
 
+def test_layered_bindings_parity_and_baked_equivalence(gpu):
+    """Inputs built from several lookups (gtlc.h GtlcCombineOp: image x image, image + image, mix through a scratch float, constant
+    operands) -- what a MaterialX graph with multiply / add / mix nodes in front of a shader input becomes: against the oracle, and
+    bit for bit against the same scene with ONE pre-combined float image per input (texel fetches: the same float32 operations)."""
+    d = scenes.layered_cornell(96, 96, spp=8)
+    img, ref = _render_parity(gpu, d)
+    b = gpu.BuiltScene(scenes.layered_cornell(96, 96, spp=8, baked=True))
+    try:
+        assert np.array_equal(b.render(), img)
+    finally:
+        b.close()
+    plain = scenes.cornell(96, 96, spp=8)
+    plain.settings, plain.rect_lights = d.settings, d.rect_lights
+    b = gpu.BuiltScene(plain)
+    try:
+        assert np.abs(b.render() - img).mean() > 1e-2, "the bindings changed nothing"
+    finally:
+        b.close()
+    _aov_parity(gpu, dataclasses.replace(d, width=48, height=48))
+
+
 @pytest.mark.logs_errors
 def test_texture_errors_are_loud(gpu):
     assert gpu.giCreateTexture(np.zeros((0, 4, 4), np.uint8)) is None and "empty texture" in gpu.giLastError()
@@ -640,6 +661,27 @@ def test_texture_errors_are_loud(gpu):
     ups = scenes.material_usd_preview_surface("x")
     assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [scenes.TextureBinding(scenes.UPS["opacity"] - 1, 0, (0, 1, 2))], [tex]) is None
     assert "cutout input" in gpu.giLastError()
+    # the combine word: unknown operation, a factor outside the block + scratch floats, anything but a plain lookup on the normal or
+    # the cutout input, a write past the scratch floats; a constant operand needs no texture, a lookup does
+    T, cmb = scenes.TextureBinding, scenes.combine
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.UPS["diffuse"], 0, (0, 1, 2), combine=7)], [tex]) is None
+    assert "combine word" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.UPS["diffuse"], 0, (0, 1, 2), combine=cmb(scenes.COMBINE_MIX, 60))], [tex]) is None
+    assert "combine word" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.BIND_NORMAL, 0, (0, 1, 2), combine=cmb(scenes.COMBINE_ADD))], [tex]) is None
+    assert "normal" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.UPS["opacity"], 0, (0,), combine=cmb(scenes.COMBINE_MULTIPLY))], [tex]) is None
+    assert "ONE plain lookup" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.UPS["opacity"], 0, (0,)), T(scenes.UPS["opacity"], 0, (1,))], [tex]) is None
+    assert "ONE plain lookup" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.BIND_SCRATCH + 2, 0, (0, 1, 2))], [tex]) is None
+    assert "outside the parameter block" in gpu.giLastError()
+    assert gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.UPS["diffuse"], -1, (0, 1, 2))], [tex]) is None
+    assert "no valid texture" in gpu.giLastError()
+    m2 = gpu.giCreateMaterial(s, ups.closure, ups.params, "m", [T(scenes.BIND_SCRATCH + 1, 0, (0, 1, 2)), T(scenes.UPS["diffuse"], -1, (0, 1, 2), bias=(0.2, 0.3, 0.4, 0.0),
+                              combine=cmb(scenes.COMBINE_MIX, scenes.BIND_SCRATCH + 3, constant=True))], [tex])
+    assert m2
+    gpu.giDestroyMaterial(m2)
     d = scenes.cornell(8, 8, spp=1)
     b = gpu.BuiltScene(d)
     try:

@@ -196,3 +196,24 @@ def test_lookup_cornell_renders_and_shows_holes():
         m.textures = [b for b in m.textures if b.param not in (scenes.UPS["opacity"], scenes.OPBR["geometry_opacity"])]
     img2 = orc.OracleScene(solid).render()[0]
     assert np.abs(img - img2).mean() > 1e-3
+
+
+# ---- inputs built from several lookups (gtlc.h GtlcCombineOp) ----------------------------------------------------------------
+def test_layered_bindings_equal_the_baked_images():
+    """multiply / add / mix of lookups, a mask carried in a scratch float, constant operands: with texel fetches of float images the
+    combination can be done ahead of time in numpy with the same float32 operations -- both forms of the scene render bit-identically,
+    and differently from the untextured box."""
+    a, _, ra = orc.OracleScene(scenes.layered_cornell(48, 48, spp=4)).render()
+    b, _, rb = orc.OracleScene(scenes.layered_cornell(48, 48, spp=4, baked=True)).render()
+    assert ra == rb and np.array_equal(a, b)
+    plain = scenes.cornell(48, 48, spp=4)
+    layered = scenes.layered_cornell(48, 48, spp=4)
+    plain.settings, plain.rect_lights = layered.settings, layered.rect_lights
+    c = orc.OracleScene(plain).render()[0]
+    assert np.abs(a - c).mean() > 1e-2
+    # the order of the bindings is the order of evaluation: the mask must be in its scratch float BEFORE the mix reads it
+    swapped = scenes.layered_cornell(48, 48, spp=4)
+    back = [m for m in swapped.materials if m.name == "BackMixConstant"][0]
+    back.textures = [back.textures[1], back.textures[2], back.textures[0]]          # mix first (factor still 0), mask last
+    e = orc.OracleScene(swapped).render()[0]
+    assert not np.array_equal(e, a)
