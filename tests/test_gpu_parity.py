@@ -614,6 +614,32 @@ def test_render_parity_textured_materials(gpu):
     assert np.array_equal(imgs[0], imgs[1])
 
 
+def test_unorm8_texels_decode_exactly(gpu):
+    """A texel-fetched RGBA8 image holding all 256 byte values renders bit-identically to the float image of the same values c / 255
+    (correctly rounded division in the decode, textures.cuh tex_fetch)."""
+    bytes_ = np.arange(256, dtype=np.uint8).reshape(8, 8, 4)
+    imgs = []
+    for tex in (scenes.Texture(bytes_), scenes.Texture((bytes_.astype(np.float32) / np.float32(255.0)).astype(np.float32))):
+        d = scenes.cornell(64, 64, spp=4)
+        for m in d.meshes:
+            scenes.assign_planar_uv(m)
+        d.textures = [tex]
+        for i, name in enumerate(("bottomplane", "backplane", "leftplane")):
+            mat = scenes.material_usd_preview_surface("Bytes%d" % i, diffuse=(0.5, 0.5, 0.5))
+            mat.textures = [scenes.TextureBinding(scenes.UPS["diffuse"], 0, ((0, 1, 2), (3, 0, 1), (2, 3, 0))[i], lookup=scenes.LOOKUP_TEXEL_2D, uv_scale=(0.9, 0.9), uv_translation=(0.05, 0.05))]
+            d.materials = list(d.materials) + [mat]
+            for k, mesh in enumerate(d.meshes):
+                if name in mesh.name.lower():
+                    d.meshes[k] = dataclasses.replace(mesh, material=len(d.materials) - 1)
+        b = gpu.BuiltScene(d)
+        try:
+            imgs.append(b.render().copy())
+        finally:
+            b.close()
+    assert imgs[0][..., :3].std() > 0.05
+    assert np.array_equal(imgs[0], imgs[1])
+
+
 def test_layered_bindings_parity_and_baked_equivalence(gpu):
     """Inputs built from several lookups (gtlc.h GtlcCombineOp: image x image, image + image, mix through a scratch float, constant
     operands) -- what a MaterialX graph with multiply / add / mix nodes in front of a shader input becomes: against the oracle, and

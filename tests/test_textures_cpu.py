@@ -217,3 +217,11 @@ def test_layered_bindings_equal_the_baked_images():
     back.textures = [back.textures[1], back.textures[2], back.textures[0]]          # mix first (factor still 0), mask last
     e = orc.OracleScene(swapped).render()[0]
     assert not np.array_equal(e, a)
+
+
+def test_rgba8_texels_decode_to_c_over_255():
+    """Every byte value through the texel fetch: (float) c / 255, correctly rounded."""
+    t = scenes.Texture(np.arange(256, dtype=np.uint8).reshape(8, 8, 4))
+    for i in range(64):
+        got = orc.tex_texel(t, i % 8, i // 8)
+        assert np.array_equal(got, (np.arange(4 * i, 4 * i + 4).astype(np.float32) / np.float32(255.0)))

@@ -18,6 +18,7 @@ ap.add_argument("--bvh-builder", type=int, default=0, help="0 host binned SAH, 1
 ap.add_argument("--trace-variant", type=int, default=0)
 ap.add_argument("--ups", action="store_true", help="replace the OpenPBR materials of c3/c5 by UsdPreviewSurface ones (same colours / roughness / metalness)")
 ap.add_argument("--tri-threshold", type=int, default=0)
+ap.add_argument("--textured", action="store_true", help="c3/c5: planar uvs on every mesh and, on every OpenPBR material, a 1024x1024 sRGB RGBA8 image on base_color + a 512x512 R32F image on specular_roughness")
 ap.add_argument("--refill-sweep", default="", help="comma list of refill thresholds (idle lanes at which a warp fetches new rays) measured after the normal lines, sort as in the last of them")
 a = ap.parse_args()
 assert gi.giInitialize(0) == gi.GiStatus.Ok, gi.giLastError()
@@ -40,6 +41,14 @@ for name in a.configs.split(","):
         O, U = scenes.OPBR, scenes.UPS
         d.materials = [m if m.closure != scenes.CLOSURE_OPENPBR else scenes.material_usd_preview_surface(m.name, diffuse=tuple(m.params[O["base_color"]:O["base_color"] + 3]),
                        roughness=float(m.params[O["specular_roughness"]]), metallic=float(m.params[O["base_metalness"]]), clearcoat=float(m.params[O["coat_weight"]])) for m in d.materials]
+    if a.textured:
+        for m in d.meshes:
+            scenes.assign_planar_uv(m)
+        d.textures = [scenes.procedural_texture("checker", 1024), scenes.procedural_texture("roughness", 512)]
+        for m in d.materials:
+            if m.closure == scenes.CLOSURE_OPENPBR:
+                m.textures = [scenes.TextureBinding(scenes.OPBR["base_color"], 0, (0, 1, 2), srgb=True, uv_scale=(4.0, 4.0)),
+                              scenes.TextureBinding(scenes.OPBR["specular_roughness"], 1, (0,), scale=(0.6, 1, 1, 1), bias=(0.05, 0, 0, 0), uv_scale=(3.0, 3.0))]
     t_gen = time.perf_counter() - t0
     import ctypes as C
     gi.set_tuning(bvhBuilder=a.bvh_builder, traceVariant=a.trace_variant, reserved=(C.c_int32 * 3)(0, 0, a.tri_threshold))
@@ -63,7 +72,7 @@ for name in a.configs.split(","):
                 best = s
         rays = best["closestRays"] + best["shadowRays"]
         print(json.dumps({"config": name, "scene": d.name, "triangles": d.triangle_count, "materials": len(d.materials), "spp": d.settings.spp,
-                          "sort": sort, "Mray_s": rays / best["msTotal"] / 1e3, "ms_total": best["msTotal"], "closest": best["closestRays"],
+                          "sort": sort, "textured": bool(a.textured), "Mray_s": rays / best["msTotal"] / 1e3, "ms_total": best["msTotal"], "closest": best["closestRays"],
                           "shadow": best["shadowRays"], "ms_trace": best["msTraceClosest"], "ms_shadow": best["msTraceAny"], "ms_shade": best["msShade"],
                           "ms_sort": best["msSort"], "bvh_builder": a.bvh_builder, "trace_variant": a.trace_variant, "bvh_build_ms": best["msBvhBuild"], "bvh_device_build_ms": best["msBvhDeviceBuild"], "bvh_nodes": best["bvhNodeCount"], "depth": best["bvhMaxDepth"],
                           "scene_gen_s": round(t_gen, 2), "launches": best["kernelLaunches"], **visits}), flush=True)
