@@ -137,8 +137,13 @@ class ClockSampler:
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        try:
+            with open(p) as f:
+                v = float(json.load(f)["hbm_gbs"])
+            if v > 0.0:
+                return v, "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception as e:                      # an unreadable file must not cost the bench line
+            print("bench: MEASURED_PEAKS.json ignored (%s)" % e, file=sys.stderr)
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
