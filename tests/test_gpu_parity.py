@@ -844,6 +844,52 @@ def test_full_size_c3_band_parity_and_properties(gpu):
         b.close()
 
 
+def test_full_size_c5_band_parity_and_properties(gpu):
+    """Config C5 at BASELINE.json's full size (64 displaced spheres of 31 250 triangles, one OpenPBR parameter set each, dome +
+    distant light, NEE, 1920x1080): a band of rows against the oracle, bit-exact hit records, and the properties the domain
+    offers at any size -- the frame does not depend on the material sort (64 bins in use), the wave size or the shard count."""
+    d = scenes.material_stress(width=1920, height=1080, spp=2, max_bounces=8)
+    assert d.triangle_count >= 1_900_000 and len(d.materials) == 64
+    b = gpu.BuiltScene(d)
+    try:
+        img = b.render().copy()
+        st = gpu.get_stats()
+        assert np.isfinite(img).all() and np.all(img[..., 3] == 1.0) and img[..., :3].min() >= 0.0
+        assert st["paths"] == 1920 * 1080 * 2 and st["shadowRays"] > 0
+        o = orc.OracleScene(d)
+        r0, r1 = 500, 506
+        band, _, rays = o.render(rows=(r0, r1), spp=2)
+        got, ref = img[r0:r1, :, :3].astype(np.float64), band[r0:r1, :, :3].astype(np.float64)
+        err = ((got - ref) ** 2).sum(-1).reshape(-1)
+        rmse = float(np.sqrt(np.sort(err)[:-8].sum() / (3 * err.size)))
+        assert rmse < 1e-3, "band RMSE %.3e" % rmse
+        assert float((np.abs(got - ref) <= 1e-3 + 1e-3 * np.abs(ref)).mean()) >= 0.999
+        probe = random_rays(40000, 43)
+        probe[:, 0:3] *= np.array([8.0, 1.0, 8.0], np.float32); probe[:, 1] -= 6.0             # in front of the wall of spheres
+        probe[:, 5] = np.abs(probe[:, 5]) + 0.5                                                # towards it
+        h = gpu.trace_rays(b.scene, probe)
+        h_ref = o.trace(probe)
+        for k in ("prim", "inst", "t", "u", "v"):
+            assert np.array_equal(h[k], h_ref[k]), k
+        assert (h["t"] > 0).mean() > 0.3
+        o.close()
+        gpu.set_tuning(sortByMaterial=0, maxPathsPerWave=1 << 21)
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(b.render(), img), "material sort / wave size changed the image"
+        gpu.set_tuning(sortByMaterial=-1, maxPathsPerWave=1 << 24)
+        acc = np.zeros_like(img)
+        for r in range(2):
+            gpu.set_shard(b.scene, r, 2, 32)
+            part = b.render()
+            acc[..., :3] += part[..., :3]
+            acc[..., 3] = np.maximum(acc[..., 3], part[..., 3])
+        gpu.set_shard(b.scene, 0, 1, 64)
+        assert np.array_equal(acc, img), "tile shards do not sum to the frame"
+    finally:
+        gpu.set_tuning(maxPathsPerWave=1 << 24, sortByMaterial=-1)
+        b.close()
+
+
 @pytest.mark.logs_errors      # a too-short primvar is ignored, loudly
 def test_render_parity_primvars(gpu):
     """R15 scene data: material inputs read from mesh / instancer primvars (constant, instance, uniform, vertex
