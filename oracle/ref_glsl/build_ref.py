@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE.  Builds oracle/_ref/libglslref.so from the reference's OWN shader sources, where they lie under
+/root/reference/src/gi/shaders, so that tests/test_reference_glsl_cpu.py can hold the oracle's restatements against them.
+
+GLSL is not C++, but the pure functions of these files (no ray-tracing built-ins, no descriptors) become C++ after three
+mechanical rewrites, done here on the fly into a temporary directory (nothing derived from the reference's text is written into
+the repository; only the shared object is kept, git-ignored):
+  * parameter qualifiers:  `in T x` -> `T x`,  `out T x` / `inout T x` -> `T& x`
+  * swizzles used as values:  `.xy` `.yx` `.zw` `.xyz` `.rgb` -> `.xy()` ...
+  * vector constructors:  `vec4(a, b, c, d)` -> `vec4{a, b, c, d}` (left-to-right evaluation of the arguments, as GLSL specifies)
+  * a line range is cut out of the files that also hold Vulkan-only code (rp_main.rgen / .chit / .miss, mdl_interface.glsl)
+The types and built-ins come from oracle/ref_glsl/glsl_shim.h; g++ runs with -fsingle-precision-constant (GLSL literals are
+floats) and -ffp-contract=off."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/src/gi/shaders"
+OUT = os.path.join(os.path.dirname(HERE), "_ref")
+
+# (source, first line, last line (inclusive, None = whole file), generated name)
+FRAGMENTS = [
+    ("aovs.glsl", None, None, "aovs.glsl"),
+    ("common.glsl", None, None, "common.glsl"),
+    ("colormap.glsl", None, None, "colormap.glsl"),
+    ("mdl_types.glsl", None, None, "mdl_types.glsl"),
+    ("rp_main_payload.glsl", 1, 98, "rp_main_payload.glsl"),
+    ("rp_main.rgen", 48, 130, "rgen_functions.inc"),           # sampleDistance .. fisGauss
+    ("rp_main.rgen", 191, 288, "rgen_camera.inc"),             # main(): pixel -> camera ray, RNG draws, clip range (leaves the sample loop open)
+    ("mdl_shading_state.glsl", None, None, "mdl_shading_state.glsl"),
+    ("rp_main.chit", 29, 131, "chit_sample_light.inc"),        # sampleLight
+    ("rp_main.miss", 36, 53, "miss_functions.inc"),            # quatRotateDir, sampleDomeLight
+    ("mdl_interface.glsl", 8, 38, "mdl_wrap.inc"),             # apply_wrap_and_crop
+    ("mdl_interface.glsl", 238, 256, "mdl_adapt_normal.inc"),  # mdl_adapt_normal
+]
+
+
+def brace_constructors(text: str) -> str:
+    """`vec4(a, b, c, d)` -> `vec4{a, b, c, d}`: GLSL evaluates constructor arguments left to right (the RNG draws of rng1d_next4f
+    depend on it), C++ only promises that for braced initialisers."""
+    out, i = [], 0
+    pat = re.compile(r"\b(?:vec[234]|ivec[234]|uvec[234])\(")
+    while True:
+        m = pat.search(text, i)
+        if not m:
+            out.append(text[i:])
+            return "".join(out)
+        j, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[j], 0)
+            j += 1
+        out.append(text[i:m.end() - 1] + "{" + brace_constructors(text[m.end():j - 1]) + "}")
+        i = j
+
+
+def translate(text: str) -> str:
+    text = re.sub(r"(?<=[(,])\s*in\s+(?=\w+\s+\w+\s*[,)])", " ", text)
+    text = re.sub(r"(?<=[(,])\s*(?:inout|out)\s+(\w+)\s+(\w+)(?=\s*[,)])", r" \1& \2", text)
+    text = re.sub(r"\.(xyz|rgb|xy|yx|zw)\b(?!\s*\()", r".\1()", text)
+    return brace_constructors(text)
+
+
+def build() -> str:
+    if not os.path.isdir(REF):
+        raise SystemExit("build_ref: %s does not exist (the reference sources are only present in the build container)" % REF)
+    os.makedirs(OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="glslref_")
+    try:
+        for src, a, b, name in FRAGMENTS:
+            with open(os.path.join(REF, src)) as f:
+                lines = f.read().split("\n")
+            if a is not None:
+                lines = lines[a - 1:b]
+            with open(os.path.join(tmp, name), "w") as f:
+                f.write(translate("\n".join(lines)) + "\n")
+        so = os.path.join(OUT, "libglslref.so")
+        cmd = ["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fsingle-precision-constant", "-ffp-contract=off", "-fno-fast-math", "-w",
+               "-I", tmp, "-I", HERE, "-I", REF, os.path.join(HERE, "ref_exports.cpp"), "-o", so, "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stderr[-6000:])
+            raise SystemExit("build_ref: g++ failed")
+        return so
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    print(build())

@@ -1,0 +1,185 @@
+// TEST INFRASTRUCTURE.  C entry points around the reference's own shader functions (see build_ref.py for how the sources get here).
+// Everything between the `#include`s of generated files is glue: the globals the fragments expect (ubo, light buffers, the ray
+// direction built-in, a recording stand-in for the dome-light texture fetch) and plain-pointer wrappers.
+#include "glsl_shim.h"
+#undef UINT32_MAX                       // common.glsl declares its own constant of that name
+#include "interface/rp_main.h"          // the reference's shared C++/GLSL header (through oracle/ref_glsl/glm/glm.hpp): UniformData, *Light
+using namespace gtl::shader_interface::rp_main;
+
+static UniformData ubo;
+static SphereLight sphereLights[16];
+static DistantLight distantLights[16];
+static RectLight rectLights[16];
+static DiskLight diskLights[16];
+static vec3 gl_WorldRayDirectionEXT;
+// rp_main.miss:46-53 reads the dome-light image; the stand-in returns the lat-long coordinate it was asked for
+static int textures_2d[4], tex_sampler;
+static inline int sampler2D(int, int) { return 0; }
+#define nonuniformEXT(x) (x)
+static inline vec4 textureLod(int, vec2 uv, uint) { return vec4(uv.x, uv.y, 0.0f, 1.0f); }
+
+// mdl_shading_state.glsl reads the hit mesh through buffer references and the ray-tracing built-ins; the stand-ins point at test arrays
+static BlasPayload blas_payloads[1];
+static const Face* g_faces; static const FVertex* g_vertices;
+struct IndexBuffer { const Face* data; explicit IndexBuffer(uint64_t) : data(g_faces) {} };
+struct VertexBuffer { const FVertex* data; explicit VertexBuffer(uint64_t) : data(g_vertices) {} };
+static int gl_InstanceCustomIndexEXT, gl_PrimitiveID;
+static mat4x3 gl_ObjectToWorldEXT, gl_WorldToObjectEXT;
+static uvec3 gl_LaunchIDEXT;
+static inline void clearAovs(uint) {}
+#define SCENE_DATA_COUNT 0
+
+#include "common.glsl"
+#include "colormap.glsl"
+#include "mdl_types.glsl"
+#include "mdl_wrap.inc"
+#include "mdl_adapt_normal.inc"
+#include "miss_functions.inc"
+#define NEXT_EVENT_ESTIMATION
+#include "chit_sample_light.inc"
+namespace mss2 {
+#define MEDIUM_STACK_SIZE 2
+#include "rp_main_payload.glsl"
+#include "rgen_functions.inc"
+#undef MEDIUM_STACK_SIZE
+}
+namespace mss0 {
+#define MEDIUM_STACK_SIZE 0
+#include "rp_main_payload.glsl"
+#undef MEDIUM_STACK_SIZE
+}
+
+#include "mdl_shading_state.glsl"
+static mss2::ShadeRayPayload rayPayload;
+// rp_main.rgen:191-288 is the head of main(): it is compiled once per combination of the compile-time switches the reference builds
+// its pipeline with (GlslShaderGen.cpp:57-72).  The fragment ends inside the sample loop, which the wrapper closes after one pass.
+#define CAMERA_VARIANT(NAME)                                                                                         \
+  namespace NAME {                                                                                                   \
+    using mss2::fisGauss;                                                                                            \
+    static void camera(uint px, uint py, float* out8, uint* rngOut)                                                  \
+    {                                                                                                                \
+      gl_LaunchIDEXT = uvec3(px, py, 0u);
+#define CAMERA_VARIANT_END                                                                                           \
+        out8[0] = ray_origin.x; out8[1] = ray_origin.y; out8[2] = ray_origin.z; out8[3] = ray_dir.x; out8[4] = ray_dir.y; out8[5] = ray_dir.z; \
+        out8[6] = clipRange.x; out8[7] = clipRange.y; *rngOut = rng_state;                                           \
+        break;                                                                                                       \
+      }                                                                                                              \
+    }                                                                                                                \
+  }
+#define MEDIUM_STACK_SIZE 2
+CAMERA_VARIANT(cam_plain)
+#include "rgen_camera.inc"
+CAMERA_VARIANT_END
+#define JITTERED_SAMPLING
+CAMERA_VARIANT(cam_jitter)
+#include "rgen_camera.inc"
+CAMERA_VARIANT_END
+#define FILTER_IMPORTANCE_SAMPLING
+CAMERA_VARIANT(cam_jitter_fis)
+#include "rgen_camera.inc"
+CAMERA_VARIANT_END
+#define DEPTH_OF_FIELD
+CAMERA_VARIANT(cam_jitter_fis_dof)
+#include "rgen_camera.inc"
+CAMERA_VARIANT_END
+#undef JITTERED_SAMPLING
+#undef FILTER_IMPORTANCE_SAMPLING
+CAMERA_VARIANT(cam_dof)
+#include "rgen_camera.inc"
+CAMERA_VARIANT_END
+#undef DEPTH_OF_FIELD
+#undef MEDIUM_STACK_SIZE
+
+static inline vec3 ld3(const float* p) { return vec3(p[0], p[1], p[2]); }
+static inline void st3(float* o, vec3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+// ---- common.glsl ----
+EXPORT uint ref_hash_theironborn(uint x) { return hash_theironborn(x); }
+EXPORT uint ref_hash_pcg32(uint* state) { return hash_pcg32(*state); }
+EXPORT float ref_uint_as_float(uint v) { return uintAsFloat(v); }
+EXPORT uint ref_rng_init(uint pixelIndex, uint sampleIndex) { return rng1d_init(pixelIndex, sampleIndex); }
+EXPORT float ref_rng_next1f(uint* state) { return rng1d_next1f(*state); }
+EXPORT void ref_rng_next4f(uint* state, float* o) { vec4 r = rng1d_next4f(*state); o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; }
+EXPORT void ref_orthonormal_basis(const float* n, float* b1, float* b2) { vec3 a, b; orthonormal_basis(ld3(n), a, b); st3(b1, a); st3(b2, b); }
+EXPORT void ref_offset_ray_origin(const float* p, const float* n, float* o) { st3(o, offset_ray_origin(ld3(p), ld3(n))); }
+EXPORT uint ref_encode_direction(const float* d) { return encode_direction(ld3(d)); }
+EXPORT void ref_decode_direction(uint e, float* o) { st3(o, decode_direction(e)); }
+EXPORT void ref_sample_hemisphere(const float* xi, float* o) { st3(o, sample_hemisphere(vec2(xi[0], xi[1]))); }
+EXPORT void ref_sample_sphere(const float* xi, const float* radius, float* o) { st3(o, sample_sphere(vec2(xi[0], xi[1]), ld3(radius))); }
+EXPORT void ref_sample_disk(const float* xi, const float* radius, float* o) { vec2 r = sample_disk(vec2(xi[0], xi[1]), vec2(radius[0], radius[1])); o[0] = r.x; o[1] = r.y; }
+EXPORT float ref_luminance(const float* c) { return luminance(ld3(c)); }
+EXPORT float ref_safe_div(float a, float b) { return safe_div(a, b); }
+// ---- colormap.glsl ----
+EXPORT void ref_colormap(int which, float t, float* o) { st3(o, which == 0 ? colormap_viridis(t) : which == 1 ? colormap_plasma(t) : which == 2 ? colormap_magma(t) : which == 3 ? colormap_inferno(t) : colormap_turbo(t)); }
+// ---- rp_main.rgen:48-130 ----
+EXPORT float ref_sample_distance(const float* albedo, const float* throughput, const float* sigma_t, float xi, float* pdf) { vec3 p; float r = mss2::sampleDistance(ld3(albedo), ld3(throughput), ld3(sigma_t), xi, p); st3(pdf, p); return r; }
+EXPORT float ref_sample_hg_cos(float r, float g) { return mss2::sampleHenyeyGreensteinCos(r, g); }
+EXPORT void ref_sample_volume_scattering_direction(const float* xi, float bias, float* dir) { vec3 d = ld3(dir); mss2::sampleVolumeScatteringDirection(vec2(xi[0], xi[1]), bias, d); st3(dir, d); }
+EXPORT int ref_russian_roulette(float xi, float* throughput, float rrInvMinTermProb) { ubo.rrInvMinTermProb = rrInvMinTermProb; vec3 t = ld3(throughput); bool r = mss2::russian_roulette(xi, t); st3(throughput, t); return r ? 1 : 0; }
+EXPORT void ref_fis_gauss(const float* xi, float* o) { vec2 r = mss2::fisGauss(vec2(xi[0], xi[1])); o[0] = r.x; o[1] = r.y; }
+// ---- rp_main_payload.glsl ----
+EXPORT uint ref_payload_get_medium_idx(uint bitfield, int mediumStackSize) { if (mediumStackSize == 2) { mss2::ShadeRayPayload p; p.bitfield = bitfield; return mss2::shadeRayPayloadGetMediumIdx(p); } mss0::ShadeRayPayload p; p.bitfield = bitfield; return mss0::shadeRayPayloadGetMediumIdx(p); }
+EXPORT uint ref_payload_set_medium_idx(uint bitfield, uint idx) { mss2::ShadeRayPayload p; p.bitfield = bitfield; mss2::shadeRayPayloadSetMediumIdx(p, idx); return p.bitfield; }
+EXPORT uint ref_payload_increment_walk(uint bitfield) { mss2::ShadeRayPayload p; p.bitfield = bitfield; mss2::shadeRayPayloadIncrementWalk(p); return p.bitfield; }
+EXPORT uint ref_payload_get_walk(uint bitfield) { mss2::ShadeRayPayload p; p.bitfield = bitfield; return mss2::shadeRayPayloadGetWalk(p); }
+// ---- rp_main.miss:39-53 ----
+EXPORT void ref_quat_rotate_dir(const float* q, const float* dir, float* o) { st3(o, quatRotateDir(vec4(q[0], q[1], q[2], q[3]), ld3(dir))); }
+EXPORT void ref_dome_light_uv(const float* rayDir, float* uv) { vec3 r = sampleDomeLight(1u, ld3(rayDir)); uv[0] = r.x; uv[1] = r.y; }
+// ---- mdl_interface.glsl:8-38, 238-256 ----
+EXPORT float ref_apply_wrap_and_crop(float coord, int wrap, int res) { return apply_wrap_and_crop(coord, wrap, vec2(0.0f, 1.0f), res); }
+EXPORT void ref_mdl_adapt_normal(const float* worldRayDir, const float* geomNormal, const float* normal, float* o)
+{
+  gl_WorldRayDirectionEXT = ld3(worldRayDir);
+  State s; s.geom_normal = ld3(geomNormal); s.normal = ld3(normal);
+  st3(o, mdl_adapt_normal(s, ld3(normal)));
+}
+// ---- rp_main.chit:30-129 ----
+// counts[4] = sphere, distant, rect, disk; the light arrays hold the interface structs byte for byte (48 / 48 / 48 / 48 bytes each)
+EXPORT void ref_sample_light(const uint* counts, const void* spheres, const void* distants, const void* rects, const void* disks, float lightIntensityMultiplier,
+                             float sensorExposure, const float* k4, const float* surfacePos, float* out8, uint* diffuseSpecularPacked)
+{
+  ubo.sphereLightCount = counts[0]; ubo.distantLightCount = counts[1]; ubo.rectLightCount = counts[2]; ubo.diskLightCount = counts[3];
+  ubo.totalLightCount = counts[0] + counts[1] + counts[2] + counts[3];
+  ubo.lightIntensityMultiplier = lightIntensityMultiplier; ubo.sensorExposure = sensorExposure;
+  // (k4.x == 0 enters the sphere branch even when there is no sphere light: the shader then reads element 0 of a buffer that holds no
+  //  light -- zeros, as the oracle assumes; the stand-in buffers start from zeros on every call for the same reason)
+  memset(sphereLights, 0, sizeof(sphereLights)); memset(distantLights, 0, sizeof(distantLights)); memset(rectLights, 0, sizeof(rectLights)); memset(diskLights, 0, sizeof(diskLights));
+  memcpy(sphereLights, spheres, sizeof(SphereLight) * counts[0]); memcpy(distantLights, distants, sizeof(DistantLight) * counts[1]);
+  memcpy(rectLights, rects, sizeof(RectLight) * counts[2]); memcpy(diskLights, disks, sizeof(DiskLight) * counts[3]);
+  vec3 dirToLight, power; float dist, invPdf; uint dsp;
+  sampleLight(vec4(k4[0], k4[1], k4[2], k4[3]), ld3(surfacePos), dirToLight, dist, power, invPdf, dsp);
+  st3(out8, dirToLight); out8[3] = dist; st3(out8 + 4, power); out8[7] = invPdf; *diffuseSpecularPacked = dsp;
+}
+EXPORT int ref_struct_sizes(int which) { return which == 0 ? (int) sizeof(SphereLight) : which == 1 ? (int) sizeof(DistantLight) : which == 2 ? (int) sizeof(RectLight) : (int) sizeof(DiskLight); }
+// ---- rp_main.rgen:191-288 ----
+// flags: bit 0 JITTERED_SAMPLING, bit 1 FILTER_IMPORTANCE_SAMPLING, bit 2 DEPTH_OF_FIELD.  cam12 / bits2 as orc_camera_ubo delivers them.
+EXPORT int ref_camera_ray(int flags, const float* cam12, const uint* bits2, uint sampleIndex, uint px, uint py, float* out8, uint* rngOut)
+{
+  ubo.cameraPosition = ld3(cam12); ubo.cameraForward = ld3(cam12 + 3); ubo.cameraUp = ld3(cam12 + 6);
+  ubo.cameraVFoV = cam12[9]; ubo.focusDistance = cam12[10]; ubo.lensRadius = cam12[11];
+  ubo.clipRangePacked = bits2[0]; ubo.imageDims = bits2[1];
+  ubo.spp = 1; ubo.sampleOffset = sampleIndex;
+  switch (flags) {
+    case 0: cam_plain::camera(px, py, out8, rngOut); return 1;
+    case 1: cam_jitter::camera(px, py, out8, rngOut); return 1;
+    case 3: cam_jitter_fis::camera(px, py, out8, rngOut); return 1;
+    case 7: cam_jitter_fis_dof::camera(px, py, out8, rngOut); return 1;
+    case 4: cam_dof::camera(px, py, out8, rngOut); return 1;
+  }
+  return 0;
+}
+// ---- mdl_shading_state.glsl ----
+// faces: the hit mesh's index triples; vertices: the vertex array its vertexOffset indexes; o2w / w2o: row-major 3x4
+EXPORT void ref_setup_shading_state(const void* faces, const void* vertices, uint vertexOffset, const float* o2w12, const float* w2o12, uint prim, float u, float v,
+                                    const float* rayDir, float* out18, int* frontFace)
+{
+  g_faces = (const Face*) faces; g_vertices = (const FVertex*) vertices;
+  blas_payloads[0].vertexOffset = vertexOffset; blas_payloads[0].bufferAddress = 0; gl_InstanceCustomIndexEXT = 0; gl_PrimitiveID = (int) prim;
+  memcpy(gl_ObjectToWorldEXT.m, o2w12, 48); memcpy(gl_WorldToObjectEXT.m, w2o12, 48);
+  gl_WorldRayDirectionEXT = ld3(rayDir);
+  State st; bool ff = false;
+  setup_mdl_shading_state(vec2(u, v), st, ff);
+  st3(out18, st.normal); st3(out18 + 3, st.geom_normal); st3(out18 + 6, st.position); st3(out18 + 9, st.tangent_u[0]); st3(out18 + 12, st.tangent_v[0]); st3(out18 + 15, st.text_coords[0]);
+  *frontFace = ff ? 1 : 0;
+}

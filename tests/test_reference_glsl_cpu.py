@@ -1,0 +1,304 @@
+"""CPU: the oracle's restatements against the reference's OWN shader functions.
+
+oracle/ref_glsl/build_ref.py compiles the pure functions of /root/reference/src/gi/shaders (common.glsl, colormap.glsl,
+rp_main_payload.glsl, the helper functions of rp_main.rgen / .chit / .miss, apply_wrap_and_crop and mdl_adapt_normal of
+mdl_interface.glsl) as C++ -- from where they lie, through a GLSL shim whose built-ins are the oracle's -- into
+oracle/_ref/libglslref.so.  Every function must return the same BITS as the oracle's hand-written restatement on seeded random
+inputs and on the edge cases of its domain: what is pinned is the reference's code (constants, operation order, branches)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "_ref", "libglslref.so")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    if not os.path.exists(SO):
+        if not os.path.isdir("/root/reference/src/gi/shaders"):
+            pytest.skip("oracle/_ref/libglslref.so is built from /root/reference, which only exists in the build container")
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_glsl"))
+        import build_ref
+        build_ref.build()
+    return C.CDLL(SO), orc.lib()
+
+
+F3 = C.c_float * 3
+
+
+def f3(v):
+    return F3(*[float(x) for x in v])
+
+
+def bits(a):
+    return np.asarray(a, np.float32).tobytes()
+
+
+def call3(fn, *args, n=3):
+    out = (C.c_float * n)()
+    fn(*args, out)
+    return bits(out[:])
+
+
+def unit(v):
+    v = np.asarray(v, np.float64)
+    return (v / np.linalg.norm(v)).astype(np.float32)
+
+
+def test_rng_and_hashes(libs):
+    R, O = libs
+    for L in (R, O):
+        for name in ("hash_theironborn", "rng_init"):
+            getattr(L, ("ref_" if L is R else "orc_") + name).restype = C.c_uint32
+    R.ref_uint_as_float.restype = O.orc_uint_as_float.restype = C.c_float
+    R.ref_rng_next1f.restype = O.orc_rng_next1f.restype = C.c_float
+    rng = np.random.default_rng(1)
+    for x in list(rng.integers(0, 2 ** 32, 2000, dtype=np.uint64)) + [0, 1, 0xFFFFFFFF, 0x80000000]:
+        x = int(x)
+        assert R.ref_hash_theironborn(C.c_uint32(x)) == O.orc_hash_theironborn(C.c_uint32(x))
+        assert R.ref_rng_init(C.c_uint32(x), C.c_uint32(x >> 7)) == O.orc_rng_init(C.c_uint32(x), C.c_uint32(x >> 7))
+        assert bits([R.ref_uint_as_float(C.c_uint32(x))]) == bits([O.orc_uint_as_float(C.c_uint32(x))])
+        a, b = C.c_uint32(x), C.c_uint32(x)
+        fa, fb = (C.c_float * 4)(), (C.c_float * 4)()
+        R.ref_rng_next4f(C.byref(a), fa); O.orc_rng_next4f(C.byref(b), fb)
+        assert a.value == b.value and bits(fa[:]) == bits(fb[:])
+        assert bits([R.ref_rng_next1f(C.byref(a))]) == bits([O.orc_rng_next1f(C.byref(b))]) and a.value == b.value
+
+
+def test_geometry_helpers(libs):
+    R, O = libs
+    R.ref_encode_direction.restype = O.orc_encode_direction.restype = C.c_uint32
+    R.ref_luminance.restype = O.orc_luminance.restype = C.c_float
+    R.ref_safe_div.restype = O.orc_safe_div.restype = C.c_float
+    R.ref_safe_div.argtypes = O.orc_safe_div.argtypes = [C.c_float, C.c_float]
+    rng = np.random.default_rng(2)
+    dirs = [unit(rng.normal(size=3)) for _ in range(3000)] + [np.array(v, np.float32) for v in
+            ((0, 0, 1), (0, 0, -1), (1, 0, 0), (0, -1, 0), (0.6, 0, -0.8), (-0.0, 0.0, 1.0), (0, 1, -0.0))]
+    for d in dirs:
+        b1r, b2r, b1o, b2o = F3(), F3(), F3(), F3()
+        R.ref_orthonormal_basis(f3(d), b1r, b2r); O.orc_orthonormal_basis(f3(d), b1o, b2o)
+        assert bits(b1r[:]) == bits(b1o[:]) and bits(b2r[:]) == bits(b2o[:])
+        e = R.ref_encode_direction(f3(d))
+        assert e == O.orc_encode_direction(f3(d))
+        assert call3(R.ref_decode_direction, C.c_uint32(e)) == call3(O.orc_decode_direction, C.c_uint32(e))
+        p = (rng.normal(size=3) * 10.0 ** rng.integers(-4, 4)).astype(np.float32)
+        assert call3(R.ref_offset_ray_origin, f3(p), f3(d)) == call3(O.orc_offset_ray_origin, f3(p), f3(d))
+        assert bits([R.ref_luminance(f3(p))]) == bits([O.orc_luminance(f3(p))])
+    for p in ((0, 0, 0), (1 / 32, -1 / 32, 0.03124), (-0.0, 5e-3, -7.0)):        # the |p| < 1/32 branch of offset_ray_origin, per component
+        for d in dirs[:50]:
+            assert call3(R.ref_offset_ray_origin, f3(p), f3(d)) == call3(O.orc_offset_ray_origin, f3(p), f3(d))
+    for a, b in ((1.0, 0.0), (0.0, 0.0), (3.0, -0.0), (1.0, 3.0), (-2.5, 1e-30)):
+        assert bits([R.ref_safe_div(a, b)]) == bits([O.orc_safe_div(a, b)])
+
+
+def test_sampling_transforms(libs):
+    R, O = libs
+    rng = np.random.default_rng(3)
+    F2 = C.c_float * 2
+    xis = [rng.random(2).astype(np.float32) for _ in range(3000)] + [np.array(v, np.float32) for v in ((0, 0), (1, 1), (0.5, 0.5), (0, 1), (0.25, 0.75), (0.5, 0.25))]
+    for xi in xis:
+        x = F2(*xi)
+        assert call3(R.ref_sample_hemisphere, x) == call3(O.orc_sample_hemisphere, x)
+        rad = (rng.random(3) * 2).astype(np.float32)
+        assert call3(R.ref_sample_sphere, x, f3(rad)) == call3(O.orc_sample_sphere, x, f3(rad))
+        r2 = F2(*rad[:2])
+        assert call3(R.ref_sample_disk, x, r2, n=2) == call3(O.orc_sample_disk, x, r2, n=2)
+        assert call3(R.ref_fis_gauss, x, n=2) == call3(O.orc_fis_gauss, x, n=2)
+
+
+def test_colormaps(libs):
+    R, O = libs
+    for fn in (R.ref_colormap, O.orc_colormap):
+        fn.argtypes = [C.c_int, C.c_float, C.c_void_p]
+    for t in list(np.linspace(0, 1, 513, dtype=np.float32)) + [np.float32(-0.5), np.float32(1.5)]:
+        for ref_id, orc_id in ((0, 0), (3, 3)):                      # viridis (Opacity AOV), inferno (Bounces AOV): the two the path uses
+            a, b = F3(), F3()
+            R.ref_colormap(ref_id, float(t), a); O.orc_colormap(orc_id, float(t), b)
+            assert bits(a[:]) == bits(b[:]), (ref_id, t)
+
+
+def test_volume_and_roulette_helpers(libs):
+    R, O = libs
+    for L, pre in ((R, "ref_"), (O, "orc_")):
+        getattr(L, pre + "sample_distance").restype = C.c_float
+        getattr(L, pre + "sample_distance").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+        getattr(L, pre + "sample_hg_cos").restype = C.c_float
+        getattr(L, pre + "sample_hg_cos").argtypes = [C.c_float, C.c_float]
+        getattr(L, pre + "sample_volume_scattering_direction").argtypes = [C.c_void_p, C.c_float, C.c_void_p]
+        getattr(L, pre + "russian_roulette").argtypes = [C.c_float, C.c_void_p, C.c_float]
+    rng = np.random.default_rng(4)
+    for k in range(3000):
+        albedo, thr, sig = (rng.random(3).astype(np.float32) for _ in range(3))
+        if k % 50 == 0:
+            thr = np.zeros(3, np.float32)                                           # the `sum <= 1e-9` branch
+        xi = float(np.float32(rng.random()))
+        pr, po = F3(), F3()
+        a = R.ref_sample_distance(f3(albedo), f3(thr), f3(sig), xi, pr)
+        b = O.orc_sample_distance(f3(albedo), f3(thr), f3(sig), xi, po)
+        assert bits([a]) == bits([b]) and bits(pr[:]) == bits(po[:])
+        g = float(np.float32(rng.uniform(-0.95, 0.95))) if k % 7 else float(np.float32(rng.uniform(-1e-3, 1e-3)))
+        assert bits([R.ref_sample_hg_cos(xi, g)]) == bits([O.orc_sample_hg_cos(xi, g)])
+        d = unit(rng.normal(size=3))
+        dr, do = f3(d), f3(d)
+        x2 = (C.c_float * 2)(*rng.random(2).astype(np.float32))
+        R.ref_sample_volume_scattering_direction(x2, g, dr); O.orc_sample_volume_scattering_direction(x2, g, do)
+        assert bits(dr[:]) == bits(do[:])
+        tr, to = f3(thr * 2), f3(thr * 2)
+        inv = float(np.float32(rng.uniform(0.2, 1.0)))
+        assert R.ref_russian_roulette(xi, tr, inv) == O.orc_russian_roulette(xi, to, inv) and bits(tr[:]) == bits(to[:])
+
+
+def test_payload_bitfield(libs):
+    R, O = libs
+    for L, pre in ((R, "ref_"), (O, "orc_")):
+        for n in ("payload_get_medium_idx", "payload_set_medium_idx", "payload_increment_walk", "payload_get_walk"):
+            getattr(L, pre + n).restype = C.c_uint32
+    rng = np.random.default_rng(5)
+    vals = [int(x) for x in rng.integers(0, 2 ** 32, 3000, dtype=np.uint64)] + [0, 0xFFFFFFFF, 0x00FFF000, 0x00FFE000, 0x0F000000, 0x00000FFF]
+    for v in vals:
+        v32 = C.c_uint32(v)
+        for mss in (0, 2):
+            assert R.ref_payload_get_medium_idx(v32, mss) == O.orc_payload_get_medium_idx(v32, mss)
+        for idx in (0, 1, 2, 15, 16, 255, 300):
+            assert R.ref_payload_set_medium_idx(v32, C.c_uint32(idx)) == O.orc_payload_set_medium_idx(v32, C.c_uint32(idx))
+        assert R.ref_payload_increment_walk(v32) == O.orc_payload_increment_walk(v32)
+        assert R.ref_payload_get_walk(v32) == O.orc_payload_get_walk(v32)
+
+
+def test_dome_and_texture_helpers(libs):
+    R, O = libs
+    R.ref_apply_wrap_and_crop.restype = O.orc_apply_wrap_and_crop.restype = C.c_float
+    R.ref_apply_wrap_and_crop.argtypes = O.orc_apply_wrap_and_crop.argtypes = [C.c_float, C.c_int, C.c_int]
+    rng = np.random.default_rng(6)
+    for k in range(3000):
+        q = unit(rng.normal(size=4)); d = unit(rng.normal(size=3))
+        q4 = (C.c_float * 4)(*q)
+        assert call3(R.ref_quat_rotate_dir, q4, f3(d)) == call3(O.orc_quat_rotate_dir, q4, f3(d))
+        assert call3(R.ref_dome_light_uv, f3(d), n=2) == call3(O.orc_dome_light_uv, f3(d), n=2)
+        coord = float(np.float32(rng.uniform(-3, 3)))
+        for wrap in (0, 1, 2):                                                  # clamp, repeat, mirrored repeat (clip is decided by the caller)
+            for res in (1, 7, 64):
+                assert bits([R.ref_apply_wrap_and_crop(coord, wrap, res)]) == bits([O.orc_apply_wrap_and_crop(coord, wrap, res)])
+        gn = unit(rng.normal(size=3)); n = unit(gn + 0.4 * rng.normal(size=3)); w = unit(rng.normal(size=3))
+        assert call3(R.ref_mdl_adapt_normal, f3(w), f3(gn), f3(n)) == call3(O.orc_mdl_adapt_normal, f3(w), f3(gn), f3(n))
+    for d in ((0, 1, 0), (0, -1, 0), (1, 0, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1)):
+        assert call3(R.ref_dome_light_uv, f3(d), n=2) == call3(O.orc_dome_light_uv, f3(d), n=2)
+
+
+LIGHT_DT = {
+    "sphere": np.dtype([("pos", "3f4"), ("dsp", "u4"), ("emission", "3f4"), ("area", "f4"), ("radius", "3f4"), ("pad", "f4")]),
+    "distant": np.dtype([("dir", "3f4"), ("angle", "f4"), ("emission", "3f4"), ("dsp", "u4"), ("pad", "3f4"), ("invPdf", "f4")]),
+    "rect": np.dtype([("origin", "3f4"), ("width", "f4"), ("emission", "3f4"), ("height", "f4"), ("frame", "2u4"), ("dsp", "u4"), ("pad", "f4")]),
+    "disk": np.dtype([("origin", "3f4"), ("rx", "f4"), ("emission", "3f4"), ("ry", "f4"), ("frame", "2u4"), ("dsp", "u4"), ("pad", "f4")]),
+}
+
+
+def test_sample_light(libs):
+    """rp_main.chit:30-129 with every light type, light selection by k4.x / k4.y, zero-area lights, the distant light's cone."""
+    R, O = libs
+    assert [R.ref_struct_sizes(i) for i in range(4)] == [48, 48, 48, 48] == [LIGHT_DT[k].itemsize for k in ("sphere", "distant", "rect", "disk")]
+    O.orc_encode_direction.restype = C.c_uint32
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        counts = rng.integers(0, 4, 4).astype(np.uint32)
+        if counts.sum() == 0:
+            counts[trial % 4] = 1
+        sp = np.zeros(max(counts[0], 1), LIGHT_DT["sphere"]); di = np.zeros(max(counts[1], 1), LIGHT_DT["distant"])
+        re = np.zeros(max(counts[2], 1), LIGHT_DT["rect"]); dk = np.zeros(max(counts[3], 1), LIGHT_DT["disk"])
+        for a in (sp, di, re, dk):
+            a["emission"] = rng.random((len(a), 3)) * 10
+            a["dsp"] = rng.integers(0, 2 ** 32, len(a), dtype=np.uint64).astype(np.uint32)
+        sp["pos"] = rng.normal(size=(len(sp), 3)); sp["radius"] = rng.random((len(sp), 3)) * 0.3; sp["area"] = rng.random(len(sp)) * (rng.random(len(sp)) > 0.2)
+        di["dir"] = [unit(rng.normal(size=3)) for _ in di]; di["angle"] = rng.random(len(di)) * 0.2 * (rng.random(len(di)) > 0.3); di["invPdf"] = rng.random(len(di)) + 0.5
+        for a in (re, dk):
+            a["origin"] = rng.normal(size=(len(a), 3))
+            a["frame"] = [[O.orc_encode_direction(f3(unit(rng.normal(size=3)))) for _ in range(2)] for _ in a]
+        re["width"] = rng.random(len(re)) * (rng.random(len(re)) > 0.2); re["height"] = rng.random(len(re))
+        dk["rx"] = rng.random(len(dk)) * (rng.random(len(dk)) > 0.2); dk["ry"] = rng.random(len(dk))
+        cnt = (C.c_uint32 * 4)(*[int(c) for c in counts])
+        mult, expo = float(np.float32(rng.uniform(0.5, 2))), float(np.float32(rng.uniform(-1, 1)))
+        for k in range(200):
+            k4 = (C.c_float * 4)(*rng.random(4).astype(np.float32))
+            if k < 8:
+                k4[0] = (0.0, 1.0)[k & 1]; k4[1] = (0.0, 1.0)[(k >> 1) & 1]; k4[2] = (0.0, 0.5)[(k >> 2) & 1]
+            pos = f3(rng.normal(size=3).astype(np.float32))
+            outs = []
+            for fn in (R.ref_sample_light, O.orc_sample_light):
+                fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                o8 = (C.c_float * 8)(); dsp = C.c_uint32(0)
+                fn(cnt, sp.ctypes.data, di.ctypes.data, re.ctypes.data, dk.ctypes.data, mult, expo, k4, pos, o8, C.byref(dsp))
+                outs.append((bits(o8[:]), dsp.value))
+            assert outs[0] == outs[1], (trial, k, list(counts), list(k4))
+
+
+def test_camera_rays(libs):
+    """rp_main.rgen:191-288, the head of main(): pixel -> camera ray with the RNG draws of jittering / Gauss filter importance sampling /
+    depth of field, the zero-component guard and the clip range along the ray -- compiled once per set of pipeline switches -- against
+    the oracle's camera_ray + clip_range_along, fed with the uniform values the oracle derives from the camera (Gi.cpp:2373-2423)."""
+    import dataclasses
+    from gatling_b200 import scenes
+    R, O = libs
+    d = scenes.cornell(37, 23, spp=1)
+    cams = [d.camera,
+            dataclasses.replace(d.camera, fStop=1.4, focalLength=50.0, focusDistance=2.5, clipStart=0.3, clipEnd=40.0),
+            dataclasses.replace(d.camera, position=(0.3, -2.0, 0.5), forward=(0.0, 1.0, 0.0), up=(0.0, 0.0, 1.0), vfov=1.2, fStop=0.0)]   # axis-aligned: zero direction components
+    for cam in cams:
+        for flags, (jit, fis, dof) in ((0, (0, 0, 0)), (1, (1, 0, 0)), (3, (1, 1, 0)), (7, (1, 1, 1)), (4, (0, 0, 1))):
+            dd = dataclasses.replace(d, camera=cam, settings=dataclasses.replace(d.settings, jitteredSampling=bool(jit), filterImportanceSampling=bool(fis), depthOfField=bool(dof)))
+            r = orc.OracleScene.render_desc(type("S", (), {"desc": dd})())
+            cam12 = (C.c_float * 12)(); bits2 = (C.c_uint32 * 2)()
+            O.orc_camera_ubo(C.byref(r), cam12, bits2)
+            for sample in (0, 5):
+                for py in range(0, dd.height, 3):
+                    for px in range(0, dd.width, 2):
+                        a, b = (C.c_float * 8)(), (C.c_float * 8)()
+                        ra, rb = C.c_uint32(0), C.c_uint32(0)
+                        assert R.ref_camera_ray(flags, cam12, bits2, sample, px, py, a, C.byref(ra)) == 1
+                        O.orc_camera_ray_full(C.byref(r), sample, px, py, b, C.byref(rb))
+                        assert bits(a[:]) == bits(b[:]) and ra.value == rb.value, (flags, sample, px, py, list(a), list(b))
+
+
+def test_shading_state(libs):
+    """mdl_shading_state.glsl (whole file): interpolation of the packed vertices, normal / tangent decoding, transforms through the instance
+    matrices, the front-face flip, re-orthonormalised tangent frame and uv -- at random hits of every instance of scenes with rotated,
+    scaled and mirrored instances -- against the oracle's setup_shading_state on the same packed buffers."""
+    from gatling_b200 import scenes
+    R, O = libs
+    O.orc_scene_views.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    O.orc_setup_shading_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.ref_setup_shading_state.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(9)
+    mirrored = scenes.cornell(8, 8, spp=1)
+    m0 = np.asarray(mirrored.meshes[-1].transform, np.float32).copy(); m0[0, :3] *= -1.0          # a left-handed instance
+    mirrored.meshes[-1].transform = m0
+    checked = 0
+    for d in (scenes.cornell(8, 8, spp=1), mirrored, scenes.kitchen_standin(tris_per_instance=60, instances=9, meshes=5, materials=4, width=8, height=8, spp=1),
+              scenes.textured_cornell(8, 8, spp=1)):
+        o = orc.OracleScene(d)
+        h = o.handle
+        faces, fverts = C.c_void_p(), C.c_void_p()
+        bases = (C.c_uint32 * 3)(); o2w, w2o = (C.c_float * 12)(), (C.c_float * 12)(); count = C.c_uint32(0)
+        O.orc_scene_views(h, 0, C.byref(faces), C.byref(fverts), bases, o2w, w2o, C.byref(count))
+        for inst in range(count.value):
+            O.orc_scene_views(h, inst, C.byref(faces), C.byref(fverts), bases, o2w, w2o, C.byref(count))
+            mesh_faces = C.c_void_p(faces.value + 12 * bases[1])
+            for _ in range(40):
+                prim = int(rng.integers(0, bases[2]))
+                u = float(np.float32(rng.random())); v = float(np.float32(rng.random() * (1.0 - u)))
+                if _ < 3:
+                    u, v = ((0.0, 0.0), (1.0, 0.0), (0.0, 1.0))[_]
+                ray = f3(unit(rng.normal(size=3)))
+                a, b = (C.c_float * 18)(), (C.c_float * 18)()
+                fa, fb = C.c_int(0), C.c_int32(0)
+                R.ref_setup_shading_state(mesh_faces, fverts, bases[0], o2w, w2o, prim, u, v, ray, a, C.byref(fa))
+                O.orc_setup_shading_state(h, inst, prim, u, v, ray, b, C.byref(fb))
+                assert fa.value == fb.value and bits(a[:]) == bits(b[:]), (d.name, inst, prim, u, v, list(a), list(b))
+                checked += 1
+        o.close()
+    assert checked > 1000
