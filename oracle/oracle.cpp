@@ -10,10 +10,13 @@
 // sampleLight, the volume / roulette helpers, the payload bit field, the dome-light mapping, texture wrapping,
 // mdl_adapt_normal, the whole of mdl_shading_state.glsl and the camera-ray head of rp_main.rgen's main() --
 // which oracle/ref_glsl/build_ref.py compiles AS C++ FROM THE REFERENCE'S OWN FILES into oracle/_ref/ and
-// tests/test_reference_glsl_cpu.py compares bit for bit with the functions below, and (2) the one golden image
-// small enough to reconstruct from its LFS pointer (tests/test_reference_pin.py).  UNPINNED remain the bodies of
-// the closest-hit / miss / ray-generation main() functions around those calls and the BSDF arithmetic (closed MDL
-// SDK).  The file follows the reference *source text* line by line where the source is in
+// tests/test_reference_glsl_cpu.py compares bit for bit with the functions below; (1b) the main() functions of
+// rp_main.rgen / .chit / .miss / _shadow.miss themselves, compiled the same way into a CPU renderer that calls
+// back here only for ray queries, the material's mdl_* entry points and the dome texture: its images equal
+// orc_render's bit for bit on every test scene (test_reference_integrator_*); and (2) the one golden image
+// small enough to reconstruct from its LFS pointer (tests/test_reference_pin.py).  UNPINNED remain the any-hit
+// decision (ORACLE_DEVIATIONS #10), the auxiliary-AOV writes and the BSDF arithmetic (closed MDL SDK).
+// The file follows the reference *source text* line by line where the source is in
 // tree (integrator: rp_main.rgen / rp_main.chit / rp_main.miss / rp_main_shadow.miss, common.glsl,
 // mdl_shading_state.glsl, Gi.cpp host encoders) and restates published definitions where the
 // arithmetic lives in third-party binaries (BSDF bodies: orc_bsdf.h; traversal: orc_scene.h).
@@ -358,22 +361,13 @@ static inline void sampleLight(const RenderCtx& c, V4 k4, V3 surfacePos, V3& dir
   invPdf *= (float) ubo.totalLightCount;                                                       // :128
 }
 
-// rp_main.chit:132-493 (MEDIUM_STACK_SIZE == 0; AOV section :191-290 handled by the caller for Color only)
-static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, const Hit& hit, V3 worldRayDir, AovSample* aov)
+// R15: textured / primvar-driven inputs are evaluated once per hit into a private copy of the parameter block (the reference
+// re-evaluates them inside every generated mdl_* function; same values).  Returns the mapped shading normal when a normal map is bound.
+static inline void material_at_hit(const Scene& s, const InstanceDesc& in, const Hit& hit, const State& st, V3 worldRayDir, const Material& base,
+                                   Material& mat, V3& mappedNormal, bool& hasMappedNormal)
 {
-  const Scene& s = *c.s;
-  const InstanceDesc& in = s.instances[hit.inst];
-  bool isLeftHanded = (in.flags & 1u) != 0;                               // :137
-  bool isDoubleSided = (in.flags & 2u) != 0;                              // :138
-  const Material& base = s.materials[in.material];
-
-  State st; bool isFrontFace;
-  setup_shading_state(s, hit, worldRayDir, st, isFrontFace);              // :143
-  const V3 normal = st.normal;                                            // :147
-  // R15: textured inputs are evaluated once per hit into a private copy of the parameter block (the reference
-  // re-evaluates them inside every generated mdl_* function; same values)
-  Material mat = base;
-  V3 mappedNormal = normal; bool hasMappedNormal = false;
+  mat = base;
+  mappedNormal = st.normal; hasMappedNormal = false;
   if (!s.materialPrimvars.empty() && !s.materialPrimvars[in.material].empty() && !s.primvarInfos.empty()) {   // scene_data_lookup_float{,2,3}
     const std::vector<GtlcPrimvarBinding>& pbs = s.materialPrimvars[in.material];
     const V3 bc = v3((1.0f - hit.u) - hit.v, hit.u, hit.v);                                     // mdl_interface.glsl:318
@@ -403,6 +397,23 @@ static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, co
   if (!s.materialTextures.empty() && !s.materialTextures[in.material].empty())
     hasMappedNormal = apply_texture_bindings(s.textures, s.materialTextures[in.material], st.text_coords.x, st.text_coords.y, st.local_position, worldRayDir,
                                              st.geom_normal, st.normal, st.tangent_u, st.tangent_v, mat.p, mappedNormal);
+
+}
+
+// rp_main.chit:132-493 (MEDIUM_STACK_SIZE == 0; AOV section :191-290 handled by the caller for Color only)
+static inline void closest_hit_shader(const RenderCtx& c, ShadeRayPayload& p, const Hit& hit, V3 worldRayDir, AovSample* aov)
+{
+  const Scene& s = *c.s;
+  const InstanceDesc& in = s.instances[hit.inst];
+  bool isLeftHanded = (in.flags & 1u) != 0;                               // :137
+  bool isDoubleSided = (in.flags & 2u) != 0;                              // :138
+  const Material& base = s.materials[in.material];
+
+  State st; bool isFrontFace;
+  setup_shading_state(s, hit, worldRayDir, st, isFrontFace);              // :143
+  const V3 normal = st.normal;                                            // :147
+  Material mat; V3 mappedNormal; bool hasMappedNormal;
+  material_at_hit(s, in, hit, st, worldRayDir, base, mat, mappedNormal, hasMappedNormal);
 
   V3 throughput = p.throughput;
   V3 radiance = p.radiance;
@@ -997,6 +1008,102 @@ void orc_setup_shading_state(void* h, uint32_t inst, uint32_t prim, float u, flo
   const V3 f[6] = { st.normal, st.geom_normal, st.position, st.tangent_u, st.tangent_v, st.text_coords };
   for (int k = 0; k < 6; k++) { out18[3 * k] = f[k].x; out18[3 * k + 1] = f[k].y; out18[3 * k + 2] = f[k].z; }
   *frontFace = ff ? 1 : 0;
+}
+// ---- entry points for the reference's integrator compiled from its own shader sources (oracle/ref_glsl/ref_pipeline.inc) ----
+// That build runs rp_main.rgen / .chit / .miss as C++ and calls back here for everything the reference gets from outside its shader
+// text: ray queries against the scene (the Vulkan driver), the material's generated mdl_* functions (MDL SDK) and the dome texture.
+struct HitCtx { const Scene* s; const InstanceDesc* in; Material mat; State st; V3 mappedNormal; bool hasMappedNormal; };
+static thread_local HitCtx g_hitCtx;
+static inline State state_from(const float* f, const HitCtx& h)
+{
+  State st = h.st;                       // local_position etc. from the oracle; the six vectors the shader code owns from the caller
+  st.normal = v3(f[0], f[1], f[2]); st.geom_normal = v3(f[3], f[4], f[5]); st.position = v3(f[6], f[7], f[8]);
+  st.tangent_u = v3(f[9], f[10], f[11]); st.tangent_v = v3(f[12], f[13], f[14]); st.text_coords = v3(f[15], f[16], f[17]);
+  return st;
+}
+int orc_trace_one(void* h, const float* o, const float* d, float tMin, float tMax, int anyHit, uint32_t seed, float* tuv, uint32_t* primInst)
+{
+  Hit hit;
+  const bool found = scene_trace(*(const Scene*) h, v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]), tMin, tMax, anyHit != 0, hit, seed);
+  tuv[0] = hit.t; tuv[1] = hit.u; tuv[2] = hit.v; primInst[0] = hit.prim; primInst[1] = hit.inst;
+  return found ? 1 : 0;
+}
+// flags: bit 0 thin-walled, 1 emissive, 2 left-handed instance, 3 double-sided instance, 4 a normal map is bound
+uint32_t orc_hit_begin(void* h, uint32_t inst, uint32_t prim, float u, float v, const float* worldRayDir)
+{
+  HitCtx& c = g_hitCtx;
+  c.s = (const Scene*) h; c.in = &c.s->instances[inst];
+  Hit hit; hit.t = 1.0f; hit.u = u; hit.v = v; hit.prim = prim; hit.inst = inst;
+  bool ff; const V3 wd = v3(worldRayDir[0], worldRayDir[1], worldRayDir[2]);
+  setup_shading_state(*c.s, hit, wd, c.st, ff);
+  const Material& base = c.s->materials[c.in->material];
+  material_at_hit(*c.s, *c.in, hit, c.st, wd, base, c.mat, c.mappedNormal, c.hasMappedNormal);
+  return (mat_is_thin_walled(base) ? 1u : 0u) | (mat_is_emissive(c.mat) ? 2u : 0u) | ((c.in->flags & 1u) ? 4u : 0u) | ((c.in->flags & 2u) ? 8u : 0u) | (c.hasMappedNormal ? 16u : 0u);
+}
+void orc_hit_mapped_normal(float* n) { n[0] = g_hitCtx.mappedNormal.x; n[1] = g_hitCtx.mappedNormal.y; n[2] = g_hitCtx.mappedNormal.z; }
+void orc_hit_volume(float* sigma_a, float* sigma_s, float* ior, float* bias)
+{
+  const Material& m = g_hitCtx.mat;
+  const V3 a = mat_volume_absorption(m), sc = mat_volume_scattering(m), i = mat_ior(m);
+  sigma_a[0] = a.x; sigma_a[1] = a.y; sigma_a[2] = a.z; sigma_s[0] = sc.x; sigma_s[1] = sc.y; sigma_s[2] = sc.z; ior[0] = i.x; ior[1] = i.y; ior[2] = i.z;
+  *bias = mat_directional_bias(m);
+}
+void orc_hit_bsdf_sample(const float* state18, const float* ior1, const float* ior2, const float* k1, const float* xi, float* k2, float* pdf, float* bsdfOverPdf, int32_t* eventType)
+{
+  BsdfSampleData d; d.ior1 = v3(ior1[0], ior1[1], ior1[2]); d.ior2 = v3(ior2[0], ior2[1], ior2[2]); d.k1 = v3(k1[0], k1[1], k1[2]);
+  d.xi = v4(xi[0], xi[1], xi[2], xi[3]); d.k2 = v3(0.0f); d.pdf = 0.0f; d.bsdf_over_pdf = v3(0.0f); d.event_type = 0;
+  bsdf_sample(g_hitCtx.mat, d, state_from(state18, g_hitCtx));
+  k2[0] = d.k2.x; k2[1] = d.k2.y; k2[2] = d.k2.z; *pdf = d.pdf; bsdfOverPdf[0] = d.bsdf_over_pdf.x; bsdfOverPdf[1] = d.bsdf_over_pdf.y; bsdfOverPdf[2] = d.bsdf_over_pdf.z; *eventType = d.event_type;
+}
+void orc_hit_bsdf_evaluate(const float* state18, const float* ior1, const float* ior2, const float* k1, const float* k2, float* diffuse, float* glossy, float* pdf)
+{
+  BsdfEvaluateData e; e.ior1 = v3(ior1[0], ior1[1], ior1[2]); e.ior2 = v3(ior2[0], ior2[1], ior2[2]); e.k1 = v3(k1[0], k1[1], k1[2]); e.k2 = v3(k2[0], k2[1], k2[2]);
+  e.bsdf_diffuse = v3(0.0f); e.bsdf_glossy = v3(0.0f); e.pdf = 0.0f;
+  bsdf_evaluate(g_hitCtx.mat, e, state_from(state18, g_hitCtx));
+  diffuse[0] = e.bsdf_diffuse.x; diffuse[1] = e.bsdf_diffuse.y; diffuse[2] = e.bsdf_diffuse.z; glossy[0] = e.bsdf_glossy.x; glossy[1] = e.bsdf_glossy.y; glossy[2] = e.bsdf_glossy.z; *pdf = e.pdf;
+}
+void orc_hit_bsdf_albedo(const float* state18, const float* k1, float* albedo)
+{
+  const V3 a = bsdf_albedo(g_hitCtx.mat, v3(k1[0], k1[1], k1[2]), state_from(state18, g_hitCtx));
+  albedo[0] = a.x; albedo[1] = a.y; albedo[2] = a.z;
+}
+void orc_hit_edf(const float* state18, const float* k1, float* edf, float* pdf, float* cosOut, float* intensity)
+{
+  EdfEvaluateData e; e.k1 = v3(k1[0], k1[1], k1[2]); e.pdf = 0.0f; e.edf = v3(0.0f); e.cos = 0.0f;
+  if (mat_is_emissive(g_hitCtx.mat)) edf_evaluate(e, state_from(state18, g_hitCtx));
+  const V3 i = mat_emission_intensity(g_hitCtx.mat);
+  edf[0] = e.edf.x; edf[1] = e.edf.y; edf[2] = e.edf.z; *pdf = e.pdf; *cosOut = e.cos; intensity[0] = i.x; intensity[1] = i.y; intensity[2] = i.z;
+}
+// The image behind textures_2d[domeLightIndex] at (u, v): index 0 = the 1x1 fallback holding the clear colour, 1 = the dome light's lat-long image
+void orc_dome_fetch(void* h, const OrcRenderDesc* r, uint32_t domeLightIndex, float u, float v, float* rgb)
+{
+  const Scene* s = (const Scene*) h;
+  V3 c;
+  if (domeLightIndex == 0 || s->domeTexels.empty()) {
+    c.x = (float)(uint8_t)(r->clearColor[0] * 255.0f) / 255.0f; c.y = (float)(uint8_t)(r->clearColor[1] * 255.0f) / 255.0f; c.z = (float)(uint8_t)(r->clearColor[2] * 255.0f) / 255.0f;
+  } else c = texture_latlong(*s, u, v);
+  rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
+}
+// Every UniformData value the shaders read, as Gi.cpp:2373-2423 fills them: 28 floats then 16 uints (see ref_exports.cpp ref_set_ubo)
+void orc_ubo_values(void* h, const OrcRenderDesc* r, float* f, uint32_t* u)
+{
+  RenderCtx c; fill_ctx(c, (const Scene*) h, r);
+  const Ubo& b = c.ubo;
+  const float fv[28] = { b.domeLightRotation[0], b.domeLightRotation[1], b.domeLightRotation[2], b.domeLightRotation[3],
+                         b.domeLightEmissionMultiplier.x, b.domeLightEmissionMultiplier.y, b.domeLightEmissionMultiplier.z, b.metersPerSceneUnit,
+                         b.cameraPosition.x, b.cameraPosition.y, b.cameraPosition.z, b.cameraForward.x, b.cameraForward.y, b.cameraForward.z,
+                         b.cameraUp.x, b.cameraUp.y, b.cameraUp.z, b.focusDistance, b.cameraVFoV, b.lensRadius, b.invTotalSampleCount, b.maxSampleValue,
+                         b.rrInvMinTermProb, b.lightIntensityMultiplier, b.sensorExposure, 0.0f, 0.0f, 0.0f };
+  const uint32_t uv[16] = { b.sphereLightCount, b.distantLightCount, b.rectLightCount, b.diskLightCount, b.totalLightCount, b.maxVolumeWalkLength, b.imageDims,
+                            b.sampleOffset, b.spp, b.maxBouncesAndRrBounceOffset, b.clipRangePacked, c.mediumStackSize,
+                            (uint32_t) ((c.fl.jittered ? 1 : 0) | (c.fl.fis ? 2 : 0) | (c.fl.dof ? 4 : 0) | (c.fl.nee ? 8 : 0) | (c.fl.clipping ? 16 : 0) | (c.fl.progressive ? 32 : 0) | (c.fl.domeCameraVisible ? 64 : 0)), 0u, 0u, 0u };
+  memcpy(f, fv, sizeof(fv)); memcpy(u, uv, sizeof(uv));
+}
+// The light buffers as the shaders see them (interface/rp_main.h layouts, 48 bytes per light)
+void orc_light_buffers(void* h, const void** spheres, const void** distants, const void** rects, const void** disks)
+{
+  const Scene* s = (const Scene*) h;
+  *spheres = s->sphereLights.data(); *distants = s->distantLights.data(); *rects = s->rectLights.data(); *disks = s->diskLights.data();
 }
 // (function-level entry points for tests/test_reference_glsl_cpu.py: the same functions, compiled from the reference's own sources)
 void orc_rng_next4f(uint32_t* state, float* o) { V4 r = rng1d_next4f(*state); o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; }

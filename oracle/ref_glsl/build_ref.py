@@ -32,6 +32,10 @@ FRAGMENTS = [
     ("rp_main.rgen", 48, 130, "rgen_functions.inc"),           # sampleDistance .. fisGauss
     ("rp_main.rgen", 191, 288, "rgen_camera.inc"),             # main(): pixel -> camera ray, RNG draws, clip range (leaves the sample loop open)
     ("mdl_shading_state.glsl", None, None, "mdl_shading_state.glsl"),
+    ("rp_main.rgen", 185, 521, "rgen_main.inc"),               # main(): the whole ray-generation shader
+    ("rp_main.chit", 132, 493, "chit_main.inc"),               # main(): the whole closest-hit shader
+    ("rp_main.miss", 15, 87, "miss_all.inc"),                  # stepVolume, quatRotateDir, sampleDomeLight, main()
+    ("rp_main_shadow.miss", 14, 17, "shadow_miss_main.inc"),   # main()
     ("rp_main.chit", 29, 131, "chit_sample_light.inc"),        # sampleLight
     ("rp_main.miss", 36, 53, "miss_functions.inc"),            # quatRotateDir, sampleDomeLight
     ("mdl_interface.glsl", 8, 38, "mdl_wrap.inc"),             # apply_wrap_and_crop

@@ -90,7 +90,9 @@ struct mat3 { float m[12]; mat3() {} explicit mat3(const mat4x3& a) { for (int i
   static inline V& operator*=(V& a, float s) { a = a * s; return a; }                                              \
   static inline V& operator/=(V& a, float s) { a = a / s; return a; }                                              \
   static inline V abs(V a) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = fabsf((&a.x)[i]); return r; }            \
-  static inline V max(V a, float s) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = fmaxf((&a.x)[i], s); return r; }
+  static inline V max(V a, float s) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = fmaxf((&a.x)[i], s); return r; }            \
+  static inline V max(V a, V b) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = fmaxf((&a.x)[i], (&b.x)[i]); return r; }        \
+  static inline V exp(V a) { V r; for (int i = 0; i < N; i++) (&r.x)[i] = expf((&a.x)[i]); return r; }
 GLSL_VEC_OPS(vec2, 2)
 GLSL_VEC_OPS(vec3, 3)
 GLSL_VEC_OPS(vec4, 4)
@@ -117,6 +119,8 @@ static inline vec3 mix(vec3 a, vec3 b, float t) { return a * (1.0f - t) + b * t;
 static inline vec3 mix(vec3 a, vec3 b, bvec3 s) { return vec3(s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z); }
 static inline ivec3 mix(ivec3 a, ivec3 b, bvec3 s) { return ivec3(s.x ? b.x : a.x, s.y ? b.y : a.y, s.z ? b.z : a.z); }
 static inline bvec3 greaterThanEqual(vec3 a, vec3 b) { bvec3 r = { a.x >= b.x, a.y >= b.y, a.z >= b.z }; return r; }
+static inline bvec3 greaterThan(vec3 a, vec3 b) { bvec3 r = { a.x > b.x, a.y > b.y, a.z > b.z }; return r; }
+static inline bool any(bvec3 a) { return a.x || a.y || a.z; }
 static inline bvec3 equal(vec3 a, vec3 b) { bvec3 r = { a.x == b.x, a.y == b.y, a.z == b.z }; return r; }
 static inline bvec2 notEqual(vec2 a, vec2 b) { bvec2 r = { a.x != b.x, a.y != b.y }; return r; }
 static inline bool all(bvec2 a) { return a.x && a.y; }

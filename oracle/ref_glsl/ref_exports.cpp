@@ -12,11 +12,9 @@ static DistantLight distantLights[16];
 static RectLight rectLights[16];
 static DiskLight diskLights[16];
 static vec3 gl_WorldRayDirectionEXT;
-// rp_main.miss:46-53 reads the dome-light image; the stand-in returns the lat-long coordinate it was asked for
-static int textures_2d[4], tex_sampler;
+static int tex_sampler;
 static inline int sampler2D(int, int) { return 0; }
 #define nonuniformEXT(x) (x)
-static inline vec4 textureLod(int, vec2 uv, uint) { return vec4(uv.x, uv.y, 0.0f, 1.0f); }
 
 // mdl_shading_state.glsl reads the hit mesh through buffer references and the ray-tracing built-ins; the stand-ins point at test arrays
 static BlasPayload blas_payloads[1];
@@ -34,9 +32,16 @@ static inline void clearAovs(uint) {}
 #include "mdl_types.glsl"
 #include "mdl_wrap.inc"
 #include "mdl_adapt_normal.inc"
+// function-level copies for the per-function tests (the whole-pipeline builds further down bring their own, in their namespaces)
+namespace fn {
+// rp_main.miss:46-53 reads the dome-light image; the stand-in returns the lat-long coordinate it was asked for
+static int textures_2d[4];
+static inline vec4 textureLod(int, vec2 uv, uint) { return vec4(uv.x, uv.y, 0.0f, 1.0f); }
 #include "miss_functions.inc"
 #define NEXT_EVENT_ESTIMATION
 #include "chit_sample_light.inc"
+#undef NEXT_EVENT_ESTIMATION
+}
 namespace mss2 {
 #define MEDIUM_STACK_SIZE 2
 #include "rp_main_payload.glsl"
@@ -90,6 +95,59 @@ CAMERA_VARIANT_END
 #undef DEPTH_OF_FIELD
 #undef MEDIUM_STACK_SIZE
 
+// ---- the whole integrator: rp_main.rgen / .chit / .miss / _shadow.miss as C++ (ref_pipeline.inc), driven through a callback table ----
+struct RefCallbacks {
+  void* scene; const void* renderDesc;
+  int (*trace)(void* scene, const float* o, const float* d, float tMin, float tMax, int anyHit, uint seed, float* tuv, uint* primInst);
+  void (*views)(void* scene, uint inst, const uint** faces, const void** fverts, uint* bases3, float* o2w12, float* w2o12, uint* instCount);
+  uint (*hitBegin)(void* scene, uint inst, uint prim, float u, float v, const float* worldRayDir);
+  void (*mappedNormal)(float* n);
+  void (*volume)(float* sigma_a, float* sigma_s, float* ior, float* bias);
+  void (*bsdfSample)(const float* state18, const float* ior1, const float* ior2, const float* k1, const float* xi, float* k2, float* pdf, float* bsdfOverPdf, int* eventType);
+  void (*bsdfEvaluate)(const float* state18, const float* ior1, const float* ior2, const float* k1, const float* k2, float* diffuse, float* glossy, float* pdf);
+  void (*bsdfAlbedo)(const float* state18, const float* k1, float* albedo);
+  void (*edf)(const float* state18, const float* k1, float* edf, float* pdf, float* cosOut, float* intensity);
+  void (*dome)(void* scene, const void* renderDesc, uint domeLightIndex, float u, float v, float* rgb);
+};
+static RefCallbacks g_cb;
+static int g_domeIndex;
+static uint64_t g_rayCounts[2];
+#define IS_THIN_WALLED
+#define IS_EMISSIVE
+#define AOV_MASK AOV_BIT_COLOR
+#define NEXT_EVENT_ESTIMATION
+#define PROGRESSIVE_ACCUMULATION
+#define JITTERED_SAMPLING
+#define FILTER_IMPORTANCE_SAMPLING
+#define DOME_LIGHT_CAMERA_VISIBLE
+// the reference's default pipeline (renderDelegate.cpp:93-110) with next-event estimation, Beer-only media ...
+#define PIPE_NS pipe_default
+#define MEDIUM_STACK_SIZE 0
+#include "ref_pipeline.inc"
+#undef PIPE_NS
+#undef MEDIUM_STACK_SIZE
+// ... and with a two-deep medium stack (volume random walk)
+#define PIPE_NS pipe_media2
+#define MEDIUM_STACK_SIZE 2
+#include "ref_pipeline.inc"
+#undef PIPE_NS
+#undef MEDIUM_STACK_SIZE
+// ... and the dome light hidden from the camera, depth of field and clipping planes on, no jitter, no progressive accumulation
+#undef DOME_LIGHT_CAMERA_VISIBLE
+#undef JITTERED_SAMPLING
+#undef FILTER_IMPORTANCE_SAMPLING
+#undef PROGRESSIVE_ACCUMULATION
+#define DEPTH_OF_FIELD
+#define CLIPPING_PLANES
+#define PIPE_NS pipe_other
+#define MEDIUM_STACK_SIZE 0
+#include "ref_pipeline.inc"
+#undef PIPE_NS
+#undef MEDIUM_STACK_SIZE
+#undef DEPTH_OF_FIELD
+#undef CLIPPING_PLANES
+#undef NEXT_EVENT_ESTIMATION
+
 static inline vec3 ld3(const float* p) { return vec3(p[0], p[1], p[2]); }
 static inline void st3(float* o, vec3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
 #define EXPORT extern "C" __attribute__((visibility("default")))
@@ -124,8 +182,8 @@ EXPORT uint ref_payload_set_medium_idx(uint bitfield, uint idx) { mss2::ShadeRay
 EXPORT uint ref_payload_increment_walk(uint bitfield) { mss2::ShadeRayPayload p; p.bitfield = bitfield; mss2::shadeRayPayloadIncrementWalk(p); return p.bitfield; }
 EXPORT uint ref_payload_get_walk(uint bitfield) { mss2::ShadeRayPayload p; p.bitfield = bitfield; return mss2::shadeRayPayloadGetWalk(p); }
 // ---- rp_main.miss:39-53 ----
-EXPORT void ref_quat_rotate_dir(const float* q, const float* dir, float* o) { st3(o, quatRotateDir(vec4(q[0], q[1], q[2], q[3]), ld3(dir))); }
-EXPORT void ref_dome_light_uv(const float* rayDir, float* uv) { vec3 r = sampleDomeLight(1u, ld3(rayDir)); uv[0] = r.x; uv[1] = r.y; }
+EXPORT void ref_quat_rotate_dir(const float* q, const float* dir, float* o) { st3(o, fn::quatRotateDir(vec4(q[0], q[1], q[2], q[3]), ld3(dir))); }
+EXPORT void ref_dome_light_uv(const float* rayDir, float* uv) { vec3 r = fn::sampleDomeLight(1u, ld3(rayDir)); uv[0] = r.x; uv[1] = r.y; }
 // ---- mdl_interface.glsl:8-38, 238-256 ----
 EXPORT float ref_apply_wrap_and_crop(float coord, int wrap, int res) { return apply_wrap_and_crop(coord, wrap, vec2(0.0f, 1.0f), res); }
 EXPORT void ref_mdl_adapt_normal(const float* worldRayDir, const float* geomNormal, const float* normal, float* o)
@@ -148,7 +206,7 @@ EXPORT void ref_sample_light(const uint* counts, const void* spheres, const void
   memcpy(sphereLights, spheres, sizeof(SphereLight) * counts[0]); memcpy(distantLights, distants, sizeof(DistantLight) * counts[1]);
   memcpy(rectLights, rects, sizeof(RectLight) * counts[2]); memcpy(diskLights, disks, sizeof(DiskLight) * counts[3]);
   vec3 dirToLight, power; float dist, invPdf; uint dsp;
-  sampleLight(vec4(k4[0], k4[1], k4[2], k4[3]), ld3(surfacePos), dirToLight, dist, power, invPdf, dsp);
+  fn::sampleLight(vec4(k4[0], k4[1], k4[2], k4[3]), ld3(surfacePos), dirToLight, dist, power, invPdf, dsp);
   st3(out8, dirToLight); out8[3] = dist; st3(out8 + 4, power); out8[7] = invPdf; *diffuseSpecularPacked = dsp;
 }
 EXPORT int ref_struct_sizes(int which) { return which == 0 ? (int) sizeof(SphereLight) : which == 1 ? (int) sizeof(DistantLight) : which == 2 ? (int) sizeof(RectLight) : (int) sizeof(DiskLight); }
@@ -182,4 +240,31 @@ EXPORT void ref_setup_shading_state(const void* faces, const void* vertices, uin
   setup_mdl_shading_state(vec2(u, v), st, ff);
   st3(out18, st.normal); st3(out18 + 3, st.geom_normal); st3(out18 + 6, st.position); st3(out18 + 9, st.tangent_u[0]); st3(out18 + 12, st.tangent_v[0]); st3(out18 + 15, st.text_coords[0]);
   *frontFace = ff ? 1 : 0;
+}
+// ---- rp_main.rgen + .chit + .miss + _shadow.miss: a whole render ----
+// f28 / u16: orc_ubo_values; lights: orc_light_buffers + the counts in u16; u16[11] = medium stack size, u16[12] = switches (bit 0 jitter,
+// 1 filter importance sampling, 2 depth of field, 3 NEE, 4 clipping planes, 5 progressive, 6 dome visible to the camera).
+// rgba: width * height vec4, holds the previous ColorAov on entry when progressive.  Returns 0 if no pipeline was compiled for the switches.
+EXPORT int ref_render(const RefCallbacks* cb, const float* f28, const uint* u16, const void* spheres, const void* distants, const void* rects, const void* disks,
+                      float* rgba, uint64_t* rayCounts)
+{
+  g_cb = *cb; g_rayCounts[0] = g_rayCounts[1] = 0;
+  ubo.domeLightRotation = vec4(f28[0], f28[1], f28[2], f28[3]); ubo.domeLightEmissionMultiplier = ld3(f28 + 4); ubo.metersPerSceneUnit = f28[7];
+  ubo.cameraPosition = ld3(f28 + 8); ubo.cameraForward = ld3(f28 + 11); ubo.cameraUp = ld3(f28 + 14); ubo.focusDistance = f28[17]; ubo.cameraVFoV = f28[18];
+  ubo.lensRadius = f28[19]; ubo.invTotalSampleCount = f28[20]; ubo.maxSampleValue = f28[21]; ubo.rrInvMinTermProb = f28[22]; ubo.lightIntensityMultiplier = f28[23];
+  ubo.sensorExposure = f28[24];
+  ubo.sphereLightCount = u16[0]; ubo.distantLightCount = u16[1]; ubo.rectLightCount = u16[2]; ubo.diskLightCount = u16[3]; ubo.totalLightCount = u16[4];
+  ubo.maxVolumeWalkLength = u16[5]; ubo.imageDims = u16[6]; ubo.sampleOffset = u16[7]; ubo.spp = u16[8]; ubo.maxBouncesAndRrBounceOffset = u16[9]; ubo.clipRangePacked = u16[10];
+  memset(sphereLights, 0, sizeof(sphereLights)); memset(distantLights, 0, sizeof(distantLights)); memset(rectLights, 0, sizeof(rectLights)); memset(diskLights, 0, sizeof(diskLights));
+  if (u16[0] > 16 || u16[1] > 16 || u16[2] > 16 || u16[3] > 16) return 0;
+  memcpy(sphereLights, spheres, sizeof(SphereLight) * u16[0]); memcpy(distantLights, distants, sizeof(DistantLight) * u16[1]);
+  memcpy(rectLights, rects, sizeof(RectLight) * u16[2]); memcpy(diskLights, disks, sizeof(DiskLight) * u16[3]);
+  const uint width = u16[6] & 0xFFFFu, height = u16[6] >> 16, mss = u16[11], sw = u16[12];
+  int ok = 1;
+  if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_default::render(width, height, (vec4*) rgba);
+  else if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 2) pipe_media2::render(width, height, (vec4*) rgba);
+  else if (sw == (4u | 8u | 16u) && mss == 0) pipe_other::render(width, height, (vec4*) rgba);
+  else ok = 0;
+  rayCounts[0] = g_rayCounts[0]; rayCounts[1] = g_rayCounts[1];
+  return ok;
 }

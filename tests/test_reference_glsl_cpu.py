@@ -302,3 +302,101 @@ def test_shading_state(libs):
                 checked += 1
         o.close()
     assert checked > 1000
+
+
+# ---- the whole integrator: rp_main.rgen / .chit / .miss / _shadow.miss compiled from the reference's files -------------------------------
+class RefCallbacks(C.Structure):
+    _fields_ = [("scene", C.c_void_p), ("renderDesc", C.c_void_p)] + [(n, C.c_void_p) for n in
+                ("trace", "views", "hitBegin", "mappedNormal", "volume", "bsdfSample", "bsdfEvaluate", "bsdfAlbedo", "edf", "dome")]
+
+
+def reference_integrator_render(libs, desc, sample_offset=0, prev=None):
+    """Renders `desc` with the reference's own shader code (oracle/ref_glsl/ref_pipeline.inc): its main() functions run as C++ and call back
+    into the oracle for ray queries, the material's mdl_* entry points and the dome texture.  Returns (rgba, (closest, shadow) ray counts)."""
+    R, O = libs
+    o = orc.OracleScene(desc)
+    r = o.render_desc(sample_offset)
+    cb = RefCallbacks()
+    cb.scene, cb.renderDesc = o.handle, C.cast(C.pointer(r), C.c_void_p)
+    for field, name in (("trace", "orc_trace_one"), ("views", "orc_scene_views"), ("hitBegin", "orc_hit_begin"), ("mappedNormal", "orc_hit_mapped_normal"),
+                        ("volume", "orc_hit_volume"), ("bsdfSample", "orc_hit_bsdf_sample"), ("bsdfEvaluate", "orc_hit_bsdf_evaluate"),
+                        ("bsdfAlbedo", "orc_hit_bsdf_albedo"), ("edf", "orc_hit_edf"), ("dome", "orc_dome_fetch")):
+        setattr(cb, field, C.cast(getattr(O, name), C.c_void_p))
+    f28, u16 = (C.c_float * 28)(), (C.c_uint32 * 16)()
+    O.orc_ubo_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    O.orc_ubo_values(o.handle, C.byref(r), f28, u16)
+    lights = [C.c_void_p() for _ in range(4)]
+    O.orc_light_buffers.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    O.orc_light_buffers(o.handle, *[C.byref(p) for p in lights])
+    img = np.zeros((desc.height, desc.width, 4), np.float32) if prev is None else np.ascontiguousarray(prev, np.float32).copy()
+    counts = (C.c_uint64 * 2)()
+    R.ref_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    ok = R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts)
+    assert ok == 1, "no reference pipeline was compiled for these render settings (ref_exports.cpp)"
+    want, _, rays = o.render(sample_offset=sample_offset, prev=prev)
+    o.close()
+    return img, (int(counts[0]), int(counts[1])), want, rays
+
+
+def _lit(d):
+    import dataclasses
+    from gatling_b200 import scenes
+    d.settings = dataclasses.replace(d.settings, nextEventEstimation=True)
+    if not d.rect_lights:
+        d.rect_lights.append(scenes.RectLight(origin=(0.0, 0.0, 0.9), t0=(1, 0, 0), t1=(0, 1, 0), base_emission=(10, 10, 10), width=0.5, height=0.5))
+    return d
+
+
+def test_reference_integrator_cornell(libs):
+    """The reference's ray-generation, closest-hit, miss and shadow-miss shaders, compiled from its own files, render the Cornell box
+    (NEE on a rect light + sphere / distant / disk lights, progressive second call): the oracle's image must be the same bits, and so
+    must the ray counts."""
+    from gatling_b200 import scenes
+    d = _lit(scenes.cornell(40, 30, spp=3, max_bounces=6))
+    d.sphere_lights.append(scenes.SphereLight(position=(0.5, -0.5, 0.2), base_emission=(4, 3, 2), radius=(0.1, 0.1, 0.1)))
+    d.distant_lights.append(scenes.DistantLight(direction=(0.3, 0.5, -0.8), base_emission=(1.0, 1.0, 1.2), angle=0.05))
+    img, counts, want, rays = reference_integrator_render(libs, d)
+    assert counts == tuple(rays) and rays[1] > 0
+    assert want[..., :3].mean() > 0.05
+    assert np.array_equal(img, want)
+    img2, counts2, want2, rays2 = reference_integrator_render(libs, d, sample_offset=3, prev=want)
+    assert counts2 == tuple(rays2) and np.array_equal(img2, want2) and not np.array_equal(want2, want)
+
+
+def test_reference_integrator_materials_and_media(libs):
+    """Same comparison on scenes that walk the rest of the closest-hit and miss shaders: layered OpenPBR / UsdPreviewSurface closures with
+    transmission (medium toggle), thin walls and emission under a dome light; textured and primvar-driven inputs with a normal map
+    (what *_init() leaves in the state); nested scattering media with the two-deep medium stack (stepVolume, walk counters, push / pop)."""
+    import dataclasses
+    from gatling_b200 import scenes
+    stress = scenes.material_stress(tris_per_mesh=60, meshes=16, width=36, height=28, spp=2, max_bounces=7)
+    kitchen = scenes.kitchen_standin(tris_per_instance=40, instances=14, meshes=7, materials=6, width=36, height=28, spp=2, max_bounces=6)
+    textured = scenes.textured_cornell(32, 32, spp=2)
+    primvars = scenes.primvar_cornell(32, 32, spp=2)
+    layered = scenes.layered_cornell(32, 32, spp=2)
+    media = scenes.volume_cornell(32, 32, spp=3, max_bounces=12, medium_stack_size=2)
+    beer = scenes.volume_cornell(32, 32, spp=2, max_bounces=8, medium_stack_size=0)
+    for d in (stress, kitchen, textured, primvars, layered, media, beer):
+        d = _lit(d) if not d.settings.nextEventEstimation else d
+        img, counts, want, rays = reference_integrator_render(libs, d)
+        assert counts == tuple(rays), d.name
+        assert np.isfinite(want).all() and want[..., :3].mean() > 0.01, d.name
+        assert np.array_equal(img, want), (d.name, float(np.abs(img - want).max()))
+
+
+def test_reference_integrator_other_switches(libs):
+    """The pipeline built with the other compile-time switches: depth of field and clipping planes on, no jitter, no progressive
+    accumulation, the dome light hidden from the camera (fallback texel for primary rays)."""
+    import dataclasses
+    from gatling_b200 import scenes
+    d = _lit(scenes.cornell(36, 28, spp=3, max_bounces=5))
+    d.meshes = d.meshes[:-1]                                         # a gap for rays to leave through
+    dome = np.zeros((8, 16, 4), np.float32); dome[..., :3] = np.linspace(0.2, 2.0, 16)[None, :, None]; dome[2, 5, :3] = 30.0
+    d.dome_light = scenes.DomeLight(dome, rotation=(0.0, 0.3826834, 0.0, 0.9238795), base_emission=(1.0, 0.9, 0.8))
+    d.camera = dataclasses.replace(d.camera, fStop=2.0, focalLength=0.5, focusDistance=6.0, clipStart=6.6, clipEnd=7.7)
+    d.settings = dataclasses.replace(d.settings, depthOfField=True, clippingPlanes=True, jitteredSampling=False, filterImportanceSampling=False,
+                                     progressiveAccumulation=False, domeLightCameraVisible=False)
+    img, counts, want, rays = reference_integrator_render(libs, d)
+    assert counts == tuple(rays) and np.array_equal(img, want)
+    plain = dataclasses.replace(d, settings=dataclasses.replace(d.settings, clippingPlanes=False))
+    assert not np.array_equal(orc.OracleScene(plain).render()[0], want)          # the clip range really cut something
