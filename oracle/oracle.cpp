@@ -15,7 +15,8 @@
 // back here only for ray queries, the material's mdl_* entry points and the dome texture: its images equal
 // orc_render's bit for bit on every test scene (test_reference_integrator_*); and (2) the one golden image
 // small enough to reconstruct from its LFS pointer (tests/test_reference_pin.py).  UNPINNED remain the any-hit
-// decision (ORACLE_DEVIATIONS #10), the auxiliary-AOV writes and the BSDF arithmetic (closed MDL SDK).
+// decision (ORACLE_DEVIATIONS #10), the ClockCycles / FaceId AOVs and the BSDF arithmetic (closed MDL SDK); the
+// other fifteen AOVs are compared as well (test_reference_integrator_auxiliary_aovs).
 // The file follows the reference *source text* line by line where the source is in
 // tree (integrator: rp_main.rgen / rp_main.chit / rp_main.miss / rp_main_shadow.miss, common.glsl,
 // mdl_shading_state.glsl, Gi.cpp host encoders) and restates published definitions where the
@@ -1098,6 +1099,12 @@ void orc_ubo_values(void* h, const OrcRenderDesc* r, float* f, uint32_t* u)
                             b.sampleOffset, b.spp, b.maxBouncesAndRrBounceOffset, b.clipRangePacked, c.mediumStackSize,
                             (uint32_t) ((c.fl.jittered ? 1 : 0) | (c.fl.fis ? 2 : 0) | (c.fl.dof ? 4 : 0) | (c.fl.nee ? 8 : 0) | (c.fl.clipping ? 16 : 0) | (c.fl.progressive ? 32 : 0) | (c.fl.domeCameraVisible ? 64 : 0)), 0u, 0u, 0u };
   memcpy(f, fv, sizeof(fv)); memcpy(u, uv, sizeof(uv));
+}
+// InstanceIds[] (rp_main_descriptors.glsl:20) and the objectId of every instance's mesh preamble (rp_main.h:142)
+void orc_instance_ids(void* h, int32_t* instanceIds, int32_t* objectIds)
+{
+  const Scene* s = (const Scene*) h;
+  for (size_t i = 0; i < s->instances.size(); i++) { instanceIds[i] = s->instances[i].instanceId; objectIds[i] = s->instances[i].objectId; }
 }
 // The light buffers as the shaders see them (interface/rp_main.h layouts, 48 bytes per light)
 void orc_light_buffers(void* h, const void** spheres, const void** distants, const void** rects, const void** disks)

@@ -32,7 +32,7 @@ FRAGMENTS = [
     ("rp_main.rgen", 48, 130, "rgen_functions.inc"),           # sampleDistance .. fisGauss
     ("rp_main.rgen", 191, 288, "rgen_camera.inc"),             # main(): pixel -> camera ray, RNG draws, clip range (leaves the sample loop open)
     ("mdl_shading_state.glsl", None, None, "mdl_shading_state.glsl"),
-    ("rp_main.rgen", 185, 521, "rgen_main.inc"),               # main(): the whole ray-generation shader
+    ("rp_main.rgen", 132, 521, "rgen_main.inc"),               # clearAovs + main(): the whole ray-generation shader
     ("rp_main.chit", 132, 493, "chit_main.inc"),               # main(): the whole closest-hit shader
     ("rp_main.miss", 15, 87, "miss_all.inc"),                  # stepVolume, quatRotateDir, sampleDomeLight, main()
     ("rp_main_shadow.miss", 14, 17, "shadow_miss_main.inc"),   # main()

@@ -19,12 +19,15 @@ static inline int sampler2D(int, int) { return 0; }
 // mdl_shading_state.glsl reads the hit mesh through buffer references and the ray-tracing built-ins; the stand-ins point at test arrays
 static BlasPayload blas_payloads[1];
 static const Face* g_faces; static const FVertex* g_vertices;
-struct IndexBuffer { const Face* data; explicit IndexBuffer(uint64_t) : data(g_faces) {} };
+static BlasPayloadBufferPreamble g_preamble;
+struct IndexBuffer { const Face* data; BlasPayloadBufferPreamble preamble; explicit IndexBuffer(uint64_t) : data(g_faces), preamble(g_preamble) {} };
+static vec4 ClearValuesF[17]; static ivec4 ClearValuesI[17];
+static const int *g_instanceIds, *g_objectIds;            // per instance (orc_instance_ids), set by the AOV render
 struct VertexBuffer { const FVertex* data; explicit VertexBuffer(uint64_t) : data(g_vertices) {} };
 static int gl_InstanceCustomIndexEXT, gl_PrimitiveID;
 static mat4x3 gl_ObjectToWorldEXT, gl_WorldToObjectEXT;
 static uvec3 gl_LaunchIDEXT;
-static inline void clearAovs(uint) {}
+static inline void clearAovs(uint) {}          // (the camera-head builds; the whole-pipeline builds compile the real one, rp_main.rgen:132-183)
 #define SCENE_DATA_COUNT 0
 
 #include "common.glsl"
@@ -146,6 +149,19 @@ static uint64_t g_rayCounts[2];
 #undef MEDIUM_STACK_SIZE
 #undef DEPTH_OF_FIELD
 #undef CLIPPING_PLANES
+// ... and the default pipeline with every auxiliary AOV bound (all of rp_main.chit:191-290, rgen:132-183,431-436,483-486,517-520) except
+// the two whose inputs the oracle does not model: ClockCycles (a timer) and FaceId (byte-packed id table behind the index buffer)
+#undef AOV_MASK
+#define AOV_MASK (0x1FFFF & ~AOV_BIT_DEBUG_CLOCK_CYCLES & ~AOV_BIT_FACE_ID)
+#define PROGRESSIVE_ACCUMULATION
+#define JITTERED_SAMPLING
+#define FILTER_IMPORTANCE_SAMPLING
+#define DOME_LIGHT_CAMERA_VISIBLE
+#define PIPE_NS pipe_aovs
+#define MEDIUM_STACK_SIZE 0
+#include "ref_pipeline.inc"
+#undef PIPE_NS
+#undef MEDIUM_STACK_SIZE
 #undef NEXT_EVENT_ESTIMATION
 
 static inline vec3 ld3(const float* p) { return vec3(p[0], p[1], p[2]); }
@@ -245,9 +261,14 @@ EXPORT void ref_setup_shading_state(const void* faces, const void* vertices, uin
 // f28 / u16: orc_ubo_values; lights: orc_light_buffers + the counts in u16; u16[11] = medium stack size, u16[12] = switches (bit 0 jitter,
 // 1 filter importance sampling, 2 depth of field, 3 NEE, 4 clipping planes, 5 progressive, 6 dome visible to the camera).
 // rgba: width * height vec4, holds the previous ColorAov on entry when progressive.  Returns 0 if no pipeline was compiled for the switches.
+// aov: NULL, or 17 pointers (by AOV id; vec3 AOVs as tightly packed float[3], ids as int, depth as float; entries 0, 6, 13 unused) that
+// selects the all-AOVs pipeline; clearF / clearI: 17 x 4 clear values; instanceIds / objectIds: per instance
 EXPORT int ref_render(const RefCallbacks* cb, const float* f28, const uint* u16, const void* spheres, const void* distants, const void* rects, const void* disks,
-                      float* rgba, uint64_t* rayCounts)
+                      float* rgba, uint64_t* rayCounts, void* const* aov, const float* clearF, const int* clearI, const int* instanceIds, const int* objectIds)
 {
+  g_instanceIds = aov ? instanceIds : nullptr; g_objectIds = aov ? objectIds : nullptr;
+  if (aov) for (int k = 0; k < 17; k++) { ClearValuesF[k] = vec4(clearF[4 * k], clearF[4 * k + 1], clearF[4 * k + 2], clearF[4 * k + 3]); ClearValuesI[k].x = clearI[4 * k]; ClearValuesI[k].y = clearI[4 * k + 1]; ClearValuesI[k].z = clearI[4 * k + 2]; ClearValuesI[k].w = clearI[4 * k + 3]; }
+  else for (int k = 0; k < 17; k++) ClearValuesF[k] = vec4(0.0f);
   g_cb = *cb; g_rayCounts[0] = g_rayCounts[1] = 0;
   ubo.domeLightRotation = vec4(f28[0], f28[1], f28[2], f28[3]); ubo.domeLightEmissionMultiplier = ld3(f28 + 4); ubo.metersPerSceneUnit = f28[7];
   ubo.cameraPosition = ld3(f28 + 8); ubo.cameraForward = ld3(f28 + 11); ubo.cameraUp = ld3(f28 + 14); ubo.focusDistance = f28[17]; ubo.cameraVFoV = f28[18];
@@ -261,7 +282,8 @@ EXPORT int ref_render(const RefCallbacks* cb, const float* f28, const uint* u16,
   memcpy(rectLights, rects, sizeof(RectLight) * u16[2]); memcpy(diskLights, disks, sizeof(DiskLight) * u16[3]);
   const uint width = u16[6] & 0xFFFFu, height = u16[6] >> 16, mss = u16[11], sw = u16[12];
   int ok = 1;
-  if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_default::render(width, height, (vec4*) rgba);
+  if (aov) { if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_aovs::render(width, height, (vec4*) rgba, aov); else ok = 0; }
+  else if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_default::render(width, height, (vec4*) rgba);
   else if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 2) pipe_media2::render(width, height, (vec4*) rgba);
   else if (sw == (4u | 8u | 16u) && mss == 0) pipe_other::render(width, height, (vec4*) rgba);
   else ok = 0;

@@ -310,9 +310,10 @@ class RefCallbacks(C.Structure):
                 ("trace", "views", "hitBegin", "mappedNormal", "volume", "bsdfSample", "bsdfEvaluate", "bsdfAlbedo", "edf", "dome")]
 
 
-def reference_integrator_render(libs, desc, sample_offset=0, prev=None):
+def reference_integrator_render(libs, desc, sample_offset=0, prev=None, aov_ids=None, clear_values=None):
     """Renders `desc` with the reference's own shader code (oracle/ref_glsl/ref_pipeline.inc): its main() functions run as C++ and call back
-    into the oracle for ray queries, the material's mdl_* entry points and the dome texture.  Returns (rgba, (closest, shadow) ray counts)."""
+    into the oracle for ray queries, the material's mdl_* entry points and the dome texture.  Returns (rgba, (closest, shadow) ray counts,
+    the oracle's rgba, the oracle's ray counts); with `aov_ids` the all-AOVs build runs and rgba / the oracle's result are {id: array}."""
     R, O = libs
     o = orc.OracleScene(desc)
     r = o.render_desc(sample_offset)
@@ -330,12 +331,33 @@ def reference_integrator_render(libs, desc, sample_offset=0, prev=None):
     O.orc_light_buffers(o.handle, *[C.byref(p) for p in lights])
     img = np.zeros((desc.height, desc.width, 4), np.float32) if prev is None else np.ascontiguousarray(prev, np.float32).copy()
     counts = (C.c_uint64 * 2)()
-    R.ref_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    ok = R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts)
-    assert ok == 1, "no reference pipeline was compiled for these render settings (ref_exports.cpp)"
-    want, _, rays = o.render(sample_offset=sample_offset, prev=prev)
+    R.ref_render.argtypes = [C.c_void_p] * 14
+    if aov_ids is None:
+        ok = R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts, None, None, None, None, None)
+        assert ok == 1, "no reference pipeline was compiled for these render settings (ref_exports.cpp)"
+        want, _, rays = o.render(sample_offset=sample_offset, prev=prev)
+        o.close()
+        return img, (int(counts[0]), int(counts[1])), want, rays
+    INT, n = (11, 14), desc.width * desc.height
+    bufs = {a: (np.zeros((n, 1), np.int32) if a in INT else np.zeros((n, 1), np.float32) if a == 12 else np.zeros((n, 3), np.float32)) for a in range(17)}
+    ptrs = (C.c_void_p * 17)(*[bufs[a].ctypes.data for a in range(17)])
+    clear_f, clear_i = np.zeros((17, 4), np.float32), np.zeros((17, 4), np.int32)
+    for a, v in (clear_values or {}).items():
+        (clear_i if a in INT else clear_f)[a, :len(v)] = v
+    ninst = len(desc.meshes) * 64 + 64
+    inst_ids, obj_ids = np.zeros(ninst, np.int32), np.zeros(ninst, np.int32)
+    O.orc_instance_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    O.orc_instance_ids(o.handle, inst_ids.ctypes.data, obj_ids.ctypes.data)
+    ok = R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts, ptrs, clear_f.ctypes.data, clear_i.ctypes.data,
+                      inst_ids.ctypes.data, obj_ids.ctypes.data)
+    assert ok == 1
+    want = o.render_aovs(aov_ids, clear_values, sample_offset=sample_offset)
     o.close()
-    return img, (int(counts[0]), int(counts[1])), want, rays
+    got = {0: img}
+    for a in aov_ids:
+        if a != 0:
+            got[a] = bufs[a].reshape(desc.height, desc.width, -1)
+    return got, (int(counts[0]), int(counts[1])), want, None
 
 
 def _lit(d):
@@ -400,3 +422,26 @@ def test_reference_integrator_other_switches(libs):
     assert counts == tuple(rays) and np.array_equal(img, want)
     plain = dataclasses.replace(d, settings=dataclasses.replace(d.settings, clippingPlanes=False))
     assert not np.array_equal(orc.OracleScene(plain).render()[0], want)          # the clip range really cut something
+
+
+def test_reference_integrator_auxiliary_aovs(libs):
+    """The build with every auxiliary AOV bound (rp_main.rgen:132-183 clearAovs, :431-436 NEE, :483-486 Bounces, :517-520 normal
+    re-normalisation; rp_main.chit:191-290): Normal, NEE, Barycentrics, Texcoords, Bounces, Opacity, Tangents, Bitangents, ThinWalled,
+    ObjectId, Depth, InstanceId, DoubleSided, Albedo and Color against the oracle's replay of the megakernel's per-pixel write order,
+    with non-trivial clear values.  (ClockCycles is a timer; FaceId reads a byte-packed table the oracle does not model.)"""
+    from gatling_b200 import scenes
+    ids = [a for a in range(17) if a not in (6, 13)]
+    clear = {a: ((7, 0, 0, 0) if a in (11, 14) else (0.25 + 0.01 * a, 0.5, 0.125 * (a % 3), 0.75)) for a in ids if a != 0}
+    for d in (_lit(scenes.cornell(30, 22, spp=3, max_bounces=5)),
+              _lit(scenes.kitchen_standin(tris_per_instance=40, instances=14, meshes=7, materials=6, width=30, height=22, spp=2, max_bounces=5)),
+              scenes.textured_cornell(28, 28, spp=2)):
+        if d.name.startswith("cornell"):
+            d.meshes = d.meshes[:-2]                                  # pixels that hit nothing keep the clear values
+        got, counts, want, _ = reference_integrator_render(libs, d, aov_ids=ids, clear_values=clear)
+        for a in ids:
+            g, w = got[a], want[a]
+            if a == 0:
+                assert np.array_equal(g, w), (d.name, a)
+            else:
+                assert np.array_equal(g, w[..., :g.shape[-1]]), (d.name, a, float(np.abs(g.astype(np.float64) - w[..., :g.shape[-1]]).max()))
+        assert len(np.unique(got[11])) > 1 and got[12].std() > 0.0 and got[16][..., :3].std() > 0.0
