@@ -1100,6 +1100,20 @@ void orc_ubo_values(void* h, const OrcRenderDesc* r, float* f, uint32_t* u)
                             (uint32_t) ((c.fl.jittered ? 1 : 0) | (c.fl.fis ? 2 : 0) | (c.fl.dof ? 4 : 0) | (c.fl.nee ? 8 : 0) | (c.fl.clipping ? 16 : 0) | (c.fl.progressive ? 32 : 0) | (c.fl.domeCameraVisible ? 64 : 0)), 0u, 0u, 0u };
   memcpy(f, fv, sizeof(fv)); memcpy(u, uv, sizeof(uv));
 }
+// Host-side light arithmetic, Gi.cpp:2635-2640 (Knud Thomsen's approximation of an ellipsoid's area; the last factor is a double) and
+// Gi.cpp:2724-2725 (solid angle of the distant light's cone; 2 pi in double)
+float orc_sphere_light_area(float radiusX, float radiusY, float radiusZ)
+{
+  float ab = powf(radiusX * radiusY, 1.6f);
+  float ac = powf(radiusX * radiusZ, 1.6f);
+  float bc = powf(radiusY * radiusZ, 1.6f);
+  return float(powf((ab + ac + bc) / 3.0f, 1.0f / 1.6f) * 4.0f * M_PI);
+}
+float orc_distant_light_inv_pdf(float angle)
+{
+  float halfAngle = 0.5f * angle;
+  return (halfAngle > 0.0f) ? float(2.0f * M_PI * (1.0f - cosf(halfAngle))) : 1.0f;
+}
 // InstanceIds[] (rp_main_descriptors.glsl:20) and the objectId of every instance's mesh preamble (rp_main.h:142)
 void orc_instance_ids(void* h, int32_t* instanceIds, int32_t* objectIds)
 {

@@ -199,16 +199,15 @@ def light_arrays(desc):
     L = lib()
     sp = np.zeros(len(desc.sphere_lights), SPHERE_LIGHT_DTYPE)
     for i, l in enumerate(desc.sphere_lights):
-        rx, ry, rz = [np.float32(v) for v in l.radius]
-        ab = np.float32(np.power(rx * ry, np.float32(1.6)))
-        ac = np.float32(np.power(rx * rz, np.float32(1.6)))
-        bc = np.float32(np.power(ry * rz, np.float32(1.6)))
-        area = np.float32(np.float32(np.power((ab + ac + bc) / np.float32(3.0), np.float32(1.0 / 1.6))) * np.float32(4.0) * np.float32(np.pi))
+        L.orc_sphere_light_area.restype = C.c_float
+        L.orc_sphere_light_area.argtypes = [C.c_float] * 3
+        area = np.float32(L.orc_sphere_light_area(*[float(np.float32(v)) for v in l.radius]))
         sp[i] = (l.position, L.orc_pack_half2x16(l.diffuse, l.specular), l.base_emission, area, l.radius, 0.0)
     di = np.zeros(len(desc.distant_lights), DISTANT_LIGHT_DTYPE)
     for i, l in enumerate(desc.distant_lights):
-        half = np.float32(0.5) * np.float32(l.angle)
-        inv_pdf = np.float32(2.0 * np.pi * (1.0 - np.cos(half, dtype=np.float32))) if half > 0 else np.float32(1.0)
+        L.orc_distant_light_inv_pdf.restype = C.c_float
+        L.orc_distant_light_inv_pdf.argtypes = [C.c_float]
+        inv_pdf = np.float32(L.orc_distant_light_inv_pdf(float(np.float32(l.angle))))
         di[i] = (l.direction, l.angle, l.base_emission, L.orc_pack_half2x16(l.diffuse, l.specular), (0, 0, 0), inv_pdf)
     re = np.zeros(len(desc.rect_lights), RECT_LIGHT_DTYPE)
     for i, l in enumerate(desc.rect_lights):

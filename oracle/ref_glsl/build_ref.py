@@ -10,7 +10,8 @@ the repository; only the shared object is kept, git-ignored):
   * vector constructors:  `vec4(a, b, c, d)` -> `vec4{a, b, c, d}` (left-to-right evaluation of the arguments, as GLSL specifies)
   * a line range is cut out of the files that also hold Vulkan-only code (rp_main.rgen / .chit / .miss, mdl_interface.glsl)
 The types and built-ins come from oracle/ref_glsl/glsl_shim.h; g++ runs with -fsingle-precision-constant (GLSL literals are
-floats) and -ffp-contract=off."""
+floats) and -ffp-contract=off.  A second translation unit (ref_host.cpp, built without that flag) holds line ranges of the reference's
+C++ host code, src/gi/impl/Gi.cpp -- the light encoders -- which need no rewriting at all."""
 import os
 import re
 import shutil
@@ -68,6 +69,13 @@ def translate(text: str) -> str:
     return brace_constructors(text)
 
 
+# C++ of the reference's host side (no rewriting): (path below /root/reference/src, first line, last line, generated name)
+HOST_FRAGMENTS = [
+    ("gi/impl/Gi.cpp", 287, 300, "gi_encode_direction.inc"),   # _EncodeOctahedral, _EncodeDirection
+    ("gi/impl/Gi.cpp", 2573, 2941, "gi_lights.inc"),           # gi{Create,Destroy,Set}{Sphere,Distant,Rect,Disk}Light*
+]
+
+
 def build() -> str:
     if not os.path.isdir(REF):
         raise SystemExit("build_ref: %s does not exist (the reference sources are only present in the build container)" % REF)
@@ -81,13 +89,26 @@ def build() -> str:
                 lines = lines[a - 1:b]
             with open(os.path.join(tmp, name), "w") as f:
                 f.write(translate("\n".join(lines)) + "\n")
+        for src, a, b, name in HOST_FRAGMENTS:
+            with open(os.path.join(os.path.dirname(os.path.dirname(REF)), src)) as f:
+                lines = f.read().split("\n")
+            with open(os.path.join(tmp, name), "w") as f:
+                f.write("\n".join(lines[a - 1:b]) + "\n")
         so = os.path.join(OUT, "libglslref.so")
-        cmd = ["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-fsingle-precision-constant", "-ffp-contract=off", "-fno-fast-math", "-w",
-               "-I", tmp, "-I", HERE, "-I", REF, os.path.join(HERE, "ref_exports.cpp"), "-o", so, "-lm"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        common = ["g++", "-std=c++17", "-O1", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", tmp, "-I", HERE, "-I", REF, "-c"]
+        objs = []
+        for unit, extra in (("ref_exports.cpp", ["-fsingle-precision-constant"]),      # GLSL: every literal is a float
+                            ("ref_host.cpp", [])):                                      # C++ host code: float / double as written
+            obj = os.path.join(tmp, unit + ".o")
+            r = subprocess.run(common + extra + [os.path.join(HERE, unit), "-o", obj], capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stderr[-6000:])
+                raise SystemExit("build_ref: g++ failed on " + unit)
+            objs.append(obj)
+        r = subprocess.run(["g++", "-shared", "-o", so] + objs + ["-lm"], capture_output=True, text=True)
         if r.returncode != 0:
-            sys.stderr.write(r.stderr[-6000:])
-            raise SystemExit("build_ref: g++ failed")
+            sys.stderr.write(r.stderr[-3000:])
+            raise SystemExit("build_ref: link failed")
         return so
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

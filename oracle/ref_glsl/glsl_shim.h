@@ -22,6 +22,7 @@ struct vec2 {
   vec2(float a, float b) : x(a), y(b) {}
   vec2 xy() const { return *this; }
   vec2 yx() const { return vec2(y, x); }
+  float& operator[](int i) { return (&x)[i]; }
 };
 struct vec3 {
   union { float x, r; }; union { float y, g; }; union { float z, b; };
@@ -34,6 +35,7 @@ struct vec3 {
   vec2 yx() const { return vec2(y, x); }
   vec3 xyz() const { return *this; }
   vec3 rgb() const { return *this; }
+  float& operator[](int i) { return (&x)[i]; }                 // (glm-style component access of the host code)
 };
 struct vec4 {
   union { float x, r; }; union { float y, g; }; union { float z, b; }; union { float w, a; };

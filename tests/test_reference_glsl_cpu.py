@@ -445,3 +445,41 @@ def test_reference_integrator_auxiliary_aovs(libs):
             else:
                 assert np.array_equal(g, w[..., :g.shape[-1]]), (d.name, a, float(np.abs(g.astype(np.float64) - w[..., :g.shape[-1]]).max()))
         assert len(np.unique(got[11])) > 1 and got[12].std() > 0.0 and got[16][..., :3].std() > 0.0
+
+
+def test_host_light_encoders(libs):
+    """The reference's HOST code for lights -- every gi{Create,Set}{Sphere,Distant,Rect,Disk}Light* of src/gi/impl/Gi.cpp:2573-2941 and
+    `_EncodeDirection` (:287-300), compiled from the reference's file -- against the light records the oracle builds for the same user
+    values (orc.light_arrays): Knud-Thomsen area, the cone's inverse pdf (in double, as written), tangent-frame packing, layout."""
+    from gatling_b200 import scenes
+    R, O = libs
+    R.refhost_set_pack_half(C.cast(O.orc_pack_half2x16, C.c_void_p))
+    R.refhost_encode_direction.restype = O.orc_host_encode_direction.restype = C.c_uint32
+    rng = np.random.default_rng(11)
+    fl = lambda v: float(np.float32(v))
+    d = scenes.cornell(4, 4, spp=1)
+    for k in range(300):
+        v3 = lambda s=1.0: tuple(fl(x) for x in rng.normal(size=3) * s)
+        ds = (fl(rng.random()), fl(rng.random() * 2))
+        sph = scenes.SphereLight(position=v3(3), base_emission=v3(5), radius=tuple(fl(x) for x in rng.random(3) * 2 * (1 if k % 9 else 0)), diffuse=ds[0], specular=ds[1])
+        dis = scenes.DistantLight(direction=tuple(unit(rng.normal(size=3)).tolist()), base_emission=v3(2), angle=fl(rng.random() * (1 if k % 5 else 0)), diffuse=ds[0], specular=ds[1])
+        rec = scenes.RectLight(origin=v3(2), t0=v3(), t1=v3(), base_emission=v3(9), width=fl(rng.random() * 3), height=fl(rng.random()), diffuse=ds[0], specular=ds[1])
+        dsk = scenes.DiskLight(origin=v3(2), t0=v3(), t1=v3(), base_emission=v3(9), radius=(fl(rng.random()), fl(rng.random() * 2)), diffuse=ds[0], specular=ds[1])
+        d.sphere_lights, d.distant_lights, d.rect_lights, d.disk_lights = [sph], [dis], [rec], [dsk]
+        sp, di, re, dk = orc.light_arrays(d)
+        out = (C.c_uint8 * 48)()
+        R.refhost_sphere_light.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+        R.refhost_sphere_light(1, f3(sph.position), f3(sph.base_emission), f3(sph.radius), sph.diffuse, sph.specular, out)
+        assert bytes(out)[:44] == sp.tobytes()[:44], (k, sph)                                   # (the last 4 bytes are padding)
+        R.refhost_distant_light.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        R.refhost_distant_light(1, f3(dis.direction), f3(dis.base_emission), dis.angle, dis.diffuse, dis.specular, out)
+        b, w = bytes(out), di.tobytes()
+        assert b[:32] == w[:32] and b[44:] == w[44:], (k, dis)                                  # (bytes 32..43 are padding)
+        R.refhost_rect_light.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_float] * 4 + [C.c_void_p]
+        R.refhost_rect_light(1, f3(rec.origin), f3(rec.t0), f3(rec.t1), f3(rec.base_emission), rec.width, rec.height, rec.diffuse, rec.specular, out)
+        assert bytes(out)[:44] == re.tobytes()[:44], (k, rec)
+        R.refhost_disk_light.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_float] * 4 + [C.c_void_p]
+        R.refhost_disk_light(1, f3(dsk.origin), f3(dsk.t0), f3(dsk.t1), f3(dsk.base_emission), dsk.radius[0], dsk.radius[1], dsk.diffuse, dsk.specular, out)
+        assert bytes(out)[:44] == dk.tobytes()[:44], (k, dsk)
+        v = f3(rng.normal(size=3) * 10.0 ** rng.integers(-3, 3))
+        assert R.refhost_encode_direction(v) == O.orc_host_encode_direction(v)
