@@ -73,6 +73,7 @@ def translate(text: str) -> str:
 HOST_FRAGMENTS = [
     ("gi/impl/Gi.cpp", 287, 300, "gi_encode_direction.inc"),   # _EncodeOctahedral, _EncodeDirection
     ("gi/impl/Gi.cpp", 2573, 2941, "gi_lights.inc"),           # gi{Create,Destroy,Set}{Sphere,Distant,Rect,Disk}Light*
+    ("gi/impl/Gi.cpp", 2375, 2425, "gi_uniforms.inc"),         # giRender: camera vectors, lens radius, the UniformData initialiser
 ]
 
 
@@ -95,7 +96,8 @@ def build() -> str:
             with open(os.path.join(tmp, name), "w") as f:
                 f.write("\n".join(lines[a - 1:b]) + "\n")
         so = os.path.join(OUT, "libglslref.so")
-        common = ["g++", "-std=c++17", "-O1", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", tmp, "-I", HERE, "-I", REF, "-c"]
+        src_root = os.path.dirname(os.path.dirname(REF))
+        common = ["g++", "-std=c++20", "-I", os.path.join(src_root, "gi"), "-I", os.path.join(src_root, "gb"), "-O1", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", tmp, "-I", HERE, "-I", REF, "-c"]
         objs = []
         for unit, extra in (("ref_exports.cpp", ["-fsingle-precision-constant"]),      # GLSL: every literal is a float
                             ("ref_host.cpp", [])):                                      # C++ host code: float / double as written

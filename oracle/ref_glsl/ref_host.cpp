@@ -1,4 +1,5 @@
-// TEST INFRASTRUCTURE.  The reference's HOST-side light encoders (src/gi/impl/Gi.cpp:287-300 `_EncodeOctahedral` / `_EncodeDirection` and
+// TEST INFRASTRUCTURE.  The reference's HOST-side code for this path, compiled from src/gi/impl/Gi.cpp: the uniform block of giRender (:2375-2425,
+// further down) and the light encoders (src/gi/impl/Gi.cpp:287-300 `_EncodeOctahedral` / `_EncodeDirection` and
 // :2573-2941, every gi{Create,Set}{Sphere,Distant,Rect,Disk}Light* function) compiled from the reference's own file -- plain C++, so no
 // rewriting, only the line ranges cut out by build_ref.py -- against stand-ins for what surrounds them in Gi.cpp: a GiScene holding four
 // dense stores, glm (the handful of functions these lines use, written as glm writes them: normalize = v * (1 / sqrt(dot)), packUnorm2x16 =
@@ -48,7 +49,60 @@ namespace gtl {
 #include "gi_lights.inc"                // Gi.cpp:2573-2941
 }
 
+// ---- Gi.cpp:2374-2423: the uniform block giRender fills for the shaders ----
+// The reference's own public header supplies GiCameraDesc / GiRenderSettings / GiRenderParams; stand-ins for the rest of giRender's locals.
+#include <gtl/gi/Gi.h>
+namespace glm {
+  struct quat { float x, y, z, w; quat() : x(0.0f), y(0.0f), z(0.0f), w(1.0f) {} float& operator[](int i) { return (&x)[i]; } };   // (x, y, z, w) in memory; make_quat reads the same order
+  static inline vec4 make_vec4(const float* p) { return vec4(p[0], p[1], p[2], p[3]); }
+}
+namespace ubofill {
+  struct DomeLight { glm::quat rotation; vec3 baseEmission; float diffuse = 1.0f, specular = 1.0f; };
+  struct CountStore { uint32_t n = 0; uint32_t elementCount() const { return n; } };
+  struct Scene { DomeLight* domeLight = nullptr; CountStore sphereLights, distantLights, rectLights, diskLights; uint32_t sampleOffset = 0; };
+  struct ShaderCache { uint32_t maxTextureIndex = 0; };
+  struct BumpAlloc { rp::UniformData storage; struct Slot { rp::UniformData* cpuPtr; uint32_t bufferOffset; }; template <typename T> Slot alloc() { return Slot{ &storage, 0u }; } };
+  static rp::UniformData fill(const gtl::GiRenderParams& params, Scene* scene, uint32_t imageWidth, uint32_t imageHeight)
+  {
+    using namespace gtl;
+    const GiRenderSettings& renderSettings = params.renderSettings;
+    ShaderCache cache; ShaderCache* shaderCache = &cache;
+    BumpAlloc bump; BumpAlloc* s_bumpAlloc = &bump;
+    uint32_t uniformOffset;
+    {
+#include "gi_uniforms.inc"              // Gi.cpp:2375-2425
+    }
+    (void) uniformOffset;
+    return bump.storage;
+  }
+}
+
 #define EXPORT extern "C" __attribute__((visibility("default")))
+// cam16: position(3) forward(3) up(3) vfov fStop focusDistance focalLength clipStart clipEnd exposure; set8: lightIntensityMultiplier maxSampleValue
+// metersPerSceneUnit rrInvMinTermProb (floats) and, as integers, maxBounces maxVolumeWalkLength rrBounceOffset spp; counts4: lights per type;
+// dome: NULL or rotation(4) baseEmission(3).  Output in the layout of orc_ubo_values (28 floats, 16 uints).
+EXPORT void refhost_uniform_data(const float* cam16, const float* setF4, const uint32_t* setU4, const uint32_t* counts4, const float* dome7, uint32_t sampleOffset,
+                                 uint32_t width, uint32_t height, float* f28, uint32_t* u16)
+{
+  gtl::GiRenderParams params{};
+  memcpy(params.camera.position, cam16, 12); memcpy(params.camera.forward, cam16 + 3, 12); memcpy(params.camera.up, cam16 + 6, 12);
+  params.camera.vfov = cam16[9]; params.camera.fStop = cam16[10]; params.camera.focusDistance = cam16[11]; params.camera.focalLength = cam16[12];
+  params.camera.clipStart = cam16[13]; params.camera.clipEnd = cam16[14]; params.camera.exposure = cam16[15];
+  gtl::GiRenderSettings& rs = params.renderSettings;
+  rs.lightIntensityMultiplier = setF4[0]; rs.maxSampleValue = setF4[1]; rs.metersPerSceneUnit = setF4[2]; rs.rrInvMinTermProb = setF4[3];
+  rs.maxBounces = setU4[0]; rs.maxVolumeWalkLength = setU4[1]; rs.rrBounceOffset = setU4[2]; rs.spp = setU4[3]; rs.frame = 0.0f; rs.time = 0.0f;
+  ubofill::Scene scene; ubofill::DomeLight domeLight;
+  scene.sphereLights.n = counts4[0]; scene.distantLights.n = counts4[1]; scene.rectLights.n = counts4[2]; scene.diskLights.n = counts4[3]; scene.sampleOffset = sampleOffset;
+  if (dome7) { domeLight.rotation.x = dome7[0]; domeLight.rotation.y = dome7[1]; domeLight.rotation.z = dome7[2]; domeLight.rotation.w = dome7[3]; domeLight.baseEmission = vec3(dome7[4], dome7[5], dome7[6]); scene.domeLight = &domeLight; }
+  const rp::UniformData u = ubofill::fill(params, &scene, width, height);
+  const float f[28] = { u.domeLightRotation.x, u.domeLightRotation.y, u.domeLightRotation.z, u.domeLightRotation.w, u.domeLightEmissionMultiplier.x, u.domeLightEmissionMultiplier.y,
+                        u.domeLightEmissionMultiplier.z, u.metersPerSceneUnit, u.cameraPosition.x, u.cameraPosition.y, u.cameraPosition.z, u.cameraForward.x, u.cameraForward.y, u.cameraForward.z,
+                        u.cameraUp.x, u.cameraUp.y, u.cameraUp.z, u.focusDistance, u.cameraVFoV, u.lensRadius, u.invTotalSampleCount, u.maxSampleValue, u.rrInvMinTermProb,
+                        u.lightIntensityMultiplier, u.sensorExposure, 0.0f, 0.0f, 0.0f };
+  const uint32_t v[16] = { u.sphereLightCount, u.distantLightCount, u.rectLightCount, u.diskLightCount, u.totalLightCount, u.maxVolumeWalkLength, u.imageDims, u.sampleOffset, u.spp,
+                           u.maxBouncesAndRrBounceOffset, u.clipRangePacked, 0u, 0u, 0u, 0u, 0u };
+  memcpy(f28, f, sizeof(f)); memcpy(u16, v, sizeof(v));
+}
 EXPORT void refhost_set_pack_half(uint32_t (*fn)(float, float)) { g_packHalf2x16 = fn; }
 EXPORT uint32_t refhost_encode_direction(const float* v) { return gtl::_EncodeDirection(vec3(v[0], v[1], v[2])); }
 // Each function creates the light and applies the setters in the order hdGatling's light adapters call them (src/hdGatling/light.cpp), then

@@ -483,3 +483,46 @@ def test_host_light_encoders(libs):
         assert bytes(out)[:44] == dk.tobytes()[:44], (k, dsk)
         v = f3(rng.normal(size=3) * 10.0 ** rng.integers(-3, 3))
         assert R.refhost_encode_direction(v) == O.orc_host_encode_direction(v)
+
+
+def test_host_uniform_block(libs):
+    """giRender's uniform block (src/gi/impl/Gi.cpp:2375-2425, compiled from the reference's file against the reference's own Gi.h): camera
+    vectors normalised, lens radius, packed image size / bounce counts / clip range, 1 / total samples, dome-light values and light counts
+    -- against what the oracle derives from the same camera and settings (fill_ctx -> orc_ubo_values)."""
+    import dataclasses
+    from gatling_b200 import scenes
+    R, O = libs
+    R.refhost_set_pack_half(C.cast(O.orc_pack_half2x16, C.c_void_p))
+    O.orc_ubo_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.refhost_uniform_data.argtypes = [C.c_void_p] * 5 + [C.c_uint32] * 3 + [C.c_void_p] * 2
+    rng = np.random.default_rng(13)
+    fl = lambda v: float(np.float32(v))
+    for k in range(200):
+        d = scenes.cornell(int(rng.integers(1, 4000)), int(rng.integers(1, 3000)), spp=int(rng.integers(1, 5000)))
+        cam = scenes.Camera(position=tuple(fl(x) for x in rng.normal(size=3) * 5), forward=tuple(fl(x) for x in rng.normal(size=3) * 3), up=tuple(fl(x) for x in rng.normal(size=3)),
+                            vfov=fl(rng.uniform(0.1, 2.5)), fStop=fl(rng.uniform(0.5, 22.0) * (k % 3 != 0)), focusDistance=fl(rng.uniform(0.1, 50)), focalLength=fl(rng.uniform(0.01, 0.2)),
+                            clipStart=fl(rng.uniform(0.001, 2.0)), clipEnd=fl(rng.uniform(5.0, 70000.0)), exposure=fl(rng.normal()))
+        st = dataclasses.replace(d.settings, lightIntensityMultiplier=fl(rng.uniform(0.1, 4)), maxSampleValue=fl(rng.uniform(1, 100)), metersPerSceneUnit=fl(rng.uniform(0.01, 10)),
+                                 rrInvMinTermProb=fl(rng.uniform(0.5, 1)), maxBounces=int(rng.integers(0, 4096)), maxVolumeWalkLength=int(rng.integers(0, 64)), rrBounceOffset=int(rng.integers(0, 64)))
+        d = dataclasses.replace(d, camera=cam, settings=st)
+        dome7 = None
+        if k % 2:
+            q = unit(rng.normal(size=4)); em = tuple(fl(x) for x in rng.random(3) * 3)
+            d.dome_light = scenes.DomeLight(np.ones((2, 4, 4), np.float32), rotation=tuple(float(x) for x in q), base_emission=em)
+            dome7 = (C.c_float * 7)(*q, *em)
+        d.sphere_lights = [scenes.SphereLight(position=(0, 0, 0), base_emission=(1, 1, 1), radius=(1, 1, 1))] * int(rng.integers(0, 3))
+        d.distant_lights = [scenes.DistantLight(direction=(0, 0, -1), base_emission=(1, 1, 1), angle=0.0)] * int(rng.integers(0, 3))
+        sample_offset = int(rng.integers(0, 100000))
+        o = orc.OracleScene(d)
+        r = o.render_desc(sample_offset)
+        fo, uo = (C.c_float * 28)(), (C.c_uint32 * 16)()
+        O.orc_ubo_values(o.handle, C.byref(r), fo, uo)
+        o.close()
+        cam16 = (C.c_float * 16)(*cam.position, *cam.forward, *cam.up, cam.vfov, cam.fStop, cam.focusDistance, cam.focalLength, cam.clipStart, cam.clipEnd, cam.exposure)
+        set_f = (C.c_float * 4)(st.lightIntensityMultiplier, st.maxSampleValue, st.metersPerSceneUnit, st.rrInvMinTermProb)
+        set_u = (C.c_uint32 * 4)(st.maxBounces, st.maxVolumeWalkLength, st.rrBounceOffset, st.spp)
+        counts = (C.c_uint32 * 4)(len(d.sphere_lights), len(d.distant_lights), len(d.rect_lights), len(d.disk_lights))
+        fr, ur = (C.c_float * 28)(), (C.c_uint32 * 16)()
+        R.refhost_uniform_data(cam16, set_f, set_u, counts, dome7, sample_offset, d.width, d.height, fr, ur)
+        assert bits(fr[:25]) == bits(fo[:25]), (k, list(fr), list(fo))
+        assert list(ur[:11]) == list(uo[:11]), (k, list(ur), list(uo))
