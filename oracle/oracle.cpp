@@ -1233,3 +1233,17 @@ extern "C" void orc_tex_texel(const GtlcTextureDesc* tex, int x, int y, int z, f
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 extern "C" float orc_srgb_texture_to_linear(float c) { return srgb_texture_to_linear(c); }
+// What `texture(sampler, coord)` / `texelFetch` return for the reference's texture functions when they run as C++ (ref_exports.cpp): the
+// hardware's part of a lookup -- linear filter with Repeat addressing / a raw texel -- with the wrap, crop and clip logic left to the caller.
+extern "C" void orc_tex_hw_sample(const GtlcTextureDesc* tex, float u, float v, float w, int is3d, float* out)
+{
+  const Texture t = texture_from_desc(tex);
+  const V4 r = is3d ? sample_linear_repeat_3d(t, u, v, w) : sample_linear_repeat(t, u, v);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+extern "C" void orc_tex_hw_texel(const GtlcTextureDesc* tex, int x, int y, int z, float* out)
+{
+  const Texture t = texture_from_desc(tex);
+  const V4 r = texel(t, x, y, z);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}

@@ -41,6 +41,7 @@ FRAGMENTS = [
     ("rp_main.miss", 36, 53, "miss_functions.inc"),            # quatRotateDir, sampleDomeLight
     ("mdl_interface.glsl", 8, 38, "mdl_wrap.inc"),             # apply_wrap_and_crop
     ("mdl_interface.glsl", 238, 256, "mdl_adapt_normal.inc"),  # mdl_adapt_normal
+    ("mdl_interface.glsl", 40, 205, "mdl_textures.inc"),       # tex_lookup_* / tex_texel_* for 2-D and 3-D textures
 ]
 
 

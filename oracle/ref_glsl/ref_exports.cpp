@@ -35,6 +35,24 @@ static inline void clearAovs(uint) {}          // (the camera-head builds; the w
 #include "mdl_types.glsl"
 #include "mdl_wrap.inc"
 #include "mdl_adapt_normal.inc"
+// mdl_interface.glsl:40-205, the MDL texture runtime: the hardware's part (size query, filtered sample, texel fetch) comes from the caller
+namespace texrt {
+struct TexCallbacks { const void* desc; void (*sample)(const void*, float, float, float, int, float*); void (*texel)(const void*, int, int, int, float*); int w, h, d; };
+static TexCallbacks g_tex;
+struct TexArray { int operator[](uint) const { return 0; } };
+static const TexArray textures_2d, textures_3d;
+struct Sampler2 { }; struct Sampler3 { };
+static inline Sampler2 sampler2D(int, int) { return Sampler2(); }
+static inline Sampler3 sampler3D(int, int) { return Sampler3(); }
+struct SizeQuery { operator ivec2() const { return ivec2(g_tex.w, g_tex.h); } operator ivec3() const { return ivec3(g_tex.w, g_tex.h, g_tex.d); } };
+static inline SizeQuery textureSize(int, int) { return SizeQuery(); }
+static inline vec4 texture(Sampler2, vec2 c) { float o[4]; g_tex.sample(g_tex.desc, c.x, c.y, 0.0f, 0, o); return vec4(o[0], o[1], o[2], o[3]); }
+static inline vec4 texture(Sampler3, vec3 c) { float o[4]; g_tex.sample(g_tex.desc, c.x, c.y, c.z, 1, o); return vec4(o[0], o[1], o[2], o[3]); }
+static inline vec4 texelFetch(Sampler2, ivec2 c, int) { float o[4]; g_tex.texel(g_tex.desc, c.x, c.y, 0, o); return vec4(o[0], o[1], o[2], o[3]); }
+static inline vec4 texelFetch(Sampler3, ivec3 c, int) { float o[4]; g_tex.texel(g_tex.desc, c.x, c.y, c.z, o); return vec4(o[0], o[1], o[2], o[3]); }
+#define TEXTURE_INDEX_OFFSET 0
+#include "mdl_textures.inc"
+}
 // function-level copies for the per-function tests (the whole-pipeline builds further down bring their own, in their namespaces)
 namespace fn {
 // rp_main.miss:46-53 reads the dome-light image; the stand-in returns the lat-long coordinate it was asked for
@@ -289,4 +307,18 @@ EXPORT int ref_render(const RefCallbacks* cb, const float* f28, const uint* u16,
   else ok = 0;
   rayCounts[0] = g_rayCounts[0]; rayCounts[1] = g_rayCounts[1];
   return ok;
+}
+// ---- mdl_interface.glsl:40-205 ----
+// mode 0: tex_lookup_float4_2d(coord.xy, wrap_u, wrap_v), 1: tex_lookup_float4_3d, 2: tex_texel_float4_2d(ivec2(coord)), 3: tex_texel_float4_3d; crop = (0, 1)
+EXPORT void ref_tex_function(int mode, const void* desc, void (*sample)(const void*, float, float, float, int, float*), void (*texel)(const void*, int, int, int, float*),
+                             int w, int h, int d, const float* coord, const int* icoord, int wrapU, int wrapV, int wrapW, float* out)
+{
+  texrt::g_tex.desc = desc; texrt::g_tex.sample = sample; texrt::g_tex.texel = texel; texrt::g_tex.w = w; texrt::g_tex.h = h; texrt::g_tex.d = d;
+  const vec2 crop(0.0f, 1.0f);
+  vec4 r;
+  if (mode == 0) r = texrt::tex_lookup_float4_2d(1, vec2(coord[0], coord[1]), wrapU, wrapV, crop, crop, 0.0f);
+  else if (mode == 1) r = texrt::tex_lookup_float4_3d(1, vec3(coord[0], coord[1], coord[2]), wrapU, wrapV, wrapW, crop, crop, crop, 0.0f);
+  else if (mode == 2) r = texrt::tex_texel_float4_2d(1, ivec2(icoord[0], icoord[1]), ivec2(0, 0), 0.0f);
+  else r = texrt::tex_texel_float4_3d(1, ivec3(icoord[0], icoord[1], icoord[2]), 0.0f);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }

@@ -526,3 +526,40 @@ def test_host_uniform_block(libs):
         R.refhost_uniform_data(cam16, set_f, set_u, counts, dome7, sample_offset, d.width, d.height, fr, ur)
         assert bits(fr[:25]) == bits(fo[:25]), (k, list(fr), list(fo))
         assert list(ur[:11]) == list(uo[:11]), (k, list(ur), list(uo))
+
+
+def test_mdl_texture_runtime(libs):
+    """mdl_interface.glsl:40-205 (tex_lookup_float4_2d / _3d, tex_texel_float4_2d / _3d) compiled from the reference's file; the hardware's
+    part of a lookup (size query, linear filter with Repeat addressing, texel fetch) is supplied by the oracle's samplers.  Against the
+    oracle's restatements: clip test, wrap + crop order, out-of-range texel fetches, for every wrap mode and all four texel formats."""
+    from gatling_b200 import scenes
+    R, O = libs
+    R.ref_tex_function.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    sample, texel = C.cast(O.orc_tex_hw_sample, C.c_void_p), C.cast(O.orc_tex_hw_texel, C.c_void_p)
+    rng = np.random.default_rng(17)
+    flat = [scenes.procedural_texture(k, 16) for k in ("checker", "roughness", "emission", "noise")]
+    vols = [scenes.procedural_volume(5, 3), scenes.procedural_volume(4, 8, channels=1)]
+    def ref(mode, tex, coord=(0, 0, 0), icoord=(0, 0, 0), wraps=(1, 1, 1)):
+        d, keep = orc._texture_desc(tex)
+        rows, cols = tex.rows_cols
+        out = (C.c_float * 4)()
+        R.ref_tex_function(mode, C.byref(d), sample, texel, cols, rows, max(tex.depth, 1), (C.c_float * 3)(*coord), (C.c_int * 3)(*icoord), wraps[0], wraps[1], wraps[2], out)
+        return np.array(out[:], np.float32)
+    for tex in flat:
+        for _ in range(400):
+            u, v = (float(np.float32(x)) for x in rng.uniform(-2.5, 2.5, 2))
+            wu, wv = (int(x) for x in rng.integers(0, 4, 2))
+            got = ref(0, tex, (u, v, 0), wraps=(wu, wv, 1))
+            want, clipped = orc.tex_lookup(tex, u, v, wu, wv)
+            assert np.array_equal(got, np.zeros(4, np.float32) if clipped else want), (u, v, wu, wv)
+            x, y = (int(t) for t in rng.integers(-3, 20, 2))
+            assert np.array_equal(ref(2, tex, icoord=(x, y, 0)), orc.tex_texel(tex, x, y))
+    for tex in vols:
+        for _ in range(400):
+            c = tuple(float(np.float32(x)) for x in rng.uniform(-2.0, 2.0, 3))
+            w3 = tuple(int(x) for x in rng.integers(0, 4, 3))
+            got = ref(1, tex, c, wraps=w3)
+            want, clipped = orc.tex_lookup_3d(tex, *c, *w3)
+            assert np.array_equal(got, np.zeros(4, np.float32) if clipped else want), (c, w3)
+            ic = tuple(int(t) for t in rng.integers(-2, 7, 3))
+            assert np.array_equal(ref(3, tex, icoord=ic), orc.tex_texel(tex, *ic))
