@@ -1100,6 +1100,19 @@ void orc_ubo_values(void* h, const OrcRenderDesc* r, float* f, uint32_t* u)
                             (uint32_t) ((c.fl.jittered ? 1 : 0) | (c.fl.fis ? 2 : 0) | (c.fl.dof ? 4 : 0) | (c.fl.nee ? 8 : 0) | (c.fl.clipping ? 16 : 0) | (c.fl.progressive ? 32 : 0) | (c.fl.domeCameraVisible ? 64 : 0)), 0u, 0u, 0u };
   memcpy(f, fv, sizeof(fv)); memcpy(u, uv, sizeof(uv));
 }
+// The hit-independent values the OpenPBR closure derives from a parameter block (orc_openpbr.h opbr_lobes, orc_bsdf.h): what
+// open_pbr_surface.mtlx feeds into its BSDF / EDF / VDF nodes.  out: a, a_c, eta, metal, spec_w, coat_w, trans_w, pad, m_f0(3), m_f82(3), trans_tint(3),
+// coat_att(3), Kd(3), sigma_a(3), sigma_s(3), emission intensity(3)  (32 floats)
+void orc_openpbr_lowered(const float* params, float* out)
+{
+  Material m; m.closure = GTLC_CLOSURE_OPENPBR; memcpy(m.p, params, sizeof(m.p));
+  const OpbrLobes o = opbr_lobes(m);
+  const V3 sa = mat_volume_absorption(m), ss = mat_volume_scattering(m), em = mat_emission_intensity(m);
+  const float v[32] = { o.a, o.a_c, o.eta, o.metal, o.spec_w, o.coat_w, o.trans_w, 0.0f, o.m_f0.x, o.m_f0.y, o.m_f0.z, o.m_f82.x, o.m_f82.y, o.m_f82.z,
+                        o.trans_tint.x, o.trans_tint.y, o.trans_tint.z, o.coat_att.x, o.coat_att.y, o.coat_att.z, o.Kd.x, o.Kd.y, o.Kd.z,
+                        sa.x, sa.y, sa.z, ss.x, ss.y, ss.z, em.x, em.y, em.z };
+  memcpy(out, v, sizeof(v));
+}
 // Host-side light arithmetic, Gi.cpp:2635-2640 (Knud Thomsen's approximation of an ellipsoid's area; the last factor is a double) and
 // Gi.cpp:2724-2725 (solid angle of the distant light's cone; 2 pi in double)
 float orc_sphere_light_area(float radiusX, float radiusY, float radiusZ)

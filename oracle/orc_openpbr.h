@@ -2,7 +2,10 @@
 //
 // OpenPBR closure: restatement of the node graph /root/reference/src/gi/mtlx/open_pbr_surface.mtlx:99-635
 // (the only in-tree specification of the layering; the MDL the reference generates from it is compiled
-// by the closed MDL SDK).  PARITY UNPINNED.  Implemented subset, top to bottom of the layer stack:
+// by the closed MDL SDK).  PARITY: the hit-independent values (opbr_lobes, the volume coefficients, the emission weight) are pinned to that
+// node graph -- tests/golden/make_openpbr_graph_vectors.py evaluates the reference's file node by node, tests/test_openpbr_graph_cpu.py
+// compares (a few ulp: pow() vs products); the lobes themselves (what each BSDF node does with its inputs) are UNPINNED, they live in the
+// MDL SDK.  Implemented subset, top to bottom of the layer stack:
 //   coat            dielectric_bsdf R (coat_weight, coat_ior, coat_roughness^2)          mtlx:542-568
 //   coat tint       base * mix(1, coat_color, coat_weight)                                mtlx:542-550
 //   coat darkening  base * mix(1, (1-Kcoat)/(1-Ebase*Kcoat), coat_weight*coat_darkening)  mtlx:472-540
