@@ -1041,6 +1041,18 @@ uint32_t orc_hit_begin(void* h, uint32_t inst, uint32_t prim, float u, float v, 
   material_at_hit(*c.s, *c.in, hit, c.st, wd, base, c.mat, c.mappedNormal, c.hasMappedNormal);
   return (mat_is_thin_walled(base) ? 1u : 0u) | (mat_is_emissive(c.mat) ? 2u : 0u) | ((c.in->flags & 1u) ? 4u : 0u) | ((c.in->flags & 2u) ? 8u : 0u) | (c.hasMappedNormal ? 16u : 0u);
 }
+// The parameter block at the current hit, after the primvar readers and texture bindings ran (orc_hit_begin)
+void orc_hit_params(float* params) { memcpy(params, g_hitCtx.mat.p, sizeof(g_hitCtx.mat.p)); }
+// The scene-data table entry of primvar reader k at instance `inst` (the reference's sceneDataInfos word, unpacked): info[0] = first float of the
+// primvar in the data array, info[1] = stride in floats | interpolation << 4 | 0x100 present | 0x200 integer data
+void orc_primvar_entry(void* h, uint32_t inst, uint32_t k, uint32_t* info2, const float** data)
+{
+  const Scene* s = (const Scene*) h;
+  info2[0] = info2[1] = 0; *data = nullptr;
+  if (s->primvarInfos.empty()) return;
+  const uint32_t* info = &s->primvarInfos[((size_t) inst * GTLC_MAX_PRIMVAR_BINDINGS + k) * 2];
+  info2[0] = info[0]; info2[1] = info[1]; *data = s->primvarData.data() + info[0];
+}
 void orc_hit_mapped_normal(float* n) { n[0] = g_hitCtx.mappedNormal.x; n[1] = g_hitCtx.mappedNormal.y; n[2] = g_hitCtx.mappedNormal.z; }
 void orc_hit_volume(float* sigma_a, float* sigma_s, float* ior, float* bias)
 {

@@ -42,6 +42,8 @@ FRAGMENTS = [
     ("mdl_interface.glsl", 8, 38, "mdl_wrap.inc"),             # apply_wrap_and_crop
     ("mdl_interface.glsl", 238, 256, "mdl_adapt_normal.inc"),  # mdl_adapt_normal
     ("mdl_interface.glsl", 40, 205, "mdl_textures.inc"),       # tex_lookup_* / tex_texel_* for 2-D and 3-D textures
+    ("mdl_interface.glsl", 266, 452, "mdl_scene_data.inc"),    # scene_data_isvalid, get_scene_data_indices, scene_data_lookup_float{,2,3,4} / _color / _int
+    ("mdl_renderer_state.glsl", None, None, "mdl_renderer_state.glsl"),
 ]
 
 

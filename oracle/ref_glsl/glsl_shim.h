@@ -57,7 +57,18 @@ struct ivec3 {
 };
 struct ivec4 { int x, y, z, w; };
 struct uvec2 { uint x, y; uvec2() : x(0), y(0) {} uvec2(uint a, uint b) : x(a), y(b) {} };
-struct uvec3 { uint x, y, z; uvec3() : x(0), y(0), z(0) {} uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {} uvec2 xy() const { return uvec2(x, y); } };
+struct uvec3 {
+  uint x, y, z;
+  uvec3() : x(0), y(0), z(0) {}
+  uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
+  explicit uvec3(uint s) : x(s), y(s), z(s) {}
+  explicit uvec3(int s) : x((uint) s), y((uint) s), z((uint) s) {}
+  uvec2 xy() const { return uvec2(x, y); }
+  uint operator[](int i) const { return (&x)[i]; }
+};
+static inline uvec3 operator*(uvec3 a, uint s) { return uvec3(a.x * s, a.y * s, a.z * s); }
+static inline uvec3 operator*(uvec3 a, int s) { return uvec3(a.x * (uint) s, a.y * (uint) s, a.z * (uint) s); }
+static inline uvec3 operator+(uvec3 a, int s) { return uvec3(a.x + (uint) s, a.y + (uint) s, a.z + (uint) s); }
 struct uvec4 {
   uint x, y, z, w;
   uvec4() : x(0), y(0), z(0), w(0) {}

@@ -53,6 +53,24 @@ static inline vec4 texelFetch(Sampler3, ivec3 c, int) { float o[4]; g_tex.texel(
 #define TEXTURE_INDEX_OFFSET 0
 #include "mdl_textures.inc"
 }
+// mdl_interface.glsl:266-452, the "scene data" (primvar) runtime: State carries the renderer state here, buffer references become pointers
+namespace scenedata {
+#undef SCENE_DATA_COUNT
+#define SCENE_DATA_COUNT 6
+#include "mdl_renderer_state.glsl"
+#define RENDERER_STATE_TYPE mdl_renderer_state
+#undef H_MDL_TYPES
+#include "mdl_types.glsl"                   // again, in this namespace: State with the renderer_state member
+struct BufferRefInt { const int* data; explicit BufferRefInt(uint64_t a) : data((const int*) a) {} };
+struct BufferRefFloat { const float* data; explicit BufferRefFloat(uint64_t a) : data((const float*) a) {} };
+struct BufferRefVec2 { const vec2* data; explicit BufferRefVec2(uint64_t a) : data((const vec2*) a) {} };
+struct BufferRefVec4 { const vec4* data; explicit BufferRefVec4(uint64_t a) : data((const vec4*) a) {} };
+static const int* InstanceIds; static int gl_InstanceID;
+#include "mdl_scene_data.inc"
+#undef RENDERER_STATE_TYPE
+#undef SCENE_DATA_COUNT
+#define SCENE_DATA_COUNT 0
+}
 // function-level copies for the per-function tests (the whole-pipeline builds further down bring their own, in their namespaces)
 namespace fn {
 // rp_main.miss:46-53 reads the dome-light image; the stand-in returns the lat-long coordinate it was asked for
@@ -321,4 +339,22 @@ EXPORT void ref_tex_function(int mode, const void* desc, void (*sample)(const vo
   else if (mode == 2) r = texrt::tex_texel_float4_2d(1, ivec2(icoord[0], icoord[1]), ivec2(0, 0), 0.0f);
   else r = texrt::tex_texel_float4_3d(1, ivec3(icoord[0], icoord[1], icoord[2]), 0.0f);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+// ---- mdl_interface.glsl:266-452 ----
+// One primvar reader at a hit.  word: the reference's packed sceneDataInfo (interpolation << 30 | (stride - 1) << 28 | offset 0) or SCENE_DATA_INVALID;
+// data: the primvar's first float; count 1..3 floats -> scene_data_lookup_float / _float2 / _float3, isInt -> scene_data_lookup_int per component.
+EXPORT void ref_scene_data_lookup(uint word, const void* data, const uint* hitIndices, float u, float v, int prim, int instanceId, int count, int isInt, const float* fallback, float* out)
+{
+  using namespace scenedata;
+  scenedata::State st;
+  st.renderer_state.hitIndices = uvec3(hitIndices[0], hitIndices[1], hitIndices[2]);
+  st.renderer_state.hitBarycentrics = vec2(u, v);
+  st.renderer_state.sceneDataBufferAddress = (uint64_t) data;
+  for (int k = 0; k < 6; k++) st.renderer_state.sceneDataInfos[k] = SCENE_DATA_INVALID;
+  st.renderer_state.sceneDataInfos[0] = word;
+  int ids[1] = { instanceId }; scenedata::InstanceIds = ids; scenedata::gl_InstanceID = 0; gl_PrimitiveID = prim;
+  if (isInt) { for (int c = 0; c < count; c++) out[c] = (float) scenedata::scene_data_lookup_int(st, 1, c, (int) fallback[c], false); return; }
+  if (count == 1) out[0] = scenedata::scene_data_lookup_float(st, 1, fallback[0], false);
+  else if (count == 2) { vec2 r = scenedata::scene_data_lookup_float2(st, 1, vec2(fallback[0], fallback[1]), false); out[0] = r.x; out[1] = r.y; }
+  else { vec3 r = scenedata::scene_data_lookup_color(st, 1, vec3(fallback[0], fallback[1], fallback[2]), false); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
 }

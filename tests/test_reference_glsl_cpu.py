@@ -563,3 +563,57 @@ def test_mdl_texture_runtime(libs):
             assert np.array_equal(got, np.zeros(4, np.float32) if clipped else want), (c, w3)
             ic = tuple(int(t) for t in rng.integers(-2, 7, 3))
             assert np.array_equal(ref(3, tex, icoord=ic), orc.tex_texel(tex, *ic))
+
+
+def test_scene_data_lookups(libs):
+    """mdl_interface.glsl:266-452 ("scene data" = primvars: scene_data_isvalid, get_scene_data_indices, scene_data_lookup_float / _float2 /
+    _float3 / _color / _int) compiled from the reference's file, buffer references as pointers: every primvar reader of the primvar test
+    scenes at random hits -- constant, per-instance, per-face and per-vertex interpolation, float and integer data, missing primvars --
+    against the values the oracle writes into the parameter block."""
+    from gatling_b200 import scenes
+    R, O = libs
+    O.orc_scene_views.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    O.orc_hit_begin.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
+    O.orc_primvar_entry.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+    O.orc_instance_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    R.ref_scene_data_lookup.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(21)
+    kinds = set()
+    for d in (scenes.primvar_cornell(8, 8, spp=1), scenes.lookup_cornell(8, 8, spp=1)):
+        o = orc.OracleScene(d)
+        h = o.handle
+        faces, fverts = C.c_void_p(), C.c_void_p()
+        bases = (C.c_uint32 * 3)(); o2w, w2o = (C.c_float * 12)(), (C.c_float * 12)(); count = C.c_uint32(0)
+        O.orc_scene_views(h, 0, C.byref(faces), C.byref(fverts), bases, o2w, w2o, C.byref(count))
+        inst_ids, obj_ids = np.zeros(count.value, np.int32), np.zeros(count.value, np.int32)
+        O.orc_instance_ids(h, inst_ids.ctypes.data, obj_ids.ctypes.data)
+        flat_meshes = [m for m in d.meshes for _ in range(1 if m.instance_transforms is None else len(m.instance_transforms))]
+        assert len(flat_meshes) == count.value
+        for inst, mesh in enumerate(flat_meshes):
+            readers = getattr(d.materials[mesh.material], "primvars", None) or []
+            if not readers:
+                continue
+            O.orc_scene_views(h, inst, C.byref(faces), C.byref(fverts), bases, o2w, w2o, C.byref(count))
+            all_faces = np.ctypeslib.as_array(C.cast(faces, C.POINTER(C.c_uint32)), shape=((bases[1] + bases[2]) * 3,))
+            for _ in range(60):
+                prim = int(rng.integers(0, bases[2]))
+                u = float(np.float32(rng.random())); v = float(np.float32(rng.random() * (1.0 - u)))
+                O.orc_hit_begin(h, inst, prim, u, v, f3((0.0, 1.0, 0.0)))
+                params = np.zeros(48, np.float32)
+                O.orc_hit_params(params.ctypes.data)
+                idx = (C.c_uint32 * 3)(*[int(x) for x in all_faces[(bases[1] + prim) * 3:(bases[1] + prim) * 3 + 3]])
+                for k, rd in enumerate(readers):
+                    info = (C.c_uint32 * 2)(); data = C.c_void_p()
+                    O.orc_primvar_entry(h, inst, k, info, C.byref(data))
+                    present, stride, interp, is_int = bool(info[1] & 0x100), info[1] & 15, (info[1] >> 4) & 15, bool(info[1] & 0x200)
+                    if present and stride != rd.count:
+                        continue                                        # a reader narrower / wider than its data: undefined in the reference (reads the neighbour)
+                    word = ((interp << 30) | ((stride - 1) << 28)) if present else 0xFFFFFFFF
+                    out = (C.c_float * 3)()
+                    fb = (C.c_float * 3)(*[float(x) for x in rd.fallback[:3]])
+                    R.ref_scene_data_lookup(word, data, idx, u, v, prim, max(int(inst_ids[inst]), 0), rd.count, int(is_int), fb, out)
+                    want = params[rd.param:rd.param + rd.count]
+                    assert bits(out[:rd.count]) == bits(want), (d.name, inst, k, rd, list(out), list(want))
+                    kinds.add((present, interp if present else -1, is_int))
+        o.close()
+    assert {(True, i, False) for i in range(4)} <= kinds and (False, -1, False) in kinds and any(k[2] for k in kinds), kinds
