@@ -196,7 +196,7 @@ def oracle_sample(a, target_seconds, steps, warmup):
         total_rays += rays[0] + rays[1]; total_secs += secs
     cores = orc.lib().orc_num_threads()
     o.close()
-    text = ("oracle-CPU port (C++/OpenMP restatement; the reference's Vulkan-RT path cannot be built or run here), %d threads bound to their places: the same scene and resolution, "
+    text = ("oracle-CPU port (C++/OpenMP restatement whose integrator renders bit-identically to the reference's own shader code compiled as C++, tests/test_reference_glsl_cpu.py; the reference's Vulkan-RT path itself cannot be built or run here), %d threads bound to their places: the same scene and resolution, "
             "image rows [%d,%d) of %d at spp %d per step, %d rays in %.1f s over %d steps" % (cores, r0, r0 + rows, H, spp, total_rays, total_secs, steps))
     return per_step, total_rays / max(total_secs, 1e-9) / 1e6, total_secs, cores, text
 
