@@ -131,3 +131,19 @@ EXPORT void refhost_disk_light(int set, float* origin, float* t0, float* t1, flo
   if (set) { gtl::giSetDiskLightOrigin(l, origin); gtl::giSetDiskLightTangents(l, t0, t1); gtl::giSetDiskLightBaseEmission(l, rgb); gtl::giSetDiskLightRadius(l, radiusX, radiusY); gtl::giSetDiskLightDiffuseSpecular(l, diffuse, specular); }
   memcpy(out48, s.diskLights.write<rp::DiskLight>(l->gpuHandle), 48); gtl::giDestroyDiskLight(&s, l);
 }
+
+// ---- src/hdGatling/main.cpp:136-143, 465-487: how the reference's graphical tests turn a float AOV into the RGBA8 image they compare ----
+#include <algorithm>
+#include <cmath>
+namespace harness {
+#include "harness_srgb.inc"
+static void to_bytes(const float* mappedMem, size_t width, size_t height, int compCount, bool isInt, bool gammaEncode, uint8_t* outBytes)
+{
+    size_t pixelCount = width * height;
+    std::vector<uint8_t> byteValues(pixelCount * 4);
+#include "harness_bytes.inc"
+    memcpy(outBytes, byteValues.data(), byteValues.size());
+}
+}
+EXPORT float refhost_accurate_linear_to_srgb(float x) { return harness::_AccurateLinearToSrgb(x); }
+EXPORT void refhost_harness_bytes(const float* pixels, uint32_t width, uint32_t height, int compCount, int isInt, int gammaEncode, uint8_t* out) { harness::to_bytes(pixels, width, height, compCount, isInt != 0, gammaEncode != 0, out); }

@@ -617,3 +617,30 @@ def test_scene_data_lookups(libs):
                     kinds.add((present, interp if present else -1, is_int))
         o.close()
     assert {(True, i, False) for i in range(4)} <= kinds and (False, -1, False) in kinds and any(k[2] for k in kinds), kinds
+
+
+def test_test_harness_conversion(libs):
+    """How the reference's graphical tests turn a float AOV into the 8-bit image they byte-compare (src/hdGatling/main.cpp:136-143
+    `_AccurateLinearToSrgb`, :465-487 the conversion loop), compiled from the reference's file, against the restatement
+    tools/compare_with_reference.py uses to reproduce the one reconstructible golden image (tests/test_reference_pin.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import compare_with_reference as cw
+    R, _ = libs
+    R.refhost_accurate_linear_to_srgb.restype = C.c_float
+    R.refhost_accurate_linear_to_srgb.argtypes = [C.c_float]
+    R.refhost_harness_bytes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(23)
+    xs = np.concatenate([rng.random(4000), rng.random(500) * 0.01, [0.0, 0.0031308, 0.00313081, 1.0, 0.5, 0.999999, 1e-8]]).astype(np.float32)
+    got = np.array([R.refhost_accurate_linear_to_srgb(float(x)) for x in xs], np.float32)
+    assert np.array_equal(got, cw.accurate_linear_to_srgb(xs))
+    for comp in (4, 3, 1):
+        img = (rng.random((9, 13, comp)) * 1.002).astype(np.float32)                       # [0, 1.002): the range a resolved colour / AOV buffer holds
+        img[0, 0] = 1.0; img[0, 1] = 0.0
+        for gamma in (1, 0):
+            out = np.zeros((9, 13, 4), np.uint8)
+            R.refhost_harness_bytes(img.ctypes.data, 13, 9, comp, 0, gamma, out.ctypes.data)
+            assert np.array_equal(out, cw.harness_bytes(img, gamma_encode=bool(gamma))), (comp, gamma)
+    ids = rng.integers(-1, 1 << 24, (9, 13), dtype=np.int64).astype(np.int32)
+    out = np.zeros((9, 13, 4), np.uint8)
+    R.refhost_harness_bytes(ids.ctypes.data, 13, 9, 1, 1, 0, out.ctypes.data)
+    assert np.array_equal(out, cw.harness_bytes(ids))
