@@ -161,7 +161,7 @@ def profiled_traffic(config):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# the CPU arm (oracle port): bench.py's only use of oracle/.  Runs in a process of its own so that the OpenMP
+# the CPU arm (the reference's compiled integrator, or the oracle port without it): bench.py's only use of oracle/.  Runs in a process of its own so that the OpenMP
 # runtime reads its settings at start-up: all host threads, bound to their places (an unbound team was seen parked
 # on one core for a whole run: 6.5x spread between boxes in round 1).
 # ---------------------------------------------------------------------------------------------------------
@@ -178,27 +178,47 @@ def oracle_sample(a, target_seconds, steps, warmup):
     from oracle import orc
     desc, _ = make_scene(a.config, a)
     o = orc.OracleScene(desc)
+    # The reference's own integrator when it is there: oracle/_ref/libglslref.so is rp_main.rgen / .chit / .miss compiled as C++ from the
+    # reference's files in the build container (it travels with the repository snapshot); the oracle then only answers its ray queries and
+    # mdl_* calls.  Otherwise the oracle's restatement of the same code (bit-identical images, tests/test_reference_glsl_cpu.py).
+    ref = orc.ReferenceIntegrator() if (orc.ReferenceIntegrator.available() and not os.environ.get("GTLC_REF_ARM_PORT")) else None
+
+    def render_band(rows, spp):
+        if ref is not None:
+            _, rays, secs = ref.render(o, rows=rows, spp=spp)
+            return secs, rays
+        _, secs, rays = o.render(rows=rows, spp=spp)
+        return secs, rays
     H = desc.height
     mid = H // 2
     cal_rows = min(H, 32)
-    o.render(rows=(mid, mid + 2), spp=1)                       # thread start-up
-    _, secs, rays = o.render(rows=(mid - cal_rows // 2, mid - cal_rows // 2 + cal_rows), spp=1)
+    render_band((mid, mid + 2), 1)                              # thread start-up
+    secs, rays = render_band((mid - cal_rows // 2, mid - cal_rows // 2 + cal_rows), 1)
     rate = (rays[0] + rays[1]) / max(secs, 1e-6)
     spp = 2
     rows = int(min(H, max(2, rate * target_seconds / max((rays[0] + rays[1]) / float(cal_rows) * spp, 1))))
     r0 = max(0, mid - rows // 2)
     for _ in range(warmup):
-        o.render(rows=(r0, r0 + rows), spp=spp)
+        render_band((r0, r0 + rows), spp)
     per_step, total_rays, total_secs = [], 0, 0.0
     for _ in range(steps):
-        _, secs, rays = o.render(rows=(r0, r0 + rows), spp=spp)
+        secs, rays = render_band((r0, r0 + rows), spp)
         per_step.append((rays[0] + rays[1]) / secs / 1e6)
         total_rays += rays[0] + rays[1]; total_secs += secs
     cores = orc.lib().orc_num_threads()
+    port = None
+    if ref is not None and steps > 1:                            # the same band once through the oracle's restatement, for scale (it skips the callback layer)
+        _, psecs, prays = o.render(rows=(r0, r0 + rows), spp=spp)
+        port = {"value": (prays[0] + prays[1]) / max(psecs, 1e-9) / 1e6, "unit": METRIC, "steps": 1, "note": "the oracle's restatement of the same integrator on the same band (identical rays)"}
     o.close()
-    text = ("oracle-CPU port (C++/OpenMP restatement whose integrator renders bit-identically to the reference's own shader code compiled as C++, tests/test_reference_glsl_cpu.py; the reference's Vulkan-RT path itself cannot be built or run here), %d threads bound to their places: the same scene and resolution, "
-            "image rows [%d,%d) of %d at spp %d per step, %d rays in %.1f s over %d steps" % (cores, r0, r0 + rows, H, spp, total_rays, total_secs, steps))
-    return per_step, total_rays / max(total_secs, 1e-9) / 1e6, total_secs, cores, text
+    what = ("the reference's own integrator -- rp_main.rgen / .chit / .miss / _shadow.miss compiled as C++ from the reference's files (oracle/_ref/libglslref.so), "
+            "OpenMP over image rows; ray queries (software BVH) and the materials' mdl_* entry points are served by the CPU oracle, the reference's Vulkan-RT "
+            "pipeline and MDL SDK being neither buildable nor runnable here" if ref is not None else
+            "oracle-CPU port (C++/OpenMP restatement whose integrator renders bit-identically to the reference's own shader code compiled as C++, "
+            "tests/test_reference_glsl_cpu.py; oracle/_ref/libglslref.so was not found)")
+    text = ("%s; %d threads bound to their places: the same scene and resolution, image rows [%d,%d) of %d at spp %d per step, %d rays in %.1f s over %d steps"
+            % (what, cores, r0, r0 + rows, H, spp, total_rays, total_secs, steps))
+    return per_step, total_rays / max(total_secs, 1e-9) / 1e6, total_secs, cores, text, ("reference" if ref is not None else "port"), port
 
 
 def spread_of(vals):
@@ -211,16 +231,16 @@ def run_reference(a):
     if os.environ.get("GTLC_REF_ENV") != "1":                  # torchrun pins OMP_NUM_THREADS=1; restart with the full, bound team
         os.execve(sys.executable, [sys.executable] + sys.argv, reference_env())
     if a.cpu_sample_only:
-        per_step, value, _, cores, text = oracle_sample(a, a.cpu_seconds / 3.0, 3, 1)
-        print(json.dumps({"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": text, "spread": spread_of(per_step)}))
+        per_step, value, _, cores, text, kind, port = oracle_sample(a, a.cpu_seconds / 3.0, 3, 1)
+        print(json.dumps({"value": value, "unit": METRIC, "cores": cores, "kind": kind, "sample": text, "spread": spread_of(per_step), **({"port": port} if port else {})}))
         return
     desc, label = make_scene(a.config, a)
     per_step_target = max(2.0, min(20.0, 120.0 / max(a.steps + a.warmup, 1)))
-    per_step, value, secs, cores, text = oracle_sample(a, per_step_target, a.steps, a.warmup)
+    per_step, value, secs, cores, text, kind, port = oracle_sample(a, per_step_target, a.steps, a.warmup)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": 1000.0 * secs / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "config": workload_config(label, desc, a, a.gpus),
-           "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": text, "spread": spread_of(per_step)},
+           "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": kind, "sample": text, "spread": spread_of(per_step), **({"port": port} if port else {})},
            "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 

@@ -525,3 +525,77 @@ def srgb_texture_to_linear(c):
     L.orc_srgb_texture_to_linear.restype = C.c_float
     L.orc_srgb_texture_to_linear.argtypes = [C.c_float]
     return float(L.orc_srgb_texture_to_linear(float(c)))
+
+
+# ---- the reference's integrator, compiled from its own shader files (oracle/ref_glsl, oracle/_ref/libglslref.so) ------------------------------
+class _RefCallbacks(C.Structure):
+    _fields_ = [("scene", C.c_void_p), ("renderDesc", C.c_void_p)] + [(n, C.c_void_p) for n in
+                ("trace", "views", "hitBegin", "mappedNormal", "volume", "bsdfSample", "bsdfEvaluate", "bsdfAlbedo", "edf", "dome")]
+
+
+class ReferenceIntegrator:
+    """rp_main.rgen / .chit / .miss / _shadow.miss of the reference, compiled as C++ from the reference's files (oracle/ref_glsl/build_ref.py),
+    rendering an OracleScene: ray queries, the materials' mdl_* entry points and the dome texture are served by the oracle through a callback
+    table, everything else -- camera rays, the bounce loop, NEE, roulette, media, accumulation, AOVs -- is the reference's own code.
+    TEST INFRASTRUCTURE (and bench.py's reference arm)."""
+    SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libglslref.so")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.SO)
+
+    def __init__(self):
+        if not self.available():
+            raise RuntimeError("oracle/_ref/libglslref.so is missing: it is built from /root/reference by oracle/ref_glsl/build_ref.py in the build container")
+        self.R = C.CDLL(self.SO)
+        self.R.ref_render.argtypes = [C.c_void_p] * 15
+        self.R.ref_render.restype = C.c_int
+
+    def render(self, scene: "OracleScene", sample_offset=0, prev=None, rows=None, spp=None, aov_ids=None, clear_values=None):
+        """Returns (rgba float32[h, w, 4] -- or {aov id: array} with `aov_ids` --, (closest, shadow) ray counts, seconds)."""
+        import time
+        O, desc = lib(), scene.desc
+        r = scene.render_desc(sample_offset, None, None, spp)
+        cb = _RefCallbacks()
+        cb.scene, cb.renderDesc = scene.handle, C.cast(C.pointer(r), C.c_void_p)
+        for field, name in (("trace", "orc_trace_one"), ("views", "orc_scene_views"), ("hitBegin", "orc_hit_begin"), ("mappedNormal", "orc_hit_mapped_normal"),
+                            ("volume", "orc_hit_volume"), ("bsdfSample", "orc_hit_bsdf_sample"), ("bsdfEvaluate", "orc_hit_bsdf_evaluate"),
+                            ("bsdfAlbedo", "orc_hit_bsdf_albedo"), ("edf", "orc_hit_edf"), ("dome", "orc_dome_fetch")):
+            setattr(cb, field, C.cast(getattr(O, name), C.c_void_p))
+        f28, u16 = (C.c_float * 28)(), (C.c_uint32 * 16)()
+        O.orc_ubo_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        O.orc_ubo_values(scene.handle, C.byref(r), f28, u16)
+        lights = [C.c_void_p() for _ in range(4)]
+        O.orc_light_buffers.argtypes = [C.c_void_p] * 5
+        O.orc_light_buffers(scene.handle, *[C.byref(p) for p in lights])
+        img = np.zeros((desc.height, desc.width, 4), np.float32) if prev is None else np.ascontiguousarray(prev if aov_ids is None else prev[0], np.float32).copy()
+        counts = (C.c_uint64 * 2)()
+        row_arg = (C.c_uint32 * 2)(*rows) if rows else None
+        if aov_ids is None:
+            t0 = time.perf_counter()
+            ok = self.R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts, None, None, None, None, None, row_arg)
+            secs = time.perf_counter() - t0
+            if ok != 1:
+                raise RuntimeError("no reference pipeline was compiled for these render settings (oracle/ref_glsl/ref_exports.cpp)")
+            return img, (int(counts[0]), int(counts[1])), secs
+        INT, n = (11, 14), desc.width * desc.height
+        bufs = {a: (np.zeros((n, 1), np.int32) if a in INT else np.zeros((n, 1), np.float32) if a == 12 else np.zeros((n, 3), np.float32)) for a in range(17)}
+        ptrs = (C.c_void_p * 17)(*[bufs[a].ctypes.data for a in range(17)])
+        clear_f, clear_i = np.zeros((17, 4), np.float32), np.zeros((17, 4), np.int32)
+        for a, v in (clear_values or {}).items():
+            (clear_i if a in INT else clear_f)[a, :len(v)] = v
+        ninst = sum(1 if m.instance_transforms is None else len(m.instance_transforms) for m in desc.meshes) + 1
+        inst_ids, obj_ids = np.zeros(ninst, np.int32), np.zeros(ninst, np.int32)
+        O.orc_instance_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        O.orc_instance_ids(scene.handle, inst_ids.ctypes.data, obj_ids.ctypes.data)
+        t0 = time.perf_counter()
+        ok = self.R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts, ptrs, clear_f.ctypes.data, clear_i.ctypes.data,
+                               inst_ids.ctypes.data, obj_ids.ctypes.data, row_arg)
+        secs = time.perf_counter() - t0
+        if ok != 1:
+            raise RuntimeError("no reference pipeline with auxiliary AOVs was compiled for these render settings")
+        got = {0: img}
+        for a in aov_ids:
+            if a != 0:
+                got[a] = bufs[a].reshape(desc.height, desc.width, -1)
+        return got, (int(counts[0]), int(counts[1])), secs

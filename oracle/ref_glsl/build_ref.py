@@ -102,7 +102,7 @@ def build() -> str:
                 f.write("\n".join(lines[a - 1:b]) + "\n")
         so = os.path.join(OUT, "libglslref.so")
         src_root = os.path.dirname(os.path.dirname(REF))
-        common = ["g++", "-std=c++20", "-I", os.path.join(src_root, "gi"), "-I", os.path.join(src_root, "gb"), "-O1", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", tmp, "-I", HERE, "-I", REF, "-c"]
+        common = ["g++", "-std=c++20", "-fopenmp", "-I", os.path.join(src_root, "gi"), "-I", os.path.join(src_root, "gb"), "-O1", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", tmp, "-I", HERE, "-I", REF, "-c"]
         objs = []
         for unit, extra in (("ref_exports.cpp", ["-fsingle-precision-constant"]),      # GLSL: every literal is a float
                             ("ref_host.cpp", [])):                                      # C++ host code: float / double as written
@@ -112,7 +112,7 @@ def build() -> str:
                 sys.stderr.write(r.stderr[-6000:])
                 raise SystemExit("build_ref: g++ failed on " + unit)
             objs.append(obj)
-        r = subprocess.run(["g++", "-shared", "-o", so] + objs + ["-lm"], capture_output=True, text=True)
+        r = subprocess.run(["g++", "-shared", "-fopenmp", "-o", so] + objs + ["-lm"], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stderr[-3000:])
             raise SystemExit("build_ref: link failed")

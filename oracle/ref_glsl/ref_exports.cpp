@@ -6,27 +6,27 @@
 #include "interface/rp_main.h"          // the reference's shared C++/GLSL header (through oracle/ref_glsl/glm/glm.hpp): UniformData, *Light
 using namespace gtl::shader_interface::rp_main;
 
-static UniformData ubo;
+static UniformData ubo;                      // (read-only while a render runs)
 static SphereLight sphereLights[16];
 static DistantLight distantLights[16];
 static RectLight rectLights[16];
 static DiskLight diskLights[16];
-static vec3 gl_WorldRayDirectionEXT;
+static thread_local vec3 gl_WorldRayDirectionEXT;
 static int tex_sampler;
 static inline int sampler2D(int, int) { return 0; }
 #define nonuniformEXT(x) (x)
 
 // mdl_shading_state.glsl reads the hit mesh through buffer references and the ray-tracing built-ins; the stand-ins point at test arrays
-static BlasPayload blas_payloads[1];
-static const Face* g_faces; static const FVertex* g_vertices;
-static BlasPayloadBufferPreamble g_preamble;
+static thread_local BlasPayload blas_payloads[1];
+static thread_local const Face* g_faces; static thread_local const FVertex* g_vertices;
+static thread_local BlasPayloadBufferPreamble g_preamble;
 struct IndexBuffer { const Face* data; BlasPayloadBufferPreamble preamble; explicit IndexBuffer(uint64_t) : data(g_faces), preamble(g_preamble) {} };
 static vec4 ClearValuesF[17]; static ivec4 ClearValuesI[17];
 static const int *g_instanceIds, *g_objectIds;            // per instance (orc_instance_ids), set by the AOV render
 struct VertexBuffer { const FVertex* data; explicit VertexBuffer(uint64_t) : data(g_vertices) {} };
-static int gl_InstanceCustomIndexEXT, gl_PrimitiveID;
-static mat4x3 gl_ObjectToWorldEXT, gl_WorldToObjectEXT;
-static uvec3 gl_LaunchIDEXT;
+static thread_local int gl_InstanceCustomIndexEXT, gl_PrimitiveID;
+static thread_local mat4x3 gl_ObjectToWorldEXT, gl_WorldToObjectEXT;
+static thread_local uvec3 gl_LaunchIDEXT;
 static inline void clearAovs(uint) {}          // (the camera-head builds; the whole-pipeline builds compile the real one, rp_main.rgen:132-183)
 #define SCENE_DATA_COUNT 0
 
@@ -149,8 +149,9 @@ struct RefCallbacks {
   void (*dome)(void* scene, const void* renderDesc, uint domeLightIndex, float u, float v, float* rgb);
 };
 static RefCallbacks g_cb;
-static int g_domeIndex;
-static uint64_t g_rayCounts[2];
+static thread_local int g_domeIndex;
+static thread_local uint64_t g_rayCounts[2];
+static uint64_t g_totalRayCounts[2];
 #define IS_THIN_WALLED
 #define IS_EMISSIVE
 #define AOV_MASK AOV_BIT_COLOR
@@ -165,6 +166,14 @@ static uint64_t g_rayCounts[2];
 #include "ref_pipeline.inc"
 #undef PIPE_NS
 #undef MEDIUM_STACK_SIZE
+// ... without next-event estimation (config C2 of BASELINE.json renders that way)
+#undef NEXT_EVENT_ESTIMATION
+#define PIPE_NS pipe_nonee
+#define MEDIUM_STACK_SIZE 0
+#include "ref_pipeline.inc"
+#undef PIPE_NS
+#undef MEDIUM_STACK_SIZE
+#define NEXT_EVENT_ESTIMATION
 // ... and with a two-deep medium stack (volume random walk)
 #define PIPE_NS pipe_media2
 #define MEDIUM_STACK_SIZE 2
@@ -299,13 +308,14 @@ EXPORT void ref_setup_shading_state(const void* faces, const void* vertices, uin
 // rgba: width * height vec4, holds the previous ColorAov on entry when progressive.  Returns 0 if no pipeline was compiled for the switches.
 // aov: NULL, or 17 pointers (by AOV id; vec3 AOVs as tightly packed float[3], ids as int, depth as float; entries 0, 6, 13 unused) that
 // selects the all-AOVs pipeline; clearF / clearI: 17 x 4 clear values; instanceIds / objectIds: per instance
+// rows: NULL or [begin, end) -- a band of image rows (the bounded samples of bench.py's reference arm); the rows run on an OpenMP team.
 EXPORT int ref_render(const RefCallbacks* cb, const float* f28, const uint* u16, const void* spheres, const void* distants, const void* rects, const void* disks,
-                      float* rgba, uint64_t* rayCounts, void* const* aov, const float* clearF, const int* clearI, const int* instanceIds, const int* objectIds)
+                      float* rgba, uint64_t* rayCounts, void* const* aov, const float* clearF, const int* clearI, const int* instanceIds, const int* objectIds, const uint* rows)
 {
   g_instanceIds = aov ? instanceIds : nullptr; g_objectIds = aov ? objectIds : nullptr;
   if (aov) for (int k = 0; k < 17; k++) { ClearValuesF[k] = vec4(clearF[4 * k], clearF[4 * k + 1], clearF[4 * k + 2], clearF[4 * k + 3]); ClearValuesI[k].x = clearI[4 * k]; ClearValuesI[k].y = clearI[4 * k + 1]; ClearValuesI[k].z = clearI[4 * k + 2]; ClearValuesI[k].w = clearI[4 * k + 3]; }
   else for (int k = 0; k < 17; k++) ClearValuesF[k] = vec4(0.0f);
-  g_cb = *cb; g_rayCounts[0] = g_rayCounts[1] = 0;
+  g_cb = *cb; g_totalRayCounts[0] = g_totalRayCounts[1] = 0;
   ubo.domeLightRotation = vec4(f28[0], f28[1], f28[2], f28[3]); ubo.domeLightEmissionMultiplier = ld3(f28 + 4); ubo.metersPerSceneUnit = f28[7];
   ubo.cameraPosition = ld3(f28 + 8); ubo.cameraForward = ld3(f28 + 11); ubo.cameraUp = ld3(f28 + 14); ubo.focusDistance = f28[17]; ubo.cameraVFoV = f28[18];
   ubo.lensRadius = f28[19]; ubo.invTotalSampleCount = f28[20]; ubo.maxSampleValue = f28[21]; ubo.rrInvMinTermProb = f28[22]; ubo.lightIntensityMultiplier = f28[23];
@@ -317,13 +327,15 @@ EXPORT int ref_render(const RefCallbacks* cb, const float* f28, const uint* u16,
   memcpy(sphereLights, spheres, sizeof(SphereLight) * u16[0]); memcpy(distantLights, distants, sizeof(DistantLight) * u16[1]);
   memcpy(rectLights, rects, sizeof(RectLight) * u16[2]); memcpy(diskLights, disks, sizeof(DiskLight) * u16[3]);
   const uint width = u16[6] & 0xFFFFu, height = u16[6] >> 16, mss = u16[11], sw = u16[12];
+  const uint r0 = rows ? rows[0] : 0u, r1 = rows ? (rows[1] < height ? rows[1] : height) : height;
   int ok = 1;
-  if (aov) { if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_aovs::render(width, height, (vec4*) rgba, aov); else ok = 0; }
-  else if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_default::render(width, height, (vec4*) rgba);
-  else if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 2) pipe_media2::render(width, height, (vec4*) rgba);
-  else if (sw == (4u | 8u | 16u) && mss == 0) pipe_other::render(width, height, (vec4*) rgba);
+  if (aov) { if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_aovs::render(width, height, r0, r1, (vec4*) rgba, aov); else ok = 0; }
+  else if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 0) pipe_default::render(width, height, r0, r1, (vec4*) rgba);
+  else if (sw == (1u | 2u | 32u | 64u) && mss == 0) pipe_nonee::render(width, height, r0, r1, (vec4*) rgba);
+  else if (sw == (1u | 2u | 8u | 32u | 64u) && mss == 2) pipe_media2::render(width, height, r0, r1, (vec4*) rgba);
+  else if (sw == (4u | 8u | 16u) && mss == 0) pipe_other::render(width, height, r0, r1, (vec4*) rgba);
   else ok = 0;
-  rayCounts[0] = g_rayCounts[0]; rayCounts[1] = g_rayCounts[1];
+  rayCounts[0] = g_totalRayCounts[0]; rayCounts[1] = g_totalRayCounts[1];
   return ok;
 }
 // ---- mdl_interface.glsl:40-205 ----

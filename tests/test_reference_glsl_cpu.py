@@ -305,59 +305,18 @@ def test_shading_state(libs):
 
 
 # ---- the whole integrator: rp_main.rgen / .chit / .miss / _shadow.miss compiled from the reference's files -------------------------------
-class RefCallbacks(C.Structure):
-    _fields_ = [("scene", C.c_void_p), ("renderDesc", C.c_void_p)] + [(n, C.c_void_p) for n in
-                ("trace", "views", "hitBegin", "mappedNormal", "volume", "bsdfSample", "bsdfEvaluate", "bsdfAlbedo", "edf", "dome")]
-
-
 def reference_integrator_render(libs, desc, sample_offset=0, prev=None, aov_ids=None, clear_values=None):
-    """Renders `desc` with the reference's own shader code (oracle/ref_glsl/ref_pipeline.inc): its main() functions run as C++ and call back
-    into the oracle for ray queries, the material's mdl_* entry points and the dome texture.  Returns (rgba, (closest, shadow) ray counts,
-    the oracle's rgba, the oracle's ray counts); with `aov_ids` the all-AOVs build runs and rgba / the oracle's result are {id: array}."""
-    R, O = libs
+    """The scene rendered by the reference's own shader code (orc.ReferenceIntegrator) and by the oracle: (image or {aov: image}, ray counts,
+    the oracle's image or {aov: image}, the oracle's ray counts)."""
     o = orc.OracleScene(desc)
-    r = o.render_desc(sample_offset)
-    cb = RefCallbacks()
-    cb.scene, cb.renderDesc = o.handle, C.cast(C.pointer(r), C.c_void_p)
-    for field, name in (("trace", "orc_trace_one"), ("views", "orc_scene_views"), ("hitBegin", "orc_hit_begin"), ("mappedNormal", "orc_hit_mapped_normal"),
-                        ("volume", "orc_hit_volume"), ("bsdfSample", "orc_hit_bsdf_sample"), ("bsdfEvaluate", "orc_hit_bsdf_evaluate"),
-                        ("bsdfAlbedo", "orc_hit_bsdf_albedo"), ("edf", "orc_hit_edf"), ("dome", "orc_dome_fetch")):
-        setattr(cb, field, C.cast(getattr(O, name), C.c_void_p))
-    f28, u16 = (C.c_float * 28)(), (C.c_uint32 * 16)()
-    O.orc_ubo_values.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    O.orc_ubo_values(o.handle, C.byref(r), f28, u16)
-    lights = [C.c_void_p() for _ in range(4)]
-    O.orc_light_buffers.argtypes = [C.c_void_p] + [C.c_void_p] * 4
-    O.orc_light_buffers(o.handle, *[C.byref(p) for p in lights])
-    img = np.zeros((desc.height, desc.width, 4), np.float32) if prev is None else np.ascontiguousarray(prev, np.float32).copy()
-    counts = (C.c_uint64 * 2)()
-    R.ref_render.argtypes = [C.c_void_p] * 14
+    ri = orc.ReferenceIntegrator()
+    got, counts, _ = ri.render(o, sample_offset=sample_offset, prev=prev, aov_ids=aov_ids, clear_values=clear_values)
     if aov_ids is None:
-        ok = R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts, None, None, None, None, None)
-        assert ok == 1, "no reference pipeline was compiled for these render settings (ref_exports.cpp)"
         want, _, rays = o.render(sample_offset=sample_offset, prev=prev)
-        o.close()
-        return img, (int(counts[0]), int(counts[1])), want, rays
-    INT, n = (11, 14), desc.width * desc.height
-    bufs = {a: (np.zeros((n, 1), np.int32) if a in INT else np.zeros((n, 1), np.float32) if a == 12 else np.zeros((n, 3), np.float32)) for a in range(17)}
-    ptrs = (C.c_void_p * 17)(*[bufs[a].ctypes.data for a in range(17)])
-    clear_f, clear_i = np.zeros((17, 4), np.float32), np.zeros((17, 4), np.int32)
-    for a, v in (clear_values or {}).items():
-        (clear_i if a in INT else clear_f)[a, :len(v)] = v
-    ninst = len(desc.meshes) * 64 + 64
-    inst_ids, obj_ids = np.zeros(ninst, np.int32), np.zeros(ninst, np.int32)
-    O.orc_instance_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    O.orc_instance_ids(o.handle, inst_ids.ctypes.data, obj_ids.ctypes.data)
-    ok = R.ref_render(C.byref(cb), f28, u16, lights[0], lights[1], lights[2], lights[3], img.ctypes.data, counts, ptrs, clear_f.ctypes.data, clear_i.ctypes.data,
-                      inst_ids.ctypes.data, obj_ids.ctypes.data)
-    assert ok == 1
-    want = o.render_aovs(aov_ids, clear_values, sample_offset=sample_offset)
+    else:
+        want, rays = o.render_aovs(aov_ids, clear_values, sample_offset=sample_offset), None
     o.close()
-    got = {0: img}
-    for a in aov_ids:
-        if a != 0:
-            got[a] = bufs[a].reshape(desc.height, desc.width, -1)
-    return got, (int(counts[0]), int(counts[1])), want, None
+    return got, counts, want, rays
 
 
 def _lit(d):
@@ -644,3 +603,18 @@ def test_test_harness_conversion(libs):
     out = np.zeros((9, 13, 4), np.uint8)
     R.refhost_harness_bytes(ids.ctypes.data, 13, 9, 1, 1, 0, out.ctypes.data)
     assert np.array_equal(out, cw.harness_bytes(ids))
+
+
+def test_reference_integrator_row_bands_and_no_nee(libs):
+    """What bench.py's reference arm runs: a band of image rows at an overridden sample count, on the OpenMP team, with and without next-event
+    estimation (configs C3 / C5 and C2 of BASELINE.json): the band equals the oracle's band, ray counts included."""
+    from gatling_b200 import scenes
+    for d in (_lit(scenes.kitchen_standin(tris_per_instance=40, instances=14, meshes=7, materials=6, width=48, height=40, spp=8, max_bounces=6)),
+              scenes.random_triangles(600, 48, 40, spp=8, max_bounces=5)):
+        o = orc.OracleScene(d)
+        got, counts, secs = orc.ReferenceIntegrator().render(o, rows=(13, 29), spp=3)
+        want, _, rays = o.render(rows=(13, 29), spp=3)
+        o.close()
+        assert counts == tuple(rays) and secs > 0.0
+        assert np.array_equal(got[13:29], want[13:29]) and want[13:29, :, :3].mean() > 0.01
+        assert not got[:13].any() and not got[29:].any()
