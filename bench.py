@@ -181,7 +181,14 @@ def oracle_sample(a, target_seconds, steps, warmup):
     # The reference's own integrator when it is there: oracle/_ref/libglslref.so is rp_main.rgen / .chit / .miss compiled as C++ from the
     # reference's files in the build container (it travels with the repository snapshot); the oracle then only answers its ray queries and
     # mdl_* calls.  Otherwise the oracle's restatement of the same code (bit-identical images, tests/test_reference_glsl_cpu.py).
-    ref = orc.ReferenceIntegrator() if (orc.ReferenceIntegrator.available() and not os.environ.get("GTLC_REF_ARM_PORT")) else None
+    ref = None
+    if orc.ReferenceIntegrator.available() and not os.environ.get("GTLC_REF_ARM_PORT"):
+        try:
+            ref = orc.ReferenceIntegrator()
+            ref.render(o, rows=(0, 1), spp=1)                   # refuses render settings no pipeline was compiled for
+        except Exception as e:                                  # the arm must produce its line: fall back to the port
+            print("bench: reference integrator unavailable (%s); timing the oracle port" % e, file=sys.stderr)
+            ref = None
 
     def render_band(rows, spp):
         if ref is not None:
