@@ -77,6 +77,7 @@ HOST_FRAGMENTS = [
     ("gi/impl/Gi.cpp", 287, 300, "gi_encode_direction.inc"),   # _EncodeOctahedral, _EncodeDirection
     ("gi/impl/Gi.cpp", 2573, 2941, "gi_lights.inc"),           # gi{Create,Destroy,Set}{Sphere,Distant,Rect,Disk}Light*
     ("gi/impl/Gi.cpp", 2375, 2425, "gi_uniforms.inc"),         # giRender: camera vectors, lens radius, the UniformData initialiser
+    ("gi/impl/Gi.cpp", 845, 859, "gi_pack_vertices.inc"),      # _giBuildGeometryStructures: GiVertex -> rp::FVertex (the loop over a mesh's vertices)
     ("hdGatling/main.cpp", 136, 143, "harness_srgb.inc"),      # _AccurateLinearToSrgb
     ("hdGatling/main.cpp", 465, 487, "harness_bytes.inc"),     # the graphical tests' float -> 8-bit RGBA loop
 ]

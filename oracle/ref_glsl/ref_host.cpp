@@ -147,3 +147,21 @@ static void to_bytes(const float* mappedMem, size_t width, size_t height, int co
 }
 EXPORT float refhost_accurate_linear_to_srgb(float x) { return harness::_AccurateLinearToSrgb(x); }
 EXPORT void refhost_harness_bytes(const float* pixels, uint32_t width, uint32_t height, int compCount, int isInt, int gammaEncode, uint8_t* out) { harness::to_bytes(pixels, width, height, compCount, isInt != 0, gammaEncode != 0, out); }
+
+// ---- Gi.cpp:845-859: how a mesh's vertices become the rp::FVertex records the shaders read ----
+namespace gtl {
+static void pack_vertices(const std::vector<GiVertex>& meshVertices, std::vector<rp::FVertex>& vertexData)
+{
+    std::vector<float> positionData;
+    vertexData.resize(meshVertices.size());
+    positionData.resize(meshVertices.size() * 3);
+#include "gi_pack_vertices.inc"
+}
+}
+EXPORT void refhost_pack_vertices(const void* giVertices, uint32_t count, void* fvertsOut)
+{
+  std::vector<gtl::GiVertex> v((const gtl::GiVertex*) giVertices, (const gtl::GiVertex*) giVertices + count);
+  std::vector<rp::FVertex> out;
+  gtl::pack_vertices(v, out);
+  memcpy(fvertsOut, out.data(), sizeof(rp::FVertex) * count);
+}

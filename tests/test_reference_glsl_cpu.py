@@ -618,3 +618,26 @@ def test_reference_integrator_row_bands_and_no_nee(libs):
         assert counts == tuple(rays) and secs > 0.0
         assert np.array_equal(got[13:29], want[13:29]) and want[13:29, :, :3].mean() > 0.01
         assert not got[:13].any() and not got[29:].any()
+
+
+def test_host_vertex_packing(libs):
+    """Gi.cpp:845-859 (the loop of _giBuildGeometryStructures that turns a mesh's GiVertex array into the rp::FVertex records
+    mdl_shading_state.glsl unpacks), compiled from the reference's file against its own Gi.h: normals and tangents through `_EncodeDirection`,
+    position + bitangent sign, uv -- against the oracle's packed vertex buffer for the same meshes."""
+    from gatling_b200 import scenes
+    R, O = libs
+    O.orc_scene_views.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.refhost_pack_vertices.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    for d in (scenes.textured_cornell(8, 8, spp=1), scenes.kitchen_standin(tris_per_instance=60, instances=9, meshes=5, materials=4, width=8, height=8, spp=1),
+              scenes.material_stress(tris_per_mesh=50, meshes=4, width=8, height=8, spp=1)):
+        o = orc.OracleScene(d)
+        verts = np.ascontiguousarray(np.concatenate([m.vertices for m in d.meshes]))
+        assert verts.dtype.itemsize == 48
+        out = np.zeros((len(verts), 8), np.float32)
+        R.refhost_pack_vertices(verts.ctypes.data, len(verts), out.ctypes.data)
+        faces, fverts = C.c_void_p(), C.c_void_p()
+        bases = (C.c_uint32 * 3)(); o2w, w2o = (C.c_float * 12)(), (C.c_float * 12)(); count = C.c_uint32(0)
+        O.orc_scene_views(o.handle, 0, C.byref(faces), C.byref(fverts), bases, o2w, w2o, C.byref(count))
+        want = np.ctypeslib.as_array(C.cast(fverts, C.POINTER(C.c_float)), shape=(len(verts), 8))
+        assert out.tobytes() == want.tobytes(), d.name
+        o.close()
