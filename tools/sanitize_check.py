@@ -49,6 +49,7 @@ for name, d, kw in (
         ("textures", scenes.textured_cornell(W, H, spp=2, max_bounces=4), {"bvhBuilder": 0}),
         ("3-D / texel lookups + evaluated cutout", scenes.lookup_cornell(W, H, spp=2, max_bounces=4), {}),
         ("primvars", scenes.primvar_cornell(W, H, spp=2, max_bounces=4), {}),
+        ("inputs combined from several lookups", scenes.layered_cornell(W, H, spp=2, max_bounces=4), {}),
         ("media", scenes.volume_cornell(W, H, spp=2, max_bounces=6), {}),
         ("OpenPBR instances + sort", scenes.kitchen_standin(tris_per_instance=200, instances=12, meshes=6, materials=5, width=W, height=H, spp=2, max_bounces=4), {"sortByMaterial": 1}),
         ("triangle soup", scenes.random_triangles(3000, W, H, spp=2, max_bounces=4), {"sortByMaterial": -1})):
