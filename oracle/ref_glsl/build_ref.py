@@ -79,6 +79,8 @@ HOST_FRAGMENTS = [
     ("gi/impl/Gi.cpp", 2375, 2425, "gi_uniforms.inc"),         # giRender: camera vectors, lens radius, the UniformData initialiser
     ("gi/impl/Gi.cpp", 845, 859, "gi_pack_vertices.inc"),      # _giBuildGeometryStructures: GiVertex -> rp::FVertex (the loop over a mesh's vertices)
     ("hdGatling/main.cpp", 136, 143, "harness_srgb.inc"),      # _AccurateLinearToSrgb
+    ("hdGatling/mesh.cpp", 83, 86, "mesh_bitangent_sign.inc"), # _CalculateBitangentSign
+    ("hdGatling/mesh.cpp", 231, 261, "mesh_fallback_tangents.inc"),  # _DuffOrthonormalBasis, _CalculateFallbackTangents
     ("hdGatling/main.cpp", 465, 487, "harness_bytes.inc"),     # the graphical tests' float -> 8-bit RGBA loop
 ]
 

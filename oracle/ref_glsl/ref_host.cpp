@@ -165,3 +165,22 @@ EXPORT void refhost_pack_vertices(const void* giVertices, uint32_t count, void* 
   gtl::pack_vertices(v, out);
   memcpy(fvertsOut, out.data(), sizeof(rp::FVertex) * count);
 }
+
+// ---- src/hdGatling/mesh.cpp:83-86, 231-261: the tangent frame hdGatling gives a mesh without authored tangents or texture coordinates ----
+// (the caller's side of giCreateMesh; gatling_b200/scenes.py prepares its test geometry the same way).  Stand-ins for the few pxr types.
+namespace meshprep {
+struct GfVec3f { float v[3]; GfVec3f() : v{ 0.0f, 0.0f, 0.0f } {} GfVec3f(float a, float b, float c) : v{ a, b, c } {} float operator[](int i) const { return v[i]; } float& operator[](int i) { return v[i]; } };
+static inline float GfDot(const GfVec3f& a, const GfVec3f& b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }          // GfVec3f::operator*: x x + y y + z z, left to right
+static inline GfVec3f GfCross(const GfVec3f& a, const GfVec3f& b) { return GfVec3f(a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]); }
+typedef std::vector<GfVec3f> VtVec3fArray;
+typedef std::vector<float> VtFloatArray;
+#include "mesh_bitangent_sign.inc"
+#include "mesh_fallback_tangents.inc"
+}
+EXPORT void refhost_fallback_tangents(const float* normals, uint32_t count, float* tangents, float* bitangentSigns)
+{
+  meshprep::VtVec3fArray n(count), t; meshprep::VtFloatArray s;
+  for (uint32_t i = 0; i < count; i++) n[i] = meshprep::GfVec3f(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+  meshprep::_CalculateFallbackTangents(n, t, s);
+  for (uint32_t i = 0; i < count; i++) { tangents[3 * i] = t[i][0]; tangents[3 * i + 1] = t[i][1]; tangents[3 * i + 2] = t[i][2]; bitangentSigns[i] = s[i]; }
+}

@@ -641,3 +641,19 @@ def test_host_vertex_packing(libs):
         want = np.ctypeslib.as_array(C.cast(fverts, C.POINTER(C.c_float)), shape=(len(verts), 8))
         assert out.tobytes() == want.tobytes(), d.name
         o.close()
+
+
+def test_caller_side_fallback_tangents(libs):
+    """src/hdGatling/mesh.cpp:83-86, 231-261 (`_CalculateBitangentSign`, `_DuffOrthonormalBasis`, `_CalculateFallbackTangents`: the tangent
+    frame hdGatling attaches to meshes without authored tangents or uvs), compiled from the reference's file -- against scenes.bake_vertices,
+    which prepares the geometry of this repository's test and bench scenes the same way."""
+    from gatling_b200 import scenes
+    R, _ = libs
+    R.refhost_fallback_tangents.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(29)
+    normals = np.array([unit(v) for v in rng.normal(size=(4000, 3))] + [(0, 0, 1), (0, 0, -1), (1, 0, 0), (0, -1, 0), (0.6, 0.0, -0.8)], np.float32)
+    t, s = np.zeros_like(normals), np.zeros(len(normals), np.float32)
+    R.refhost_fallback_tangents(np.ascontiguousarray(normals).ctypes.data, len(normals), t.ctypes.data, s.ctypes.data)
+    v = scenes.bake_vertices(np.zeros_like(normals), normals)
+    assert np.array_equal(v["tangent"], t) and np.array_equal(v["bitangentSign"], s)
+    assert set(np.unique(s)) <= {-1.0, 1.0}
